@@ -1,0 +1,221 @@
+#!/usr/bin/env python
+"""Generate golden vectors by RUNNING THE UNMODIFIED REFERENCE in this container.
+
+Usage (build container only; /root/reference does not exist on the GPU box)::
+
+    python tools/make_goldens.py [case ...]      # default: all cases
+
+The reference (pure Python, imported from /root/reference) is driven through its
+public API in ``code="external"`` mode on the deterministic toy table bank of
+``cosmicfishpie_b200.toy_tables``; outputs are frozen as small ``.npz`` fixtures
+under ``tests/golden/``.  These fixtures are what pins the oracle (``oracle/``)
+and, through it, the CUDA path.  Nothing in the product imports this file.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, os.path.join(REPO, "tools", "_stubs"))  # 6-line `nautilus` stub
+
+from cosmicfishpie_b200 import toy_tables as tt  # noqa: E402
+
+GOLD = os.path.join(REPO, "tests", "golden")
+SCRATCH = os.environ.get("CFP_SCRATCH", "/tmp/cfp_gold")
+PARS7 = list(tt.COSMO_KEYS)
+KSTRIDE = 16  # lattices are stored every 16th k sample to keep fixtures small
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def bank_dir():
+    d = os.path.join(SCRATCH, "bank")
+    if not os.path.isdir(os.path.join(d, "fiducial_eps_0")):
+        tt.write_bank(d, eps_values=(0.01,))
+    return d
+
+
+def base_options(outroot, spectro=True, photo=False, **kw):
+    o = {
+        "accuracy": 1,
+        "feedback": 0,
+        "code": "external",
+        "outroot": outroot,
+        "results_dir": os.path.join(SCRATCH, "results") + "/",
+        "survey_name": "Euclid",
+        "survey_name_spectro": "Euclid-Spectroscopic-ISTF-Pessimistic" if spectro else False,
+        "survey_name_photo": "Euclid-Photometric-ISTF-Pessimistic" if photo else False,
+        "cosmo_model": "w0waCDM",
+        "derivatives": "3PT",
+    }
+    o.update(kw)
+    return o
+
+
+def fisher_payload(F, fm):
+    names = list(F.get_param_names())
+    return {
+        "fisher": np.array(F.fisher_matrix),
+        "param_names": np.array(names),
+        "sigma": np.array(F.get_confidence_bounds()),
+        "freeparams_keys": np.array(list(fm.freeparams.keys())),
+        "freeparams_eps": np.array([fm.freeparams[k] for k in fm.freeparams]),
+    }
+
+
+def run_gcsp(tag, freepars, options_extra=None, specifications=None, max_z_bins=None, spectro_yaml=None):
+    import cosmicfishpie.fishermatrix.cosmicfish as cff
+
+    ext = tt.extfiles_for(bank_dir())
+    o = base_options(tag, spectro=True, photo=False, **(options_extra or {}))
+    if spectro_yaml:
+        o["survey_name_spectro"] = spectro_yaml
+    t0 = time.time()
+    with quiet():
+        fm = cff.FisherMatrix(
+            fiducialpars=dict(tt.FIDUCIAL),
+            freepars=dict(freepars),
+            options=o,
+            specifications=specifications or {},
+            observables=["GCsp"],
+            extfiles=ext,
+            cosmoModel="w0waCDM",
+            surveyName="Euclid",
+        )
+        F = fm.compute(max_z_bins=max_z_bins)
+    wall = time.time() - t0
+    out = fisher_payload(F, fm)
+    out["wall_s"] = wall
+    out["zmids"] = np.array(fm.zmids)
+    out["k_grid"] = fm.Pk_kgrid
+    out["mu_grid"] = fm.Pk_mugrid
+    out["veff_strided"] = np.array([v[:, ::KSTRIDE] for v in fm.veff_arr])
+    # fiducial ln P_obs lattice (strided) straight from the fiducial observable
+    lnp = np.array(
+        [fm.pk_obs_fid.lnpobs_gg(z, fm.Pk_kmesh, fm.Pk_mumesh)[:, ::KSTRIDE] for z in fm.zmids]
+    )
+    out["lnpobs_fid_strided"] = lnp
+    for par in fm.freeparams:
+        out["deriv_strided__" + par] = np.array(
+            [np.asarray(fm.derivs_dict[par][i])[:, ::KSTRIDE] * np.ones_like(lnp[0]) for i in range(len(fm.zmids))]
+        )
+    out["volume_survey"] = np.array([fm.pk_cov.volume_survey(i) for i in range(len(fm.zmids))])
+    out["n_density"] = np.array([fm.pk_cov.n_density(z) for z in fm.zmids])
+    pkF = np.array([fm.fisher_per_bin(i) for i in range(len(fm.zmids))])
+    out["fisher_per_bin"] = pkF
+    np.savez_compressed(os.path.join(GOLD, tag + ".npz"), **out)
+    print(f"{tag}: npar={len(out['param_names'])} wall={wall:.2f}s F00={out['fisher'][0,0]:.10e}")
+    return fm
+
+
+def run_photo(tag, observables, freepars, options_extra=None, specifications=None, photo_yaml=None, save_derivs=()):
+    import cosmicfishpie.fishermatrix.cosmicfish as cff
+
+    ext = tt.extfiles_for(bank_dir())
+    o = base_options(tag, spectro=False, photo=True, **(options_extra or {}))
+    if photo_yaml:
+        o["survey_name_photo"] = photo_yaml
+    t0 = time.time()
+    with quiet():
+        fm = cff.FisherMatrix(
+            fiducialpars=dict(tt.FIDUCIAL),
+            freepars=dict(freepars),
+            options=o,
+            specifications=specifications or {},
+            observables=list(observables),
+            extfiles=ext,
+            cosmoModel="w0waCDM",
+            surveyName="Euclid",
+        )
+        F = fm.compute()
+    wall = time.time() - t0
+    out = fisher_payload(F, fm)
+    out["wall_s"] = wall
+    cls = fm.photo_LSS.cls
+    keys = [k for k in cls if k != "ells"]
+    out["ells"] = np.array(cls["ells"])
+    out["cl_keys"] = np.array(keys)
+    out["cls"] = np.array([cls[k] for k in keys])
+    out["covmat"] = np.array([np.array(c, dtype=float) for c in fm.photo_LSS.covmat])
+    out["cov_cols"] = np.array(list(fm.photo_LSS.covmat[0].columns))
+    for par in save_derivs:
+        d = fm.photo_derivs[par]
+        out["dcl__" + par] = np.array([d[k] for k in keys])
+    pc = fm.photo_obs_fid
+    pc.compute_all()
+    out["z_grid"] = pc.z
+    out["sqrtP_WL"] = pc.sqrtPell["WL"][::8, ::4]
+    np.savez_compressed(os.path.join(GOLD, tag + ".npz"), **out)
+    print(f"{tag}: npar={len(out['param_names'])} wall={wall:.2f}s F00={out['fisher'][0,0]:.10e}")
+    return fm
+
+
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+@case
+def gcsp_cfg1():
+    """BASELINE cfg1 analogue: GCsp {Omegam,h} + auto nuisances, 3PT, 17x1025."""
+    run_gcsp("gcsp_cfg1", {"Omegam": 0.01, "h": 0.01})
+
+
+@case
+def gcsp_w0wa():
+    """cfg4 analogue on the default lattice: 7 cosmo + 4 lnbg + 4 Ps."""
+    run_gcsp("gcsp_w0wa", {p: 0.01 for p in PARS7})
+
+
+@case
+def gcsp_small():
+    """Small lattice with EVEN sample counts (scipy simpson's even-N correction) and 2 bins."""
+    run_gcsp(
+        "gcsp_small",
+        {"Omegam": 0.01, "h": 0.01, "w0": 0.01},
+        options_extra={"spectro_Pk_k_samples": 64, "spectro_Pk_mu_samples": 8},
+        max_z_bins=2,
+    )
+
+
+@case
+def wl_cfg2():
+    """BASELINE cfg2 analogue: WL only, 5 cosmo + 3 IA."""
+    run_photo("wl_cfg2", ["WL"], {p: 0.01 for p in PARS7[:5]}, save_derivs=("Omegam", "AIA", "etaIA"))
+
+
+@case
+def gcph_small():
+    """GCph only, coarse grids (ell_sampling=20, accuracy unchanged)."""
+    run_photo("gcph_small", ["GCph"], {"Omegam": 0.01, "sigma8": 0.01}, options_extra={"ell_sampling": 20},
+              save_derivs=("Omegam", "b3"))
+
+
+@case
+def photo_3x2pt():
+    """3x2pt w0waCDM 7 cosmo + 10 b + 3 IA (ISTF pessimistic, 10+10 bins)."""
+    run_photo("photo_3x2pt", ["WL", "GCph"], {p: 0.01 for p in PARS7},
+              save_derivs=("Omegam", "w0", "b1", "b7", "AIA", "betaIA"))
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    os.makedirs(SCRATCH, exist_ok=True)
+    os.chdir(SCRATCH)  # the reference creates ./cache and ./memory_cache at import
+    which = sys.argv[1:] or list(CASES)
+    for name in which:
+        CASES[name]()
