@@ -1,0 +1,317 @@
+"""ctypes binding of libcfp_b200.so (the C ABI declared in include/cfp_b200.h).
+
+There is NO CPU fallback: if the shared library is missing, or no CUDA device is usable, every
+compute entry point raises.  The library is built in-tree by ``__graft_entry__.build()`` /
+``make -C cosmicfishpie_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcfp_b200.so")
+
+# mirror of include/cfp_b200.h -----------------------------------------------------------------
+ABI_VERSION = 1
+BANK_DESC = 5
+TAB_PLIN, TAB_PNL, TAB_F, TAB_D, NTAB = 0, 1, 2, 3, 4
+(SP_Z, SP_COSMO, SP_QPAR, SP_QPER, SP_HUBBLE, SP_DZ, SP_BIAS, SP_A1, SP_A2, SP_SIGMAP, SP_I0, SP_I1, SP_I2,
+ SP_SVRESCALE, SP_FS8, SP_INVS8SQ, SP_KHFAC, SP_PSHOT, SP_NSCAL) = range(19)
+SPF_AP, SPF_FOG, SPF_LINEAR, SPF_KH_BEFORE_ERR = 1, 2, 4, 8
+MAT_LNP, MAT_DERIVS = 1, 2
+
+EXPORTS = [
+    "cfp_abi_version", "cfp_last_error", "cfp_ctx_create", "cfp_ctx_destroy", "cfp_ctx_sync",
+    "cfp_ctx_launch_count", "cfp_ctx_last_run_ms", "cfp_bank_upload", "cfp_bank_free", "cfp_bank_eval",
+    "cfp_spectro_plan_create", "cfp_spectro_plan_destroy", "cfp_spectro_plan_set_slice", "cfp_spectro_plan_run",
+    "cfp_spectro_plan_fisher_d", "cfp_spectro_plan_fetch", "cfp_photo_plan_create", "cfp_photo_plan_destroy",
+    "cfp_photo_plan_set_slice", "cfp_photo_plan_run", "cfp_photo_plan_fisher_d", "cfp_photo_plan_fetch",
+]
+
+
+class CfpError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+_vp = C.c_void_p
+
+
+def load():
+    """Load the shared library (once).  Raises CfpError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise CfpError(
+            f"{LIB_PATH} not found: the CUDA extension is not built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C cosmicfishpie_b200/csrc`). "
+            "cosmicfishpie_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    lib.cfp_abi_version.restype = C.c_int
+    lib.cfp_last_error.restype = C.c_char_p
+    lib.cfp_ctx_create.argtypes = [C.c_int, C.POINTER(_vp)]
+    lib.cfp_ctx_destroy.argtypes = [_vp]
+    lib.cfp_ctx_sync.argtypes = [_vp]
+    lib.cfp_ctx_launch_count.argtypes = [_vp]
+    lib.cfp_ctx_launch_count.restype = C.c_int64
+    lib.cfp_ctx_last_run_ms.argtypes = [_vp]
+    lib.cfp_ctx_last_run_ms.restype = C.c_double
+    lib.cfp_bank_upload.argtypes = [_vp, _dp, C.c_size_t, _lp, C.c_int, C.c_int, C.POINTER(_vp)]
+    lib.cfp_bank_free.argtypes = [_vp, _vp]
+    lib.cfp_bank_eval.argtypes = [_vp, _vp, C.c_int, C.c_int, _dp, _dp, C.c_size_t, _dp]
+    lib.cfp_spectro_plan_create.argtypes = [
+        _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, C.c_int, _dp, _dp,
+        _dp, _dp, _ip, C.c_int, _dp, _dp, C.c_uint, C.c_int, C.c_int, C.POINTER(_vp)]
+    lib.cfp_spectro_plan_destroy.argtypes = [_vp]
+    lib.cfp_spectro_plan_set_slice.argtypes = [_vp, C.c_int64, C.c_int64]
+    lib.cfp_spectro_plan_run.argtypes = [_vp, C.c_int, _vp]
+    lib.cfp_spectro_plan_fisher_d.argtypes = [_vp]
+    lib.cfp_spectro_plan_fisher_d.restype = _vp
+    lib.cfp_spectro_plan_fetch.argtypes = [_vp, _dp, _dp, _dp, _dp]
+    lib.cfp_photo_plan_create.argtypes = [
+        _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp, C.c_double, _dp, _dp, _dp,
+        _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int, C.POINTER(_vp)]
+    lib.cfp_photo_plan_destroy.argtypes = [_vp]
+    lib.cfp_photo_plan_set_slice.argtypes = [_vp, C.c_int, C.c_int]
+    lib.cfp_photo_plan_run.argtypes = [_vp, _vp]
+    lib.cfp_photo_plan_fisher_d.argtypes = [_vp]
+    lib.cfp_photo_plan_fisher_d.restype = _vp
+    lib.cfp_photo_plan_fetch.argtypes = [_vp, _dp, _dp, _dp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("cfp_abi_version",):
+            pass
+    if lib.cfp_abi_version() != ABI_VERSION:
+        raise CfpError(f"ABI mismatch: library {lib.cfp_abi_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().cfp_last_error().decode(errors="replace")
+        raise CfpError(f"{what} failed (status {rc}): {msg}")
+
+
+def f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a: Optional[np.ndarray], typ=_dp):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+class Context:
+    """One per GPU (cfp_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        self.handle = _vp()
+        _check(self.lib.cfp_ctx_create(int(device), C.byref(self.handle)), "cfp_ctx_create")
+        self.device = int(device)
+
+    def sync(self):
+        _check(self.lib.cfp_ctx_sync(self.handle), "cfp_ctx_sync")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.cfp_ctx_launch_count(self.handle))
+
+    @property
+    def last_run_ms(self) -> float:
+        return float(self.lib.cfp_ctx_last_run_ms(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.lib.cfp_ctx_destroy(self.handle)
+            self.handle = _vp()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device: Optional[int] = None) -> Context:
+    """Process-wide context for `device` (default: LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class Bank:
+    """Device-resident cosmology table bank (cfp_bank): bicubic (tx, ty, c) per cosmology and table."""
+
+    def __init__(self, ctx: Context, tcks):
+        """tcks[c][slot] = (tx, ty, c_flat) or None."""
+        self.ctx = ctx
+        n_cosmo = len(tcks)
+        desc = np.zeros((n_cosmo, NTAB, BANK_DESC), dtype=np.int64)
+        parts, off = [], 0
+        for ci, row in enumerate(tcks):
+            for slot in range(NTAB):
+                t = row[slot] if slot < len(row) else None
+                if t is None:
+                    continue
+                tx, ty, cc = (f64(x).ravel() for x in t)
+                assert cc.size == (tx.size - 4) * (ty.size - 4)
+                desc[ci, slot] = (tx.size, ty.size, off, off + tx.size, off + tx.size + ty.size)
+                parts += [tx, ty, cc]
+                off += tx.size + ty.size + cc.size
+        self.blob = np.concatenate(parts)
+        self.desc = desc
+        self.n_cosmo = n_cosmo
+        self.nbytes = self.blob.nbytes + desc.nbytes
+        self.handle = _vp()
+        _check(ctx.lib.cfp_bank_upload(ctx.handle, _p(self.blob), self.blob.size, _p(desc, _lp), n_cosmo, NTAB,
+                                       C.byref(self.handle)), "cfp_bank_upload")
+
+    def eval(self, cosmo: int, table: int, z, k) -> np.ndarray:
+        z, k = np.broadcast_arrays(f64(z), f64(k))
+        z, k = f64(z).ravel(), f64(k).ravel()
+        out = np.empty_like(z)
+        _check(self.ctx.lib.cfp_bank_eval(self.ctx.handle, self.handle, cosmo, table, _p(z), _p(k), z.size, _p(out)),
+               "cfp_bank_eval")
+        return out
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.cfp_bank_free(self.ctx.handle, self.handle)
+            self.handle = _vp()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SpectroPlan:
+    def __init__(self, ctx: Context, bank: Bank, *, k, mu, wk, wmu, scal, alias, pnw_k, pnw_p, stw, stden, ps_bin,
+                 ps_src, nbar, vol, flags, tab_plin=TAB_PLIN, tab_f=TAB_F):
+        self.ctx, self.bank = ctx, bank
+        self.k, self.mu, self.wk, self.wmu = f64(k), f64(mu), f64(wk), f64(wmu)
+        self.scal = f64(scal)
+        self.S, self.Z = self.scal.shape[:2]
+        assert self.scal.shape[2] == SP_NSCAL
+        self.alias = i32(alias)
+        self.pnw_k, self.pnw_p = f64(pnw_k), f64(pnw_p)
+        self.stw, self.stden, self.ps_bin = f64(stw), f64(stden), i32(ps_bin)
+        self.npar = self.stw.shape[0]
+        self.nbar, self.vol = f64(nbar), f64(vol)
+        self.Nk, self.Nmu = self.k.size, self.mu.size
+        nnw = self.pnw_k.shape[-1]
+        assert self.pnw_k.shape == (bank.n_cosmo, nnw) and self.pnw_p.shape == (bank.n_cosmo, self.Z, nnw)
+        assert self.alias.shape == (self.S, self.Z) and self.stw.shape == (self.npar, self.S)
+        self.handle = _vp()
+        _check(ctx.lib.cfp_spectro_plan_create(
+            ctx.handle, bank.handle, self.S, self.Z, self.Nmu, self.Nk, self.npar, _p(self.k), _p(self.mu),
+            _p(self.wk), _p(self.wmu), _p(self.scal), _p(self.alias, _ip), nnw, _p(self.pnw_k), _p(self.pnw_p),
+            _p(self.stw), _p(self.stden), _p(self.ps_bin, _ip), int(ps_src), _p(self.nbar), _p(self.vol),
+            int(flags), int(tab_plin), int(tab_f), C.byref(self.handle)), "cfp_spectro_plan_create")
+        self.h2d_bytes = sum(a.nbytes for a in (self.k, self.mu, self.wk, self.wmu, self.scal, self.alias, self.pnw_k,
+                                                self.pnw_p, self.stw, self.stden, self.ps_bin, self.nbar, self.vol))
+
+    def set_slice(self, begin: int, end: int):
+        _check(self.ctx.lib.cfp_spectro_plan_set_slice(self.handle, int(begin), int(end)), "cfp_spectro_plan_set_slice")
+
+    def run(self, materialize: int = 0, stream: int = 0):
+        _check(self.ctx.lib.cfp_spectro_plan_run(self.handle, int(materialize), _vp(stream) if stream else None),
+               "cfp_spectro_plan_run")
+
+    def fisher_device_ptr(self) -> int:
+        return int(self.ctx.lib.cfp_spectro_plan_fisher_d(self.handle) or 0)
+
+    def fetch(self, lnp=False, derivs=False):
+        F = np.empty((self.Z, self.npar, self.npar))
+        L = np.empty((self.S, self.Z, self.Nmu, self.Nk)) if lnp else None
+        D = np.empty((self.npar, self.Z, self.Nmu, self.Nk)) if derivs else None
+        V = np.empty((self.Z, self.Nmu, self.Nk)) if derivs else None
+        _check(self.ctx.lib.cfp_spectro_plan_fetch(self.handle, _p(F), _p(L), _p(D), _p(V)), "cfp_spectro_plan_fetch")
+        return F, L, D, V
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.cfp_spectro_plan_destroy(self.handle)
+            self.handle = _vp()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PhotoPlan:
+    def __init__(self, ctx: Context, bank: Bank, *, cosmo_of_s, ell, z, dz, chi, hub, wlpref, kind, ngal, bias, ia,
+                 lmin, lmax, noise, sqrtfsky, stw, stden, kmax, tab_p=TAB_PNL):
+        self.ctx, self.bank = ctx, bank
+        self.cosmo_of_s = i32(cosmo_of_s)
+        self.ell, self.z = f64(ell), f64(z)
+        self.chi, self.hub, self.wlpref = f64(chi), f64(hub), f64(wlpref)
+        self.kind = i32(kind)
+        self.ngal, self.bias, self.ia = f64(ngal), f64(bias), f64(ia)
+        self.lmin, self.lmax, self.noise, self.sqrtfsky = f64(lmin), f64(lmax), f64(noise), f64(sqrtfsky)
+        self.stw, self.stden = f64(stw), f64(stden)
+        self.S, self.NC = self.cosmo_of_s.size, self.chi.shape[0]
+        self.Nl, self.Nz, self.Nb, self.npar = self.ell.size, self.z.size, self.kind.size, self.stw.shape[0]
+        assert self.chi.shape == (self.NC, self.Nz) and self.hub.shape == (self.NC, self.Nz)
+        assert self.ngal.shape == (self.Nb, self.Nz) and self.bias.shape == (self.S, self.Nb, self.Nz)
+        assert self.ia.shape == (self.S, self.Nz) and self.stw.shape == (self.npar, self.S)
+        self.handle = _vp()
+        _check(ctx.lib.cfp_photo_plan_create(
+            ctx.handle, bank.handle, self.S, self.NC, self.Nl, self.Nz, self.Nb, self.npar, _p(self.cosmo_of_s, _ip),
+            _p(self.ell), _p(self.z), float(dz), _p(self.chi), _p(self.hub), _p(self.wlpref), _p(self.kind, _ip),
+            _p(self.ngal), _p(self.bias), _p(self.ia), _p(self.lmin), _p(self.lmax), _p(self.noise),
+            _p(self.sqrtfsky), _p(self.stw), _p(self.stden), float(kmax), int(tab_p), C.byref(self.handle)),
+            "cfp_photo_plan_create")
+        self.h2d_bytes = sum(a.nbytes for a in (self.cosmo_of_s, self.ell, self.z, self.chi, self.hub, self.wlpref,
+                                                self.kind, self.ngal, self.bias, self.ia, self.lmin, self.lmax,
+                                                self.noise, self.sqrtfsky, self.stw, self.stden))
+
+    def set_slice(self, l_begin: int, l_end: int):
+        _check(self.ctx.lib.cfp_photo_plan_set_slice(self.handle, int(l_begin), int(l_end)), "cfp_photo_plan_set_slice")
+
+    def run(self, stream: int = 0):
+        _check(self.ctx.lib.cfp_photo_plan_run(self.handle, _vp(stream) if stream else None), "cfp_photo_plan_run")
+
+    def fisher_device_ptr(self) -> int:
+        return int(self.ctx.lib.cfp_photo_plan_fisher_d(self.handle) or 0)
+
+    def fetch(self, cls=False, sqrtp=False):
+        F = np.empty((self.npar, self.npar))
+        Cl = np.empty((self.S, self.Nl, self.Nb, self.Nb)) if cls else None
+        T = np.empty((self.NC, self.Nl, self.Nz)) if sqrtp else None
+        _check(self.ctx.lib.cfp_photo_plan_fetch(self.handle, _p(F), _p(Cl), _p(T)), "cfp_photo_plan_fetch")
+        return F, Cl, T
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.cfp_photo_plan_destroy(self.handle)
+            self.handle = _vp()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass

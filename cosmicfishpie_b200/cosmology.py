@@ -1,0 +1,259 @@
+"""Host-side cosmology input: cached Boltzmann tables -> spline facade -> device table bank.
+
+This is the INPUT BOUNDARY of the hot path.  Boltzmann output (P(k,z), H(z),
+growth ...) is computed once elsewhere, cached as tables, and consumed identically by the reference
+and by this package.  Here the tables are turned into the same FITPACK splines the reference builds
+(`external_input.calculate_interpol_results`, cosmicfishpie/cosmology/cosmology.py:1423-1540) so that
+the knots/coefficients shipped to the GPU are *the* piecewise polynomials the reference evaluates.
+
+Two sources are accepted for `extfiles`:
+  * the reference's directory layout (cosmology.py:1249-1373), `extfiles["directory"]`
+  * an in-memory bank `extfiles["tables"] = {folder_name: {z,k,H,s8,D,f,Pl,Pnl}}`
+    (what `cosmicfishpie_b200.toy_tables.make_bank` returns) -- same numbers, no text parsing.
+
+Only `code="external"` exists here: the Boltzmann solvers themselves are out of scope.
+"""
+from __future__ import annotations
+
+import glob
+import math
+import os
+from typing import Dict, Optional
+
+import numpy as np
+from scipy.integrate import trapezoid
+from scipy.interpolate import InterpolatedUnivariateSpline, RectBivariateSpline
+from scipy.signal import savgol_filter
+
+from . import _lib
+
+C_KMS = 299792.458  # scipy.constants.speed_of_light / 1000
+
+DEFAULT_FILE_NAMES = {  # config.py:289-304
+    "H_z": "background_Hz",
+    "D_zk": "D_Growth-zk",
+    "f_zk": "f_GrowthRate-zk",
+    "Pl_zk": "Plin-zk",
+    "Pnl_zk": "Pnonlin-zk",
+    "s8_z": "sigma8-z",
+    "z_arr": "z_values_list",
+    "k_arr": "k_values_list",
+}
+_KEYMAP = {"z": "z_arr", "k": "k_arr", "H": "H_z", "s8": "s8_z", "D": "D_zk", "f": "f_zk", "Pl": "Pl_zk", "Pnl": "Pnl_zk"}
+
+
+def round_decimals_up(number: float) -> float:
+    """One-decimal mantissa ceiling (utilities/utils.py numerics.round_decimals_up)."""
+    exponent = math.floor(math.log10(number))
+    return math.ceil(number / (10**exponent) * 10) / 10 * (10**exponent)
+
+
+def folder_for(cosmopars, fiducial, external) -> str:
+    """Which table folder serves `cosmopars`: snap (theta/theta_fid - 1) to the nearest tabulated
+    epsilon of the first parameter that differs from the fiducial (cosmology.py:1375-1421)."""
+    names = external["paramnames"]
+    fnames = external.get("folder_paramnames") or names
+    eps = np.array(external["eps_values"], dtype=float)
+    allowed = np.concatenate((eps, -eps, np.array([0.0])))
+    for par, fpar in zip(names, fnames):
+        if np.isclose(cosmopars[par], fiducial[par], rtol=1e-5):
+            continue
+        if fiducial[par] != 0:
+            d = cosmopars[par] / fiducial[par] - 1.0
+        else:
+            d = cosmopars[par] - fiducial[par]
+        tag = "pl" if d > 0 else "mn"
+        d = allowed[np.abs(allowed - d).argmin()]
+        tok = "{:.1E}".format(round_decimals_up(abs(d))).replace(".", "p")
+        if external.get("E-00", True) is False:
+            tok = tok.replace("E-0", "E-")
+        return f"{fpar}_{tag}_eps_{tok}"
+    return external.get("fiducial_folder", "fiducial_eps_0")
+
+
+_TABLE_CACHE: Dict[tuple, dict] = {}
+
+
+def load_tables(external: dict, folder: str) -> dict:
+    """Raw arrays of one folder, cached per (source, folder)."""
+    if "tables" in external and external["tables"] is not None:
+        return external["tables"][folder]
+    key = (os.path.abspath(external["directory"]), folder)
+    if key in _TABLE_CACHE:
+        return _TABLE_CACHE[key]
+    names = dict(DEFAULT_FILE_NAMES)
+    names.update({k: v for k, v in (external.get("file_names") or {}).items() if v is not None})
+    out = {}
+    for short, long in _KEYMAP.items():
+        path = None
+        for base in (folder, external.get("fiducial_folder", "fiducial_eps_0")):  # fiducial fallback for grids/H
+            hits = glob.glob(os.path.join(external["directory"], base, names[long] + ".*"))
+            if hits:
+                path = hits[0]
+                break
+        if path is None:
+            raise FileNotFoundError(f"{names[long]}.* not found under {external['directory']}/{folder}")
+        out[short] = np.loadtxt(path)
+    _TABLE_CACHE[key] = out
+    return out
+
+
+def _dcom_trapz(zi, hfunc):
+    zt = np.linspace(0.0, zi, 100)  # cosmology.py:36-55
+    return trapezoid(1 / hfunc(zt), zt)
+
+
+class cosmo_functions:
+    """Spline facade of one cosmology (reference: cosmology.py:1546-2010, external branch).
+
+    Host accessors keep the reference names (`Hubble`, `angdist`, `comoving`, `matpow`, `f_growthrate`,
+    `growth`, `sigma8_of_z`, `Omegam_of_z`, `nonwiggle_pow`, `E_hubble`).  `bank_row()` exports the
+    bicubic tck of the (z,k) tables for the device bank.
+    """
+
+    c = C_KMS
+
+    def __init__(self, cosmopars, input=None, config=None):
+        if config is None:
+            from . import config as config_module
+
+            config = config_module.current()
+        self.config = config
+        self.settings = config.settings
+        self.input = input if input is not None else config.input_type
+        if self.input != "external":
+            raise NotImplementedError(
+                f"cosmicfishpie_b200 consumes cached Boltzmann tables only (code='external'); got {self.input!r}"
+            )
+        self.code = "external"
+        self.external = config.external
+        self.cosmopars = cosmopars
+        self.fiducialcosmopars = config.fiducialparams
+        self.folder = folder_for(cosmopars, self.fiducialcosmopars, self.external)
+        t = load_tables(self.external, self.folder)
+        pkf = rf = kf = 1.0
+        if self.external.get("k-units") == "h/Mpc":  # cosmology.py:1438-1444
+            pkf = (1 / cosmopars["h"]) ** 3
+            kf = cosmopars["h"]
+        ru = self.external.get("r-units")
+        if ru == "Mpc/h":
+            rf = 1 / cosmopars["h"]
+        elif ru == "km/s/Mpc":
+            rf = C_KMS
+        zg = np.asarray(t["z"], float).flatten()
+        kg = kf * np.asarray(t["k"], float).flatten()
+        self.zgrid, self.kgrid = zg, kg
+        self.h_of_z = InterpolatedUnivariateSpline(zg, (1 / rf) * np.asarray(t["H"], float).flatten())
+        dcom = np.array([_dcom_trapz(zi, self.h_of_z) for zi in zg])
+        self.com_dist = InterpolatedUnivariateSpline(zg, dcom)
+        self.ang_dist = InterpolatedUnivariateSpline(zg, dcom / (1 + zg))
+        self.D_growth_zk = RectBivariateSpline(zg, kg, t["D"], kx=3, ky=3)
+        self.f_growthrate_zk = RectBivariateSpline(zg, kg, t["f"], kx=3, ky=3)
+        self.s8_of_z = InterpolatedUnivariateSpline(zg, np.asarray(t["s8"], float).flatten())
+        self.Pk_l = RectBivariateSpline(zg, kg, pkf * np.asarray(t["Pl"], float), kx=3, ky=3)
+        self.Pk_nl = RectBivariateSpline(zg, kg, pkf * np.asarray(t["Pnl"], float), kx=3, ky=3)
+        self.results = self  # reference code reaches splines through `.results`
+        self._nw_cache = {}
+
+    # --- host accessors --------------------------------------------------------------------
+    def Hubble(self, z, physical=False):
+        return (self.c if physical else 1) * self.h_of_z(z)
+
+    def E_hubble(self, z):
+        return self.Hubble(z) / self.Hubble(0.0)
+
+    def angdist(self, z):
+        return self.ang_dist(z)
+
+    def comoving(self, z):
+        return self.com_dist(z)
+
+    def matpow(self, z, k, nonlinear=False, tracer="matter"):
+        return (self.Pk_nl if nonlinear else self.Pk_l)(z, k, grid=False)
+
+    def f_growthrate(self, z, k=None, gamma=False, tracer="matter"):
+        return self.f_growthrate_zk(z, 0.0001 if k is None else k, grid=False)
+
+    def growth(self, z, k=None):
+        return self.D_growth_zk(z, 0.0001 if k is None else k, grid=False)
+
+    def sigma8_of_z(self, z, tracer="matter"):
+        return self.s8_of_z(z)
+
+    def fsigma8_of_z(self, z, k=None, gamma=False, tracer="matter"):
+        return self.f_growthrate(z, k) * self.sigma8_of_z(z)
+
+    def Omegam_of_z(self, z):
+        return (self.cosmopars["Omegam"] * (1 + z) ** 3) / self.E_hubble(z) ** 2
+
+    def SigmaMG(self, z, k):
+        return np.array(1)
+
+    def nonwiggle_table(self, z, nonlinear=False):
+        """Knots and coefficients of the degree-1 no-wiggle spline at redshift z
+        (Savitzky-Golay smoothing in ln k, cosmology.py:1760-1813)."""
+        key = (float(z), bool(nonlinear))
+        if key not in self._nw_cache:
+            s = self.settings
+            h = self.cosmopars["h"]
+            lk = np.linspace(np.log(h * s["savgol_internalkmin"]), np.log(h * np.max(self.kgrid)),
+                             s["savgol_internalsamples"])
+            dlnk = np.mean(lk[1:] - lk[0:-1])
+            n_sg = int(np.round(s["savgol_width"] / np.log(1 + dlnk)))
+            lp = InterpolatedUnivariateSpline(lk, np.log(self.matpow(z, np.exp(lk), nonlinear=nonlinear).flatten()), k=1)
+            sg = savgol_filter(lp(lk), n_sg, s["savgol_polyorder"])
+            spl = InterpolatedUnivariateSpline(np.exp(lk), np.exp(sg), k=1)
+            t, c, _ = spl._eval_args
+            n = len(t) - 2
+            self._nw_cache[key] = (np.ascontiguousarray(t[1:-1]), np.ascontiguousarray(c[:n]), spl)
+        return self._nw_cache[key]
+
+    def nonwiggle_pow(self, z, k, nonlinear=False, tracer="matter"):
+        return self.nonwiggle_table(z, nonlinear)[2](k)
+
+    # --- device export -----------------------------------------------------------------------
+    def bank_row(self):
+        """[P_lin, P_nl, f, D] bicubic (tx, ty, c) in the slot order of include/cfp_b200.h."""
+        row = [None] * _lib.NTAB
+        for slot, spl in ((_lib.TAB_PLIN, self.Pk_l), (_lib.TAB_PNL, self.Pk_nl), (_lib.TAB_F, self.f_growthrate_zk),
+                          (_lib.TAB_D, self.D_growth_zk)):
+            tx, ty, c = spl.tck
+            row[slot] = (tx, ty, c)
+        return row
+
+
+class CosmoSet:
+    """The distinct cosmologies of one job (fiducial + stencil points), their host facades and the
+    device bank.  Index 0 is always the fiducial."""
+
+    def __init__(self, config, ctx: Optional[_lib.Context] = None):
+        self.config = config
+        self.ctx = ctx
+        self._by_key = {}
+        self.cosmos = []
+        self.add(config.fiducialparams, config.fiducialcosmo)
+        self._bank = None
+
+    @staticmethod
+    def _key(cosmopars):
+        return tuple(sorted((k, v) for k, v in cosmopars.items()))
+
+    def add(self, cosmopars, cosmo=None) -> int:
+        key = self._key(cosmopars)
+        if key not in self._by_key:
+            if cosmo is None:
+                cosmo = cosmo_functions(dict(cosmopars), self.config.input_type, self.config)
+            self._by_key[key] = len(self.cosmos)
+            self.cosmos.append(cosmo)
+            self._bank = None
+        return self._by_key[key]
+
+    def __len__(self):
+        return len(self.cosmos)
+
+    def bank(self) -> _lib.Bank:
+        if self._bank is None:
+            if self.ctx is None:
+                self.ctx = _lib.default_context()
+            self._bank = _lib.Bank(self.ctx, [c.bank_row() for c in self.cosmos])
+        return self._bank

@@ -1,0 +1,126 @@
+// Shared internals of libcfp_b200.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "cfp_b200.h"
+
+void cfp_set_error(const char* fmt, ...);
+
+#define CFP_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      cfp_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return CFP_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define CFP_REQUIRE(cond, msg)                               \
+  do {                                                       \
+    if (!(cond)) {                                           \
+      cfp_set_error("%s:%d: %s", __FILE__, __LINE__, msg);   \
+      return CFP_ERR_INVALID;                                \
+    }                                                        \
+  } while (0)
+
+struct cfp_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+  double last_ms = 0.0;
+};
+
+struct cfp_bank {
+  cfp_ctx* ctx = nullptr;
+  int n_cosmo = 0, n_tables = 0;
+  size_t n = 0;
+  double* blob_d = nullptr;
+  int64_t* desc_d = nullptr;
+  std::vector<int64_t> desc_h;  // [n_cosmo][n_tables][CFP_BANK_DESC]
+  const int64_t* desc(int c, int t) const { return &desc_h[((size_t)c * n_tables + t) * CFP_BANK_DESC]; }
+};
+
+// Upload helper: cudaMalloc + async copy on the context stream.
+template <typename T>
+int cfp_upload(cfp_ctx* ctx, const T* src_h, size_t count, T** dst_d) {
+  *dst_d = nullptr;
+  if (count == 0) return CFP_OK;
+  CFP_CUDA(cudaMalloc((void**)dst_d, count * sizeof(T)));
+  if (src_h) {
+    CFP_CUDA(cudaMemcpyAsync(*dst_d, src_h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    CFP_CUDA(cudaMemsetAsync(*dst_d, 0, count * sizeof(T), ctx->stream));
+  }
+  return CFP_OK;
+}
+
+// ------------------------------------------------------------------ device spline helpers
+// Interval search with FITPACK semantics (fpbisp.f): the largest l in [3, n-5] with
+// t[l] <= x, for x already clamped to [t[3], t[n-4]].
+__device__ __forceinline__ int cfp_find_interval(const double* __restrict__ t, int n, double x) {
+  int lo = 3, hi = n - 5;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (__ldg(t + mid) <= x)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
+
+// Non-zero cubic B-spline basis values at x in [t[l], t[l+1]) -- de Boor / fpbspl.f recurrence.
+__device__ __forceinline__ void cfp_bspl3(const double* __restrict__ t, int l, double x, double h[4]) {
+  double hh[3];
+  h[0] = 1.0;
+#pragma unroll
+  for (int j = 1; j <= 3; ++j) {
+#pragma unroll
+    for (int i = 0; i < j; ++i) hh[i] = h[i];
+    h[0] = 0.0;
+#pragma unroll
+    for (int i = 0; i < j; ++i) {
+      const double tli = __ldg(t + l + i + 1);
+      const double tlj = __ldg(t + l + i + 1 - j);
+      if (tli == tlj) {
+        h[i + 1] = 0.0;
+      } else {
+        // explicit round-to-nearest intrinsics: no FMA contraction, so the result is
+        // bit-identical to the (non-FMA) FITPACK build scipy ships
+        const double f = __ddiv_rn(hh[i], __dsub_rn(tli, tlj));
+        h[i] = __dadd_rn(h[i], __dmul_rn(f, __dsub_rn(tli, x)));
+        h[i + 1] = __dmul_rn(f, __dsub_rn(x, tlj));
+      }
+    }
+  }
+}
+
+// Point-wise bicubic evaluation (bispeu / fpbisp.f order of accumulation).
+__device__ __forceinline__ double cfp_bispev_point(const double* __restrict__ tx, int nx,
+                                                   const double* __restrict__ ty, int ny,
+                                                   const double* __restrict__ c, double x, double y) {
+  x = fmin(fmax(x, __ldg(tx + 3)), __ldg(tx + nx - 4));
+  y = fmin(fmax(y, __ldg(ty + 3)), __ldg(ty + ny - 4));
+  const int lx = cfp_find_interval(tx, nx, x);
+  const int ly = cfp_find_interval(ty, ny, y);
+  double hx[4], hy[4];
+  cfp_bspl3(tx, lx, x, hx);
+  cfp_bspl3(ty, ly, y, hy);
+  const int ncy = ny - 4;
+  const double* cc = c + (size_t)(lx - 3) * ncy + (ly - 3);
+  double sp = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sp = __dadd_rn(sp, __dmul_rn(__dmul_rn(__ldg(cc + (size_t)i * ncy + j), hx[i]), hy[j]));
+  }
+  return sp;
+}

@@ -1,0 +1,144 @@
+// Context, error handling and the cosmology table bank of libcfp_b200.so.
+#include <cstdarg>
+
+#include "cfp_common.cuh"
+
+static thread_local std::string g_cfp_error;
+
+void cfp_set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_cfp_error = buf;
+}
+
+extern "C" int cfp_abi_version(void) { return CFP_ABI_VERSION; }
+
+extern "C" const char* cfp_last_error(void) { return g_cfp_error.c_str(); }
+
+extern "C" int cfp_ctx_create(int device, cfp_ctx** out) {
+  CFP_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  CFP_CUDA(cudaGetDeviceCount(&ndev));
+  CFP_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+  CFP_CUDA(cudaSetDevice(device));
+  cfp_ctx* ctx = new cfp_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  CFP_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  CFP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CFP_CUDA(cudaEventCreate(&ctx->ev0));
+  CFP_CUDA(cudaEventCreate(&ctx->ev1));
+  *out = ctx;
+  return CFP_OK;
+}
+
+extern "C" int cfp_ctx_destroy(cfp_ctx* ctx) {
+  if (!ctx) return CFP_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return CFP_OK;
+}
+
+extern "C" int cfp_ctx_sync(cfp_ctx* ctx) {
+  CFP_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  CFP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CFP_OK;
+}
+
+extern "C" int64_t cfp_ctx_launch_count(const cfp_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" double cfp_ctx_last_run_ms(const cfp_ctx* ctx) { return ctx ? ctx->last_ms : -1.0; }
+
+// ------------------------------------------------------------------------------ bank
+extern "C" int cfp_bank_upload(cfp_ctx* ctx, const double* blob_h, size_t n_doubles,
+                               const int64_t* desc_h, int n_cosmo, int n_tables, cfp_bank** out) {
+  CFP_REQUIRE(ctx && blob_h && desc_h && out, "NULL argument");
+  CFP_REQUIRE(n_cosmo > 0 && n_tables > 0 && n_doubles > 0, "empty bank");
+  *out = nullptr;
+  const size_t nd = (size_t)n_cosmo * n_tables * CFP_BANK_DESC;
+  for (int c = 0; c < n_cosmo; ++c)
+    for (int t = 0; t < n_tables; ++t) {
+      const int64_t* d = desc_h + ((size_t)c * n_tables + t) * CFP_BANK_DESC;
+      if (d[0] == 0 && d[1] == 0) continue;  // empty slot
+      CFP_REQUIRE(d[0] >= 8 && d[1] >= 8, "bicubic table needs >= 8 knots per axis");
+      CFP_REQUIRE(d[2] >= 0 && (size_t)(d[2] + d[0]) <= n_doubles, "tx out of range");
+      CFP_REQUIRE(d[3] >= 0 && (size_t)(d[3] + d[1]) <= n_doubles, "ty out of range");
+      CFP_REQUIRE(d[4] >= 0 && (size_t)(d[4] + (d[0] - 4) * (d[1] - 4)) <= n_doubles, "c out of range");
+    }
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cfp_bank* b = new cfp_bank();
+  b->ctx = ctx;
+  b->n_cosmo = n_cosmo;
+  b->n_tables = n_tables;
+  b->n = n_doubles;
+  b->desc_h.assign(desc_h, desc_h + nd);
+  int rc = cfp_upload(ctx, blob_h, n_doubles, &b->blob_d);
+  if (rc == CFP_OK) rc = cfp_upload(ctx, desc_h, nd, &b->desc_d);
+  if (rc == CFP_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = CFP_ERR_CUDA;
+  if (rc != CFP_OK) {
+    cudaFree(b->blob_d);
+    cudaFree(b->desc_d);
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return CFP_OK;
+}
+
+extern "C" int cfp_bank_free(cfp_ctx* ctx, cfp_bank* bank) {
+  if (!bank) return CFP_OK;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaFree(bank->blob_d);
+  cudaFree(bank->desc_d);
+  delete bank;
+  return CFP_OK;
+}
+
+__global__ void cfp_bank_eval_kernel(const double* __restrict__ blob, int64_t nx, int64_t ny, int64_t otx,
+                                     int64_t oty, int64_t oc, const double* __restrict__ z,
+                                     const double* __restrict__ k, size_t n, double* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = cfp_bispev_point(blob + otx, (int)nx, blob + oty, (int)ny, blob + oc, z[i], k[i]);
+}
+
+extern "C" int cfp_bank_eval(cfp_ctx* ctx, const cfp_bank* bank, int cosmo, int table, const double* z_h,
+                             const double* k_h, size_t n, double* out_h) {
+  CFP_REQUIRE(ctx && bank && z_h && k_h && out_h, "NULL argument");
+  CFP_REQUIRE(cosmo >= 0 && cosmo < bank->n_cosmo && table >= 0 && table < bank->n_tables, "index out of range");
+  if (n == 0) return CFP_OK;
+  const int64_t* d = bank->desc(cosmo, table);
+  CFP_REQUIRE(d[0] >= 8 && d[1] >= 8, "empty table slot");
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  double *z_d = nullptr, *k_d = nullptr, *o_d = nullptr;
+  int rc = cfp_upload(ctx, z_h, n, &z_d);
+  if (rc == CFP_OK) rc = cfp_upload(ctx, k_h, n, &k_d);
+  if (rc == CFP_OK) rc = cfp_upload<double>(ctx, nullptr, n, &o_d);
+  if (rc == CFP_OK) {
+    const int bs = 128;
+    cfp_bank_eval_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, ctx->stream>>>(bank->blob_d, d[0], d[1], d[2], d[3],
+                                                                              d[4], z_d, k_d, n, o_d);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_h, o_d, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      cfp_set_error("cfp_bank_eval: %s", cudaGetErrorString(e));
+      rc = CFP_ERR_CUDA;
+    }
+  }
+  cudaFree(z_d);
+  cudaFree(k_d);
+  cudaFree(o_d);
+  return rc;
+}

@@ -1,0 +1,521 @@
+// Photometric 3x2pt: Limber kernels, C_ell contraction on FP64 tensor cores, Cholesky/trace Fisher.
+//
+// Kernels (all FP64):
+//   photo_sqrtp_kernel    T[c][l][z] = sqrt(P(z,(l+1/2)/chi))/chi for kappa < kmax, else 0; point-wise
+//                         bicubic B-spline evaluation with FITPACK semantics        (photo_obs.py:457-512)
+//   photo_eff_kernel      lensing efficiency by backward cumulative trapezoid      (photo_obs.py:113-160)
+//   photo_window_kernel   per stencil point: W_a(z)/sqrt(H) and W^IA_a(z)/sqrt(H)   (photo_obs.py:514-722)
+//   photo_cls_kernel      C_l[a][b] = sum_z w_z K_a K_b, K_a = T W_a + T W^IA_a, as a batch of
+//                         (Nb x Nz)(Nz x Nb) SYRKs on mma.sync m8n8k4 f64 (DMMA)    (photo_obs.py:878-928)
+//   photo_fisher_kernel   per multipole bin: covariance, Cholesky, Y_p = L^-1 (Phi dC_p) L^-T and
+//                         F_pq += w_l sum_ij Y_p[ij] Y_q[ji]   (photo_cov.py:198-245, cosmicfish.py:643-744)
+//   photo_reduce_kernel   fixed-order sum over multipole bins.
+#include <algorithm>
+#include <cmath>
+
+#include "cfp_common.cuh"
+
+namespace {
+
+constexpr int CLS_THREADS = 128;
+constexpr int CLS_WARPS = CLS_THREADS / 32;
+constexpr int MAX_PNB = 8;  // Nb <= 64 tomographic rows
+
+__global__ void photo_sqrtp_kernel(const double* __restrict__ blob, const int64_t* __restrict__ desc, int n_tables,
+                                   int tab, int NC, int Nl, int Nz, const double* __restrict__ ell,
+                                   const double* __restrict__ z, const double* __restrict__ chi, double kmax,
+                                   double* __restrict__ T) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t tot = (size_t)NC * Nl * Nz;
+  if (idx >= tot) return;
+  const int iz = (int)(idx % Nz);
+  const int il = (int)((idx / Nz) % Nl);
+  const int c = (int)(idx / ((size_t)Nz * Nl));
+  const double ch = chi[(size_t)c * Nz + iz];
+  const double kappa = (ell[il] + 0.5) / ch;  // photo_obs.py:481
+  double v = 0.0;
+  if (kappa < kmax) {
+    const int64_t* d = desc + ((size_t)c * n_tables + tab) * CFP_BANK_DESC;
+    const double p = cfp_bispev_point(blob + d[2], (int)d[0], blob + d[3], (int)d[1], blob + d[4], z[iz], kappa);
+    v = sqrt(p) / ch;
+  }
+  T[idx] = v;
+}
+
+// one thread per (cosmology, WL row): eff = I1 - chi * I2 with backward cumulative trapezoids
+__global__ void photo_eff_kernel(int NC, int Nb, int Nz, const int* __restrict__ kind, const double* __restrict__ ngal,
+                                 const double* __restrict__ chi, double dz, double* __restrict__ eff) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NC * Nb) return;
+  const int c = idx / Nb, a = idx % Nb;
+  double* e = eff + (size_t)idx * Nz;
+  if (kind[a] != 0) {
+    for (int i = 0; i < Nz; ++i) e[i] = 0.0;
+    return;
+  }
+  const double* n = ngal + (size_t)a * Nz;
+  const double* ch = chi + (size_t)c * Nz;
+  double I1 = 0.0, I2 = 0.0;
+  e[Nz - 1] = I1 - ch[Nz - 1] * I2;
+  double n_hi = n[Nz - 1], q_hi = n[Nz - 1] / ch[Nz - 1];
+  for (int i = Nz - 2; i >= 0; --i) {
+    const double n_lo = n[i], q_lo = n[i] / ch[i];
+    I1 = I1 + 0.5 * (n_hi + n_lo) * dz;
+    I2 = I2 + 0.5 * (q_hi + q_lo) * dz;
+    e[i] = I1 - ch[i] * I2;
+    n_hi = n_lo;
+    q_hi = q_lo;
+  }
+}
+
+// U[s][a][z] = W_a/sqrt(H), V[s][a][z] = W^IA_a/sqrt(H), rows padded to ldz
+__global__ void photo_window_kernel(int S, int Nb, int Nz, int ldz, int nrow_pad, const int* __restrict__ cosmo_of_s,
+                                    const int* __restrict__ kind, const double* __restrict__ z,
+                                    const double* __restrict__ chi, const double* __restrict__ hub,
+                                    const double* __restrict__ wlpref, const double* __restrict__ ngal,
+                                    const double* __restrict__ bias, const double* __restrict__ ia,
+                                    const double* __restrict__ eff, double* __restrict__ U, double* __restrict__ V) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t tot = (size_t)S * nrow_pad * ldz;
+  if (idx >= tot) return;
+  const int iz = (int)(idx % ldz);
+  const int a = (int)((idx / ldz) % nrow_pad);
+  const int s = (int)(idx / ((size_t)ldz * nrow_pad));
+  double u = 0.0, v = 0.0;
+  if (a < Nb && iz < Nz) {
+    const int c = cosmo_of_s[s];
+    const double H = hub[(size_t)c * Nz + iz];
+    const double sh = sqrt(H);
+    const double ng = ngal[(size_t)a * Nz + iz];
+    if (kind[a] == 0) {  // lensing row, photo_obs.py:584-590
+      const double w = wlpref[c] * (1.0 + z[iz]) * chi[(size_t)c * Nz + iz] * eff[((size_t)c * Nb + a) * Nz + iz];
+      const double wia = ng * ia[(size_t)s * Nz + iz] * H;
+      u = w / sh;
+      v = wia / sh;
+    } else {  // clustering row, photo_obs.py:542, 715-717
+      const double w = (ng * H) * bias[((size_t)s * Nb + a) * Nz + iz];
+      u = w / sh;
+      v = 0.0;
+    }
+  }
+  U[idx] = u;
+  V[idx] = v;
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+struct ClsParams {
+  int S, Nl, Nz, Nb, nb, ldz, nz4, lch, l_begin, l_end;
+  const int* cosmo_of_s;
+  const double *U, *V;   // [S][nb*8][ldz]
+  const double* T;       // [NC][Nl][Nz]
+  const double* wz;      // [nz4] trapezoid weights (zero padded)
+  const double *ell, *lmin, *lmax;
+  double* cls;           // [S][Nl][Nb][Nb]
+};
+
+template <int NB>
+__global__ void __launch_bounds__(CLS_THREADS) photo_cls_kernel(ClsParams P) {
+  constexpr int NT = NB * (NB + 1) / 2;
+  extern __shared__ double smem[];
+  const int rows = NB * 8;
+  double* sU = smem;
+  double* sV = smem + (size_t)rows * P.ldz;
+  const int s = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    const double* gU = P.U + (size_t)s * rows * P.ldz;
+    const double* gV = P.V + (size_t)s * rows * P.ldz;
+    for (int i = tid; i < rows * P.ldz; i += CLS_THREADS) {
+      sU[i] = gU[i];
+      sV[i] = gV[i];
+    }
+  }
+  __syncthreads();
+  const int c = P.cosmo_of_s[s];
+  const int l0 = P.l_begin + blockIdx.x * P.lch;
+  const int l1 = min(l0 + P.lch, P.l_end);
+  const int g = lane >> 2, tg = lane & 3;
+  for (int il = l0 + warp; il < l1; il += CLS_WARPS) {
+    const double* Trow = P.T + ((size_t)c * P.Nl + il) * P.Nz;
+    double acc[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+    for (int z0 = 0; z0 < P.nz4; z0 += 4) {
+      const int iz = z0 + tg;
+      const double t = (iz < P.Nz) ? __ldg(Trow + iz) : 0.0;
+      const double w = P.wz[iz];
+      double a[NB];
+#pragma unroll
+      for (int ib = 0; ib < NB; ++ib) {
+        const int off = (ib * 8 + g) * P.ldz + iz;
+        a[ib] = t * sU[off] + t * sV[off];  // photo_obs.py:905-919 (sqrtP*W + sqrtP_IA*W_IA)
+      }
+      int tt = 0;
+#pragma unroll
+      for (int ib = 0; ib < NB; ++ib)
+#pragma unroll
+        for (int jb = 0; jb <= ib; ++jb) {
+          dmma884(acc[tt][0], acc[tt][1], a[ib], w * a[jb]);
+          ++tt;
+        }
+    }
+    // masked write-back (both triangles); rows outside their multipole range carry no signal
+    const double L = P.ell[il];
+    double* out = P.cls + ((size_t)s * P.Nl + il) * P.Nb * P.Nb;
+    int tt = 0;
+#pragma unroll
+    for (int ib = 0; ib < NB; ++ib)
+#pragma unroll
+      for (int jb = 0; jb <= ib; ++jb) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int i = ib * 8 + g, j = jb * 8 + tg * 2 + r;
+          if (i < P.Nb && j < P.Nb && j <= i) {
+            const bool ok = (L >= P.lmin[i]) && (L <= P.lmax[i]) && (L >= P.lmin[j]) && (L <= P.lmax[j]);
+            const double v = ok ? acc[tt][r] : 0.0;
+            out[(size_t)i * P.Nb + j] = v;
+            out[(size_t)j * P.Nb + i] = v;
+          }
+        }
+        ++tt;
+      }
+  }
+}
+
+struct FishParams {
+  int S, Nl, Nb, npar, l_begin, l_end, ldb;
+  const double* cls;  // [S][Nl][Nb][Nb]
+  const double *ell, *noise, *sqrtfsky;
+  const double *stw, *stden;  // [npar][S], [npar]
+  double* Y;          // scratch [Nl-1][npar][Nb*ldb]
+  double* Fl;         // [Nl-1][npar][npar]
+};
+
+// One CTA per multipole bin (left-edge index li).
+__global__ void __launch_bounds__(256) photo_fisher_kernel(FishParams P) {
+  extern __shared__ double sm[];
+  const int Nb = P.Nb, ld = P.ldb;
+  double* sL = sm;              // [Nb][ld]  Cholesky factor (lower)
+  double* sInvD = sm + Nb * ld; // [Nb]
+  const int li = P.l_begin + blockIdx.x;
+  const int tid = threadIdx.x;
+  if (li >= P.l_end) return;
+  const double* C0 = P.cls + ((size_t)0 * P.Nl + li) * Nb * Nb;
+  for (int e = tid; e < Nb * Nb; e += blockDim.x) {
+    const int i = e / Nb, j = e % Nb;
+    sL[i * ld + j] = C0[e] + ((i == j) ? P.noise[i] : 0.0);
+  }
+  __syncthreads();
+  // right-looking Cholesky, in place (lower triangle)
+  for (int k = 0; k < Nb; ++k) {
+    if (tid == 0) {
+      const double d = sqrt(sL[k * ld + k]);
+      sL[k * ld + k] = d;
+      sInvD[k] = 1.0 / d;
+    }
+    __syncthreads();
+    for (int i = k + 1 + tid; i < Nb; i += blockDim.x) sL[i * ld + k] *= sInvD[k];
+    __syncthreads();
+    const int m = Nb - k - 1;
+    for (int e = tid; e < m * m; e += blockDim.x) {
+      const int i = k + 1 + e / m, j = k + 1 + e % m;
+      if (j <= i) sL[i * ld + j] -= sL[i * ld + k] * sL[j * ld + k];
+    }
+    __syncthreads();
+  }
+  // Y_p = L^-1 (Phi dC_p) L^-T ; stage 1: X = L^-1 M (column tasks), stage 2: Y^T = L^-1 X^T (row tasks)
+  double* Yl = P.Y + (size_t)blockIdx.x * P.npar * Nb * ld;
+  const int ntask = P.npar * Nb;
+  for (int task = tid; task < ntask; task += blockDim.x) {
+    const int p = task / Nb, col = task % Nb;
+    double* Yp = Yl + (size_t)p * Nb * ld;
+    const double den = P.stden[p];
+    for (int i = 0; i < Nb; ++i) {
+      double acc = 0.0;
+      for (int s = 0; s < P.S; ++s) {
+        const double w = P.stw[(size_t)p * P.S + s];
+        if (w != 0.0) acc += w * P.cls[(((size_t)s * P.Nl + li) * Nb + i) * Nb + col];
+      }
+      double x = (acc / den) * P.sqrtfsky[i];  // M = Phi dC
+      for (int k = 0; k < i; ++k) x -= sL[i * ld + k] * Yp[k * ld + col];
+      Yp[i * ld + col] = x * sInvD[i];
+    }
+  }
+  __syncthreads();
+  for (int task = tid; task < ntask; task += blockDim.x) {
+    const int p = task / Nb, row = task % Nb;
+    double* Yr = Yl + (size_t)p * Nb * ld + (size_t)row * ld;
+    for (int j = 0; j < Nb; ++j) {
+      double x = Yr[j];
+      for (int k = 0; k < j; ++k) x -= sL[j * ld + k] * Yr[k];
+      Yr[j] = x * sInvD[j];
+    }
+  }
+  __syncthreads();
+  // F_l[p][q] = w_l sum_ij Y_p[i][j] Y_q[j][i]; cosmicfish.py:681-683, 704, 723
+  const double lc = 0.5 * P.ell[li] + 0.5 * P.ell[li + 1];
+  const double wl = (lc + 0.5) * (P.ell[li + 1] - P.ell[li]);
+  double* Fl = P.Fl + (size_t)blockIdx.x * P.npar * P.npar;
+  const int npair = P.npar * (P.npar + 1) / 2;
+  for (int e = tid; e < npair; e += blockDim.x) {
+    int p = 0, acc = 0;
+    while (acc + p + 1 <= e) {
+      acc += p + 1;
+      ++p;
+    }
+    const int q = e - acc;
+    const double* Yp = Yl + (size_t)p * Nb * ld;
+    const double* Yq = Yl + (size_t)q * Nb * ld;
+    double s = 0.0;
+    for (int i = 0; i < Nb; ++i)
+      for (int j = 0; j < Nb; ++j) s += Yp[i * ld + j] * Yq[j * ld + i];
+    s *= wl;
+    Fl[p * P.npar + q] = s;
+    Fl[q * P.npar + p] = s;
+  }
+}
+
+__global__ void photo_reduce_kernel(const double* __restrict__ Fl, int nbins, int n, double* __restrict__ F) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double s = 0.0;
+  for (int l = 0; l < nbins; ++l) s += Fl[(size_t)l * n + e];
+  F[e] = s;
+}
+
+}  // namespace
+
+struct cfp_photo_plan {
+  cfp_ctx* ctx = nullptr;
+  const cfp_bank* bank = nullptr;
+  int S = 0, NC = 0, Nl = 0, Nz = 0, Nb = 0, npar = 0, nb = 0, ldz = 0, nz4 = 0, ldb = 0, tab_p = 0;
+  int l_begin = 0, l_end = 0;
+  double dz = 0.0, kmax = 0.0;
+  int *cosmo_of_s_d = nullptr, *kind_d = nullptr;
+  double *ell_d = nullptr, *z_d = nullptr, *chi_d = nullptr, *hub_d = nullptr, *wlpref_d = nullptr, *ngal_d = nullptr;
+  double *bias_d = nullptr, *ia_d = nullptr, *lmin_d = nullptr, *lmax_d = nullptr, *noise_d = nullptr;
+  double *sqrtfsky_d = nullptr, *stw_d = nullptr, *stden_d = nullptr, *wz_d = nullptr;
+  double *T_d = nullptr, *eff_d = nullptr, *U_d = nullptr, *V_d = nullptr, *cls_d = nullptr, *Y_d = nullptr;
+  double *Fl_d = nullptr, *fisher_d = nullptr;
+  bool ran = false;
+  std::vector<void*> owned;
+};
+
+static void photo_free(cfp_photo_plan* p) {
+  for (void* q : p->owned) cudaFree(q);
+  delete p;
+}
+
+#define PH_UP(T, src, cnt, dst)                                \
+  do {                                                         \
+    int _rc = cfp_upload<T>(ctx, src, cnt, &(dst));            \
+    if (_rc != CFP_OK) {                                       \
+      photo_free(pl);                                          \
+      return _rc;                                              \
+    }                                                          \
+    pl->owned.push_back((void*)(dst));                         \
+  } while (0)
+
+extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb,
+                                     int npar, const int32_t* cosmo_of_s_h, const double* ell_h, const double* z_h,
+                                     double dz, const double* chi_h, const double* hub_h, const double* wlpref_h,
+                                     const int32_t* kind_h, const double* ngal_h, const double* bias_h,
+                                     const double* ia_h, const double* lmin_h, const double* lmax_h,
+                                     const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
+                                     const double* stden_h, double kmax, int tab_p, cfp_photo_plan** out) {
+  CFP_REQUIRE(ctx && bank && out, "NULL ctx/bank/out");
+  CFP_REQUIRE(cosmo_of_s_h && ell_h && z_h && chi_h && hub_h && wlpref_h && kind_h && ngal_h && bias_h && ia_h &&
+                  lmin_h && lmax_h && noise_h && sqrtfsky_h && stw_h && stden_h,
+              "NULL input array");
+  CFP_REQUIRE(S >= 1 && NC >= 1 && Nl >= 2 && Nz >= 2 && Nb >= 1 && npar >= 1, "bad dimensions");
+  CFP_REQUIRE(Nb <= MAX_PNB * 8, "more than 64 tomographic rows");
+  CFP_REQUIRE(NC <= bank->n_cosmo, "NC exceeds the bank");
+  CFP_REQUIRE(tab_p >= 0 && tab_p < bank->n_tables, "bad table slot");
+  for (int s = 0; s < S; ++s) CFP_REQUIRE(cosmo_of_s_h[s] >= 0 && cosmo_of_s_h[s] < NC, "cosmology index out of range");
+  for (int c = 0; c < NC; ++c) CFP_REQUIRE(bank->desc(c, tab_p)[0] >= 8, "cosmology lacks the power spectrum table");
+  *out = nullptr;
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cfp_photo_plan* pl = new cfp_photo_plan();
+  pl->ctx = ctx, pl->bank = bank;
+  pl->S = S, pl->NC = NC, pl->Nl = Nl, pl->Nz = Nz, pl->Nb = Nb, pl->npar = npar, pl->tab_p = tab_p;
+  pl->nb = (Nb + 7) / 8;
+  pl->nz4 = (Nz + 3) / 4 * 4;
+  int ldz = pl->nz4;
+  while (!((ldz % 16) == 4 || (ldz % 16) == 12)) ldz += 4;  // conflict-free DMMA fragment loads
+  pl->ldz = ldz;
+  pl->ldb = Nb | 1;
+  pl->dz = dz, pl->kmax = kmax;
+  pl->l_begin = 0, pl->l_end = Nl - 1;
+  std::vector<double> wz(ldz, 0.0);
+  for (int i = 0; i < Nz; ++i) wz[i] = dz * ((i == 0 || i == Nz - 1) ? 0.5 : 1.0);  // photo_obs.py:921
+  PH_UP(int, cosmo_of_s_h, (size_t)S, pl->cosmo_of_s_d);
+  PH_UP(int, kind_h, (size_t)Nb, pl->kind_d);
+  PH_UP(double, ell_h, (size_t)Nl, pl->ell_d);
+  PH_UP(double, z_h, (size_t)Nz, pl->z_d);
+  PH_UP(double, chi_h, (size_t)NC * Nz, pl->chi_d);
+  PH_UP(double, hub_h, (size_t)NC * Nz, pl->hub_d);
+  PH_UP(double, wlpref_h, (size_t)NC, pl->wlpref_d);
+  PH_UP(double, ngal_h, (size_t)Nb * Nz, pl->ngal_d);
+  PH_UP(double, bias_h, (size_t)S * Nb * Nz, pl->bias_d);
+  PH_UP(double, ia_h, (size_t)S * Nz, pl->ia_d);
+  PH_UP(double, lmin_h, (size_t)Nb, pl->lmin_d);
+  PH_UP(double, lmax_h, (size_t)Nb, pl->lmax_d);
+  PH_UP(double, noise_h, (size_t)Nb, pl->noise_d);
+  PH_UP(double, sqrtfsky_h, (size_t)Nb, pl->sqrtfsky_d);
+  PH_UP(double, stw_h, (size_t)npar * S, pl->stw_d);
+  PH_UP(double, stden_h, (size_t)npar, pl->stden_d);
+  PH_UP(double, wz.data(), (size_t)ldz, pl->wz_d);
+  PH_UP(double, nullptr, (size_t)NC * Nl * Nz, pl->T_d);
+  PH_UP(double, nullptr, (size_t)NC * Nb * Nz, pl->eff_d);
+  PH_UP(double, nullptr, (size_t)S * pl->nb * 8 * ldz, pl->U_d);
+  PH_UP(double, nullptr, (size_t)S * pl->nb * 8 * ldz, pl->V_d);
+  PH_UP(double, nullptr, (size_t)S * Nl * Nb * Nb, pl->cls_d);
+  PH_UP(double, nullptr, (size_t)(Nl - 1) * npar * Nb * pl->ldb, pl->Y_d);
+  PH_UP(double, nullptr, (size_t)(Nl - 1) * npar * npar, pl->Fl_d);
+  PH_UP(double, nullptr, (size_t)npar * npar, pl->fisher_d);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    cfp_set_error("cfp_photo_plan_create: upload failed");
+    photo_free(pl);
+    return CFP_ERR_CUDA;
+  }
+  *out = pl;
+  return CFP_OK;
+}
+
+extern "C" int cfp_photo_plan_destroy(cfp_photo_plan* plan) {
+  if (!plan) return CFP_OK;
+  cudaSetDevice(plan->ctx->device);
+  cudaStreamSynchronize(plan->ctx->stream);
+  photo_free(plan);
+  return CFP_OK;
+}
+
+extern "C" int cfp_photo_plan_set_slice(cfp_photo_plan* plan, int l_begin, int l_end) {
+  CFP_REQUIRE(plan != nullptr, "plan is NULL");
+  CFP_REQUIRE(l_begin >= 0 && l_begin <= l_end && l_end <= plan->Nl - 1, "slice out of range");
+  plan->l_begin = l_begin;
+  plan->l_end = l_end;
+  return CFP_OK;
+}
+
+template <int NB>
+static cudaError_t launch_cls(const ClsParams& P, dim3 grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(photo_cls_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  photo_cls_kernel<NB><<<grid, CLS_THREADS, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+extern "C" int cfp_photo_plan_run(cfp_photo_plan* pl, void* stream) {
+  CFP_REQUIRE(pl != nullptr, "plan is NULL");
+  cfp_ctx* ctx = pl->ctx;
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  CFP_CUDA(cudaEventRecord(ctx->ev0, st));
+  {
+    const size_t tot = (size_t)pl->NC * pl->Nl * pl->Nz;
+    photo_sqrtp_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(
+        pl->bank->blob_d, pl->bank->desc_d, pl->bank->n_tables, pl->tab_p, pl->NC, pl->Nl, pl->Nz, pl->ell_d, pl->z_d,
+        pl->chi_d, pl->kmax, pl->T_d);
+    ctx->launches++;
+    CFP_CUDA(cudaGetLastError());
+  }
+  {
+    const int tot = pl->NC * pl->Nb;
+    photo_eff_kernel<<<(tot + 63) / 64, 64, 0, st>>>(pl->NC, pl->Nb, pl->Nz, pl->kind_d, pl->ngal_d, pl->chi_d, pl->dz,
+                                                      pl->eff_d);
+    ctx->launches++;
+    CFP_CUDA(cudaGetLastError());
+  }
+  {
+    const size_t tot = (size_t)pl->S * pl->nb * 8 * pl->ldz;
+    photo_window_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+        pl->S, pl->Nb, pl->Nz, pl->ldz, pl->nb * 8, pl->cosmo_of_s_d, pl->kind_d, pl->z_d, pl->chi_d, pl->hub_d,
+        pl->wlpref_d, pl->ngal_d, pl->bias_d, pl->ia_d, pl->eff_d, pl->U_d, pl->V_d);
+    ctx->launches++;
+    CFP_CUDA(cudaGetLastError());
+  }
+  // C_ell of every stencil point at every multipole of the slice (+ the right edge of the last bin is
+  // not needed: the Fisher uses left-edge values only, cosmicfish.py:704-723) -- but C_ell is part of
+  // the public result, so all multipoles [l_begin, l_end] are produced.
+  {
+    ClsParams P;
+    P.S = pl->S, P.Nl = pl->Nl, P.Nz = pl->Nz, P.Nb = pl->Nb, P.nb = pl->nb, P.ldz = pl->ldz, P.nz4 = pl->nz4;
+    P.l_begin = pl->l_begin;
+    P.l_end = std::min(pl->l_end + 1, pl->Nl);
+    const int nl = P.l_end - P.l_begin;
+    int lch = std::max(CLS_WARPS, (nl * pl->S + 2 * ctx->sm_count - 1) / (2 * ctx->sm_count));
+    lch = (lch + CLS_WARPS - 1) / CLS_WARPS * CLS_WARPS;
+    P.lch = lch;
+    P.cosmo_of_s = pl->cosmo_of_s_d, P.U = pl->U_d, P.V = pl->V_d, P.T = pl->T_d, P.wz = pl->wz_d;
+    P.ell = pl->ell_d, P.lmin = pl->lmin_d, P.lmax = pl->lmax_d, P.cls = pl->cls_d;
+    const dim3 grid((nl + lch - 1) / lch, pl->S);
+    const size_t smem = (size_t)2 * pl->nb * 8 * pl->ldz * sizeof(double);
+    cudaError_t e = cudaSuccess;
+    if (nl > 0) {
+      switch (pl->nb) {
+        case 1: e = launch_cls<1>(P, grid, smem, st); break;
+        case 2: e = launch_cls<2>(P, grid, smem, st); break;
+        case 3: e = launch_cls<3>(P, grid, smem, st); break;
+        case 4: e = launch_cls<4>(P, grid, smem, st); break;
+        case 5: e = launch_cls<5>(P, grid, smem, st); break;
+        case 6: e = launch_cls<6>(P, grid, smem, st); break;
+        case 7: e = launch_cls<7>(P, grid, smem, st); break;
+        default: e = launch_cls<8>(P, grid, smem, st); break;
+      }
+      ctx->launches++;
+    }
+    if (e != cudaSuccess) {
+      cfp_set_error("photo_cls_kernel launch: %s (smem %zu B)", cudaGetErrorString(e), smem);
+      return CFP_ERR_CUDA;
+    }
+  }
+  {
+    FishParams P;
+    P.S = pl->S, P.Nl = pl->Nl, P.Nb = pl->Nb, P.npar = pl->npar, P.l_begin = pl->l_begin, P.l_end = pl->l_end;
+    P.ldb = pl->ldb;
+    P.cls = pl->cls_d, P.ell = pl->ell_d, P.noise = pl->noise_d, P.sqrtfsky = pl->sqrtfsky_d;
+    P.stw = pl->stw_d, P.stden = pl->stden_d, P.Y = pl->Y_d, P.Fl = pl->Fl_d;
+    const int nbins = pl->l_end - pl->l_begin;
+    const size_t smem = ((size_t)pl->Nb * pl->ldb + pl->Nb) * sizeof(double);
+    if (nbins > 0) {
+      photo_fisher_kernel<<<nbins, 256, smem, st>>>(P);
+      ctx->launches++;
+      CFP_CUDA(cudaGetLastError());
+    }
+    const int n = pl->npar * pl->npar;
+    photo_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(pl->Fl_d, nbins, n, pl->fisher_d);
+    ctx->launches++;
+    CFP_CUDA(cudaGetLastError());
+  }
+  CFP_CUDA(cudaEventRecord(ctx->ev1, st));
+  pl->ran = true;
+  return CFP_OK;
+}
+
+extern "C" const double* cfp_photo_plan_fisher_d(const cfp_photo_plan* plan) { return plan ? plan->fisher_d : nullptr; }
+
+extern "C" int cfp_photo_plan_fetch(cfp_photo_plan* pl, double* fisher_h, double* cls_h, double* sqrtp_h) {
+  CFP_REQUIRE(pl != nullptr, "plan is NULL");
+  if (!pl->ran) {
+    cfp_set_error("cfp_photo_plan_fetch: plan has not been run");
+    return CFP_ERR_STATE;
+  }
+  cfp_ctx* ctx = pl->ctx;
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  CFP_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+  if (fisher_h)
+    CFP_CUDA(cudaMemcpy(fisher_h, pl->fisher_d, (size_t)pl->npar * pl->npar * sizeof(double), cudaMemcpyDeviceToHost));
+  if (cls_h)
+    CFP_CUDA(cudaMemcpy(cls_h, pl->cls_d, (size_t)pl->S * pl->Nl * pl->Nb * pl->Nb * sizeof(double), cudaMemcpyDeviceToHost));
+  if (sqrtp_h)
+    CFP_CUDA(cudaMemcpy(sqrtp_h, pl->T_d, (size_t)pl->NC * pl->Nl * pl->Nz * sizeof(double), cudaMemcpyDeviceToHost));
+  return CFP_OK;
+}

@@ -1,0 +1,699 @@
+// Spectroscopic galaxy clustering: P_obs(k,mu,z) lattice, derivatives and Fisher reduction.
+//
+// Kernels (all FP64):
+//   spectro_prepare_kernel   per (cosmology, z-bin, table): contracts the bicubic B-spline of
+//                            P_lin(z,k) / f(z,k) with the z-basis at the bin redshift and converts
+//                            the resulting 1-D cubic B-spline to piecewise-polynomial (Taylor)
+//                            form per knot interval; converts the no-wiggle samples to
+//                            (value, slope) pairs.  Output lives in HBM, is a few MB and is read
+//                            by the main kernel through L1/L2.
+//   spectro_fisher_kernel    one CTA = one z-bin x 256-cell tiles of the (mu,k) lattice.  Each
+//                            thread evaluates ln P_obs of its cell at every stencil point
+//                            (AP remap, Kaiser, FoG, dewiggling, spec-z error), accumulates the
+//                            derivative stencils into a shared-memory tile d[par][cell], and each
+//                            warp contracts its 32 cells into the Gram matrix
+//                            F_ij += w d_i d_j with FP64 tensor-core MMAs (mma.sync m8n8k4 = DMMA;
+//                            tcgen05 has no f64 kind).  Per-CTA partial sums go to HBM.
+//   spectro_reduce_kernel    fixed-order sum of the CTA partials -> F[Z][npar][npar] (deterministic).
+//
+// Reference semantics restated here: cosmicfishpie/LSSsurvey/spectro_obs.py:342-933,
+// spectro_cov.py:207-228,481-532, fishermatrix/derivatives.py:93-207, cosmicfish.py:495-542.
+#include <algorithm>
+#include <cmath>
+
+#include "cfp_common.cuh"
+
+namespace {
+
+constexpr int TILE = 256;       // cells per CTA tile (= threads per CTA)
+constexpr int LDPAD = 4;        // row padding of the derivative tile (bank-conflict free DMMA loads)
+constexpr int LD = TILE + LDPAD;
+constexpr int MAX_NB = 6;       // npar <= 48
+constexpr double INV_8PI2 = 0.012665147955292222;  // 1/(8 pi^2)
+
+struct TabInfo {  // per (cosmology, table): knot window of the k-direction
+  int64_t off_brk;  // offset of ty[3] in the bank blob: breakpoints brk[0..nint]
+  int nint;         // number of polynomial pieces = ny - 7
+  int pad;
+};
+
+struct SpectroParams {
+  int S, Z, Nmu, Nk, npar, nb, nnw, NC;
+  unsigned flags;
+  int ps_src;
+  int materialize;
+  int maxint;
+  int64_t cell_begin, cell_end;
+  const double *k, *mu, *smu, *wk, *wmu;
+  const double* scal;     // [S][Z][NSCAL]
+  const int* alias;       // [S][Z]
+  const int* st_ptr;      // CSR over stencil points: parameters fed by point s
+  const int* st_par;
+  const double* st_w;
+  const double* st_den;   // [npar]
+  const int* ps_bin;      // [npar]
+  const int* dead;        // [npar][Z]
+  const double *nbar, *vol;
+  const double* blob;     // bank blob (for breakpoints)
+  const TabInfo* tinfo;   // [NC][2]
+  const double* pp;       // [(c*Z+zb)*2+tab][maxint][4]
+  const double* pnw_k;    // [NC][nnw]
+  const double* pnwpp;    // [(c*Z+zb)][nnw][2]
+  double* partial;        // [Z][gridDim.x][T*64]
+  double *lnp, *derivs, *veff;
+};
+
+// ------------------------------------------------------------------ prepare
+struct PrepParams {
+  int NC, Z, nnw, maxint, maxncy;
+  const double* blob;
+  const int64_t* desc;  // [NC][n_tables][5]
+  int n_tables;
+  int tab[2];
+  const double* zbin;   // [Z]
+  double* dcoef;        // scratch [(c*Z+zb)*2+tab][maxncy]
+  double* pp;
+  const double *pnw_k, *pnw_p;
+  double* pnwpp;
+};
+
+__global__ void spectro_prepare_kernel(PrepParams P) {
+  const int job = blockIdx.x;  // (c*Z + zb)
+  const int c = job / P.Z, zb = job % P.Z;
+  const int tab = blockIdx.y;  // 0: P_lin, 1: f, 2: no-wiggle
+  if (tab == 2) {
+    const double* xk = P.pnw_k + (size_t)c * P.nnw;
+    const double* yp = P.pnw_p + (size_t)job * P.nnw;
+    double* o = P.pnwpp + (size_t)job * P.nnw * 2;
+    for (int l = threadIdx.x; l < P.nnw; l += blockDim.x) {
+      const double y0 = yp[l];
+      double sl = 0.0;
+      if (l + 1 < P.nnw) sl = (yp[l + 1] - y0) / (xk[l + 1] - xk[l]);
+      o[2 * l] = y0;
+      o[2 * l + 1] = sl;
+    }
+    return;
+  }
+  const int64_t* d = P.desc + ((size_t)c * P.n_tables + P.tab[tab]) * CFP_BANK_DESC;
+  const int nx = (int)d[0], ny = (int)d[1];
+  const double* tx = P.blob + d[2];
+  const double* ty = P.blob + d[3];
+  const double* cf = P.blob + d[4];
+  const int ncy = ny - 4;
+  double z = P.zbin[zb];
+  z = fmin(fmax(z, tx[3]), tx[nx - 4]);
+  const int lx = cfp_find_interval(tx, nx, z);
+  double hx[4];
+  cfp_bspl3(tx, lx, z, hx);
+  double* dc = P.dcoef + ((size_t)job * 2 + tab) * P.maxncy;
+  for (int j = threadIdx.x; j < ncy; j += blockDim.x) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += hx[i] * cf[(size_t)(lx - 3 + i) * ncy + j];
+    dc[j] = s;
+  }
+  __syncthreads();
+  // piece l (global knot index l = 3 + m): polynomial in u = k - ty[l]
+  const int nint = ny - 7;
+  double* pp = P.pp + ((size_t)job * 2 + tab) * P.maxint * 4;
+  for (int m = threadIdx.x; m < nint; m += blockDim.x) {
+    const int l = m + 3;
+    const double tl = ty[l];
+    // polynomial de Boor: h[i] are cubic polynomials in u (coefficients low -> high)
+    double h[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) h[i][q] = 0.0;
+    h[0][0] = 1.0;
+#pragma unroll
+    for (int j = 1; j <= 3; ++j) {
+      double hh[3][4];
+#pragma unroll
+      for (int i = 0; i < j; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hh[i][q] = h[i][q];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) h[0][q] = 0.0;
+#pragma unroll
+      for (int i = 0; i < j; ++i) {
+        const double tli = ty[l + i + 1], tlj = ty[l + i + 1 - j];
+        const double inv = (tli == tlj) ? 0.0 : 1.0 / (tli - tlj);
+        const double a0 = (tli - tl) * inv;  // (tli - x)/(tli-tlj) = a0 - inv*u
+        const double b0 = (tl - tlj) * inv;  // (x - tlj)/(tli-tlj) = b0 + inv*u
+        double nxt[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double lowq = (q > 0) ? hh[i][q - 1] : 0.0;
+          h[i][q] += hh[i][q] * a0 - lowq * inv;
+          nxt[q] = hh[i][q] * b0 + lowq * inv;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[i + 1][q] = nxt[q];
+      }
+    }
+    double out[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double cj = dc[l - 3 + i];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) out[q] += cj * h[i][q];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pp[(size_t)m * 4 + q] = out[q];
+  }
+}
+
+// ------------------------------------------------------------------ lattice evaluation
+struct SPoint {
+  double rqpar, rqper, dzH, bias, A1, A2, sigmap, I0, I1, I2, svr2, fs8, invs8sq, khfac, bao, pshot;
+  const double *brk_pl, *pp_pl, *brk_f, *pp_f, *brk_nw, *pp_nw;
+  int nint_pl, nint_f, nint_nw;
+  bool qbias;
+};
+
+__device__ __forceinline__ void load_spoint(const SpectroParams& P, int s, int zb, SPoint& o) {
+  const double* sc = P.scal + ((size_t)s * P.Z + zb) * CFP_SP_NSCAL;
+  const int c = (int)__ldg(sc + CFP_SP_COSMO);
+  const double qpar = __ldg(sc + CFP_SP_QPAR), qper = __ldg(sc + CFP_SP_QPER);
+  o.rqpar = 1.0 / qpar;
+  o.rqper = 1.0 / qper;
+  o.dzH = __ldg(sc + CFP_SP_DZ) * (1.0 / __ldg(sc + CFP_SP_HUBBLE));
+  o.bias = __ldg(sc + CFP_SP_BIAS);
+  o.A1 = __ldg(sc + CFP_SP_A1);
+  o.A2 = __ldg(sc + CFP_SP_A2);
+  o.qbias = (o.A1 != 0.0) || (o.A2 != 0.0);
+  o.sigmap = __ldg(sc + CFP_SP_SIGMAP);
+  o.I0 = __ldg(sc + CFP_SP_I0);
+  o.I1 = __ldg(sc + CFP_SP_I1);
+  o.I2 = __ldg(sc + CFP_SP_I2);
+  const double r = __ldg(sc + CFP_SP_SVRESCALE);
+  o.svr2 = r * r;
+  o.fs8 = __ldg(sc + CFP_SP_FS8);
+  o.invs8sq = __ldg(sc + CFP_SP_INVS8SQ);
+  o.khfac = __ldg(sc + CFP_SP_KHFAC);
+  o.pshot = __ldg(sc + CFP_SP_PSHOT);
+  o.bao = (P.flags & CFP_SPF_AP) ? 1.0 / (qper * qper * qpar) : 1.0;
+  const TabInfo ti0 = P.tinfo[c * 2 + 0], ti1 = P.tinfo[c * 2 + 1];
+  const size_t job = (size_t)c * P.Z + zb;
+  o.brk_pl = P.blob + ti0.off_brk;
+  o.nint_pl = ti0.nint;
+  o.pp_pl = P.pp + (job * 2 + 0) * P.maxint * 4;
+  o.brk_f = P.blob + ti1.off_brk;
+  o.nint_f = ti1.nint;
+  o.pp_f = P.pp + (job * 2 + 1) * P.maxint * 4;
+  o.brk_nw = P.pnw_k + (size_t)c * P.nnw;
+  o.nint_nw = P.nnw - 1;
+  o.pp_nw = P.pnwpp + job * P.nnw * 2;
+}
+
+// piece index j in [0, nint-1] with brk[j] <= x < brk[j+1] (clamped at both ends); `hint` < 0
+// means unknown.  Neighbouring stencil points / cells move by at most a piece or two.
+__device__ __forceinline__ int locate(const double* __restrict__ brk, int nint, double x, int hint) {
+  int j;
+  if (hint < 0) {
+    int lo = 0, hi = nint - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(brk + mid) <= x)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+    j = lo;
+  } else {
+    j = hint;
+    while (j < nint - 1 && x >= __ldg(brk + j + 1)) ++j;
+    while (j > 0 && x < __ldg(brk + j)) --j;
+  }
+  return j;
+}
+
+__device__ __forceinline__ double eval_pobs(const SPoint& p, unsigned flags, double k, double mu, double smu,
+                                            int& hpl, int& hf, int& hnw) {
+  // spectroscopic redshift error on the pre-AP wavenumber (spectro_obs.py:476-506, 880-889)
+  const double kerr = (flags & CFP_SPF_KH_BEFORE_ERR) ? k * p.khfac : k;
+  const double err = p.dzH * (kerr * mu * p.rqpar);
+  const double ez = exp(-0.5 * err * err);
+  const double kk = k * p.khfac;
+  double kap = kk, muap = mu;
+  if (flags & CFP_SPF_AP) {  // spectro_obs.py:441-474
+    const double kpar = kk * mu * p.rqpar;
+    const double kper = kk * smu * p.rqper;
+    kap = sqrt(kpar * kpar + kper * kper);
+    muap = kpar / kap;
+  }
+  const double mu2 = muap * muap;
+  double bterm = p.bias;
+  if (p.qbias) bterm *= (1.0 + kap * kap * p.A2) / (1.0 + kap * p.A1);
+  // tabulated P_lin(k'), f(k') (FITPACK clamps the argument to the knot range)
+  double x = fmin(fmax(kap, __ldg(p.brk_pl)), __ldg(p.brk_pl + p.nint_pl));
+  hpl = locate(p.brk_pl, p.nint_pl, x, hpl);
+  double u = x - __ldg(p.brk_pl + hpl);
+  const double* q = p.pp_pl + (size_t)hpl * 4;
+  const double pdd = (__ldg(q) + u * (__ldg(q + 1) + u * (__ldg(q + 2) + u * __ldg(q + 3)))) * p.invs8sq;
+  x = fmin(fmax(kap, __ldg(p.brk_f)), __ldg(p.brk_f + p.nint_f));
+  hf = locate(p.brk_f, p.nint_f, x, hf);
+  u = x - __ldg(p.brk_f + hf);
+  q = p.pp_f + (size_t)hf * 4;
+  const double fg = (__ldg(q) + u * (__ldg(q + 1) + u * (__ldg(q + 2) + u * __ldg(q + 3)))) * p.fs8;
+  const double kaiser = bterm + fg * mu2;  // spectro_obs.py:584-637
+  double fog = 1.0, pdw = pdd;
+  if (!(flags & CFP_SPF_LINEAR)) {
+    if (flags & CFP_SPF_FOG) {  // spectro_obs.py:639-676
+      const double t = kap * muap * p.sigmap;
+      fog = 1.0 / (1.0 + t * t);
+    }
+    // dewiggling, spectro_obs.py:699-722, 811-843; degree-1 spline with extrapolation
+    hnw = locate(p.brk_nw, p.nint_nw, kap, hnw);
+    const double pnw = (__ldg(p.pp_nw + 2 * hnw) + __ldg(p.pp_nw + 2 * hnw + 1) * (kap - __ldg(p.brk_nw + hnw))) * p.invs8sq;
+    const double sv2 = (p.I0 + 2.0 * mu2 * p.I1 + mu2 * p.I2) * p.svr2;
+    const double e = exp(-sv2 * kap * kap);
+    pdw = pdd * e + pnw * (1.0 - e);
+  }
+  return p.bao * (kaiser * kaiser) * pdw * fog * (ez * ez) + p.pshot;
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int NB>
+__global__ void __launch_bounds__(TILE) spectro_fisher_kernel(SpectroParams P) {
+  constexpr int T = NB * (NB + 1) / 2;
+  extern __shared__ double smem[];
+  double* sm_d = smem;                   // [NB*8][LD]
+  double* sm_w = smem + NB * 8 * LD;     // [TILE]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int zb = blockIdx.y;
+  const int64_t ncell = P.cell_end - P.cell_begin;
+  const int64_t ntile = (ncell + TILE - 1) / TILE;
+  const int64_t lattice = (int64_t)P.Nmu * P.Nk;
+
+  double acc[T][2];
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t][0] = acc[t][1] = 0.0;
+
+  const double nbar = P.nbar[zb], vol = P.vol[zb];
+
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int64_t cell = P.cell_begin + tile * TILE + tid;
+    const bool valid = cell < P.cell_end;
+    const int mi = valid ? (int)(cell / P.Nk) : 0;
+    const int ki = valid ? (int)(cell % P.Nk) : 0;
+    const double k = __ldg(P.k + ki), mu = __ldg(P.mu + mi), smu = __ldg(P.smu + mi);
+    for (int p = 0; p < NB * 8; ++p) sm_d[p * LD + tid] = 0.0;
+    int hpl = -1, hf = -1, hnw = -1;
+    double P0 = 1.0, lnP0 = 0.0, Psrc = 1.0;
+    for (int s = 0; s < P.S; ++s) {
+      const bool own = (s == 0) || (__ldg(P.alias + s * P.Z + zb) == s);
+      const int j0 = __ldg(P.st_ptr + s), j1 = __ldg(P.st_ptr + s + 1);
+      bool needed = (s == 0) || (s == P.ps_src) || (P.materialize & CFP_MAT_LNP);
+      for (int j = j0; j < j1 && !needed; ++j) needed = !__ldg(P.dead + __ldg(P.st_par + j) * P.Z + zb);
+      if (!needed) continue;
+      double Pobs, lnP;
+      if (own) {
+        SPoint sp;
+        load_spoint(P, s, zb, sp);
+        Pobs = eval_pobs(sp, P.flags, k, mu, smu, hpl, hf, hnw);
+        lnP = log(Pobs);
+      } else {
+        Pobs = P0;
+        lnP = lnP0;
+      }
+      if (s == 0) {
+        P0 = Pobs;
+        lnP0 = lnP;
+      }
+      if (s == P.ps_src) Psrc = Pobs;
+      if ((P.materialize & CFP_MAT_LNP) && valid) P.lnp[((size_t)s * P.Z + zb) * lattice + cell] = lnP;
+      for (int j = j0; j < j1; ++j) {
+        const int par = __ldg(P.st_par + j);
+        if (!__ldg(P.dead + par * P.Z + zb)) sm_d[par * LD + tid] += __ldg(P.st_w + j) * lnP;
+      }
+    }
+    // finish the derivatives of this cell
+    for (int par = 0; par < P.npar; ++par) {
+      const int pb = __ldg(P.ps_bin + par);
+      double d;
+      if (pb >= 0)
+        d = (pb == zb) ? 1.0 / Psrc : 0.0;  // spectro_cov.py:510-532
+      else
+        d = __ldg(P.dead + par * P.Z + zb) ? 0.0 : sm_d[par * LD + tid] / __ldg(P.st_den + par);
+      sm_d[par * LD + tid] = d;
+      if ((P.materialize & CFP_MAT_DERIVS) && valid) P.derivs[((size_t)par * P.Z + zb) * lattice + cell] = d;
+    }
+    // effective volume on the fiducial spectrum and the quadrature weight of the cell
+    const double npobs = nbar * P0;
+    const double r = npobs / (1.0 + npobs);
+    const double veff = INV_8PI2 * r * r;  // spectro_cov.py:223-225
+    if ((P.materialize & CFP_MAT_DERIVS) && valid) P.veff[(size_t)zb * lattice + cell] = veff;
+    // cosmicfish.py:541: k^2 * 2 * V_survey * veff, times the Simpson weights of :510-511
+    sm_w[tid] = valid ? (k * k * 2.0 * vol * veff) * (__ldg(P.wmu + mi) * __ldg(P.wk + ki)) : 0.0;
+    __syncwarp();
+    // Gram update on the FP64 tensor cores: this warp's 32 cells, 8 k-steps of 4 cells
+#pragma unroll 2
+    for (int ks = 0; ks < 8; ++ks) {
+      const int c = warp * 32 + ks * 4 + (lane & 3);
+      const double w = sm_w[c];
+      double a[NB];
+#pragma unroll
+      for (int ib = 0; ib < NB; ++ib) a[ib] = sm_d[(ib * 8 + (lane >> 2)) * LD + c];
+      int t = 0;
+#pragma unroll
+      for (int ib = 0; ib < NB; ++ib)
+#pragma unroll
+        for (int jb = 0; jb <= ib; ++jb) {
+          dmma884(acc[t][0], acc[t][1], a[ib], w * a[jb]);
+          ++t;
+        }
+    }
+    __syncwarp();
+  }
+  // cross-warp reduction in fixed order, then one partial per CTA
+  __syncthreads();
+  double* red = smem;  // [8 warps][T][64]
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    red[((size_t)warp * T + t) * 64 + lane * 2 + 0] = acc[t][0];
+    red[((size_t)warp * T + t) * 64 + lane * 2 + 1] = acc[t][1];
+  }
+  __syncthreads();
+  double* out = P.partial + ((size_t)zb * gridDim.x + blockIdx.x) * (T * 64);
+  for (int e = tid; e < T * 64; e += TILE) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < TILE / 32; ++w) s += red[(size_t)w * T * 64 + e];
+    out[e] = s;
+  }
+}
+
+__global__ void spectro_reduce_kernel(const double* __restrict__ partial, int ncta, int nb, int npar,
+                                      double* __restrict__ F) {
+  const int zb = blockIdx.x;
+  const int T = nb * (nb + 1) / 2;
+  for (int e = threadIdx.x; e < T * 64; e += blockDim.x) {
+    double s = 0.0;
+    for (int c = 0; c < ncta; ++c) s += partial[((size_t)zb * ncta + c) * (T * 64) + e];
+    // decode (tile, lane, r) -> (i, j)
+    const int t = e / 64, l = (e % 64) / 2, r = e % 2;
+    int ib = 0, acc = 0;
+    while (acc + ib + 1 <= t) {
+      acc += ib + 1;
+      ++ib;
+    }
+    const int jb = t - acc;
+    const int i = ib * 8 + (l >> 2), j = jb * 8 + (l & 3) * 2 + r;
+    if (i < npar && j < npar && j <= i) {
+      F[((size_t)zb * npar + i) * npar + j] = s;
+      F[((size_t)zb * npar + j) * npar + i] = s;
+    }
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ plan
+struct cfp_spectro_plan {
+  cfp_ctx* ctx = nullptr;
+  const cfp_bank* bank = nullptr;
+  int S = 0, Z = 0, Nmu = 0, Nk = 0, npar = 0, nb = 0, nnw = 0, NC = 0;
+  unsigned flags = 0;
+  int ps_src = 0, tab_pl = 0, tab_f = 0;
+  int maxint = 0, maxncy = 0, grid_x = 0;
+  int64_t cell_begin = 0, cell_end = 0;
+  double *k_d = nullptr, *mu_d = nullptr, *smu_d = nullptr, *wk_d = nullptr, *wmu_d = nullptr;
+  double *scal_d = nullptr, *pnw_k_d = nullptr, *pnw_p_d = nullptr, *nbar_d = nullptr, *vol_d = nullptr;
+  double *st_w_d = nullptr, *st_den_d = nullptr, *zbin_d = nullptr;
+  int *alias_d = nullptr, *ps_bin_d = nullptr, *st_ptr_d = nullptr, *st_par_d = nullptr, *dead_d = nullptr;
+  TabInfo* tinfo_d = nullptr;
+  double *pp_d = nullptr, *pnwpp_d = nullptr, *dcoef_d = nullptr;
+  double *partial_d = nullptr, *fisher_d = nullptr;
+  double *lnp_d = nullptr, *derivs_d = nullptr, *veff_d = nullptr;
+  bool ran = false;
+  std::vector<void*> owned;
+};
+
+static void spectro_free(cfp_spectro_plan* p) {
+  for (void* q : p->owned) cudaFree(q);
+  cudaFree(p->lnp_d);
+  cudaFree(p->derivs_d);
+  cudaFree(p->veff_d);
+  cudaFree(p->partial_d);
+  delete p;
+}
+
+#define SP_UP(T, src, cnt, dst)                                \
+  do {                                                         \
+    int _rc = cfp_upload<T>(ctx, src, cnt, &(dst));            \
+    if (_rc != CFP_OK) {                                       \
+      spectro_free(pl);                                        \
+      return _rc;                                              \
+    }                                                          \
+    pl->owned.push_back((void*)(dst));                         \
+  } while (0)
+
+extern "C" int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, int Z, int Nmu, int Nk,
+                                       int npar, const double* k_h, const double* mu_h, const double* wk_h,
+                                       const double* wmu_h, const double* scal_h, const int32_t* alias_h,
+                                       int nnw, const double* pnw_k_h, const double* pnw_p_h,
+                                       const double* stw_h, const double* stden_h, const int32_t* ps_bin_h,
+                                       int ps_src, const double* nbar_h, const double* vol_h, unsigned flags,
+                                       int tab_plin, int tab_f, cfp_spectro_plan** out) {
+  CFP_REQUIRE(ctx && bank && out, "NULL ctx/bank/out");
+  CFP_REQUIRE(k_h && mu_h && wk_h && wmu_h && scal_h && alias_h && pnw_k_h && pnw_p_h && stw_h && stden_h &&
+                  ps_bin_h && nbar_h && vol_h,
+              "NULL input array");
+  CFP_REQUIRE(S >= 1 && Z >= 1 && Nmu >= 1 && Nk >= 1 && npar >= 1 && nnw >= 2, "bad dimensions");
+  CFP_REQUIRE(npar <= MAX_NB * 8, "npar exceeds 48");
+  CFP_REQUIRE(ps_src >= 0 && ps_src < S, "ps_src out of range");
+  CFP_REQUIRE(tab_plin >= 0 && tab_plin < bank->n_tables && tab_f >= 0 && tab_f < bank->n_tables, "bad table slot");
+  *out = nullptr;
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  const int NC = bank->n_cosmo;
+  for (int s = 0; s < S; ++s)
+    for (int z = 0; z < Z; ++z) {
+      const double cd = scal_h[((size_t)s * Z + z) * CFP_SP_NSCAL + CFP_SP_COSMO];
+      CFP_REQUIRE(cd >= 0 && cd < NC && cd == std::floor(cd), "cosmology index out of range");
+      const int a = alias_h[s * Z + z];
+      CFP_REQUIRE(a == s || a == 0, "alias must be s or 0");
+    }
+  cfp_spectro_plan* pl = new cfp_spectro_plan();
+  pl->ctx = ctx;
+  pl->bank = bank;
+  pl->S = S, pl->Z = Z, pl->Nmu = Nmu, pl->Nk = Nk, pl->npar = npar, pl->nnw = nnw, pl->NC = NC;
+  pl->nb = (npar + 7) / 8;
+  pl->flags = flags;
+  pl->ps_src = ps_src;
+  pl->tab_pl = tab_plin, pl->tab_f = tab_f;
+  pl->cell_begin = 0;
+  pl->cell_end = (int64_t)Nmu * Nk;
+
+  // knot windows
+  std::vector<TabInfo> ti((size_t)NC * 2);
+  int maxint = 1, maxncy = 1;
+  for (int c = 0; c < NC; ++c)
+    for (int t = 0; t < 2; ++t) {
+      const int64_t* d = bank->desc(c, t == 0 ? tab_plin : tab_f);
+      if (d[0] < 8 || d[1] < 8) {
+        cfp_set_error("cfp_spectro_plan_create: cosmology %d lacks table slot %d", c, t == 0 ? tab_plin : tab_f);
+        spectro_free(pl);
+        return CFP_ERR_INVALID;
+      }
+      ti[c * 2 + t].off_brk = d[3] + 3;
+      ti[c * 2 + t].nint = (int)d[1] - 7;
+      ti[c * 2 + t].pad = 0;
+      maxint = std::max(maxint, (int)d[1] - 7);
+      maxncy = std::max(maxncy, (int)d[1] - 4);
+    }
+  pl->maxint = maxint;
+  pl->maxncy = maxncy;
+
+  // stencil in CSR form per stencil point; dead (parameter, bin) pairs
+  std::vector<int> st_ptr(S + 1, 0), st_par, dead((size_t)npar * Z, 0);
+  std::vector<double> st_w;
+  for (int s = 0; s < S; ++s) {
+    for (int p = 0; p < npar; ++p)
+      if (stw_h[(size_t)p * S + s] != 0.0 && ps_bin_h[p] < 0) {
+        st_par.push_back(p);
+        st_w.push_back(stw_h[(size_t)p * S + s]);
+      }
+    st_ptr[s + 1] = (int)st_par.size();
+  }
+  for (int p = 0; p < npar; ++p)
+    for (int z = 0; z < Z; ++z) {
+      if (ps_bin_h[p] >= 0) continue;
+      bool all_fid = true;
+      for (int s = 0; s < S; ++s)
+        if (stw_h[(size_t)p * S + s] != 0.0 && !(s == 0 || alias_h[s * Z + z] == 0)) all_fid = false;
+      dead[(size_t)p * Z + z] = all_fid ? 1 : 0;
+    }
+  if (st_par.empty()) {
+    st_par.push_back(0);
+    st_w.push_back(0.0);
+  }
+  std::vector<double> smu(Nmu), zbin(Z);
+  for (int i = 0; i < Nmu; ++i) smu[i] = std::sqrt(1.0 - mu_h[i] * mu_h[i]);
+  for (int z = 0; z < Z; ++z) zbin[z] = scal_h[(size_t)z * CFP_SP_NSCAL + CFP_SP_Z];
+
+  SP_UP(double, k_h, (size_t)Nk, pl->k_d);
+  SP_UP(double, mu_h, (size_t)Nmu, pl->mu_d);
+  SP_UP(double, smu.data(), (size_t)Nmu, pl->smu_d);
+  SP_UP(double, wk_h, (size_t)Nk, pl->wk_d);
+  SP_UP(double, wmu_h, (size_t)Nmu, pl->wmu_d);
+  SP_UP(double, scal_h, (size_t)S * Z * CFP_SP_NSCAL, pl->scal_d);
+  SP_UP(int, alias_h, (size_t)S * Z, pl->alias_d);
+  SP_UP(double, pnw_k_h, (size_t)NC * nnw, pl->pnw_k_d);
+  SP_UP(double, pnw_p_h, (size_t)NC * Z * nnw, pl->pnw_p_d);
+  SP_UP(double, stden_h, (size_t)npar, pl->st_den_d);
+  SP_UP(int, ps_bin_h, (size_t)npar, pl->ps_bin_d);
+  SP_UP(double, nbar_h, (size_t)Z, pl->nbar_d);
+  SP_UP(double, vol_h, (size_t)Z, pl->vol_d);
+  SP_UP(int, st_ptr.data(), st_ptr.size(), pl->st_ptr_d);
+  SP_UP(int, st_par.data(), st_par.size(), pl->st_par_d);
+  SP_UP(double, st_w.data(), st_w.size(), pl->st_w_d);
+  SP_UP(int, dead.data(), dead.size(), pl->dead_d);
+  SP_UP(double, zbin.data(), (size_t)Z, pl->zbin_d);
+  SP_UP(TabInfo, ti.data(), ti.size(), pl->tinfo_d);
+  SP_UP(double, nullptr, (size_t)NC * Z * 2 * maxint * 4, pl->pp_d);
+  SP_UP(double, nullptr, (size_t)NC * Z * nnw * 2, pl->pnwpp_d);
+  SP_UP(double, nullptr, (size_t)NC * Z * 2 * maxncy, pl->dcoef_d);
+  SP_UP(double, nullptr, (size_t)Z * npar * npar, pl->fisher_d);
+  // the uploads read caller-owned host memory asynchronously: finish them before returning
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    cfp_set_error("cfp_spectro_plan_create: upload failed");
+    spectro_free(pl);
+    return CFP_ERR_CUDA;
+  }
+  *out = pl;
+  return CFP_OK;
+}
+
+extern "C" int cfp_spectro_plan_destroy(cfp_spectro_plan* plan) {
+  if (!plan) return CFP_OK;
+  cudaSetDevice(plan->ctx->device);
+  cudaStreamSynchronize(plan->ctx->stream);
+  spectro_free(plan);
+  return CFP_OK;
+}
+
+extern "C" int cfp_spectro_plan_set_slice(cfp_spectro_plan* plan, int64_t cell_begin, int64_t cell_end) {
+  CFP_REQUIRE(plan != nullptr, "plan is NULL");
+  CFP_REQUIRE(cell_begin >= 0 && cell_begin <= cell_end && cell_end <= (int64_t)plan->Nmu * plan->Nk,
+              "slice out of range");
+  plan->cell_begin = cell_begin;
+  plan->cell_end = cell_end;
+  return CFP_OK;
+}
+
+template <int NB>
+static cudaError_t launch_fisher(const SpectroParams& P, dim3 grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(spectro_fisher_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  spectro_fisher_kernel<NB><<<grid, TILE, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void* stream) {
+  CFP_REQUIRE(pl != nullptr, "plan is NULL");
+  cfp_ctx* ctx = pl->ctx;
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const size_t lattice = (size_t)pl->Nmu * pl->Nk;
+  if ((materialize & CFP_MAT_LNP) && !pl->lnp_d)
+    CFP_CUDA(cudaMalloc((void**)&pl->lnp_d, (size_t)pl->S * pl->Z * lattice * sizeof(double)));
+  if ((materialize & CFP_MAT_DERIVS) && !pl->derivs_d) {
+    CFP_CUDA(cudaMalloc((void**)&pl->derivs_d, (size_t)pl->npar * pl->Z * lattice * sizeof(double)));
+    CFP_CUDA(cudaMalloc((void**)&pl->veff_d, (size_t)pl->Z * lattice * sizeof(double)));
+  }
+  const int64_t ncell = pl->cell_end - pl->cell_begin;
+  const int64_t ntile = std::max<int64_t>(1, (ncell + TILE - 1) / TILE);
+  const int T = pl->nb * (pl->nb + 1) / 2;
+  // persistent-style grid: ~4 CTAs per SM in total, never more CTAs than tiles
+  int gx = (int)std::min<int64_t>(ntile, std::max(1, (ctx->sm_count * 4 + pl->Z - 1) / pl->Z));
+  if (gx != pl->grid_x) {
+    cudaFree(pl->partial_d);
+    pl->partial_d = nullptr;
+    CFP_CUDA(cudaMalloc((void**)&pl->partial_d, (size_t)pl->Z * gx * T * 64 * sizeof(double)));
+    pl->grid_x = gx;
+  }
+  CFP_CUDA(cudaEventRecord(ctx->ev0, st));
+  PrepParams pp;
+  pp.NC = pl->NC, pp.Z = pl->Z, pp.nnw = pl->nnw, pp.maxint = pl->maxint, pp.maxncy = pl->maxncy;
+  pp.blob = pl->bank->blob_d, pp.desc = pl->bank->desc_d, pp.n_tables = pl->bank->n_tables;
+  pp.tab[0] = pl->tab_pl, pp.tab[1] = pl->tab_f;
+  pp.zbin = pl->zbin_d, pp.dcoef = pl->dcoef_d, pp.pp = pl->pp_d;
+  pp.pnw_k = pl->pnw_k_d, pp.pnw_p = pl->pnw_p_d, pp.pnwpp = pl->pnwpp_d;
+  spectro_prepare_kernel<<<dim3(pl->NC * pl->Z, 3), 128, 0, st>>>(pp);
+  ctx->launches++;
+  CFP_CUDA(cudaGetLastError());
+
+  SpectroParams P;
+  P.S = pl->S, P.Z = pl->Z, P.Nmu = pl->Nmu, P.Nk = pl->Nk, P.npar = pl->npar, P.nb = pl->nb, P.nnw = pl->nnw;
+  P.NC = pl->NC, P.flags = pl->flags, P.ps_src = pl->ps_src, P.materialize = materialize, P.maxint = pl->maxint;
+  P.cell_begin = pl->cell_begin, P.cell_end = pl->cell_end;
+  P.k = pl->k_d, P.mu = pl->mu_d, P.smu = pl->smu_d, P.wk = pl->wk_d, P.wmu = pl->wmu_d;
+  P.scal = pl->scal_d, P.alias = pl->alias_d, P.st_ptr = pl->st_ptr_d, P.st_par = pl->st_par_d;
+  P.st_w = pl->st_w_d, P.st_den = pl->st_den_d, P.ps_bin = pl->ps_bin_d, P.dead = pl->dead_d;
+  P.nbar = pl->nbar_d, P.vol = pl->vol_d, P.blob = pl->bank->blob_d, P.tinfo = pl->tinfo_d, P.pp = pl->pp_d;
+  P.pnw_k = pl->pnw_k_d, P.pnwpp = pl->pnwpp_d, P.partial = pl->partial_d;
+  P.lnp = pl->lnp_d, P.derivs = pl->derivs_d, P.veff = pl->veff_d;
+  const dim3 grid(gx, pl->Z);
+  const size_t smem = std::max((size_t)(pl->nb * 8 * LD + TILE), (size_t)(TILE / 32) * T * 64) * sizeof(double);
+  cudaError_t e = cudaSuccess;
+  switch (pl->nb) {
+    case 1: e = launch_fisher<1>(P, grid, smem, st); break;
+    case 2: e = launch_fisher<2>(P, grid, smem, st); break;
+    case 3: e = launch_fisher<3>(P, grid, smem, st); break;
+    case 4: e = launch_fisher<4>(P, grid, smem, st); break;
+    case 5: e = launch_fisher<5>(P, grid, smem, st); break;
+    default: e = launch_fisher<6>(P, grid, smem, st); break;
+  }
+  ctx->launches++;
+  if (e != cudaSuccess) {
+    cfp_set_error("spectro_fisher_kernel launch: %s", cudaGetErrorString(e));
+    return CFP_ERR_CUDA;
+  }
+  spectro_reduce_kernel<<<pl->Z, 256, 0, st>>>(pl->partial_d, gx, pl->nb, pl->npar, pl->fisher_d);
+  ctx->launches++;
+  CFP_CUDA(cudaGetLastError());
+  CFP_CUDA(cudaEventRecord(ctx->ev1, st));
+  pl->ran = true;
+  return CFP_OK;
+}
+
+extern "C" const double* cfp_spectro_plan_fisher_d(const cfp_spectro_plan* plan) {
+  return plan ? plan->fisher_d : nullptr;
+}
+
+extern "C" int cfp_spectro_plan_fetch(cfp_spectro_plan* pl, double* fisher_h, double* lnp_h, double* derivs_h,
+                                      double* veff_h) {
+  CFP_REQUIRE(pl != nullptr, "plan is NULL");
+  if (!pl->ran) {
+    cfp_set_error("cfp_spectro_plan_fetch: plan has not been run");
+    return CFP_ERR_STATE;
+  }
+  cfp_ctx* ctx = pl->ctx;
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  CFP_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+  const size_t lattice = (size_t)pl->Nmu * pl->Nk;
+  if (fisher_h)
+    CFP_CUDA(cudaMemcpy(fisher_h, pl->fisher_d, (size_t)pl->Z * pl->npar * pl->npar * sizeof(double), cudaMemcpyDeviceToHost));
+  if (lnp_h) {
+    CFP_REQUIRE(pl->lnp_d != nullptr, "lnP was not materialised by the last run");
+    CFP_CUDA(cudaMemcpy(lnp_h, pl->lnp_d, (size_t)pl->S * pl->Z * lattice * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (derivs_h) {
+    CFP_REQUIRE(pl->derivs_d != nullptr, "derivatives were not materialised by the last run");
+    CFP_CUDA(cudaMemcpy(derivs_h, pl->derivs_d, (size_t)pl->npar * pl->Z * lattice * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (veff_h) {
+    CFP_REQUIRE(pl->veff_d != nullptr, "veff was not materialised by the last run");
+    CFP_CUDA(cudaMemcpy(veff_h, pl->veff_d, (size_t)pl->Z * lattice * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return CFP_OK;
+}

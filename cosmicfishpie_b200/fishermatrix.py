@@ -1,0 +1,281 @@
+"""`FisherMatrix(...).compute()` -- the public entry point, same signature as the reference
+(cosmicfishpie/fishermatrix/cosmicfish.py:43-364) for the observables GCsp, WL, GCph and WL+GCph.
+
+The class keeps the attributes other code reads off a reference instance:
+  photo   : photo_obs_fid, photo_LSS, photo_derivs
+  spectro : pk_obs_fid, pk_cov, pk_deriv, derivs_dict, veff_arr, zmids, obs_spectrum,
+            Pk_kgrid/Pk_mugrid/Pk_kmesh/Pk_mumesh/Pk_ksamp/Pk_musamp, kmin_fish/kmax_fish
+  both    : settings, specs, observables, freeparams, allparams, fiducialcosmopars, fiducialcosmo, ...
+`derivs_dict` and `veff_arr` (hundreds of MB on fine lattices) are materialised lazily: compute() runs the
+fused kernel, which never writes the per-parameter lattices to HBM; touching either attribute re-runs the
+kernel in materialising mode.
+
+Extra options understood here (all optional, defaults reproduce the reference):
+  options["stencil"]   "3PT" (default) | "5PT" | "4PT_FWD"  -- the reference ignores
+                       settings["derivatives"] and always uses 3PT, so a separate key is used
+  options["device"]    CUDA device index (default LOCAL_RANK or 0)
+"""
+from __future__ import annotations
+
+import copy
+import json
+import os
+import subprocess
+import sys
+from time import time
+
+import numpy as np
+
+from . import _lib
+from . import config as config_module
+from . import fisher_matrix as fm
+from . import spectro as spectro_mod
+
+VERSION = "1.3.0"  # the reference release whose results this package reproduces
+
+
+class FisherMatrix:
+    cf_version = f"CosmicFish_v{VERSION}"
+
+    def __init__(self, options=dict(), specifications=dict(), observables=None, freepars=None, extfiles=None,
+                 fiducialpars=None, photobiaspars=None, photopars=None, spectrononlinearpars=None,
+                 spectrobiaspars=None, IApars=None, IMbiaspars=None, PShotpars=None, surveyName="Euclid",
+                 cosmoModel="w0waCDM", latexnames=None, parallel=False, parallel_cpus=4):
+        if options["feedback"] > 0:  # KeyError without "feedback", like the reference (cosmicfish.py:130)
+            print("**** cosmicfishpie_b200: B200-native observable -> Fisher hot path ****")
+            sys.stdout.flush()
+        cfg = config_module.Config(
+            options=options, specifications=specifications, observables=observables, freepars=freepars,
+            extfiles=extfiles, fiducialpars=fiducialpars, photobiaspars=photobiaspars, photopars=photopars,
+            IApars=IApars, spectrononlinearpars=spectrononlinearpars, spectrobiaspars=spectrobiaspars,
+            IMbiaspars=IMbiaspars, PShotpars=PShotpars, surveyName=surveyName, cosmoModel=cosmoModel,
+            latexnames=latexnames)
+        self.config = cfg
+        self.settings = copy.deepcopy(cfg.settings)
+        self.specs = copy.deepcopy(cfg.specs)
+        self.fiducialcosmopars = copy.deepcopy(cfg.fiducialparams)
+        self.fiducialparams = self.fiducialcosmopars
+        self.fiducialcosmo = cfg.fiducialcosmo
+        self.photopars = copy.deepcopy(cfg.photoparams)
+        self.photobiaspars = copy.deepcopy(cfg.Photobiasparams)
+        self.IApars = copy.deepcopy(cfg.IAparams)
+        self.Spectrobiaspars = copy.deepcopy(cfg.Spectrobiasparams)
+        self.Spectrobiasparams = self.Spectrobiaspars
+        self.Spectrononlinpars = copy.deepcopy(cfg.Spectrononlinearparams)
+        self.Spectrononlinearparams = self.Spectrononlinpars
+        self.IMbiaspars = copy.deepcopy(cfg.IMbiasparams)
+        self.IMbiasparams = self.IMbiaspars
+        self.PShotpars = copy.deepcopy(cfg.PShotparams)
+        self.PShotparams = self.PShotpars
+        self.observables = copy.deepcopy(cfg.obs)
+        self.obs = self.observables
+        self.input_type = cfg.input_type
+        self.external = cfg.external
+        self.freeparams = copy.deepcopy(cfg.freeparams)
+        self.latex_names = cfg.latex_names
+        allpars = {}
+        for d in (self.fiducialcosmopars, self.photobiaspars, self.photopars, self.IApars, self.Spectrobiaspars,
+                  self.Spectrononlinpars, self.IMbiaspars, self.PShotpars):
+            allpars.update(d)
+        self.allparams = allpars
+        self.allparams_fidus = dict(allpars)
+        self.parallel = parallel  # the reference only starts/stops a Ray session here; nothing to do
+        self.feed_lvl = self.settings["feedback"]
+        self.stencil = self.settings.get("stencil", "3PT")
+        self._ctx = None  # created on first use so that configuration / host prep work without a GPU
+        self._spectro_job = None
+        self._lazy = {}
+        self.timings = {}
+
+    @property
+    def ctx(self) -> _lib.Context:
+        if self._ctx is None:
+            self._ctx = _lib.default_context(self.settings.get("device"))
+        return self._ctx
+
+    # ------------------------------------------------------------------------------------------
+    def compute(self, max_z_bins=None):
+        """Compute the Fisher matrix of the configured observables; returns a `fisher_matrix` object
+        (re-read from the exported text file, like the reference) or None when `outroot` is empty."""
+        t0 = time()
+        if "GCph" in self.observables or "WL" in self.observables:
+            finalFisher = self._compute_photo()
+        elif "GCsp" in self.observables:
+            finalFisher = self._compute_spectro(max_z_bins)
+        else:
+            raise AttributeError("Observables list not defined properly")
+        t1 = time()
+        self.timings["compute_s"] = t1 - t0
+        self.fisher_array = finalFisher
+        return self.export_fisher(finalFisher, totaltime=t1 - t0)
+
+    # --- spectro ------------------------------------------------------------------------------
+    def set_pk_settings(self):
+        """k, mu lattice in 1/Mpc (cosmicfish.py:366-381)."""
+        h = self.fiducialcosmopars["h"]
+        self.kmin_fish = self.specs["kmin_GCsp"] * h
+        self.kmax_fish = self.specs["kmax_GCsp"] * h
+        self.Pk_ksamp = self.settings["spectro_Pk_k_samples"]
+        self.Pk_musamp = self.settings["spectro_Pk_mu_samples"]
+        self.Pk_kgrid = np.linspace(self.kmin_fish, self.kmax_fish, self.Pk_ksamp)
+        self.Pk_mugrid = np.linspace(0.0, 1.0, self.Pk_musamp)
+        self.Pk_kmesh, self.Pk_mumesh = np.meshgrid(self.Pk_kgrid, self.Pk_mugrid)
+
+    def eliminate_zbinned_freepars(self, nmax):
+        """Drop `name_<bin>` parameters of bins beyond nmax (cosmicfish.py:813-839)."""
+        for key in list(self.freeparams):
+            if "_" in key:
+                try:
+                    ibin = int(key.split("_")[1])
+                except ValueError:
+                    continue
+                if ibin > nmax:
+                    self.freeparams.pop(key)
+
+    def _compute_spectro(self, max_z_bins=None):
+        t0 = time()
+        self.set_pk_settings()
+        self.obs_spectrum = ["g", "g"]
+        self.pk_obs_fid = spectro_mod.ComputeGalSpectro(
+            cosmopars=self.fiducialcosmopars, fiducial_cosmopars=self.fiducialcosmopars,
+            spectrobiaspars=self.Spectrobiaspars, spectrononlinearpars=self.Spectrononlinpars,
+            IMbiaspars=self.IMbiaspars, PShotpars=self.PShotpars, configuration=self)
+        self.pk_cov = spectro_mod.SpectroCov(self.fiducialcosmopars, fiducial_specobs=self.pk_obs_fid,
+                                             bias_samples=self.obs_spectrum, configuration=self)
+        self.zmids = self.pk_cov.inter_z_bin_mids
+        if max_z_bins is not None and isinstance(max_z_bins, int):
+            self.eliminate_zbinned_freepars(max_z_bins)
+            self.zmids = self.zmids[0:max_z_bins]
+        self.fish_z_arr = np.array(self.zmids)
+        self.pk_deriv = spectro_mod.SpectroDerivs(
+            self.fish_z_arr, self.Pk_kmesh, self.Pk_mumesh, fiducial_spectro_obj=self.pk_obs_fid,
+            bias_samples=self.obs_spectrum, configuration=self, stencil=self.stencil)
+        job = self.pk_deriv.build_job(self.pk_cov, freeparams=self.freeparams)
+        self._spectro_job = job
+        t1 = time()
+        plan = job.run(materialize=0)
+        Fz, _, _, _ = plan.fetch()
+        t2 = time()
+        self.timings.update(host_prep_s=t1 - t0, device_s=t2 - t1, kernel_ms=self.ctx.last_run_ms)
+        self.allparams = self.pk_deriv.fiducial_allpars
+        self.parslist = list(self.freeparams.keys())
+        self.pk_fisher_per_bin = Fz
+        self._lazy.clear()
+        return np.sum(Fz, axis=0)
+
+    def _materialise_spectro(self):
+        if "derivs" not in self._lazy:
+            if self._spectro_job is None:
+                raise AttributeError("compute() has not been run for a spectroscopic observable")
+            derivs = self.pk_deriv.compute_derivs()
+            self._lazy["derivs"] = derivs
+            self._lazy["veff"] = [self.pk_deriv.veff[i] for i in range(len(self.zmids))]
+
+    @property
+    def derivs_dict(self):
+        self._materialise_spectro()
+        return self._lazy["derivs"]
+
+    @property
+    def veff_arr(self):
+        self._materialise_spectro()
+        return self._lazy["veff"]
+
+    def pk_LSS_Fisher(self, nbins):
+        """Per-bin Fisher matrices [nbins][npar][npar] (cosmicfish.py:407-443), from the fused kernel."""
+        return np.array(self.pk_fisher_per_bin[:nbins])
+
+    def fisher_per_bin(self, ibin):
+        return np.array(self.pk_fisher_per_bin[ibin])
+
+    # --- photo --------------------------------------------------------------------------------
+    def _compute_photo(self):
+        from . import photo as photo_mod
+
+        t0 = time()
+        self.photo_obs_fid = photo_mod.ComputeCls(self.fiducialcosmopars, self.photopars, self.IApars,
+                                                  self.photobiaspars, print_info_specs=True,
+                                                  fiducial_cosmo=self.fiducialcosmo, configuration=self)
+        self.photo_LSS = photo_mod.PhotoCov(self.fiducialcosmopars, self.photopars, self.IApars, self.photobiaspars,
+                                            fiducial_Cls=self.photo_obs_fid, configuration=self,
+                                            stencil=self.stencil)
+        t1 = time()
+        F = self.photo_LSS.compute_fisher(self.freeparams)
+        t2 = time()
+        self.timings.update(host_prep_s=self.photo_LSS.timings.get("host_prep_s", t1 - t0),
+                            device_s=self.photo_LSS.timings.get("device_s", t2 - t1), kernel_ms=self.ctx.last_run_ms)
+        return F
+
+    @property
+    def photo_derivs(self):
+        return self.photo_LSS.compute_derivs()
+
+    def photo_LSS_fishermatrix_einsum(self, noisy_cls=None, covmat=None, derivs=None, lss_obj=None):
+        """Kept for API compatibility (cosmicfish.py:643-744): the Fisher of the configured job."""
+        obj = lss_obj if lss_obj is not None else self.photo_LSS
+        return obj.compute_fisher(self.freeparams)
+
+    photo_LSS_fishermatrix = photo_LSS_fishermatrix_einsum
+
+    # --- export -------------------------------------------------------------------------------
+    @staticmethod
+    def _git_version():
+        try:
+            return subprocess.check_output(["git", "rev-parse", "HEAD"], stderr=subprocess.DEVNULL).decode().strip()
+        except Exception:
+            return "unknown"
+
+    def export_fisher(self, fishmat, totaltime=None):
+        """Write <results_dir>/<cf_version>_<outroot>_<obs>_FM{.txt,.paramnames,_specs.dat,_specs.json} and
+        return the matrix re-read from the text file (cosmicfish.py:841-1002); None if outroot == ''."""
+        if self.settings["outroot"] == "":
+            return None
+        obstring = "".join(self.observables)
+        cols = list(self.freeparams)
+        os.makedirs(self.settings["results_dir"], exist_ok=True)
+        root = self.settings["results_dir"] + "/" + self.cf_version + "_" + self.settings["outroot"] + "_" + obstring + "_FM"
+        with open(root + self.settings["fishermatrix_file_extension"], "w") as f:
+            f.write("#" + " ".join(["", *cols]) + "\n")
+            for row in np.asarray(fishmat):
+                f.write("\t".join(repr(float(v)) for v in row) + "\n")
+        with open(root + ".paramnames", "w") as f:
+            f.write("#\n#\n# This file contains the parameter names for a derived Fisher matrix.\n#\n")
+            for par in cols:
+                f.write(str(par) + "    " + str(self.latex_names.get(par, str(par))) + "    "
+                        + "{:.6f}".format(self.allparams[par]) + "\n")
+        out = fm.fisher_matrix(file_name=root + ".txt")
+        git = self._git_version()
+        with open(root + "_specs.dat", "w") as f:
+            f.write("**Git version commit: %s \n" % git)
+            if totaltime is not None:
+                f.write("**Time needed for computation of Fisher matrix: {:.3f} seconds \n".format(totaltime))
+            f.write("**Observables: %s \n" % obstring)
+            for title, d in (("CosmicFish settings", self.settings), ("Fiducial parameters", self.fiducialcosmopars),
+                             ("Free parameters", self.freeparams), ("Survey specifications", self.specs)):
+                f.write("### %s ###\n" % title)
+                for key, value in sorted(d.items()):
+                    f.write("%s:%s\n" % (key, value))
+
+        def _jsonify(o):
+            if isinstance(o, dict):
+                return {str(k): _jsonify(v) for k, v in o.items() if k != "tables"}
+            if isinstance(o, (list, tuple, range)):
+                return [_jsonify(v) for v in o]
+            if isinstance(o, np.ndarray):
+                return o.tolist()
+            if isinstance(o, (np.floating, np.integer)):
+                return o.item()
+            return o
+
+        try:
+            with open(root + "_specs.json", "w") as jf:
+                json.dump({"metadata": {"cf_version": self.cf_version, "git_commit": git,
+                                        "observables": list(self.observables),
+                                        "totaltime_sec": None if totaltime is None else float(totaltime),
+                                        "backend": "cosmicfishpie_b200"},
+                           "options": _jsonify(self.settings), "specifications": _jsonify(self.specs),
+                           "fiducialpars": _jsonify(self.fiducialcosmopars), "freepars": _jsonify(self.freeparams),
+                           "allparams": _jsonify(self.allparams)}, jf, indent=2)
+        except Exception:  # best effort, like the reference
+            pass
+        return out

@@ -1,0 +1,553 @@
+"""Spectroscopic galaxy clustering (GCsp): host-side mirror of the reference's operator interface.
+
+Same class names, constructor arguments and public methods as the reference
+(cosmicfishpie/LSSsurvey/spectro_obs.py `ComputeGalSpectro`, spectro_cov.py `SpectroCov`,
+`SpectroDerivs`), but every lattice evaluation, the derivative stencil and the Fisher reduction run in
+the CUDA kernels of csrc/cfp_spectro.cu through the C ABI (include/cfp_b200.h).  The host only
+prepares O(100) scalars per (stencil point, z-bin) from 1-D splines plus the no-wiggle tables.
+
+There is no CPU implementation of the lattice math in this package.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List, Optional
+
+import numpy as np
+from scipy.integrate import trapezoid
+
+from . import _lib, stencils
+from .cosmology import CosmoSet, cosmo_functions
+from .quadrature import simpson_weights
+
+SR = np.power(180 / np.pi, 2)
+AREASKY = 4 * np.pi * SR
+
+
+def moving_average(data, periods=2):
+    return np.convolve(data, np.ones(periods) / periods, mode="valid")
+
+
+def bisection(array, value):
+    """Bin lookup with np.isclose edge rules (reference: utilities/utils.py:131-155)."""
+    array = np.asarray(array)
+    n = len(array)
+    if np.isclose(value, array[0]) or value < array[0]:
+        return 0
+    if np.isclose(value, array[-1]) or value > array[-1]:
+        return n - 2
+    lo, hi = 0, n - 1
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if np.isclose(array[mid], value):
+            return mid
+        if array[mid] < value:
+            lo = mid + 1
+        else:
+            hi = mid
+    return lo - 1
+
+
+class SpectroNuisance:
+    """z-bins, dN/dOmega/dz, bias and sigma_p/sigma_v rescale lookups (nuisance.py:232-366)."""
+
+    def __init__(self, specs, spectrobiasparams, spectrononlinearpars):
+        self.specs = specs
+        zb, inds = [], []
+        for key, val in specs["z_bins_sp"].items():
+            zb.append(val)
+            inds.append(key)
+        self.sp_zbins = np.unique(np.concatenate(zb))
+        self.sp_zbins_inds = inds
+        self.sp_zbins_mids = moving_average(self.sp_zbins)
+        self.sp_dndz = np.array([specs["dndOmegadz"][i] for i in inds])
+        self.sp_bias_model = specs["sp_bias_model"]
+        self.sp_bias_root = specs["sp_bias_root"]
+        self.sp_bias_sample = specs["sp_bias_sample"]
+        self.Spectrobiasparams = spectrobiasparams
+        self.spectrononlinearpars = spectrononlinearpars
+
+    def gcsp_zbins(self):
+        return self.sp_zbins
+
+    def gcsp_zbins_mids(self):
+        return self.sp_zbins_mids
+
+    def gcsp_dndz(self):
+        return self.sp_dndz
+
+    def gcsp_bias_at_zm(self):
+        b = np.ones(len(self.sp_zbins_mids))
+        if "linear" in self.sp_bias_model:
+            for i, zi in enumerate(self.sp_zbins_inds):
+                b[i] = self.Spectrobiasparams[self.sp_bias_root + self.sp_bias_sample + "_" + str(zi)]
+            if self.sp_bias_model == "linear_log":
+                b = np.exp(b)
+        return b
+
+    def gcsp_zvalue_to_zindex(self, z):
+        n = bisection(self.sp_zbins, z) + 1
+        return min(max(n, self.sp_zbins_inds[0]), self.sp_zbins_inds[-1])
+
+    def gcsp_bias_at_z(self, z):
+        return self.gcsp_bias_at_zm()[self.gcsp_zvalue_to_zindex(z) - 1]
+
+    def vectorized_gcsp_bias_at_z(self, z):
+        return np.vectorize(self.gcsp_bias_at_z)(z)
+
+    def qbias_coeffs(self):
+        if self.sp_bias_model == "linear_Qbias":
+            return self.Spectrobiasparams.get("A1", 0.0), self.Spectrobiasparams.get("A2", 0.0)
+        return 0.0, 0.0
+
+    def gcsp_rescale_sigmapv_at_z(self, z, sigma_key="sigmap"):
+        return self.spectrononlinearpars.get(sigma_key + "_" + str(self.gcsp_zvalue_to_zindex(z)), 1.0)
+
+    def extra_Pshot_noise(self):
+        return 0  # nuisance.py:364-366
+
+
+_K_MOMENTS = np.logspace(np.log10(0.001), np.log10(5), 1024)  # spectro_obs.py:261-263
+
+
+def _theta_moments(cosmo: cosmo_functions, z: float):
+    """(I0, I1, I2): (1/6pi^2) int P_lin f^m dk on the fixed 1024-point grid (spectro_obs.py:724-755)."""
+    cache = cosmo.__dict__.setdefault("_moment_cache", {})
+    key = float(z)
+    if key not in cache:
+        pp = cosmo.matpow(z, _K_MOMENTS).flatten()
+        f = cosmo.f_growthrate(z, _K_MOMENTS)
+        cache[key] = tuple(
+            (1 / (6 * np.pi**2)) * trapezoid(pp * (f**m).flatten(), x=_K_MOMENTS) for m in (0, 1, 2)
+        )
+    return cache[key]
+
+
+class ComputeGalSpectro:
+    """Observed galaxy power spectrum of one parameter point (reference: spectro_obs.py:20-933).
+
+    `observed_Pgg` / `lnpobs_gg` evaluate on the GPU.  Intensity-mapping members are not provided
+    (IM is out of scope)."""
+
+    def __init__(self, cosmopars, fiducial_cosmopars=None, spectrobiaspars=None, IMbiaspars=None,
+                 spectrononlinearpars=None, PShotpars=None, fiducial_cosmo=None, bias_samples=None,
+                 use_bias_funcs=False, configuration=None, cosmo_set: Optional[CosmoSet] = None):
+        if configuration is None:
+            from . import config as config_module
+
+            configuration = config_module.current()
+        self.config = configuration
+        cfg = getattr(configuration, "config", configuration)  # a FisherMatrix duck-types as a config
+        self._cfg = cfg
+        self.feed_lvl = configuration.settings["feedback"]
+        self.observables = copy.deepcopy(configuration.obs)
+        self.specs = copy.deepcopy(configuration.specs)
+        self.settings = configuration.settings
+        self.s8terms = self.settings["bfs8terms"]
+        self.tracer = self.settings["GCsp_Tracer"]
+        if self.tracer != "matter":
+            raise NotImplementedError("GCsp_Tracer='clustering' (cb tables) is not supported")
+        self.fiducial_cosmopars = copy.deepcopy(cfg.fiducialparams if fiducial_cosmopars is None else fiducial_cosmopars)
+        if self.fiducial_cosmopars != cfg.fiducialparams:
+            raise AttributeError("fiducial_cosmopars not equal to the configuration's fiducialparams")
+        self.fiducialcosmo = cfg.fiducialcosmo
+        self.cosmopars = cosmopars
+        self.cosmo_set = cosmo_set if cosmo_set is not None else _cosmo_set_of(cfg)
+        self.cosmo_index = self.cosmo_set.add(cosmopars)
+        self.cosmo = self.cosmo_set.cosmos[self.cosmo_index]
+        self.fiducial_spectrobiaspars = copy.deepcopy(cfg.Spectrobiasparams)
+        self.spectrobiaspars = self.fiducial_spectrobiaspars if spectrobiaspars is None else spectrobiaspars
+        self.fiducial_spectrononlinearpars = copy.deepcopy(cfg.Spectrononlinearparams)
+        self.spectrononlinearpars = (
+            self.fiducial_spectrononlinearpars if spectrononlinearpars is None else spectrononlinearpars
+        )
+        self.fiducial_IMbiaspars = copy.deepcopy(cfg.IMbiasparams)
+        self.IMbiaspars = self.fiducial_IMbiaspars if IMbiaspars is None else IMbiaspars
+        self.nuisance = SpectroNuisance(self.specs, self.spectrobiaspars, self.spectrononlinearpars)
+        self.extraPshot = self.nuisance.extra_Pshot_noise()
+        self.gcsp_z_bin_mids = self.nuisance.gcsp_zbins_mids()
+        self.fiducial_PShotpars = copy.deepcopy(cfg.PShotparams)
+        self.PShotpars = self.fiducial_PShotpars if PShotpars is None else PShotpars
+        self.allpars = {**self.cosmopars, **self.spectrobiaspars, **self.IMbiaspars, **self.PShotpars,
+                        **self.spectrononlinearpars}
+        self.fiducial_allpars = {**self.fiducial_cosmopars, **self.fiducial_spectrobiaspars,
+                                 **self.fiducial_IMbiaspars, **self.fiducial_PShotpars,
+                                 **self.fiducial_spectrononlinearpars}
+        self.obs_spectrum = ["g", "g"]
+        self.specs["kmax"] = self.specs["kmax_GCsp"]
+        self.specs["kmin"] = self.specs["kmin_GCsp"]
+        self.k_grid = _K_MOMENTS
+        self.linear_switch = self.settings["GCsp_linear"]
+        self.FoG_switch = self.settings["FoG_switch"]
+        self.APbool = self.settings["AP_effect"]
+        self.fix_cosmo_nl_terms = self.settings["fix_cosmo_nl_terms"]
+        prtz = self.specs.get("nonlinear_parametrization", {"default": ""}) or {}
+        self.rescale_sigmap = prtz.get("rescale_sigmap", False)
+        self.rescale_sigmav = prtz.get("rescale_sigmav", False)
+        self.dz_err = self.specs["spec_sigma_dz"]
+        self.dz_type = self.specs["spec_sigma_dz_type"]
+        self.kh_rescaling_bug = self.settings["kh_rescaling_bug"]
+        self.kh_rescaling_beforespecerr_bug = self.settings["kh_rescaling_beforespecerr_bug"]
+        self.bias_samples = bias_samples
+        self.use_bias_funcs = use_bias_funcs
+        if use_bias_funcs:
+            raise NotImplementedError("use_bias_funcs=True is not supported")
+
+    # --- cheap host scalars (same formulas as the reference) ----------------------------------
+    def qparallel(self, z):
+        return self.fiducialcosmo.Hubble(z) / self.cosmo.Hubble(z)
+
+    def qperpendicular(self, z):
+        return self.cosmo.angdist(z) / self.fiducialcosmo.angdist(z)
+
+    def BAO_term(self, z):
+        return 1 / (self.qperpendicular(z) ** 2 * self.qparallel(z)) if self.APbool else 1
+
+    def P_ThetaTheta_Moments(self, zz, moment=0):
+        c = self.fiducialcosmo if self.fix_cosmo_nl_terms else self.cosmo
+        return _theta_moments(c, zz)[moment]
+
+    def sigmapNL(self, zz):
+        if self.linear_switch:
+            return 0
+        sp = np.sqrt(self.P_ThetaTheta_Moments(zz, 2))
+        if self.rescale_sigmap:
+            sp *= self.nuisance.gcsp_rescale_sigmapv_at_z(zz, sigma_key="sigmap")
+        return sp
+
+    def flags(self) -> int:
+        f = 0
+        if self.APbool:
+            f |= _lib.SPF_AP
+        if self.FoG_switch:
+            f |= _lib.SPF_FOG
+        if self.linear_switch:
+            f |= _lib.SPF_LINEAR
+        if self.kh_rescaling_beforespecerr_bug:
+            f |= _lib.SPF_KH_BEFORE_ERR
+        return f
+
+    def scalar_block(self, z: float) -> np.ndarray:
+        """The CFP_SP_* block of this parameter point at redshift z (include/cfp_b200.h)."""
+        b = np.zeros(_lib.SP_NSCAL)
+        b[_lib.SP_Z] = z
+        b[_lib.SP_COSMO] = self.cosmo_index
+        b[_lib.SP_QPAR] = self.qparallel(z)
+        b[_lib.SP_QPER] = self.qperpendicular(z)
+        b[_lib.SP_HUBBLE] = self.cosmo.Hubble(z)
+        b[_lib.SP_DZ] = self.dz_err if self.dz_type == "constant" else self.dz_err * (1 + z)
+        b[_lib.SP_BIAS] = self.nuisance.gcsp_bias_at_z(z)
+        b[_lib.SP_A1], b[_lib.SP_A2] = self.nuisance.qbias_coeffs()
+        if not self.linear_switch:
+            m0, m1, m2 = (self.P_ThetaTheta_Moments(z, m) for m in (0, 1, 2))
+            b[_lib.SP_SIGMAP] = self.sigmapNL(z)
+            b[_lib.SP_I0], b[_lib.SP_I1], b[_lib.SP_I2] = m0, m1, m2
+        b[_lib.SP_SVRESCALE] = (
+            self.nuisance.gcsp_rescale_sigmapv_at_z(z, sigma_key="sigmav") if self.rescale_sigmav else 1.0
+        )
+        if self.s8terms:
+            s8 = float(self.cosmo.sigma8_of_z(z))
+            b[_lib.SP_FS8], b[_lib.SP_INVS8SQ] = s8, 1.0 / s8**2
+        else:
+            b[_lib.SP_FS8], b[_lib.SP_INVS8SQ] = 1.0, 1.0
+        b[_lib.SP_KHFAC] = (
+            self.cosmo.cosmopars["h"] / self.fiducialcosmo.cosmopars["h"] if self.kh_rescaling_bug else 1.0
+        )
+        b[_lib.SP_PSHOT] = self.extraPshot
+        return b
+
+    # --- lattice evaluation on the device --------------------------------------------------------
+    def observed_Pgg(self, z, k, mu, b_i=None):
+        """P_obs(z; k, mu) for a separable mesh (k, mu from np.meshgrid) or any broadcastable pair of
+        arrays; evaluated by the CUDA lattice kernel (reference: spectro_obs.py:845-911)."""
+        if b_i is not None:
+            raise NotImplementedError("b_i override is not supported")
+        return np.exp(self.lnpobs_gg(z, k, mu))
+
+    def lnpobs_gg(self, z, k, mu, b_i=None):
+        if b_i is not None:
+            raise NotImplementedError("b_i override is not supported")
+        k = np.asarray(k, dtype=float)
+        mu = np.asarray(mu, dtype=float)
+        kb, mb = np.broadcast_arrays(k, mu)
+        shape = kb.shape
+        if kb.ndim == 2 and np.all(kb == kb[0:1, :]) and np.all(mb == mb[:, 0:1]):
+            kg, mg = kb[0, :], mb[:, 0]  # meshgrid layout (Nmu, Nk)
+            out = _evaluate_lattice([self], [float(z)], kg, mg)[0, 0]
+            return out.reshape(shape)
+        flat_k, flat_m = kb.ravel(), mb.ravel()
+        out = np.empty(flat_k.size)
+        # generic point list: one lattice row per distinct mu keeps the kernel's separable layout
+        for m in np.unique(flat_m):
+            sel = flat_m == m
+            out[sel] = _evaluate_lattice([self], [float(z)], flat_k[sel], np.array([m]))[0, 0, 0]
+        return out.reshape(shape)
+
+
+def _cosmo_set_of(cfg) -> CosmoSet:
+    cs = cfg.__dict__.get("_cosmo_set")
+    if cs is None:
+        cs = CosmoSet(cfg)
+        cfg.__dict__["_cosmo_set"] = cs
+    return cs
+
+
+def _pnw_arrays(cosmo_set: CosmoSet, zs, used):
+    """No-wiggle knots/values [NC][nnw], [NC][Z][nnw]; rows of unused cosmologies are left as ones."""
+    nnw = cosmo_set.config.settings["savgol_internalsamples"]
+    NC, Z = len(cosmo_set), len(zs)
+    pk = np.ones((NC, nnw))
+    pk[:] = np.arange(1, nnw + 1)[None, :]
+    pp = np.ones((NC, Z, nnw))
+    for c in sorted(used):
+        for j, z in enumerate(zs):
+            kk, vv, _ = cosmo_set.cosmos[c].nonwiggle_table(z)
+            pk[c] = kk
+            pp[c, j] = vv
+    return pk, pp
+
+
+def _evaluate_lattice(points: List[ComputeGalSpectro], zs, kgrid, mugrid) -> np.ndarray:
+    """ln P_obs [S][Z][Nmu][Nk] of several parameter points (no derivatives)."""
+    cs = points[0].cosmo_set
+    S, Z = len(points), len(zs)
+    scal = np.array([[p.scalar_block(z) for z in zs] for p in points])
+    alias = np.tile(np.arange(S, dtype=np.int32)[:, None], (1, Z))
+    linear = points[0].linear_switch
+    used = {p.cosmo_index for p in points}
+    pk, pp = _pnw_arrays(cs, zs, set() if linear else used)
+    plan = _lib.SpectroPlan(
+        cs.ctx or _lib.default_context(), cs.bank(), k=kgrid, mu=mugrid, wk=np.zeros_like(kgrid),
+        wmu=np.zeros_like(mugrid), scal=scal, alias=alias, pnw_k=pk, pnw_p=pp, stw=np.zeros((1, S)),
+        stden=np.ones(1), ps_bin=np.array([-1], dtype=np.int32), ps_src=0, nbar=np.zeros(Z), vol=np.zeros(Z),
+        flags=points[0].flags())
+    plan.run(materialize=_lib.MAT_LNP)
+    _, lnp, _, _ = plan.fetch(lnp=True)
+    plan.close()
+    return lnp
+
+
+class SpectroCov:
+    """Survey volume, number density and effective volume (reference: spectro_cov.py:19-228)."""
+
+    def __init__(self, fiducialpars, fiducial_specobs=None, bias_samples=["g", "g"], configuration=None):
+        if configuration is None:
+            from . import config as config_module
+
+            configuration = config_module.current()
+        self.config = configuration
+        self.feed_lvl = configuration.settings["feedback"]
+        try:
+            self.fsky_spectro = configuration.specs["fsky_spectro"]
+            self.area_survey = self.fsky_spectro * AREASKY
+        except KeyError:
+            self.area_survey = configuration.specs["area_survey_spectro"]
+            self.fsky_spectro = self.area_survey / AREASKY
+        if fiducial_specobs is None:
+            fiducial_specobs = ComputeGalSpectro(fiducialpars, fiducial_cosmopars=fiducialpars,
+                                                 bias_samples=bias_samples, configuration=configuration)
+        self.pk_obs = fiducial_specobs
+        n = self.pk_obs.nuisance
+        self.dnz = n.gcsp_dndz()
+        self.z_bins = n.gcsp_zbins()
+        self.z_bin_mids = n.gcsp_zbins_mids()
+        self.dz_bins = np.diff(self.z_bins)
+        self.global_z_bin_mids = self.inter_z_bin_mids = self.z_bin_mids
+        self.global_z_bins = self.inter_z_bins = self.z_bins
+
+    def volume_bin(self, zi, zj):
+        d1 = self.pk_obs.fiducialcosmo.angdist(zi)
+        d2 = self.pk_obs.fiducialcosmo.angdist(zj)
+        return (4 * np.pi / 3) * (pow((1 + zj) * d2, 3) - pow((1 + zi) * d1, 3))
+
+    def d_volume(self, ibin):
+        return self.volume_bin(self.global_z_bins[ibin], self.global_z_bins[ibin + 1])
+
+    def volume_survey(self, ibin):
+        return self.fsky_spectro * self.d_volume(ibin)
+
+    @property
+    def volume_survey_array(self):
+        """Missing in the reference (SURVEY.md §8a-L2'): per-bin survey volumes, used by the likelihood."""
+        return np.array([self.volume_survey(i) for i in range(len(self.global_z_bin_mids))])
+
+    def n_density(self, zi):
+        w = np.where(np.isclose(self.inter_z_bin_mids, zi, rtol=1e-2))[0]
+        if len(w) == 0:
+            print(f"Warning: zi = {zi} not in global_z_bin_mids")
+            return 0
+        i = w[0]
+        return AREASKY * (self.dnz[i] * self.dz_bins[i] / self.d_volume(i))
+
+    def veff(self, zi, k, mu):
+        npobs = self.n_density(zi) * self.pk_obs.observed_Pgg(zi, k, mu)
+        cov = (1 / (8 * (np.pi**2))) * (npobs / (1 + npobs)) ** 2
+        if zi < self.inter_z_bin_mids[0] or zi > self.inter_z_bin_mids[-1]:
+            cov = np.zeros_like(cov)
+        return cov
+
+    def noisy_P_ij(self, z, k, mu, si="g", sj="g"):
+        if not (si == "g" and sj == "g"):
+            raise NotImplementedError("only the galaxy auto-spectrum is in scope")
+        return self.pk_obs.observed_Pgg(z, k, mu) + 1 / self.n_density(z)
+
+
+class SpectroJob:
+    """Everything one GCsp Fisher needs on the device: stencil points, scalar blocks, aliases,
+    no-wiggle tables, quadrature weights.  Built once per FisherMatrix.compute()."""
+
+    def __init__(self, fiducial_obs: ComputeGalSpectro, cov: SpectroCov, zmids, kgrid, mugrid, freeparams: Dict,
+                 stencil: str = "3PT"):
+        cfg = fiducial_obs._cfg
+        self.fid = fiducial_obs
+        self.cov = cov
+        self.zmids = np.asarray(zmids, dtype=float)
+        self.kgrid, self.mugrid = np.asarray(kgrid, float), np.asarray(mugrid, float)
+        self.freeparams = dict(freeparams)
+        self.parnames = list(self.freeparams)
+        self.fiducial_allpars = fiducial_obs.fiducial_allpars
+        pts, den = stencils.get(stencil)
+        cs = fiducial_obs.cosmo_set
+        fid_all = self.fiducial_allpars
+        points = [fiducial_obs]        # s = 0
+        point_pars = [dict(fid_all)]
+        npar = len(self.parnames)
+        stw_rows, stden, ps_bin = [], np.ones(npar), -np.ones(npar, dtype=np.int32)
+        last_eval, ps_src = None, None
+        for ip, par in enumerate(self.parnames):
+            row = {}
+            if "Ps" in par:  # analytic shot-noise derivative, spectro_cov.py:510-532
+                if last_eval is None:
+                    raise AttributeError("a Ps_* parameter precedes every finite-difference parameter: the reference "
+                                         "has no observable to evaluate 1/P_obs on (spectro_cov.py:526)")
+                if ps_src is not None and ps_src != last_eval:
+                    raise NotImplementedError("Ps_* parameters interleaved with finite-difference parameters")
+                ps_src = last_eval
+                ps_bin[ip] = int(par.split("_")[-1]) - 1
+                stw_rows.append(row)
+                continue
+            h = stencils.stepsize(fid_all[par], self.freeparams[par])
+            stden[ip] = den * h
+            for m, w in pts:
+                if m == 0:
+                    row[0] = row.get(0, 0.0) + w
+                    continue
+                ap = copy.deepcopy(fid_all)
+                ap[par] = ap[par] + m * h
+                points.append(self._point(ap, cfg, cs))
+                point_pars.append(ap)
+                row[len(points) - 1] = w
+                last_eval = len(points) - 1
+            stw_rows.append(row)
+        self.points, self.point_pars = points, point_pars
+        S, Z = len(points), len(self.zmids)
+        self.stw = np.zeros((npar, S))
+        for ip, row in enumerate(stw_rows):
+            for s, w in row.items():
+                self.stw[ip, s] = w
+        self.stden, self.ps_bin, self.ps_src = stden, ps_bin, (0 if ps_src is None else ps_src)
+        self.scal = np.array([[p.scalar_block(z) for z in self.zmids] for p in points])
+        # a stencil point whose block equals the fiducial's in a bin reuses the fiducial lattice there
+        same = np.all(self.scal == self.scal[0:1], axis=2)
+        self.alias = np.where(same, 0, np.arange(S)[:, None]).astype(np.int32)
+        used = {int(c) for c in self.scal[:, :, _lib.SP_COSMO].ravel()}
+        self.pnw_k, self.pnw_p = _pnw_arrays(cs, self.zmids, set() if fiducial_obs.linear_switch else used)
+        self.wk, self.wmu = simpson_weights(self.kgrid), simpson_weights(self.mugrid)
+        self.nbar = np.array([cov.n_density(z) for z in self.zmids])
+        self.vol = np.array([cov.volume_survey(i) for i in range(Z)])
+        self.flags = fiducial_obs.flags()
+        self.cosmo_set = cs
+        self._plan = None
+
+    @staticmethod
+    def _point(allpars, cfg, cs):
+        """ComputeGalSpectro of one stencil point (spectro_cov.py:456-475)."""
+        return ComputeGalSpectro(
+            cosmopars={k: allpars[k] for k in cfg.fiducialparams},
+            fiducial_cosmopars=cfg.fiducialparams,
+            spectrobiaspars={k: allpars[k] for k in cfg.Spectrobiasparams},
+            spectrononlinearpars={k: allpars[k] for k in cfg.Spectrononlinearparams},
+            PShotpars={k: allpars[k] for k in cfg.PShotparams},
+            configuration=cfg, cosmo_set=cs)
+
+    def plan(self) -> _lib.SpectroPlan:
+        if self._plan is None:
+            cs = self.cosmo_set
+            self._plan = _lib.SpectroPlan(
+                cs.ctx or _lib.default_context(), cs.bank(), k=self.kgrid, mu=self.mugrid, wk=self.wk, wmu=self.wmu,
+                scal=self.scal, alias=self.alias, pnw_k=self.pnw_k, pnw_p=self.pnw_p, stw=self.stw, stden=self.stden,
+                ps_bin=self.ps_bin, ps_src=self.ps_src, nbar=self.nbar, vol=self.vol, flags=self.flags)
+        return self._plan
+
+    def run(self, materialize=0):
+        p = self.plan()
+        p.run(materialize=materialize)
+        return p
+
+    def close(self):
+        if self._plan is not None:
+            self._plan.close()
+            self._plan = None
+
+
+class SpectroDerivs:
+    """Derivatives of ln P_obs w.r.t. every free parameter (reference: spectro_cov.py:373-601).
+
+    `compute_derivs` returns the reference's structure {par: {"z_bins": z_array, i: (Nmu, Nk)}}; the
+    lattices, the stencil and (through `fisher_per_bin`) the Fisher reduction are one fused device pass."""
+
+    def __init__(self, z_array, pk_kmesh, pk_mumesh, fiducial_spectro_obj, bias_samples=["g", "g"],
+                 configuration=None, stencil="3PT"):
+        self.observables = fiducial_spectro_obj.observables
+        self.bias_samples = bias_samples
+        self.fiducial_cosmopars = fiducial_spectro_obj.fiducial_cosmopars
+        self.fiducial_spectrobiaspars = fiducial_spectro_obj.fiducial_spectrobiaspars
+        self.fiducial_PShotpars = fiducial_spectro_obj.PShotpars
+        self.fiducial_allpars = fiducial_spectro_obj.fiducial_allpars
+        self.fiducial_spectrononlinearpars = fiducial_spectro_obj.fiducial_spectrononlinearpars
+        self.fiducial_cosmo = fiducial_spectro_obj.fiducialcosmo
+        self.fiducial_obj = fiducial_spectro_obj
+        self.z_array = np.asarray(z_array)
+        self.pk_kmesh, self.pk_mumesh = pk_kmesh, pk_mumesh
+        self.freeparams = None
+        self.stencil = stencil
+        self.config = configuration if configuration is not None else fiducial_spectro_obj.config
+        self.feed_lvl = self.config.settings["feedback"]
+        self.job: Optional[SpectroJob] = None
+        self.pobs = None
+
+    def get_obs(self, allpars):
+        """{"z_bins": z_array, i: ln P_obs lattice} at an arbitrary parameter point (spectro_cov.py:481-508)."""
+        cfg = self.fiducial_obj._cfg
+        self.pobs = SpectroJob._point(allpars, cfg, self.fiducial_obj.cosmo_set)
+        lat = _evaluate_lattice([self.pobs], list(self.z_array), self.pk_kmesh[0, :], self.pk_mumesh[:, 0])
+        out = {"z_bins": self.z_array}
+        for i in range(len(self.z_array)):
+            out[i] = lat[0, i]
+        return out
+
+    def build_job(self, cov: SpectroCov, freeparams=None) -> SpectroJob:
+        if freeparams:
+            self.freeparams = freeparams
+        self.job = SpectroJob(self.fiducial_obj, cov, self.z_array, self.pk_kmesh[0, :], self.pk_mumesh[:, 0],
+                              self.freeparams, self.stencil)
+        return self.job
+
+    def compute_derivs(self, freeparams=dict(), cov: Optional[SpectroCov] = None):
+        if freeparams != dict():
+            self.freeparams = freeparams
+        if self.job is None:
+            if cov is None:
+                cov = SpectroCov(self.fiducial_cosmopars, fiducial_specobs=self.fiducial_obj, configuration=self.config)
+            self.build_job(cov)
+        plan = self.job.run(materialize=_lib.MAT_DERIVS)
+        _, _, D, V = plan.fetch(derivs=True)
+        self.veff = V
+        derivs = {}
+        for ip, par in enumerate(self.job.parnames):
+            d = {i: D[ip, i] for i in range(len(self.z_array))}
+            if self.job.ps_bin[ip] < 0:
+                d = {"z_bins": self.z_array, **d}
+            derivs[par] = d
+        self.derivs = derivs
+        return derivs

@@ -1,0 +1,220 @@
+/*
+ * cfp_b200.h -- C ABI of the B200-native cosmicfishpie hot path (libcfp_b200.so).
+ *
+ * Conventions
+ *   - every entry point is extern "C", returns 0 on success or a negative cfp_status;
+ *     the message of the last failure on the calling thread is cfp_last_error().
+ *   - no exceptions, no torch/STL types cross the boundary; plain pointers and sizes.
+ *   - pointers suffixed _h are HOST pointers, _d are DEVICE pointers; the caller owns every
+ *     buffer it passes; objects returned through `**out` are owned by the library and are
+ *     released with the matching *_destroy/_free call.
+ *   - all floating point data is IEEE FP64, arrays are C-contiguous (row-major).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the context's own stream).
+ *   - one cfp_ctx per GPU; plans and banks belong to the context that created them.
+ *     A context is not thread-safe; use one per host thread.
+ *
+ * Each entry point cites the reference (santiagocasas/cosmicfishpie v1.3.0) interface it
+ * replaces as `file:line`, relative to the reference repository root.
+ */
+#ifndef CFP_B200_H
+#define CFP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFP_ABI_VERSION 1
+
+typedef enum {
+  CFP_OK = 0,
+  CFP_ERR_INVALID = -1, /* bad argument (NULL, size, range) */
+  CFP_ERR_CUDA = -2,    /* CUDA runtime error, see cfp_last_error() */
+  CFP_ERR_NOMEM = -3,
+  CFP_ERR_STATE = -4 /* object used before it was prepared / run */
+} cfp_status;
+
+typedef struct cfp_ctx cfp_ctx;
+typedef struct cfp_bank cfp_bank;
+typedef struct cfp_spectro_plan cfp_spectro_plan;
+typedef struct cfp_photo_plan cfp_photo_plan;
+
+/* ---------------------------------------------------------------- context ------------- */
+int cfp_abi_version(void);
+const char* cfp_last_error(void);
+int cfp_ctx_create(int device, cfp_ctx** out);
+int cfp_ctx_destroy(cfp_ctx* ctx);
+int cfp_ctx_sync(cfp_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t cfp_ctx_launch_count(const cfp_ctx* ctx);
+/* device time [ms] of the last *_run call, measured with CUDA events on the launch stream */
+double cfp_ctx_last_run_ms(const cfp_ctx* ctx);
+
+/* ---------------------------------------------------------------- table bank ----------
+ * Replaces the spline facade `cosmo_functions.matpow / f_growthrate / growth`
+ * (cosmicfishpie/cosmology/cosmology.py:1682-1738, 1859-1877, 1911-1949) built by
+ * `external_input.calculate_interpol_results` (cosmology.py:1423-1540): for every cosmology
+ * of the stencil the FITPACK bicubic (tx, ty, c) of each tabulated function of (z, k).
+ *
+ * blob_h  : all knots and coefficients, concatenated
+ * desc_h  : int64 [n_cosmo][n_tables][CFP_BANK_DESC] = {nx, ny, off_tx, off_ty, off_c}
+ *           nx, ny = number of knots in z and k (degree 3 both ways; the coefficient
+ *           matrix is (nx-4) x (ny-4), z-major); offsets are in doubles into blob_h.
+ * Table slots are the caller's convention; this package uses CFP_TAB_*.
+ */
+#define CFP_BANK_DESC 5
+#define CFP_TAB_PLIN 0
+#define CFP_TAB_PNL 1
+#define CFP_TAB_F 2
+#define CFP_TAB_D 3
+#define CFP_NTAB 4
+
+int cfp_bank_upload(cfp_ctx* ctx, const double* blob_h, size_t n_doubles, const int64_t* desc_h,
+                    int n_cosmo, int n_tables, cfp_bank** out);
+int cfp_bank_free(cfp_ctx* ctx, cfp_bank* bank);
+/* Point-wise bicubic evaluation, semantics of FITPACK bispeu / RectBivariateSpline.__call__
+ * (grid=False), including clamping of the arguments to the knot range
+ * (cosmology.py:1736-1738, 1876, 1944).  x = z, y = k, n points, out_h[n]. */
+int cfp_bank_eval(cfp_ctx* ctx, const cfp_bank* bank, int cosmo, int table, const double* z_h,
+                  const double* k_h, size_t n, double* out_h);
+
+/* ---------------------------------------------------------------- spectro (GCsp) ------
+ * One plan = one Fisher-matrix job: the observed galaxy power spectrum on the
+ * (stencil point s, z-bin b, mu, k) lattice, the finite-difference / analytic derivatives and
+ * the Fisher reduction.  Replaces, fused into two kernels:
+ *   ComputeGalSpectro.observed_Pgg / lnpobs_gg   cosmicfishpie/LSSsurvey/spectro_obs.py:845-933
+ *   SpectroCov.veff                              cosmicfishpie/LSSsurvey/spectro_cov.py:207-228
+ *   SpectroDerivs.get_obs / exact_derivs         cosmicfishpie/LSSsurvey/spectro_cov.py:481-532
+ *   derivatives.derivative_3pt (any linear stencil) cosmicfishpie/fishermatrix/derivatives.py:93-207
+ *   FisherMatrix.fish_integrand / fisher_integral / pk_LSS_Fisher
+ *                                                cosmicfishpie/fishermatrix/cosmicfish.py:407-542
+ *
+ * Per (stencil point, z-bin) scalar block, CFP_SP_NSCAL doubles (host-evaluated 1-D splines
+ * and nuisance values; see cosmicfishpie_b200/spectro.py for how each is obtained):
+ */
+enum {
+  CFP_SP_Z = 0,       /* bin-centre redshift */
+  CFP_SP_COSMO,       /* index of the cosmology in the bank (as a double) */
+  CFP_SP_QPAR,        /* H_fid(z)/H(z)                 spectro_obs.py:342-358 */
+  CFP_SP_QPER,        /* D_A(z)/D_A,fid(z)             spectro_obs.py:360-376 */
+  CFP_SP_HUBBLE,      /* H(z) of the sample cosmology  spectro_obs.py:505 */
+  CFP_SP_DZ,          /* sigma_z, or sigma_z (1+z)     spectro_obs.py:500-504 */
+  CFP_SP_BIAS,        /* b_g of the bin                nuisance.py:249-301 */
+  CFP_SP_A1,          /* Q-bias scale dependence       nuisance.py:306-325 */
+  CFP_SP_A2,
+  CFP_SP_SIGMAP,      /* sigma_p (after rescale)       spectro_obs.py:678-697 */
+  CFP_SP_I0,          /* P_theta-theta moments         spectro_obs.py:699-755 */
+  CFP_SP_I1,
+  CFP_SP_I2,
+  CFP_SP_SVRESCALE,   /* sigma_v rescale factor        nuisance.py:346-350 */
+  CFP_SP_FS8,         /* multiplies f(z,k): sigma8(z) if bfs8terms else 1   spectro_obs.py:624-627 */
+  CFP_SP_INVS8SQ,     /* 1/sigma8(z)^2 if bfs8terms else 1                  spectro_obs.py:773-777 */
+  CFP_SP_KHFAC,       /* h/h_fid if kh_rescaling_bug else 1                 spectro_obs.py:419-425 */
+  CFP_SP_PSHOT,       /* extra shot noise added to P_obs (0 in the reference, nuisance.py:364-366) */
+  CFP_SP_NSCAL
+};
+/* flags (bit mask) */
+#define CFP_SPF_AP 1u              /* Alcock-Paczynski remap on      (settings AP_effect) */
+#define CFP_SPF_FOG 2u             /* Lorentzian FoG on              (settings FoG_switch) */
+#define CFP_SPF_LINEAR 4u          /* GCsp_linear: no FoG, no dewiggling */
+#define CFP_SPF_KH_BEFORE_ERR 8u   /* kh_rescaling_beforespecerr_bug */
+
+/* Create a plan and upload the job description.
+ *   S, Z, Nmu, Nk, npar : stencil points, z-bins, lattice, free parameters
+ *   k_h[Nk], mu_h[Nmu]  : FisherMatrix.set_pk_settings grids (cosmicfish.py:366-381), 1/Mpc
+ *   wk_h[Nk], wmu_h[Nmu]: quadrature weights reproducing scipy.integrate.simpson on those grids
+ *   scal_h[S][Z][CFP_SP_NSCAL]
+ *   alias_h[S][Z]       : s if the point must be evaluated in this bin, 0 if its (cosmology,
+ *                         scalars) are identical to the fiducial point 0 there (e.g. a bias step
+ *                         of another bin): the fiducial lattice is reused, not recomputed
+ *   nnw, pnw_k_h[n_cosmo][nnw], pnw_p_h[n_cosmo][Z][nnw]: no-wiggle spectrum samples, the knots
+ *                         and values of the degree-1 spline of cosmology.py:1804-1812
+ *   stw_h[npar][S], stden_h[npar] : derivative stencil, d_p = (sum_s stw[p][s] lnP_s) / stden[p]
+ *                         (3PT: weights +1/-1 on theta+-h, denominator 2h  derivatives.py:93-111;
+ *                         any linear stencil -- 5PT, 4PT_FWD derivatives.py:209-225 -- fits).
+ *                         A parameter whose stencil points all alias to the fiducial in a bin has
+ *                         an exactly zero derivative there, as in the reference.
+ *   ps_bin_h[npar]      : -1 for finite-difference parameters; for an analytic shot-noise
+ *                         parameter Ps_i the z-bin index i-1: d_p = delta(b, i-1) / P_obs(ps_src)
+ *   ps_src              : stencil point whose P_obs enters the analytic derivative (the reference
+ *                         uses the LAST evaluated point, spectro_cov.py:465,526)
+ *   nbar_h[Z], vol_h[Z] : fiducial number density and survey volume per bin (spectro_cov.py:169-205)
+ *   tab_plin, tab_f     : bank table slots of P_lin(z,k) and f(z,k)
+ */
+int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, int Z, int Nmu, int Nk,
+                            int npar, const double* k_h, const double* mu_h, const double* wk_h,
+                            const double* wmu_h, const double* scal_h, const int32_t* alias_h,
+                            int nnw, const double* pnw_k_h, const double* pnw_p_h,
+                            const double* stw_h, const double* stden_h, const int32_t* ps_bin_h,
+                            int ps_src, const double* nbar_h, const double* vol_h, unsigned flags,
+                            int tab_plin, int tab_f, cfp_spectro_plan** out);
+int cfp_spectro_plan_destroy(cfp_spectro_plan* plan);
+/* Restrict the plan to a slice of the flattened (mu,k) lattice [cell_begin, cell_end) of every
+ * bin: the multi-GPU partition (each rank owns a slice; partial Fishers are summed). */
+int cfp_spectro_plan_set_slice(cfp_spectro_plan* plan, int64_t cell_begin, int64_t cell_end);
+/* Launch: table preparation (z-contraction + piecewise-polynomial form) and the fused
+ * lattice / derivative / Fisher kernel.  materialize: bit 0 = keep lnP[S][Z][Nmu][Nk],
+ * bit 1 = keep derivs[npar][Z][Nmu][Nk] and veff[Z][Nmu][Nk] (the API-preserving mode). */
+#define CFP_MAT_LNP 1
+#define CFP_MAT_DERIVS 2
+int cfp_spectro_plan_run(cfp_spectro_plan* plan, int materialize, void* stream);
+/* Device pointer of the result F[Z][npar][npar] (valid until the plan is destroyed). */
+const double* cfp_spectro_plan_fisher_d(const cfp_spectro_plan* plan);
+/* Copy results to the host (synchronises). Any pointer may be NULL. */
+int cfp_spectro_plan_fetch(cfp_spectro_plan* plan, double* fisher_h, double* lnp_h,
+                           double* derivs_h, double* veff_h);
+
+/* ---------------------------------------------------------------- photo (WL/GCph/3x2pt)
+ * One plan = one photometric Fisher job.  Replaces:
+ *   ComputeCls.sqrtP_limber                      cosmicfishpie/LSSsurvey/photo_obs.py:457-512
+ *   much_faster_integral_efficiency              cosmicfishpie/LSSsurvey/photo_obs.py:113-160
+ *   ComputeCls.lensing_kernel / galaxy_kernel / genwindow   photo_obs.py:514-722
+ *   ComputeCls.clsintegral / computecls_vectorized          photo_obs.py:798-928
+ *   PhotoCov.getclsnoise / get_covmat            cosmicfishpie/LSSsurvey/photo_cov.py:164-245
+ *   derivatives.derivative_3pt                   cosmicfishpie/fishermatrix/derivatives.py:93-207
+ *   FisherMatrix.photo_LSS_fishermatrix_einsum   cosmicfishpie/fishermatrix/cosmicfish.py:643-744
+ *
+ * Tomographic rows are ordered as the reference orders its covariance columns: all bins of
+ * observable 0, then all bins of observable 1 (cosmicfish.py:686-691).  kind[a] = 0 for a
+ * lensing (WL) row, 1 for a clustering (GCph) row.
+ *
+ *   S, NC, Nl, Nz, Nb, npar
+ *   cosmo_of_s_h[S]      : cosmology index of each stencil point
+ *   ell_h[Nl], z_h[Nz]   : photo_obs.py:309-316 grids;  dz = mean spacing (photo_obs.py:316)
+ *   chi_h[NC][Nz], hub_h[NC][Nz] : comoving distance and H(z) on the z grid (host 1-D splines)
+ *   wlpref_h[NC]         : 1.5 H0^2 Omega_m                        photo_obs.py:584
+ *   kind_h[Nb]           : 0 = WL row, 1 = GCph row
+ *   ngal_h[Nb][Nz]       : normalised n_i(z) of each row's bin       photo_window.py:220-242
+ *   bias_h[S][Nb][Nz]    : galaxy bias b(z) per stencil point (rows of kind 0: ignored)
+ *   ia_h[S][Nz]          : intrinsic-alignment window IA(z) per stencil point  nuisance.py:155-191
+ *   lmin_h[Nb], lmax_h[Nb] : multipole range of each row's observable  photo_obs.py:899-900
+ *   noise_h[Nb]          : shape / shot noise added on the diagonal    photo_cov.py:111-114
+ *   sqrtfsky_h[Nb]       : sqrt(f_sky) of each row's observable        photo_cov.py:228
+ *   stw_h[npar][S], stden_h[npar] : derivative stencil (as for the spectro plan)
+ *   kmax                 : Limber k cut (strict <)                     photo_obs.py:482
+ *   tab_p                : bank slot of the matter power spectrum used (P_nl or P_lin)
+ */
+int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz,
+                          int Nb, int npar, const int32_t* cosmo_of_s_h, const double* ell_h,
+                          const double* z_h, double dz, const double* chi_h, const double* hub_h,
+                          const double* wlpref_h, const int32_t* kind_h, const double* ngal_h,
+                          const double* bias_h, const double* ia_h, const double* lmin_h,
+                          const double* lmax_h, const double* noise_h, const double* sqrtfsky_h,
+                          const double* stw_h, const double* stden_h, double kmax, int tab_p,
+                          cfp_photo_plan** out);
+int cfp_photo_plan_destroy(cfp_photo_plan* plan);
+/* multi-GPU partition: this rank owns multipoles [l_begin, l_end) */
+int cfp_photo_plan_set_slice(cfp_photo_plan* plan, int l_begin, int l_end);
+/* Launch K3 (Limber kernels), K4 (FP64 tensor-core C_ell contraction) and K5 (Cholesky + trace
+ * Fisher).  C_ell of all stencil points is always kept: cls[S][Nl][Nb][Nb]. */
+int cfp_photo_plan_run(cfp_photo_plan* plan, void* stream);
+const double* cfp_photo_plan_fisher_d(const cfp_photo_plan* plan);
+/* fisher_h[npar][npar], cls_h[S][Nl][Nb][Nb] (signal only, no noise), sqrtp_h[NC][Nl][Nz] */
+int cfp_photo_plan_fetch(cfp_photo_plan* plan, double* fisher_h, double* cls_h, double* sqrtp_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFP_B200_H */
