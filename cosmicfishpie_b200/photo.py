@@ -1,0 +1,456 @@
+"""Photometric probes (WL, GCph, 3x2pt): host-side mirror of the reference's operator interface.
+
+Same class names and public methods as the reference (cosmicfishpie/LSSsurvey/photo_window.py
+`GalaxyPhotoDist`, photo_obs.py `ComputeCls`, photo_cov.py `PhotoCov`).  The Limber power-spectrum table,
+lensing efficiencies, tomographic kernels, the C_ell contraction, the covariance Cholesky and the Fisher
+trace run in the CUDA kernels of csrc/cfp_photo.cu; the host prepares cosmology-independent windows
+(n_i(z), erf photo-z convolution), 1-D background splines on the z grid, and the O(50)-point IA window.
+
+There is no CPU implementation of the C_ell / Fisher math in this package.
+"""
+from __future__ import annotations
+
+import copy
+import os
+from time import time
+from typing import Dict, List, Optional
+
+import numpy as np
+from scipy.integrate import trapezoid
+from scipy.interpolate import InterpolatedUnivariateSpline, interp1d
+from scipy.special import erf
+
+from . import _lib, stencils
+from .cosmology import CosmoSet
+
+_WINDOW_CACHE: Dict[tuple, "GalaxyPhotoDist"] = {}
+
+
+def _cfg_of(configuration):
+    if configuration is None:
+        from . import config as config_module
+
+        configuration = config_module.current()
+    return configuration, getattr(configuration, "config", configuration)
+
+
+class GalaxyPhotoDist:
+    """n(z) and photo-z convolved, normalised bin distributions (reference: photo_window.py:15-242).
+
+    Vectorised over z.  The only operation numpy evaluates differently for scalars and arrays is `pow`
+    (libm vs SIMD); the reference calls point by point, so `dNdz` takes its power per element and the
+    windows agree with the reference bit for bit."""
+
+    def __init__(self, photopars, configuration=None):
+        configuration, _ = _cfg_of(configuration)
+        sp = configuration.specs
+        self.z_bins_WL = sp["z_bins_WL"]
+        self.n_bins_WL = len(self.z_bins_WL)
+        self.z_bins_GCph = sp["z_bins_GCph"]
+        self.n_bins_GCph = len(self.z_bins_GCph)
+        self.z0, self.z0_p, self.ngamma = sp["z0"], sp["z0_p"], sp["ngamma"]
+        self.photo = photopars
+        self.z_min = np.min([sp["z_bins_GCph"][0], sp["z_bins_WL"][0]])
+        self.z_max = np.max([sp["z_bins_GCph"][-1], sp["z_bins_WL"][-1]])
+        self.normalization = {"GCph": self.norm("GCph"), "WL": self.norm("WL")}
+
+    def dNdz(self, z):
+        z = np.asarray(z, dtype=float)
+        expo = z / self.z0
+        powv = np.array([e**self.ngamma for e in expo.ravel()]).reshape(expo.shape)
+        return (z / self.z0_p) ** 2 * np.exp(-powv)
+
+    def ngal_photoz(self, z, i, obs):
+        if obs == "GCph":
+            zb = self.z_bins_GCph
+        elif obs == "WL":
+            zb = self.z_bins_WL
+        else:
+            raise ValueError("obs must be either 'GCph' or 'WL'")
+        z = np.asarray(z, dtype=float)
+        p = self.photo
+        r = np.sqrt(1 / 2)
+        t1 = p["cb"] * p["fout"] * erf((r * (z - p["zo"] - p["co"] * zb[i - 1])) / (p["sigma_o"] * (1 + z)))
+        t2 = -p["cb"] * p["fout"] * erf((r * (z - p["zo"] - p["co"] * zb[i])) / (p["sigma_o"] * (1 + z)))
+        t3 = p["co"] * (1 - p["fout"]) * erf((r * (z - p["zb"] - p["cb"] * zb[i - 1])) / (p["sigma_b"] * (1 + z)))
+        t4 = -p["co"] * (1 - p["fout"]) * erf((r * (z - p["zb"] - p["cb"] * zb[i])) / (p["sigma_b"] * (1 + z)))
+        return self.dNdz(z) * (t1 + t2 + t3 + t4) / (2 * p["co"] * p["cb"])
+
+    def norm(self, obs):
+        zb = self.z_bins_GCph if obs == "GCph" else self.z_bins_WL
+        zint = np.linspace(0.0, self.z_max, 1000)
+        dz = self.z_max / 1000  # (sic) photo_window.py:210
+        out = [trapezoid(self.ngal_photoz(zint, i, obs), dx=dz) for i in range(1, len(zb))]
+        out.insert(0, None)
+        return out
+
+    def norm_ngal_photoz(self, z, i, obs):
+        return self.ngal_photoz(z, i, obs) / self.normalization[obs][i]
+
+
+def galaxy_photo_dist(photopars, configuration) -> GalaxyPhotoDist:
+    """Windows depend only on (bin edges, n(z) shape, photo-z parameters): computed once and cached."""
+    sp = configuration.specs
+    key = (tuple(sp["z_bins_WL"]), tuple(sp["z_bins_GCph"]), float(sp["z0"]), float(sp["ngamma"]),
+           tuple(sorted(photopars.items())))
+    if key not in _WINDOW_CACHE:
+        _WINDOW_CACHE[key] = GalaxyPhotoDist(photopars, configuration)
+    return _WINDOW_CACHE[key]
+
+
+_LUM_CACHE = {}
+
+
+def _lumratio_table(extdir):
+    if extdir not in _LUM_CACHE:
+        txt = os.path.join(extdir or "", "lumratio_file.dat")
+        if extdir and os.path.isfile(txt):
+            _LUM_CACHE[extdir] = np.loadtxt(txt)
+        else:
+            _LUM_CACHE[extdir] = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "lumratio.npy"))
+    return _LUM_CACHE[extdir]
+
+
+class PhotoNuisance:
+    """Galaxy bias models and the eNLA intrinsic-alignment window (reference: nuisance.py:89-230)."""
+
+    def __init__(self, configuration=None):
+        configuration, _ = _cfg_of(configuration)
+        self.specs, self.settings = configuration.specs, configuration.settings
+        self.observables = configuration.obs
+        sp = self.specs
+        self.z = np.linspace(min(sp["z_bins_WL"][0], sp["z_bins_GCph"][0]),
+                             max(sp["z_bins_WL"][-1], sp["z_bins_GCph"][-1]) + 1, 50 * self.settings["accuracy"])
+        if "WL" in self.observables:
+            lum = _lumratio_table(self.settings.get("external_data_dir"))
+            self.lumratio = interp1d(lum[:, 0], lum[:, 1], kind="linear")
+            self._lum_z = self.lumratio(self.z)
+
+    def gcph_bias(self, biaspars, ibin=1):
+        z = self.z
+        model = biaspars["bias_model"]
+        if model == "sqrt":
+            return interp1d(z, biaspars["b0"] * np.sqrt(1 + z), kind="linear")
+        if model == "binned":
+            edges = np.asarray(self.specs["z_bins_GCph"])
+            brang = self.specs["binrange_GCph"]
+            last = brang[-1]
+            vals = np.array([biaspars[f"b{k}"] for k in brang], dtype=float)
+            return lambda za: vals[np.clip(np.searchsorted(edges, np.asarray(za), side="right") - 1, 0, last - 1)]
+        if model == "binned_constant":
+            return lambda za: np.full(np.shape(za), biaspars["b" + str(ibin)], dtype=float)
+        if model == "flagship":
+            b = biaspars["A"] + biaspars["B"] / (1 + np.exp(-biaspars["C"] * (z - biaspars["D"])))
+            return interp1d(z, b, kind="linear")
+        raise ValueError("unknown galaxy bias model: " + str(model))
+
+    def IA(self, IApars, cosmo):
+        if IApars["IA_model"] != "eNLA":
+            raise ValueError("only the eNLA intrinsic alignment model exists")
+        Om = cosmo.Omegam_of_z(0.0)
+        piv = self.settings["pivot_z_IA"]
+        z = self.z
+        CIA = 0.0134 * (1 + piv)
+        fac = -IApars["AIA"] * CIA * Om
+        z_dep = (1 + z) / (1 + piv)
+        win = fac * z_dep ** IApars["etaIA"] * ((self._lum_z ** IApars["betaIA"]) / (cosmo.growth(z).flatten()))
+        return InterpolatedUnivariateSpline(z, win, k=1)
+
+
+class _PhotoGrid:
+    """ell / z sampling and tomographic row layout shared by every stencil point (photo_obs.py:287-318)."""
+
+    def __init__(self, configuration):
+        configuration, cfg = _cfg_of(configuration)
+        sp, st = configuration.specs, configuration.settings
+        self.observables = [o for o in configuration.obs if o in ("GCph", "WL")]
+        if not self.observables:
+            raise ValueError("Observables not specified correctly")
+        self.binrange = {"GCph": sp["binrange_GCph"], "WL": sp["binrange_WL"]}
+        if len(self.observables) == 2:
+            ellmax, ellmin = max(sp["lmax_GCph"], sp["lmax_WL"]), min(sp["lmin_GCph"], sp["lmin_WL"])
+        else:
+            o = self.observables[0]
+            ellmax, ellmin = sp["lmax_" + o], sp["lmin_" + o]
+        self.ellmax, self.ellmin = ellmax, ellmin
+        self.zsamp = int(round(200 * st["accuracy"]))
+        if st["ell_sampling"] == "accuracy":
+            self.ellsamp = int(round(100 * st["accuracy"]))
+        elif isinstance(st["ell_sampling"], int):
+            self.ellsamp = st["ell_sampling"]
+        else:
+            raise ValueError("ell_sampling should be an integer or 'accuracy'")
+        self.ell = np.logspace(np.log10(ellmin), np.log10(ellmax + 10), num=self.ellsamp)
+        self.z_min = np.min([sp["z_bins_GCph"][0], sp["z_bins_WL"][0]])
+        self.z_max = np.max([sp["z_bins_GCph"][-1], sp["z_bins_WL"][-1]])
+        self.z = np.linspace(self.z_min, self.z_max, self.zsamp)
+        self.dz = np.mean(np.diff(self.z))
+        # rows: all bins of observable 0, then observable 1 (cosmicfish.py:686-691)
+        self.rows = [(o, i) for o in self.observables for i in self.binrange[o]]
+        self.cols = [f"{o} {i}" for o, i in self.rows]
+        self.kind = np.array([0 if o == "WL" else 1 for o, _ in self.rows], dtype=np.int32)
+        self.lmin = np.array([sp["lmin_" + o] for o, _ in self.rows], dtype=float)
+        self.lmax = np.array([sp["lmax_" + o] for o, _ in self.rows], dtype=float)
+        noise_wl = (sp["ellipt_error"] ** 2.0) / np.array(sp["ngalbin_WL"])       # photo_cov.py:111
+        noise_gc = 1.0 / np.array(sp["ngalbin_GCph"])                            # photo_cov.py:114
+        self.noise = np.array([noise_wl[i - 1] if o == "WL" else noise_gc[i - 1] for o, i in self.rows])
+        self.sqrtfsky = np.array([np.sqrt(sp["fsky_" + o]) for o, _ in self.rows])  # photo_cov.py:228
+        self.kmax = float(sp["kmax"])
+        self.tab_p = _lib.TAB_PNL if st["nonlinear"] else _lib.TAB_PLIN
+        if st["GCph_Tracer"] != "matter":
+            raise NotImplementedError("GCph_Tracer='clustering' (cb tables) is not supported")
+        if st["activateMG"] or st["external_activateMG"]:
+            raise NotImplementedError("modified-gravity Sigma(z,k) is not supported")
+
+
+class PhotoJob:
+    """One photometric job on the device: stencil points (parameter dictionaries) -> C_ell of each and,
+    if a stencil is given, the Fisher matrix."""
+
+    def __init__(self, configuration, points: List[dict], stw, stden, cosmo_set: Optional[CosmoSet] = None):
+        configuration, cfg = _cfg_of(configuration)
+        self.configuration, self.cfg = configuration, cfg
+        g = self.grid = _PhotoGrid(configuration)
+        cs = self.cosmo_set = cosmo_set if cosmo_set is not None else _cosmo_set_of(cfg)
+        nuis = PhotoNuisance(configuration)
+        fid_photo = cfg.photoparams
+        S, Nz, Nb = len(points), g.zsamp, len(g.rows)
+        self.cosmo_of_s = np.zeros(S, dtype=np.int32)
+        self.bias = np.ones((S, Nb, Nz))
+        self.ia = np.zeros((S, Nz))
+        for s, ap in enumerate(points):
+            photopars = {k: ap[k] for k in fid_photo}
+            if photopars != fid_photo:
+                raise NotImplementedError("photo-z parameters cannot be varied per stencil point yet")
+            cp = {k: ap[k] for k in cfg.fiducialparams}
+            c = cs.add(cp)
+            self.cosmo_of_s[s] = c
+            if "WL" in g.observables:
+                self.ia[s] = nuis.IA({k: ap[k] for k in cfg.IAparams}, cs.cosmos[c])(g.z)
+            if "GCph" in g.observables:
+                bp = {k: ap[k] for k in cfg.Photobiasparams}
+                for a, (o, i) in enumerate(g.rows):
+                    if o == "GCph":
+                        self.bias[s, a] = nuis.gcph_bias(bp, i)(g.z)
+        NC = len(cs)
+        self.chi = np.array([c.comoving(g.z) for c in cs.cosmos])
+        self.hub = np.array([c.Hubble(g.z) for c in cs.cosmos])
+        self.wlpref = np.array([(3.0 / 2.0) * c.Hubble(0.0) ** 2.0 * c.Omegam_of_z(0.0) for c in cs.cosmos])
+        win = galaxy_photo_dist(fid_photo, configuration)
+        self.window = win
+        self.ngal = np.array([win.norm_ngal_photoz(g.z, i, o) for o, i in g.rows])
+        self.stw, self.stden = np.asarray(stw, float), np.asarray(stden, float)
+        self.NC = NC
+        self._plan = None
+
+    def plan(self) -> _lib.PhotoPlan:
+        if self._plan is None:
+            g, cs = self.grid, self.cosmo_set
+            self._plan = _lib.PhotoPlan(
+                cs.ctx or _lib.default_context(), cs.bank(), cosmo_of_s=self.cosmo_of_s, ell=g.ell, z=g.z, dz=g.dz,
+                chi=self.chi, hub=self.hub, wlpref=self.wlpref, kind=g.kind, ngal=self.ngal, bias=self.bias,
+                ia=self.ia, lmin=g.lmin, lmax=g.lmax, noise=g.noise, sqrtfsky=g.sqrtfsky, stw=self.stw,
+                stden=self.stden, kmax=g.kmax, tab_p=g.tab_p)
+        return self._plan
+
+    def run(self):
+        p = self.plan()
+        p.run()
+        return p
+
+    def close(self):
+        if self._plan is not None:
+            self._plan.close()
+            self._plan = None
+
+
+def _cosmo_set_of(cfg) -> CosmoSet:
+    cs = cfg.__dict__.get("_cosmo_set")
+    if cs is None:
+        cs = CosmoSet(cfg)
+        cfg.__dict__["_cosmo_set"] = cs
+    return cs
+
+
+def _cls_dict(grid: _PhotoGrid, cl: np.ndarray) -> dict:
+    """[Nl][Nb][Nb] -> the reference's dictionary {"ells": ..., "WL 1xGCph 3": (Nl,), ...}."""
+    out = {"ells": grid.ell}
+    for a, ca in enumerate(grid.cols):
+        for b, cb in enumerate(grid.cols):
+            out[ca + "x" + cb] = np.ascontiguousarray(cl[:, a, b])
+    return out
+
+
+class ComputeCls:
+    """Angular power spectra of one parameter point (reference: photo_obs.py:163-928)."""
+
+    def __init__(self, cosmopars, photopars, IApars, biaspars, print_info_specs=False, fiducial_cosmo=None,
+                 configuration=None):
+        configuration, cfg = _cfg_of(configuration)
+        self.configuration, self._cfg = configuration, cfg
+        self.feed_lvl = configuration.settings["feedback"]
+        self.cosmopars, self.photopars, self.IApars, self.biaspars = cosmopars, photopars, IApars, biaspars
+        self.cosmo_set = _cosmo_set_of(cfg)
+        self.cosmo = self.cosmo_set.cosmos[self.cosmo_set.add(cosmopars)] if fiducial_cosmo is None else fiducial_cosmo
+        g = self.grid = _PhotoGrid(configuration)
+        self.observables, self.binrange = g.observables, g.binrange
+        self.binrange_WL, self.binrange_GCph = g.binrange["WL"], g.binrange["GCph"]
+        configuration.specs["ellmax"], configuration.specs["ellmin"] = g.ellmax, g.ellmin
+        self.tracer = configuration.settings["GCph_Tracer"]
+        self.zsamp, self.ellsamp, self.ell = g.zsamp, g.ellsamp, g.ell
+        self.z_min, self.z_max, self.z, self.dz = g.z_min, g.z_max, g.z, g.dz
+        self.window = galaxy_photo_dist(photopars, configuration)
+        self.result = None
+        if print_info_specs and self.feed_lvl >= 2:
+            print(f"*** ell in [{g.ellmin}, {g.ellmax}] x{g.ellsamp}, z in [{g.z_min}, {g.z_max}] x{g.zsamp} ***")
+
+    def compute_all(self):
+        allpars = {**self.cosmopars, **self.IApars, **self.biaspars, **self.photopars}
+        job = PhotoJob(self.configuration, [allpars], np.zeros((1, 1)), np.ones(1), self.cosmo_set)
+        plan = job.run()
+        _, cl, T = plan.fetch(cls=True, sqrtp=True)
+        job.close()
+        self.result = _cls_dict(self.grid, cl[0])
+        sq = np.ascontiguousarray(T[job.cosmo_of_s[0]].T)  # (Nz, Nl) like the reference's sqrtPell tables
+        self.sqrtPell = {"WL": sq, "WL_IA": sq, "GCph": sq, "GCph_IA": np.zeros_like(sq)}
+        return None
+
+    computecls = computecls_vectorized = lambda self: (self.compute_all(), self.result)[1]
+
+
+class PhotoCov:
+    """C_ell cache, noise, covariance and the Fisher of the photometric probes
+    (reference: photo_cov.py:24-381 + cosmicfish.py:643-744, fused on the device)."""
+
+    def __init__(self, cosmopars, photopars, IApars, biaspars, fiducial_Cls=None, enable_cache=True, cache_size=32,
+                 configuration=None, stencil="3PT"):
+        configuration, cfg = _cfg_of(configuration)
+        self.configuration, self._cfg = configuration, cfg
+        self.cosmopars, self.photopars, self.IApars, self.biaspars = cosmopars, photopars, IApars, biaspars
+        self.allparsfid = {**cosmopars, **IApars, **biaspars, **photopars}
+        self.fiducial_Cls = fiducial_Cls
+        g = self.grid = _PhotoGrid(configuration)
+        sp = configuration.specs
+        self.observables, self.binrange = g.observables, g.binrange
+        self.binrange_WL, self.binrange_GCph = sp["binrange_WL"], sp["binrange_GCph"]
+        self.feed_lvl = configuration.settings["feedback"]
+        self.fsky_WL, self.fsky_GCph = sp.get("fsky_WL"), sp.get("fsky_GCph")
+        self.ngalbin_WL, self.ngalbin_GCph = np.array(sp["ngalbin_WL"]), np.array(sp["ngalbin_GCph"])
+        self.numbins_WL, self.numbins_GCph = len(sp["z_bins_WL"]) - 1, len(sp["z_bins_GCph"]) - 1
+        self.ellipt_error = sp["ellipt_error"]
+        self.stencil = stencil
+        self.timings = {}
+        self._job = None
+        self._cls_all = None
+        self._cache = {}
+
+    # --- single-point interface ------------------------------------------------------------------
+    def getcls(self, allpars):
+        """{"ells", "X ixY j"} at an arbitrary parameter point (photo_cov.py:116-162)."""
+        key = tuple(sorted((k, v) for k, v in allpars.items() if not isinstance(v, (dict, list))))
+        if key not in self._cache:
+            job = PhotoJob(self.configuration, [dict(allpars)], np.zeros((1, 1)), np.ones(1))
+            plan = job.run()
+            _, cl, _ = plan.fetch(cls=True)
+            job.close()
+            self._cache[key] = _cls_dict(self.grid, cl[0])
+        return self._cache[key]
+
+    def getclsnoise(self, cls):
+        noisy = dict(cls)
+        for a, (o, i) in enumerate(self.grid.rows):
+            k = f"{o} {i}x{o} {i}"
+            noisy[k] = noisy[k] + self.grid.noise[a]
+        return noisy
+
+    def get_covmat(self, noisy_cls):
+        """Per-multipole covariance (C + N)/sqrt(f_sky) as an array [Nl][Nb][Nb]; column order `cov_cols`
+        (the reference returns a list of pandas DataFrames with the same values, photo_cov.py:198-245)."""
+        cols = self.grid.cols
+        self.cov_cols = cols
+        cov = np.empty((len(noisy_cls["ells"]), len(cols), len(cols)))
+        for a, ca in enumerate(cols):
+            for b, cb in enumerate(cols):
+                cov[:, a, b] = noisy_cls[ca + "x" + cb] / self.grid.sqrtfsky[a]
+        return cov
+
+    # --- the whole job ---------------------------------------------------------------------------
+    def _freeparams(self, freeparams=None):
+        fp = dict(self._cfg.freeparams if freeparams is None else freeparams)
+        missing = [k for k in fp if k not in self.allparsfid]
+        for k in missing:  # photo_cov.py:270-293
+            if k in self._cfg.fiducialparams:
+                self.allparsfid[k] = self._cfg.fiducialparams[k]
+            elif k == "Omegab":
+                self.allparsfid[k] = 0.05
+            else:
+                raise ValueError("Fiducial values missing for free parameters: " + k)
+        return fp
+
+    def build_job(self, freeparams=None) -> PhotoJob:
+        fp = self._freeparams(freeparams)
+        pts, den = stencils.get(self.stencil)
+        points = [dict(self.allparsfid)]
+        rows, stden = [], np.ones(len(fp))
+        for ip, par in enumerate(fp):
+            h = stencils.stepsize(self.allparsfid[par], fp[par])
+            stden[ip] = den * h
+            row = {}
+            for m, w in pts:
+                if m == 0:
+                    row[0] = row.get(0, 0.0) + w
+                    continue
+                ap = copy.deepcopy(self.allparsfid)
+                ap[par] = ap[par] + m * h
+                points.append(ap)
+                row[len(points) - 1] = w
+            rows.append(row)
+        stw = np.zeros((len(fp), len(points)))
+        for ip, row in enumerate(rows):
+            for s, w in row.items():
+                stw[ip, s] = w
+        self.parnames = list(fp)
+        self.points = points
+        self._job = PhotoJob(self.configuration, points, stw, stden)
+        self._cls_all = None
+        return self._job
+
+    def compute_fisher(self, freeparams=None) -> np.ndarray:
+        t0 = time()
+        job = self.build_job(freeparams)
+        plan = job.plan()
+        t1 = time()
+        plan.run()
+        F, _, _ = plan.fetch()
+        t2 = time()
+        self.timings = {"host_prep_s": t1 - t0, "device_s": t2 - t1}
+        self.fisher = F
+        return F
+
+    def _all_cls(self):
+        if self._job is None:
+            self.build_job()
+            self._job.run()
+        if self._cls_all is None:
+            _, self._cls_all, _ = self._job.plan().fetch(cls=True)
+        return self._cls_all
+
+    def compute_covmat(self):
+        cl = self._all_cls()[0]
+        self.cls = _cls_dict(self.grid, cl)
+        self.noisy_cls = self.getclsnoise(self.cls)
+        self.covmat = self.get_covmat(self.noisy_cls)
+        return self.noisy_cls, self.covmat
+
+    def compute_derivs(self, print_info_specs=False):
+        """{par: {"ells": ..., "X ixY j": dC/dpar (Nl,)}} from the device C_ell of every stencil point."""
+        cl = self._all_cls()
+        job = self._job
+        derivs = {}
+        for ip, par in enumerate(self.parnames):
+            acc = np.zeros_like(cl[0])
+            for s in np.nonzero(job.stw[ip])[0]:
+                acc = acc + job.stw[ip, s] * cl[s]
+            derivs[par] = _cls_dict(self.grid, acc / job.stden[ip])
+        self.derivs = derivs
+        return derivs
