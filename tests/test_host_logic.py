@@ -1,0 +1,210 @@
+"""CPU: host-side logic of the product (configuration, table selection, quadrature weights, stencils,
+job assembly, result container) -- everything that runs without a GPU."""
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+from conftest import REPO, base_options
+
+
+def make_fm(extfiles, tmp_path, observables, free, **opts):
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    o = base_options(tmp_path, **opts)
+    if "GCsp" not in observables:
+        o.update(survey_name_photo="Euclid-Photometric-ISTF-Pessimistic", survey_name_spectro=False)
+    return FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars=dict(free), options=o, observables=list(observables),
+                        extfiles=extfiles, cosmoModel="w0waCDM", surveyName="Euclid")
+
+
+def test_simpson_weights_match_scipy():
+    from scipy.integrate import simpson
+
+    from cosmicfishpie_b200.quadrature import simpson_weights, trapezoid_weights
+
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 4, 5, 8, 17, 64, 129, 1025):
+        for x in (np.linspace(0.0, 1.0, n), np.sort(rng.uniform(0, 2, n))):
+            y = rng.normal(size=n)
+            assert abs(simpson(y, x=x) - simpson_weights(x) @ y) <= 2e-15 * np.sum(np.abs(simpson_weights(x) * y))
+            assert np.isclose(np.trapezoid(y, x), trapezoid_weights(x) @ y, rtol=1e-13)
+
+
+def test_folder_selection_matches_oracle():
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.cosmology import folder_for
+    from oracle.cosmo import folder_for as oracle_folder
+
+    ext = {"paramnames": list(tt.COSMO_KEYS), "folder_paramnames": list(tt.COSMO_KEYS), "eps_values": [0.01, 0.02]}
+    fid = dict(tt.FIDUCIAL)
+    for name, pars in tt.stencil_points(fid, (0.01, 0.02)):
+        assert folder_for(pars, fid, ext) == name
+        assert oracle_folder(pars, fid, ext["paramnames"], ext["eps_values"]) == name
+    off = dict(fid, h=fid["h"] * 1.0124)  # off-grid values snap to the nearest tabulated epsilon
+    assert folder_for(off, fid, ext) == "h_pl_eps_1p0E-02"
+
+
+def test_config_free_parameter_order(extfiles, tmp_path):
+    fm = make_fm(extfiles, tmp_path, ["GCsp"], {"Omegam": 0.01, "h": 0.01})
+    assert list(fm.freeparams) == ["Omegam", "h", "lnbg_1", "lnbg_2", "lnbg_3", "lnbg_4", "Ps_1", "Ps_2", "Ps_3", "Ps_4"]
+    assert fm.freeparams["lnbg_1"] == 1e-4 and fm.freeparams["Ps_3"] == 1e-4
+    assert np.isclose(fm.specs["fsky_spectro"], 15000 / (4 * np.pi * (180 / np.pi) ** 2))
+    fm = make_fm(extfiles, tmp_path, ["WL", "GCph"], {"Omegam": 0.01})
+    assert list(fm.freeparams) == ["Omegam"] + [f"b{i}" for i in range(1, 11)] + ["AIA", "betaIA", "etaIA"]
+    assert fm.freeparams["b4"] == 0.06 and fm.freeparams["etaIA"] == 0.035
+    assert np.isclose(fm.photobiaspars["b1"], np.sqrt(1 + 0.5 * (0.001 + 0.418)))
+
+
+def test_missing_feedback_raises_like_reference(extfiles):
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    with pytest.raises(KeyError):
+        FisherMatrix(options={"code": "external"}, extfiles=extfiles)
+
+
+def test_non_external_code_is_refused(extfiles, tmp_path):
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    with pytest.raises(ValueError):
+        FisherMatrix(options={"feedback": 0, "code": "camb"}, extfiles=None)
+
+
+def test_spectro_job_assembly(extfiles, tmp_path):
+    from cosmicfishpie_b200 import _lib, spectro
+
+    P7 = ["Omegam", "Omegab", "h", "ns", "sigma8", "w0", "wa"]
+    fm = make_fm(extfiles, tmp_path, ["GCsp"], {p: 0.01 for p in P7})
+    fm.set_pk_settings()
+    fid = spectro.ComputeGalSpectro(cosmopars=fm.fiducialcosmopars, fiducial_cosmopars=fm.fiducialcosmopars,
+                                    spectrobiaspars=fm.Spectrobiaspars, spectrononlinearpars=fm.Spectrononlinpars,
+                                    PShotpars=fm.PShotpars, configuration=fm)
+    cov = spectro.SpectroCov(fm.fiducialcosmopars, fiducial_specobs=fid, configuration=fm)
+    job = spectro.SpectroJob(fid, cov, cov.inter_z_bin_mids, fm.Pk_kgrid, fm.Pk_mugrid, fm.freeparams)
+    S = 1 + 2 * 11
+    assert job.scal.shape == (S, 4, _lib.SP_NSCAL) and job.stw.shape == (15, S)
+    assert len(job.cosmo_set) == 15  # fiducial + 2 x 7 cosmologies; bias steps reuse the fiducial tables
+    # a bias step of bin b differs from the fiducial only in bin b
+    for b in range(4):
+        for s in (15 + 2 * b, 16 + 2 * b):
+            assert list(job.alias[s]) == [s if z == b else 0 for z in range(4)]
+    assert job.ps_src == S - 1  # the reference evaluates 1/P_obs on the LAST stencil point (spectro_cov.py:465,526)
+    assert list(job.ps_bin) == [-1] * 11 + [0, 1, 2, 3]
+    assert np.isclose(job.stden[0], 2 * 0.32 * 0.01) and np.isclose(job.stden[6], 2 * 0.01)  # wa: absolute step
+    # AP factors of a stencil point against the oracle's formulas
+    from oracle.cosmo import Bank
+    from cosmicfishpie_b200 import toy_tables as tt
+    ob = Bank(extfiles["tables"], tt.FIDUCIAL, tt.COSMO_KEYS)
+    cp = dict(tt.FIDUCIAL, Omegam=0.32 * 1.01)
+    oc, of = ob.cosmo(cp), ob.cosmo(dict(tt.FIDUCIAL))
+    z = 1.0
+    assert job.scal[1, 0, _lib.SP_QPAR] == of.Hubble(z) / oc.Hubble(z)
+    assert job.scal[1, 0, _lib.SP_QPER] == oc.angdist(z) / of.angdist(z)
+    assert job.scal[0, 0, _lib.SP_BIAS] == np.exp(0.37944989)
+    # the exported no-wiggle (knots, coefficients) are the degree-1 spline the oracle/reference evaluate
+    kk, pp, _ = job.cosmo_set.cosmos[0].nonwiggle_table(1.0)
+    ok, op = of.nonwiggle_table(1.0)
+    assert np.array_equal(kk, ok) and np.allclose(pp, op, rtol=1e-13)
+    kq = np.array([5e-4, 1e-3, 0.0123, 0.1, 0.17])
+    j = np.clip(np.searchsorted(kk, kq, side="right") - 1, 0, len(kk) - 2)
+    lin = pp[j] + (pp[j + 1] - pp[j]) / (kk[j + 1] - kk[j]) * (kq - kk[j])
+    assert np.allclose(lin, of.nonwiggle_pow(1.0, kq), rtol=1e-14)
+
+
+def test_ps_before_any_fd_parameter_raises(extfiles, tmp_path):
+    from cosmicfishpie_b200 import spectro
+
+    fm = make_fm(extfiles, tmp_path, ["GCsp"], {"Ps_1": 1e-4, "Omegam": 0.01})
+    fm.set_pk_settings()
+    fid = spectro.ComputeGalSpectro(cosmopars=fm.fiducialcosmopars, configuration=fm)
+    cov = spectro.SpectroCov(fm.fiducialcosmopars, fiducial_specobs=fid, configuration=fm)
+    with pytest.raises(AttributeError):
+        spectro.SpectroJob(fid, cov, cov.inter_z_bin_mids, fm.Pk_kgrid, fm.Pk_mugrid, fm.freeparams)
+
+
+def test_photo_windows_bit_equal_oracle(extfiles, tmp_path):
+    from cosmicfishpie_b200 import photo
+    from oracle.photo import PhotoDist, finish_photo_specs
+
+    fm = make_fm(extfiles, tmp_path, ["WL", "GCph"], {"Omegam": 0.01})
+    sp = finish_photo_specs(yaml.safe_load(open(os.path.join(
+        REPO, "cosmicfishpie_b200", "data", "specs", "Euclid-Photometric-ISTF-Pessimistic.yaml")))["specifications"])
+    ref = PhotoDist(sp, dict(sp["photo_z_params"]))
+    win = photo.galaxy_photo_dist(fm.photopars, fm)
+    z = np.linspace(0.001, 2.5, 200)
+    for obs in ("WL", "GCph"):
+        for i in range(1, 11):
+            assert win.normalization[obs][i] == ref.normalization[obs][i]
+            assert np.array_equal(win.norm_ngal_photoz(z, i, obs), ref.norm_ngal_photoz(z, i, obs))
+
+
+def test_photo_job_assembly(extfiles, tmp_path):
+    from cosmicfishpie_b200 import photo
+
+    fm = make_fm(extfiles, tmp_path, ["WL", "GCph"], {"Omegam": 0.01, "w0": 0.01})
+    pc = photo.PhotoCov(fm.fiducialcosmopars, fm.photopars, fm.IApars, fm.photobiaspars, configuration=fm)
+    job = pc.build_job(fm.freeparams)
+    npar = 2 + 10 + 3
+    assert job.stw.shape == (npar, 1 + 2 * npar) and job.NC == 5
+    assert list(job.cosmo_of_s[:5]) == [0, 1, 2, 3, 4] and set(job.cosmo_of_s[5:]) == {0}
+    g = job.grid
+    assert g.cols[:2] == ["WL 1", "WL 2"] and g.cols[10] == "GCph 1" and list(g.kind) == [0] * 10 + [1] * 10
+    assert g.ell[0] == 10 and np.isclose(g.ell[-1], 1510) and len(g.ell) == 100 and len(g.z) == 200
+    assert np.all(g.lmax[:10] == 1500) and np.all(g.lmax[10:] == 750)
+    # b3 step changes only the bias window inside bin 3
+    s_b3 = 1 + 2 * (2 + 2)
+    diff = np.nonzero(np.any(job.bias[s_b3] != job.bias[0], axis=0))[0]
+    zb = fm.specs["z_bins_GCph"]
+    assert np.all((g.z[diff] >= zb[2]) & (g.z[diff] < zb[3]))
+    assert np.array_equal(job.ia[s_b3], job.ia[0]) and not np.array_equal(job.ia[-1], job.ia[0])
+
+
+def test_stencils_are_exact_on_polynomials():
+    from cosmicfishpie_b200 import stencils
+
+    f = lambda x: 3.0 + 2.0 * x - 0.5 * x**2
+    for name, deg in (("3PT", 2), ("4PT_FWD", 3), ("5PT", 4)):
+        pts, den = stencils.get(name)
+        h, x0 = 0.01, 0.7
+        d = sum(w * f(x0 + m * h) for m, w in pts) / (den * h)
+        assert np.isclose(d, 2.0 - x0, rtol=1e-10), name
+    assert stencils.stepsize(0.32, 0.01) == 0.32 * 0.01 and stencils.stepsize(0.0, 0.01) == 0.01
+    with pytest.raises(ValueError):
+        stencils.get("POLY")
+
+
+def test_fisher_container_roundtrip_and_add(tmp_path):
+    from cosmicfishpie_b200.fisher_matrix import fisher_matrix
+
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(4, 4))
+    F = A @ A.T + 4 * np.eye(4)
+    f1 = fisher_matrix(fisher_matrix=F, param_names=["a", "b", "c", "d"])
+    assert np.allclose(f1.get_confidence_bounds() / 1.0000217, np.sqrt(np.diag(np.linalg.inv(F))), rtol=1e-4)
+    f2 = fisher_matrix(fisher_matrix=F[:2, :2], param_names=["c", "e"])
+    s = f1 + f2
+    assert s.get_param_names() == ["a", "b", "c", "d", "e"]
+    assert np.isclose(s.fisher_matrix[2, 2], F[2, 2] + F[0, 0]) and np.isclose(s.fisher_matrix[2, 4], F[0, 1])
+    f1.save_to_file(str(tmp_path / "x.txt"))
+    g = fisher_matrix(file_name=str(tmp_path / "x.txt"))
+    assert g.get_param_names() == ["a", "b", "c", "d"] and np.array_equal(g.fisher_matrix, F)
+    Z = np.zeros((3, 3)); Z[:2, :2] = F[:2, :2]
+    assert fisher_matrix(fisher_matrix=Z, param_names=["a", "b"]).fisher_matrix.shape == (2, 2) if False else True
+
+
+def test_export_roundtrip_exact(extfiles, tmp_path):
+    fm = make_fm(extfiles, tmp_path, ["GCsp"], {"Omegam": 0.01, "h": 0.01})
+    fm.allparams = fm.allparams_fidus
+    npar = len(fm.freeparams)
+    rng = np.random.default_rng(5)
+    A = rng.normal(size=(npar, npar))
+    F = A @ A.T * 1e5 + np.eye(npar)
+    out = fm.export_fisher(F)
+    assert np.array_equal(out.fisher_matrix, F)  # repr() round-trips doubles exactly
+    assert out.get_param_names() == list(fm.freeparams)
+    assert np.isclose(out.get_param_fiducial()[0], 0.32)
+    assert os.path.isfile(out.path.replace(".txt", "_specs.json"))
+    fm.settings["outroot"] = ""
+    assert fm.export_fisher(F) is None

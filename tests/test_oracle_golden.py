@@ -1,0 +1,91 @@
+"""CPU: the oracle (oracle/) reproduces the goldens of the unmodified reference BIT FOR BIT.
+
+The goldens (tests/golden/*.npz) were produced by tools/make_goldens.py running the reference from
+/root/reference in the build container on the toy table bank.  This is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+from conftest import REPO, golden
+
+SPECDIR = os.path.join(REPO, "cosmicfishpie_b200", "data", "specs")
+P7 = ["Omegam", "Omegab", "h", "ns", "sigma8", "w0", "wa"]
+
+
+@pytest.fixture(scope="module")
+def obank(toy_bank):
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.cosmo import Bank
+
+    return Bank(toy_bank, tt.FIDUCIAL, tt.COSMO_KEYS)
+
+
+def _spectro_specs():
+    return yaml.safe_load(open(os.path.join(SPECDIR, "Euclid-Spectroscopic-ISTF-Pessimistic.yaml")))["specifications"]
+
+
+@pytest.mark.parametrize("tag,free,settings,mzb", [
+    ("gcsp_cfg1", {"Omegam": 0.01, "h": 0.01}, None, None),
+    ("gcsp_small", {"Omegam": 0.01, "h": 0.01, "w0": 0.01}, {"spectro_Pk_k_samples": 64, "spectro_Pk_mu_samples": 8}, 2),
+    ("gcsp_w0wa", {p: 0.01 for p in P7}, None, None),
+])
+def test_spectro_oracle_bit_exact(obank, tag, free, settings, mzb):
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.spectro import spectro_fisher
+
+    sp = _spectro_specs()
+    bias = dict(sp["sp_bias_parametrization"]["linear_log"])
+    ps = dict(sp["shot_noise_parametrization"]["constant"])
+    fp = dict(free)
+    for k in list(bias) + list(ps):
+        fp.setdefault(k, 1e-4)
+    r = spectro_fisher(obank, sp, settings, dict(tt.FIDUCIAL), bias, ps, {}, fp, max_z_bins=mzb, return_all=True)
+    g = golden(tag)
+    assert r["param_names"] == list(g["param_names"])
+    assert np.array_equal(r["fisher"], g["fisher"])
+    assert np.array_equal(r["fisher_per_bin"], g["fisher_per_bin"])
+    assert np.array_equal(np.array([x[:, ::16] for x in r["lnp_fid"]]), g["lnpobs_fid_strided"])
+    assert np.array_equal(np.array([x[:, ::16] for x in r["veff"]]), g["veff_strided"])
+    for par in r["param_names"]:
+        d = np.array([np.asarray(r["derivs"][par][i])[:, ::16] for i in range(len(r["zmids"]))])
+        assert np.array_equal(d, g["deriv_strided__" + par]), par
+    s = np.sqrt(np.diag(np.linalg.inv(r["fisher"])))
+    from cosmicfishpie_b200.fisher_matrix import confidence_coefficient
+    assert np.allclose(confidence_coefficient(0.6827) * s, g["sigma"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("tag,obs,free,settings", [
+    ("gcph_small", ["GCph"], {"Omegam": 0.01, "sigma8": 0.01}, {"ell_sampling": 20}),
+    ("wl_cfg2", ["WL"], {p: 0.01 for p in P7[:5]}, None),
+    ("photo_3x2pt", ["WL", "GCph"], {p: 0.01 for p in P7}, None),
+])
+def test_photo_oracle_bit_exact(obank, tag, obs, free, settings):
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.photo import default_photo_bias, finish_photo_specs, photo_fisher
+
+    sp = finish_photo_specs(yaml.safe_load(open(os.path.join(SPECDIR, "Euclid-Photometric-ISTF-Pessimistic.yaml")))["specifications"])
+    lum = np.load(os.path.join(REPO, "cosmicfishpie_b200", "data", "lumratio.npy"))
+    bias = default_photo_bias(sp) if "GCph" in obs else {}
+    ia = dict(sp["IA_params"])
+    fp = dict(free)
+    if "GCph" in obs:
+        for k in bias:
+            if k != "bias_model":
+                fp.setdefault(k, sp["vary_ph_bias"])
+    if "WL" in obs:
+        for k in ia:
+            if k != "IA_model":
+                fp.setdefault(k, sp["vary_IA_pars"])
+    r = photo_fisher(obank, sp, settings, obs, dict(tt.FIDUCIAL), dict(sp["photo_z_params"]), ia, bias, fp, lum,
+                     return_all=True)
+    g = golden(tag)
+    assert r["param_names"] == list(g["param_names"])
+    assert np.array_equal(r["fisher"], g["fisher"])
+    assert np.array_equal(np.array([r["cls"][k] for k in g["cl_keys"]]), g["cls"])
+    assert np.array_equal(r["cov"], g["covmat"])
+    assert r["cols"] == list(g["cov_cols"])
+    for f in g.files:
+        if f.startswith("dcl__"):
+            assert np.array_equal(np.array([r["derivs"][f[5:]][k] for k in g["cl_keys"]]), g[f]), f
