@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Benchmark of the observable -> Fisher hot path (BASELINE.json metric: Fisher matrices / s).
+
+    python bench.py --gpus 1 --steps K --warmup W               # this package on N GPUs
+    python bench.py --impl reference --steps K --warmup W       # CPU arm (oracle port of the reference)
+
+One STEP = one Euclid forecast: a 3x2pt photometric Fisher (WL+GCph+XC, 13+13 tomographic bins,
+lmax_WL = 5000, w0waCDM 7 cosmological + 13 galaxy-bias + 3 IA parameters, 100 multipoles x 200 z) PLUS a
+GCsp Fisher (4 z-bins, 7 cosmological + 4 bias + 4 shot-noise parameters, 3PT stencil, fine lattice
+N_mu x N_k = 129 x 8193), summed into one combined Fisher matrix.  Inputs are synthetic (deterministic toy
+Boltzmann tables, cosmicfishpie_b200/toy_tables.py) in the reference's `external` table format.
+
+Numbers in the JSON line
+  value      combined Fisher matrices / s with every input resident in HBM (plans uploaded, device timing by
+             CUDA events on the launch stream, L2 flushed between steps)
+  e2e        the same metric through the public API `FisherMatrix(...).compute()` from HOST tables: spline
+             fitting, per-job host preparation, H2D of the table bank and job arrays, kernels, D2H of the
+             Fisher matrices and file export are all inside the timed region (what a reference user times)
+  cabi_e2e   through the C ABI only (cfp_*_plan_create from host buffers + run + fetch)
+  roofline   dominant kernel (spectro_fisher_kernel) against the measured FP64 DFMA peak of this GPU; the
+             HBM view of the API-preserving (materialising) mode is in `roofline_hbm`
+  cpu_baseline  the oracle (numpy/scipy port of the reference algorithm) on one host core, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+from cosmicfishpie_b200 import toy_tables as tt  # noqa: E402
+
+P7 = list(tt.COSMO_KEYS)
+PHOTO_SPEC = "Euclid-Photometric-13bins-lmax5000"
+SPECTRO_SPEC = "Euclid-Spectroscopic-ISTF-Pessimistic"
+NMU, NK = 129, 8193
+WORKLOAD = f"euclid_3x2pt_13bins_lmax5000_npar23 + gcsp_4bins_npar15_3PT_lattice{NMU}x{NK}"
+# FP64 operations per lattice-cell evaluation of spectro_fisher_kernel, counted once from ncu
+# (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on, DFMA = 2) -- see profiles/ and DESIGN.md
+F_CELL = 298.0
+
+
+def ext_dict(bank):
+    return {"tables": bank, "directory": "<memory>", "paramnames": P7, "folder_paramnames": P7,
+            "k-units": "1/Mpc", "r-units": "Mpc", "eps_values": [0.01]}
+
+
+def base_options(tmp, **kw):
+    o = {"accuracy": 1, "feedback": 0, "code": "external", "outroot": "bench", "results_dir": tmp,
+         "survey_name": "Euclid", "cosmo_model": "w0waCDM", "derivatives": "3PT"}
+    o.update(kw)
+    return o
+
+
+def make_photo_fm(bank, tmp):
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    return FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={p: 0.01 for p in P7},
+                        options=base_options(tmp, survey_name_photo=PHOTO_SPEC, survey_name_spectro=False),
+                        observables=["WL", "GCph"], extfiles=ext_dict(bank))
+
+
+def make_spectro_fm(bank, tmp, nmu=NMU, nk=NK):
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    return FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={p: 0.01 for p in P7},
+                        options=base_options(tmp, survey_name_spectro=SPECTRO_SPEC, survey_name_photo=False,
+                                             spectro_Pk_k_samples=nk, spectro_Pk_mu_samples=nmu),
+                        observables=["GCsp"], extfiles=ext_dict(bank))
+
+
+# ------------------------------------------------------------------------------ CPU arm (oracle)
+def oracle_sample(bank, nmu_s=17, nk_s=1025):
+    """One bounded CPU sample of the step: the full 3x2pt Fisher plus the GCsp Fisher on a 17x1025 lattice,
+    whose time is scaled by the cell ratio to the 129x8193 workload lattice.  Returns seconds per step."""
+    import yaml
+
+    from oracle.cosmo import Bank
+    from oracle.photo import default_photo_bias, finish_photo_specs, photo_fisher
+    from oracle.spectro import spectro_fisher
+
+    specdir = os.path.join(REPO, "cosmicfishpie_b200", "data", "specs")
+    ob = Bank(bank, tt.FIDUCIAL, tt.COSMO_KEYS)
+    ph = finish_photo_specs(yaml.safe_load(open(os.path.join(specdir, PHOTO_SPEC + ".yaml")))["specifications"])
+    lum = np.load(os.path.join(REPO, "cosmicfishpie_b200", "data", "lumratio.npy"))
+    bias, ia = default_photo_bias(ph), dict(ph["IA_params"])
+    fp = {p: 0.01 for p in P7}
+    fp.update({k: ph["vary_ph_bias"] for k in bias if k != "bias_model"})
+    fp.update({k: ph["vary_IA_pars"] for k in ia if k != "IA_model"})
+    t0 = time.perf_counter()
+    photo_fisher(ob, ph, None, ["WL", "GCph"], dict(tt.FIDUCIAL), dict(ph["photo_z_params"]), ia, bias, fp, lum)
+    t_photo = time.perf_counter() - t0
+    sp = yaml.safe_load(open(os.path.join(specdir, SPECTRO_SPEC + ".yaml")))["specifications"]
+    sb, ps = dict(sp["sp_bias_parametrization"]["linear_log"]), dict(sp["shot_noise_parametrization"]["constant"])
+    fs = {p: 0.01 for p in P7}
+    fs.update({k: 1e-4 for k in list(sb) + list(ps)})
+    t0 = time.perf_counter()
+    spectro_fisher(ob, sp, {"spectro_Pk_k_samples": nk_s, "spectro_Pk_mu_samples": nmu_s}, dict(tt.FIDUCIAL), sb, ps,
+                   {}, fs)
+    t_sp = time.perf_counter() - t0
+    scale = (NMU * NK) / float(nmu_s * nk_s)
+    return t_photo + t_sp * scale, {"photo_s": t_photo, "spectro_sample_s": t_sp, "spectro_scale": scale}
+
+
+def _oracle_worker(_):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    bank = tt.make_bank(eps_values=(0.01,))
+    return oracle_sample(bank)[0]
+
+
+def run_reference(args):
+    """`--impl reference`: the CPU implementation on all host cores (independent processes, which is how
+    the reference parallelises -- Nautilus pool=N; a single Fisher is single-threaded)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup and 0):  # the CPU arm needs no warm-up: caches are per process
+            pool.map(_oracle_worker, range(cores))
+        per_step = []
+        for _ in range(max(1, args.steps)):
+            t0 = time.perf_counter()
+            times = pool.map(_oracle_worker, range(cores))
+            wall = time.perf_counter() - t0
+            # every worker processed the bounded sample; its scaled step time is what it returned
+            per_step.append((wall, max(times)))
+    t_step = float(np.mean([t for _, t in per_step]))
+    value = cores / t_step
+    sample = ("per process: full 3x2pt 13+13-bin Fisher + GCsp Fisher on a 17x1025 lattice, spectro time scaled x"
+              f"{(NMU * NK) / (17 * 1025):.1f} (cell ratio) to the 129x8193 workload lattice; {cores} independent "
+              "single-threaded processes")
+    line = {"impl": "reference", "metric": "fisher_matrices_per_s", "value": value, "unit": "Fisher/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step / cores, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": value, "unit": "Fisher/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "Fisher/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_gpu(args):
+    import torch
+
+    from cosmicfishpie_b200 import _lib
+    from cosmicfishpie_b200 import distributed as cdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tmp = tempfile.mkdtemp(prefix=f"cfp_bench_r{rank}_")
+    bank = tt.make_bank(eps_values=(0.01,))
+    ctx = _lib.default_context(local)
+
+    # ---- resident plans (host prep + upload outside the timed region of `value`) -------------------
+    fm_ph = make_photo_fm(bank, tmp)
+    fm_sp = make_spectro_fm(bank, tmp)
+    fm_ph.compute()
+    fm_sp.compute()
+    pplan = fm_ph.photo_LSS._job.plan()
+    splan = fm_sp._spectro_job.plan()
+    ncell = NMU * NK
+    nbins = pplan.Nl - 1
+    cb, ce = cdist.split_range(ncell, rank, world)
+    lb, le = cdist.split_range(nbins, rank, world)
+    splan.set_slice(cb, ce)
+    pplan.set_slice(lb, le)
+    stream = torch.cuda.Stream()
+    sptr = stream.cuda_stream
+    Fsp = cdist.device_view(splan.fisher_device_ptr(), (splan.Z, splan.npar, splan.npar), local)
+    Fph = cdist.device_view(pplan.fisher_device_ptr(), (pplan.npar, pplan.npar), local)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def step():
+        pplan.run(stream=sptr)
+        splan.run(materialize=0, stream=sptr)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                torch.distributed.all_reduce(Fph)
+                torch.distributed.all_reduce(Fsp)
+
+    launches0 = ctx.launches
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches1 = ctx.launches
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        for a, b in ev:
+            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+            a.record(stream)
+            step()
+            b.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    launches_timed = ctx.launches - launches1
+    ms_local = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- dominant kernel alone: spectro_fisher_kernel ------------------------------------------------
+    kms = []
+    for _ in range(max(3, min(args.steps, 10))):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        splan.run(materialize=0, stream=sptr)
+        kms.append(splan.kernel_ms())
+    k_ms = float(np.mean(kms))
+    clk = clocks.stop() if rank == 0 else None
+    job = fm_sp._spectro_job
+    evals = int(sum(1 + np.count_nonzero(job.alias[1:, z]) for z in range(splan.Z))) * (ce - cb)
+    gram = 2.0 * (8 * splan.npar_pad if hasattr(splan, "npar_pad") else 8 * ((splan.npar + 7) // 8)) ** 2 / 2.0
+    flops = F_CELL * evals + gram * splan.Z * (ce - cb)
+    peak_dfma = ctx.peak_fp64(0)
+    peak_dmma = ctx.peak_fp64(1)
+    achieved = flops / (k_ms * 1e-3) / 1e12
+    roof = {"bound": "fp64", "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s", "frac": achieved / peak_dfma,
+            "traffic": None, "kernel": "spectro_fisher_kernel", "kernel_ms": k_ms,
+            "peak_source": "measured live: cfp_peak_fp64 DFMA microbenchmark (MEASURED_PEAKS.json has no FP64 entry)",
+            "peak_dmma_tflops": peak_dmma, "flop_per_cell_eval": F_CELL, "cell_evals": evals}
+    # HBM view: the API-preserving mode writes derivs[npar][Z][cells] + veff[Z][cells] once
+    with torch.cuda.stream(stream):
+        flush.zero_()
+    splan.run(materialize=_lib.MAT_DERIVS, stream=sptr)
+    m_ms = splan.kernel_ms()
+    bytes_alg = 8.0 * splan.Z * (ce - cb) * (splan.npar + 1)
+    hbm_peak = 6551.7
+    try:
+        hbm_peak = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        src = "MEASURED_PEAKS.json (measured)"
+    except Exception:
+        hbm_peak, src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    roof_hbm = {"bound": "hbm", "achieved": bytes_alg / (m_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": bytes_alg / (m_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "kernel": "spectro_fisher_kernel "
+                "(materialising derivs+veff)", "kernel_ms": m_ms, "peak_source": src}
+    splan.set_slice(0, ncell)
+    pplan.set_slice(0, nbins)
+
+    # ---- end to end through the public API, from host tables -----------------------------------------
+    from cosmicfishpie_b200 import cosmology as ccos
+
+    def api_step():
+        ccos._TABLE_CACHE.clear()
+        a = make_photo_fm(bank, tmp)
+        cdist.shard(a, rank, world)
+        Fa = a.compute()
+        b = make_spectro_fm(bank, tmp)
+        cdist.shard(b, rank, world)
+        Fb = b.compute()
+        tot = Fa + Fb
+        h2d = (a.photo_LSS._job.plan().h2d_bytes + a.photo_LSS._job.cosmo_set.bank().nbytes
+               + b._spectro_job.plan().h2d_bytes + b._spectro_job.cosmo_set.bank().nbytes)
+        d2h = 8 * (a.fisher_array.size + b.pk_fisher_per_bin.size)
+        a.photo_LSS._job.close()
+        b._spectro_job.close()
+        return tot, h2d, d2h
+
+    n_e2e = max(2, min(args.steps, 5))
+    api_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        Ftot, h2d, d2h = api_step()
+    torch.cuda.synchronize()
+    t_api = (time.perf_counter() - t0) / n_e2e
+    t = torch.tensor([t_api], dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    t_api = float(t.item())
+
+    # ---- C ABI only: plan_create from host buffers + run + fetch -------------------------------------
+    def cabi_step():
+        jp, js = fm_ph.photo_LSS._job, fm_sp._spectro_job
+        jp.close()
+        js.close()
+        p1, p2 = jp.plan(), js.plan()
+        p1.set_slice(lb, le)
+        p2.set_slice(cb, ce)
+        p1.run()
+        p2.run()
+        p1.fetch()
+        p2.fetch()
+
+    cabi_step()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        cabi_step()
+    t_cabi = (time.perf_counter() - t0) / n_e2e
+
+    if rank == 0:
+        cpu = None
+        if world == 1 or True:
+            t_cpu, detail = oracle_sample(bank)
+            cpu = {"value": 1.0 / t_cpu, "unit": "Fisher/s", "cores": 1, "kind": "port",
+                   "sample": "full 3x2pt 13+13-bin Fisher (%.1f s) + GCsp Fisher on a 17x1025 lattice (%.2f s) scaled x%.1f "
+                             "by cell count to 129x8193" % (detail["photo_s"], detail["spectro_sample_s"], detail["spectro_scale"])}
+        line = {
+            "metric": "fisher_matrices_per_s", "value": value, "unit": "Fisher/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2_flush_between_steps": True,
+                       "partition": "spectro lattice cells and photo multipole bins split over ranks; one NCCL "
+                                    "all-reduce of the Fisher partial sums per probe" if world > 1 else "single GPU"},
+            "clocks": clk,
+            "e2e": {"value": 1.0 / t_api, "unit": "Fisher/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "what": "FisherMatrix(...).compute() x2 (3x2pt, GCsp) + sum, from host tables incl. spline fits, "
+                            "host prep, H2D, kernels, D2H, export", "s_per_step": t_api},
+            "cabi_e2e": {"value": 1.0 / t_cabi, "unit": "Fisher/s", "s_per_step": t_cabi,
+                         "what": "cfp_*_plan_create(host buffers) + run + fetch, table bank resident"},
+            "gpu_launches": int(launches_timed),
+            "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu,
+            "fisher_trace": float(np.trace(Ftot.fisher_matrix)),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

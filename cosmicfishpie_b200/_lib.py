@@ -26,7 +26,8 @@ MAT_LNP, MAT_DERIVS = 1, 2
 
 EXPORTS = [
     "cfp_abi_version", "cfp_last_error", "cfp_ctx_create", "cfp_ctx_destroy", "cfp_ctx_sync",
-    "cfp_ctx_launch_count", "cfp_ctx_last_run_ms", "cfp_bank_upload", "cfp_bank_free", "cfp_bank_eval",
+    "cfp_ctx_launch_count", "cfp_ctx_last_run_ms", "cfp_peak_fp64", "cfp_spectro_plan_kernel_ms",
+    "cfp_photo_plan_kernel_ms", "cfp_bank_upload", "cfp_bank_free", "cfp_bank_eval",
     "cfp_spectro_plan_create", "cfp_spectro_plan_destroy", "cfp_spectro_plan_set_slice", "cfp_spectro_plan_run",
     "cfp_spectro_plan_fisher_d", "cfp_spectro_plan_fetch", "cfp_photo_plan_create", "cfp_photo_plan_destroy",
     "cfp_photo_plan_set_slice", "cfp_photo_plan_run", "cfp_photo_plan_fisher_d", "cfp_photo_plan_fetch",
@@ -66,6 +67,11 @@ def load():
     lib.cfp_ctx_launch_count.restype = C.c_int64
     lib.cfp_ctx_last_run_ms.argtypes = [_vp]
     lib.cfp_ctx_last_run_ms.restype = C.c_double
+    lib.cfp_peak_fp64.argtypes = [_vp, C.c_int, _dp]
+    lib.cfp_spectro_plan_kernel_ms.argtypes = [_vp]
+    lib.cfp_spectro_plan_kernel_ms.restype = C.c_double
+    lib.cfp_photo_plan_kernel_ms.argtypes = [_vp, C.c_int]
+    lib.cfp_photo_plan_kernel_ms.restype = C.c_double
     lib.cfp_bank_upload.argtypes = [_vp, _dp, C.c_size_t, _lp, C.c_int, C.c_int, C.POINTER(_vp)]
     lib.cfp_bank_free.argtypes = [_vp, _vp]
     lib.cfp_bank_eval.argtypes = [_vp, _vp, C.c_int, C.c_int, _dp, _dp, C.c_size_t, _dp]
@@ -134,6 +140,12 @@ class Context:
     @property
     def last_run_ms(self) -> float:
         return float(self.lib.cfp_ctx_last_run_ms(self.handle))
+
+    def peak_fp64(self, kind: int) -> float:
+        """Measured FP64 TFLOP/s: kind 0 = DFMA, 1 = DMMA."""
+        out = C.c_double(0.0)
+        _check(self.lib.cfp_peak_fp64(self.handle, int(kind), C.byref(out)), "cfp_peak_fp64")
+        return float(out.value)
 
     def close(self):
         if self.handle:
@@ -239,6 +251,9 @@ class SpectroPlan:
         _check(self.ctx.lib.cfp_spectro_plan_run(self.handle, int(materialize), _vp(stream) if stream else None),
                "cfp_spectro_plan_run")
 
+    def kernel_ms(self) -> float:
+        return float(self.ctx.lib.cfp_spectro_plan_kernel_ms(self.handle))
+
     def fisher_device_ptr(self) -> int:
         return int(self.ctx.lib.cfp_spectro_plan_fisher_d(self.handle) or 0)
 
@@ -294,6 +309,9 @@ class PhotoPlan:
 
     def run(self, stream: int = 0):
         _check(self.ctx.lib.cfp_photo_plan_run(self.handle, _vp(stream) if stream else None), "cfp_photo_plan_run")
+
+    def kernel_ms(self, which: int) -> float:
+        return float(self.ctx.lib.cfp_photo_plan_kernel_ms(self.handle, int(which)))
 
     def fisher_device_ptr(self) -> int:
         return int(self.ctx.lib.cfp_photo_plan_fisher_d(self.handle) or 0)

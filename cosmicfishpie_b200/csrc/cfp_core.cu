@@ -1,4 +1,5 @@
 // Context, error handling and the cosmology table bank of libcfp_b200.so.
+#include <algorithm>
 #include <cstdarg>
 
 #include "cfp_common.cuh"
@@ -141,4 +142,65 @@ extern "C" int cfp_bank_eval(cfp_ctx* ctx, const cfp_bank* bank, int cosmo, int 
   cudaFree(k_d);
   cudaFree(o_d);
   return rc;
+}
+
+// ------------------------------------------------------------------------------ FP64 peaks
+__global__ void __launch_bounds__(256) cfp_dfma_peak_kernel(double* out, int iters, double x) {
+  double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double y = x * 0.5;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
+    a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+__global__ void __launch_bounds__(256) cfp_dmma_peak_kernel(double* out, int iters, double x) {
+  double c[8][2];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) c[t][0] = c[t][1] = 0.0;
+  const double a = x + threadIdx.x * 1e-9, b = x - threadIdx.x * 1e-9;
+#pragma unroll 2
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c[t][0]), "+d"(c[t][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) s += c[t][0] + c[t][1];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int cfp_peak_fp64(cfp_ctx* ctx, int kind, double* tflops_out) {
+  CFP_REQUIRE(ctx && tflops_out, "NULL argument");
+  CFP_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (DFMA) or 1 (DMMA)");
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 8, threads = 256;
+  const int iters = kind == 0 ? 8192 : 2048;
+  double* out = nullptr;
+  CFP_CUDA(cudaMalloc((void**)&out, (size_t)blocks * threads * sizeof(double)));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {  // first rep warms up
+    CFP_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (kind == 0)
+      cfp_dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters, 0.999999);
+    else
+      cfp_dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters, 0.999999);
+    ctx->launches++;
+    CFP_CUDA(cudaGetLastError());
+    CFP_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    CFP_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CFP_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    const double flops = kind == 0 ? (double)blocks * threads * iters * 8.0 * 2.0
+                                   : (double)blocks * (threads / 32) * iters * 8.0 * 512.0;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaFree(out);
+  *tflops_out = best;
+  return CFP_OK;
 }

@@ -303,10 +303,13 @@ struct cfp_photo_plan {
   double *T_d = nullptr, *eff_d = nullptr, *U_d = nullptr, *V_d = nullptr, *cls_d = nullptr, *Y_d = nullptr;
   double *Fl_d = nullptr, *fisher_d = nullptr;
   bool ran = false;
+  cudaEvent_t kev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<void*> owned;
 };
 
 static void photo_free(cfp_photo_plan* p) {
+  for (auto& e : p->kev)
+    if (e) cudaEventDestroy(e);
   for (void* q : p->owned) cudaFree(q);
   delete p;
 }
@@ -417,6 +420,9 @@ extern "C" int cfp_photo_plan_run(cfp_photo_plan* pl, void* stream) {
   CFP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   CFP_CUDA(cudaEventRecord(ctx->ev0, st));
+  for (auto& e : pl->kev)
+    if (!e) CFP_CUDA(cudaEventCreate(&e));
+  CFP_CUDA(cudaEventRecord(pl->kev[0], st));
   {
     const size_t tot = (size_t)pl->NC * pl->Nl * pl->Nz;
     photo_sqrtp_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(
@@ -425,6 +431,7 @@ extern "C" int cfp_photo_plan_run(cfp_photo_plan* pl, void* stream) {
     ctx->launches++;
     CFP_CUDA(cudaGetLastError());
   }
+  CFP_CUDA(cudaEventRecord(pl->kev[1], st));
   {
     const int tot = pl->NC * pl->Nb;
     photo_eff_kernel<<<(tot + 63) / 64, 64, 0, st>>>(pl->NC, pl->Nb, pl->Nz, pl->kind_d, pl->ngal_d, pl->chi_d, pl->dz,
@@ -454,6 +461,7 @@ extern "C" int cfp_photo_plan_run(cfp_photo_plan* pl, void* stream) {
     P.lch = lch;
     P.cosmo_of_s = pl->cosmo_of_s_d, P.U = pl->U_d, P.V = pl->V_d, P.T = pl->T_d, P.wz = pl->wz_d;
     P.ell = pl->ell_d, P.lmin = pl->lmin_d, P.lmax = pl->lmax_d, P.cls = pl->cls_d;
+    CFP_CUDA(cudaEventRecord(pl->kev[2], st));
     const dim3 grid((nl + lch - 1) / lch, pl->S);
     const size_t smem = (size_t)2 * pl->nb * 8 * pl->ldz * sizeof(double);
     cudaError_t e = cudaSuccess;
@@ -474,6 +482,7 @@ extern "C" int cfp_photo_plan_run(cfp_photo_plan* pl, void* stream) {
       cfp_set_error("photo_cls_kernel launch: %s (smem %zu B)", cudaGetErrorString(e), smem);
       return CFP_ERR_CUDA;
     }
+    CFP_CUDA(cudaEventRecord(pl->kev[3], st));
   }
   {
     FishParams P;
@@ -483,11 +492,13 @@ extern "C" int cfp_photo_plan_run(cfp_photo_plan* pl, void* stream) {
     P.stw = pl->stw_d, P.stden = pl->stden_d, P.Y = pl->Y_d, P.Fl = pl->Fl_d;
     const int nbins = pl->l_end - pl->l_begin;
     const size_t smem = ((size_t)pl->Nb * pl->ldb + pl->Nb) * sizeof(double);
+    CFP_CUDA(cudaEventRecord(pl->kev[4], st));
     if (nbins > 0) {
       photo_fisher_kernel<<<nbins, 256, smem, st>>>(P);
       ctx->launches++;
       CFP_CUDA(cudaGetLastError());
     }
+    CFP_CUDA(cudaEventRecord(pl->kev[5], st));
     const int n = pl->npar * pl->npar;
     photo_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(pl->Fl_d, nbins, n, pl->fisher_d);
     ctx->launches++;
@@ -496,6 +507,15 @@ extern "C" int cfp_photo_plan_run(cfp_photo_plan* pl, void* stream) {
   CFP_CUDA(cudaEventRecord(ctx->ev1, st));
   pl->ran = true;
   return CFP_OK;
+}
+
+extern "C" double cfp_photo_plan_kernel_ms(cfp_photo_plan* pl, int which) {
+  if (!pl || !pl->ran || which < 0 || which > 2) return -1.0;
+  cudaSetDevice(pl->ctx->device);
+  if (cudaEventSynchronize(pl->kev[5]) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, pl->kev[2 * which], pl->kev[2 * which + 1]) != cudaSuccess) return -1.0;
+  return ms;
 }
 
 extern "C" const double* cfp_photo_plan_fisher_d(const cfp_photo_plan* plan) { return plan ? plan->fisher_d : nullptr; }

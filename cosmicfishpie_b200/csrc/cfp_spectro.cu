@@ -433,10 +433,13 @@ struct cfp_spectro_plan {
   double *partial_d = nullptr, *fisher_d = nullptr;
   double *lnp_d = nullptr, *derivs_d = nullptr, *veff_d = nullptr;
   bool ran = false;
+  cudaEvent_t kev0 = nullptr, kev1 = nullptr;
   std::vector<void*> owned;
 };
 
 static void spectro_free(cfp_spectro_plan* p) {
+  if (p->kev0) cudaEventDestroy(p->kev0);
+  if (p->kev1) cudaEventDestroy(p->kev1);
   for (void* q : p->owned) cudaFree(q);
   cudaFree(p->lnp_d);
   cudaFree(p->derivs_d);
@@ -640,6 +643,11 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
   P.nbar = pl->nbar_d, P.vol = pl->vol_d, P.blob = pl->bank->blob_d, P.tinfo = pl->tinfo_d, P.pp = pl->pp_d;
   P.pnw_k = pl->pnw_k_d, P.pnwpp = pl->pnwpp_d, P.partial = pl->partial_d;
   P.lnp = pl->lnp_d, P.derivs = pl->derivs_d, P.veff = pl->veff_d;
+  if (!pl->kev0) {
+    CFP_CUDA(cudaEventCreate(&pl->kev0));
+    CFP_CUDA(cudaEventCreate(&pl->kev1));
+  }
+  CFP_CUDA(cudaEventRecord(pl->kev0, st));
   const dim3 grid(gx, pl->Z);
   const size_t smem = std::max((size_t)(pl->nb * 8 * LD + TILE), (size_t)(TILE / 32) * T * 64) * sizeof(double);
   cudaError_t e = cudaSuccess;
@@ -656,12 +664,22 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
     cfp_set_error("spectro_fisher_kernel launch: %s", cudaGetErrorString(e));
     return CFP_ERR_CUDA;
   }
+  CFP_CUDA(cudaEventRecord(pl->kev1, st));
   spectro_reduce_kernel<<<pl->Z, 256, 0, st>>>(pl->partial_d, gx, pl->nb, pl->npar, pl->fisher_d);
   ctx->launches++;
   CFP_CUDA(cudaGetLastError());
   CFP_CUDA(cudaEventRecord(ctx->ev1, st));
   pl->ran = true;
   return CFP_OK;
+}
+
+extern "C" double cfp_spectro_plan_kernel_ms(cfp_spectro_plan* pl) {
+  if (!pl || !pl->ran || !pl->kev1) return -1.0;
+  cudaSetDevice(pl->ctx->device);
+  if (cudaEventSynchronize(pl->kev1) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, pl->kev0, pl->kev1) != cudaSuccess) return -1.0;
+  return ms;
 }
 
 extern "C" const double* cfp_spectro_plan_fisher_d(const cfp_spectro_plan* plan) {

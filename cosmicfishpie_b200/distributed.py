@@ -1,0 +1,74 @@
+"""Multi-GPU partition of one Fisher job: one process per GPU (torch.distributed), independent slices,
+one small all-reduce.
+
+The Fisher matrix is a sum over lattice cells (GCsp: flattened (mu,k) cells of every z-bin) or over
+multipole bins (photo), so each rank evaluates ALL stencil points on its own slice -- the tables are a few
+MB and are uploaded by every rank -- and the only exchange is the (Z x) npar x npar partial Fisher
+(<= 4 x 48 x 48 doubles), all-reduced once per probe over NCCL/NVLink.  Quadrature weights
+are separable and precomputed per node, so slices need no halo.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+
+
+def split_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [begin, end) of rank `rank` out of `world` over n units."""
+    base, rem = divmod(int(n), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def is_distributed() -> bool:
+    try:
+        import torch.distributed as dist
+
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    except Exception:
+        return False
+
+
+def rank_world() -> Tuple[int, int]:
+    if not is_distributed():
+        return 0, 1
+    import torch.distributed as dist
+
+    return dist.get_rank(), dist.get_world_size()
+
+
+def shard(fm, rank: int, world: int):
+    """Make `fm.compute()` evaluate only rank's slice and all-reduce the partial Fisher."""
+    fm._shard = (int(rank), int(world))
+    return fm
+
+
+def allreduce_numpy(a: np.ndarray) -> np.ndarray:
+    """Sum a host array over all ranks (NCCL: staged through the current CUDA device; gloo: CPU)."""
+    if not is_distributed():
+        return a
+    import torch
+    import torch.distributed as dist
+
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+    dist.all_reduce(t)
+    return t.numpy()
+
+
+class _DevArray:
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": "<f8",
+                                         "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+def device_view(ptr: int, shape, device: int = 0):
+    """Zero-copy torch view of a device buffer owned by a cfp plan (e.g. the Fisher result), so that
+    torch.distributed can all-reduce it in place on the launch stream."""
+    import torch
+
+    return torch.as_tensor(_DevArray(ptr, shape), device=torch.device("cuda", device))

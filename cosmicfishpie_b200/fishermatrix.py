@@ -28,6 +28,7 @@ import numpy as np
 
 from . import _lib
 from . import config as config_module
+from . import distributed as cdist
 from . import fisher_matrix as fm
 from . import spectro as spectro_mod
 
@@ -86,6 +87,7 @@ class FisherMatrix:
         self._spectro_job = None
         self._lazy = {}
         self.timings = {}
+        self._shard = None  # (rank, world) set by distributed.shard(); default: torch.distributed if initialised
 
     @property
     def ctx(self) -> _lib.Context:
@@ -153,8 +155,14 @@ class FisherMatrix:
         job = self.pk_deriv.build_job(self.pk_cov, freeparams=self.freeparams)
         self._spectro_job = job
         t1 = time()
-        plan = job.run(materialize=0)
+        rank, world = self._shard if self._shard is not None else cdist.rank_world()
+        plan = job.plan()
+        plan.set_slice(*cdist.split_range(self.Pk_ksamp * self.Pk_musamp, rank, world))
+        plan.run(materialize=0)
         Fz, _, _, _ = plan.fetch()
+        if world > 1:
+            Fz = cdist.allreduce_numpy(Fz)
+        plan.set_slice(0, self.Pk_ksamp * self.Pk_musamp)
         t2 = time()
         self.timings.update(host_prep_s=t1 - t0, device_s=t2 - t1, kernel_ms=self.ctx.last_run_ms)
         self.allparams = self.pk_deriv.fiducial_allpars
@@ -200,7 +208,8 @@ class FisherMatrix:
                                             fiducial_Cls=self.photo_obs_fid, configuration=self,
                                             stencil=self.stencil)
         t1 = time()
-        F = self.photo_LSS.compute_fisher(self.freeparams)
+        shard = self._shard if self._shard is not None else cdist.rank_world()
+        F = self.photo_LSS.compute_fisher(self.freeparams, shard=shard)
         t2 = time()
         self.timings.update(host_prep_s=self.photo_LSS.timings.get("host_prep_s", t1 - t0),
                             device_s=self.photo_LSS.timings.get("device_s", t2 - t1), kernel_ms=self.ctx.last_run_ms)

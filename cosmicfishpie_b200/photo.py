@@ -415,13 +415,24 @@ class PhotoCov:
         self._cls_all = None
         return self._job
 
-    def compute_fisher(self, freeparams=None) -> np.ndarray:
+    def compute_fisher(self, freeparams=None, shard=(0, 1)) -> np.ndarray:
+        """Fisher matrix of the job; `shard=(rank, world)` restricts this process to its slice of the
+        multipole bins and all-reduces the partial sums (cosmicfishpie_b200.distributed)."""
+        from . import distributed as cdist
+
         t0 = time()
         job = self.build_job(freeparams)
         plan = job.plan()
         t1 = time()
+        rank, world = shard
+        nbins = plan.Nl - 1
+        plan.set_slice(*cdist.split_range(nbins, rank, world))
         plan.run()
         F, _, _ = plan.fetch()
+        if world > 1:
+            F = cdist.allreduce_numpy(F)
+            plan.set_slice(0, nbins)
+            plan.run()  # every rank keeps the full C_ell set for compute_covmat()/compute_derivs()
         t2 = time()
         self.timings = {"host_prep_s": t1 - t0, "device_s": t2 - t1}
         self.fisher = F

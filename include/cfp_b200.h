@@ -52,6 +52,11 @@ int64_t cfp_ctx_launch_count(const cfp_ctx* ctx);
 /* device time [ms] of the last *_run call, measured with CUDA events on the launch stream */
 double cfp_ctx_last_run_ms(const cfp_ctx* ctx);
 
+/* Measured FP64 throughput of this GPU in TFLOP/s (the roofline denominators for the FP64 kernels;
+ * MEASURED_PEAKS.json records HBM and bf16 only): kind 0 = DFMA on the vector pipe, kind 1 = DMMA
+ * (mma.sync m8n8k4 f64, the FP64 tensor path).  Runs a ~20 ms register-resident microbenchmark. */
+int cfp_peak_fp64(cfp_ctx* ctx, int kind, double* tflops_out);
+
 /* ---------------------------------------------------------------- table bank ----------
  * Replaces the spline facade `cosmo_functions.matpow / f_growthrate / growth`
  * (cosmicfishpie/cosmology/cosmology.py:1682-1738, 1859-1877, 1911-1949) built by
@@ -160,6 +165,9 @@ int cfp_spectro_plan_set_slice(cfp_spectro_plan* plan, int64_t cell_begin, int64
 #define CFP_MAT_LNP 1
 #define CFP_MAT_DERIVS 2
 int cfp_spectro_plan_run(cfp_spectro_plan* plan, int materialize, void* stream);
+/* Device time [ms] of the fused lattice/derivative/Fisher kernel alone in the last run (CUDA events on
+ * the launch stream around that one launch); synchronises. */
+double cfp_spectro_plan_kernel_ms(cfp_spectro_plan* plan);
 /* Device pointer of the result F[Z][npar][npar] (valid until the plan is destroyed). */
 const double* cfp_spectro_plan_fisher_d(const cfp_spectro_plan* plan);
 /* Copy results to the host (synchronises). Any pointer may be NULL. */
@@ -210,6 +218,9 @@ int cfp_photo_plan_set_slice(cfp_photo_plan* plan, int l_begin, int l_end);
 /* Launch K3 (Limber kernels), K4 (FP64 tensor-core C_ell contraction) and K5 (Cholesky + trace
  * Fisher).  C_ell of all stencil points is always kept: cls[S][Nl][Nb][Nb]. */
 int cfp_photo_plan_run(cfp_photo_plan* plan, void* stream);
+/* Device time [ms] of one kernel of the last run: which = 0 Limber table, 1 C_ell contraction (DMMA),
+ * 2 Cholesky/trace Fisher; synchronises. */
+double cfp_photo_plan_kernel_ms(cfp_photo_plan* plan, int which);
 const double* cfp_photo_plan_fisher_d(const cfp_photo_plan* plan);
 /* fisher_h[npar][npar], cls_h[S][Nl][Nb][Nb] (signal only, no noise), sqrtp_h[NC][Nl][Nz] */
 int cfp_photo_plan_fetch(cfp_photo_plan* plan, double* fisher_h, double* cls_h, double* sqrtp_h);

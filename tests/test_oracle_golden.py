@@ -56,16 +56,17 @@ def test_spectro_oracle_bit_exact(obank, tag, free, settings, mzb):
     assert np.allclose(confidence_coefficient(0.6827) * s, g["sigma"], rtol=1e-12)
 
 
-@pytest.mark.parametrize("tag,obs,free,settings", [
-    ("gcph_small", ["GCph"], {"Omegam": 0.01, "sigma8": 0.01}, {"ell_sampling": 20}),
-    ("wl_cfg2", ["WL"], {p: 0.01 for p in P7[:5]}, None),
-    ("photo_3x2pt", ["WL", "GCph"], {p: 0.01 for p in P7}, None),
+@pytest.mark.parametrize("tag,obs,free,settings,spec", [
+    ("gcph_small", ["GCph"], {"Omegam": 0.01, "sigma8": 0.01}, {"ell_sampling": 20}, "Euclid-Photometric-ISTF-Pessimistic"),
+    ("wl_cfg2", ["WL"], {p: 0.01 for p in P7[:5]}, None, "Euclid-Photometric-ISTF-Pessimistic"),
+    ("photo_3x2pt", ["WL", "GCph"], {p: 0.01 for p in P7}, None, "Euclid-Photometric-ISTF-Pessimistic"),
+    ("photo_cfg3", ["WL", "GCph"], {p: 0.01 for p in P7}, None, "Euclid-Photometric-13bins-lmax5000"),
 ])
-def test_photo_oracle_bit_exact(obank, tag, obs, free, settings):
+def test_photo_oracle_bit_exact(obank, tag, obs, free, settings, spec):
     from cosmicfishpie_b200 import toy_tables as tt
     from oracle.photo import default_photo_bias, finish_photo_specs, photo_fisher
 
-    sp = finish_photo_specs(yaml.safe_load(open(os.path.join(SPECDIR, "Euclid-Photometric-ISTF-Pessimistic.yaml")))["specifications"])
+    sp = finish_photo_specs(yaml.safe_load(open(os.path.join(SPECDIR, spec + ".yaml")))["specifications"])
     lum = np.load(os.path.join(REPO, "cosmicfishpie_b200", "data", "lumratio.npy"))
     bias = default_photo_bias(sp) if "GCph" in obs else {}
     ia = dict(sp["IA_params"])

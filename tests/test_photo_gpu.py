@@ -11,6 +11,9 @@ CASES = {
     "gcph_small": dict(obs=["GCph"], free={"Omegam": 0.01, "sigma8": 0.01}, opts={"ell_sampling": 20}),
     "wl_cfg2": dict(obs=["WL"], free={p: 0.01 for p in P7[:5]}, opts={}),
     "photo_3x2pt": dict(obs=["WL", "GCph"], free={p: 0.01 for p in P7}, opts={}),
+    # BASELINE.json configs[2]: 13+13 bins, lmax 5000, 23 parameters (custom spec shipped in data/specs)
+    "photo_cfg3": dict(obs=["WL", "GCph"], free={p: 0.01 for p in P7}, opts={},
+                       spec="Euclid-Photometric-13bins-lmax5000"),
 }
 
 
@@ -19,8 +22,8 @@ def run_case(name, extfiles, tmp_path):
     from cosmicfishpie_b200.fishermatrix import FisherMatrix
 
     c = CASES[name]
-    opts = base_options(tmp_path, survey_name_photo="Euclid-Photometric-ISTF-Pessimistic", survey_name_spectro=False,
-                        **c["opts"])
+    opts = base_options(tmp_path, survey_name_photo=c.get("spec", "Euclid-Photometric-ISTF-Pessimistic"),
+                        survey_name_spectro=False, **c["opts"])
     fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars=dict(c["free"]), options=opts, observables=list(c["obs"]),
                       extfiles=extfiles, cosmoModel="w0waCDM", surveyName="Euclid")
     return fm, fm.compute()

@@ -212,6 +212,15 @@ def photo_3x2pt():
               save_derivs=("Omegam", "w0", "b1", "b7", "AIA", "betaIA"))
 
 
+@case
+def photo_cfg3():
+    """BASELINE cfg3: 3x2pt, 13+13 bins, lmax 5000, 7 cosmo + 13 b + 3 IA (custom spec YAML shipped in
+    cosmicfishpie_b200/data/specs, loaded by the reference through options['specs_dir'])."""
+    run_photo("photo_cfg3", ["WL", "GCph"], {p: 0.01 for p in PARS7},
+              options_extra={"specs_dir": os.path.join(REPO, "cosmicfishpie_b200", "data", "specs")},
+              photo_yaml="Euclid-Photometric-13bins-lmax5000", save_derivs=("Omegam", "b13", "etaIA"))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     os.makedirs(SCRATCH, exist_ok=True)
