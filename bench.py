@@ -294,6 +294,11 @@ def run_gpu(args):
     splan.set_slice(0, ncell)
     pplan.set_slice(0, nbins)
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_per_step, "kernel_ms": k_ms, "roofline": roof}))
+        return
+
     # ---- end to end through the public API, from host tables -----------------------------------------
     from cosmicfishpie_b200 import cosmology as ccos
 
@@ -382,6 +387,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--profile", action="store_true",
+                    help="resident-plan loop only (no e2e / CPU baseline): the command line used under ncu")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -30,12 +30,20 @@ constexpr int LDPAD = 4;        // row padding of the derivative tile (bank-conf
 constexpr int LD = TILE + LDPAD;
 constexpr int MAX_NB = 6;       // npar <= 48
 constexpr double INV_8PI2 = 0.012665147955292222;  // 1/(8 pi^2)
+constexpr int CUBIC_BLK = 6;    // doubles per cubic piece:  [lo, hi, c0, c1, c2, c3]
+constexpr int LIN_BLK = 4;      // doubles per linear piece: [lo, hi, y, slope]
 
-struct TabInfo {  // per (cosmology, table): knot window of the k-direction
-  int64_t off_brk;  // offset of ty[3] in the bank blob: breakpoints brk[0..nint]
-  int nint;         // number of polynomial pieces = ny - 7
-  int pad;
+// Everything the lattice loop needs for one (stencil point, z-bin), derived once by
+// spectro_setup_kernel instead of once per thread per cell.
+struct SDev {
+  double rqpar, rqper, dzH, bias, A1, A2, sigmap, I0, I12, svr2, fs8, invs8sq, khfac, bao, pshot, w0;
+  const double *blkA, *blkB, *blkN;  // piece tables of P_lin(k), f(k), P_nw(k) at this (cosmology, z)
+  int nA, nB, nN;                    // number of pieces
+  int flags;                         // SD_*
+  int par0;                          // parameter fed by this point with weight w0 (-1: none)
+  int csr0, csr1;                    // further (parameter, weight) pairs in the CSR arrays
 };
+enum { SD_OWN = 1, SD_QBIAS = 2, SD_SHARED_KNOTS = 4, SD_SRC = 8, SD_PSHOT = 16 };
 
 struct SpectroParams {
   int S, Z, Nmu, Nk, npar, nb, nnw, NC;
@@ -54,11 +62,14 @@ struct SpectroParams {
   const int* ps_bin;      // [npar]
   const int* dead;        // [npar][Z]
   const double *nbar, *vol;
-  const double* blob;     // bank blob (for breakpoints)
-  const TabInfo* tinfo;   // [NC][2]
-  const double* pp;       // [(c*Z+zb)*2+tab][maxint][4]
-  const double* pnw_k;    // [NC][nnw]
-  const double* pnwpp;    // [(c*Z+zb)][nnw][2]
+  const int64_t* desc;    // bank descriptors
+  int n_tables, tab_pl, tab_f;
+  const double* blob;
+  double* blk;            // [(c*Z+zb)*2+tab][maxint][CUBIC_BLK]
+  double* blknw;          // [(c*Z+zb)][nnw-1][LIN_BLK]
+  SDev* sdev;             // [Z][S]
+  int* work;              // [Z][S] stencil points to visit per bin, in order
+  int* nwork;             // [Z]
   double* partial;        // [Z][gridDim.x][T*64]
   double *lnp, *derivs, *veff;
 };
@@ -72,9 +83,9 @@ struct PrepParams {
   int tab[2];
   const double* zbin;   // [Z]
   double* dcoef;        // scratch [(c*Z+zb)*2+tab][maxncy]
-  double* pp;
+  double* blk;
   const double *pnw_k, *pnw_p;
-  double* pnwpp;
+  double* blknw;
 };
 
 __global__ void spectro_prepare_kernel(PrepParams P) {
@@ -84,13 +95,13 @@ __global__ void spectro_prepare_kernel(PrepParams P) {
   if (tab == 2) {
     const double* xk = P.pnw_k + (size_t)c * P.nnw;
     const double* yp = P.pnw_p + (size_t)job * P.nnw;
-    double* o = P.pnwpp + (size_t)job * P.nnw * 2;
-    for (int l = threadIdx.x; l < P.nnw; l += blockDim.x) {
+    double* o = P.blknw + (size_t)job * (P.nnw - 1) * LIN_BLK;
+    for (int l = threadIdx.x; l < P.nnw - 1; l += blockDim.x) {
       const double y0 = yp[l];
-      double sl = 0.0;
-      if (l + 1 < P.nnw) sl = (yp[l + 1] - y0) / (xk[l + 1] - xk[l]);
-      o[2 * l] = y0;
-      o[2 * l + 1] = sl;
+      o[LIN_BLK * l + 0] = xk[l];
+      o[LIN_BLK * l + 1] = xk[l + 1];
+      o[LIN_BLK * l + 2] = y0;
+      o[LIN_BLK * l + 3] = (yp[l + 1] - y0) / (xk[l + 1] - xk[l]);
     }
     return;
   }
@@ -115,7 +126,7 @@ __global__ void spectro_prepare_kernel(PrepParams P) {
   __syncthreads();
   // piece l (global knot index l = 3 + m): polynomial in u = k - ty[l]
   const int nint = ny - 7;
-  double* pp = P.pp + ((size_t)job * 2 + tab) * P.maxint * 4;
+  double* blk = P.blk + ((size_t)job * 2 + tab) * P.maxint * CUBIC_BLK;
   for (int m = threadIdx.x; m < nint; m += blockDim.x) {
     const int l = m + 3;
     const double tl = ty[l];
@@ -159,119 +170,177 @@ __global__ void spectro_prepare_kernel(PrepParams P) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) out[q] += cj * h[i][q];
     }
+    double* o = blk + (size_t)m * CUBIC_BLK;
+    o[0] = tl;
+    o[1] = ty[l + 1];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) pp[(size_t)m * 4 + q] = out[q];
+    for (int q = 0; q < 4; ++q) o[2 + q] = out[q];
+  }
+}
+
+// one thread per (z-bin, stencil point): derived scalars, table pointers, stencil feed; thread 0 of
+// each bin then builds the bin's work list
+__global__ void spectro_setup_kernel(SpectroParams P) {
+  const int zb = blockIdx.x;
+  for (int s = threadIdx.x; s < P.S; s += blockDim.x) {
+    const double* sc = P.scal + ((size_t)s * P.Z + zb) * CFP_SP_NSCAL;
+    SDev o;
+    const int c = (int)sc[CFP_SP_COSMO];
+    const double qpar = sc[CFP_SP_QPAR], qper = sc[CFP_SP_QPER];
+    o.rqpar = 1.0 / qpar;
+    o.rqper = 1.0 / qper;
+    o.dzH = sc[CFP_SP_DZ] * (1.0 / sc[CFP_SP_HUBBLE]);
+    o.bias = sc[CFP_SP_BIAS];
+    o.A1 = sc[CFP_SP_A1];
+    o.A2 = sc[CFP_SP_A2];
+    o.sigmap = sc[CFP_SP_SIGMAP];
+    o.I0 = sc[CFP_SP_I0];
+    o.I12 = 2.0 * sc[CFP_SP_I1] + sc[CFP_SP_I2];
+    o.svr2 = sc[CFP_SP_SVRESCALE] * sc[CFP_SP_SVRESCALE];
+    o.fs8 = sc[CFP_SP_FS8];
+    o.invs8sq = sc[CFP_SP_INVS8SQ];
+    o.khfac = sc[CFP_SP_KHFAC];
+    o.pshot = sc[CFP_SP_PSHOT];
+    o.bao = (P.flags & CFP_SPF_AP) ? 1.0 / (qper * qper * qpar) : 1.0;
+    const int64_t* dA = P.desc + ((size_t)c * P.n_tables + P.tab_pl) * CFP_BANK_DESC;
+    const int64_t* dB = P.desc + ((size_t)c * P.n_tables + P.tab_f) * CFP_BANK_DESC;
+    const size_t job = (size_t)c * P.Z + zb;
+    o.blkA = P.blk + (job * 2 + 0) * P.maxint * CUBIC_BLK;
+    o.blkB = P.blk + (job * 2 + 1) * P.maxint * CUBIC_BLK;
+    o.blkN = P.blknw + job * (P.nnw - 1) * LIN_BLK;
+    o.nA = (int)dA[1] - 7;
+    o.nB = (int)dB[1] - 7;
+    o.nN = P.nnw - 1;
+    bool shared = (dA[1] == dB[1]);
+    if (shared) {
+      const double* ta = P.blob + dA[3];
+      const double* tb = P.blob + dB[3];
+      for (int i = 0; i < (int)dA[1] && shared; ++i) shared = (ta[i] == tb[i]);
+    }
+    const bool own = (s == 0) || (P.alias[s * P.Z + zb] == s);
+    o.flags = (own ? SD_OWN : 0) | ((o.A1 != 0.0 || o.A2 != 0.0) ? SD_QBIAS : 0) | (shared ? SD_SHARED_KNOTS : 0) |
+              ((s == 0 || s == P.ps_src) ? SD_SRC : 0) | (o.pshot != 0.0 ? SD_PSHOT : 0);
+    // stencil feed: first live (parameter, weight) inline, the rest through the CSR arrays
+    o.par0 = -1;
+    o.w0 = 0.0;
+    o.csr0 = o.csr1 = 0;
+    const int j0 = P.st_ptr[s], j1 = P.st_ptr[s + 1];
+    int jj = j0;
+    for (; jj < j1; ++jj)
+      if (!P.dead[P.st_par[jj] * P.Z + zb]) {
+        o.par0 = P.st_par[jj];
+        o.w0 = P.st_w[jj];
+        ++jj;
+        break;
+      }
+    o.csr0 = jj;
+    o.csr1 = j1;
+    P.sdev[(size_t)zb * P.S + s] = o;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int s = 0; s < P.S; ++s) {
+      const SDev& o = P.sdev[(size_t)zb * P.S + s];
+      bool needed = (s == 0) || (s == P.ps_src) || (P.materialize & CFP_MAT_LNP) || (o.par0 >= 0);
+      if (needed) P.work[zb * P.S + n++] = s;
+    }
+    P.nwork[zb] = n;
   }
 }
 
 // ------------------------------------------------------------------ lattice evaluation
-struct SPoint {
-  double rqpar, rqper, dzH, bias, A1, A2, sigmap, I0, I1, I2, svr2, fs8, invs8sq, khfac, bao, pshot;
-  const double *brk_pl, *pp_pl, *brk_f, *pp_f, *brk_nw, *pp_nw;
-  int nint_pl, nint_f, nint_nw;
-  bool qbias;
-};
-
-__device__ __forceinline__ void load_spoint(const SpectroParams& P, int s, int zb, SPoint& o) {
-  const double* sc = P.scal + ((size_t)s * P.Z + zb) * CFP_SP_NSCAL;
-  const int c = (int)__ldg(sc + CFP_SP_COSMO);
-  const double qpar = __ldg(sc + CFP_SP_QPAR), qper = __ldg(sc + CFP_SP_QPER);
-  o.rqpar = 1.0 / qpar;
-  o.rqper = 1.0 / qper;
-  o.dzH = __ldg(sc + CFP_SP_DZ) * (1.0 / __ldg(sc + CFP_SP_HUBBLE));
-  o.bias = __ldg(sc + CFP_SP_BIAS);
-  o.A1 = __ldg(sc + CFP_SP_A1);
-  o.A2 = __ldg(sc + CFP_SP_A2);
-  o.qbias = (o.A1 != 0.0) || (o.A2 != 0.0);
-  o.sigmap = __ldg(sc + CFP_SP_SIGMAP);
-  o.I0 = __ldg(sc + CFP_SP_I0);
-  o.I1 = __ldg(sc + CFP_SP_I1);
-  o.I2 = __ldg(sc + CFP_SP_I2);
-  const double r = __ldg(sc + CFP_SP_SVRESCALE);
-  o.svr2 = r * r;
-  o.fs8 = __ldg(sc + CFP_SP_FS8);
-  o.invs8sq = __ldg(sc + CFP_SP_INVS8SQ);
-  o.khfac = __ldg(sc + CFP_SP_KHFAC);
-  o.pshot = __ldg(sc + CFP_SP_PSHOT);
-  o.bao = (P.flags & CFP_SPF_AP) ? 1.0 / (qper * qper * qpar) : 1.0;
-  const TabInfo ti0 = P.tinfo[c * 2 + 0], ti1 = P.tinfo[c * 2 + 1];
-  const size_t job = (size_t)c * P.Z + zb;
-  o.brk_pl = P.blob + ti0.off_brk;
-  o.nint_pl = ti0.nint;
-  o.pp_pl = P.pp + (job * 2 + 0) * P.maxint * 4;
-  o.brk_f = P.blob + ti1.off_brk;
-  o.nint_f = ti1.nint;
-  o.pp_f = P.pp + (job * 2 + 1) * P.maxint * 4;
-  o.brk_nw = P.pnw_k + (size_t)c * P.nnw;
-  o.nint_nw = P.nnw - 1;
-  o.pp_nw = P.pnwpp + job * P.nnw * 2;
-}
-
-// piece index j in [0, nint-1] with brk[j] <= x < brk[j+1] (clamped at both ends); `hint` < 0
-// means unknown.  Neighbouring stencil points / cells move by at most a piece or two.
-__device__ __forceinline__ int locate(const double* __restrict__ brk, int nint, double x, int hint) {
+// piece index j in [0, n-1] whose [lo, hi) contains x (clamped at both ends); hint < 0 = unknown.
+// Neighbouring stencil points / cells move by at most a piece or two.
+template <int STRIDE>
+__device__ __forceinline__ int locate(const double* __restrict__ blk, int n, double x, int hint, double& lo) {
   int j;
+  double2 b;
   if (hint < 0) {
-    int lo = 0, hi = nint - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (__ldg(brk + mid) <= x)
-        lo = mid;
+    int a = 0, c = n - 1;
+    while (a < c) {
+      const int mid = (a + c + 1) >> 1;
+      if (__ldg(blk + (size_t)mid * STRIDE) <= x)
+        a = mid;
       else
-        hi = mid - 1;
+        c = mid - 1;
     }
-    j = lo;
-  } else {
-    j = hint;
-    while (j < nint - 1 && x >= __ldg(brk + j + 1)) ++j;
-    while (j > 0 && x < __ldg(brk + j)) --j;
+    j = a;
+    lo = __ldg(blk + (size_t)j * STRIDE);
+    return j;
   }
+  j = hint;
+  b = __ldg(reinterpret_cast<const double2*>(blk + (size_t)j * STRIDE));
+  while (x >= b.y && j < n - 1) {
+    ++j;
+    b = __ldg(reinterpret_cast<const double2*>(blk + (size_t)j * STRIDE));
+  }
+  while (x < b.x && j > 0) {
+    --j;
+    b = __ldg(reinterpret_cast<const double2*>(blk + (size_t)j * STRIDE));
+  }
+  lo = b.x;
   return j;
 }
 
-__device__ __forceinline__ double eval_pobs(const SPoint& p, unsigned flags, double k, double mu, double smu,
-                                            int& hpl, int& hf, int& hnw) {
+__device__ __forceinline__ double cubic_at(const double* __restrict__ blk, int j, double u) {
+  const double2 c01 = __ldg(reinterpret_cast<const double2*>(blk + (size_t)j * CUBIC_BLK + 2));
+  const double2 c23 = __ldg(reinterpret_cast<const double2*>(blk + (size_t)j * CUBIC_BLK + 4));
+  return c01.x + u * (c01.y + u * (c23.x + u * c23.y));
+}
+
+// X = P_obs / exp(-err^2) and err^2 (so that ln P_obs = ln X - err^2 needs a single log and no exp)
+__device__ __forceinline__ double eval_x(const SDev& p, unsigned flags, double k, double mu, double smu, int& hA,
+                                         int& hB, int& hN, double& err2) {
   // spectroscopic redshift error on the pre-AP wavenumber (spectro_obs.py:476-506, 880-889)
   const double kerr = (flags & CFP_SPF_KH_BEFORE_ERR) ? k * p.khfac : k;
   const double err = p.dzH * (kerr * mu * p.rqpar);
-  const double ez = exp(-0.5 * err * err);
+  err2 = err * err;
   const double kk = k * p.khfac;
   double kap = kk, muap = mu;
   if (flags & CFP_SPF_AP) {  // spectro_obs.py:441-474
     const double kpar = kk * mu * p.rqpar;
     const double kper = kk * smu * p.rqper;
-    kap = sqrt(kpar * kpar + kper * kper);
-    muap = kpar / kap;
+    const double s2 = kpar * kpar + kper * kper;
+    const double r = rsqrt(s2);
+    kap = s2 * r;
+    muap = kpar * r;
   }
   const double mu2 = muap * muap;
   double bterm = p.bias;
-  if (p.qbias) bterm *= (1.0 + kap * kap * p.A2) / (1.0 + kap * p.A1);
+  if (p.flags & SD_QBIAS) bterm *= (1.0 + kap * kap * p.A2) / (1.0 + kap * p.A1);
   // tabulated P_lin(k'), f(k') (FITPACK clamps the argument to the knot range)
-  double x = fmin(fmax(kap, __ldg(p.brk_pl)), __ldg(p.brk_pl + p.nint_pl));
-  hpl = locate(p.brk_pl, p.nint_pl, x, hpl);
-  double u = x - __ldg(p.brk_pl + hpl);
-  const double* q = p.pp_pl + (size_t)hpl * 4;
-  const double pdd = (__ldg(q) + u * (__ldg(q + 1) + u * (__ldg(q + 2) + u * __ldg(q + 3)))) * p.invs8sq;
-  x = fmin(fmax(kap, __ldg(p.brk_f)), __ldg(p.brk_f + p.nint_f));
-  hf = locate(p.brk_f, p.nint_f, x, hf);
-  u = x - __ldg(p.brk_f + hf);
-  q = p.pp_f + (size_t)hf * 4;
-  const double fg = (__ldg(q) + u * (__ldg(q + 1) + u * (__ldg(q + 2) + u * __ldg(q + 3)))) * p.fs8;
-  const double kaiser = bterm + fg * mu2;  // spectro_obs.py:584-637
-  double fog = 1.0, pdw = pdd;
-  if (!(flags & CFP_SPF_LINEAR)) {
-    if (flags & CFP_SPF_FOG) {  // spectro_obs.py:639-676
-      const double t = kap * muap * p.sigmap;
-      fog = 1.0 / (1.0 + t * t);
-    }
-    // dewiggling, spectro_obs.py:699-722, 811-843; degree-1 spline with extrapolation
-    hnw = locate(p.brk_nw, p.nint_nw, kap, hnw);
-    const double pnw = (__ldg(p.pp_nw + 2 * hnw) + __ldg(p.pp_nw + 2 * hnw + 1) * (kap - __ldg(p.brk_nw + hnw))) * p.invs8sq;
-    const double sv2 = (p.I0 + 2.0 * mu2 * p.I1 + mu2 * p.I2) * p.svr2;
-    const double e = exp(-sv2 * kap * kap);
-    pdw = pdd * e + pnw * (1.0 - e);
+  double lo;
+  double x = fmin(fmax(kap, __ldg(p.blkA)), __ldg(p.blkA + (size_t)(p.nA - 1) * CUBIC_BLK + 1));
+  hA = locate<CUBIC_BLK>(p.blkA, p.nA, x, hA, lo);
+  double u = x - lo;
+  const double pdd = cubic_at(p.blkA, hA, u) * p.invs8sq;
+  if (p.flags & SD_SHARED_KNOTS) {
+    hB = hA;
+  } else {
+    x = fmin(fmax(kap, __ldg(p.blkB)), __ldg(p.blkB + (size_t)(p.nB - 1) * CUBIC_BLK + 1));
+    hB = locate<CUBIC_BLK>(p.blkB, p.nB, x, hB, lo);
+    u = x - lo;
   }
-  return p.bao * (kaiser * kaiser) * pdw * fog * (ez * ez) + p.pshot;
+  const double fg = cubic_at(p.blkB, hB, u) * p.fs8;
+  const double kaiser = bterm + fg * mu2;  // spectro_obs.py:584-637
+  double num = p.bao * (kaiser * kaiser);
+  if (!(flags & CFP_SPF_LINEAR)) {
+    // dewiggling, spectro_obs.py:699-722, 811-843; degree-1 spline with extrapolation
+    hN = locate<LIN_BLK>(p.blkN, p.nN, kap, hN, lo);
+    const double2 ys = __ldg(reinterpret_cast<const double2*>(p.blkN + (size_t)hN * LIN_BLK + 2));
+    const double pnw = (ys.x + ys.y * (kap - lo)) * p.invs8sq;
+    const double sv2 = (p.I0 + mu2 * p.I12) * p.svr2;
+    const double e = exp(-sv2 * (kap * kap));
+    num *= pnw + e * (pdd - pnw);  // pdd e + pnw (1 - e)
+    if (flags & CFP_SPF_FOG) {     // Lorentzian FoG, spectro_obs.py:639-676
+      const double t = kap * muap * p.sigmap;
+      num = num / (1.0 + t * t);
+    }
+  } else {
+    num *= pdd;
+  }
+  return num;
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -281,16 +350,26 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 template <int NB>
-__global__ void __launch_bounds__(TILE) spectro_fisher_kernel(SpectroParams P) {
+__global__ void __launch_bounds__(TILE, 2) spectro_fisher_kernel(SpectroParams P) {
   constexpr int T = NB * (NB + 1) / 2;
   extern __shared__ double smem[];
   double* sm_d = smem;                   // [NB*8][LD]
   double* sm_w = smem + NB * 8 * LD;     // [TILE]
+  SDev* sm_s = reinterpret_cast<SDev*>(sm_w + TILE);  // [S]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int zb = blockIdx.y;
   const int64_t ncell = P.cell_end - P.cell_begin;
   const int64_t ntile = (ncell + TILE - 1) / TILE;
   const int64_t lattice = (int64_t)P.Nmu * P.Nk;
+  {
+    const int nwords = P.S * (int)(sizeof(SDev) / sizeof(double));
+    const double* src = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S);
+    double* dst = reinterpret_cast<double*>(sm_s);
+    for (int i = tid; i < nwords; i += TILE) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int nwork = P.nwork[zb];
+  const int* work = P.work + zb * P.S;
 
   double acc[T][2];
 #pragma unroll
@@ -302,23 +381,26 @@ __global__ void __launch_bounds__(TILE) spectro_fisher_kernel(SpectroParams P) {
     const int64_t cell = P.cell_begin + tile * TILE + tid;
     const bool valid = cell < P.cell_end;
     const int mi = valid ? (int)(cell / P.Nk) : 0;
-    const int ki = valid ? (int)(cell % P.Nk) : 0;
+    const int ki = valid ? (int)(cell - (int64_t)mi * P.Nk) : 0;
     const double k = __ldg(P.k + ki), mu = __ldg(P.mu + mi), smu = __ldg(P.smu + mi);
+#pragma unroll 4
     for (int p = 0; p < NB * 8; ++p) sm_d[p * LD + tid] = 0.0;
-    int hpl = -1, hf = -1, hnw = -1;
+    int hA = -1, hB = -1, hN = -1;
     double P0 = 1.0, lnP0 = 0.0, Psrc = 1.0;
-    for (int s = 0; s < P.S; ++s) {
-      const bool own = (s == 0) || (__ldg(P.alias + s * P.Z + zb) == s);
-      const int j0 = __ldg(P.st_ptr + s), j1 = __ldg(P.st_ptr + s + 1);
-      bool needed = (s == 0) || (s == P.ps_src) || (P.materialize & CFP_MAT_LNP);
-      for (int j = j0; j < j1 && !needed; ++j) needed = !__ldg(P.dead + __ldg(P.st_par + j) * P.Z + zb);
-      if (!needed) continue;
-      double Pobs, lnP;
-      if (own) {
-        SPoint sp;
-        load_spoint(P, s, zb, sp);
-        Pobs = eval_pobs(sp, P.flags, k, mu, smu, hpl, hf, hnw);
-        lnP = log(Pobs);
+    for (int wi = 0; wi < nwork; ++wi) {
+      const int s = work[wi];
+      const SDev& sp = sm_s[s];
+      double lnP, Pobs = 0.0;
+      if (sp.flags & SD_OWN) {
+        double err2;
+        const double X = eval_x(sp, P.flags, k, mu, smu, hA, hB, hN, err2);
+        if (sp.flags & SD_PSHOT) {
+          Pobs = X * exp(-err2) + sp.pshot;
+          lnP = log(Pobs);
+        } else {
+          lnP = log(X) - err2;
+          if (sp.flags & SD_SRC) Pobs = exp(lnP);
+        }
       } else {
         Pobs = P0;
         lnP = lnP0;
@@ -329,9 +411,12 @@ __global__ void __launch_bounds__(TILE) spectro_fisher_kernel(SpectroParams P) {
       }
       if (s == P.ps_src) Psrc = Pobs;
       if ((P.materialize & CFP_MAT_LNP) && valid) P.lnp[((size_t)s * P.Z + zb) * lattice + cell] = lnP;
-      for (int j = j0; j < j1; ++j) {
-        const int par = __ldg(P.st_par + j);
-        if (!__ldg(P.dead + par * P.Z + zb)) sm_d[par * LD + tid] += __ldg(P.st_w + j) * lnP;
+      if (sp.par0 >= 0) {
+        sm_d[sp.par0 * LD + tid] += sp.w0 * lnP;
+        for (int j = sp.csr0; j < sp.csr1; ++j) {
+          const int par = __ldg(P.st_par + j);
+          if (!__ldg(P.dead + par * P.Z + zb)) sm_d[par * LD + tid] += __ldg(P.st_w + j) * lnP;
+        }
       }
     }
     // finish the derivatives of this cell
@@ -341,7 +426,7 @@ __global__ void __launch_bounds__(TILE) spectro_fisher_kernel(SpectroParams P) {
       if (pb >= 0)
         d = (pb == zb) ? 1.0 / Psrc : 0.0;  // spectro_cov.py:510-532
       else
-        d = __ldg(P.dead + par * P.Z + zb) ? 0.0 : sm_d[par * LD + tid] / __ldg(P.st_den + par);
+        d = sm_d[par * LD + tid] / __ldg(P.st_den + par);  // dead parameters accumulate nothing: exactly 0
       sm_d[par * LD + tid] = d;
       if ((P.materialize & CFP_MAT_DERIVS) && valid) P.derivs[((size_t)par * P.Z + zb) * lattice + cell] = d;
     }
@@ -428,8 +513,9 @@ struct cfp_spectro_plan {
   double *scal_d = nullptr, *pnw_k_d = nullptr, *pnw_p_d = nullptr, *nbar_d = nullptr, *vol_d = nullptr;
   double *st_w_d = nullptr, *st_den_d = nullptr, *zbin_d = nullptr;
   int *alias_d = nullptr, *ps_bin_d = nullptr, *st_ptr_d = nullptr, *st_par_d = nullptr, *dead_d = nullptr;
-  TabInfo* tinfo_d = nullptr;
-  double *pp_d = nullptr, *pnwpp_d = nullptr, *dcoef_d = nullptr;
+  double *blk_d = nullptr, *blknw_d = nullptr, *dcoef_d = nullptr;
+  SDev* sdev_d = nullptr;
+  int *work_d = nullptr, *nwork_d = nullptr;
   double *partial_d = nullptr, *fisher_d = nullptr;
   double *lnp_d = nullptr, *derivs_d = nullptr, *veff_d = nullptr;
   bool ran = false;
@@ -495,7 +581,6 @@ extern "C" int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S
   pl->cell_end = (int64_t)Nmu * Nk;
 
   // knot windows
-  std::vector<TabInfo> ti((size_t)NC * 2);
   int maxint = 1, maxncy = 1;
   for (int c = 0; c < NC; ++c)
     for (int t = 0; t < 2; ++t) {
@@ -505,9 +590,6 @@ extern "C" int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S
         spectro_free(pl);
         return CFP_ERR_INVALID;
       }
-      ti[c * 2 + t].off_brk = d[3] + 3;
-      ti[c * 2 + t].nint = (int)d[1] - 7;
-      ti[c * 2 + t].pad = 0;
       maxint = std::max(maxint, (int)d[1] - 7);
       maxncy = std::max(maxncy, (int)d[1] - 4);
     }
@@ -559,9 +641,11 @@ extern "C" int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S
   SP_UP(double, st_w.data(), st_w.size(), pl->st_w_d);
   SP_UP(int, dead.data(), dead.size(), pl->dead_d);
   SP_UP(double, zbin.data(), (size_t)Z, pl->zbin_d);
-  SP_UP(TabInfo, ti.data(), ti.size(), pl->tinfo_d);
-  SP_UP(double, nullptr, (size_t)NC * Z * 2 * maxint * 4, pl->pp_d);
-  SP_UP(double, nullptr, (size_t)NC * Z * nnw * 2, pl->pnwpp_d);
+  SP_UP(double, nullptr, (size_t)NC * Z * 2 * maxint * CUBIC_BLK, pl->blk_d);
+  SP_UP(double, nullptr, (size_t)NC * Z * (nnw - 1) * LIN_BLK, pl->blknw_d);
+  SP_UP(SDev, nullptr, (size_t)Z * S, pl->sdev_d);
+  SP_UP(int, nullptr, (size_t)Z * S, pl->work_d);
+  SP_UP(int, nullptr, (size_t)Z, pl->nwork_d);
   SP_UP(double, nullptr, (size_t)NC * Z * 2 * maxncy, pl->dcoef_d);
   SP_UP(double, nullptr, (size_t)Z * npar * npar, pl->fisher_d);
   // the uploads read caller-owned host memory asynchronously: finish them before returning
@@ -627,8 +711,8 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
   pp.NC = pl->NC, pp.Z = pl->Z, pp.nnw = pl->nnw, pp.maxint = pl->maxint, pp.maxncy = pl->maxncy;
   pp.blob = pl->bank->blob_d, pp.desc = pl->bank->desc_d, pp.n_tables = pl->bank->n_tables;
   pp.tab[0] = pl->tab_pl, pp.tab[1] = pl->tab_f;
-  pp.zbin = pl->zbin_d, pp.dcoef = pl->dcoef_d, pp.pp = pl->pp_d;
-  pp.pnw_k = pl->pnw_k_d, pp.pnw_p = pl->pnw_p_d, pp.pnwpp = pl->pnwpp_d;
+  pp.zbin = pl->zbin_d, pp.dcoef = pl->dcoef_d, pp.blk = pl->blk_d;
+  pp.pnw_k = pl->pnw_k_d, pp.pnw_p = pl->pnw_p_d, pp.blknw = pl->blknw_d;
   spectro_prepare_kernel<<<dim3(pl->NC * pl->Z, 3), 128, 0, st>>>(pp);
   ctx->launches++;
   CFP_CUDA(cudaGetLastError());
@@ -640,16 +724,22 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
   P.k = pl->k_d, P.mu = pl->mu_d, P.smu = pl->smu_d, P.wk = pl->wk_d, P.wmu = pl->wmu_d;
   P.scal = pl->scal_d, P.alias = pl->alias_d, P.st_ptr = pl->st_ptr_d, P.st_par = pl->st_par_d;
   P.st_w = pl->st_w_d, P.st_den = pl->st_den_d, P.ps_bin = pl->ps_bin_d, P.dead = pl->dead_d;
-  P.nbar = pl->nbar_d, P.vol = pl->vol_d, P.blob = pl->bank->blob_d, P.tinfo = pl->tinfo_d, P.pp = pl->pp_d;
-  P.pnw_k = pl->pnw_k_d, P.pnwpp = pl->pnwpp_d, P.partial = pl->partial_d;
+  P.nbar = pl->nbar_d, P.vol = pl->vol_d, P.blob = pl->bank->blob_d, P.desc = pl->bank->desc_d;
+  P.n_tables = pl->bank->n_tables, P.tab_pl = pl->tab_pl, P.tab_f = pl->tab_f;
+  P.blk = pl->blk_d, P.blknw = pl->blknw_d, P.sdev = pl->sdev_d, P.work = pl->work_d, P.nwork = pl->nwork_d;
+  P.partial = pl->partial_d;
   P.lnp = pl->lnp_d, P.derivs = pl->derivs_d, P.veff = pl->veff_d;
+  spectro_setup_kernel<<<pl->Z, 64, 0, st>>>(P);
+  ctx->launches++;
+  CFP_CUDA(cudaGetLastError());
   if (!pl->kev0) {
     CFP_CUDA(cudaEventCreate(&pl->kev0));
     CFP_CUDA(cudaEventCreate(&pl->kev1));
   }
   CFP_CUDA(cudaEventRecord(pl->kev0, st));
   const dim3 grid(gx, pl->Z);
-  const size_t smem = std::max((size_t)(pl->nb * 8 * LD + TILE), (size_t)(TILE / 32) * T * 64) * sizeof(double);
+  const size_t smem = std::max((size_t)(pl->nb * 8 * LD + TILE) * sizeof(double) + (size_t)pl->S * sizeof(SDev),
+                               (size_t)(TILE / 32) * T * 64 * sizeof(double));
   cudaError_t e = cudaSuccess;
   switch (pl->nb) {
     case 1: e = launch_fisher<1>(P, grid, smem, st); break;
