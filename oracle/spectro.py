@@ -199,6 +199,19 @@ class GalSpectro:
     def lnpobs_gg(self, z, k, mu):
         return np.log(self.observed_Pgg(z, k, mu))
 
+    def observed_P_gg_ij(self, z, k, mu):
+        """spectro_obs.py:985-1019 `observed_P_ij` for si = sj = "g" (the form the likelihood uses; same
+        physics as observed_Pgg, different order of the floating-point products)."""
+        err = self.spec_err_z(z, k, mu)
+        k = self.k_units_change(k)
+        k, mu = self.kmu_ap(z, k, mu)
+        bao = self.bao(z)
+        ka = self.kaiser(z, k, mu)
+        fog = self.fog(z, k, mu)
+        pdw = self.dewiggled(z, k, mu)
+        fac = ka * 1 * err * 1 + np.sqrt(0.0)
+        return bao * fog * pdw * fac * fac
+
 
 class SpectroCov:
     """spectro_cov.py:134-228 on the fiducial observable."""
@@ -241,7 +254,7 @@ class SpectroCov:
 
     def noisy_Pgg(self, z, k, mu):
         """spectro_cov.py:361-370 for si=sj='g' (observed_P_ij == observed_Pgg for gg with zero extra shot)."""
-        return self.obs.observed_Pgg(z, k, mu) + 1 / self.n_density(z)
+        return self.obs.observed_P_gg_ij(z, k, mu) + 1 / self.n_density(z)
 
 
 def spectro_fisher(bank, specs, settings, fiducial_cosmopars, spectrobiaspars, pshotpars, nonlinpars,

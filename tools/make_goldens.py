@@ -221,6 +221,80 @@ def photo_cfg3():
               photo_yaml="Euclid-Photometric-13bins-lmax5000", save_derivs=("Omegam", "b13", "etaIA"))
 
 
+LIKE_POINTS_PHOTO = {
+    "fid": {},
+    "nuis": {"b1": 1.02, "b7": 0.985, "AIA": 1.04, "etaIA": 0.97, "betaIA": 1.01},     # multiplicative shifts
+    "cosmo": {"Omegam": 1.01},
+    "both": {"h": 0.99, "b3": 1.03, "AIA": 0.95},
+}
+LIKE_POINTS_SPECTRO = {
+    "fid": {},
+    "nuis": {"lnbg_1": 1.01, "lnbg_4": 0.99},
+    "cosmo": {"h": 1.01},
+    "shot": {"Ps_2": ("abs", 35.0), "lnbg_3": 1.005, "w0": 0.99},
+}
+
+
+def _shift(allpars, shifts):
+    out = {}
+    for k, v in shifts.items():
+        out[k] = v[1] if isinstance(v, tuple) else allpars[k] * v
+    return out
+
+
+@case
+def like_photo():
+    """Photometric likelihood (3x2pt 10+10 bins): data cells and log-likelihood at a few parameter points."""
+    from cosmicfishpie.likelihood.photo_like import PhotometricLikelihood
+
+    fm = run_photo("_tmp_like_photo", ["WL", "GCph"], {p: 0.01 for p in PARS7})
+    os.remove(os.path.join(GOLD, "_tmp_like_photo.npz"))
+    with quiet():
+        like = PhotometricLikelihood(cosmo_data=fm)
+    out = {k: np.array(v) for k, v in like.data_obs.items()}
+    names, vals = [], []
+    allp = dict(fm.allparams)
+    for name, sh in LIKE_POINTS_PHOTO.items():
+        with quiet():
+            vals.append(like.loglike(param_dict=_shift(allp, sh)))
+        names.append(name)
+    out["point_names"] = np.array(names)
+    out["loglike"] = np.array(vals)
+    np.savez_compressed(os.path.join(GOLD, "like_photo.npz"), **out)
+    print("like_photo:", dict(zip(names, vals)))
+
+
+@case
+def like_spectro():
+    """Spectroscopic likelihood functions (spectro_like.py:25-233): wedges and Legendre multipoles."""
+    from cosmicfishpie.likelihood import spectro_like as sl
+
+    fm = run_gcsp("_tmp_like_spectro", {p: 0.01 for p in PARS7})
+    os.remove(os.path.join(GOLD, "_tmp_like_spectro.npz"))
+    # attribute the reference forgets to define (SURVEY 8a-L2')
+    fm.pk_cov.volume_survey_array = np.array([fm.pk_cov.volume_survey(i) for i in range(len(fm.zmids))])
+    with quiet():
+        data = sl.observable_Pgg(fm.pk_cov, fm)
+        pl_data = sl.legendre_Pgg(data, fm)
+        cov, icov = sl.compute_covariance_legendre(pl_data, fm)
+    out = {"data_strided": data[:, :, ::KSTRIDE], "pl_data_strided": pl_data[::KSTRIDE], "cov_strided": cov[::KSTRIDE]}
+    names, w, lg = [], [], []
+    allp = dict(fm.allparams)
+    for name, sh in LIKE_POINTS_SPECTRO.items():
+        with quiet():
+            th = sl.compute_theory_spectro(_shift(allp, sh), fm, "wedges")
+            w.append(sl.compute_wedge_chi2(data, th, fm))
+            lg.append(sl.compute_chi2_legendre(pl_data, sl.legendre_Pgg(th, fm), icov))
+        if name == "shot":
+            out["theory_shot_strided"] = th[:, :, ::KSTRIDE]
+        names.append(name)
+    out["point_names"] = np.array(names)
+    out["chi2_wedges"] = np.array(w)
+    out["chi2_legendre"] = np.array(lg)
+    np.savez_compressed(os.path.join(GOLD, "like_spectro.npz"), **out)
+    print("like_spectro wedges:", dict(zip(names, w)), "legendre:", dict(zip(names, lg)))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     os.makedirs(SCRATCH, exist_ok=True)
