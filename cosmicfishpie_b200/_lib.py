@@ -31,6 +31,7 @@ EXPORTS = [
     "cfp_spectro_plan_create", "cfp_spectro_plan_destroy", "cfp_spectro_plan_set_slice", "cfp_spectro_plan_run",
     "cfp_spectro_plan_fisher_d", "cfp_spectro_plan_fetch", "cfp_photo_plan_create", "cfp_photo_plan_destroy",
     "cfp_photo_plan_set_slice", "cfp_photo_plan_run", "cfp_photo_plan_fisher_d", "cfp_photo_plan_fetch",
+    "cfp_photo_plan_chi2", "cfp_spectro_plan_chi2", "cfp_cells_chi2", "cfp_wedge_chi2",
 ]
 
 
@@ -93,6 +94,10 @@ def load():
     lib.cfp_photo_plan_fisher_d.argtypes = [_vp]
     lib.cfp_photo_plan_fisher_d.restype = _vp
     lib.cfp_photo_plan_fetch.argtypes = [_vp, _dp, _dp, _dp]
+    lib.cfp_photo_plan_chi2.argtypes = [_vp, _dp, C.c_int, _ip, _ip, _dp, _dp, _vp]
+    lib.cfp_spectro_plan_chi2.argtypes = [_vp, _dp, _dp, _dp, _dp, _vp]
+    lib.cfp_cells_chi2.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, _ip, _ip, _dp, _dp]
+    lib.cfp_wedge_chi2.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("cfp_abi_version",):
@@ -146,6 +151,25 @@ class Context:
         out = C.c_double(0.0)
         _check(self.lib.cfp_peak_fp64(self.handle, int(kind), C.byref(out)), "cfp_peak_fp64")
         return float(out.value)
+
+    def cells_chi2(self, theory, data, blk_off, blk_n, blk_w) -> np.ndarray:
+        """theory [S][Nl][Nb][Nb], data [Nl][Nb][Nb] (noise included) -> chi2[S]  (cfp_cells_chi2)."""
+        theory, data = f64(theory), f64(data)
+        S, Nl, Nb = theory.shape[0], theory.shape[1], theory.shape[2]
+        off, n, w = i32(blk_off), i32(blk_n), f64(blk_w)
+        out = np.empty(S)
+        _check(self.lib.cfp_cells_chi2(self.handle, S, Nl, Nb, _p(theory), _p(data), off.size, _p(off, _ip), _p(n, _ip),
+                                       _p(w), _p(out)), "cfp_cells_chi2")
+        return out
+
+    def wedge_chi2(self, theory, data, k, wk, wmu, vol) -> np.ndarray:
+        """theory [S][Z][Nmu][Nk], data [Z][Nmu][Nk] -> chi2[S]  (cfp_wedge_chi2)."""
+        theory, data = f64(theory), f64(data)
+        S, Z, Nmu, Nk = theory.shape
+        out = np.empty(S)
+        _check(self.lib.cfp_wedge_chi2(self.handle, S, Z, Nmu, Nk, _p(theory), _p(data), _p(f64(k)), _p(f64(wk)),
+                                       _p(f64(wmu)), _p(f64(vol)), _p(out)), "cfp_wedge_chi2")
+        return out
 
     def close(self):
         if self.handle:
@@ -257,6 +281,17 @@ class SpectroPlan:
     def fisher_device_ptr(self) -> int:
         return int(self.ctx.lib.cfp_spectro_plan_fisher_d(self.handle) or 0)
 
+    def chi2(self, shot, data=None, shot_data=None, stream: int = 0) -> np.ndarray:
+        """Wedge chi^2 of every point of the plan against `data` (default: point 0 + noise)."""
+        shot = f64(shot)
+        assert shot.shape == (self.S, self.Z)
+        data = None if data is None else f64(data)
+        sd = None if shot_data is None else f64(shot_data)
+        out = np.empty(self.S)
+        _check(self.ctx.lib.cfp_spectro_plan_chi2(self.handle, _p(data), _p(shot), _p(sd), _p(out),
+                                                  _vp(stream) if stream else None), "cfp_spectro_plan_chi2")
+        return out
+
     def fetch(self, lnp=False, derivs=False):
         F = np.empty((self.Z, self.npar, self.npar))
         L = np.empty((self.S, self.Z, self.Nmu, self.Nk)) if lnp else None
@@ -315,6 +350,16 @@ class PhotoPlan:
 
     def fisher_device_ptr(self) -> int:
         return int(self.ctx.lib.cfp_photo_plan_fisher_d(self.handle) or 0)
+
+    def chi2(self, blk_off, blk_n, blk_w, data=None, stream: int = 0) -> np.ndarray:
+        """chi^2 of every point of the plan; blocks of tomographic rows with per-multipole weights."""
+        off, n, w = i32(blk_off), i32(blk_n), f64(blk_w)
+        assert w.shape == (off.size, self.Nl)
+        data = None if data is None else f64(data)
+        out = np.empty(self.S)
+        _check(self.ctx.lib.cfp_photo_plan_chi2(self.handle, _p(data), off.size, _p(off, _ip), _p(n, _ip), _p(w), _p(out),
+                                                _vp(stream) if stream else None), "cfp_photo_plan_chi2")
+        return out
 
     def fetch(self, cls=False, sqrtp=False):
         F = np.empty((self.npar, self.npar))

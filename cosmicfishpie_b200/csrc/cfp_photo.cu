@@ -288,6 +288,98 @@ __global__ void photo_reduce_kernel(const double* __restrict__ Fl, int nbins, in
   F[e] = s;
 }
 
+
+// ---------------------------------------------------------------------------- likelihood
+constexpr int CHI_WARPS = 4;
+
+// One warp per (point, multipole, block): q = tr(A^-1 B) + ln det A - lndetB - n, A = C_l(s) + N.
+// A is factorised (Cholesky) in shared memory, lane i then solves A y = b_i and keeps y_i.
+__global__ void __launch_bounds__(CHI_WARPS * 32) photo_chi2_kernel(
+    int S, int Nl, int Nb, int nblk, const int* __restrict__ blk_off, const int* __restrict__ blk_n,
+    const double* __restrict__ cls, const double* __restrict__ noise, const double* __restrict__ data,
+    const double* __restrict__ lndetB, int data_mode, int nmax, double* __restrict__ q) {
+  extern __shared__ double chism[];
+  const int CHI_LD = nmax | 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t unit = (size_t)blockIdx.x * CHI_WARPS + warp;
+  const size_t total = (size_t)S * Nl * nblk;
+  if (unit >= total) return;
+  const int b = (int)(unit % nblk);
+  const int il = (int)((unit / nblk) % Nl);
+  const int s = (int)(unit / ((size_t)nblk * Nl));
+  const int off = blk_off[b], n = blk_n[b];
+  double* L = chism + (size_t)warp * 2 * nmax * CHI_LD;
+  double* W = L + (size_t)nmax * CHI_LD;
+  const double* A = cls + ((size_t)s * Nl + il) * Nb * Nb;
+  const double* B = data + (size_t)il * Nb * Nb;
+  for (int e = lane; e < n * n; e += 32) {
+    const int i = e / n, j = e % n;
+    L[i * CHI_LD + j] = A[(size_t)(off + i) * Nb + off + j] + ((i == j) ? noise[off + i] : 0.0);
+    W[i * CHI_LD + j] = B[(size_t)(off + i) * Nb + off + j];
+  }
+  __syncwarp();
+  double lndet = 0.0;
+  for (int k = 0; k < n; ++k) {
+    const double d = sqrt(L[k * CHI_LD + k]);
+    lndet += log(d);
+    __syncwarp();
+    if (lane > k && lane < n) L[lane * CHI_LD + k] /= d;
+    if (lane == k) L[k * CHI_LD + k] = d;
+    __syncwarp();
+    if (lane > k && lane < n) {
+      const double lik = L[lane * CHI_LD + k];
+      for (int j = k + 1; j <= lane; ++j) L[lane * CHI_LD + j] -= lik * L[j * CHI_LD + k];
+    }
+    __syncwarp();
+  }
+  lndet *= 2.0;
+  double yi = 0.0;
+  if (lane < n) {
+    const int i = lane;
+    for (int r = 0; r < n; ++r) {  // forward: L m = b_i
+      double x = W[r * CHI_LD + i];
+      for (int k = 0; k < r; ++k) x -= L[r * CHI_LD + k] * W[k * CHI_LD + i];
+      W[r * CHI_LD + i] = x / L[r * CHI_LD + r];
+    }
+    for (int r = n - 1; r >= i; --r) {  // backward: L^T y = m, down to component i
+      double x = W[r * CHI_LD + i];
+      for (int k = r + 1; k < n; ++k) x -= L[k * CHI_LD + r] * W[k * CHI_LD + i];
+      x /= L[r * CHI_LD + r];
+      W[r * CHI_LD + i] = x;
+      if (r == i) yi = x;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) yi += __shfl_xor_sync(0xffffffffu, yi, o);
+  if (lane == 0) {
+    if (data_mode)  // setup pass on the data itself: store ln det B
+      q[unit] = lndet;
+    else
+      q[unit] = yi + lndet - lndetB[(size_t)il * nblk + b] - (double)n;
+  }
+}
+
+__global__ void photo_chi2_reduce_kernel(int S, int Nl, int nblk, const double* __restrict__ q,
+                                         const double* __restrict__ w, double* __restrict__ chi2) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double acc = 0.0;
+  for (int b = 0; b < nblk; ++b)
+    for (int l = 0; l < Nl; ++l) {
+      const double wl = w[(size_t)b * Nl + l];
+      if (wl != 0.0) acc += wl * q[((size_t)s * Nl + l) * nblk + b];
+    }
+  chi2[s] = acc;
+}
+
+__global__ void photo_add_noise_kernel(int Nl, int Nb, const double* __restrict__ cls0, const double* __restrict__ noise,
+                                       double* __restrict__ data) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Nl * Nb * Nb) return;
+  const int ij = e % (Nb * Nb);
+  data[e] = cls0[e] + ((ij / Nb == ij % Nb) ? noise[ij / Nb] : 0.0);
+}
+
 }  // namespace
 
 struct cfp_photo_plan {
@@ -414,12 +506,26 @@ static cudaError_t launch_cls(const ClsParams& P, dim3 grid, size_t smem, cudaSt
   return cudaGetLastError();
 }
 
+static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell);
+static int photo_run_fisher(cfp_photo_plan* pl, cudaStream_t st);
+
 extern "C" int cfp_photo_plan_run(cfp_photo_plan* pl, void* stream) {
   CFP_REQUIRE(pl != nullptr, "plan is NULL");
   cfp_ctx* ctx = pl->ctx;
   CFP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   CFP_CUDA(cudaEventRecord(ctx->ev0, st));
+  int rc = photo_run_cls(pl, st, false);
+  if (rc != CFP_OK) return rc;
+  rc = photo_run_fisher(pl, st);
+  if (rc != CFP_OK) return rc;
+  CFP_CUDA(cudaEventRecord(ctx->ev1, st));
+  pl->ran = true;
+  return CFP_OK;
+}
+
+static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
+  cfp_ctx* ctx = pl->ctx;
   for (auto& e : pl->kev)
     if (!e) CFP_CUDA(cudaEventCreate(&e));
   CFP_CUDA(cudaEventRecord(pl->kev[0], st));
@@ -453,8 +559,8 @@ extern "C" int cfp_photo_plan_run(cfp_photo_plan* pl, void* stream) {
   {
     ClsParams P;
     P.S = pl->S, P.Nl = pl->Nl, P.Nz = pl->Nz, P.Nb = pl->Nb, P.nb = pl->nb, P.ldz = pl->ldz, P.nz4 = pl->nz4;
-    P.l_begin = pl->l_begin;
-    P.l_end = std::min(pl->l_end + 1, pl->Nl);
+    P.l_begin = all_ell ? 0 : pl->l_begin;
+    P.l_end = all_ell ? pl->Nl : std::min(pl->l_end + 1, pl->Nl);
     const int nl = P.l_end - P.l_begin;
     int lch = std::max(CLS_WARPS, (nl * pl->S + 2 * ctx->sm_count - 1) / (2 * ctx->sm_count));
     lch = (lch + CLS_WARPS - 1) / CLS_WARPS * CLS_WARPS;
@@ -484,6 +590,11 @@ extern "C" int cfp_photo_plan_run(cfp_photo_plan* pl, void* stream) {
     }
     CFP_CUDA(cudaEventRecord(pl->kev[3], st));
   }
+  return CFP_OK;
+}
+
+static int photo_run_fisher(cfp_photo_plan* pl, cudaStream_t st) {
+  cfp_ctx* ctx = pl->ctx;
   {
     FishParams P;
     P.S = pl->S, P.Nl = pl->Nl, P.Nb = pl->Nb, P.npar = pl->npar, P.l_begin = pl->l_begin, P.l_end = pl->l_end;
@@ -504,7 +615,87 @@ extern "C" int cfp_photo_plan_run(cfp_photo_plan* pl, void* stream) {
     ctx->launches++;
     CFP_CUDA(cudaGetLastError());
   }
-  CFP_CUDA(cudaEventRecord(ctx->ev1, st));
+  return CFP_OK;
+}
+
+extern "C" int cfp_photo_plan_chi2(cfp_photo_plan* pl, const double* data_h, int nblk, const int32_t* blk_off_h,
+                                   const int32_t* blk_n_h, const double* blk_w_h, double* chi2_h, void* stream) {
+  CFP_REQUIRE(pl && blk_off_h && blk_n_h && blk_w_h && chi2_h, "NULL argument");
+  CFP_REQUIRE(nblk >= 1 && nblk <= 8, "1..8 blocks");
+  for (int b = 0; b < nblk; ++b)
+    CFP_REQUIRE(blk_n_h[b] >= 1 && blk_n_h[b] <= 32 && blk_off_h[b] >= 0 && blk_off_h[b] + blk_n_h[b] <= pl->Nb,
+                "block out of range (at most 32 rows per block)");
+  cfp_ctx* ctx = pl->ctx;
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const int S = pl->S, Nl = pl->Nl, Nb = pl->Nb;
+  int *off_d = nullptr, *n_d = nullptr;
+  double *w_d = nullptr, *data_d = nullptr, *lndet_d = nullptr, *q_d = nullptr, *chi2_d = nullptr;
+  int rc = CFP_OK;
+  auto cleanup = [&]() {
+    cudaFree(off_d), cudaFree(n_d), cudaFree(w_d), cudaFree(data_d), cudaFree(lndet_d), cudaFree(q_d), cudaFree(chi2_d);
+  };
+#define CHI_TRY(x)            \
+  do {                        \
+    rc = (x);                 \
+    if (rc != CFP_OK) {       \
+      cleanup();              \
+      return rc;              \
+    }                         \
+  } while (0)
+  CHI_TRY(cfp_upload(ctx, blk_off_h, (size_t)nblk, &off_d));
+  CHI_TRY(cfp_upload(ctx, blk_n_h, (size_t)nblk, &n_d));
+  CHI_TRY(cfp_upload(ctx, blk_w_h, (size_t)nblk * Nl, &w_d));
+  CHI_TRY(cfp_upload<double>(ctx, data_h, (size_t)Nl * Nb * Nb, &data_d));
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nl * nblk, &lndet_d));
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S * Nl * nblk, &q_d));
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d));
+  if (st != ctx->stream) cudaStreamSynchronize(ctx->stream);  // uploads ran on the context stream
+  cudaEventRecord(ctx->ev0, st);
+  CHI_TRY(photo_run_cls(pl, st, true));
+  if (!data_h) {
+    photo_add_noise_kernel<<<(Nl * Nb * Nb + 255) / 256, 256, 0, st>>>(Nl, Nb, pl->cls_d, pl->noise_d, data_d);
+    ctx->launches++;
+  }
+  int nmax = 1;
+  for (int b = 0; b < nblk; ++b) nmax = std::max(nmax, (int)blk_n_h[b]);
+  const size_t chi_smem = (size_t)CHI_WARPS * 2 * nmax * (nmax | 1) * sizeof(double);
+  if (cudaFuncSetAttribute(photo_chi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chi_smem) != cudaSuccess) {
+    cfp_set_error("cfp_photo_plan_chi2: cannot reserve %zu B of shared memory", chi_smem);
+    cleanup();
+    return CFP_ERR_CUDA;
+  }
+  // ln det of the data blocks: the same kernel on a zero-noise "theory" = data
+  double* zero_d = nullptr;
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nb, &zero_d));
+  if (st != ctx->stream) cudaStreamSynchronize(ctx->stream);
+  {
+    const size_t units = (size_t)Nl * nblk;
+    photo_chi2_kernel<<<(unsigned)((units + CHI_WARPS - 1) / CHI_WARPS), CHI_WARPS * 32, chi_smem, st>>>(
+        1, Nl, Nb, nblk, off_d, n_d, data_d, zero_d, data_d, nullptr, 1, nmax, lndet_d);
+    ctx->launches++;
+  }
+  {
+    const size_t units = (size_t)S * Nl * nblk;
+    photo_chi2_kernel<<<(unsigned)((units + CHI_WARPS - 1) / CHI_WARPS), CHI_WARPS * 32, chi_smem, st>>>(
+        S, Nl, Nb, nblk, off_d, n_d, pl->cls_d, pl->noise_d, data_d, lndet_d, 0, nmax, q_d);
+    ctx->launches++;
+    photo_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Nl, nblk, q_d, w_d, chi2_d);
+    ctx->launches++;
+  }
+  cudaEventRecord(ctx->ev1, st);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(chi2_h, chi2_d, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  if (e == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+  cudaFree(zero_d);
+  cleanup();
+#undef CHI_TRY
+  if (e != cudaSuccess) {
+    cfp_set_error("cfp_photo_plan_chi2: %s", cudaGetErrorString(e));
+    return CFP_ERR_CUDA;
+  }
   pl->ran = true;
   return CFP_OK;
 }
@@ -537,5 +728,65 @@ extern "C" int cfp_photo_plan_fetch(cfp_photo_plan* pl, double* fisher_h, double
     CFP_CUDA(cudaMemcpy(cls_h, pl->cls_d, (size_t)pl->S * pl->Nl * pl->Nb * pl->Nb * sizeof(double), cudaMemcpyDeviceToHost));
   if (sqrtp_h)
     CFP_CUDA(cudaMemcpy(sqrtp_h, pl->T_d, (size_t)pl->NC * pl->Nl * pl->Nz * sizeof(double), cudaMemcpyDeviceToHost));
+  return CFP_OK;
+}
+
+extern "C" int cfp_cells_chi2(cfp_ctx* ctx, int S, int Nl, int Nb, const double* theory_h, const double* data_h, int nblk,
+                              const int32_t* blk_off_h, const int32_t* blk_n_h, const double* blk_w_h, double* chi2_h) {
+  CFP_REQUIRE(ctx && theory_h && data_h && blk_off_h && blk_n_h && blk_w_h && chi2_h, "NULL argument");
+  CFP_REQUIRE(S >= 1 && Nl >= 1 && Nb >= 1 && nblk >= 1 && nblk <= 8, "bad dimensions");
+  int nmax = 1;
+  for (int b = 0; b < nblk; ++b) {
+    CFP_REQUIRE(blk_n_h[b] >= 1 && blk_n_h[b] <= 32 && blk_off_h[b] >= 0 && blk_off_h[b] + blk_n_h[b] <= Nb,
+                "block out of range (at most 32 rows per block)");
+    nmax = std::max(nmax, (int)blk_n_h[b]);
+  }
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int *off_d = nullptr, *n_d = nullptr;
+  double *w_d = nullptr, *th_d = nullptr, *data_d = nullptr, *zero_d = nullptr, *lndet_d = nullptr, *q_d = nullptr, *chi2_d = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(off_d), cudaFree(n_d), cudaFree(w_d), cudaFree(th_d), cudaFree(data_d), cudaFree(zero_d), cudaFree(lndet_d);
+    cudaFree(q_d), cudaFree(chi2_d);
+  };
+  int rc;
+#define CHI_TRY(x)      \
+  do {                  \
+    rc = (x);           \
+    if (rc != CFP_OK) { \
+      cleanup();        \
+      return rc;        \
+    }                   \
+  } while (0)
+  CHI_TRY(cfp_upload(ctx, blk_off_h, (size_t)nblk, &off_d));
+  CHI_TRY(cfp_upload(ctx, blk_n_h, (size_t)nblk, &n_d));
+  CHI_TRY(cfp_upload(ctx, blk_w_h, (size_t)nblk * Nl, &w_d));
+  CHI_TRY(cfp_upload(ctx, theory_h, (size_t)S * Nl * Nb * Nb, &th_d));
+  CHI_TRY(cfp_upload(ctx, data_h, (size_t)Nl * Nb * Nb, &data_d));
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nb, &zero_d));
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nl * nblk, &lndet_d));
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S * Nl * nblk, &q_d));
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d));
+#undef CHI_TRY
+  const size_t chi_smem = (size_t)CHI_WARPS * 2 * nmax * (nmax | 1) * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(photo_chi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chi_smem);
+  if (e == cudaSuccess) {
+    size_t units = (size_t)Nl * nblk;
+    photo_chi2_kernel<<<(unsigned)((units + CHI_WARPS - 1) / CHI_WARPS), CHI_WARPS * 32, chi_smem, st>>>(
+        1, Nl, Nb, nblk, off_d, n_d, data_d, zero_d, data_d, nullptr, 1, nmax, lndet_d);
+    units = (size_t)S * Nl * nblk;
+    photo_chi2_kernel<<<(unsigned)((units + CHI_WARPS - 1) / CHI_WARPS), CHI_WARPS * 32, chi_smem, st>>>(
+        S, Nl, Nb, nblk, off_d, n_d, th_d, zero_d, data_d, lndet_d, 0, nmax, q_d);
+    photo_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Nl, nblk, q_d, w_d, chi2_d);
+    ctx->launches += 3;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(chi2_h, chi2_d, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) {
+    cfp_set_error("cfp_cells_chi2: %s", cudaGetErrorString(e));
+    return CFP_ERR_CUDA;
+  }
   return CFP_OK;
 }

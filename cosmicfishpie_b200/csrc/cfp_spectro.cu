@@ -67,6 +67,7 @@ struct SpectroParams {
   const double* blob;
   double* blk;            // [(c*Z+zb)*2+tab][maxint][CUBIC_BLK]
   double* blknw;          // [(c*Z+zb)][nnw-1][LIN_BLK]
+  const int* shared_knots;  // [NC]
   SDev* sdev;             // [Z][S]
   int* work;              // [Z][S] stencil points to visit per bin, in order
   int* nwork;             // [Z]
@@ -86,6 +87,7 @@ struct PrepParams {
   double* blk;
   const double *pnw_k, *pnw_p;
   double* blknw;
+  int* shared_knots;    // [NC] 1 if P_lin and f share their k-knots
 };
 
 __global__ void spectro_prepare_kernel(PrepParams P) {
@@ -107,6 +109,14 @@ __global__ void spectro_prepare_kernel(PrepParams P) {
   }
   const int64_t* d = P.desc + ((size_t)c * P.n_tables + P.tab[tab]) * CFP_BANK_DESC;
   const int nx = (int)d[0], ny = (int)d[1];
+  if (tab == 0 && zb == 0) {  // do P_lin(z,k) and f(z,k) share their k-knots? (one piece search serves both)
+    const int64_t* d2 = P.desc + ((size_t)c * P.n_tables + P.tab[1]) * CFP_BANK_DESC;
+    int same = (d2[1] == d[1]);
+    if (same)
+      for (int i = threadIdx.x; i < ny; i += blockDim.x) same &= (P.blob[d[3] + i] == P.blob[d2[3] + i]);
+    same = __syncthreads_and(same);
+    if (threadIdx.x == 0) P.shared_knots[c] = same;
+  }
   const double* tx = P.blob + d[2];
   const double* ty = P.blob + d[3];
   const double* cf = P.blob + d[4];
@@ -211,12 +221,7 @@ __global__ void spectro_setup_kernel(SpectroParams P) {
     o.nA = (int)dA[1] - 7;
     o.nB = (int)dB[1] - 7;
     o.nN = P.nnw - 1;
-    bool shared = (dA[1] == dB[1]);
-    if (shared) {
-      const double* ta = P.blob + dA[3];
-      const double* tb = P.blob + dB[3];
-      for (int i = 0; i < (int)dA[1] && shared; ++i) shared = (ta[i] == tb[i]);
-    }
+    const bool shared = P.shared_knots[c] != 0;
     const bool own = (s == 0) || (P.alias[s * P.Z + zb] == s);
     o.flags = (own ? SD_OWN : 0) | ((o.A1 != 0.0 || o.A2 != 0.0) ? SD_QBIAS : 0) | (shared ? SD_SHARED_KNOTS : 0) |
               ((s == 0 || s == P.ps_src) ? SD_SRC : 0) | (o.pshot != 0.0 ? SD_PSHOT : 0);
@@ -238,7 +243,7 @@ __global__ void spectro_setup_kernel(SpectroParams P) {
     P.sdev[(size_t)zb * P.S + s] = o;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && !(P.materialize & 16)) {  // bit 4: batch (likelihood) mode needs no work list
     int n = 0;
     for (int s = 0; s < P.S; ++s) {
       const SDev& o = P.sdev[(size_t)zb * P.S + s];
@@ -498,6 +503,102 @@ __global__ void spectro_reduce_kernel(const double* __restrict__ partial, int nc
   }
 }
 
+
+// ---------------------------------------------------------------------------- likelihood (wedges)
+// data[zb][cell] = P_obs(stencil point 0) + 1/nbar + shot_data[zb]
+__global__ void __launch_bounds__(TILE) spectro_data_kernel(SpectroParams P, const double* __restrict__ shot_data,
+                                                            double* __restrict__ data) {
+  __shared__ SDev sp;
+  const int zb = blockIdx.y, tid = threadIdx.x;
+  if (tid < (int)(sizeof(SDev) / sizeof(double)))
+    reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S)[tid];
+  __syncthreads();
+  const int64_t lattice = (int64_t)P.Nmu * P.Nk;
+  const double extra = 1.0 / P.nbar[zb] + (shot_data ? shot_data[zb] : 0.0);
+  int hA = -1, hB = -1, hN = -1;
+  for (int64_t cell = (int64_t)blockIdx.x * TILE + tid; cell < lattice; cell += (int64_t)gridDim.x * TILE) {
+    const int mi = (int)(cell / P.Nk), ki = (int)(cell - (int64_t)mi * P.Nk);
+    double err2;
+    const double X = eval_x(sp, P.flags, __ldg(P.k + ki), __ldg(P.mu + mi), __ldg(P.smu + mi), hA, hB, hN, err2);
+    data[(size_t)zb * lattice + cell] = X * exp(-err2) + sp.pshot + extra;
+  }
+}
+
+// grid (gx, Z, S): partial[s][zb][cta] = sum over this CTA's cells of w (P_d - P_t)^2 / P_d^2
+__global__ void __launch_bounds__(TILE) spectro_chi2_kernel(SpectroParams P, const double* __restrict__ data,
+                                                            const double* __restrict__ shot, int s_begin,
+                                                            double* __restrict__ partial) {
+  __shared__ SDev sp;
+  __shared__ double red[TILE / 32];
+  const int zb = blockIdx.y, s = s_begin + blockIdx.z, tid = threadIdx.x;
+  if (tid < (int)(sizeof(SDev) / sizeof(double)))
+    reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S + s)[tid];
+  __syncthreads();
+  const int64_t lattice = (int64_t)P.Nmu * P.Nk;
+  const double extra = 1.0 / P.nbar[zb] + shot[(size_t)s * P.Z + zb];
+  const double pref = 2.0 * P.vol[zb] * INV_8PI2;  // spectro_like.py:162-178
+  int hA = -1, hB = -1, hN = -1;
+  double acc = 0.0;
+  for (int64_t cell = (int64_t)blockIdx.x * TILE + tid; cell < lattice; cell += (int64_t)gridDim.x * TILE) {
+    const int mi = (int)(cell / P.Nk), ki = (int)(cell - (int64_t)mi * P.Nk);
+    const double k = __ldg(P.k + ki);
+    double err2;
+    const double X = eval_x(sp, P.flags, k, __ldg(P.mu + mi), __ldg(P.smu + mi), hA, hB, hN, err2);
+    const double Pt = X * exp(-err2) + sp.pshot + extra;
+    const double Pd = __ldg(data + (size_t)zb * lattice + cell);
+    const double r = (Pd - Pt) / Pd;
+    acc += (__ldg(P.wmu + mi) * __ldg(P.wk + ki)) * (pref * k * k) * (r * r);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((tid & 31) == 0) red[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < TILE / 32; ++w) t += red[w];
+    partial[((size_t)s * P.Z + zb) * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// stand-alone wedge chi^2 on given lattices: grid (gx, Z, S)
+__global__ void __launch_bounds__(TILE) wedge_chi2_kernel(int Z, int Nmu, int Nk, const double* __restrict__ theory,
+                                                          const double* __restrict__ data, const double* __restrict__ k,
+                                                          const double* __restrict__ wk, const double* __restrict__ wmu,
+                                                          const double* __restrict__ vol, double* __restrict__ partial) {
+  __shared__ double red[TILE / 32];
+  const int zb = blockIdx.y, s = blockIdx.z, tid = threadIdx.x;
+  const int64_t lattice = (int64_t)Nmu * Nk;
+  const double pref = 2.0 * vol[zb] * INV_8PI2;
+  double acc = 0.0;
+  for (int64_t cell = (int64_t)blockIdx.x * TILE + tid; cell < lattice; cell += (int64_t)gridDim.x * TILE) {
+    const int mi = (int)(cell / Nk), ki = (int)(cell - (int64_t)mi * Nk);
+    const double kk = k[ki];
+    const double Pd = data[(size_t)zb * lattice + cell];
+    const double Pt = theory[((size_t)s * Z + zb) * lattice + cell];
+    const double r = (Pd - Pt) / Pd;
+    acc += (wmu[mi] * wk[ki]) * (pref * kk * kk) * (r * r);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((tid & 31) == 0) red[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < TILE / 32; ++w) t += red[w];
+    partial[((size_t)s * Z + zb) * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+__global__ void spectro_chi2_reduce_kernel(int S, int per, const double* __restrict__ partial, double* __restrict__ chi2) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double t = 0.0;
+  for (int i = 0; i < per; ++i) t += partial[(size_t)s * per + i];
+  chi2[s] = t;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------ plan
@@ -515,7 +616,7 @@ struct cfp_spectro_plan {
   int *alias_d = nullptr, *ps_bin_d = nullptr, *st_ptr_d = nullptr, *st_par_d = nullptr, *dead_d = nullptr;
   double *blk_d = nullptr, *blknw_d = nullptr, *dcoef_d = nullptr;
   SDev* sdev_d = nullptr;
-  int *work_d = nullptr, *nwork_d = nullptr;
+  int *work_d = nullptr, *nwork_d = nullptr, *shared_d = nullptr;
   double *partial_d = nullptr, *fisher_d = nullptr;
   double *lnp_d = nullptr, *derivs_d = nullptr, *veff_d = nullptr;
   bool ran = false;
@@ -646,6 +747,7 @@ extern "C" int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S
   SP_UP(SDev, nullptr, (size_t)Z * S, pl->sdev_d);
   SP_UP(int, nullptr, (size_t)Z * S, pl->work_d);
   SP_UP(int, nullptr, (size_t)Z, pl->nwork_d);
+  SP_UP(int, nullptr, (size_t)NC, pl->shared_d);
   SP_UP(double, nullptr, (size_t)NC * Z * 2 * maxncy, pl->dcoef_d);
   SP_UP(double, nullptr, (size_t)Z * npar * npar, pl->fisher_d);
   // the uploads read caller-owned host memory asynchronously: finish them before returning
@@ -683,6 +785,98 @@ static cudaError_t launch_fisher(const SpectroParams& P, dim3 grid, size_t smem,
   return cudaGetLastError();
 }
 
+static void spectro_fill_params(cfp_spectro_plan* pl, int materialize, SpectroParams& P) {
+  P.S = pl->S, P.Z = pl->Z, P.Nmu = pl->Nmu, P.Nk = pl->Nk, P.npar = pl->npar, P.nb = pl->nb, P.nnw = pl->nnw;
+  P.NC = pl->NC, P.flags = pl->flags, P.ps_src = pl->ps_src, P.materialize = materialize, P.maxint = pl->maxint;
+  P.cell_begin = pl->cell_begin, P.cell_end = pl->cell_end;
+  P.k = pl->k_d, P.mu = pl->mu_d, P.smu = pl->smu_d, P.wk = pl->wk_d, P.wmu = pl->wmu_d;
+  P.scal = pl->scal_d, P.alias = pl->alias_d, P.st_ptr = pl->st_ptr_d, P.st_par = pl->st_par_d;
+  P.st_w = pl->st_w_d, P.st_den = pl->st_den_d, P.ps_bin = pl->ps_bin_d, P.dead = pl->dead_d;
+  P.nbar = pl->nbar_d, P.vol = pl->vol_d, P.blob = pl->bank->blob_d, P.desc = pl->bank->desc_d;
+  P.n_tables = pl->bank->n_tables, P.tab_pl = pl->tab_pl, P.tab_f = pl->tab_f;
+  P.blk = pl->blk_d, P.blknw = pl->blknw_d, P.sdev = pl->sdev_d, P.work = pl->work_d, P.nwork = pl->nwork_d;
+  P.shared_knots = pl->shared_d;
+  P.partial = pl->partial_d;
+  P.lnp = pl->lnp_d, P.derivs = pl->derivs_d, P.veff = pl->veff_d;
+}
+
+static int spectro_prepare(cfp_spectro_plan* pl, const SpectroParams& P, cudaStream_t st) {
+  cfp_ctx* ctx = pl->ctx;
+  PrepParams pp;
+  pp.NC = pl->NC, pp.Z = pl->Z, pp.nnw = pl->nnw, pp.maxint = pl->maxint, pp.maxncy = pl->maxncy;
+  pp.blob = pl->bank->blob_d, pp.desc = pl->bank->desc_d, pp.n_tables = pl->bank->n_tables;
+  pp.tab[0] = pl->tab_pl, pp.tab[1] = pl->tab_f;
+  pp.zbin = pl->zbin_d, pp.dcoef = pl->dcoef_d, pp.blk = pl->blk_d;
+  pp.pnw_k = pl->pnw_k_d, pp.pnw_p = pl->pnw_p_d, pp.blknw = pl->blknw_d;
+  pp.shared_knots = pl->shared_d;
+  spectro_prepare_kernel<<<dim3(pl->NC * pl->Z, 3), 128, 0, st>>>(pp);
+  ctx->launches++;
+  CFP_CUDA(cudaGetLastError());
+  spectro_setup_kernel<<<pl->Z, 64, 0, st>>>(P);
+  ctx->launches++;
+  CFP_CUDA(cudaGetLastError());
+  return CFP_OK;
+}
+
+extern "C" int cfp_spectro_plan_chi2(cfp_spectro_plan* pl, const double* data_h, const double* shot_h,
+                                     const double* shot_data_h, double* chi2_h, void* stream) {
+  CFP_REQUIRE(pl && shot_h && chi2_h, "NULL argument");
+  cfp_ctx* ctx = pl->ctx;
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const int S = pl->S, Z = pl->Z;
+  const size_t lattice = (size_t)pl->Nmu * pl->Nk;
+  const int64_t ntile = (int64_t)((lattice + TILE - 1) / TILE);
+  // enough CTAs per (point, bin) to fill the GPU for small batches, few for large ones
+  int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ntile, (4 * (int64_t)ctx->sm_count + (int64_t)S * Z - 1) / ((int64_t)S * Z)));
+  double *data_d = nullptr, *shot_d = nullptr, *sd_d = nullptr, *part_d = nullptr, *chi2_d = nullptr;
+  auto cleanup = [&]() { cudaFree(data_d), cudaFree(shot_d), cudaFree(sd_d), cudaFree(part_d), cudaFree(chi2_d); };
+  int rc;
+#define CHI_TRY(x)      \
+  do {                  \
+    rc = (x);           \
+    if (rc != CFP_OK) { \
+      cleanup();        \
+      return rc;        \
+    }                   \
+  } while (0)
+  CHI_TRY(cfp_upload<double>(ctx, data_h, (size_t)Z * lattice, &data_d));
+  CHI_TRY(cfp_upload(ctx, shot_h, (size_t)S * Z, &shot_d));
+  if (shot_data_h) CHI_TRY(cfp_upload(ctx, shot_data_h, (size_t)Z, &sd_d));
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S * Z * gx, &part_d));
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d));
+  if (st != ctx->stream) cudaStreamSynchronize(ctx->stream);
+  cudaEventRecord(ctx->ev0, st);
+  SpectroParams P;
+  spectro_fill_params(pl, 16, P);
+  CHI_TRY(spectro_prepare(pl, P, st));
+  if (!data_h) {
+    const int gd = (int)std::min<int64_t>(ntile, 2 * ctx->sm_count);
+    spectro_data_kernel<<<dim3(gd, Z), TILE, 0, st>>>(P, sd_d, data_d);
+    ctx->launches++;
+  }
+  for (int s0 = 0; s0 < S; s0 += 32768) {
+    const int ns = std::min(32768, S - s0);
+    spectro_chi2_kernel<<<dim3(gx, Z, ns), TILE, 0, st>>>(P, data_d, shot_d, s0, part_d);
+    ctx->launches++;
+  }
+  spectro_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Z * gx, part_d, chi2_d);
+  ctx->launches++;
+  cudaEventRecord(ctx->ev1, st);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(chi2_h, chi2_d, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  if (e == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+  cleanup();
+#undef CHI_TRY
+  if (e != cudaSuccess) {
+    cfp_set_error("cfp_spectro_plan_chi2: %s", cudaGetErrorString(e));
+    return CFP_ERR_CUDA;
+  }
+  return CFP_OK;
+}
+
 extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void* stream) {
   CFP_REQUIRE(pl != nullptr, "plan is NULL");
   cfp_ctx* ctx = pl->ctx;
@@ -707,31 +901,12 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
     pl->grid_x = gx;
   }
   CFP_CUDA(cudaEventRecord(ctx->ev0, st));
-  PrepParams pp;
-  pp.NC = pl->NC, pp.Z = pl->Z, pp.nnw = pl->nnw, pp.maxint = pl->maxint, pp.maxncy = pl->maxncy;
-  pp.blob = pl->bank->blob_d, pp.desc = pl->bank->desc_d, pp.n_tables = pl->bank->n_tables;
-  pp.tab[0] = pl->tab_pl, pp.tab[1] = pl->tab_f;
-  pp.zbin = pl->zbin_d, pp.dcoef = pl->dcoef_d, pp.blk = pl->blk_d;
-  pp.pnw_k = pl->pnw_k_d, pp.pnw_p = pl->pnw_p_d, pp.blknw = pl->blknw_d;
-  spectro_prepare_kernel<<<dim3(pl->NC * pl->Z, 3), 128, 0, st>>>(pp);
-  ctx->launches++;
-  CFP_CUDA(cudaGetLastError());
-
   SpectroParams P;
-  P.S = pl->S, P.Z = pl->Z, P.Nmu = pl->Nmu, P.Nk = pl->Nk, P.npar = pl->npar, P.nb = pl->nb, P.nnw = pl->nnw;
-  P.NC = pl->NC, P.flags = pl->flags, P.ps_src = pl->ps_src, P.materialize = materialize, P.maxint = pl->maxint;
-  P.cell_begin = pl->cell_begin, P.cell_end = pl->cell_end;
-  P.k = pl->k_d, P.mu = pl->mu_d, P.smu = pl->smu_d, P.wk = pl->wk_d, P.wmu = pl->wmu_d;
-  P.scal = pl->scal_d, P.alias = pl->alias_d, P.st_ptr = pl->st_ptr_d, P.st_par = pl->st_par_d;
-  P.st_w = pl->st_w_d, P.st_den = pl->st_den_d, P.ps_bin = pl->ps_bin_d, P.dead = pl->dead_d;
-  P.nbar = pl->nbar_d, P.vol = pl->vol_d, P.blob = pl->bank->blob_d, P.desc = pl->bank->desc_d;
-  P.n_tables = pl->bank->n_tables, P.tab_pl = pl->tab_pl, P.tab_f = pl->tab_f;
-  P.blk = pl->blk_d, P.blknw = pl->blknw_d, P.sdev = pl->sdev_d, P.work = pl->work_d, P.nwork = pl->nwork_d;
-  P.partial = pl->partial_d;
-  P.lnp = pl->lnp_d, P.derivs = pl->derivs_d, P.veff = pl->veff_d;
-  spectro_setup_kernel<<<pl->Z, 64, 0, st>>>(P);
-  ctx->launches++;
-  CFP_CUDA(cudaGetLastError());
+  spectro_fill_params(pl, materialize, P);
+  {
+    int rc = spectro_prepare(pl, P, st);
+    if (rc != CFP_OK) return rc;
+  }
   if (!pl->kev0) {
     CFP_CUDA(cudaEventCreate(&pl->kev0));
     CFP_CUDA(cudaEventCreate(&pl->kev1));
@@ -802,6 +977,47 @@ extern "C" int cfp_spectro_plan_fetch(cfp_spectro_plan* pl, double* fisher_h, do
   if (veff_h) {
     CFP_REQUIRE(pl->veff_d != nullptr, "veff was not materialised by the last run");
     CFP_CUDA(cudaMemcpy(veff_h, pl->veff_d, (size_t)pl->Z * lattice * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return CFP_OK;
+}
+
+extern "C" int cfp_wedge_chi2(cfp_ctx* ctx, int S, int Z, int Nmu, int Nk, const double* theory_h, const double* data_h,
+                              const double* k_h, const double* wk_h, const double* wmu_h, const double* vol_h,
+                              double* chi2_h) {
+  CFP_REQUIRE(ctx && theory_h && data_h && k_h && wk_h && wmu_h && vol_h && chi2_h, "NULL argument");
+  CFP_REQUIRE(S >= 1 && S <= 65535 && Z >= 1 && Nmu >= 1 && Nk >= 1, "bad dimensions");
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t lattice = (size_t)Nmu * Nk;
+  const int gx = (int)std::max<size_t>(1, std::min<size_t>((lattice + TILE - 1) / TILE, 64));
+  double *th_d = nullptr, *da_d = nullptr, *k_d = nullptr, *wk_d = nullptr, *wmu_d = nullptr, *vol_d = nullptr;
+  double *part_d = nullptr, *chi2_d = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(th_d), cudaFree(da_d), cudaFree(k_d), cudaFree(wk_d), cudaFree(wmu_d), cudaFree(vol_d), cudaFree(part_d);
+    cudaFree(chi2_d);
+  };
+  int rc = cfp_upload(ctx, theory_h, (size_t)S * Z * lattice, &th_d);
+  if (rc == CFP_OK) rc = cfp_upload(ctx, data_h, (size_t)Z * lattice, &da_d);
+  if (rc == CFP_OK) rc = cfp_upload(ctx, k_h, (size_t)Nk, &k_d);
+  if (rc == CFP_OK) rc = cfp_upload(ctx, wk_h, (size_t)Nk, &wk_d);
+  if (rc == CFP_OK) rc = cfp_upload(ctx, wmu_h, (size_t)Nmu, &wmu_d);
+  if (rc == CFP_OK) rc = cfp_upload(ctx, vol_h, (size_t)Z, &vol_d);
+  if (rc == CFP_OK) rc = cfp_upload<double>(ctx, nullptr, (size_t)S * Z * gx, &part_d);
+  if (rc == CFP_OK) rc = cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d);
+  if (rc != CFP_OK) {
+    cleanup();
+    return rc;
+  }
+  wedge_chi2_kernel<<<dim3(gx, Z, S), TILE, 0, st>>>(Z, Nmu, Nk, th_d, da_d, k_d, wk_d, wmu_d, vol_d, part_d);
+  spectro_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Z * gx, part_d, chi2_d);
+  ctx->launches += 2;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(chi2_h, chi2_d, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) {
+    cfp_set_error("cfp_wedge_chi2: %s", cudaGetErrorString(e));
+    return CFP_ERR_CUDA;
   }
   return CFP_OK;
 }

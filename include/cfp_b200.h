@@ -225,6 +225,45 @@ const double* cfp_photo_plan_fisher_d(const cfp_photo_plan* plan);
 /* fisher_h[npar][npar], cls_h[S][Nl][Nb][Nb] (signal only, no noise), sqrtp_h[NC][Nl][Nz] */
 int cfp_photo_plan_fetch(cfp_photo_plan* plan, double* fisher_h, double* cls_h, double* sqrtp_h);
 
+/* ---------------------------------------------------------------- batched likelihoods ---
+ * The stencil points of a plan double as a BATCH of parameter points (S = batch size): the same kernels
+ * evaluate the observables of every point, then a chi^2 kernel replaces the Fisher reduction.
+ *
+ * Photometric (replaces _cells_from_cls, _chi2_per_obs, PhotometricLikelihood.compute_chi2,
+ * cosmicfishpie/likelihood/photo_like.py:28-97,180-256): for every point s and multipole l and each block b
+ * (a contiguous range of tomographic rows [off, off+n)):
+ *     q = tr(A^-1 B) + ln det A - ln det B - n,   A = theory block (C_l + N), B = data block
+ * (identical to the reference's determinant-ratio form by Cramer's rule), chi2[s] = sum_b sum_l w[b][l] q.
+ * The caller folds (2l+1), the multipole quadrature of photo_like.py:189-204,90-96 and the f_sky factors into w.
+ *   data_h[Nl][Nb][Nb] : data spectra INCLUDING noise, or NULL = stencil point 0 plus the plan's noise
+ *   nblk, blk_off_h[nblk], blk_n_h[nblk] (n <= 32), blk_w_h[nblk][Nl]
+ *   chi2_h[S]          : output
+ */
+int cfp_photo_plan_chi2(cfp_photo_plan* plan, const double* data_h, int nblk, const int32_t* blk_off_h,
+                        const int32_t* blk_n_h, const double* blk_w_h, double* chi2_h, void* stream);
+
+/* Spectroscopic wedges (replaces observable_Pgg, compute_wedge_chi2, compute_theory_spectro,
+ * cosmicfishpie/likelihood/spectro_like.py:25-41,143-233): for every point s
+ *     chi2[s] = sum_z sum_cells wmu wk 2 k^2 V_z / (8 pi^2) (P_d - P_t)^2 / P_d^2,
+ *     P_t = P_obs(s) + 1/nbar_z + shot_h[s][z],   P_d = data
+ * with the plan's Simpson weights, volumes and number densities.
+ *   data_h[Z][Nmu][Nk] : data spectra including noise, or NULL = stencil point 0 + 1/nbar_z + shot_data_h[z]
+ *   shot_h[S][Z], shot_data_h[Z] (may be NULL = 0)
+ */
+int cfp_spectro_plan_chi2(cfp_spectro_plan* plan, const double* data_h, const double* shot_h,
+                          const double* shot_data_h, double* chi2_h, void* stream);
+
+/* Stand-alone forms on spectra the caller already holds (host arrays): the operator seams
+ * `_chi2_per_obs(cell_fid, cell_th, ells, dells)` (photo_like.py:78-97) and
+ * `compute_wedge_chi2(P_obs_data, P_obs_theory, cosmoFM)` (spectro_like.py:143-189).
+ *   theory_h[S][Nl][Nb][Nb], data_h[Nl][Nb][Nb] : spectra including noise; blocks/weights as above
+ *   theory_h[S][Z][Nmu][Nk], data_h[Z][Nmu][Nk], k_h[Nk], wk_h[Nk], wmu_h[Nmu], vol_h[Z]
+ */
+int cfp_cells_chi2(cfp_ctx* ctx, int S, int Nl, int Nb, const double* theory_h, const double* data_h, int nblk,
+                   const int32_t* blk_off_h, const int32_t* blk_n_h, const double* blk_w_h, double* chi2_h);
+int cfp_wedge_chi2(cfp_ctx* ctx, int S, int Z, int Nmu, int Nk, const double* theory_h, const double* data_h,
+                   const double* k_h, const double* wk_h, const double* wmu_h, const double* vol_h, double* chi2_h);
+
 #ifdef __cplusplus
 }
 #endif

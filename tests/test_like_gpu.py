@@ -1,0 +1,107 @@
+"""GPU parity: batched photometric and spectroscopic likelihoods vs goldens of the unmodified reference
+(tools/make_goldens.py cases like_photo / like_spectro)."""
+import numpy as np
+import pytest
+
+from conftest import base_options, golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+P7 = ["Omegam", "Omegab", "h", "ns", "sigma8", "w0", "wa"]
+POINTS_PHOTO = {
+    "fid": {},
+    "nuis": {"b1": 1.02, "b7": 0.985, "AIA": 1.04, "etaIA": 0.97, "betaIA": 1.01},
+    "cosmo": {"Omegam": 1.01},
+    "both": {"h": 0.99, "b3": 1.03, "AIA": 0.95},
+}
+POINTS_SPECTRO = {
+    "fid": {},
+    "nuis": {"lnbg_1": 1.01, "lnbg_4": 0.99},
+    "cosmo": {"h": 1.01},
+    "shot": {"Ps_2": ("abs", 35.0), "lnbg_3": 1.005, "w0": 0.99},
+}
+
+
+def shift(allp, sh):
+    return {k: (v[1] if isinstance(v, tuple) else allp[k] * v) for k, v in sh.items()}
+
+
+@pytest.fixture(scope="module")
+def photo_fm(extfiles, tmp_path_factory):
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    o = base_options(tmp_path_factory.mktemp("lp"), survey_name_photo="Euclid-Photometric-ISTF-Pessimistic",
+                     survey_name_spectro=False)
+    fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={p: 0.01 for p in P7}, options=o,
+                      observables=["WL", "GCph"], extfiles=extfiles)
+    fm.compute()
+    return fm
+
+
+@pytest.fixture(scope="module")
+def spectro_fm(extfiles, tmp_path_factory):
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={p: 0.01 for p in P7},
+                      options=base_options(tmp_path_factory.mktemp("ls")), observables=["GCsp"], extfiles=extfiles)
+    fm.compute()
+    return fm
+
+
+def test_photo_likelihood_matches_reference(photo_fm):
+    from cosmicfishpie_b200.likelihood import PhotometricLikelihood
+
+    g = golden("like_photo")
+    like = PhotometricLikelihood(cosmo_data=photo_fm)
+    for k in ("Cell_LL", "Cell_GG", "Cell_GL"):
+        assert rel_err(like.data_obs[k], g[k]) < 1e-12, k
+    assert np.array_equal(like.data_obs["ells"], g["ells"])
+    allp = dict(photo_fm.allparams)
+    dicts = [shift(allp, POINTS_PHOTO[str(n)]) for n in g["point_names"]]
+    single = np.array([like.loglike(param_dict=d) for d in dicts])
+    keys = sorted({k for d in dicts for k in d})
+    mat = np.array([[d.get(k, allp[k]) for k in keys] for d in dicts])
+    batch = like.loglike_batch(mat, keys=keys)
+    ref = g["loglike"]
+    assert abs(single[0]) < 1e-7 and abs(batch[0]) < 1e-7  # fiducial: reference gives 4.4e-11 (rounding noise)
+    assert np.max(np.abs(single[1:] - ref[1:]) / np.abs(ref[1:])) < 1e-9
+    assert np.max(np.abs(batch[1:] - ref[1:]) / np.abs(ref[1:])) < 1e-9
+    # operator seam: chi2 of an explicitly computed theory vector
+    th = like.compute_theory(dicts[1])
+    assert abs(-0.5 * like.compute_chi2(th) - ref[1]) / abs(ref[1]) < 1e-9
+
+
+def test_photo_likelihood_large_batch_is_consistent(photo_fm):
+    from cosmicfishpie_b200.likelihood import PhotometricLikelihood
+
+    like = PhotometricLikelihood(cosmo_data=photo_fm)
+    rng = np.random.default_rng(0)
+    keys = [f"b{i}" for i in range(1, 11)] + ["AIA", "betaIA", "etaIA"]
+    fid = np.array([photo_fm.allparams[k] for k in keys])
+    mat = fid * (1 + 0.03 * rng.standard_normal((300, len(keys))))
+    mat[0] = fid
+    ll = like.loglike_batch(mat, keys=keys)
+    assert ll.shape == (300,) and np.all(np.isfinite(ll)) and abs(ll[0]) < 1e-7 and np.all(ll[1:] < 0)
+    again = like.loglike_batch(mat[[5, 17, 123]], keys=keys)
+    assert np.array_equal(again, ll[[5, 17, 123]])  # deterministic, independent of batch composition
+
+
+def test_spectro_likelihood_matches_reference(spectro_fm):
+    from cosmicfishpie_b200 import likelihood as lk
+
+    g = golden("like_spectro")
+    like = lk.SpectroLikelihood(cosmoFM_data=spectro_fm)
+    assert rel_err(like.data_obs[:, :, ::16], g["data_strided"]) < 1e-13
+    allp = dict(spectro_fm.allparams)
+    dicts = [shift(allp, POINTS_SPECTRO[str(n)]) for n in g["point_names"]]
+    ref = g["chi2_wedges"]
+    chi2_batch = like.chi2_batch(dicts)
+    assert chi2_batch[0] < 1e-18 and ref[0] == 0.0
+    assert np.max(np.abs(chi2_batch[1:] - ref[1:]) / ref[1:]) < 1e-10
+    th = like.compute_theory(dicts[3])
+    assert rel_err(th[:, :, ::16], g["theory_shot_strided"]) < 1e-13
+    assert abs(like.compute_chi2(th) - ref[3]) / ref[3] < 1e-10
+    assert abs(like.loglike(param_dict=dicts[2]) + 0.5 * ref[2]) / ref[2] < 1e-10
+    assert abs(lk.loglike(param_vec=dicts[1], cosmoFM_data=spectro_fm) + 0.5 * ref[1]) / ref[1] < 1e-10
