@@ -164,7 +164,8 @@ class FisherMatrix:
             Fz = cdist.allreduce_numpy(Fz)
         plan.set_slice(0, self.Pk_ksamp * self.Pk_musamp)
         t2 = time()
-        self.timings.update(host_prep_s=t1 - t0, device_s=t2 - t1, kernel_ms=self.ctx.last_run_ms)
+        self.timings.update(host_prep_s=t1 - t0, device_s=t2 - t1,
+                            kernel_ms=getattr(getattr(plan, "ctx", None), "last_run_ms", float("nan")))
         self.allparams = self.pk_deriv.fiducial_allpars
         self.parslist = list(self.freeparams.keys())
         self.pk_fisher_per_bin = Fz
@@ -211,8 +212,10 @@ class FisherMatrix:
         shard = self._shard if self._shard is not None else cdist.rank_world()
         F = self.photo_LSS.compute_fisher(self.freeparams, shard=shard)
         t2 = time()
+        plan = self.photo_LSS._job.plan()
         self.timings.update(host_prep_s=self.photo_LSS.timings.get("host_prep_s", t1 - t0),
-                            device_s=self.photo_LSS.timings.get("device_s", t2 - t1), kernel_ms=self.ctx.last_run_ms)
+                            device_s=self.photo_LSS.timings.get("device_s", t2 - t1),
+                            kernel_ms=getattr(getattr(plan, "ctx", None), "last_run_ms", float("nan")))
         return F
 
     @property

@@ -208,3 +208,30 @@ def test_export_roundtrip_exact(extfiles, tmp_path):
     assert os.path.isfile(out.path.replace(".txt", "_specs.json"))
     fm.settings["outroot"] = ""
     assert fm.export_fisher(F) is None
+
+
+def test_likelihood_quadrature_weights_match_reference_sum():
+    """sum_l w[l] q[l] reproduces photo_like.py:90-96 with the inserted cut multipole of :189-204."""
+    from cosmicfishpie_b200.likelihood import quadrature_weights
+    from oracle.likelihood import ell_subset
+
+    ells = np.logspace(1, np.log10(1510), 100)
+    rng = np.random.default_rng(2)
+    q = rng.normal(size=100)
+    for limit in (750, 1500, 1510.0, 5000, None, 10):
+        n, e, d = ell_subset(ells, limit)
+        integrand = (2 * e + 1) * q[:n]
+        ref = np.sum(np.concatenate([((integrand[1:] + integrand[:-1]) / 2) * d[:-1], integrand[-1:] * d[-1:]]))
+        assert np.isclose(quadrature_weights(ells, limit) @ q, ref, rtol=1e-13), limit
+
+
+def test_split_range_partitions_exactly():
+    from cosmicfishpie_b200.distributed import split_range
+
+    for n in (0, 1, 7, 99, 1056897):
+        for world in (1, 2, 3, 8):
+            parts = [split_range(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1

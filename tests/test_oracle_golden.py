@@ -90,3 +90,49 @@ def test_photo_oracle_bit_exact(obank, tag, obs, free, settings, spec):
     for f in g.files:
         if f.startswith("dcl__"):
             assert np.array_equal(np.array([r["derivs"][f[5:]][k] for k in g["cl_keys"]]), g[f]), f
+
+
+LIKE_PHOTO = {"fid": {}, "nuis": {"b1": 1.02, "b7": 0.985, "AIA": 1.04, "etaIA": 0.97, "betaIA": 1.01},
+              "cosmo": {"Omegam": 1.01}, "both": {"h": 0.99, "b3": 1.03, "AIA": 0.95}}
+LIKE_SPECTRO = {"fid": {}, "nuis": {"lnbg_1": 1.01, "lnbg_4": 0.99}, "cosmo": {"h": 1.01},
+                "shot": {"Ps_2": ("abs", 35.0), "lnbg_3": 1.005, "w0": 0.99}}
+
+
+def test_photo_likelihood_oracle_bit_exact(obank):
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.likelihood import PhotoLikelihood
+    from oracle.photo import default_photo_bias, finish_photo_specs
+
+    sp = finish_photo_specs(yaml.safe_load(open(os.path.join(SPECDIR, "Euclid-Photometric-ISTF-Pessimistic.yaml")))["specifications"])
+    lum = np.load(os.path.join(REPO, "cosmicfishpie_b200", "data", "lumratio.npy"))
+    bias, ia = default_photo_bias(sp), dict(sp["IA_params"])
+    L = PhotoLikelihood(obank, sp, None, ["WL", "GCph"], dict(tt.FIDUCIAL), dict(sp["photo_z_params"]), ia, bias, lum)
+    g = golden("like_photo")
+    for k in ("Cell_LL", "Cell_GG", "Cell_GL"):
+        assert np.array_equal(L.data[k], g[k])
+    allp = {**tt.FIDUCIAL, **bias, **ia}
+    for name, ref in zip(g["point_names"], g["loglike"]):
+        par = {k: allp[k] * v for k, v in LIKE_PHOTO[str(name)].items()}
+        assert L.loglike(par) == ref, name
+
+
+def test_spectro_likelihood_oracle_bit_exact(obank):
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.likelihood import SpectroLikelihoodOracle
+
+    sp = _spectro_specs()
+    bias = dict(sp["sp_bias_parametrization"]["linear_log"])
+    ps = dict(sp["shot_noise_parametrization"]["constant"])
+    L = SpectroLikelihoodOracle(obank, sp, None, dict(tt.FIDUCIAL), bias, ps, {})
+    g = golden("like_spectro")
+    assert np.array_equal(L.data[:, :, ::16], g["data_strided"])
+    pld = L.legendre(L.data)
+    cov, icov = L.legendre_cov(pld)
+    assert np.array_equal(pld[::16], g["pl_data_strided"]) and np.array_equal(cov[::16], g["cov_strided"])
+    allp = {**tt.FIDUCIAL, **bias, **ps}
+    for i, name in enumerate(g["point_names"]):
+        par = {k: (v[1] if isinstance(v, tuple) else allp[k] * v) for k, v in LIKE_SPECTRO[str(name)].items()}
+        th = L.theory(par)
+        assert L.wedge_chi2(th) == g["chi2_wedges"][i]
+        assert L.legendre_chi2(pld, L.legendre(th), icov) == g["chi2_legendre"][i]
+    # the backend-free known answer of the reference's own test (tests/spectro_like_test.py:60-73): 5/(4 pi^2)
