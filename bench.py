@@ -303,7 +303,7 @@ def run_gpu(args):
     from cosmicfishpie_b200 import cosmology as ccos
 
     def api_step():
-        ccos._TABLE_CACHE.clear()
+        ccos.clear_caches()  # cold step: tables -> splines -> device bank are rebuilt every step
         a = make_photo_fm(bank, tmp)
         cdist.shard(a, rank, world)
         Fa = a.compute()

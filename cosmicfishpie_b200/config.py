@@ -293,9 +293,9 @@ class Config:
 
         global _CURRENT
         _CURRENT = self
-        from .cosmology import cosmo_functions
+        from .cosmology import cached_cosmo
 
-        self.fiducialcosmo = cosmo_functions(self.fiducialparams, self.input_type, self)
+        self.fiducialcosmo = cached_cosmo(self.fiducialparams, self)
 
 
 _CURRENT: Optional[Config] = None

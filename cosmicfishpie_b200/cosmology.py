@@ -98,9 +98,26 @@ def load_tables(external: dict, folder: str) -> dict:
     return out
 
 
-def _dcom_trapz(zi, hfunc):
-    zt = np.linspace(0.0, zi, 100)  # cosmology.py:36-55
-    return trapezoid(1 / hfunc(zt), zt)
+def _dcom_all(zgrid, hfunc):
+    """Comoving distance at every table redshift by the reference's 100-point trapezoid of 1/H
+    (cosmology.py:36-55, 1467-1469), all redshifts in one spline call (bit-identical to the per-z loop)."""
+    zt = np.array([np.linspace(0.0, zi, 100) for zi in zgrid])
+    return trapezoid(1 / hfunc(zt.ravel()).reshape(zt.shape), zt, axis=1)
+
+
+class _LazySpline:
+    """RectBivariateSpline built on first use (a GCsp job never touches P_nl, a photo job never f)."""
+
+    def __init__(self, zg, kg, table):
+        self._args = (zg, kg, table)
+        self._spl = None
+
+    def get(self):
+        if self._spl is None:
+            zg, kg, tab = self._args
+            self._spl = RectBivariateSpline(zg, kg, tab, kx=3, ky=3)
+            self._args = None
+        return self._spl
 
 
 class cosmo_functions:
@@ -144,16 +161,24 @@ class cosmo_functions:
         kg = kf * np.asarray(t["k"], float).flatten()
         self.zgrid, self.kgrid = zg, kg
         self.h_of_z = InterpolatedUnivariateSpline(zg, (1 / rf) * np.asarray(t["H"], float).flatten())
-        dcom = np.array([_dcom_trapz(zi, self.h_of_z) for zi in zg])
+        dcom = _dcom_all(zg, self.h_of_z)
         self.com_dist = InterpolatedUnivariateSpline(zg, dcom)
         self.ang_dist = InterpolatedUnivariateSpline(zg, dcom / (1 + zg))
-        self.D_growth_zk = RectBivariateSpline(zg, kg, t["D"], kx=3, ky=3)
-        self.f_growthrate_zk = RectBivariateSpline(zg, kg, t["f"], kx=3, ky=3)
+        self._lazy = {
+            "D_growth_zk": _LazySpline(zg, kg, t["D"]),
+            "f_growthrate_zk": _LazySpline(zg, kg, t["f"]),
+            "Pk_l": _LazySpline(zg, kg, pkf * np.asarray(t["Pl"], float)),
+            "Pk_nl": _LazySpline(zg, kg, pkf * np.asarray(t["Pnl"], float)),
+        }
         self.s8_of_z = InterpolatedUnivariateSpline(zg, np.asarray(t["s8"], float).flatten())
-        self.Pk_l = RectBivariateSpline(zg, kg, pkf * np.asarray(t["Pl"], float), kx=3, ky=3)
-        self.Pk_nl = RectBivariateSpline(zg, kg, pkf * np.asarray(t["Pnl"], float), kx=3, ky=3)
         self.results = self  # reference code reaches splines through `.results`
         self._nw_cache = {}
+
+    def __getattr__(self, name):  # the four (z,k) splines, fitted on first access
+        lazy = self.__dict__.get("_lazy")
+        if lazy is not None and name in lazy:
+            return lazy[name].get()
+        raise AttributeError(name)
 
     # --- host accessors --------------------------------------------------------------------
     def Hubble(self, z, physical=False):
@@ -212,23 +237,49 @@ class cosmo_functions:
         return self.nonwiggle_table(z, nonlinear)[2](k)
 
     # --- device export -----------------------------------------------------------------------
-    def bank_row(self):
-        """[P_lin, P_nl, f, D] bicubic (tx, ty, c) in the slot order of include/cfp_b200.h."""
+    def bank_row(self, slots=None):
+        """Bicubic (tx, ty, c) per table slot of include/cfp_b200.h; `slots` limits which tables are fitted."""
+        names = {_lib.TAB_PLIN: "Pk_l", _lib.TAB_PNL: "Pk_nl", _lib.TAB_F: "f_growthrate_zk", _lib.TAB_D: "D_growth_zk"}
         row = [None] * _lib.NTAB
-        for slot, spl in ((_lib.TAB_PLIN, self.Pk_l), (_lib.TAB_PNL, self.Pk_nl), (_lib.TAB_F, self.f_growthrate_zk),
-                          (_lib.TAB_D, self.D_growth_zk)):
-            tx, ty, c = spl.tck
-            row[slot] = (tx, ty, c)
+        for slot, name in names.items():
+            if slots is None or slot in slots:
+                row[slot] = getattr(self, name).tck
         return row
+
+
+_COSMO_CACHE: Dict[tuple, tuple] = {}
+
+
+def clear_caches():
+    """Forget parsed tables and fitted cosmologies (bench.py uses this to time cold end-to-end steps)."""
+    _TABLE_CACHE.clear()
+    _COSMO_CACHE.clear()
+
+
+def cached_cosmo(cosmopars, config) -> "cosmo_functions":
+    """Boltzmann input is computed once and cached (north_star): one spline facade per (table source, folder,
+    parameter values, units, no-wiggle settings), shared by every FisherMatrix / likelihood of the process."""
+    ext, st = config.external, config.settings
+    src = id(ext["tables"]) if ext.get("tables") is not None else os.path.abspath(ext["directory"])
+    key = (src, tuple(sorted((k, v) for k, v in cosmopars.items())), tuple(sorted(config.fiducialparams.items())),
+           tuple(ext["paramnames"]), tuple(ext["eps_values"]), ext.get("k-units"), ext.get("r-units"),
+           st["savgol_internalkmin"], st["savgol_internalsamples"], st["savgol_width"], st["savgol_polyorder"])
+    hit = _COSMO_CACHE.get(key)
+    if hit is not None and hit[0] is ext.get("tables"):  # identity check: id() values can be recycled
+        return hit[1]
+    c = cosmo_functions(dict(cosmopars), config.input_type, config)
+    _COSMO_CACHE[key] = (ext.get("tables"), c)
+    return c
 
 
 class CosmoSet:
     """The distinct cosmologies of one job (fiducial + stencil points), their host facades and the
     device bank.  Index 0 is always the fiducial."""
 
-    def __init__(self, config, ctx: Optional[_lib.Context] = None):
+    def __init__(self, config, ctx: Optional[_lib.Context] = None, slots=None):
         self.config = config
         self.ctx = ctx
+        self.slots = slots  # table slots the device bank needs (None = all four)
         self._by_key = {}
         self.cosmos = []
         self.add(config.fiducialparams, config.fiducialcosmo)
@@ -242,7 +293,7 @@ class CosmoSet:
         key = self._key(cosmopars)
         if key not in self._by_key:
             if cosmo is None:
-                cosmo = cosmo_functions(dict(cosmopars), self.config.input_type, self.config)
+                cosmo = cached_cosmo(cosmopars, self.config)
             self._by_key[key] = len(self.cosmos)
             self.cosmos.append(cosmo)
             self._bank = None
@@ -255,5 +306,5 @@ class CosmoSet:
         if self._bank is None:
             if self.ctx is None:
                 self.ctx = _lib.default_context()
-            self._bank = _lib.Bank(self.ctx, [c.bank_row() for c in self.cosmos])
+            self._bank = _lib.Bank(self.ctx, [c.bank_row(self.slots) for c in self.cosmos])
         return self._bank

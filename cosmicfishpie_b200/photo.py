@@ -267,7 +267,7 @@ class PhotoJob:
 def _cosmo_set_of(cfg) -> CosmoSet:
     cs = cfg.__dict__.get("_cosmo_set")
     if cs is None:
-        cs = CosmoSet(cfg)
+        cs = CosmoSet(cfg, slots=(_lib.TAB_PNL if cfg.settings["nonlinear"] else _lib.TAB_PLIN,))
         cfg.__dict__["_cosmo_set"] = cs
     return cs
 

@@ -287,7 +287,7 @@ class ComputeGalSpectro:
 def _cosmo_set_of(cfg) -> CosmoSet:
     cs = cfg.__dict__.get("_cosmo_set")
     if cs is None:
-        cs = CosmoSet(cfg)
+        cs = CosmoSet(cfg, slots=(_lib.TAB_PLIN, _lib.TAB_F))
         cfg.__dict__["_cosmo_set"] = cs
     return cs
 
