@@ -264,6 +264,8 @@ def run_gpu(args):
         splan.run(materialize=0, stream=sptr)
         kms.append(splan.kernel_ms())
     k_ms = float(np.mean(kms))
+    pplan.run(stream=sptr)
+    photo_ms = {"limber_table": pplan.kernel_ms(0), "cls_dmma": pplan.kernel_ms(1), "fisher": pplan.kernel_ms(2)}
     clk = clocks.stop() if rank == 0 else None
     job = fm_sp._spectro_job
     evals = int(sum(1 + np.count_nonzero(job.alias[1:, z]) for z in range(splan.Z))) * (ce - cb)
@@ -296,7 +298,8 @@ def run_gpu(args):
 
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms_per_step, "kernel_ms": k_ms, "roofline": roof}))
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_per_step, "kernel_ms": k_ms, "photo_kernel_ms": photo_ms,
+                              "roofline": roof}))
         return
 
     # ---- end to end through the public API, from host tables -----------------------------------------
@@ -414,7 +417,7 @@ def run_gpu(args):
                            "scaling": "weak", "what": "loglike_batch through the public API (host prep + H2D + kernels + "
                                                       "D2H), nuisance parameters drawn around the fiducial"},
             "gpu_launches": int(launches_timed),
-            "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu,
+            "roofline": roof, "roofline_hbm": roof_hbm, "photo_kernel_ms": photo_ms, "cpu_baseline": cpu,
             "fisher_trace": float(np.trace(Ftot.fisher_matrix)),
         }
         print(json.dumps(line))

@@ -42,29 +42,36 @@ __global__ void photo_sqrtp_kernel(const double* __restrict__ blob, const int64_
   T[idx] = v;
 }
 
-// one thread per (cosmology, WL row): eff = I1 - chi * I2 with backward cumulative trapezoids
+// one CTA per cosmology, one thread per WL row: eff = I1 - chi * I2 with backward cumulative trapezoids
+// (sequential in z like np.cumsum; chi and the n_i(z) rows are staged in shared memory first so the
+// 200-step recurrence does not pay a global-memory latency per step)
 __global__ void photo_eff_kernel(int NC, int Nb, int Nz, const int* __restrict__ kind, const double* __restrict__ ngal,
                                  const double* __restrict__ chi, double dz, double* __restrict__ eff) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= NC * Nb) return;
-  const int c = idx / Nb, a = idx % Nb;
-  double* e = eff + (size_t)idx * Nz;
-  if (kind[a] != 0) {
-    for (int i = 0; i < Nz; ++i) e[i] = 0.0;
-    return;
-  }
-  const double* n = ngal + (size_t)a * Nz;
-  const double* ch = chi + (size_t)c * Nz;
-  double I1 = 0.0, I2 = 0.0;
-  e[Nz - 1] = I1 - ch[Nz - 1] * I2;
-  double n_hi = n[Nz - 1], q_hi = n[Nz - 1] / ch[Nz - 1];
-  for (int i = Nz - 2; i >= 0; --i) {
-    const double n_lo = n[i], q_lo = n[i] / ch[i];
-    I1 = I1 + 0.5 * (n_hi + n_lo) * dz;
-    I2 = I2 + 0.5 * (q_hi + q_lo) * dz;
-    e[i] = I1 - ch[i] * I2;
-    n_hi = n_lo;
-    q_hi = q_lo;
+  extern __shared__ double effsm[];  // chi[Nz], ngal[Nb][Nz]
+  const int c = blockIdx.x;
+  double* sch = effsm;
+  double* sn = effsm + Nz;
+  for (int i = threadIdx.x; i < Nz; i += blockDim.x) sch[i] = chi[(size_t)c * Nz + i];
+  for (int i = threadIdx.x; i < Nb * Nz; i += blockDim.x) sn[i] = ngal[i];
+  __syncthreads();
+  for (int a = threadIdx.x; a < Nb; a += blockDim.x) {
+    double* e = eff + ((size_t)c * Nb + a) * Nz;
+    if (kind[a] != 0) {
+      for (int i = 0; i < Nz; ++i) e[i] = 0.0;
+      continue;
+    }
+    const double* n = sn + (size_t)a * Nz;
+    double I1 = 0.0, I2 = 0.0;
+    e[Nz - 1] = I1 - sch[Nz - 1] * I2;
+    double n_hi = n[Nz - 1], q_hi = n[Nz - 1] / sch[Nz - 1];
+    for (int i = Nz - 2; i >= 0; --i) {
+      const double n_lo = n[i], q_lo = n[i] / sch[i];
+      I1 = I1 + 0.5 * (n_hi + n_lo) * dz;
+      I2 = I2 + 0.5 * (q_hi + q_lo) * dz;
+      e[i] = I1 - sch[i] * I2;
+      n_hi = n_lo;
+      q_hi = q_lo;
+    }
   }
 }
 
@@ -191,92 +198,114 @@ struct FishParams {
   int S, Nl, Nb, npar, l_begin, l_end, ldb;
   const double* cls;  // [S][Nl][Nb][Nb]
   const double *ell, *noise, *sqrtfsky;
-  const double *stw, *stden;  // [npar][S], [npar]
+  const int* stp_ptr;   // CSR of the stencil per parameter: stencil points and weights
+  const int* stp_s;
+  const double* stp_w;
+  const double* stden;  // [npar]
   double* Y;          // scratch [Nl-1][npar][Nb*ldb]
   double* Fl;         // [Nl-1][npar][npar]
 };
 
-// One CTA per multipole bin (left-edge index li).
-__global__ void __launch_bounds__(256) photo_fisher_kernel(FishParams P) {
+// One CTA per multipole bin (left-edge index li).  All steps are data-parallel (no triangular-solve chains):
+//   1. A = C_l(fiducial) + N in shared memory, inverted in place by Gauss-Jordan (SPD, no pivoting needed;
+//      cond <= 2e4, the reference itself uses an explicit pinv)
+//   2. M_p = Phi dC_p (global scratch), Z_p = A^-1 M_p (shared memory when it fits, else global)
+//   3. F_pq = w_l sum_ij Z_p[i][j] Z_q[j][i] = w_l Tr(dC_p Sigma^-1 dC_q Sigma^-1), one warp per (p,q)
+constexpr int FISH_THREADS = 512;
+
+__global__ void __launch_bounds__(FISH_THREADS) photo_fisher_kernel(FishParams P, int z_in_smem) {
   extern __shared__ double sm[];
   const int Nb = P.Nb, ld = P.ldb;
-  double* sL = sm;              // [Nb][ld]  Cholesky factor (lower)
-  double* sInvD = sm + Nb * ld; // [Nb]
+  double* sA = sm;                 // [Nb][ld]
+  double* sPiv = sm + Nb * ld;     // [Nb] pivot column copy
+  double* sZ = sPiv + Nb;          // [npar][Nb][ld] if z_in_smem
   const int li = P.l_begin + blockIdx.x;
   const int tid = threadIdx.x;
   if (li >= P.l_end) return;
   const double* C0 = P.cls + ((size_t)0 * P.Nl + li) * Nb * Nb;
   for (int e = tid; e < Nb * Nb; e += blockDim.x) {
     const int i = e / Nb, j = e % Nb;
-    sL[i * ld + j] = C0[e] + ((i == j) ? P.noise[i] : 0.0);
+    sA[i * ld + j] = C0[e] + ((i == j) ? P.noise[i] : 0.0);
+  }
+  double* Ml = P.Y + (size_t)blockIdx.x * 2 * P.npar * Nb * ld;  // M_p, then (fallback) Z_p behind it
+  for (int e = tid; e < P.npar * Nb * Nb; e += blockDim.x) {
+    const int p = e / (Nb * Nb), ij = e % (Nb * Nb), i = ij / Nb, j = ij % Nb;
+    double acc = 0.0;
+    for (int q = P.stp_ptr[p]; q < P.stp_ptr[p + 1]; ++q)
+      acc += P.stp_w[q] * P.cls[((size_t)P.stp_s[q] * P.Nl + li) * Nb * Nb + ij];
+    Ml[(size_t)p * Nb * ld + i * ld + j] = (acc / P.stden[p]) * P.sqrtfsky[i];
   }
   __syncthreads();
-  // right-looking Cholesky, in place (lower triangle)
+  // in-place Gauss-Jordan inversion: every thread computes the new values of its (<= 8) elements from the
+  // old matrix into registers, the CTA synchronises, then they are written back
+  const int per = (Nb * Nb + blockDim.x - 1) / blockDim.x;  // uniform across the CTA (Nb <= 64 -> per <= 8)
   for (int k = 0; k < Nb; ++k) {
-    if (tid == 0) {
-      const double d = sqrt(sL[k * ld + k]);
-      sL[k * ld + k] = d;
-      sInvD[k] = 1.0 / d;
-    }
-    __syncthreads();
-    for (int i = k + 1 + tid; i < Nb; i += blockDim.x) sL[i * ld + k] *= sInvD[k];
-    __syncthreads();
-    const int m = Nb - k - 1;
-    for (int e = tid; e < m * m; e += blockDim.x) {
-      const int i = k + 1 + e / m, j = k + 1 + e % m;
-      if (j <= i) sL[i * ld + j] -= sL[i * ld + k] * sL[j * ld + k];
-    }
-    __syncthreads();
-  }
-  // Y_p = L^-1 (Phi dC_p) L^-T ; stage 1: X = L^-1 M (column tasks), stage 2: Y^T = L^-1 X^T (row tasks)
-  double* Yl = P.Y + (size_t)blockIdx.x * P.npar * Nb * ld;
-  const int ntask = P.npar * Nb;
-  for (int task = tid; task < ntask; task += blockDim.x) {
-    const int p = task / Nb, col = task % Nb;
-    double* Yp = Yl + (size_t)p * Nb * ld;
-    const double den = P.stden[p];
-    for (int i = 0; i < Nb; ++i) {
-      double acc = 0.0;
-      for (int s = 0; s < P.S; ++s) {
-        const double w = P.stw[(size_t)p * P.S + s];
-        if (w != 0.0) acc += w * P.cls[(((size_t)s * P.Nl + li) * Nb + i) * Nb + col];
+    const double piv = 1.0 / sA[k * ld + k];
+    double v[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int e = tid + it * blockDim.x;
+      if (it < per && e < Nb * Nb) {
+        const int i = e / Nb, j = e % Nb;
+        const double aik = sA[i * ld + k], akj = sA[k * ld + j];
+        if (i == k)
+          v[it] = (j == k) ? piv : akj * piv;
+        else if (j == k)
+          v[it] = -aik * piv;
+        else
+          v[it] = sA[i * ld + j] - aik * (akj * piv);
       }
-      double x = (acc / den) * P.sqrtfsky[i];  // M = Phi dC
-      for (int k = 0; k < i; ++k) x -= sL[i * ld + k] * Yp[k * ld + col];
-      Yp[i * ld + col] = x * sInvD[i];
     }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int e = tid + it * blockDim.x;
+      if (it < per && e < Nb * Nb) sA[(e / Nb) * ld + (e % Nb)] = v[it];
+    }
+    __syncthreads();
+  }
+  // Z_p = A^-1 M_p
+  double* Z = z_in_smem ? sZ : (Ml + (size_t)P.npar * Nb * ld);
+  for (int e = tid; e < P.npar * Nb * Nb; e += blockDim.x) {
+    const int p = e / (Nb * Nb), ij = e % (Nb * Nb), i = ij / Nb, j = ij % Nb;
+    const double* Mp = Ml + (size_t)p * Nb * ld;
+    double a0 = 0.0, a1 = 0.0;
+    int k = 0;
+    for (; k + 1 < Nb; k += 2) {
+      a0 += sA[i * ld + k] * Mp[k * ld + j];
+      a1 += sA[i * ld + k + 1] * Mp[(k + 1) * ld + j];
+    }
+    if (k < Nb) a0 += sA[i * ld + k] * Mp[k * ld + j];
+    Z[(size_t)p * Nb * ld + i * ld + j] = a0 + a1;
   }
   __syncthreads();
-  for (int task = tid; task < ntask; task += blockDim.x) {
-    const int p = task / Nb, row = task % Nb;
-    double* Yr = Yl + (size_t)p * Nb * ld + (size_t)row * ld;
-    for (int j = 0; j < Nb; ++j) {
-      double x = Yr[j];
-      for (int k = 0; k < j; ++k) x -= sL[j * ld + k] * Yr[k];
-      Yr[j] = x * sInvD[j];
-    }
-  }
-  __syncthreads();
-  // F_l[p][q] = w_l sum_ij Y_p[i][j] Y_q[j][i]; cosmicfish.py:681-683, 704, 723
+  // F_l[p][q] = w_l sum_ij Z_p[i][j] Z_q[j][i]; cosmicfish.py:681-683, 704, 723.  One warp per (p,q) pair.
   const double lc = 0.5 * P.ell[li] + 0.5 * P.ell[li + 1];
   const double wl = (lc + 0.5) * (P.ell[li + 1] - P.ell[li]);
   double* Fl = P.Fl + (size_t)blockIdx.x * P.npar * P.npar;
   const int npair = P.npar * (P.npar + 1) / 2;
-  for (int e = tid; e < npair; e += blockDim.x) {
+  const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  for (int e = warp; e < npair; e += nwarp) {
     int p = 0, acc = 0;
     while (acc + p + 1 <= e) {
       acc += p + 1;
       ++p;
     }
     const int q = e - acc;
-    const double* Yp = Yl + (size_t)p * Nb * ld;
-    const double* Yq = Yl + (size_t)q * Nb * ld;
+    const double* Zp = Z + (size_t)p * Nb * ld;
+    const double* Zq = Z + (size_t)q * Nb * ld;
     double s = 0.0;
-    for (int i = 0; i < Nb; ++i)
-      for (int j = 0; j < Nb; ++j) s += Yp[i * ld + j] * Yq[j * ld + i];
-    s *= wl;
-    Fl[p * P.npar + q] = s;
-    Fl[q * P.npar + p] = s;
+    for (int ij = lane; ij < Nb * Nb; ij += 32) {
+      const int i = ij / Nb, j = ij % Nb;
+      s += Zp[i * ld + j] * Zq[j * ld + i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      s *= wl;
+      Fl[p * P.npar + q] = s;
+      Fl[q * P.npar + p] = s;
+    }
   }
 }
 
@@ -391,7 +420,8 @@ struct cfp_photo_plan {
   int *cosmo_of_s_d = nullptr, *kind_d = nullptr;
   double *ell_d = nullptr, *z_d = nullptr, *chi_d = nullptr, *hub_d = nullptr, *wlpref_d = nullptr, *ngal_d = nullptr;
   double *bias_d = nullptr, *ia_d = nullptr, *lmin_d = nullptr, *lmax_d = nullptr, *noise_d = nullptr;
-  double *sqrtfsky_d = nullptr, *stw_d = nullptr, *stden_d = nullptr, *wz_d = nullptr;
+  double *sqrtfsky_d = nullptr, *stw_d = nullptr, *stden_d = nullptr, *wz_d = nullptr, *stp_w_d = nullptr;
+  int *stp_ptr_d = nullptr, *stp_s_d = nullptr;
   double *T_d = nullptr, *eff_d = nullptr, *U_d = nullptr, *V_d = nullptr, *cls_d = nullptr, *Y_d = nullptr;
   double *Fl_d = nullptr, *fisher_d = nullptr;
   bool ran = false;
@@ -465,12 +495,31 @@ extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, 
   PH_UP(double, stw_h, (size_t)npar * S, pl->stw_d);
   PH_UP(double, stden_h, (size_t)npar, pl->stden_d);
   PH_UP(double, wz.data(), (size_t)ldz, pl->wz_d);
+  {
+    std::vector<int> ptr(npar + 1, 0), ss;
+    std::vector<double> ww;
+    for (int p = 0; p < npar; ++p) {
+      for (int q = 0; q < S; ++q)
+        if (stw_h[(size_t)p * S + q] != 0.0) {
+          ss.push_back(q);
+          ww.push_back(stw_h[(size_t)p * S + q]);
+        }
+      ptr[p + 1] = (int)ss.size();
+    }
+    if (ss.empty()) {
+      ss.push_back(0);
+      ww.push_back(0.0);
+    }
+    PH_UP(int, ptr.data(), ptr.size(), pl->stp_ptr_d);
+    PH_UP(int, ss.data(), ss.size(), pl->stp_s_d);
+    PH_UP(double, ww.data(), ww.size(), pl->stp_w_d);
+  }
   PH_UP(double, nullptr, (size_t)NC * Nl * Nz, pl->T_d);
   PH_UP(double, nullptr, (size_t)NC * Nb * Nz, pl->eff_d);
   PH_UP(double, nullptr, (size_t)S * pl->nb * 8 * ldz, pl->U_d);
   PH_UP(double, nullptr, (size_t)S * pl->nb * 8 * ldz, pl->V_d);
   PH_UP(double, nullptr, (size_t)S * Nl * Nb * Nb, pl->cls_d);
-  PH_UP(double, nullptr, (size_t)(Nl - 1) * npar * Nb * pl->ldb, pl->Y_d);
+  PH_UP(double, nullptr, (size_t)(Nl - 1) * 2 * npar * Nb * pl->ldb, pl->Y_d);
   PH_UP(double, nullptr, (size_t)(Nl - 1) * npar * npar, pl->Fl_d);
   PH_UP(double, nullptr, (size_t)npar * npar, pl->fisher_d);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -539,9 +588,11 @@ static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
   }
   CFP_CUDA(cudaEventRecord(pl->kev[1], st));
   {
-    const int tot = pl->NC * pl->Nb;
-    photo_eff_kernel<<<(tot + 63) / 64, 64, 0, st>>>(pl->NC, pl->Nb, pl->Nz, pl->kind_d, pl->ngal_d, pl->chi_d, pl->dz,
-                                                      pl->eff_d);
+    const size_t esm = (size_t)(pl->Nb + 1) * pl->Nz * sizeof(double);
+    if (esm > 48 * 1024)
+      CFP_CUDA(cudaFuncSetAttribute(photo_eff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+    photo_eff_kernel<<<pl->NC, 64, esm, st>>>(pl->NC, pl->Nb, pl->Nz, pl->kind_d, pl->ngal_d, pl->chi_d, pl->dz,
+                                              pl->eff_d);
     ctx->launches++;
     CFP_CUDA(cudaGetLastError());
   }
@@ -600,12 +651,17 @@ static int photo_run_fisher(cfp_photo_plan* pl, cudaStream_t st) {
     P.S = pl->S, P.Nl = pl->Nl, P.Nb = pl->Nb, P.npar = pl->npar, P.l_begin = pl->l_begin, P.l_end = pl->l_end;
     P.ldb = pl->ldb;
     P.cls = pl->cls_d, P.ell = pl->ell_d, P.noise = pl->noise_d, P.sqrtfsky = pl->sqrtfsky_d;
-    P.stw = pl->stw_d, P.stden = pl->stden_d, P.Y = pl->Y_d, P.Fl = pl->Fl_d;
+    P.stp_ptr = pl->stp_ptr_d, P.stp_s = pl->stp_s_d, P.stp_w = pl->stp_w_d;
+    P.stden = pl->stden_d, P.Y = pl->Y_d, P.Fl = pl->Fl_d;
     const int nbins = pl->l_end - pl->l_begin;
-    const size_t smem = ((size_t)pl->Nb * pl->ldb + pl->Nb) * sizeof(double);
+    size_t smem = ((size_t)pl->Nb * pl->ldb + pl->Nb) * sizeof(double);
+    const size_t zsm = (size_t)pl->npar * pl->Nb * pl->ldb * sizeof(double);
+    const int z_in_smem = (smem + zsm <= 200 * 1024) ? 1 : 0;
+    if (z_in_smem) smem += zsm;
+    CFP_CUDA(cudaFuncSetAttribute(photo_fisher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CFP_CUDA(cudaEventRecord(pl->kev[4], st));
     if (nbins > 0) {
-      photo_fisher_kernel<<<nbins, 256, smem, st>>>(P);
+      photo_fisher_kernel<<<nbins, FISH_THREADS, smem, st>>>(P, z_in_smem);
       ctx->launches++;
       CFP_CUDA(cudaGetLastError());
     }
