@@ -46,7 +46,7 @@ NMU, NK = 129, 8193
 WORKLOAD = f"euclid_3x2pt_13bins_lmax5000_npar23 + gcsp_4bins_npar15_3PT_lattice{NMU}x{NK}"
 # FP64 operations per lattice-cell evaluation of spectro_fisher_kernel, counted once from ncu
 # (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on, DFMA = 2) -- see profiles/ and DESIGN.md
-F_CELL = 298.0
+F_CELL = 170.0
 
 
 def ext_dict(bank):

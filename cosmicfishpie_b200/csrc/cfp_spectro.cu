@@ -287,28 +287,27 @@ __device__ __forceinline__ double fast_rsqrt(double x) {  // x > 0, normal
   return fma(y, e, y);
 }
 
+// Polynomial coefficients live in constant memory: a 64-bit literal costs two UMOV issue slots per use on
+// sm_100a (profiles/r1c: 45 UMOV per cell evaluation), a constant-bank operand costs none.
+__constant__ double CFP_EXP_C[14] = {
+    1.6059043836821613e-10, 2.0876756987868100e-09, 2.5052108385441720e-08, 2.7557319223985888e-07,
+    2.7557319223985893e-06, 2.4801587301587302e-05, 1.9841269841269841e-04, 1.3888888888888889e-03,
+    8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0};  // 1/13! ... 1/0!
+__constant__ double CFP_LOG_C[9] = {1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0,
+                                    1.0 / 9.0,  1.0 / 7.0,  1.0 / 5.0,  1.0 / 3.0};
+__constant__ double CFP_K[5] = {1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01,
+                                -1.90821492927058770002e-10, -700.0};  // log2(e), 1.5*2^52, -ln2_hi, -ln2_lo, clamp
+
 __device__ __forceinline__ double fast_exp_neg(double x) {  // x <= 0
-  x = fmax(x, -700.0);
-  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer in the low word
-  double t = fma(x, 1.4426950408889634074, MAGIC);
+  x = fmax(x, CFP_K[4]);
+  double t = fma(x, CFP_K[0], CFP_K[1]);  // magic constant rounds x log2(e) to the nearest integer (low word)
   const int n = __double2loint(t);
-  t -= MAGIC;
-  double r = fma(t, -6.93147180369123816490e-01, x);
-  r = fma(t, -1.90821492927058770002e-10, r);
-  double p = 1.6059043836821613e-10;          // 1/13!
-  p = fma(p, r, 2.0876756987868100e-09);      // 1/12!
-  p = fma(p, r, 2.5052108385441720e-08);      // 1/11!
-  p = fma(p, r, 2.7557319223985888e-07);      // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06);      // 1/9!
-  p = fma(p, r, 2.4801587301587302e-05);      // 1/8!
-  p = fma(p, r, 1.9841269841269841e-04);      // 1/7!
-  p = fma(p, r, 1.3888888888888889e-03);      // 1/6!
-  p = fma(p, r, 8.3333333333333332e-03);      // 1/5!
-  p = fma(p, r, 4.1666666666666664e-02);      // 1/4!
-  p = fma(p, r, 1.6666666666666666e-01);      // 1/3!
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+  t -= CFP_K[1];
+  double r = fma(t, CFP_K[2], x);
+  r = fma(t, CFP_K[3], r);
+  double p = CFP_EXP_C[0];
+#pragma unroll
+  for (int i = 1; i < 14; ++i) p = fma(p, r, CFP_EXP_C[i]);
   return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
@@ -323,19 +322,14 @@ __device__ __forceinline__ double fast_log(double x) {  // x > 0, normal
   const double m = __hiloint2double(hi, lo);  // [sqrt(1/2), sqrt(2))
   const double f = fast_div(m - 1.0, m + 1.0);
   const double s = f * f;
-  double p = 1.0 / 19.0;
-  p = fma(p, s, 1.0 / 17.0);
-  p = fma(p, s, 1.0 / 15.0);
-  p = fma(p, s, 1.0 / 13.0);
-  p = fma(p, s, 1.0 / 11.0);
-  p = fma(p, s, 1.0 / 9.0);
-  p = fma(p, s, 1.0 / 7.0);
-  p = fma(p, s, 1.0 / 5.0);
-  p = fma(p, s, 1.0 / 3.0);
-  p = p * s;                        // atanh(f)/f - 1
+  double p = CFP_LOG_C[0];
+#pragma unroll
+  for (int i = 1; i < 9; ++i) p = fma(p, s, CFP_LOG_C[i]);
+  p = p * s;  // atanh(f)/f - 1
   const double de = (double)e;
+  const double f2 = f + f;
   // ln x = e ln2 + 2 f (1 + p)
-  return fma(de, 6.93147180369123816490e-01, fma(2.0 * f, p, fma(de, 1.90821492927058770002e-10, 2.0 * f)));
+  return fma(de, -CFP_K[2], fma(f2, p, fma(de, -CFP_K[3], f2)));
 }
 
 // ------------------------------------------------------------------ lattice evaluation
