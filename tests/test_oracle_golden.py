@@ -92,6 +92,71 @@ def test_photo_oracle_bit_exact(obank, tag, obs, free, settings, spec):
             assert np.array_equal(np.array([r["derivs"][f[5:]][k] for k in g["cl_keys"]]), g[f]), f
 
 
+SMALL = {"spectro_Pk_k_samples": 65, "spectro_Pk_mu_samples": 9}
+F3 = {"Omegam": 0.01, "h": 0.01, "w0": 0.01}
+
+
+@pytest.mark.parametrize("tag,settings,spec_over,yaml_name", [
+    ("gcsp_var_noap_nofog", dict(SMALL, AP_effect=False, FoG_switch=False), {}, None),
+    ("gcsp_var_linear", dict(SMALL, GCsp_linear=True), {}, None),
+    ("gcsp_var_bfs8", dict(SMALL, bfs8terms=True), {}, None),
+    ("gcsp_var_dzdep", dict(SMALL), {"spec_sigma_dz_type": "z-dependent", "spec_sigma_dz": 0.001}, None),
+    ("gcsp_var_nlcosmo", dict(SMALL, fix_cosmo_nl_terms=False), {}, None),
+    ("gcsp_var_qbias", dict(SMALL), {}, "Euclid-Spectroscopic-ISTF-Pessimistic-Qbias"),
+])
+def test_spectro_oracle_variants_bit_exact(obank, tag, settings, spec_over, yaml_name):
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.spectro import spectro_fisher
+
+    sp = _spectro_specs()  # defaults first, then the named survey (config.py:481-567)
+    if yaml_name:
+        sp.update(yaml.safe_load(open(os.path.join(SPECDIR, yaml_name + ".yaml")))["specifications"])
+    sp.update(spec_over)
+    bias = dict(sp["sp_bias_parametrization"][sp["sp_bias_model"]])
+    ps = dict(sp["shot_noise_parametrization"][sp["shot_noise_model"]])
+    fp = dict(F3)
+    for k in list(bias) + list(ps):
+        fp.setdefault(k, 1e-4)
+    r = spectro_fisher(obank, sp, settings, dict(tt.FIDUCIAL), bias, ps, {}, fp, max_z_bins=2, return_all=True)
+    g = golden(tag)
+    assert r["param_names"] == list(g["param_names"])
+    assert np.array_equal(r["fisher"], g["fisher"])
+    assert np.array_equal(np.array([x[:, ::16] for x in r["lnp_fid"]]), g["lnpobs_fid_strided"])
+
+
+@pytest.mark.parametrize("tag,obs,free,settings,spec_over", [
+    ("photo_var_linear_pk", ["WL", "GCph"], {"Omegam": 0.01, "h": 0.01}, {"ell_sampling": 16, "nonlinear": False}, {}),
+    ("photo_var_sqrtbias", ["GCph"], {"sigma8": 0.01}, {"ell_sampling": 16}, {"ph_bias_model": "sqrt"}),
+    ("photo_var_gcfirst", ["GCph", "WL"], {"Omegam": 0.01}, {"ell_sampling": 12, "pivot_z_IA": 0.3}, {}),
+])
+def test_photo_oracle_variants_bit_exact(obank, tag, obs, free, settings, spec_over):
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.photo import default_photo_bias, finish_photo_specs, photo_fisher
+
+    raw = yaml.safe_load(open(os.path.join(SPECDIR, "Euclid-Photometric-ISTF-Pessimistic.yaml")))["specifications"]
+    sp = finish_photo_specs(raw)
+    sp.update(spec_over)
+    lum = np.load(os.path.join(REPO, "cosmicfishpie_b200", "data", "lumratio.npy"))
+    bias = default_photo_bias(sp) if "GCph" in obs else {}
+    ia = dict(sp["IA_params"])
+    fp = dict(free)
+    if "GCph" in obs:
+        for k in bias:
+            if k != "bias_model":
+                fp.setdefault(k, sp["vary_ph_bias"])
+    if "WL" in obs:
+        for k in ia:
+            if k != "IA_model":
+                fp.setdefault(k, sp["vary_IA_pars"])
+    r = photo_fisher(obank, sp, settings, obs, dict(tt.FIDUCIAL), dict(sp["photo_z_params"]), ia, bias, fp, lum,
+                     return_all=True)
+    g = golden(tag)
+    assert r["param_names"] == list(g["param_names"])
+    assert r["cols"] == list(g["cov_cols"])
+    assert np.array_equal(np.array([r["cls"][k] for k in g["cl_keys"]]), g["cls"])
+    assert np.array_equal(r["fisher"], g["fisher"])
+
+
 LIKE_PHOTO = {"fid": {}, "nuis": {"b1": 1.02, "b7": 0.985, "AIA": 1.04, "etaIA": 0.97, "betaIA": 1.01},
               "cosmo": {"Omegam": 1.01}, "both": {"h": 0.99, "b3": 1.03, "AIA": 0.95}}
 LIKE_SPECTRO = {"fid": {}, "nuis": {"lnbg_1": 1.01, "lnbg_4": 0.99}, "cosmo": {"h": 1.01},

@@ -17,6 +17,15 @@ CASES = {
 }
 
 
+CASES.update({  # goldens: tools/make_goldens.py PHOTO_VARIANTS
+    "photo_var_linear_pk": dict(obs=["WL", "GCph"], free={"Omegam": 0.01, "h": 0.01},
+                                opts={"ell_sampling": 16, "nonlinear": False}),
+    "photo_var_sqrtbias": dict(obs=["GCph"], free={"sigma8": 0.01}, opts={"ell_sampling": 16},
+                               specs={"ph_bias_model": "sqrt"}),
+    "photo_var_gcfirst": dict(obs=["GCph", "WL"], free={"Omegam": 0.01}, opts={"ell_sampling": 12, "pivot_z_IA": 0.3}),
+})
+
+
 def run_case(name, extfiles, tmp_path):
     from cosmicfishpie_b200 import toy_tables as tt
     from cosmicfishpie_b200.fishermatrix import FisherMatrix
@@ -25,7 +34,7 @@ def run_case(name, extfiles, tmp_path):
     opts = base_options(tmp_path, survey_name_photo=c.get("spec", "Euclid-Photometric-ISTF-Pessimistic"),
                         survey_name_spectro=False, **c["opts"])
     fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars=dict(c["free"]), options=opts, observables=list(c["obs"]),
-                      extfiles=extfiles, cosmoModel="w0waCDM", surveyName="Euclid")
+                      specifications=dict(c.get("specs", {})), extfiles=extfiles, cosmoModel="w0waCDM", surveyName="Euclid")
     return fm, fm.compute()
 
 

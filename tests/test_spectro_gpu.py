@@ -16,13 +16,29 @@ CASES = {
 }
 
 
+SMALL = {"spectro_Pk_k_samples": 65, "spectro_Pk_mu_samples": 9}
+F3 = {"Omegam": 0.01, "h": 0.01, "w0": 0.01}
+# one branch of spectro_obs.py each (goldens: tools/make_goldens.py GCSP_VARIANTS)
+CASES.update({
+    "gcsp_var_noap_nofog": dict(free=F3, opts=dict(SMALL, AP_effect=False, FoG_switch=False), mzb=2),
+    "gcsp_var_linear": dict(free=F3, opts=dict(SMALL, GCsp_linear=True), mzb=2),
+    "gcsp_var_bfs8": dict(free=F3, opts=dict(SMALL, bfs8terms=True), mzb=2),
+    "gcsp_var_dzdep": dict(free=F3, opts=dict(SMALL), mzb=2,
+                           specs={"spec_sigma_dz_type": "z-dependent", "spec_sigma_dz": 0.001}),
+    "gcsp_var_nlcosmo": dict(free=F3, opts=dict(SMALL, fix_cosmo_nl_terms=False), mzb=2),
+    "gcsp_var_qbias": dict(free=F3, opts=dict(SMALL, survey_name_spectro="Euclid-Spectroscopic-ISTF-Pessimistic-Qbias"),
+                           mzb=2),
+})
+
+
 def run_case(name, extfiles, tmp_path):
     from cosmicfishpie_b200 import toy_tables as tt
     from cosmicfishpie_b200.fishermatrix import FisherMatrix
 
     c = CASES[name]
     fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars=dict(c["free"]), options=base_options(tmp_path, **c["opts"]),
-                      observables=["GCsp"], extfiles=extfiles, cosmoModel="w0waCDM", surveyName="Euclid")
+                      specifications=dict(c.get("specs", {})), observables=["GCsp"], extfiles=extfiles,
+                      cosmoModel="w0waCDM", surveyName="Euclid")
     F = fm.compute(max_z_bins=c["mzb"])
     return fm, F
 
@@ -41,7 +57,8 @@ def test_fisher_matches_reference(name, extfiles, tmp_path):
     assert perbin < 1e-8, perbin
 
 
-@pytest.mark.parametrize("name", ["gcsp_cfg1", "gcsp_small"])
+@pytest.mark.parametrize("name", ["gcsp_cfg1", "gcsp_small", "gcsp_var_noap_nofog", "gcsp_var_linear", "gcsp_var_bfs8",
+                                  "gcsp_var_qbias"])
 def test_lattices_match_reference(name, extfiles, tmp_path):
     g = golden(name)
     fm, _ = run_case(name, extfiles, tmp_path)

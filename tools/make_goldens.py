@@ -221,6 +221,40 @@ def photo_cfg3():
               photo_yaml="Euclid-Photometric-13bins-lmax5000", save_derivs=("Omegam", "b13", "etaIA"))
 
 
+SMALL = {"spectro_Pk_k_samples": 65, "spectro_Pk_mu_samples": 9}
+MYSPECS = os.path.join(REPO, "cosmicfishpie_b200", "data", "specs")
+# option / specification variants of the spectroscopic path (each exercises one branch of spectro_obs.py)
+GCSP_VARIANTS = {
+    "gcsp_var_noap_nofog": dict(options_extra=dict(SMALL, AP_effect=False, FoG_switch=False)),
+    "gcsp_var_linear": dict(options_extra=dict(SMALL, GCsp_linear=True)),
+    "gcsp_var_bfs8": dict(options_extra=dict(SMALL, bfs8terms=True)),
+    "gcsp_var_dzdep": dict(options_extra=dict(SMALL), specifications={"spec_sigma_dz_type": "z-dependent", "spec_sigma_dz": 0.001}),
+    "gcsp_var_nlcosmo": dict(options_extra=dict(SMALL, fix_cosmo_nl_terms=False)),
+    "gcsp_var_qbias": dict(options_extra=dict(SMALL, specs_dir=MYSPECS), spectro_yaml="Euclid-Spectroscopic-ISTF-Pessimistic-Qbias"),
+}
+PHOTO_VARIANTS = {
+    "photo_var_linear_pk": dict(obs=["WL", "GCph"], free={"Omegam": 0.01, "h": 0.01}, options_extra={"ell_sampling": 16, "nonlinear": False}),
+    "photo_var_sqrtbias": dict(obs=["GCph"], free={"sigma8": 0.01}, options_extra={"ell_sampling": 16}, specifications={"ph_bias_model": "sqrt"}),
+    "photo_var_gcfirst": dict(obs=["GCph", "WL"], free={"Omegam": 0.01}, options_extra={"ell_sampling": 12, "pivot_z_IA": 0.3}),
+}
+
+
+def _make_variant(name):
+    def fn():
+        if name in GCSP_VARIANTS:
+            v = GCSP_VARIANTS[name]
+            run_gcsp(name, {"Omegam": 0.01, "h": 0.01, "w0": 0.01}, max_z_bins=2, **v)
+        else:
+            v = dict(PHOTO_VARIANTS[name])
+            run_photo(name, v.pop("obs"), v.pop("free"), **v)
+    fn.__name__ = name
+    return fn
+
+
+for _n in list(GCSP_VARIANTS) + list(PHOTO_VARIANTS):
+    CASES[_n] = _make_variant(_n)
+
+
 LIKE_POINTS_PHOTO = {
     "fid": {},
     "nuis": {"b1": 1.02, "b7": 0.985, "AIA": 1.04, "etaIA": 0.97, "betaIA": 1.01},     # multiplicative shifts
