@@ -314,7 +314,7 @@ class PhotoCov:
 
 
 def photo_fisher(bank, specs, settings, observables, fiducial_cosmopars, photopars, IApars, biaspars,
-                 freeparams, lumratio_table, return_all=False):
+                 freeparams, lumratio_table, return_all=False, stencil="3PT"):
     """FisherMatrix.compute() photo branch (cosmicfish.py:225-251, 643-744)."""
     s = dict(DEFAULT_SETTINGS)
     s.update(settings or {})
@@ -326,13 +326,19 @@ def photo_fisher(bank, specs, settings, observables, fiducial_cosmopars, photopa
     for par in freeparams:  # derivatives.py:131-207
         fid = pc.allparsfid
         step = fid[par] * freeparams[par] if fid[par] != 0.0 else freeparams[par]
-        fwd = copy.deepcopy(fid)
-        fwd[par] = fwd[par] + step
-        of = pc.getcls(fwd)
-        bwd = copy.deepcopy(fid)
-        bwd[par] = bwd[par] - step
-        ob = pc.getcls(bwd)
-        derivs[par] = {k: (of[k] if k == "ells" else (of[k] - ob[k]) / (2 * step)) for k in of}
+        from .spectro import STENCILS
+
+        pts, den = STENCILS[stencil]
+        acc = None
+        for m, w in pts:
+            ap = copy.deepcopy(fid)
+            ap[par] = ap[par] + m * step
+            o = pc.getcls(ap)
+            if acc is None:
+                acc = {k: (o[k] if k == "ells" else w * o[k]) for k in o}
+            else:
+                acc = {k: (acc[k] if k == "ells" else acc[k] + w * o[k]) for k in o}
+        derivs[par] = {k: (acc[k] if k == "ells" else acc[k] / (den * step)) for k in acc}
     lvec = noisy["ells"]
     lave = np.convolve(lvec, np.ones(2) / 2, mode="valid")
     dl = np.diff(lvec)

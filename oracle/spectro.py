@@ -257,8 +257,15 @@ class SpectroCov:
         return self.obs.observed_P_gg_ij(z, k, mu) + 1 / self.n_density(z)
 
 
+STENCILS = {  # (offset multiple of h, weight) and denominator factor; derivatives.py:93-111, 209-225
+    "3PT": ([(+1, +1.0), (-1, -1.0)], 2.0),
+    "4PT_FWD": ([(0, -11.0), (1, 18.0), (2, -9.0), (3, 2.0)], 6.0),
+    "5PT": ([(+2, -1.0), (+1, +8.0), (-1, -8.0), (-2, +1.0)], 12.0),  # not in the reference (north_star)
+}
+
+
 def spectro_fisher(bank, specs, settings, fiducial_cosmopars, spectrobiaspars, pshotpars, nonlinpars,
-                   freeparams, max_z_bins=None, return_all=False):
+                   freeparams, max_z_bins=None, return_all=False, stencil="3PT"):
     """FisherMatrix.compute() spectro branch (cosmicfish.py:253-330)."""
     s = dict(DEFAULT_SETTINGS)
     s.update(settings or {})
@@ -308,13 +315,14 @@ def spectro_fisher(bank, specs, settings, fiducial_cosmopars, spectrobiaspars, p
             derivs[par] = d
             continue
         step = fid_all[par] * freeparams[par] if fid_all[par] != 0.0 else freeparams[par]
-        fwd = copy.deepcopy(fid_all)
-        fwd[par] = fwd[par] + step
-        of = get_obs(fwd)
-        bwd = copy.deepcopy(fid_all)
-        bwd[par] = bwd[par] - step
-        ob = get_obs(bwd)
-        derivs[par] = {i: (of[i] - ob[i]) / (2 * step) for i in of}
+        pts, den = STENCILS[stencil]
+        acc = None
+        for m, w in pts:
+            ap = copy.deepcopy(fid_all)
+            ap[par] = ap[par] + m * step
+            o = get_obs(ap)
+            acc = {i: w * o[i] for i in o} if acc is None else {i: acc[i] + w * o[i] for i in o}
+        derivs[par] = {i: acc[i] / (den * step) for i in acc}
 
     plist = list(freeparams)
     F = np.zeros((len(zmids), len(plist), len(plist)))
