@@ -42,36 +42,71 @@ __global__ void photo_sqrtp_kernel(const double* __restrict__ blob, const int64_
   T[idx] = v;
 }
 
-// one CTA per cosmology, one thread per WL row: eff = I1 - chi * I2 with backward cumulative trapezoids
-// (sequential in z like np.cumsum; chi and the n_i(z) rows are staged in shared memory first so the
-// 200-step recurrence does not pay a global-memory latency per step)
-__global__ void photo_eff_kernel(int NC, int Nb, int Nz, const int* __restrict__ kind, const double* __restrict__ ngal,
-                                 const double* __restrict__ chi, double dz, double* __restrict__ eff) {
-  extern __shared__ double effsm[];  // chi[Nz], ngal[Nb][Nz]
+// one CTA per cosmology: eff = I1 - chi * I2 with backward cumulative trapezoids (sequential in z like
+// np.cumsum).  n_i(z) and n_i(z)/chi(z) are staged in shared memory by the whole CTA first, so the serial
+// 200-step recurrence of each lensing row runs on shared-memory operands only.
+__global__ void __launch_bounds__(256) photo_eff_kernel(int NC, int Nb, int Nz, const int* __restrict__ kind,
+                                                        const double* __restrict__ ngal, const double* __restrict__ chi,
+                                                        double dz, double* __restrict__ eff) {
+  extern __shared__ double effsm[];  // chi[Nz], n[Nb][Nz], q[Nb][Nz], e[Nb][Nz]
   const int c = blockIdx.x;
   double* sch = effsm;
-  double* sn = effsm + Nz;
+  double* sn = sch + Nz;
+  double* sq = sn + (size_t)Nb * Nz;
+  double* se = sq + (size_t)Nb * Nz;
   for (int i = threadIdx.x; i < Nz; i += blockDim.x) sch[i] = chi[(size_t)c * Nz + i];
-  for (int i = threadIdx.x; i < Nb * Nz; i += blockDim.x) sn[i] = ngal[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < Nb * Nz; i += blockDim.x) {
+    const double v = ngal[i];
+    sn[i] = v;
+    sq[i] = v / sch[i % Nz];
+  }
   __syncthreads();
   for (int a = threadIdx.x; a < Nb; a += blockDim.x) {
-    double* e = eff + ((size_t)c * Nb + a) * Nz;
+    double* e = se + (size_t)a * Nz;
     if (kind[a] != 0) {
       for (int i = 0; i < Nz; ++i) e[i] = 0.0;
       continue;
     }
     const double* n = sn + (size_t)a * Nz;
+    const double* q = sq + (size_t)a * Nz;
     double I1 = 0.0, I2 = 0.0;
     e[Nz - 1] = I1 - sch[Nz - 1] * I2;
-    double n_hi = n[Nz - 1], q_hi = n[Nz - 1] / sch[Nz - 1];
     for (int i = Nz - 2; i >= 0; --i) {
-      const double n_lo = n[i], q_lo = n[i] / sch[i];
-      I1 = I1 + 0.5 * (n_hi + n_lo) * dz;
-      I2 = I2 + 0.5 * (q_hi + q_lo) * dz;
+      I1 = I1 + 0.5 * (n[i + 1] + n[i]) * dz;
+      I2 = I2 + 0.5 * (q[i + 1] + q[i]) * dz;
       e[i] = I1 - sch[i] * I2;
-      n_hi = n_lo;
-      q_hi = q_lo;
     }
+  }
+  __syncthreads();
+  double* out = eff + (size_t)c * Nb * Nz;
+  for (int i = threadIdx.x; i < Nb * Nz; i += blockDim.x) out[i] = se[i];
+}
+
+// fallback for grids whose rows do not fit in shared memory: one thread per (cosmology, row), global operands
+__global__ void photo_eff_kernel_global(int NC, int Nb, int Nz, const int* __restrict__ kind,
+                                        const double* __restrict__ ngal, const double* __restrict__ chi, double dz,
+                                        double* __restrict__ eff) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NC * Nb) return;
+  const int c = idx / Nb, a = idx % Nb;
+  double* e = eff + (size_t)idx * Nz;
+  if (kind[a] != 0) {
+    for (int i = 0; i < Nz; ++i) e[i] = 0.0;
+    return;
+  }
+  const double* n = ngal + (size_t)a * Nz;
+  const double* ch = chi + (size_t)c * Nz;
+  double I1 = 0.0, I2 = 0.0;
+  e[Nz - 1] = I1 - ch[Nz - 1] * I2;
+  double n_hi = n[Nz - 1], q_hi = n[Nz - 1] / ch[Nz - 1];
+  for (int i = Nz - 2; i >= 0; --i) {
+    const double n_lo = n[i], q_lo = n[i] / ch[i];
+    I1 = I1 + 0.5 * (n_hi + n_lo) * dz;
+    I2 = I2 + 0.5 * (q_hi + q_lo) * dz;
+    e[i] = I1 - ch[i] * I2;
+    n_hi = n_lo;
+    q_hi = q_lo;
   }
 }
 
@@ -473,6 +508,12 @@ extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, 
   int ldz = pl->nz4;
   while (!((ldz % 16) == 4 || (ldz % 16) == 12)) ldz += 4;  // conflict-free DMMA fragment loads
   pl->ldz = ldz;
+  if ((size_t)2 * pl->nb * 8 * ldz * sizeof(double) > 220 * 1024) {
+    cfp_set_error("cfp_photo_plan_create: Nb_pad x Nz = %d x %d does not fit the shared-memory tile of the C_ell kernel "
+                  "(limit 2*Nb_pad*Nz*8 B <= 220 KB)", pl->nb * 8, ldz);
+    photo_free(pl);
+    return CFP_ERR_INVALID;
+  }
   pl->ldb = Nb | 1;
   pl->dz = dz, pl->kmax = kmax;
   pl->l_begin = 0, pl->l_end = Nl - 1;
@@ -588,11 +629,17 @@ static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
   }
   CFP_CUDA(cudaEventRecord(pl->kev[1], st));
   {
-    const size_t esm = (size_t)(pl->Nb + 1) * pl->Nz * sizeof(double);
-    if (esm > 48 * 1024)
-      CFP_CUDA(cudaFuncSetAttribute(photo_eff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
-    photo_eff_kernel<<<pl->NC, 64, esm, st>>>(pl->NC, pl->Nb, pl->Nz, pl->kind_d, pl->ngal_d, pl->chi_d, pl->dz,
-                                              pl->eff_d);
+    const size_t esm = (size_t)(3 * pl->Nb + 1) * pl->Nz * sizeof(double);
+    if (esm <= 200 * 1024) {
+      if (esm > 48 * 1024)
+        CFP_CUDA(cudaFuncSetAttribute(photo_eff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+      photo_eff_kernel<<<pl->NC, 256, esm, st>>>(pl->NC, pl->Nb, pl->Nz, pl->kind_d, pl->ngal_d, pl->chi_d, pl->dz,
+                                                pl->eff_d);
+    } else {
+      const int tot = pl->NC * pl->Nb;
+      photo_eff_kernel_global<<<(tot + 63) / 64, 64, 0, st>>>(pl->NC, pl->Nb, pl->Nz, pl->kind_d, pl->ngal_d, pl->chi_d,
+                                                             pl->dz, pl->eff_d);
+    }
     ctx->launches++;
     CFP_CUDA(cudaGetLastError());
   }
