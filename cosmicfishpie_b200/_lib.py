@@ -32,6 +32,7 @@ EXPORTS = [
     "cfp_spectro_plan_fisher_d", "cfp_spectro_plan_fetch", "cfp_photo_plan_create", "cfp_photo_plan_destroy",
     "cfp_photo_plan_set_slice", "cfp_photo_plan_run", "cfp_photo_plan_fisher_d", "cfp_photo_plan_fetch",
     "cfp_photo_plan_chi2", "cfp_spectro_plan_chi2", "cfp_cells_chi2", "cfp_wedge_chi2",
+    "cfp_legendre_project", "cfp_legendre_covariance", "cfp_legendre_chi2",
 ]
 
 
@@ -98,6 +99,9 @@ def load():
     lib.cfp_spectro_plan_chi2.argtypes = [_vp, _dp, _dp, _dp, _dp, _vp]
     lib.cfp_cells_chi2.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, _ip, _ip, _dp, _dp]
     lib.cfp_wedge_chi2.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+    lib.cfp_legendre_project.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
+    lib.cfp_legendre_covariance.argtypes = [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
+    lib.cfp_legendre_chi2.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("cfp_abi_version",):
@@ -169,6 +173,31 @@ class Context:
         out = np.empty(S)
         _check(self.lib.cfp_wedge_chi2(self.handle, S, Z, Nmu, Nk, _p(theory), _p(data), _p(f64(k)), _p(f64(wk)),
                                        _p(f64(wmu)), _p(f64(vol)), _p(out)), "cfp_wedge_chi2")
+        return out
+
+    def legendre_project(self, lat, lw) -> np.ndarray:
+        """lat [S][Z][Nmu][Nk], lw [3][Nmu] -> P_ell [S][Nk][Z][3]  (cfp_legendre_project)."""
+        lat, lw = f64(lat), f64(lw)
+        S, Z, Nmu, Nk = lat.shape
+        out = np.empty((S, Nk, Z, 3))
+        _check(self.lib.cfp_legendre_project(self.handle, S, Z, Nmu, Nk, _p(lat), _p(lw), _p(out)), "cfp_legendre_project")
+        return out
+
+    def legendre_covariance(self, pl, k, vol, m):
+        """pl [Nk][Z][3] -> (cov, icov) [Nk][Z][3][3]  (cfp_legendre_covariance)."""
+        pl = f64(pl)
+        Nk, Z = pl.shape[:2]
+        cov, icov = np.empty((Nk, Z, 3, 3)), np.empty((Nk, Z, 3, 3))
+        _check(self.lib.cfp_legendre_covariance(self.handle, Nk, Z, _p(pl), _p(f64(k)), _p(f64(vol)), _p(f64(m)), _p(cov),
+                                                _p(icov)), "cfp_legendre_covariance")
+        return cov, icov
+
+    def legendre_chi2(self, pl_data, pl_theory, icov) -> np.ndarray:
+        pl_data, pl_theory, icov = f64(pl_data), f64(pl_theory), f64(icov)
+        S, Nk, Z = pl_theory.shape[:3]
+        out = np.empty(S)
+        _check(self.lib.cfp_legendre_chi2(self.handle, S, Nk, Z, _p(pl_data), _p(pl_theory), _p(icov), _p(out)),
+               "cfp_legendre_chi2")
         return out
 
     def close(self):

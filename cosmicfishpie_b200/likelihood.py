@@ -270,6 +270,46 @@ def compute_wedge_chi2(P_obs_data, P_obs_theory, cosmoFM_data):
                                 cosmoFM_data.pk_cov.volume_survey_array)[0])
 
 
+# Wigner-3j sum matrices for the multipole covariance (utilities/legendre_tools.py:56-123): m00, m22, m44, m02, m24, m04
+_M3J_REF = np.array([  # with the reference's 15-digit literals, so results agree to the last bits
+    [1.00000000000000, 0, 0, 0, 0.200000000000000, 0, 0, 0, 0.111111111111111],
+    [0.200000000000000, 2 / 35, 2 / 35, 2 / 35, 0.0857142857142857, 12 / 385, 2 / 35, 12 / 385, 0.0397158397158397],
+    [0.111111111111111, 20 / 693, 18 / 1001, 20 / 693, 0.0397158397158397, 20 / 1001, 18 / 1001, 20 / 1001, 0.0310865604983252],
+    [0, 0.200000000000000, 0, 0.200000000000000, 2 / 35, 0.0571428571428571, 0, 0.0571428571428571, 20 / 693],
+    [0, 0.0571428571428571, 20 / 693, 0.0571428571428571, 12 / 385, 0.0397158397158397, 20 / 693, 0.0397158397158397, 20 / 1001],
+    [0, 0, 0.111111111111111, 0, 2 / 35, 20 / 693, 0.111111111111111, 20 / 693, 18 / 1001],
+])
+leg_ells = np.arange(0, 5, 2, dtype="int")
+
+
+def _legendre_weights(mugrid):
+    """(2 ell + 1) * Simpson weight * L_ell(mu) for ell = 0, 2, 4 (spectro_like.py:49-54)."""
+    from scipy.special import eval_legendre
+
+    w = simpson_weights(mugrid)
+    return np.array([(2.0 * ell + 1) * w * eval_legendre(ell, mugrid) for ell in leg_ells])
+
+
+def legendre_Pgg(obs_Pgg, cosmoFM):
+    """Multipoles P_ell(k, z), ell = 0,2,4, shape (Nk, Nz, 3) (reference: spectro_like.py:48-56)."""
+    ctx = _lib.default_context(cosmoFM.settings.get("device"))
+    return ctx.legendre_project(np.asarray(obs_Pgg)[None], _legendre_weights(cosmoFM.Pk_mugrid))[0]
+
+
+def compute_covariance_legendre(P_ell, cosmoFM):
+    """k-bin integrated Gaussian covariance of the multipoles and its inverse (reference: spectro_like.py:69-122)."""
+    ctx = _lib.default_context(cosmoFM.settings.get("device"))
+    if P_ell.shape[0] != len(cosmoFM.Pk_kgrid):
+        raise ValueError("k_grid and P_ell have different lengths in k")
+    return ctx.legendre_covariance(P_ell, cosmoFM.Pk_kgrid, cosmoFM.pk_cov.volume_survey_array, _M3J_REF)
+
+
+def compute_chi2_legendre(P_ell_data, P_ell_theory, inv_covariance, cosmoFM=None):
+    """Reference: spectro_like.py:125-140."""
+    ctx = _lib.default_context(None if cosmoFM is None else cosmoFM.settings.get("device"))
+    return float(ctx.legendre_chi2(P_ell_data, np.asarray(P_ell_theory)[None], inv_covariance)[0])
+
+
 def _spectro_point(param_dict, fm):
     """(ComputeGalSpectro of the point, shot noise per bin)  (reference: spectro_like.py:192-224)."""
     p = deepcopy(param_dict)
@@ -291,22 +331,26 @@ def compute_theory_spectro(param_dict, cosmoFM_theory, leg_flag="wedges"):
     out = observable_Pgg(cov, cosmoFM_theory, nuisance_shot=shot)
     if leg_flag == "wedges":
         return out
-    raise NotImplementedError("Legendre multipoles are not implemented on the device yet (leg_flag='wedges' only)")
+    if leg_flag == "legendre":
+        return legendre_Pgg(out, cosmoFM_theory)
+    raise ValueError(f"Unknown leg_flag '{leg_flag}'. Use 'wedges' or 'legendre'.")
 
 
 class SpectroLikelihood(Likelihood, NautilusMixin):
-    """Reference: likelihood/spectro_like.py:236-299 (wedges)."""
+    """Reference: likelihood/spectro_like.py:236-299 (wedges and Legendre multipoles)."""
 
     def __init__(self, *, cosmoFM_data, cosmoFM_theory=None, leg_flag="wedges", data_obs=None, nuisance_shot=None):
-        if leg_flag != "wedges":
-            raise NotImplementedError("only leg_flag='wedges' is implemented on the device")
+        if leg_flag not in ("wedges", "legendre"):
+            raise ValueError(f"Unknown leg_flag '{leg_flag}'. Use 'wedges' or 'legendre'.")
+        self._inv_cov_legendre = None
+        self._data_wedges = None
         self._preloaded_data = None if data_obs is None else np.array(data_obs)
         self._nuisance_shot = None if nuisance_shot is None else np.array(nuisance_shot, dtype=float)
         super().__init__(cosmo_data=cosmoFM_data, cosmo_theory=cosmoFM_theory, leg_flag=leg_flag)
 
     @property
     def data_wedges(self):
-        return self.data_obs
+        return self._data_wedges
 
     def compute_data(self):
         fm = self.cosmo_data
@@ -314,16 +358,48 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
             raise AttributeError("cosmoFM_data.pk_cov is not available. Ensure the FisherMatrix was initialised for "
                                  "spectroscopic probes and compute() was called.")
         if self._preloaded_data is not None:
-            return self._preloaded_data
-        return observable_Pgg(fm.pk_cov, fm, nuisance_shot=self._nuisance_shot)
+            data = self._preloaded_data
+            if self.leg_flag == "legendre":
+                _, self._inv_cov_legendre = compute_covariance_legendre(data, fm)
+            else:
+                self._data_wedges = data
+            return data
+        obs = observable_Pgg(fm.pk_cov, fm, nuisance_shot=self._nuisance_shot)
+        self._data_wedges = obs
+        if self.leg_flag == "legendre":
+            p_ell = legendre_Pgg(obs, fm)
+            _, self._inv_cov_legendre = compute_covariance_legendre(p_ell, fm)
+            return p_ell
+        return obs
 
     def compute_theory(self, param_dict):
         return compute_theory_spectro(param_dict, self.cosmo_theory, self.leg_flag)
 
     def compute_chi2(self, theory_obs) -> float:
-        return compute_wedge_chi2(self.data_obs, theory_obs, self.cosmo_data)
+        if self.leg_flag == "wedges":
+            return compute_wedge_chi2(self.data_obs, theory_obs, self.cosmo_data)
+        return compute_chi2_legendre(self.data_obs, theory_obs, self._inv_cov_legendre, self.cosmo_data)
+
+    def _chi2_batch_legendre(self, param_dicts) -> np.ndarray:
+        """Multipole chi^2: theory lattices of a chunk of points on the device, projected and contracted there."""
+        fm = self.cosmo_theory
+        zs = list(fm.pk_cov.global_z_bin_mids)
+        ctx = _lib.default_context(fm.settings.get("device"))
+        lw = _legendre_weights(fm.Pk_mugrid)
+        inv_n = np.array([1 / fm.pk_cov.n_density(z) for z in zs])
+        out = np.empty(len(param_dicts))
+        lattice_bytes = 8 * len(zs) * fm.Pk_musamp * fm.Pk_ksamp
+        chunk = max(1, min(512, int(2**30 // lattice_bytes)))
+        for i0 in range(0, len(param_dicts), chunk):
+            pts, shots = zip(*[_spectro_point(p, fm) for p in param_dicts[i0:i0 + chunk]])
+            lat = np.exp(spectro_mod._evaluate_lattice(list(pts), zs, fm.Pk_kgrid, fm.Pk_mugrid))
+            lat += (inv_n[None, :] + np.array(shots))[:, :, None, None]
+            out[i0:i0 + chunk] = ctx.legendre_chi2(self.data_obs, ctx.legendre_project(lat, lw), self._inv_cov_legendre)
+        return out
 
     def chi2_batch(self, param_dicts) -> np.ndarray:
+        if self.leg_flag == "legendre":
+            return self._chi2_batch_legendre(param_dicts)
         fm = self.cosmo_theory
         zs = list(fm.pk_cov.global_z_bin_mids)
         out = np.empty(len(param_dicts))
@@ -343,7 +419,7 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
                 stden=np.ones(1), ps_bin=np.array([-1], np.int32), ps_src=0,
                 nbar=np.array([fm.pk_cov.n_density(z) for z in zs]), vol=fm.pk_cov.volume_survey_array,
                 flags=pts[0].flags())
-            out[i0:i0 + chunk] = plan.chi2(np.array(shots), data=self.data_obs)
+            out[i0:i0 + chunk] = plan.chi2(np.array(shots), data=self._data_wedges)
             plan.close()
         return out
 

@@ -264,6 +264,23 @@ int cfp_cells_chi2(cfp_ctx* ctx, int S, int Nl, int Nb, const double* theory_h, 
 int cfp_wedge_chi2(cfp_ctx* ctx, int S, int Z, int Nmu, int Nk, const double* theory_h, const double* data_h,
                    const double* k_h, const double* wk_h, const double* wmu_h, const double* vol_h, double* chi2_h);
 
+/* Legendre-multipole form of the spectroscopic likelihood (ell = 0, 2, 4), host arrays in and out:
+ *   cfp_legendre_project      legendre_Pgg                  cosmicfishpie/likelihood/spectro_like.py:48-56
+ *       lat_h[S][Z][Nmu][Nk], lw_h[3][Nmu] = (2 ell + 1) * Simpson weight * L_ell(mu)  ->  pl_h[S][Nk][Z][3]
+ *   cfp_legendre_covariance   compute_covariance_legendre   spectro_like.py:69-122 (k-bin integrated Gaussian
+ *       covariance with the Wigner-3j sum matrices of utilities/legendre_tools.py:56-123, then its inverse)
+ *       pl_h[Nk][Z][3] (data), k_h[Nk], vol_h[Z], m_h[6][3][3] = m00,m22,m44,m02,m24,m04
+ *       ->  cov_h[Nk][Z][3][3], icov_h[Nk][Z][3][3]
+ *   cfp_legendre_chi2         compute_chi2_legendre         spectro_like.py:125-140
+ *       pl_data_h[Nk][Z][3], pl_theory_h[S][Nk][Z][3], icov_h  ->  chi2_h[S]
+ */
+int cfp_legendre_project(cfp_ctx* ctx, int S, int Z, int Nmu, int Nk, const double* lat_h, const double* lw_h,
+                         double* pl_h);
+int cfp_legendre_covariance(cfp_ctx* ctx, int Nk, int Z, const double* pl_h, const double* k_h, const double* vol_h,
+                            const double* m_h, double* cov_h, double* icov_h);
+int cfp_legendre_chi2(cfp_ctx* ctx, int S, int Nk, int Z, const double* pl_data_h, const double* pl_theory_h,
+                      const double* icov_h, double* chi2_h);
+
 #ifdef __cplusplus
 }
 #endif

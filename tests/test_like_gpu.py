@@ -105,3 +105,24 @@ def test_spectro_likelihood_matches_reference(spectro_fm):
     assert abs(like.compute_chi2(th) - ref[3]) / ref[3] < 1e-10
     assert abs(like.loglike(param_dict=dicts[2]) + 0.5 * ref[2]) / ref[2] < 1e-10
     assert abs(lk.loglike(param_vec=dicts[1], cosmoFM_data=spectro_fm) + 0.5 * ref[1]) / ref[1] < 1e-10
+
+
+def test_spectro_legendre_matches_reference(spectro_fm):
+    from cosmicfishpie_b200 import likelihood as lk
+
+    g = golden("like_spectro")
+    like = lk.SpectroLikelihood(cosmoFM_data=spectro_fm, leg_flag="legendre")
+    assert rel_err(like.data_obs[::16], g["pl_data_strided"]) < 1e-13
+    cov, icov = lk.compute_covariance_legendre(like.data_obs, spectro_fm)
+    for a in range(3):
+        for b in range(3):
+            assert rel_err(cov[::16, :, a, b], g["cov_strided"][:, :, a, b]) < 1e-12, (a, b)
+    allp = dict(spectro_fm.allparams)
+    dicts = [shift(allp, POINTS_SPECTRO[str(n)]) for n in g["point_names"]]
+    ref = g["chi2_legendre"]
+    chi2 = like.chi2_batch(dicts)
+    assert chi2[0] < 1e-15
+    # the 3x3 multipole covariances are ill-conditioned (cond ~ 1e6), so inverse-covariance products agree to ~1e-9
+    assert np.max(np.abs(chi2[1:] - ref[1:]) / ref[1:]) < 1e-7
+    th = like.compute_theory(dicts[2])
+    assert abs(like.compute_chi2(th) - ref[2]) / ref[2] < 1e-7
