@@ -244,44 +244,45 @@ struct FishParams {
 // One CTA per multipole bin (left-edge index li).  All steps are data-parallel (no triangular-solve chains):
 //   1. A = C_l(fiducial) + N in shared memory, inverted in place by Gauss-Jordan (SPD, no pivoting needed;
 //      cond <= 2e4, the reference itself uses an explicit pinv)
-//   2. M_p = Phi dC_p (global scratch), Z_p = A^-1 M_p (shared memory when it fits, else global)
+//   2. one WARP per parameter: M_p = Phi dC_p into a per-warp shared tile, Z_p = A^-1 M_p into shared memory
+//      (global scratch when all Z_p do not fit); warps run independently, so load latency is hidden across warps
 //   3. F_pq = w_l sum_ij Z_p[i][j] Z_q[j][i] = w_l Tr(dC_p Sigma^-1 dC_q Sigma^-1), one warp per (p,q)
-constexpr int FISH_THREADS = 512;
+constexpr int FISH_THREADS = 256;
+constexpr int FISH_WARPS = FISH_THREADS / 32;
 
 __global__ void __launch_bounds__(FISH_THREADS) photo_fisher_kernel(FishParams P, int z_in_smem) {
   extern __shared__ double sm[];
   const int Nb = P.Nb, ld = P.ldb;
-  double* sA = sm;                 // [Nb][ld]
-  double* sPiv = sm + Nb * ld;     // [Nb] pivot column copy
-  double* sZ = sPiv + Nb;          // [npar][Nb][ld] if z_in_smem
+  double* sA = sm;                                  // [Nb][ld]
+  double* sM = sA + Nb * ld;                        // [FISH_WARPS][Nb][ld]
+  double* sZ = sM + (size_t)FISH_WARPS * Nb * ld;   // [npar][Nb][ld] if z_in_smem
   const int li = P.l_begin + blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (li >= P.l_end) return;
   const double* C0 = P.cls + ((size_t)0 * P.Nl + li) * Nb * Nb;
   for (int e = tid; e < Nb * Nb; e += blockDim.x) {
     const int i = e / Nb, j = e % Nb;
     sA[i * ld + j] = C0[e] + ((i == j) ? P.noise[i] : 0.0);
   }
-  double* Ml = P.Y + (size_t)blockIdx.x * 2 * P.npar * Nb * ld;  // M_p, then (fallback) Z_p behind it
-  for (int e = tid; e < P.npar * Nb * Nb; e += blockDim.x) {
-    const int p = e / (Nb * Nb), ij = e % (Nb * Nb), i = ij / Nb, j = ij % Nb;
-    double acc = 0.0;
-    for (int q = P.stp_ptr[p]; q < P.stp_ptr[p + 1]; ++q)
-      acc += P.stp_w[q] * P.cls[((size_t)P.stp_s[q] * P.Nl + li) * Nb * Nb + ij];
-    Ml[(size_t)p * Nb * ld + i * ld + j] = (acc / P.stden[p]) * P.sqrtfsky[i];
-  }
   __syncthreads();
-  // in-place Gauss-Jordan inversion: every thread computes the new values of its (<= 8) elements from the
+  // in-place Gauss-Jordan inversion: every thread computes the new values of its (<= 16) elements from the
   // old matrix into registers, the CTA synchronises, then they are written back
-  const int per = (Nb * Nb + blockDim.x - 1) / blockDim.x;  // uniform across the CTA (Nb <= 64 -> per <= 8)
+  const int per = (Nb * Nb + blockDim.x - 1) / blockDim.x;  // uniform across the CTA (Nb <= 64 -> per <= 16)
+  int ei[16], ej[16];
+#pragma unroll
+  for (int it = 0; it < 16; ++it) {
+    const int e = tid + it * blockDim.x;
+    ei[it] = e / Nb;
+    ej[it] = e % Nb;
+  }
   for (int k = 0; k < Nb; ++k) {
     const double piv = 1.0 / sA[k * ld + k];
-    double v[8];
+    double v[16];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < 16; ++it) {
       const int e = tid + it * blockDim.x;
       if (it < per && e < Nb * Nb) {
-        const int i = e / Nb, j = e % Nb;
+        const int i = ei[it], j = ej[it];
         const double aik = sA[i * ld + k], akj = sA[k * ld + j];
         if (i == k)
           v[it] = (j == k) ? piv : akj * piv;
@@ -293,53 +294,68 @@ __global__ void __launch_bounds__(FISH_THREADS) photo_fisher_kernel(FishParams P
     }
     __syncthreads();
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < 16; ++it) {
       const int e = tid + it * blockDim.x;
-      if (it < per && e < Nb * Nb) sA[(e / Nb) * ld + (e % Nb)] = v[it];
+      if (it < per && e < Nb * Nb) sA[ei[it] * ld + ej[it]] = v[it];
     }
     __syncthreads();
   }
-  // Z_p = A^-1 M_p
-  double* Z = z_in_smem ? sZ : (Ml + (size_t)P.npar * Nb * ld);
-  for (int e = tid; e < P.npar * Nb * Nb; e += blockDim.x) {
-    const int p = e / (Nb * Nb), ij = e % (Nb * Nb), i = ij / Nb, j = ij % Nb;
-    const double* Mp = Ml + (size_t)p * Nb * ld;
-    double a0 = 0.0, a1 = 0.0;
-    int k = 0;
-    for (; k + 1 < Nb; k += 2) {
-      a0 += sA[i * ld + k] * Mp[k * ld + j];
-      a1 += sA[i * ld + k + 1] * Mp[(k + 1) * ld + j];
-    }
-    if (k < Nb) a0 += sA[i * ld + k] * Mp[k * ld + j];
-    Z[(size_t)p * Nb * ld + i * ld + j] = a0 + a1;
+  double* Z = z_in_smem ? sZ : (P.Y + (size_t)blockIdx.x * P.npar * Nb * ld);
+  double* Mw = sM + (size_t)warp * Nb * ld;
+  // lane = column j (no integer division in the inner loops); Nb <= 64 -> at most two column passes
+  for (int p = warp; p < P.npar; p += FISH_WARPS) {
+    const int q0 = P.stp_ptr[p], q1 = P.stp_ptr[p + 1];
+    const double rden = P.stden[p];
+    for (int j = lane; j < Nb; j += 32)
+      for (int i = 0; i < Nb; ++i) {
+        double acc = 0.0;
+        for (int q = q0; q < q1; ++q)
+          acc += P.stp_w[q] * __ldg(P.cls + (((size_t)P.stp_s[q] * P.Nl + li) * Nb + i) * Nb + j);
+        Mw[i * ld + j] = (acc / rden) * P.sqrtfsky[i];
+      }
+    __syncwarp();
+    double* Zp = Z + (size_t)p * Nb * ld;
+    for (int j = lane; j < Nb; j += 32)
+      for (int i = 0; i < Nb; ++i) {
+        double a0 = 0.0, a1 = 0.0;
+        int k = 0;
+        for (; k + 1 < Nb; k += 2) {
+          a0 += sA[i * ld + k] * Mw[k * ld + j];
+          a1 += sA[i * ld + k + 1] * Mw[(k + 1) * ld + j];
+        }
+        if (k < Nb) a0 += sA[i * ld + k] * Mw[k * ld + j];
+        Zp[i * ld + j] = a0 + a1;
+      }
+    __syncwarp();
   }
   __syncthreads();
-  // F_l[p][q] = w_l sum_ij Z_p[i][j] Z_q[j][i]; cosmicfish.py:681-683, 704, 723.  One warp per (p,q) pair.
+  // F_l[p][q] = w_l sum_ij Z_p[i][j] Z_q[j][i]; cosmicfish.py:681-683, 704, 723.  One warp per (p,q) pair,
+  // pairs enumerated in triangular order, each warp advancing by FISH_WARPS pairs.
   const double lc = 0.5 * P.ell[li] + 0.5 * P.ell[li + 1];
   const double wl = (lc + 0.5) * (P.ell[li + 1] - P.ell[li]);
   double* Fl = P.Fl + (size_t)blockIdx.x * P.npar * P.npar;
-  const int npair = P.npar * (P.npar + 1) / 2;
-  const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  for (int e = warp; e < npair; e += nwarp) {
-    int p = 0, acc = 0;
-    while (acc + p + 1 <= e) {
-      acc += p + 1;
-      ++p;
-    }
-    const int q = e - acc;
-    const double* Zp = Z + (size_t)p * Nb * ld;
-    const double* Zq = Z + (size_t)q * Nb * ld;
+  int pp = 0, qq = warp;
+  while (qq > pp) {
+    qq -= pp + 1;
+    ++pp;
+  }
+  while (pp < P.npar) {
+    const double* Zp = Z + (size_t)pp * Nb * ld;
+    const double* Zq = Z + (size_t)qq * Nb * ld;
     double s = 0.0;
-    for (int ij = lane; ij < Nb * Nb; ij += 32) {
-      const int i = ij / Nb, j = ij % Nb;
-      s += Zp[i * ld + j] * Zq[j * ld + i];
-    }
+    for (int j = lane; j < Nb; j += 32)
+      for (int i = 0; i < Nb; ++i) s += Zp[i * ld + j] * Zq[j * ld + i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) {
       s *= wl;
-      Fl[p * P.npar + q] = s;
-      Fl[q * P.npar + p] = s;
+      Fl[pp * P.npar + qq] = s;
+      Fl[qq * P.npar + pp] = s;
+    }
+    qq += FISH_WARPS;
+    while (qq > pp) {
+      qq -= pp + 1;
+      ++pp;
     }
   }
 }
@@ -701,9 +717,9 @@ static int photo_run_fisher(cfp_photo_plan* pl, cudaStream_t st) {
     P.stp_ptr = pl->stp_ptr_d, P.stp_s = pl->stp_s_d, P.stp_w = pl->stp_w_d;
     P.stden = pl->stden_d, P.Y = pl->Y_d, P.Fl = pl->Fl_d;
     const int nbins = pl->l_end - pl->l_begin;
-    size_t smem = ((size_t)pl->Nb * pl->ldb + pl->Nb) * sizeof(double);
+    size_t smem = (size_t)(1 + FISH_WARPS) * pl->Nb * pl->ldb * sizeof(double);
     const size_t zsm = (size_t)pl->npar * pl->Nb * pl->ldb * sizeof(double);
-    const int z_in_smem = (smem + zsm <= 200 * 1024) ? 1 : 0;
+    const int z_in_smem = (smem + zsm <= 220 * 1024) ? 1 : 0;
     if (z_in_smem) smem += zsm;
     CFP_CUDA(cudaFuncSetAttribute(photo_fisher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CFP_CUDA(cudaEventRecord(pl->kev[4], st));
