@@ -47,6 +47,8 @@ WORKLOAD = f"euclid_3x2pt_13bins_lmax5000_npar23 + gcsp_4bins_npar15_3PT_lattice
 # FP64 operations per lattice-cell evaluation of spectro_fisher_kernel, counted once from ncu
 # (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on, DFMA = 2) -- see profiles/ and DESIGN.md
 F_CELL = 170.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one spectro_fisher_kernel launch (ncu --set full, profiles/r1c)
+TRAFFIC_BYTES = 2.22e6
 
 
 def ext_dict(bank):
@@ -284,7 +286,7 @@ def run_gpu(args):
     peak_dmma = ctx.peak_fp64(1)
     achieved = flops / (k_ms * 1e-3) / 1e12
     roof = {"bound": "fp64", "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s", "frac": achieved / peak_dfma,
-            "traffic": None, "kernel": "spectro_fisher_kernel", "kernel_ms": k_ms,
+            "traffic": TRAFFIC_BYTES if world == 1 else None, "kernel": "spectro_fisher_kernel", "kernel_ms": k_ms,
             "peak_source": "measured live: cfp_peak_fp64 DFMA microbenchmark (MEASURED_PEAKS.json has no FP64 entry)",
             "peak_dmma_tflops": peak_dmma, "flop_per_cell_eval": F_CELL, "cell_evals": evals}
     # HBM view: the API-preserving mode writes derivs[npar][Z][cells] + veff[Z][cells] once
