@@ -70,12 +70,15 @@ class Likelihood(ABC):
         params = self.build_param_dict(param_vec=param_vec, param_dict=param_dict, prior=prior)
         return float(-0.5 * self.chi2_batch([params])[0])
 
+    def chi2_matrix(self, names, matrix) -> np.ndarray:
+        """chi^2 of every row of `matrix` [B, len(names)]; subclasses override this with an array fast path."""
+        return self.chi2_batch([dict(zip(names, row)) for row in matrix])
+
     def loglike_batch(self, param_matrix, prior=None, keys: Optional[Iterable[str]] = None) -> np.ndarray:
         """log-likelihood of every row of `param_matrix` [B, ndim]; columns named by `prior.keys` or `keys`."""
         names = list(keys) if keys is not None else list(getattr(prior, "keys"))
         pm = np.atleast_2d(np.asarray(param_matrix, dtype=float))
-        dicts = [dict(zip(names, row)) for row in pm]
-        return -0.5 * self.chi2_batch(dicts)
+        return -0.5 * self.chi2_matrix(names, pm)
 
 
 class NautilusMixin:
@@ -236,6 +239,20 @@ class PhotometricLikelihood(Likelihood, NautilusMixin):
         ctx = _lib.default_context(self.cosmo_data.settings.get("device"))
         return float(ctx.cells_chi2(self._full_from_cells(theory_obs)[None], self._data_full, off, n, w)[0])
 
+    def chi2_matrix(self, names, matrix) -> np.ndarray:
+        known = set(self.cosmo_theory.fiducialcosmopars) | set(self.cosmo_theory.IApars) | set(self.cosmo_theory.photobiaspars)
+        keep = [i for i, n in enumerate(names) if n in known]  # unused parameters are ignored, as in the reference
+        names = [names[i] for i in keep]
+        matrix = np.ascontiguousarray(np.atleast_2d(matrix)[:, keep])
+        off, n, w = self._blocks()
+        out = np.empty(matrix.shape[0])
+        chunk = 4096
+        for i in range(0, matrix.shape[0], chunk):
+            job = photo_mod.PhotoJob.from_matrix(self.cosmo_theory, names, matrix[i:i + chunk])
+            out[i:i + chunk] = job.plan().chi2(off, n, w, data=self._data_full)
+            job.close()
+        return out
+
     def chi2_batch(self, param_dicts) -> np.ndarray:
         points = [self._allpars(p) for p in param_dicts]
         off, n, w = self._blocks()
@@ -395,6 +412,75 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
             lat = np.exp(spectro_mod._evaluate_lattice(list(pts), zs, fm.Pk_kgrid, fm.Pk_mugrid))
             lat += (inv_n[None, :] + np.array(shots))[:, :, None, None]
             out[i0:i0 + chunk] = ctx.legendre_chi2(self.data_obs, ctx.legendre_project(lat, lw), self._inv_cov_legendre)
+        return out
+
+    def chi2_matrix(self, names, matrix) -> np.ndarray:
+        """Array fast path of the wedge chi^2 for a batch given as a matrix: per-point scalar blocks are assembled
+        from one cached block per (cosmology, bin) plus the nuisance columns, no Python object per point."""
+        if self.leg_flag != "wedges":
+            return self.chi2_batch([dict(zip(names, row)) for row in matrix])
+        fm = self.cosmo_theory
+        fid_obs = fm.pk_obs_fid
+        cs = fid_obs.cosmo_set
+        zs = list(fm.pk_cov.global_z_bin_mids)
+        matrix = np.atleast_2d(np.asarray(matrix, dtype=float))
+        B, Z = matrix.shape[0], len(zs)
+        col = {n: i for i, n in enumerate(names)}
+
+        def column(key, fid):
+            return matrix[:, col[key]] if key in col else np.full(B, float(fid))
+
+        ckeys = [k for k in fm.fiducialcosmopars if k in col]
+        cosmo_of_s = np.zeros(B, dtype=np.int64)
+        if ckeys:
+            uniq, inv = np.unique(matrix[:, [col[k] for k in ckeys]], axis=0, return_inverse=True)
+            idx = np.empty(len(uniq), dtype=np.int64)
+            for u, row in enumerate(uniq):
+                cp = dict(fm.fiducialcosmopars)
+                cp.update({k: float(v) for k, v in zip(ckeys, row)})
+                idx[u] = cs.add(cp)
+            cosmo_of_s = idx[np.asarray(inv).ravel()]
+        base = {}
+        for c in np.unique(cosmo_of_s):
+            obs = spectro_mod.ComputeGalSpectro(cs.cosmos[c].cosmopars, spectrobiaspars=fm.Spectrobiaspars,
+                                                spectrononlinearpars=fm.Spectrononlinpars, PShotpars=fm.PShotpars,
+                                                configuration=fm, cosmo_set=cs)
+            base[c] = np.array([obs.scalar_block(z) for z in zs])
+        scal = np.stack([base[c] for c in cosmo_of_s])  # [B, Z, NSCAL]
+        nu = fid_obs.nuisance
+        for zb, z in enumerate(zs):
+            b = nu.gcsp_zvalue_to_zindex(z)
+            key = nu.sp_bias_root + nu.sp_bias_sample + "_" + str(b)
+            vals = column(key, fm.Spectrobiaspars[key])
+            scal[:, zb, _lib.SP_BIAS] = np.exp(vals) if nu.sp_bias_model == "linear_log" else vals
+            if fid_obs.rescale_sigmap and not fid_obs.linear_switch:
+                k2 = "sigmap_" + str(b)
+                scal[:, zb, _lib.SP_SIGMAP] = np.sqrt(scal[:, zb, _lib.SP_I2]) * column(k2, fm.Spectrononlinpars.get(k2, 1.0))
+            if fid_obs.rescale_sigmav:
+                k2 = "sigmav_" + str(b)
+                scal[:, zb, _lib.SP_SVRESCALE] = column(k2, fm.Spectrononlinpars.get(k2, 1.0))
+        if nu.sp_bias_model == "linear_Qbias":
+            scal[:, :, _lib.SP_A1] = column("A1", fm.Spectrobiaspars.get("A1", 0.0))[:, None]
+            scal[:, :, _lib.SP_A2] = column("A2", fm.Spectrobiaspars.get("A2", 0.0))[:, None]
+        shot = np.zeros((B, Z))
+        for i, key in enumerate(fm.PShotpars.keys()):
+            if i < Z:
+                shot[:, i] = column(key, fm.PShotpars[key])
+        used = {int(c) for c in np.unique(cosmo_of_s)}
+        pk, pp = spectro_mod._pnw_arrays(cs, zs, set() if fid_obs.linear_switch else used)
+        wk, wmu = simpson_weights(fm.Pk_kgrid), simpson_weights(fm.Pk_mugrid)
+        nbar = np.array([fm.pk_cov.n_density(z) for z in zs])
+        out = np.empty(B)
+        chunk = 8192
+        for i0 in range(0, B, chunk):
+            S = min(chunk, B - i0)
+            plan = _lib.SpectroPlan(
+                cs.ctx or _lib.default_context(), cs.bank(), k=fm.Pk_kgrid, mu=fm.Pk_mugrid, wk=wk, wmu=wmu,
+                scal=scal[i0:i0 + S], alias=np.tile(np.arange(S, dtype=np.int32)[:, None], (1, Z)), pnw_k=pk, pnw_p=pp,
+                stw=np.zeros((1, S)), stden=np.ones(1), ps_bin=np.array([-1], np.int32), ps_src=0, nbar=nbar,
+                vol=fm.pk_cov.volume_survey_array, flags=fid_obs.flags())
+            out[i0:i0 + S] = plan.chi2(shot[i0:i0 + S], data=self._data_wedges)
+            plan.close()
         return out
 
     def chi2_batch(self, param_dicts) -> np.ndarray:

@@ -243,6 +243,87 @@ class PhotoJob:
         self.NC = NC
         self._plan = None
 
+    @classmethod
+    def from_matrix(cls, configuration, names, matrix, cosmo_set: Optional[CosmoSet] = None):
+        """Batch of parameter points given as a matrix [B, len(names)] (likelihood sampling): the per-point
+        windows are assembled with array operations instead of one Python object per point.  Unlisted
+        parameters stay at their fiducial values.  Same numbers as the point-by-point constructor up to the
+        rounding of the IA window's linear interpolation."""
+        configuration, cfg = _cfg_of(configuration)
+        self = cls.__new__(cls)
+        self.configuration, self.cfg = configuration, cfg
+        g = self.grid = _PhotoGrid(configuration)
+        cs = self.cosmo_set = cosmo_set if cosmo_set is not None else _cosmo_set_of(cfg)
+        nuis = PhotoNuisance(configuration)
+        matrix = np.atleast_2d(np.asarray(matrix, dtype=float))
+        B, Nz, Nb = matrix.shape[0], g.zsamp, len(g.rows)
+        col = {n: i for i, n in enumerate(names)}
+        for n in names:
+            if n in cfg.photoparams:
+                raise NotImplementedError("photo-z parameters cannot be varied per point yet")
+
+        def column(key, fid):
+            return matrix[:, col[key]] if key in col else np.full(B, float(fid))
+
+        # cosmology of every point -> index into the bank (nearest tabulated cosmology, as the reference does)
+        ckeys = [k for k in cfg.fiducialparams if k in col]
+        self.cosmo_of_s = np.zeros(B, dtype=np.int32)
+        if ckeys:
+            sub = matrix[:, [col[k] for k in ckeys]]
+            uniq, inv = np.unique(sub, axis=0, return_inverse=True)
+            idx = np.empty(len(uniq), dtype=np.int32)
+            for u, row in enumerate(uniq):
+                cp = dict(cfg.fiducialparams)
+                cp.update({k: float(v) for k, v in zip(ckeys, row)})
+                idx[u] = cs.add(cp)
+            self.cosmo_of_s = idx[np.asarray(inv).ravel()]
+        self.bias = np.ones((B, Nb, Nz))
+        self.ia = np.zeros((B, Nz))
+        if "WL" in g.observables:
+            ia = cfg.IAparams
+            if ia["IA_model"] != "eNLA":
+                raise ValueError("only the eNLA intrinsic alignment model exists")
+            A, eta, beta = column("AIA", ia["AIA"]), column("etaIA", ia["etaIA"]), column("betaIA", ia["betaIA"])
+            piv = nuis.settings["pivot_z_IA"]
+            zz = nuis.z
+            Om = np.array([c.Omegam_of_z(0.0) for c in cs.cosmos])[self.cosmo_of_s]
+            growth = np.array([c.growth(zz).flatten() for c in cs.cosmos])[self.cosmo_of_s]      # [B, 50]
+            fac = -A * (0.0134 * (1 + piv)) * Om
+            z_dep = (1 + zz) / (1 + piv)
+            win = fac[:, None] * z_dep[None, :] ** eta[:, None] * ((nuis._lum_z[None, :] ** beta[:, None]) / growth)
+            j = np.clip(np.searchsorted(zz, g.z, side="right") - 1, 0, len(zz) - 2)
+            t = (g.z - zz[j]) / (zz[j + 1] - zz[j])
+            self.ia = win[:, j] * (1.0 - t)[None, :] + win[:, j + 1] * t[None, :]
+        if "GCph" in g.observables:
+            bp = cfg.Photobiasparams
+            model = bp["bias_model"]
+            gc_rows = [a for a, (o, _) in enumerate(g.rows) if o == "GCph"]
+            if model == "binned":
+                edges = np.asarray(configuration.specs["z_bins_GCph"])
+                brang = list(configuration.specs["binrange_GCph"])
+                vals = np.stack([column(f"b{k}", bp[f"b{k}"]) for k in brang], axis=1)            # [B, nbins]
+                zi = np.clip(np.searchsorted(edges, g.z, side="right") - 1, 0, brang[-1] - 1)
+                self.bias[:, gc_rows, :] = vals[:, zi][:, None, :]
+            elif model == "binned_constant":
+                for a in gc_rows:
+                    i = g.rows[a][1]
+                    self.bias[:, a, :] = column(f"b{i}", bp[f"b{i}"])[:, None]
+            else:
+                pts = [dict(bp, **{k: float(matrix[s, col[k]]) for k in bp if k in col}) for s in range(B)]
+                for s, b in enumerate(pts):
+                    for a in gc_rows:
+                        self.bias[s, a] = nuis.gcph_bias(b, g.rows[a][1])(g.z)
+        self.chi = np.array([c.comoving(g.z) for c in cs.cosmos])
+        self.hub = np.array([c.Hubble(g.z) for c in cs.cosmos])
+        self.wlpref = np.array([(3.0 / 2.0) * c.Hubble(0.0) ** 2.0 * c.Omegam_of_z(0.0) for c in cs.cosmos])
+        win_ = galaxy_photo_dist(cfg.photoparams, configuration)
+        self.window = win_
+        self.ngal = np.array([win_.norm_ngal_photoz(g.z, i, o) for o, i in g.rows])
+        self.stw, self.stden = np.zeros((1, B)), np.ones(1)
+        self.NC = len(cs)
+        self._plan = None
+        return self
+
     def plan(self) -> _lib.PhotoPlan:
         if self._plan is None:
             g, cs = self.grid, self.cosmo_set

@@ -107,6 +107,32 @@ def test_spectro_likelihood_matches_reference(spectro_fm):
     assert abs(lk.loglike(param_vec=dicts[1], cosmoFM_data=spectro_fm) + 0.5 * ref[1]) / ref[1] < 1e-10
 
 
+def test_matrix_fast_paths_agree_with_point_by_point(photo_fm, spectro_fm):
+    """loglike_batch assembles the per-point inputs with array operations; it must agree with the
+    one-object-per-point path (which is the one checked against the reference above)."""
+    from cosmicfishpie_b200 import likelihood as lk
+
+    rng = np.random.default_rng(7)
+    Lp = lk.PhotometricLikelihood(cosmo_data=photo_fm)
+    keys = ["Omegam", "b2", "b9", "AIA", "etaIA", "betaIA", "not_a_parameter"]
+    fid = np.array([photo_fm.allparams.get(k, 1.0) for k in keys])
+    mat = fid * (1 + 0.02 * rng.standard_normal((12, len(keys))))
+    mat[:, 0] = fid[0] * rng.choice([0.99, 1.0, 1.01], size=12)  # tabulated cosmologies
+    a = Lp.loglike_batch(mat, keys=keys)
+    b = -0.5 * Lp.chi2_batch([dict(zip(keys, r)) for r in mat])
+    assert np.max(np.abs(a - b) / np.abs(b)) < 1e-10
+    Ls = lk.SpectroLikelihood(cosmoFM_data=spectro_fm)
+    keys = ["h", "lnbg_1", "lnbg_3", "Ps_2", "Ps_4"]
+    fid = np.array([spectro_fm.allparams[k] for k in keys])
+    mat = np.tile(fid, (10, 1))
+    mat[:, 1:3] *= 1 + 0.01 * rng.standard_normal((10, 2))
+    mat[:, 3:] = rng.uniform(0, 40, size=(10, 2))
+    mat[:, 0] = fid[0] * rng.choice([0.99, 1.0, 1.01], size=10)
+    a = Ls.loglike_batch(mat, keys=keys)
+    b = -0.5 * Ls.chi2_batch([dict(zip(keys, r)) for r in mat])
+    assert np.max(np.abs(a - b) / np.abs(b)) < 1e-12
+
+
 def test_spectro_legendre_matches_reference(spectro_fm):
     from cosmicfishpie_b200 import likelihood as lk
 
