@@ -123,7 +123,15 @@ def _ngal_per_bin(ngal_sqarmin, zbins):
     return ((ngal_sqarmin * 3600) / nbins) * SR * np.ones_like(np.asarray(zbins[:-1], dtype=float))
 
 
+_YAML_CACHE = {}
+
+
 def _load_yaml_specs(folder, name, default_name, fail):
+    """`specifications:` mapping of a survey YAML; parsed once per (path, mtime) and deep-copied per use."""
+    return copy.deepcopy(_load_yaml_specs_cached(folder, name, default_name, fail))
+
+
+def _load_yaml_specs_cached(folder, name, default_name, fail):
     path = os.path.join(folder, name + ".yaml")
     if not os.path.isfile(path):
         if fail:
@@ -131,8 +139,11 @@ def _load_yaml_specs(folder, name, default_name, fail):
         print(f"WARNING: specifications file : {path} not found!")
         path = os.path.join(SPECS_DIR_DEFAULT, default_name + ".yaml")
         print(f"Using default specifications: {path}")
-    with open(path, "r") as fh:
-        return yaml.safe_load(fh)["specifications"]
+    key = (os.path.abspath(path), os.path.getmtime(path))
+    if key not in _YAML_CACHE:
+        with open(path, "r") as fh:
+            _YAML_CACHE[key] = yaml.safe_load(fh)["specifications"]
+    return _YAML_CACHE[key]
 
 
 def _photo_specs(folder, name, fail):

@@ -121,7 +121,8 @@ class FisherMatrix:
         self.Pk_musamp = self.settings["spectro_Pk_mu_samples"]
         self.Pk_kgrid = np.linspace(self.kmin_fish, self.kmax_fish, self.Pk_ksamp)
         self.Pk_mugrid = np.linspace(0.0, 1.0, self.Pk_musamp)
-        self.Pk_kmesh, self.Pk_mumesh = np.meshgrid(self.Pk_kgrid, self.Pk_mugrid)
+        # read-only broadcast views (the fine lattice is 8 MB per mesh): same values and shapes as np.meshgrid's copies
+        self.Pk_kmesh, self.Pk_mumesh = np.meshgrid(self.Pk_kgrid, self.Pk_mugrid, copy=False)
 
     def eliminate_zbinned_freepars(self, nmax):
         """Drop `name_<bin>` parameters of bins beyond nmax (cosmicfish.py:813-839)."""

@@ -24,12 +24,12 @@ def simpson_weights(x) -> np.ndarray:
     h = np.diff(x)
 
     def basic(stop):  # pairs (0,1,2), (2,3,4), ... up to index `stop`
-        for i in range(0, stop - 1, 2):
-            h0, h1 = h[i], h[i + 1]
-            hs, hp, r = h0 + h1, h0 * h1, h0 / h1
-            w[i] += hs / 6.0 * (2.0 - 1.0 / r)
-            w[i + 1] += hs / 6.0 * (hs * hs / hp)
-            w[i + 2] += hs / 6.0 * (2.0 - r)
+        i = np.arange(0, stop - 1, 2)
+        h0, h1 = h[i], h[i + 1]
+        hs, hp, r = h0 + h1, h0 * h1, h0 / h1
+        np.add.at(w, i, hs / 6.0 * (2.0 - 1.0 / r))
+        np.add.at(w, i + 1, hs / 6.0 * (hs * hs / hp))
+        np.add.at(w, i + 2, hs / 6.0 * (2.0 - r))
 
     if n % 2 == 1:
         basic(n - 1)
