@@ -146,7 +146,7 @@ def run_reference(args):
               "single-threaded processes")
     line = {"impl": "reference", "metric": "fisher_matrices_per_s", "value": value, "unit": "Fisher/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step / cores, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": value, "unit": "Fisher/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Fisher/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -220,43 +220,59 @@ def run_gpu(args):
     Fph = cdist.device_view(pplan.fisher_device_ptr(), (pplan.npar, pplan.npar), local)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
-    def step():
+    def step(sharded=False):
         pplan.run(stream=sptr)
         splan.run(materialize=0, stream=sptr)
-        if world > 1:
+        if sharded and world > 1:
             with torch.cuda.stream(stream):
                 torch.distributed.all_reduce(Fph)
                 torch.distributed.all_reduce(Fsp)
 
-    launches0 = ctx.launches
-    for _ in range(max(3, args.warmup)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
+    def timed_loop(sharded):
+        """W warm-up steps, then exactly K steps timed with CUDA events on the launch stream (L2 flushed between
+        steps, outside the event pairs); returns (ms per step = max over ranks, kernels launched)."""
+        if sharded:
+            splan.set_slice(cb, ce)
+            pplan.set_slice(lb, le)
+        else:
+            splan.set_slice(0, ncell)
+            pplan.set_slice(0, nbins)
+        for _ in range(max(3, args.warmup)):
+            step(sharded)
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        n0 = ctx.launches
+        with torch.cuda.stream(stream):
+            for a, b in ev:
+                flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+                a.record(stream)
+                step(sharded)
+                b.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item()) / args.steps, ctx.launches - n0
+
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches1 = ctx.launches
-    torch.cuda.synchronize()
-    with torch.cuda.stream(stream):
-        for a, b in ev:
-            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
-            a.record(stream)
-            step()
-            b.record(stream)
-    torch.cuda.synchronize()
+    # headline: a batch of independent forecasts, one per GPU per step (weak scaling, no collective)
+    ms_per_step, launches_timed = timed_loop(sharded=False)
+    value = world * 1e3 / ms_per_step
+    # one forecast split over the GPUs (lattice cells / multipole bins) + NCCL all-reduce of the partial Fishers
+    strong = None
     if world > 1:
-        torch.distributed.barrier()
-    launches_timed = ctx.launches - launches1
-    ms_local = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
-    value = 1e3 / ms_per_step
+        ms_strong, _ = timed_loop(sharded=True)
+        strong = {"value": 1e3 / ms_strong, "unit": "Fisher/s", "ms_per_step": ms_strong, "scaling": "strong",
+                  "what": "ONE forecast per step split over the ranks (spectro lattice cells, photo multipole bins), "
+                          "one NCCL all-reduce of the partial Fisher matrices per probe inside the timed region"}
+    splan.set_slice(cb, ce)
+    pplan.set_slice(lb, le)
 
     # ---- dominant kernel alone: spectro_fisher_kernel ------------------------------------------------
     kms = []
@@ -320,10 +336,10 @@ def run_gpu(args):
         if cold:
             ccos.clear_caches()  # tables -> FITPACK splines are re-fitted, as the reference does per Fisher
         a = make_photo_fm(bank, tmp)
-        cdist.shard(a, rank, world)
+        cdist.shard(a, 0, 1)  # every rank computes its own full forecast (weak scaling, like `value`)
         Fa = a.compute()
         b = make_spectro_fm(bank, tmp)
-        cdist.shard(b, rank, world)
+        cdist.shard(b, 0, 1)
         Fb = b.compute()
         tot = Fa + Fb
         h2d = (a.photo_LSS._job.plan().h2d_bytes + a.photo_LSS._job.cosmo_set.bank().nbytes
@@ -385,8 +401,6 @@ def run_gpu(args):
         jp.close()
         js.close()
         p1, p2 = jp.plan(), js.plan()
-        p1.set_slice(lb, le)
-        p2.set_slice(cb, ce)
         p1.run()
         p2.run()
         p1.fetch()
@@ -407,22 +421,23 @@ def run_gpu(args):
                              "by cell count to 129x8193" % (detail["photo_s"], detail["spectro_sample_s"], detail["spectro_scale"])}
         line = {
             "metric": "fisher_matrices_per_s", "value": value, "unit": "Fisher/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2_flush_between_steps": True,
-                       "partition": "spectro lattice cells and photo multipole bins split over ranks; one NCCL "
-                                    "all-reduce of the Fisher partial sums per probe" if world > 1 else "single GPU"},
+                       "partition": "a batch of independent forecasts, one per GPU per step, no collective "
+                                    "(strong_scaling: one forecast sharded over the GPUs + NCCL all-reduce)"},
+            "strong_scaling": strong,
             "clocks": clk,
-            "e2e": {"value": 1.0 / t_api, "unit": "Fisher/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": world / t_api, "unit": "Fisher/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": "public API per step: FisherMatrix(...) + compute() for 3x2pt and for GCsp, summed; per-job "
                             "host prep, H2D of the table bank and job arrays, kernels, D2H, file export. The spline "
                             "facades of the cached Boltzmann tables are reused across steps (north_star: Boltzmann input "
                             "is computed once on the host and cached); e2e_cold re-fits them every step",
                     "s_per_step": t_api},
-            "e2e_cold": {"value": 1.0 / t_cold, "unit": "Fisher/s", "s_per_step": t_cold,
+            "e2e_cold": {"value": world / t_cold, "unit": "Fisher/s", "s_per_step": t_cold,
                          "what": "as e2e but every cache cleared each step (tables -> FITPACK fits -> bank), i.e. what "
                                  "the reference redoes for every Fisher matrix"},
-            "cabi_e2e": {"value": 1.0 / t_cabi, "unit": "Fisher/s", "s_per_step": t_cabi,
+            "cabi_e2e": {"value": world / t_cabi, "unit": "Fisher/s", "s_per_step": t_cabi,
                          "what": "cfp_*_plan_create(host buffers) + run + fetch, table bank resident"},
             "likelihood": {"photo_3x2pt_13bins": like_photo, "spectro_wedges_129x8193": like_spectro,
                            "scaling": "weak", "what": "loglike_batch through the public API (host prep + H2D + kernels + "
