@@ -33,6 +33,7 @@ EXPORTS = [
     "cfp_photo_plan_set_slice", "cfp_photo_plan_run", "cfp_photo_plan_fisher_d", "cfp_photo_plan_fetch",
     "cfp_photo_plan_chi2", "cfp_spectro_plan_chi2", "cfp_cells_chi2", "cfp_wedge_chi2",
     "cfp_legendre_project", "cfp_legendre_covariance", "cfp_legendre_chi2",
+    "cfp_bank_upload_rows", "cfp_host_alloc", "cfp_host_free",
 ]
 
 
@@ -76,6 +77,9 @@ def load():
     lib.cfp_photo_plan_kernel_ms.restype = C.c_double
     lib.cfp_bank_upload.argtypes = [_vp, _dp, C.c_size_t, _lp, C.c_int, C.c_int, C.POINTER(_vp)]
     lib.cfp_bank_free.argtypes = [_vp, _vp]
+    lib.cfp_bank_upload_rows.argtypes = [_vp, C.POINTER(_vp), _lp, _lp, C.c_int, C.c_int, C.POINTER(_vp)]
+    lib.cfp_host_alloc.argtypes = [_vp, C.c_size_t, C.POINTER(_vp)]
+    lib.cfp_host_free.argtypes = [_vp, _vp]
     lib.cfp_bank_eval.argtypes = [_vp, _vp, C.c_int, C.c_int, _dp, _dp, C.c_size_t, _dp]
     lib.cfp_spectro_plan_create.argtypes = [
         _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, C.c_int, _dp, _dp,
@@ -224,8 +228,67 @@ def default_context(device: Optional[int] = None) -> Context:
     return _default_ctx[device]
 
 
+class PinnedBuffer:
+    """Page-locked host array of float64 (cfp_host_alloc) -- buffers that are uploaded again and again."""
+
+    def __init__(self, ctx: Context, n_doubles: int):
+        self.ctx, self.ptr = ctx, _vp()
+        _check(ctx.lib.cfp_host_alloc(ctx.handle, int(n_doubles) * 8, C.byref(self.ptr)), "cfp_host_alloc")
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, _dp), shape=(int(n_doubles),))
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self.ctx.lib.cfp_host_free(self.ctx.handle, self.ptr)
+            self.ptr = _vp()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BankRow:
+    """The fitted tables of ONE cosmology packed for upload: [tx | ty | c] per slot in a pinned block plus the
+    row-local descriptor.  Built once per cosmology and table selection, reused by every bank that needs it."""
+
+    def __init__(self, ctx: Context, row):
+        desc = np.zeros((NTAB, BANK_DESC), dtype=np.int64)
+        parts, off = [], 0
+        for slot in range(NTAB):
+            t = row[slot] if slot < len(row) else None
+            if t is None:
+                continue
+            tx, ty, cc = (f64(x).ravel() for x in t)
+            assert cc.size == (tx.size - 4) * (ty.size - 4)
+            desc[slot] = (tx.size, ty.size, off, off + tx.size, off + tx.size + ty.size)
+            parts += [tx, ty, cc]
+            off += tx.size + ty.size + cc.size
+        self.buf = PinnedBuffer(ctx, off)
+        np.concatenate(parts, out=self.buf.array)
+        self.desc, self.n = desc, off
+
+
 class Bank:
     """Device-resident cosmology table bank (cfp_bank): bicubic (tx, ty, c) per cosmology and table."""
+
+    @classmethod
+    def from_rows(cls, ctx: Context, rows):
+        """Bank of pre-packed `BankRow`s (one per cosmology): no re-packing, page-locked H2D."""
+        self = cls.__new__(cls)
+        self.ctx, self.rows = ctx, list(rows)
+        n = len(self.rows)
+        self.desc = np.ascontiguousarray(np.stack([r.desc for r in self.rows]))
+        ptrs = (_vp * n)(*[r.buf.ptr.value for r in self.rows])
+        lens = np.array([r.n for r in self.rows], dtype=np.int64)
+        self.blob = None
+        self.n_cosmo = n
+        self.nbytes = int(lens.sum()) * 8 + self.desc.nbytes
+        self.handle = _vp()
+        _check(ctx.lib.cfp_bank_upload_rows(ctx.handle, ptrs, _p(lens, _lp), _p(self.desc, _lp), n, NTAB,
+                                            C.byref(self.handle)), "cfp_bank_upload_rows")
+        return self
 
     def __init__(self, ctx: Context, tcks):
         """tcks[c][slot] = (tx, ty, c_flat) or None."""

@@ -246,6 +246,16 @@ class cosmo_functions:
                 row[slot] = getattr(self, name).tck
         return row
 
+    def packed_row(self, ctx, slots=None) -> "_lib.BankRow":
+        """`bank_row` packed once into page-locked memory (per device context and table selection)."""
+        cache = self.__dict__.setdefault("_packed_rows", {})
+        key = (id(ctx), None if slots is None else tuple(slots))
+        hit = cache.get(key)
+        if hit is None or hit[0] is not ctx:
+            hit = (ctx, _lib.BankRow(ctx, self.bank_row(slots)))
+            cache[key] = hit
+        return hit[1]
+
 
 _COSMO_CACHE: Dict[tuple, tuple] = {}
 
@@ -306,5 +316,5 @@ class CosmoSet:
         if self._bank is None:
             if self.ctx is None:
                 self.ctx = _lib.default_context()
-            self._bank = _lib.Bank(self.ctx, [c.bank_row(self.slots) for c in self.cosmos])
+            self._bank = _lib.Bank.from_rows(self.ctx, [c.packed_row(self.ctx, self.slots) for c in self.cosmos])
         return self._bank

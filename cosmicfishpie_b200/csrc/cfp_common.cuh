@@ -35,7 +35,22 @@ struct cfp_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
   double last_ms = 0.0;
+  cudaMemPool_t pool = nullptr;  // stream-ordered arena: plan create/destroy never reach the driver allocator
 };
+
+// Device memory comes from the context's pool, ordered on the context stream.  Work that runs on a caller's
+// stream synchronises with the context stream after allocating and before releasing (see the plan code).
+inline cudaError_t cfp_dev_alloc(cfp_ctx* ctx, void** p, size_t bytes) {
+  if (ctx->pool) return cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream);
+  return cudaMalloc(p, bytes);
+}
+inline void cfp_dev_free(cfp_ctx* ctx, void* p) {
+  if (!p) return;
+  if (ctx && ctx->pool)
+    cudaFreeAsync(p, ctx->stream);
+  else
+    cudaFree(p);
+}
 
 struct cfp_bank {
   cfp_ctx* ctx = nullptr;
@@ -47,12 +62,12 @@ struct cfp_bank {
   const int64_t* desc(int c, int t) const { return &desc_h[((size_t)c * n_tables + t) * CFP_BANK_DESC]; }
 };
 
-// Upload helper: cudaMalloc + async copy on the context stream.
+// Upload helper: pool allocation + async copy on the context stream.
 template <typename T>
 int cfp_upload(cfp_ctx* ctx, const T* src_h, size_t count, T** dst_d) {
   *dst_d = nullptr;
   if (count == 0) return CFP_OK;
-  CFP_CUDA(cudaMalloc((void**)dst_d, count * sizeof(T)));
+  CFP_CUDA(cfp_dev_alloc(ctx, (void**)dst_d, count * sizeof(T)));
   if (src_h) {
     CFP_CUDA(cudaMemcpyAsync(*dst_d, src_h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
   } else {

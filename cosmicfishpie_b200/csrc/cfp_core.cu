@@ -34,6 +34,19 @@ extern "C" int cfp_ctx_create(int device, cfp_ctx** out) {
   CFP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CFP_CUDA(cudaEventCreate(&ctx->ev0));
   CFP_CUDA(cudaEventCreate(&ctx->ev1));
+  // Arena for every device buffer of banks and plans: a private stream-ordered pool that keeps what it
+  // has been given (release threshold = max), so create/destroy cycles cost no driver allocation.
+  const char* no_pool = getenv("CFP_NO_POOL");
+  if (!(no_pool && atoi(no_pool) != 0)) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    CFP_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
+    uint64_t keep = UINT64_MAX;
+    CFP_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   *out = ctx;
   return CFP_OK;
 }
@@ -44,6 +57,7 @@ extern "C" int cfp_ctx_destroy(cfp_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return CFP_OK;
@@ -87,8 +101,70 @@ extern "C" int cfp_bank_upload(cfp_ctx* ctx, const double* blob_h, size_t n_doub
   if (rc == CFP_OK) rc = cfp_upload(ctx, desc_h, nd, &b->desc_d);
   if (rc == CFP_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = CFP_ERR_CUDA;
   if (rc != CFP_OK) {
-    cudaFree(b->blob_d);
-    cudaFree(b->desc_d);
+    cfp_dev_free(ctx, b->blob_d);
+    cfp_dev_free(ctx, b->desc_d);
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return CFP_OK;
+}
+
+extern "C" int cfp_host_alloc(cfp_ctx* ctx, size_t bytes, void** out) {
+  CFP_REQUIRE(ctx && out && bytes > 0, "bad argument");
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  CFP_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return CFP_OK;
+}
+
+extern "C" int cfp_host_free(cfp_ctx* ctx, void* p) {
+  (void)ctx;  // page-locked memory is not tied to a device; the handle may already be gone at interpreter exit
+  if (!p) return CFP_OK;
+  CFP_CUDA(cudaFreeHost(p));
+  return CFP_OK;
+}
+
+extern "C" int cfp_bank_upload_rows(cfp_ctx* ctx, const double* const* rows_h, const int64_t* row_len,
+                                    const int64_t* desc_h, int n_cosmo, int n_tables, cfp_bank** out) {
+  CFP_REQUIRE(ctx && rows_h && row_len && desc_h && out, "NULL argument");
+  CFP_REQUIRE(n_cosmo > 0 && n_tables > 0, "empty bank");
+  *out = nullptr;
+  const size_t nd = (size_t)n_cosmo * n_tables * CFP_BANK_DESC;
+  std::vector<int64_t> desc(desc_h, desc_h + nd);
+  std::vector<size_t> start(n_cosmo);
+  size_t total = 0;
+  for (int c = 0; c < n_cosmo; ++c) {
+    CFP_REQUIRE(rows_h[c] != nullptr && row_len[c] > 0, "empty bank row");
+    start[c] = total;
+    for (int t = 0; t < n_tables; ++t) {
+      int64_t* d = &desc[((size_t)c * n_tables + t) * CFP_BANK_DESC];
+      if (d[0] == 0 && d[1] == 0) continue;  // empty slot
+      CFP_REQUIRE(d[0] >= 8 && d[1] >= 8, "bicubic table needs >= 8 knots per axis");
+      CFP_REQUIRE(d[2] >= 0 && d[2] + d[0] <= row_len[c], "tx out of range");
+      CFP_REQUIRE(d[3] >= 0 && d[3] + d[1] <= row_len[c], "ty out of range");
+      CFP_REQUIRE(d[4] >= 0 && d[4] + (d[0] - 4) * (d[1] - 4) <= row_len[c], "c out of range");
+      d[2] += (int64_t)total, d[3] += (int64_t)total, d[4] += (int64_t)total;  // row-local -> bank offsets
+    }
+    total += (size_t)row_len[c];
+  }
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cfp_bank* b = new cfp_bank();
+  b->ctx = ctx;
+  b->n_cosmo = n_cosmo;
+  b->n_tables = n_tables;
+  b->n = total;
+  b->desc_h = desc;
+  cudaError_t e = cfp_dev_alloc(ctx, (void**)&b->blob_d, total * sizeof(double));
+  for (int c = 0; c < n_cosmo && e == cudaSuccess; ++c)
+    e = cudaMemcpyAsync(b->blob_d + start[c], rows_h[c], (size_t)row_len[c] * sizeof(double), cudaMemcpyHostToDevice,
+                        ctx->stream);
+  int rc = e == cudaSuccess ? cfp_upload(ctx, b->desc_h.data(), nd, &b->desc_d) : CFP_ERR_CUDA;
+  // rows may be pageable or pinned (cfp_host_alloc); either way the copies are complete on return
+  if (rc == CFP_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = CFP_ERR_CUDA;
+  if (rc != CFP_OK) {
+    if (e != cudaSuccess) cfp_set_error("cfp_bank_upload_rows: %s", cudaGetErrorString(e));
+    cfp_dev_free(ctx, b->blob_d);
+    cfp_dev_free(ctx, b->desc_d);
     delete b;
     return rc;
   }
@@ -98,9 +174,10 @@ extern "C" int cfp_bank_upload(cfp_ctx* ctx, const double* blob_h, size_t n_doub
 
 extern "C" int cfp_bank_free(cfp_ctx* ctx, cfp_bank* bank) {
   if (!bank) return CFP_OK;
-  if (ctx) cudaSetDevice(ctx->device);
-  cudaFree(bank->blob_d);
-  cudaFree(bank->desc_d);
+  cfp_ctx* owner = bank->ctx ? bank->ctx : ctx;
+  if (owner) cudaSetDevice(owner->device);
+  cfp_dev_free(owner, bank->blob_d);
+  cfp_dev_free(owner, bank->desc_d);
   delete bank;
   return CFP_OK;
 }
@@ -138,9 +215,9 @@ extern "C" int cfp_bank_eval(cfp_ctx* ctx, const cfp_bank* bank, int cosmo, int 
       rc = CFP_ERR_CUDA;
     }
   }
-  cudaFree(z_d);
-  cudaFree(k_d);
-  cudaFree(o_d);
+  cfp_dev_free(ctx, z_d);
+  cfp_dev_free(ctx, k_d);
+  cfp_dev_free(ctx, o_d);
   return rc;
 }
 
@@ -182,7 +259,7 @@ extern "C" int cfp_peak_fp64(cfp_ctx* ctx, int kind, double* tflops_out) {
   const int blocks = ctx->sm_count * 8, threads = 256;
   const int iters = kind == 0 ? 8192 : 2048;
   double* out = nullptr;
-  CFP_CUDA(cudaMalloc((void**)&out, (size_t)blocks * threads * sizeof(double)));
+  CFP_CUDA(cfp_dev_alloc(ctx, (void**)&out, (size_t)blocks * threads * sizeof(double)));
   double best = 0.0;
   for (int rep = 0; rep < 4; ++rep) {  // first rep warms up
     CFP_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -200,7 +277,7 @@ extern "C" int cfp_peak_fp64(cfp_ctx* ctx, int kind, double* tflops_out) {
                                    : (double)blocks * (threads / 32) * iters * 8.0 * 512.0;
     if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
   }
-  cudaFree(out);
+  cfp_dev_free(ctx, out);
   *tflops_out = best;
   return CFP_OK;
 }

@@ -134,11 +134,13 @@ __global__ void __launch_bounds__(256) legendre_chi2_kernel(int Nk, int Z, const
 
 struct DevBufs {
   std::vector<void*> p;
+  cfp_ctx* owner = nullptr;
   ~DevBufs() {
-    for (void* q : p) cudaFree(q);
+    for (void* q : p) cfp_dev_free(owner, q);
   }
   template <typename T>
   int up(cfp_ctx* ctx, const T* h, size_t n, T** d) {
+    owner = ctx;
     int rc = cfp_upload<T>(ctx, h, n, d);
     if (rc == CFP_OK) p.push_back((void*)*d);
     return rc;

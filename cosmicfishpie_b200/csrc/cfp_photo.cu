@@ -476,6 +476,7 @@ struct cfp_photo_plan {
   double *T_d = nullptr, *eff_d = nullptr, *U_d = nullptr, *V_d = nullptr, *cls_d = nullptr, *Y_d = nullptr;
   double *Fl_d = nullptr, *fisher_d = nullptr;
   bool ran = false;
+  cudaStream_t last_st = nullptr;  // stream of the most recent run (the pool releases on the context stream)
   cudaEvent_t kev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<void*> owned;
 };
@@ -483,7 +484,7 @@ struct cfp_photo_plan {
 static void photo_free(cfp_photo_plan* p) {
   for (auto& e : p->kev)
     if (e) cudaEventDestroy(e);
-  for (void* q : p->owned) cudaFree(q);
+  for (void* q : p->owned) cfp_dev_free(p->ctx, q);
   delete p;
 }
 
@@ -591,7 +592,7 @@ extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, 
 extern "C" int cfp_photo_plan_destroy(cfp_photo_plan* plan) {
   if (!plan) return CFP_OK;
   cudaSetDevice(plan->ctx->device);
-  cudaStreamSynchronize(plan->ctx->stream);
+  if (plan->last_st && plan->last_st != plan->ctx->stream) cudaStreamSynchronize(plan->last_st);
   photo_free(plan);
   return CFP_OK;
 }
@@ -632,6 +633,7 @@ extern "C" int cfp_photo_plan_run(cfp_photo_plan* pl, void* stream) {
 
 static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
   cfp_ctx* ctx = pl->ctx;
+  pl->last_st = st;
   for (auto& e : pl->kev)
     if (!e) CFP_CUDA(cudaEventCreate(&e));
   CFP_CUDA(cudaEventRecord(pl->kev[0], st));
@@ -752,7 +754,8 @@ extern "C" int cfp_photo_plan_chi2(cfp_photo_plan* pl, const double* data_h, int
   double *w_d = nullptr, *data_d = nullptr, *lndet_d = nullptr, *q_d = nullptr, *chi2_d = nullptr;
   int rc = CFP_OK;
   auto cleanup = [&]() {
-    cudaFree(off_d), cudaFree(n_d), cudaFree(w_d), cudaFree(data_d), cudaFree(lndet_d), cudaFree(q_d), cudaFree(chi2_d);
+    for (void* q : {(void*)off_d, (void*)n_d, (void*)w_d, (void*)data_d, (void*)lndet_d, (void*)q_d, (void*)chi2_d})
+      cfp_dev_free(ctx, q);
   };
 #define CHI_TRY(x)            \
   do {                        \
@@ -808,7 +811,7 @@ extern "C" int cfp_photo_plan_chi2(cfp_photo_plan* pl, const double* data_h, int
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   float ms = 0.f;
   if (e == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
-  cudaFree(zero_d);
+  cfp_dev_free(ctx, zero_d);
   cleanup();
 #undef CHI_TRY
   if (e != cudaSuccess) {
@@ -865,8 +868,9 @@ extern "C" int cfp_cells_chi2(cfp_ctx* ctx, int S, int Nl, int Nb, const double*
   int *off_d = nullptr, *n_d = nullptr;
   double *w_d = nullptr, *th_d = nullptr, *data_d = nullptr, *zero_d = nullptr, *lndet_d = nullptr, *q_d = nullptr, *chi2_d = nullptr;
   auto cleanup = [&]() {
-    cudaFree(off_d), cudaFree(n_d), cudaFree(w_d), cudaFree(th_d), cudaFree(data_d), cudaFree(zero_d), cudaFree(lndet_d);
-    cudaFree(q_d), cudaFree(chi2_d);
+    for (void* q : {(void*)off_d, (void*)n_d, (void*)w_d, (void*)th_d, (void*)data_d, (void*)zero_d, (void*)lndet_d,
+                    (void*)q_d, (void*)chi2_d})
+      cfp_dev_free(ctx, q);
   };
   int rc;
 #define CHI_TRY(x)      \

@@ -737,6 +737,7 @@ struct cfp_spectro_plan {
   double *partial_d = nullptr, *fisher_d = nullptr;
   double *lnp_d = nullptr, *derivs_d = nullptr, *veff_d = nullptr;
   bool ran = false;
+  cudaStream_t last_st = nullptr;  // stream of the most recent run (the pool releases on the context stream)
   cudaEvent_t kev0 = nullptr, kev1 = nullptr;
   std::vector<void*> owned;
 };
@@ -744,11 +745,11 @@ struct cfp_spectro_plan {
 static void spectro_free(cfp_spectro_plan* p) {
   if (p->kev0) cudaEventDestroy(p->kev0);
   if (p->kev1) cudaEventDestroy(p->kev1);
-  for (void* q : p->owned) cudaFree(q);
-  cudaFree(p->lnp_d);
-  cudaFree(p->derivs_d);
-  cudaFree(p->veff_d);
-  cudaFree(p->partial_d);
+  for (void* q : p->owned) cfp_dev_free(p->ctx, q);
+  cfp_dev_free(p->ctx, p->lnp_d);
+  cfp_dev_free(p->ctx, p->derivs_d);
+  cfp_dev_free(p->ctx, p->veff_d);
+  cfp_dev_free(p->ctx, p->partial_d);
   delete p;
 }
 
@@ -880,7 +881,7 @@ extern "C" int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S
 extern "C" int cfp_spectro_plan_destroy(cfp_spectro_plan* plan) {
   if (!plan) return CFP_OK;
   cudaSetDevice(plan->ctx->device);
-  cudaStreamSynchronize(plan->ctx->stream);
+  if (plan->last_st && plan->last_st != plan->ctx->stream) cudaStreamSynchronize(plan->last_st);
   spectro_free(plan);
   return CFP_OK;
 }
@@ -955,7 +956,9 @@ extern "C" int cfp_spectro_plan_chi2(cfp_spectro_plan* pl, const double* data_h,
   // enough CTAs per (point, bin) to fill the GPU for small batches, few for large ones
   int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ntile, (4 * (int64_t)ctx->sm_count + (int64_t)S * Z - 1) / ((int64_t)S * Z)));
   double *data_d = nullptr, *shot_d = nullptr, *sd_d = nullptr, *part_d = nullptr, *chi2_d = nullptr;
-  auto cleanup = [&]() { cudaFree(data_d), cudaFree(shot_d), cudaFree(sd_d), cudaFree(part_d), cudaFree(chi2_d); };
+  auto cleanup = [&]() {
+    for (void* q : {(void*)data_d, (void*)shot_d, (void*)sd_d, (void*)part_d, (void*)chi2_d}) cfp_dev_free(ctx, q);
+  };
   int rc;
 #define CHI_TRY(x)      \
   do {                  \
@@ -1008,11 +1011,15 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
   CFP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   const size_t lattice = (size_t)pl->Nmu * pl->Nk;
-  if ((materialize & CFP_MAT_LNP) && !pl->lnp_d)
-    CFP_CUDA(cudaMalloc((void**)&pl->lnp_d, (size_t)pl->S * pl->Z * lattice * sizeof(double)));
+  bool allocated = false;
+  if ((materialize & CFP_MAT_LNP) && !pl->lnp_d) {
+    CFP_CUDA(cfp_dev_alloc(ctx, (void**)&pl->lnp_d, (size_t)pl->S * pl->Z * lattice * sizeof(double)));
+    allocated = true;
+  }
   if ((materialize & CFP_MAT_DERIVS) && !pl->derivs_d) {
-    CFP_CUDA(cudaMalloc((void**)&pl->derivs_d, (size_t)pl->npar * pl->Z * lattice * sizeof(double)));
-    CFP_CUDA(cudaMalloc((void**)&pl->veff_d, (size_t)pl->Z * lattice * sizeof(double)));
+    CFP_CUDA(cfp_dev_alloc(ctx, (void**)&pl->derivs_d, (size_t)pl->npar * pl->Z * lattice * sizeof(double)));
+    CFP_CUDA(cfp_dev_alloc(ctx, (void**)&pl->veff_d, (size_t)pl->Z * lattice * sizeof(double)));
+    allocated = true;
   }
   const int64_t ncell = pl->cell_end - pl->cell_begin;
   // two cells per thread when the lattice is big enough to still fill the GPU and the tile fits in smem
@@ -1026,11 +1033,16 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
   if (const char* em = getenv("CFP_SPECTRO_MINB")) minb = std::max(1, atoi(em));
   int gx = (int)std::min<int64_t>(ntile, std::max(1, (ctx->sm_count * minb + pl->Z - 1) / pl->Z));
   if (gx != pl->grid_x) {
-    cudaFree(pl->partial_d);
+    if (pl->partial_d && pl->last_st && pl->last_st != ctx->stream) CFP_CUDA(cudaStreamSynchronize(pl->last_st));
+    cfp_dev_free(ctx, pl->partial_d);
     pl->partial_d = nullptr;
-    CFP_CUDA(cudaMalloc((void**)&pl->partial_d, (size_t)pl->Z * gx * T * 64 * sizeof(double)));
+    CFP_CUDA(cfp_dev_alloc(ctx, (void**)&pl->partial_d, (size_t)pl->Z * gx * T * 64 * sizeof(double)));
     pl->grid_x = gx;
+    allocated = true;
   }
+  // pool allocations are ordered on the context stream; a caller's stream must not start before them
+  if (allocated && st != ctx->stream) CFP_CUDA(cudaStreamSynchronize(ctx->stream));
+  pl->last_st = st;
   CFP_CUDA(cudaEventRecord(ctx->ev0, st));
   SpectroParams P;
   spectro_fill_params(pl, materialize, P);
@@ -1146,8 +1158,9 @@ extern "C" int cfp_wedge_chi2(cfp_ctx* ctx, int S, int Z, int Nmu, int Nk, const
   double *th_d = nullptr, *da_d = nullptr, *k_d = nullptr, *wk_d = nullptr, *wmu_d = nullptr, *vol_d = nullptr;
   double *part_d = nullptr, *chi2_d = nullptr;
   auto cleanup = [&]() {
-    cudaFree(th_d), cudaFree(da_d), cudaFree(k_d), cudaFree(wk_d), cudaFree(wmu_d), cudaFree(vol_d), cudaFree(part_d);
-    cudaFree(chi2_d);
+    for (void* q : {(void*)th_d, (void*)da_d, (void*)k_d, (void*)wk_d, (void*)wmu_d, (void*)vol_d, (void*)part_d,
+                    (void*)chi2_d})
+      cfp_dev_free(ctx, q);
   };
   int rc = cfp_upload(ctx, theory_h, (size_t)S * Z * lattice, &th_d);
   if (rc == CFP_OK) rc = cfp_upload(ctx, data_h, (size_t)Z * lattice, &da_d);

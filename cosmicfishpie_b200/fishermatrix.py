@@ -231,12 +231,18 @@ class FisherMatrix:
     photo_LSS_fishermatrix = photo_LSS_fishermatrix_einsum
 
     # --- export -------------------------------------------------------------------------------
-    @staticmethod
-    def _git_version():
-        try:
-            return subprocess.check_output(["git", "rev-parse", "HEAD"], stderr=subprocess.DEVNULL).decode().strip()
-        except Exception:
-            return "unknown"
+    _git_version_cache = {}
+
+    @classmethod
+    def _git_version(cls):
+        cwd = os.getcwd()  # one `git rev-parse` per working directory, not one subprocess per Fisher matrix
+        if cwd not in cls._git_version_cache:
+            try:
+                v = subprocess.check_output(["git", "rev-parse", "HEAD"], stderr=subprocess.DEVNULL).decode().strip()
+            except Exception:
+                v = "unknown"
+            cls._git_version_cache[cwd] = v
+        return cls._git_version_cache[cwd]
 
     def export_fisher(self, fishmat, totaltime=None):
         """Write <results_dir>/<cf_version>_<outroot>_<obs>_FM{.txt,.paramnames,_specs.dat,_specs.json} and

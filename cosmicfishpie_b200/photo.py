@@ -203,6 +203,17 @@ class _PhotoGrid:
             raise NotImplementedError("modified-gravity Sigma(z,k) is not supported")
 
 
+def _ngal_rows(win, g: _PhotoGrid) -> np.ndarray:
+    """Normalised n_i(z) of every tomographic row on the job's z grid, cached on the window object."""
+    cache = win.__dict__.setdefault("_ngal_rows_cache", {})
+    key = (g.zsamp, float(g.z_min), float(g.z_max), tuple(g.rows))
+    if key not in cache:
+        arr = np.array([win.norm_ngal_photoz(g.z, i, o) for o, i in g.rows])
+        arr.setflags(write=False)
+        cache[key] = arr
+    return cache[key]
+
+
 class PhotoJob:
     """One photometric job on the device: stencil points (parameter dictionaries) -> C_ell of each and,
     if a stencil is given, the Fisher matrix."""
@@ -218,6 +229,10 @@ class PhotoJob:
         self.cosmo_of_s = np.zeros(S, dtype=np.int32)
         self.bias = np.ones((S, Nb, Nz))
         self.ia = np.zeros((S, Nz))
+        # most stencil points share their nuisance values with the fiducial: evaluate each distinct
+        # (IA parameters, cosmology) window and each distinct bias row once
+        ia_memo, bias_memo = {}, {}
+        per_bin_bias = cfg.Photobiasparams.get("bias_model") == "binned_constant"
         for s, ap in enumerate(points):
             photopars = {k: ap[k] for k in fid_photo}
             if photopars != fid_photo:
@@ -226,19 +241,28 @@ class PhotoJob:
             c = cs.add(cp)
             self.cosmo_of_s[s] = c
             if "WL" in g.observables:
-                self.ia[s] = nuis.IA({k: ap[k] for k in cfg.IAparams}, cs.cosmos[c])(g.z)
+                key = (c,) + tuple(ap[k] for k in cfg.IAparams)
+                if key not in ia_memo:
+                    ia_memo[key] = nuis.IA({k: ap[k] for k in cfg.IAparams}, cs.cosmos[c])(g.z)
+                self.ia[s] = ia_memo[key]
             if "GCph" in g.observables:
-                bp = {k: ap[k] for k in cfg.Photobiasparams}
+                bkey = tuple(ap[k] for k in cfg.Photobiasparams)
+                bp = None
                 for a, (o, i) in enumerate(g.rows):
                     if o == "GCph":
-                        self.bias[s, a] = nuis.gcph_bias(bp, i)(g.z)
+                        key = bkey + ((i,) if per_bin_bias else ())
+                        if key not in bias_memo:
+                            if bp is None:
+                                bp = {k: ap[k] for k in cfg.Photobiasparams}
+                            bias_memo[key] = nuis.gcph_bias(bp, i)(g.z)
+                        self.bias[s, a] = bias_memo[key]
         NC = len(cs)
         self.chi = np.array([c.comoving(g.z) for c in cs.cosmos])
         self.hub = np.array([c.Hubble(g.z) for c in cs.cosmos])
         self.wlpref = np.array([(3.0 / 2.0) * c.Hubble(0.0) ** 2.0 * c.Omegam_of_z(0.0) for c in cs.cosmos])
         win = galaxy_photo_dist(fid_photo, configuration)
         self.window = win
-        self.ngal = np.array([win.norm_ngal_photoz(g.z, i, o) for o, i in g.rows])
+        self.ngal = _ngal_rows(win, g)
         self.stw, self.stden = np.asarray(stw, float), np.asarray(stden, float)
         self.NC = NC
         self._plan = None
@@ -318,7 +342,7 @@ class PhotoJob:
         self.wlpref = np.array([(3.0 / 2.0) * c.Hubble(0.0) ** 2.0 * c.Omegam_of_z(0.0) for c in cs.cosmos])
         win_ = galaxy_photo_dist(cfg.photoparams, configuration)
         self.window = win_
-        self.ngal = np.array([win_.norm_ngal_photoz(g.z, i, o) for o, i in g.rows])
+        self.ngal = _ngal_rows(win_, g)
         self.stw, self.stden = np.zeros((1, B)), np.ones(1)
         self.NC = len(cs)
         self._plan = None
@@ -481,7 +505,7 @@ class PhotoCov:
                 if m == 0:
                     row[0] = row.get(0, 0.0) + w
                     continue
-                ap = copy.deepcopy(self.allparsfid)
+                ap = dict(self.allparsfid)  # flat {name: number}
                 ap[par] = ap[par] + m * h
                 points.append(ap)
                 row[len(points) - 1] = w

@@ -28,18 +28,24 @@ def moving_average(data, periods=2):
     return np.convolve(data, np.ones(periods) / periods, mode="valid")
 
 
+def _isclose(a, b):
+    """np.isclose(a, b) for finite scalars with numpy's default tolerances (asymmetric in b)."""
+    return abs(a - b) <= 1e-8 + 1e-5 * abs(b)
+
+
 def bisection(array, value):
     """Bin lookup with np.isclose edge rules (reference: utilities/utils.py:131-155)."""
-    array = np.asarray(array)
+    array = [float(a) for a in array]
+    value = float(value)
     n = len(array)
-    if np.isclose(value, array[0]) or value < array[0]:
+    if _isclose(value, array[0]) or value < array[0]:
         return 0
-    if np.isclose(value, array[-1]) or value > array[-1]:
+    if _isclose(value, array[-1]) or value > array[-1]:
         return n - 2
     lo, hi = 0, n - 1
     while lo < hi:
         mid = (lo + hi) // 2
-        if np.isclose(array[mid], value):
+        if _isclose(array[mid], value):
             return mid
         if array[mid] < value:
             lo = mid + 1
@@ -140,14 +146,16 @@ class ComputeGalSpectro:
         cfg = getattr(configuration, "config", configuration)  # a FisherMatrix duck-types as a config
         self._cfg = cfg
         self.feed_lvl = configuration.settings["feedback"]
-        self.observables = copy.deepcopy(configuration.obs)
-        self.specs = copy.deepcopy(configuration.specs)
+        # private top-level copies: only top-level keys ("kmax", "kmin") are rebound below, nested
+        # specification entries are read-only here, so one level is enough
+        self.observables = list(configuration.obs)
+        self.specs = dict(configuration.specs)
         self.settings = configuration.settings
         self.s8terms = self.settings["bfs8terms"]
         self.tracer = self.settings["GCsp_Tracer"]
         if self.tracer != "matter":
             raise NotImplementedError("GCsp_Tracer='clustering' (cb tables) is not supported")
-        self.fiducial_cosmopars = copy.deepcopy(cfg.fiducialparams if fiducial_cosmopars is None else fiducial_cosmopars)
+        self.fiducial_cosmopars = dict(cfg.fiducialparams if fiducial_cosmopars is None else fiducial_cosmopars)
         if self.fiducial_cosmopars != cfg.fiducialparams:
             raise AttributeError("fiducial_cosmopars not equal to the configuration's fiducialparams")
         self.fiducialcosmo = cfg.fiducialcosmo
@@ -155,18 +163,18 @@ class ComputeGalSpectro:
         self.cosmo_set = cosmo_set if cosmo_set is not None else _cosmo_set_of(cfg)
         self.cosmo_index = self.cosmo_set.add(cosmopars)
         self.cosmo = self.cosmo_set.cosmos[self.cosmo_index]
-        self.fiducial_spectrobiaspars = copy.deepcopy(cfg.Spectrobiasparams)
+        self.fiducial_spectrobiaspars = dict(cfg.Spectrobiasparams)
         self.spectrobiaspars = self.fiducial_spectrobiaspars if spectrobiaspars is None else spectrobiaspars
-        self.fiducial_spectrononlinearpars = copy.deepcopy(cfg.Spectrononlinearparams)
+        self.fiducial_spectrononlinearpars = dict(cfg.Spectrononlinearparams)
         self.spectrononlinearpars = (
             self.fiducial_spectrononlinearpars if spectrononlinearpars is None else spectrononlinearpars
         )
-        self.fiducial_IMbiaspars = copy.deepcopy(cfg.IMbiasparams)
+        self.fiducial_IMbiaspars = dict(cfg.IMbiasparams)
         self.IMbiaspars = self.fiducial_IMbiaspars if IMbiaspars is None else IMbiaspars
         self.nuisance = SpectroNuisance(self.specs, self.spectrobiaspars, self.spectrononlinearpars)
         self.extraPshot = self.nuisance.extra_Pshot_noise()
         self.gcsp_z_bin_mids = self.nuisance.gcsp_zbins_mids()
-        self.fiducial_PShotpars = copy.deepcopy(cfg.PShotparams)
+        self.fiducial_PShotpars = dict(cfg.PShotparams)
         self.PShotpars = self.fiducial_PShotpars if PShotpars is None else PShotpars
         self.allpars = {**self.cosmopars, **self.spectrobiaspars, **self.IMbiaspars, **self.PShotpars,
                         **self.spectrononlinearpars}
@@ -432,7 +440,7 @@ class SpectroJob:
                 if m == 0:
                     row[0] = row.get(0, 0.0) + w
                     continue
-                ap = copy.deepcopy(fid_all)
+                ap = dict(fid_all)  # flat {name: number}
                 ap[par] = ap[par] + m * h
                 points.append(self._point(ap, cfg, cs))
                 point_pars.append(ap)

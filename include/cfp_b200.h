@@ -79,6 +79,17 @@ int cfp_peak_fp64(cfp_ctx* ctx, int kind, double* tflops_out);
 int cfp_bank_upload(cfp_ctx* ctx, const double* blob_h, size_t n_doubles, const int64_t* desc_h,
                     int n_cosmo, int n_tables, cfp_bank** out);
 int cfp_bank_free(cfp_ctx* ctx, cfp_bank* bank);
+
+/* The same bank assembled from one host block per cosmology (rows_h[c], row_len[c] doubles), so that a caller
+ * that caches the fitted tables of each cosmology (cosmology.py:1249-1540 caches them per `cosmo_functions`
+ * instance) re-uploads them without re-packing.  desc_h offsets are in doubles from the start of the
+ * cosmology's OWN row.  Rows allocated with cfp_host_alloc are page-locked and copy at full PCIe rate.   */
+int cfp_bank_upload_rows(cfp_ctx* ctx, const double* const* rows_h, const int64_t* row_len,
+                         const int64_t* desc_h, int n_cosmo, int n_tables, cfp_bank** out);
+
+/* Page-locked host memory for buffers that are uploaded repeatedly (table rows, likelihood batches). */
+int cfp_host_alloc(cfp_ctx* ctx, size_t bytes, void** out);
+int cfp_host_free(cfp_ctx* ctx, void* p);
 /* Point-wise bicubic evaluation, semantics of FITPACK bispeu / RectBivariateSpline.__call__
  * (grid=False), including clamping of the arguments to the knot range
  * (cosmology.py:1736-1738, 1876, 1944).  x = z, y = k, n points, out_h[n]. */

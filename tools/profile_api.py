@@ -1,0 +1,63 @@
+"""cProfile of the public-API forecast (`FisherMatrix(...).compute()`, warm process caches) on the GPU box:
+where the host side of `bench.py`'s e2e number goes.  Usage: python tools/profile_api.py [n_iter] [out.txt]"""
+import cProfile
+import io
+import os
+import pstats
+import sys
+import tempfile
+import time
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+import bench  # noqa: E402
+from cosmicfishpie_b200 import toy_tables as tt  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+    out = sys.argv[2] if len(sys.argv) > 2 else None
+    tmp = tempfile.mkdtemp(prefix="cfp_prof_")
+    bank = tt.make_bank(eps_values=(0.01,))
+
+    def step(which):
+        res = []
+        if which in ("photo", "both"):
+            a = bench.make_photo_fm(bank, tmp)
+            res.append(a.compute())
+            a.photo_LSS._job.close()
+            a.photo_LSS._job.cosmo_set.bank().close()
+        if which in ("spectro", "both"):
+            b = bench.make_spectro_fm(bank, tmp)
+            res.append(b.compute())
+            b._spectro_job.close()
+            b._spectro_job.cosmo_set.bank().close()
+        return res
+
+    step("both")
+    step("both")
+    buf = io.StringIO()
+    for which in ("photo", "spectro"):
+        t0 = time.perf_counter()
+        for _ in range(n):
+            step(which)
+        dt = (time.perf_counter() - t0) / n
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(n):
+            step(which)
+        pr.disable()
+        buf.write(f"==== {which}: {dt * 1e3:.2f} ms per forecast (unprofiled), n={n}\n")
+        ps = pstats.Stats(pr, stream=buf).strip_dirs().sort_stats("cumulative")
+        ps.print_stats(45)
+        ps.sort_stats("tottime").print_stats(30)
+    txt = buf.getvalue()
+    if out:
+        open(out, "w").write(txt)
+    else:
+        print(txt)
+
+
+if __name__ == "__main__":
+    main()
