@@ -181,6 +181,26 @@ class cosmo_functions:
         raise AttributeError(name)
 
     # --- host accessors --------------------------------------------------------------------
+    def scalar(self, name, z):
+        """`getattr(self, name)(z)` for a scalar redshift, remembered: jobs ask for the same few background
+        values at the same bin centres again and again."""
+        memo = self.__dict__.setdefault("_scalar_memo", {})
+        key = (name, float(z))
+        if key not in memo:
+            memo[key] = getattr(self, name)(z)
+        return memo[key]
+
+    def on_grid(self, name, z):
+        """`getattr(self, name)(z)` on a redshift grid, remembered per grid (read-only result)."""
+        memo = self.__dict__.setdefault("_grid_memo", {})
+        z = np.ascontiguousarray(z, dtype=float)
+        key = (name, z.tobytes())
+        if key not in memo:
+            v = np.asarray(getattr(self, name)(z))
+            v.setflags(write=False)
+            memo[key] = v
+        return memo[key]
+
     def Hubble(self, z, physical=False):
         return (self.c if physical else 1) * self.h_of_z(z)
 

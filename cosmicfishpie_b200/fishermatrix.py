@@ -287,14 +287,15 @@ class FisherMatrix:
             return o
 
         try:
-            with open(root + "_specs.json", "w") as jf:
-                json.dump({"metadata": {"cf_version": self.cf_version, "git_commit": git,
-                                        "observables": list(self.observables),
-                                        "totaltime_sec": None if totaltime is None else float(totaltime),
-                                        "backend": "cosmicfishpie_b200"},
-                           "options": _jsonify(self.settings), "specifications": _jsonify(self.specs),
-                           "fiducialpars": _jsonify(self.fiducialcosmopars), "freepars": _jsonify(self.freeparams),
-                           "allparams": _jsonify(self.allparams)}, jf, indent=2)
+            text = json.dumps({"metadata": {"cf_version": self.cf_version, "git_commit": git,
+                                            "observables": list(self.observables),
+                                            "totaltime_sec": None if totaltime is None else float(totaltime),
+                                            "backend": "cosmicfishpie_b200"},
+                               "options": _jsonify(self.settings), "specifications": _jsonify(self.specs),
+                               "fiducialpars": _jsonify(self.fiducialcosmopars),
+                               "freepars": _jsonify(self.freeparams), "allparams": _jsonify(self.allparams)}, indent=2)
+            with open(root + "_specs.json", "w") as jf:  # one write instead of one per token
+                jf.write(text)
         except Exception:  # best effort, like the reference
             pass
         return out

@@ -147,13 +147,13 @@ class PhotoNuisance:
     def IA(self, IApars, cosmo):
         if IApars["IA_model"] != "eNLA":
             raise ValueError("only the eNLA intrinsic alignment model exists")
-        Om = cosmo.Omegam_of_z(0.0)
+        Om = cosmo.scalar("Omegam_of_z", 0.0)
         piv = self.settings["pivot_z_IA"]
         z = self.z
         CIA = 0.0134 * (1 + piv)
         fac = -IApars["AIA"] * CIA * Om
         z_dep = (1 + z) / (1 + piv)
-        win = fac * z_dep ** IApars["etaIA"] * ((self._lum_z ** IApars["betaIA"]) / (cosmo.growth(z).flatten()))
+        win = fac * z_dep ** IApars["etaIA"] * ((self._lum_z ** IApars["betaIA"]) / (cosmo.on_grid("growth", z).flatten()))
         return InterpolatedUnivariateSpline(z, win, k=1)
 
 
@@ -257,9 +257,10 @@ class PhotoJob:
                             bias_memo[key] = nuis.gcph_bias(bp, i)(g.z)
                         self.bias[s, a] = bias_memo[key]
         NC = len(cs)
-        self.chi = np.array([c.comoving(g.z) for c in cs.cosmos])
-        self.hub = np.array([c.Hubble(g.z) for c in cs.cosmos])
-        self.wlpref = np.array([(3.0 / 2.0) * c.Hubble(0.0) ** 2.0 * c.Omegam_of_z(0.0) for c in cs.cosmos])
+        self.chi = np.array([c.on_grid("comoving", g.z) for c in cs.cosmos])
+        self.hub = np.array([c.on_grid("Hubble", g.z) for c in cs.cosmos])
+        self.wlpref = np.array([(3.0 / 2.0) * c.scalar("Hubble", 0.0) ** 2.0 * c.scalar("Omegam_of_z", 0.0)
+                                for c in cs.cosmos])
         win = galaxy_photo_dist(fid_photo, configuration)
         self.window = win
         self.ngal = _ngal_rows(win, g)
@@ -310,8 +311,8 @@ class PhotoJob:
             A, eta, beta = column("AIA", ia["AIA"]), column("etaIA", ia["etaIA"]), column("betaIA", ia["betaIA"])
             piv = nuis.settings["pivot_z_IA"]
             zz = nuis.z
-            Om = np.array([c.Omegam_of_z(0.0) for c in cs.cosmos])[self.cosmo_of_s]
-            growth = np.array([c.growth(zz).flatten() for c in cs.cosmos])[self.cosmo_of_s]      # [B, 50]
+            Om = np.array([c.scalar("Omegam_of_z", 0.0) for c in cs.cosmos])[self.cosmo_of_s]
+            growth = np.array([c.on_grid("growth", zz).flatten() for c in cs.cosmos])[self.cosmo_of_s]  # [B, 50]
             fac = -A * (0.0134 * (1 + piv)) * Om
             z_dep = (1 + zz) / (1 + piv)
             win = fac[:, None] * z_dep[None, :] ** eta[:, None] * ((nuis._lum_z[None, :] ** beta[:, None]) / growth)
@@ -337,9 +338,10 @@ class PhotoJob:
                 for s, b in enumerate(pts):
                     for a in gc_rows:
                         self.bias[s, a] = nuis.gcph_bias(b, g.rows[a][1])(g.z)
-        self.chi = np.array([c.comoving(g.z) for c in cs.cosmos])
-        self.hub = np.array([c.Hubble(g.z) for c in cs.cosmos])
-        self.wlpref = np.array([(3.0 / 2.0) * c.Hubble(0.0) ** 2.0 * c.Omegam_of_z(0.0) for c in cs.cosmos])
+        self.chi = np.array([c.on_grid("comoving", g.z) for c in cs.cosmos])
+        self.hub = np.array([c.on_grid("Hubble", g.z) for c in cs.cosmos])
+        self.wlpref = np.array([(3.0 / 2.0) * c.scalar("Hubble", 0.0) ** 2.0 * c.scalar("Omegam_of_z", 0.0)
+                                for c in cs.cosmos])
         win_ = galaxy_photo_dist(cfg.photoparams, configuration)
         self.window = win_
         self.ngal = _ngal_rows(win_, g)

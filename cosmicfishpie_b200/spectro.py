@@ -203,10 +203,10 @@ class ComputeGalSpectro:
 
     # --- cheap host scalars (same formulas as the reference) ----------------------------------
     def qparallel(self, z):
-        return self.fiducialcosmo.Hubble(z) / self.cosmo.Hubble(z)
+        return self.fiducialcosmo.scalar("Hubble", z) / self.cosmo.scalar("Hubble", z)
 
     def qperpendicular(self, z):
-        return self.cosmo.angdist(z) / self.fiducialcosmo.angdist(z)
+        return self.cosmo.scalar("angdist", z) / self.fiducialcosmo.scalar("angdist", z)
 
     def BAO_term(self, z):
         return 1 / (self.qperpendicular(z) ** 2 * self.qparallel(z)) if self.APbool else 1
@@ -242,7 +242,7 @@ class ComputeGalSpectro:
         b[_lib.SP_COSMO] = self.cosmo_index
         b[_lib.SP_QPAR] = self.qparallel(z)
         b[_lib.SP_QPER] = self.qperpendicular(z)
-        b[_lib.SP_HUBBLE] = self.cosmo.Hubble(z)
+        b[_lib.SP_HUBBLE] = self.cosmo.scalar("Hubble", z)
         b[_lib.SP_DZ] = self.dz_err if self.dz_type == "constant" else self.dz_err * (1 + z)
         b[_lib.SP_BIAS] = self.nuisance.gcsp_bias_at_z(z)
         b[_lib.SP_A1], b[_lib.SP_A2] = self.nuisance.qbias_coeffs()
@@ -254,7 +254,7 @@ class ComputeGalSpectro:
             self.nuisance.gcsp_rescale_sigmapv_at_z(z, sigma_key="sigmav") if self.rescale_sigmav else 1.0
         )
         if self.s8terms:
-            s8 = float(self.cosmo.sigma8_of_z(z))
+            s8 = float(self.cosmo.scalar("sigma8_of_z", z))
             b[_lib.SP_FS8], b[_lib.SP_INVS8SQ] = s8, 1.0 / s8**2
         else:
             b[_lib.SP_FS8], b[_lib.SP_INVS8SQ] = 1.0, 1.0
