@@ -28,7 +28,6 @@ namespace {
 
 constexpr int TILE = 256;       // cells per CTA tile (= threads per CTA)
 constexpr int LDPAD = 4;        // row padding of the derivative tile (bank-conflict free DMMA loads)
-constexpr int LD = TILE + LDPAD;
 constexpr int MAX_NB = 6;       // npar <= 48
 constexpr double INV_8PI2 = 0.012665147955292222;  // 1/(8 pi^2)
 constexpr int CUBIC_BLK = 6;    // doubles per cubic piece:  [lo, hi, c0, c1, c2, c3]
@@ -38,6 +37,8 @@ constexpr int LIN_BLK = 4;      // doubles per linear piece: [lo, hi, y, slope]
 // spectro_setup_kernel instead of once per thread per cell.
 struct SDev {
   double rqpar, rqper, dzH, bias, A1, A2, sigmap, I0, I12, svr2, fs8, invs8sq, khfac, bao, pshot, w0;
+  double xminA, xmaxA, xminB, xmaxB;  // knot range of the P_lin / f tables (FITPACK clamps the argument to it)
+  double baos;                        // bao * invs8sq
   const double *blkA, *blkB, *blkN;  // piece tables of P_lin(k), f(k), P_nw(k) at this (cosmology, z)
   int nA, nB, nN;                    // number of pieces
   int flags;                         // SD_*
@@ -45,6 +46,18 @@ struct SDev {
   int csr0, csr1;                    // further (parameter, weight) pairs in the CSR arrays
 };
 enum { SD_OWN = 1, SD_QBIAS = 2, SD_SHARED_KNOTS = 4, SD_SRC = 8, SD_PSHOT = 16 };
+
+// What one (stencil point, z-bin) needs per mu ROW of the lattice: with the Alcock-Paczynski remap
+// k' = k G(mu), mu' = mu'(mu) every mu-dependent factor of P_obs is constant along a row, so the cell loop
+// is left with k' = k G, the three table look-ups, one exp, one division and one log.
+struct RowC {
+  double G;     // k' / k
+  double fmu2;  // fs8 * mu'^2              (Kaiser: bias + f(k') * fmu2)
+  double errc;  // err / k                  (spectroscopic redshift error exponent = (k errc)^2)
+  double sv2;   // (I0 + mu'^2 I12) svr2    (dewiggling damping exponent = sv2 k'^2)
+  double fogc;  // mu' sigma_p              (Lorentzian FoG: 1 + (k' fogc)^2)
+  double pad;
+};
 
 struct SpectroParams {
   int S, Z, Nmu, Nk, npar, nb, nnw, NC;
@@ -222,6 +235,11 @@ __global__ void spectro_setup_kernel(SpectroParams P) {
     o.nA = (int)dA[1] - 7;
     o.nB = (int)dB[1] - 7;
     o.nN = P.nnw - 1;
+    o.xminA = o.blkA[0];
+    o.xmaxA = o.blkA[(size_t)(o.nA - 1) * CUBIC_BLK + 1];
+    o.xminB = o.blkB[0];
+    o.xmaxB = o.blkB[(size_t)(o.nB - 1) * CUBIC_BLK + 1];
+    o.baos = o.bao * o.invs8sq;
     const bool shared = P.shared_knots[c] != 0;
     const bool own = (s == 0) || (P.alias[s * P.Z + zb] == s);
     o.flags = (own ? SD_OWN : 0) | ((o.A1 != 0.0 || o.A2 != 0.0) ? SD_QBIAS : 0) | (shared ? SD_SHARED_KNOTS : 0) |
@@ -372,53 +390,61 @@ __device__ __forceinline__ double cubic_at(const double* __restrict__ blk, int j
   return c01.x + u * (c01.y + u * (c23.x + u * c23.y));
 }
 
-// X = P_obs / exp(-err^2) and err^2 (so that ln P_obs = ln X - err^2 needs a single log and no exp)
-__device__ __forceinline__ double eval_x(const SDev& p, unsigned flags, double k, double mu, double smu, int& hA,
-                                         int& hB, int& hN, double& err2) {
-  // spectroscopic redshift error on the pre-AP wavenumber (spectro_obs.py:476-506, 880-889)
-  const double kerr = (flags & CFP_SPF_KH_BEFORE_ERR) ? k * p.khfac : k;
-  const double err = p.dzH * (kerr * mu * p.rqpar);
-  err2 = err * err;
-  const double kk = k * p.khfac;
-  double kap = kk, muap = mu;
-  if (flags & CFP_SPF_AP) {  // spectro_obs.py:441-474
-    const double kpar = kk * mu * p.rqpar;
-    const double kper = kk * smu * p.rqper;
-    const double s2 = kpar * kpar + kper * kper;
-    const double r = fast_rsqrt(s2);
-    kap = s2 * r;
-    muap = kpar * r;
+// Row constants of one (stencil point, bin) at one mu (spectro_obs.py:441-506: AP remap and redshift error)
+__device__ __forceinline__ RowC row_consts(const SDev& p, unsigned flags, double mu, double smu) {
+  RowC r;
+  const double mpar = mu * p.rqpar;
+  double R = 1.0, muap = mu;
+  if (flags & CFP_SPF_AP) {
+    const double mper = smu * p.rqper;
+    const double s2 = mpar * mpar + mper * mper;
+    const double ri = fast_rsqrt(s2);
+    R = s2 * ri;
+    muap = mpar * ri;
   }
+  r.G = p.khfac * R;
   const double mu2 = muap * muap;
+  r.fmu2 = p.fs8 * mu2;
+  r.errc = p.dzH * (((flags & CFP_SPF_KH_BEFORE_ERR) ? p.khfac : 1.0) * mpar);
+  r.sv2 = (p.I0 + mu2 * p.I12) * p.svr2;
+  r.fogc = muap * p.sigmap;
+  r.pad = 0.0;
+  return r;
+}
+
+// X = P_obs / exp(-err^2) and err^2 (so that ln P_obs = ln X - err^2 needs a single log and no exp)
+__device__ __forceinline__ double eval_x(const SDev& p, const RowC& rc, unsigned flags, double k, int& hA, int& hB,
+                                         int& hN, double& err2) {
+  const double err = k * rc.errc;
+  err2 = err * err;
+  const double kap = k * rc.G;
   double bterm = p.bias;
   if (p.flags & SD_QBIAS) bterm *= fast_div(1.0 + kap * kap * p.A2, 1.0 + kap * p.A1);
   // tabulated P_lin(k'), f(k') (FITPACK clamps the argument to the knot range)
   double lo;
-  double x = fmin(fmax(kap, __ldg(p.blkA)), __ldg(p.blkA + (size_t)(p.nA - 1) * CUBIC_BLK + 1));
+  double x = fmin(fmax(kap, p.xminA), p.xmaxA);
   hA = locate<CUBIC_BLK>(p.blkA, p.nA, x, hA, lo);
   double u = x - lo;
-  const double pdd = cubic_at(p.blkA, hA, u) * p.invs8sq;
+  const double pdd = cubic_at(p.blkA, hA, u);
   if (p.flags & SD_SHARED_KNOTS) {
     hB = hA;
   } else {
-    x = fmin(fmax(kap, __ldg(p.blkB)), __ldg(p.blkB + (size_t)(p.nB - 1) * CUBIC_BLK + 1));
+    x = fmin(fmax(kap, p.xminB), p.xmaxB);
     hB = locate<CUBIC_BLK>(p.blkB, p.nB, x, hB, lo);
     u = x - lo;
   }
-  const double fg = cubic_at(p.blkB, hB, u) * p.fs8;
-  const double kaiser = bterm + fg * mu2;  // spectro_obs.py:584-637
-  double num = p.bao * (kaiser * kaiser);
+  const double kaiser = fma(cubic_at(p.blkB, hB, u), rc.fmu2, bterm);  // spectro_obs.py:584-637
+  double num = p.baos * (kaiser * kaiser);
   if (!(flags & CFP_SPF_LINEAR)) {
     // dewiggling, spectro_obs.py:699-722, 811-843; degree-1 spline with extrapolation
     hN = locate<LIN_BLK>(p.blkN, p.nN, kap, hN, lo);
     const double2 ys = __ldg(reinterpret_cast<const double2*>(p.blkN + (size_t)hN * LIN_BLK + 2));
-    const double pnw = (ys.x + ys.y * (kap - lo)) * p.invs8sq;
-    const double sv2 = (p.I0 + mu2 * p.I12) * p.svr2;
-    const double e = fast_exp_neg(-sv2 * (kap * kap));
-    num *= pnw + e * (pdd - pnw);  // pdd e + pnw (1 - e)
-    if (flags & CFP_SPF_FOG) {     // Lorentzian FoG, spectro_obs.py:639-676
-      const double t = kap * muap * p.sigmap;
-      num = fast_div(num, 1.0 + t * t);
+    const double pnw = fma(ys.y, kap - lo, ys.x);
+    const double e = fast_exp_neg(-rc.sv2 * (kap * kap));
+    num *= fma(e, pdd - pnw, pnw);  // pdd e + pnw (1 - e)
+    if (flags & CFP_SPF_FOG) {      // Lorentzian FoG, spectro_obs.py:639-676
+      const double t = kap * rc.fogc;
+      num = fast_div(num, fma(t, t, 1.0));
     }
   } else {
     num *= pdd;
@@ -432,25 +458,27 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// CPT = lattice cells per thread: two independent evaluation chains per thread hide the FP64 latency
-// (Horner chains of exp/log/spline pieces) that 16 resident warps per SM cannot hide alone.
 // Resident CTAs per SM the kernel is compiled for: 64 registers/thread (4 CTAs, 32 warps per SM) still fit the
 // evaluation without spills when the Gram tile is small; measured 1.83 -> 1.30 ms against 2 CTAs per SM.
+// (Two cells per thread were tried and lost to one cell per thread at higher occupancy: profiles/r1c.)
 constexpr int fisher_min_blocks(int nb) { return nb <= 2 ? 4 : (nb == 3 ? 3 : 2); }
+constexpr int MAX_STAGED_ROWS = 4;  // mu rows a 256-cell tile may touch and still stage its row constants
 
-template <int NB, int CPT, int MINB = fisher_min_blocks(NB)>
-__global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParams P) {
+// STAGED: the row constants of the (at most nrows) mu rows a tile touches are computed once per tile into
+// shared memory by a few threads; otherwise (tiny Nk: a tile spans many rows) every thread derives its own.
+template <int NB, bool STAGED, int MINB = fisher_min_blocks(NB)>
+__global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParams P, int nrows) {
   constexpr int T = NB * (NB + 1) / 2;
-  constexpr int CELLS = TILE * CPT;
-  constexpr int LDC = CELLS + LDPAD;
+  constexpr int LDC = TILE + LDPAD;
   extern __shared__ double smem[];
-  double* sm_d = smem;                    // [NB*8][LDC]
-  double* sm_w = smem + NB * 8 * LDC;     // [CELLS]
-  SDev* sm_s = reinterpret_cast<SDev*>(sm_w + CELLS);  // [S]
+  double* sm_d = smem;                                 // [NB*8][LDC]
+  double* sm_w = smem + NB * 8 * LDC;                  // [TILE]
+  SDev* sm_s = reinterpret_cast<SDev*>(sm_w + TILE);   // [S]
+  RowC* sm_r = reinterpret_cast<RowC*>(sm_s + P.S);    // [nrows][S]   (STAGED only)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int zb = blockIdx.y;
   const int64_t ncell = P.cell_end - P.cell_begin;
-  const int64_t ntile = (ncell + CELLS - 1) / CELLS;
+  const int64_t ntile = (ncell + TILE - 1) / TILE;
   const int64_t lattice = (int64_t)P.Nmu * P.Nk;
   {
     const int nwords = P.S * (int)(sizeof(SDev) / sizeof(double));
@@ -469,101 +497,96 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
   const double nbar = P.nbar[zb], vol = P.vol[zb];
 
   for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
-    int64_t cell[CPT];
-    bool valid[CPT];
-    int mi[CPT], ki[CPT];
-    double k[CPT], mu[CPT], smu[CPT];
-    int hA[CPT], hB[CPT], hN[CPT];
-    double P0[CPT], lnP0[CPT], Psrc[CPT];
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      cell[c] = P.cell_begin + tile * CELLS + c * TILE + tid;
-      valid[c] = cell[c] < P.cell_end;
-      mi[c] = valid[c] ? (int)(cell[c] / P.Nk) : 0;
-      ki[c] = valid[c] ? (int)(cell[c] - (int64_t)mi[c] * P.Nk) : 0;
-      k[c] = __ldg(P.k + ki[c]);
-      mu[c] = __ldg(P.mu + mi[c]);
-      smu[c] = __ldg(P.smu + mi[c]);
-      hA[c] = hB[c] = hN[c] = -1;
-      P0[c] = Psrc[c] = 1.0;
-      lnP0[c] = 0.0;
-#pragma unroll 4
-      for (int p = 0; p < NB * 8; ++p) sm_d[p * LDC + c * TILE + tid] = 0.0;
+    const int64_t cell0 = P.cell_begin + tile * TILE;
+    const int64_t cell = cell0 + tid;
+    const bool valid = cell < P.cell_end;
+    const int mi = valid ? (int)(cell / P.Nk) : 0;
+    const int ki = valid ? (int)(cell - (int64_t)mi * P.Nk) : 0;
+    const double k = __ldg(P.k + ki);
+    const RowC* myrow = nullptr;
+    double mu = 0.0, smu = 0.0;
+    if (STAGED) {
+      const int r0 = (int)(cell0 / P.Nk);
+      __syncthreads();  // every warp is done with the previous tile's rows
+      for (int t = tid; t < nrows * nwork; t += TILE) {
+        const int rs = t / nwork, s = work[t - rs * nwork];
+        const int r = min(r0 + rs, P.Nmu - 1);
+        if (sm_s[s].flags & SD_OWN) sm_r[rs * P.S + s] = row_consts(sm_s[s], P.flags, __ldg(P.mu + r), __ldg(P.smu + r));
+      }
+      __syncthreads();
+      myrow = sm_r + (valid ? mi - r0 : 0) * P.S;
+    } else {
+      mu = __ldg(P.mu + mi);
+      smu = __ldg(P.smu + mi);
     }
+    int hA = -1, hB = -1, hN = -1;
+    double P0 = 1.0, Psrc = 1.0, lnP0 = 0.0;
+#pragma unroll 4
+    for (int p = 0; p < NB * 8; ++p) sm_d[p * LDC + tid] = 0.0;
     for (int wi = 0; wi < nwork; ++wi) {
       const int s = work[wi];
       const SDev& sp = sm_s[s];
-      double lnP[CPT], Pobs[CPT];
+      double lnP, Pobs;
       if (sp.flags & SD_OWN) {
-        double X[CPT], err2[CPT];
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) X[c] = eval_x(sp, P.flags, k[c], mu[c], smu[c], hA[c], hB[c], hN[c], err2[c]);
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          Pobs[c] = 0.0;
-          if (sp.flags & SD_PSHOT) {
-            Pobs[c] = X[c] * fast_exp_neg(-err2[c]) + sp.pshot;
-            lnP[c] = fast_log(Pobs[c]);
-          } else {
-            lnP[c] = fast_log(X[c]) - err2[c];
-            if (sp.flags & SD_SRC) Pobs[c] = X[c] * fast_exp_neg(-err2[c]);
-          }
+        double err2, X;
+        if (STAGED) {
+          X = eval_x(sp, myrow[s], P.flags, k, hA, hB, hN, err2);
+        } else {
+          const RowC rc = row_consts(sp, P.flags, mu, smu);
+          X = eval_x(sp, rc, P.flags, k, hA, hB, hN, err2);
+        }
+        Pobs = 0.0;
+        if (sp.flags & SD_PSHOT) {
+          Pobs = X * fast_exp_neg(-err2) + sp.pshot;
+          lnP = fast_log(Pobs);
+        } else {
+          lnP = fast_log(X) - err2;
+          if (sp.flags & SD_SRC) Pobs = X * fast_exp_neg(-err2);
         }
       } else {
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          Pobs[c] = P0[c];
-          lnP[c] = lnP0[c];
-        }
+        Pobs = P0;
+        lnP = lnP0;
       }
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        if (s == 0) {
-          P0[c] = Pobs[c];
-          lnP0[c] = lnP[c];
-        }
-        if (s == P.ps_src) Psrc[c] = Pobs[c];
-        if ((P.materialize & CFP_MAT_LNP) && valid[c]) P.lnp[((size_t)s * P.Z + zb) * lattice + cell[c]] = lnP[c];
-        if (sp.par0 >= 0) {
-          sm_d[sp.par0 * LDC + c * TILE + tid] += sp.w0 * lnP[c];
-          for (int j = sp.csr0; j < sp.csr1; ++j) {
-            const int par = __ldg(P.st_par + j);
-            if (!__ldg(P.dead + par * P.Z + zb)) sm_d[par * LDC + c * TILE + tid] += __ldg(P.st_w + j) * lnP[c];
-          }
+      if (s == 0) {
+        P0 = Pobs;
+        lnP0 = lnP;
+      }
+      if (s == P.ps_src) Psrc = Pobs;
+      if ((P.materialize & CFP_MAT_LNP) && valid) P.lnp[((size_t)s * P.Z + zb) * lattice + cell] = lnP;
+      if (sp.par0 >= 0) {
+        sm_d[sp.par0 * LDC + tid] += sp.w0 * lnP;
+        for (int j = sp.csr0; j < sp.csr1; ++j) {
+          const int par = __ldg(P.st_par + j);
+          if (!__ldg(P.dead + par * P.Z + zb)) sm_d[par * LDC + tid] += __ldg(P.st_w + j) * lnP;
         }
       }
     }
-    // finish the derivatives of the cells
+    // finish the derivatives of the cell
     for (int par = 0; par < P.npar; ++par) {
       const int pb = __ldg(P.ps_bin + par);
       const double den = __ldg(P.st_den + par);
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        double d;
-        if (pb >= 0)
-          d = (pb == zb) ? 1.0 / Psrc[c] : 0.0;  // spectro_cov.py:510-532
-        else
-          d = sm_d[par * LDC + c * TILE + tid] / den;  // dead parameters accumulate nothing: exactly 0
-        sm_d[par * LDC + c * TILE + tid] = d;
-        if ((P.materialize & CFP_MAT_DERIVS) && valid[c]) P.derivs[((size_t)par * P.Z + zb) * lattice + cell[c]] = d;
-      }
+      double d;
+      if (pb >= 0)
+        d = (pb == zb) ? 1.0 / Psrc : 0.0;  // spectro_cov.py:510-532
+      else
+        d = sm_d[par * LDC + tid] / den;  // dead parameters accumulate nothing: exactly 0
+      sm_d[par * LDC + tid] = d;
+      if ((P.materialize & CFP_MAT_DERIVS) && valid) P.derivs[((size_t)par * P.Z + zb) * lattice + cell] = d;
     }
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) {
+    {
       // effective volume on the fiducial spectrum and the quadrature weight of the cell
-      const double npobs = nbar * P0[c];
+      const double npobs = nbar * P0;
       const double r = npobs / (1.0 + npobs);
       const double veff = INV_8PI2 * r * r;  // spectro_cov.py:223-225
-      if ((P.materialize & CFP_MAT_DERIVS) && valid[c]) P.veff[(size_t)zb * lattice + cell[c]] = veff;
+      if ((P.materialize & CFP_MAT_DERIVS) && valid) P.veff[(size_t)zb * lattice + cell] = veff;
       // cosmicfish.py:541: k^2 * 2 * V_survey * veff, times the Simpson weights of :510-511
-      sm_w[c * TILE + tid] =
-          valid[c] ? (k[c] * k[c] * 2.0 * vol * veff) * (__ldg(P.wmu + mi[c]) * __ldg(P.wk + ki[c])) : 0.0;
+      sm_w[tid] = valid ? (k * k * 2.0 * vol * veff) * (__ldg(P.wmu + mi) * __ldg(P.wk + ki)) : 0.0;
     }
     __syncwarp();
-    // Gram update on the FP64 tensor cores: this warp's 32*CPT cells, k-steps of 4 cells
+    // Gram update on the FP64 tensor cores: this warp's 32 cells, k-steps of 4 cells
 #pragma unroll 2
-    for (int ks = 0; ks < 8 * CPT; ++ks) {
-      const int c = (ks >> 3) * TILE + warp * 32 + (ks & 7) * 4 + (lane & 3);
+    for (int ks = 0; ks < 8; ++ks) {
+      const int c = warp * 32 + ks * 4 + (lane & 3);
       const double w = sm_w[c];
       double a[NB];
 #pragma unroll
@@ -622,9 +645,32 @@ __global__ void spectro_reduce_kernel(const double* __restrict__ partial, int nc
 
 
 // ---------------------------------------------------------------------------- likelihood (wedges)
+// Grid-stride walk over the lattice that keeps (mu index, k index) incrementally -- no 64-bit division per
+// cell -- and re-derives the row constants only when the thread's mu row changes.
+struct CellWalk {
+  int64_t cell;
+  int mi, ki, dmi, dki;
+  __device__ __forceinline__ CellWalk(int64_t first, int64_t stride, int Nk) {
+    cell = first;
+    mi = (int)(first / Nk);
+    ki = (int)(first - (int64_t)mi * Nk);
+    dmi = (int)(stride / Nk);
+    dki = (int)(stride - (int64_t)dmi * Nk);
+  }
+  __device__ __forceinline__ void next(int64_t stride, int Nk) {
+    cell += stride;
+    mi += dmi;
+    ki += dki;
+    if (ki >= Nk) {
+      ki -= Nk;
+      ++mi;
+    }
+  }
+};
+
 // data[zb][cell] = P_obs(stencil point 0) + 1/nbar + shot_data[zb]
-__global__ void __launch_bounds__(TILE) spectro_data_kernel(SpectroParams P, const double* __restrict__ shot_data,
-                                                            double* __restrict__ data) {
+__global__ void __launch_bounds__(TILE, 3) spectro_data_kernel(SpectroParams P, const double* __restrict__ shot_data,
+                                                               double* __restrict__ data) {
   __shared__ SDev sp;
   const int zb = blockIdx.y, tid = threadIdx.x;
   if (tid < (int)(sizeof(SDev) / sizeof(double)))
@@ -632,19 +678,24 @@ __global__ void __launch_bounds__(TILE) spectro_data_kernel(SpectroParams P, con
   __syncthreads();
   const int64_t lattice = (int64_t)P.Nmu * P.Nk;
   const double extra = 1.0 / P.nbar[zb] + (shot_data ? shot_data[zb] : 0.0);
-  int hA = -1, hB = -1, hN = -1;
-  for (int64_t cell = (int64_t)blockIdx.x * TILE + tid; cell < lattice; cell += (int64_t)gridDim.x * TILE) {
-    const int mi = (int)(cell / P.Nk), ki = (int)(cell - (int64_t)mi * P.Nk);
+  int hA = -1, hB = -1, hN = -1, row = -1;
+  RowC rc;
+  const int64_t stride = (int64_t)gridDim.x * TILE;
+  for (CellWalk w((int64_t)blockIdx.x * TILE + tid, stride, P.Nk); w.cell < lattice; w.next(stride, P.Nk)) {
+    if (w.mi != row) {
+      row = w.mi;
+      rc = row_consts(sp, P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
+    }
     double err2;
-    const double X = eval_x(sp, P.flags, __ldg(P.k + ki), __ldg(P.mu + mi), __ldg(P.smu + mi), hA, hB, hN, err2);
-    data[(size_t)zb * lattice + cell] = X * fast_exp_neg(-err2) + sp.pshot + extra;
+    const double X = eval_x(sp, rc, P.flags, __ldg(P.k + w.ki), hA, hB, hN, err2);
+    data[(size_t)zb * lattice + w.cell] = X * fast_exp_neg(-err2) + sp.pshot + extra;
   }
 }
 
 // grid (gx, Z, S): partial[s][zb][cta] = sum over this CTA's cells of w (P_d - P_t)^2 / P_d^2
-__global__ void __launch_bounds__(TILE) spectro_chi2_kernel(SpectroParams P, const double* __restrict__ data,
-                                                            const double* __restrict__ shot, int s_begin,
-                                                            double* __restrict__ partial) {
+__global__ void __launch_bounds__(TILE, 3) spectro_chi2_kernel(SpectroParams P, const double* __restrict__ data,
+                                                               const double* __restrict__ shot, int s_begin,
+                                                               double* __restrict__ partial) {
   __shared__ SDev sp;
   __shared__ double red[TILE / 32];
   const int zb = blockIdx.y, s = s_begin + blockIdx.z, tid = threadIdx.x;
@@ -652,19 +703,27 @@ __global__ void __launch_bounds__(TILE) spectro_chi2_kernel(SpectroParams P, con
     reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S + s)[tid];
   __syncthreads();
   const int64_t lattice = (int64_t)P.Nmu * P.Nk;
-  const double extra = 1.0 / P.nbar[zb] + shot[(size_t)s * P.Z + zb];
+  const double extra = 1.0 / P.nbar[zb] + shot[(size_t)s * P.Z + zb] + sp.pshot;
   const double pref = 2.0 * P.vol[zb] * INV_8PI2;  // spectro_like.py:162-178
-  int hA = -1, hB = -1, hN = -1;
+  const double* __restrict__ dz = data + (size_t)zb * lattice;
+  int hA = -1, hB = -1, hN = -1, row = -1;
+  RowC rc;
+  double wrow = 0.0;
   double acc = 0.0;
-  for (int64_t cell = (int64_t)blockIdx.x * TILE + tid; cell < lattice; cell += (int64_t)gridDim.x * TILE) {
-    const int mi = (int)(cell / P.Nk), ki = (int)(cell - (int64_t)mi * P.Nk);
-    const double k = __ldg(P.k + ki);
+  const int64_t stride = (int64_t)gridDim.x * TILE;
+  for (CellWalk w((int64_t)blockIdx.x * TILE + tid, stride, P.Nk); w.cell < lattice; w.next(stride, P.Nk)) {
+    if (w.mi != row) {
+      row = w.mi;
+      rc = row_consts(sp, P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
+      wrow = __ldg(P.wmu + row) * pref;
+    }
+    const double k = __ldg(P.k + w.ki);
+    const double Pd = __ldg(dz + w.cell);
     double err2;
-    const double X = eval_x(sp, P.flags, k, __ldg(P.mu + mi), __ldg(P.smu + mi), hA, hB, hN, err2);
-    const double Pt = X * fast_exp_neg(-err2) + sp.pshot + extra;
-    const double Pd = __ldg(data + (size_t)zb * lattice + cell);
-    const double r = (Pd - Pt) / Pd;
-    acc += (__ldg(P.wmu + mi) * __ldg(P.wk + ki)) * (pref * k * k) * (r * r);
+    const double X = eval_x(sp, rc, P.flags, k, hA, hB, hN, err2);
+    const double Pt = fma(X, fast_exp_neg(-err2), extra);
+    const double r = (Pd - Pt) * fast_rcp(Pd);
+    acc = fma((wrow * __ldg(P.wk + w.ki)) * (k * k), r * r, acc);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -895,19 +954,27 @@ extern "C" int cfp_spectro_plan_set_slice(cfp_spectro_plan* plan, int64_t cell_b
   return CFP_OK;
 }
 
-template <int NB, int CPT>
-static cudaError_t launch_fisher(const SpectroParams& P, dim3 grid, size_t smem, cudaStream_t st) {
-  cudaError_t e =
-      cudaFuncSetAttribute(spectro_fisher_kernel<NB, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  spectro_fisher_kernel<NB, CPT><<<grid, TILE, smem, st>>>(P);
+template <int NB>
+static cudaError_t launch_fisher(const SpectroParams& P, dim3 grid, size_t smem, int nrows, cudaStream_t st) {
+  if (nrows > 0) {
+    cudaError_t e = cudaFuncSetAttribute(spectro_fisher_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    spectro_fisher_kernel<NB, true><<<grid, TILE, smem, st>>>(P, nrows);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(spectro_fisher_kernel<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    spectro_fisher_kernel<NB, false><<<grid, TILE, smem, st>>>(P, 0);
+  }
   return cudaGetLastError();
 }
 
-static size_t fisher_smem(int nb, int cpt, int S) {
+// nrows = mu rows whose constants are staged per tile (0: threads derive their own)
+static size_t fisher_smem(int nb, int S, int nrows) {
   const int T = nb * (nb + 1) / 2;
-  const size_t cells = (size_t)TILE * cpt;
-  return std::max((size_t)(nb * 8 * (cells + LDPAD) + cells) * sizeof(double) + (size_t)S * sizeof(SDev),
+  return std::max((size_t)(nb * 8 * (TILE + LDPAD) + TILE) * sizeof(double) + (size_t)S * sizeof(SDev) +
+                      (size_t)nrows * S * sizeof(RowC),
                   (size_t)(TILE / 32) * T * 64 * sizeof(double));
 }
 
@@ -1022,15 +1089,10 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
     allocated = true;
   }
   const int64_t ncell = pl->cell_end - pl->cell_begin;
-  // two cells per thread when the lattice is big enough to still fill the GPU and the tile fits in smem
-  // one cell per thread: on B200 more resident warps beat two interleaved cells per thread (profiles/r1c)
-  int cpt = 1;
-  if (const char* ec = getenv("CFP_SPECTRO_CPT")) cpt = atoi(ec) == 2 ? 2 : 1;
-  const int64_t ntile = std::max<int64_t>(1, (ncell + TILE * cpt - 1) / (TILE * cpt));
+  const int64_t ntile = std::max<int64_t>(1, (ncell + TILE - 1) / TILE);
   const int T = pl->nb * (pl->nb + 1) / 2;
   // persistent grid: one wave of (resident CTAs per SM) x (SM count) CTAs, never more CTAs than tiles
-  int minb = fisher_min_blocks(pl->nb);
-  if (const char* em = getenv("CFP_SPECTRO_MINB")) minb = std::max(1, atoi(em));
+  const int minb = fisher_min_blocks(pl->nb);
   int gx = (int)std::min<int64_t>(ntile, std::max(1, (ctx->sm_count * minb + pl->Z - 1) / pl->Z));
   if (gx != pl->grid_x) {
     if (pl->partial_d && pl->last_st && pl->last_st != ctx->stream) CFP_CUDA(cudaStreamSynchronize(pl->last_st));
@@ -1056,28 +1118,15 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
   }
   CFP_CUDA(cudaEventRecord(pl->kev0, st));
   const dim3 grid(gx, pl->Z);
-  const size_t smem = fisher_smem(pl->nb, cpt, pl->S);
+  // a tile of TILE consecutive cells touches at most this many mu rows
+  int nrows = std::min(pl->Nmu, (TILE + pl->Nk - 2) / pl->Nk + 1);
+  if (nrows > MAX_STAGED_ROWS) nrows = 0;
+  const size_t smem = fisher_smem(pl->nb, pl->S, nrows);
   cudaError_t e = cudaSuccess;
-#define CFP_LAUNCH_NB(NBV)                                                   \
-  case NBV:                                                                  \
-    e = (cpt == 2) ? launch_fisher<NBV, 2>(P, grid, smem, st) : launch_fisher<NBV, 1>(P, grid, smem, st); \
+#define CFP_LAUNCH_NB(NBV)                                   \
+  case NBV:                                                  \
+    e = launch_fisher<NBV>(P, grid, smem, nrows, st);        \
     break;
-  const char* exp_minb = getenv("CFP_SPECTRO_MINB");  // experiment switch (occupancy vs registers), NB == 2 only
-  if (exp_minb && pl->nb == 2) {
-    const int mb = atoi(exp_minb);
-    cudaError_t (*fn)(const SpectroParams&, dim3, size_t, cudaStream_t) = nullptr;
-    auto L = [&](auto k) {
-      cudaError_t e2 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e2 != cudaSuccess) return e2;
-      k<<<grid, TILE, smem, st>>>(P);
-      return cudaGetLastError();
-    };
-    (void)fn;
-    if (cpt == 2)
-      e = mb == 3 ? L(spectro_fisher_kernel<2, 2, 3>) : mb == 4 ? L(spectro_fisher_kernel<2, 2, 4>) : L(spectro_fisher_kernel<2, 2, 2>);
-    else
-      e = mb == 3 ? L(spectro_fisher_kernel<2, 1, 3>) : mb == 4 ? L(spectro_fisher_kernel<2, 1, 4>) : L(spectro_fisher_kernel<2, 1, 2>);
-  } else
   switch (pl->nb) {
     CFP_LAUNCH_NB(1)
     CFP_LAUNCH_NB(2)
@@ -1085,7 +1134,7 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
     CFP_LAUNCH_NB(4)
     CFP_LAUNCH_NB(5)
     default:
-      e = (cpt == 2) ? launch_fisher<6, 2>(P, grid, smem, st) : launch_fisher<6, 1>(P, grid, smem, st);
+      e = launch_fisher<6>(P, grid, smem, nrows, st);
       break;
   }
 #undef CFP_LAUNCH_NB
