@@ -33,7 +33,8 @@ EXPORTS = [
     "cfp_photo_plan_set_slice", "cfp_photo_plan_run", "cfp_photo_plan_fisher_d", "cfp_photo_plan_fetch",
     "cfp_photo_plan_chi2", "cfp_spectro_plan_chi2", "cfp_cells_chi2", "cfp_wedge_chi2",
     "cfp_legendre_project", "cfp_legendre_covariance", "cfp_legendre_chi2",
-    "cfp_bank_upload_rows", "cfp_host_alloc", "cfp_host_free",
+    "cfp_bank_upload_rows", "cfp_host_alloc", "cfp_host_free", "cfp_spectro_plan_chi2_dev", "cfp_dev_upload",
+    "cfp_dev_release",
 ]
 
 
@@ -80,6 +81,9 @@ def load():
     lib.cfp_bank_upload_rows.argtypes = [_vp, C.POINTER(_vp), _lp, _lp, C.c_int, C.c_int, C.POINTER(_vp)]
     lib.cfp_host_alloc.argtypes = [_vp, C.c_size_t, C.POINTER(_vp)]
     lib.cfp_host_free.argtypes = [_vp, _vp]
+    lib.cfp_spectro_plan_chi2_dev.argtypes = [_vp, _vp, _dp, _dp, _vp]
+    lib.cfp_dev_upload.argtypes = [_vp, _dp, C.c_size_t, C.POINTER(_vp)]
+    lib.cfp_dev_release.argtypes = [_vp, _vp]
     lib.cfp_bank_eval.argtypes = [_vp, _vp, C.c_int, C.c_int, _dp, _dp, C.c_size_t, _dp]
     lib.cfp_spectro_plan_create.argtypes = [
         _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, C.c_int, _dp, _dp,
@@ -249,6 +253,26 @@ class PinnedBuffer:
             pass
 
 
+class DeviceArray:
+    """float64 array resident on the device (cfp_dev_upload), e.g. the data vector of a likelihood."""
+
+    def __init__(self, ctx: Context, host):
+        host = f64(host)
+        self.ctx, self.shape, self.ptr = ctx, host.shape, _vp()
+        _check(ctx.lib.cfp_dev_upload(ctx.handle, _p(host), host.size, C.byref(self.ptr)), "cfp_dev_upload")
+
+    def close(self):
+        if self.ptr:
+            self.ctx.lib.cfp_dev_release(self.ctx.handle, self.ptr)
+            self.ptr = _vp()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class BankRow:
     """The fitted tables of ONE cosmology packed for upload: [tx | ty | c] per slot in a pinned block plus the
     row-local descriptor.  Built once per cosmology and table selection, reused by every bank that needs it."""
@@ -373,13 +397,18 @@ class SpectroPlan:
     def fisher_device_ptr(self) -> int:
         return int(self.ctx.lib.cfp_spectro_plan_fisher_d(self.handle) or 0)
 
-    def chi2(self, shot, data=None, shot_data=None, stream: int = 0) -> np.ndarray:
+    def chi2(self, shot, data=None, shot_data=None, stream: int = 0, data_dev=None) -> np.ndarray:
         """Wedge chi^2 of every point of the plan against `data` (default: point 0 + noise)."""
         shot = f64(shot)
         assert shot.shape == (self.S, self.Z)
         data = None if data is None else f64(data)
         sd = None if shot_data is None else f64(shot_data)
         out = np.empty(self.S)
+        if isinstance(data_dev, DeviceArray):
+            assert data_dev.shape == (self.Z, self.Nmu, self.Nk) and data is None and sd is None
+            _check(self.ctx.lib.cfp_spectro_plan_chi2_dev(self.handle, data_dev.ptr, _p(shot), _p(out),
+                                                          _vp(stream) if stream else None), "cfp_spectro_plan_chi2_dev")
+            return out
         _check(self.ctx.lib.cfp_spectro_plan_chi2(self.handle, _p(data), _p(shot), _p(sd), _p(out),
                                                   _vp(stream) if stream else None), "cfp_spectro_plan_chi2")
         return out

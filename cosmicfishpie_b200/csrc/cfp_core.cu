@@ -124,6 +124,22 @@ extern "C" int cfp_host_free(cfp_ctx* ctx, void* p) {
   return CFP_OK;
 }
 
+extern "C" int cfp_dev_upload(cfp_ctx* ctx, const double* src_h, size_t n_doubles, double** out_d) {
+  CFP_REQUIRE(ctx && src_h && out_d && n_doubles > 0, "bad argument");
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  int rc = cfp_upload(ctx, src_h, n_doubles, out_d);
+  if (rc == CFP_OK) CFP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return rc;
+}
+
+extern "C" int cfp_dev_release(cfp_ctx* ctx, double* p_d) {
+  CFP_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  CFP_CUDA(cudaStreamSynchronize(ctx->stream));
+  cfp_dev_free(ctx, p_d);
+  return CFP_OK;
+}
+
 extern "C" int cfp_bank_upload_rows(cfp_ctx* ctx, const double* const* rows_h, const int64_t* row_len,
                                     const int64_t* desc_h, int n_cosmo, int n_tables, cfp_bank** out) {
   CFP_REQUIRE(ctx && rows_h && row_len && desc_h && out, "NULL argument");

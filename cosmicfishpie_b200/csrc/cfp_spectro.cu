@@ -692,11 +692,17 @@ __global__ void __launch_bounds__(TILE, 3) spectro_data_kernel(SpectroParams P, 
   }
 }
 
-// grid (gx, Z, S): partial[s][zb][cta] = sum over this CTA's cells of w (P_d - P_t)^2 / P_d^2
+// grid (gx, Z, S): partial[s][zb][cta] = sum over this CTA's cells of w (P_d - P_t)^2 / P_d^2.
+// A CTA owns blocks of TILE consecutive k and walks DOWN the mu rows of each block: along a column k' = k G(mu)
+// drifts by a fraction of a piece per step, so the piece hints of the three tables stay valid, loads of the data
+// lattice stay coalesced, and the row constants of the point (staged once per CTA) are broadcast reads.
+constexpr int CHI_ROWS = 256;  // mu rows staged at a time (12 KB of RowC + 2 KB of row weights)
 __global__ void __launch_bounds__(TILE, 3) spectro_chi2_kernel(SpectroParams P, const double* __restrict__ data,
                                                                const double* __restrict__ shot, int s_begin,
                                                                double* __restrict__ partial) {
   __shared__ SDev sp;
+  __shared__ RowC rows[CHI_ROWS];
+  __shared__ double wrow[CHI_ROWS];
   __shared__ double red[TILE / 32];
   const int zb = blockIdx.y, s = s_begin + blockIdx.z, tid = threadIdx.x;
   if (tid < (int)(sizeof(SDev) / sizeof(double)))
@@ -706,24 +712,34 @@ __global__ void __launch_bounds__(TILE, 3) spectro_chi2_kernel(SpectroParams P, 
   const double extra = 1.0 / P.nbar[zb] + shot[(size_t)s * P.Z + zb] + sp.pshot;
   const double pref = 2.0 * P.vol[zb] * INV_8PI2;  // spectro_like.py:162-178
   const double* __restrict__ dz = data + (size_t)zb * lattice;
-  int hA = -1, hB = -1, hN = -1, row = -1;
-  RowC rc;
-  double wrow = 0.0;
+  const int nkb = (P.Nk + TILE - 1) / TILE;
   double acc = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * TILE;
-  for (CellWalk w((int64_t)blockIdx.x * TILE + tid, stride, P.Nk); w.cell < lattice; w.next(stride, P.Nk)) {
-    if (w.mi != row) {
-      row = w.mi;
-      rc = row_consts(sp, P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
-      wrow = __ldg(P.wmu + row) * pref;
+  for (int r0 = 0; r0 < P.Nmu; r0 += CHI_ROWS) {
+    const int nr = min(CHI_ROWS, P.Nmu - r0);
+    __syncthreads();
+    for (int r = tid; r < nr; r += TILE) {
+      rows[r] = row_consts(sp, P.flags, __ldg(P.mu + r0 + r), __ldg(P.smu + r0 + r));
+      wrow[r] = __ldg(P.wmu + r0 + r) * pref;
     }
-    const double k = __ldg(P.k + w.ki);
-    const double Pd = __ldg(dz + w.cell);
-    double err2;
-    const double X = eval_x(sp, rc, P.flags, k, hA, hB, hN, err2);
-    const double Pt = fma(X, fast_exp_neg(-err2), extra);
-    const double r = (Pd - Pt) * fast_rcp(Pd);
-    acc = fma((wrow * __ldg(P.wk + w.ki)) * (k * k), r * r, acc);
+    __syncthreads();
+    for (int kb = blockIdx.x; kb < nkb; kb += gridDim.x) {
+      const int ki = kb * TILE + tid;
+      if (ki >= P.Nk) continue;
+      const double k = __ldg(P.k + ki);
+      const double wcol = __ldg(P.wk + ki) * (k * k);
+      const double* __restrict__ dcol = dz + (size_t)r0 * P.Nk + ki;
+      int hA = -1, hB = -1, hN = -1;
+      double colsum = 0.0;
+      for (int r = 0; r < nr; ++r) {
+        const double Pd = __ldg(dcol + (size_t)r * P.Nk);
+        double err2;
+        const double X = eval_x(sp, rows[r], P.flags, k, hA, hB, hN, err2);
+        const double Pt = fma(X, fast_exp_neg(-err2), extra);
+        const double q = (Pd - Pt) * fast_rcp(Pd);
+        colsum = fma(wrow[r], q * q, colsum);
+      }
+      acc = fma(wcol, colsum, acc);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -1011,8 +1027,22 @@ static int spectro_prepare(cfp_spectro_plan* pl, const SpectroParams& P, cudaStr
   return CFP_OK;
 }
 
+static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const double* data_dev, const double* shot_h,
+                             const double* shot_data_h, double* chi2_h, void* stream);
+
 extern "C" int cfp_spectro_plan_chi2(cfp_spectro_plan* pl, const double* data_h, const double* shot_h,
                                      const double* shot_data_h, double* chi2_h, void* stream) {
+  return spectro_chi2_impl(pl, data_h, nullptr, shot_h, shot_data_h, chi2_h, stream);
+}
+
+extern "C" int cfp_spectro_plan_chi2_dev(cfp_spectro_plan* pl, const double* data_d, const double* shot_h,
+                                         double* chi2_h, void* stream) {
+  CFP_REQUIRE(data_d != nullptr, "data_d is NULL");
+  return spectro_chi2_impl(pl, nullptr, data_d, shot_h, nullptr, chi2_h, stream);
+}
+
+static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const double* data_dev, const double* shot_h,
+                             const double* shot_data_h, double* chi2_h, void* stream) {
   CFP_REQUIRE(pl && shot_h && chi2_h, "NULL argument");
   cfp_ctx* ctx = pl->ctx;
   CFP_CUDA(cudaSetDevice(ctx->device));
@@ -1020,8 +1050,20 @@ extern "C" int cfp_spectro_plan_chi2(cfp_spectro_plan* pl, const double* data_h,
   const int S = pl->S, Z = pl->Z;
   const size_t lattice = (size_t)pl->Nmu * pl->Nk;
   const int64_t ntile = (int64_t)((lattice + TILE - 1) / TILE);
-  // enough CTAs per (point, bin) to fill the GPU for small batches, few for large ones
-  int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ntile, (4 * (int64_t)ctx->sm_count + (int64_t)S * Z - 1) / ((int64_t)S * Z)));
+  // CTAs per (point, bin): each takes every gx-th block of TILE wavenumbers.  Pick the split that needs the
+  // fewest (waves of resident CTAs) x (blocks per CTA), i.e. fills the GPU for small batches and avoids a
+  // ragged last wave for large ones.
+  const int nkb = (pl->Nk + TILE - 1) / TILE;
+  int gx = 1;
+  {
+    const int64_t slots = 3 * (int64_t)ctx->sm_count;  // spectro_chi2_kernel: 3 resident CTAs per SM
+    int64_t best = INT64_MAX;
+    for (int g = 1; g <= std::min(nkb, 64); ++g) {
+      const int64_t ctas = (int64_t)g * S * Z;
+      const int64_t cost = ((ctas + slots - 1) / slots) * ((nkb + g - 1) / g);
+      if (cost < best) best = cost, gx = g;
+    }
+  }
   double *data_d = nullptr, *shot_d = nullptr, *sd_d = nullptr, *part_d = nullptr, *chi2_d = nullptr;
   auto cleanup = [&]() {
     for (void* q : {(void*)data_d, (void*)shot_d, (void*)sd_d, (void*)part_d, (void*)chi2_d}) cfp_dev_free(ctx, q);
@@ -1035,7 +1077,7 @@ extern "C" int cfp_spectro_plan_chi2(cfp_spectro_plan* pl, const double* data_h,
       return rc;        \
     }                   \
   } while (0)
-  CHI_TRY(cfp_upload<double>(ctx, data_h, (size_t)Z * lattice, &data_d));
+  if (!data_dev) CHI_TRY(cfp_upload<double>(ctx, data_h, (size_t)Z * lattice, &data_d));
   CHI_TRY(cfp_upload(ctx, shot_h, (size_t)S * Z, &shot_d));
   if (shot_data_h) CHI_TRY(cfp_upload(ctx, shot_data_h, (size_t)Z, &sd_d));
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S * Z * gx, &part_d));
@@ -1045,14 +1087,15 @@ extern "C" int cfp_spectro_plan_chi2(cfp_spectro_plan* pl, const double* data_h,
   SpectroParams P;
   spectro_fill_params(pl, 16, P);
   CHI_TRY(spectro_prepare(pl, P, st));
-  if (!data_h) {
+  if (!data_h && !data_dev) {
     const int gd = (int)std::min<int64_t>(ntile, 2 * ctx->sm_count);
     spectro_data_kernel<<<dim3(gd, Z), TILE, 0, st>>>(P, sd_d, data_d);
     ctx->launches++;
   }
+  const double* data_use = data_dev ? data_dev : data_d;
   for (int s0 = 0; s0 < S; s0 += 32768) {
     const int ns = std::min(32768, S - s0);
-    spectro_chi2_kernel<<<dim3(gx, Z, ns), TILE, 0, st>>>(P, data_d, shot_d, s0, part_d);
+    spectro_chi2_kernel<<<dim3(gx, Z, ns), TILE, 0, st>>>(P, data_use, shot_d, s0, part_d);
     ctx->launches++;
   }
   spectro_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Z * gx, part_d, chi2_d);

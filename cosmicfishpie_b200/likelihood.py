@@ -369,6 +369,14 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
     def data_wedges(self):
         return self._data_wedges
 
+    def _data_on_device(self, ctx):
+        """The wedge data lattice, uploaded once per device context and kept there for every batch."""
+        hit = self.__dict__.get("_data_dev")
+        if hit is None or hit[0] is not ctx or hit[1] is not self._data_wedges:
+            hit = (ctx, self._data_wedges, _lib.DeviceArray(ctx, self._data_wedges))
+            self.__dict__["_data_dev"] = hit
+        return hit[2]
+
     def compute_data(self):
         fm = self.cosmo_data
         if not hasattr(fm, "pk_cov") or fm.pk_cov is None:
@@ -479,7 +487,7 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
                 scal=scal[i0:i0 + S], alias=np.tile(np.arange(S, dtype=np.int32)[:, None], (1, Z)), pnw_k=pk, pnw_p=pp,
                 stw=np.zeros((1, S)), stden=np.ones(1), ps_bin=np.array([-1], np.int32), ps_src=0, nbar=nbar,
                 vol=fm.pk_cov.volume_survey_array, flags=fid_obs.flags())
-            out[i0:i0 + S] = plan.chi2(shot[i0:i0 + S], data=self._data_wedges)
+            out[i0:i0 + S] = plan.chi2(shot[i0:i0 + S], data_dev=self._data_on_device(plan.ctx))
             plan.close()
         return out
 
@@ -505,7 +513,7 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
                 stden=np.ones(1), ps_bin=np.array([-1], np.int32), ps_src=0,
                 nbar=np.array([fm.pk_cov.n_density(z) for z in zs]), vol=fm.pk_cov.volume_survey_array,
                 flags=pts[0].flags())
-            out[i0:i0 + chunk] = plan.chi2(np.array(shots), data=self._data_wedges)
+            out[i0:i0 + chunk] = plan.chi2(np.array(shots), data_dev=self._data_on_device(plan.ctx))
             plan.close()
         return out
 

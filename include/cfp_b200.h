@@ -264,6 +264,13 @@ int cfp_photo_plan_chi2(cfp_photo_plan* plan, const double* data_h, int nblk, co
 int cfp_spectro_plan_chi2(cfp_spectro_plan* plan, const double* data_h, const double* shot_h,
                           const double* shot_data_h, double* chi2_h, void* stream);
 
+/* The same with the data lattice already resident on the device (cfp_dev_upload): a sampler evaluates
+ * thousands of batches against ONE data vector, which therefore crosses PCIe once, not once per batch. */
+int cfp_spectro_plan_chi2_dev(cfp_spectro_plan* plan, const double* data_d, const double* shot_h, double* chi2_h,
+                              void* stream);
+int cfp_dev_upload(cfp_ctx* ctx, const double* src_h, size_t n_doubles, double** out_d);
+int cfp_dev_release(cfp_ctx* ctx, double* p_d);
+
 /* Stand-alone forms on spectra the caller already holds (host arrays): the operator seams
  * `_chi2_per_obs(cell_fid, cell_th, ells, dells)` (photo_like.py:78-97) and
  * `compute_wedge_chi2(P_obs_data, P_obs_theory, cosmoFM)` (spectro_like.py:143-189).
