@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 from typing import Optional
 
 import numpy as np
@@ -215,6 +216,8 @@ class Context:
 
     def __del__(self):  # pragma: no cover
         try:
+            if sys.is_finalizing():  # interpreter teardown: destruction order is arbitrary, the OS reclaims
+                return
             self.close()
         except Exception:
             pass
@@ -243,11 +246,13 @@ class PinnedBuffer:
     def close(self):
         if self.ptr:
             self.array = None
-            self.ctx.lib.cfp_host_free(self.ctx.handle, self.ptr)
+            self.ctx.lib.cfp_host_free(None, self.ptr)
             self.ptr = _vp()
 
     def __del__(self):  # pragma: no cover
         try:
+            if sys.is_finalizing():  # interpreter teardown: destruction order is arbitrary, the OS reclaims
+                return
             self.close()
         except Exception:
             pass
@@ -263,11 +268,14 @@ class DeviceArray:
 
     def close(self):
         if self.ptr:
-            self.ctx.lib.cfp_dev_release(self.ctx.handle, self.ptr)
+            if self.ctx.handle:  # a destroyed context has already returned its whole arena
+                self.ctx.lib.cfp_dev_release(self.ctx.handle, self.ptr)
             self.ptr = _vp()
 
     def __del__(self):  # pragma: no cover
         try:
+            if sys.is_finalizing():  # interpreter teardown: destruction order is arbitrary, the OS reclaims
+                return
             self.close()
         except Exception:
             pass
@@ -348,11 +356,14 @@ class Bank:
 
     def close(self):
         if self.handle:
-            self.ctx.lib.cfp_bank_free(self.ctx.handle, self.handle)
+            if self.ctx.handle:  # a destroyed context has already returned its whole arena
+                self.ctx.lib.cfp_bank_free(self.ctx.handle, self.handle)
             self.handle = _vp()
 
     def __del__(self):  # pragma: no cover
         try:
+            if sys.is_finalizing():  # interpreter teardown: destruction order is arbitrary, the OS reclaims
+                return
             self.close()
         except Exception:
             pass
@@ -423,11 +434,14 @@ class SpectroPlan:
 
     def close(self):
         if self.handle:
-            self.ctx.lib.cfp_spectro_plan_destroy(self.handle)
+            if self.ctx.handle:  # a destroyed context has already returned its whole arena
+                self.ctx.lib.cfp_spectro_plan_destroy(self.handle)
             self.handle = _vp()
 
     def __del__(self):  # pragma: no cover
         try:
+            if sys.is_finalizing():  # interpreter teardown: destruction order is arbitrary, the OS reclaims
+                return
             self.close()
         except Exception:
             pass
@@ -491,11 +505,14 @@ class PhotoPlan:
 
     def close(self):
         if self.handle:
-            self.ctx.lib.cfp_photo_plan_destroy(self.handle)
+            if self.ctx.handle:  # a destroyed context has already returned its whole arena
+                self.ctx.lib.cfp_photo_plan_destroy(self.handle)
             self.handle = _vp()
 
     def __del__(self):  # pragma: no cover
         try:
+            if sys.is_finalizing():  # interpreter teardown: destruction order is arbitrary, the OS reclaims
+                return
             self.close()
         except Exception:
             pass

@@ -35,17 +35,32 @@ constexpr int LIN_BLK = 4;      // doubles per linear piece: [lo, hi, y, slope]
 
 // Everything the lattice loop needs for one (stencil point, z-bin), derived once by
 // spectro_setup_kernel instead of once per thread per cell.
-struct SDev {
-  double rqpar, rqper, dzH, bias, A1, A2, sigmap, I0, I12, svr2, fs8, invs8sq, khfac, bao, pshot, w0;
-  double xminA, xmaxA, xminB, xmaxB;  // knot range of the P_lin / f tables (FITPACK clamps the argument to it)
-  double baos;                        // bao * invs8sq
-  const double *blkA, *blkB, *blkN;  // piece tables of P_lin(k), f(k), P_nw(k) at this (cosmology, z)
-  int nA, nB, nN;                    // number of pieces
-  int flags;                         // SD_*
-  int par0;                          // parameter fed by this point with weight w0 (-1: none)
+struct alignas(16) SDev {
+  // hot fields first, in 16-byte pairs so that the lattice loop fetches them with 128-bit shared loads
+  double bias, baos;                 // galaxy bias; bao * invs8sq
+  double xminA, xmaxA;               // knot range of the P_lin table (FITPACK clamps the argument to it)
+  const double *blkA, *blkB;         // piece tables of P_lin(k), f(k) at this (cosmology, z)
+  const double* blkN;                // piece table of P_nw(k)
+  int nA, nN;                        // number of pieces
+  double w0;                         // weight of this point in the derivative of parameter par0
+  int flags, par0;                   // SD_*; parameter fed with weight w0 (-1: none)
   int csr0, csr1;                    // further (parameter, weight) pairs in the CSR arrays
+  int nB, pad0;
+  double xminB, xmaxB;
+  // row-constant inputs and the rest
+  double rqpar, rqper, dzH, A1, A2, sigmap, I0, I12, svr2, fs8, invs8sq, khfac, bao, pshot;
 };
-enum { SD_OWN = 1, SD_QBIAS = 2, SD_SHARED_KNOTS = 4, SD_SRC = 8, SD_PSHOT = 16 };
+enum {
+  SD_OWN = 1,           // evaluated (not an alias of the fiducial in this bin)
+  SD_QBIAS = 2,
+  SD_SHARED_KNOTS = 4,  // P_lin and f share their k knots: one piece search serves both
+  SD_SRC = 8,           // P_obs itself is needed (fiducial, or the point the Ps_* derivative reads)
+  SD_PSHOT = 16,
+  SD_BIASONLY = 32,     // differs from the fiducial only in the galaxy bias: re-uses the fiducial's table look-ups
+  SD_FID = 64,          // stencil point 0
+  SD_PSSRC = 128,       // the point whose P_obs feeds d lnP / d Ps_i
+  SD_NOCLAMP = 256      // k' of the whole lattice lies inside the knot range of both tables: no clamping needed
+};
 
 // What one (stencil point, z-bin) needs per mu ROW of the lattice: with the Alcock-Paczynski remap
 // k' = k G(mu), mu' = mu'(mu) every mu-dependent factor of P_obs is constant along a row, so the cell loop
@@ -73,6 +88,8 @@ struct SpectroParams {
   const int* st_par;
   const double* st_w;
   const double* st_den;   // [npar]
+  const double* st_rden;  // [npar] 1 / st_den
+  double kmin, kmax;      // range of the wavenumber grid
   const int* ps_bin;      // [npar]
   const int* dead;        // [npar][Z]
   const double *nbar, *vol;
@@ -84,7 +101,7 @@ struct SpectroParams {
   const int* shared_knots;  // [NC]
   SDev* sdev;             // [Z][S]
   int* work;              // [Z][S] stencil points to visit per bin, in order
-  int* nwork;             // [Z]
+  int* nwork;             // [Z][4]: full, bias-only and alias points in the bin's work list (after the fiducial)
   double* partial;        // [Z][gridDim.x][T*64]
   double *lnp, *derivs, *veff;
 };
@@ -243,7 +260,25 @@ __global__ void spectro_setup_kernel(SpectroParams P) {
     const bool shared = P.shared_knots[c] != 0;
     const bool own = (s == 0) || (P.alias[s * P.Z + zb] == s);
     o.flags = (own ? SD_OWN : 0) | ((o.A1 != 0.0 || o.A2 != 0.0) ? SD_QBIAS : 0) | (shared ? SD_SHARED_KNOTS : 0) |
-              ((s == 0 || s == P.ps_src) ? SD_SRC : 0) | (o.pshot != 0.0 ? SD_PSHOT : 0);
+              ((s == 0 || s == P.ps_src) ? SD_SRC : 0) | (o.pshot != 0.0 ? SD_PSHOT : 0) | (s == 0 ? SD_FID : 0) |
+              (s == P.ps_src ? SD_PSSRC : 0);
+    if (s != 0 && own) {
+      // same cosmology and same scalars as the fiducial except (possibly) the bias?
+      const double* s0 = P.scal + (size_t)zb * CFP_SP_NSCAL;
+      bool same = true;
+      for (int q = 0; q < CFP_SP_NSCAL; ++q)
+        if (q != CFP_SP_BIAS) same = same && (sc[q] == s0[q]);
+      if (same) o.flags |= SD_BIASONLY;
+    }
+    o.pad0 = 0;
+    {
+      // k' = k khfac sqrt(mu^2 rqpar^2 + (1 - mu^2) rqper^2) lies between k khfac min(rq) and k khfac max(rq)
+      const double gmin = o.khfac * fmin(o.rqpar, o.rqper) * (1.0 - 1e-12);
+      const double gmax = o.khfac * fmax(o.rqpar, o.rqper) * (1.0 + 1e-12);
+      const double g_lo = (P.flags & CFP_SPF_AP) ? gmin : o.khfac, g_hi = (P.flags & CFP_SPF_AP) ? gmax : o.khfac;
+      const double klo = P.kmin * g_lo, khi = P.kmax * g_hi;
+      if (klo > fmax(o.xminA, o.xminB) && khi < fmin(o.xmaxA, o.xmaxB)) o.flags |= SD_NOCLAMP;
+    }
     // stencil feed: first live (parameter, weight) inline, the rest through the CSR arrays
     o.par0 = -1;
     o.w0 = 0.0;
@@ -263,13 +298,21 @@ __global__ void spectro_setup_kernel(SpectroParams P) {
   }
   __syncthreads();
   if (threadIdx.x == 0 && !(P.materialize & 16)) {  // bit 4: batch (likelihood) mode needs no work list
-    int n = 0;
-    for (int s = 0; s < P.S; ++s) {
-      const SDev& o = P.sdev[(size_t)zb * P.S + s];
-      bool needed = (s == 0) || (s == P.ps_src) || (P.materialize & CFP_MAT_LNP) || (o.par0 >= 0);
-      if (needed) P.work[zb * P.S + n++] = s;
-    }
-    P.nwork[zb] = n;
+    // work list of the bin: [fiducial | full evaluations | bias-only | aliases of the fiducial that feed a
+    // derivative or are materialised]; the lattice loop runs one branch-free loop per class
+    int n = 0, cnt[3] = {0, 0, 0};
+    P.work[zb * P.S + n++] = 0;
+    for (int cls = 0; cls < 3; ++cls)
+      for (int s = 1; s < P.S; ++s) {
+        const SDev& o = P.sdev[(size_t)zb * P.S + s];
+        const bool needed = (s == P.ps_src) || (P.materialize & CFP_MAT_LNP) || (o.par0 >= 0);
+        const int c = !(o.flags & SD_OWN) ? 2 : ((o.flags & SD_BIASONLY) ? 1 : 0);
+        if (needed && c == cls) P.work[zb * P.S + n++] = s, ++cnt[cls];
+      }
+    P.nwork[zb * 4 + 0] = cnt[0];
+    P.nwork[zb * 4 + 1] = cnt[1];
+    P.nwork[zb * 4 + 2] = cnt[2];
+    P.nwork[zb * 4 + 3] = n;
   }
 }
 
@@ -412,44 +455,61 @@ __device__ __forceinline__ RowC row_consts(const SDev& p, unsigned flags, double
   return r;
 }
 
-// X = P_obs / exp(-err^2) and err^2 (so that ln P_obs = ln X - err^2 needs a single log and no exp)
+// X = P_obs / exp(-err^2) and err^2 (so that ln P_obs = ln X - err^2 needs a single log and no exp).
+// X = (bterm + F)^2 W with  bterm = bias * qf (Q-bias factor),  F = f(k') fs8 mu'^2,
+// W = bao/s8^2 * dewiggled P(k') / FoG: a point that differs from the fiducial only in its bias re-uses
+// qf, F and W of the fiducial (eval_bias_only).
 __device__ __forceinline__ double eval_x(const SDev& p, const RowC& rc, unsigned flags, double k, int& hA, int& hB,
-                                         int& hN, double& err2) {
+                                         int& hN, double& err2, double& qf, double& F, double& W) {
   const double err = k * rc.errc;
   err2 = err * err;
   const double kap = k * rc.G;
-  double bterm = p.bias;
-  if (p.flags & SD_QBIAS) bterm *= fast_div(1.0 + kap * kap * p.A2, 1.0 + kap * p.A1);
+  qf = 1.0;
+  if (p.flags & SD_QBIAS) qf = fast_div(1.0 + kap * kap * p.A2, 1.0 + kap * p.A1);
   // tabulated P_lin(k'), f(k') (FITPACK clamps the argument to the knot range)
   double lo;
-  double x = fmin(fmax(kap, p.xminA), p.xmaxA);
+  double x = kap;
+  if (!(p.flags & SD_NOCLAMP)) {
+    x = x < p.xminA ? p.xminA : x;
+    x = x > p.xmaxA ? p.xmaxA : x;
+  }
   hA = locate<CUBIC_BLK>(p.blkA, p.nA, x, hA, lo);
   double u = x - lo;
   const double pdd = cubic_at(p.blkA, hA, u);
   if (p.flags & SD_SHARED_KNOTS) {
     hB = hA;
   } else {
-    x = fmin(fmax(kap, p.xminB), p.xmaxB);
+    x = kap;
+    if (!(p.flags & SD_NOCLAMP)) {
+      x = x < p.xminB ? p.xminB : x;
+      x = x > p.xmaxB ? p.xmaxB : x;
+    }
     hB = locate<CUBIC_BLK>(p.blkB, p.nB, x, hB, lo);
     u = x - lo;
   }
-  const double kaiser = fma(cubic_at(p.blkB, hB, u), rc.fmu2, bterm);  // spectro_obs.py:584-637
-  double num = p.baos * (kaiser * kaiser);
+  F = cubic_at(p.blkB, hB, u) * rc.fmu2;  // spectro_obs.py:584-637
   if (!(flags & CFP_SPF_LINEAR)) {
     // dewiggling, spectro_obs.py:699-722, 811-843; degree-1 spline with extrapolation
     hN = locate<LIN_BLK>(p.blkN, p.nN, kap, hN, lo);
     const double2 ys = __ldg(reinterpret_cast<const double2*>(p.blkN + (size_t)hN * LIN_BLK + 2));
     const double pnw = fma(ys.y, kap - lo, ys.x);
     const double e = fast_exp_neg(-rc.sv2 * (kap * kap));
-    num *= fma(e, pdd - pnw, pnw);  // pdd e + pnw (1 - e)
-    if (flags & CFP_SPF_FOG) {      // Lorentzian FoG, spectro_obs.py:639-676
+    W = p.baos * fma(e, pdd - pnw, pnw);  // pdd e + pnw (1 - e)
+    if (flags & CFP_SPF_FOG) {            // Lorentzian FoG, spectro_obs.py:639-676
       const double t = kap * rc.fogc;
-      num = fast_div(num, fma(t, t, 1.0));
+      W = fast_div(W, fma(t, t, 1.0));
     }
   } else {
-    num *= pdd;
+    W = p.baos * pdd;
   }
-  return num;
+  const double kaiser = fma(p.bias, qf, F);
+  return (kaiser * kaiser) * W;
+}
+
+__device__ __forceinline__ double eval_x(const SDev& p, const RowC& rc, unsigned flags, double k, int& hA, int& hB,
+                                         int& hN, double& err2) {
+  double qf, F, W;
+  return eval_x(p, rc, flags, k, hA, hB, hN, err2, qf, F, W);
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -462,23 +522,24 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // evaluation without spills when the Gram tile is small; measured 1.83 -> 1.30 ms against 2 CTAs per SM.
 // (Two cells per thread were tried and lost to one cell per thread at higher occupancy: profiles/r1c.)
 constexpr int fisher_min_blocks(int nb) { return nb <= 2 ? 4 : (nb == 3 ? 3 : 2); }
-constexpr int MAX_STAGED_ROWS = 4;  // mu rows a 256-cell tile may touch and still stage its row constants
-
-// STAGED: the row constants of the (at most nrows) mu rows a tile touches are computed once per tile into
-// shared memory by a few threads; otherwise (tiny Nk: a tile spans many rows) every thread derives its own.
-template <int NB, bool STAGED, int MINB = fisher_min_blocks(NB)>
-__global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParams P, int nrows) {
+// The lattice of one bin is cut into tiles of TILE consecutive wavenumbers x ONE mu row; a CTA takes a contiguous
+// run of tiles in (k block, mu row) order, i.e. it walks down the rows of a k block.  Along that walk k' = k G(mu)
+// moves by a fraction of a table piece per step, so every thread keeps valid piece hints from tile to tile, and
+// the row constants of all stencil points are staged in shared memory once per tile by a few threads.
+template <int NB, int MINB = fisher_min_blocks(NB)>
+__global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParams P, int row_lo, int nrows) {
   constexpr int T = NB * (NB + 1) / 2;
   constexpr int LDC = TILE + LDPAD;
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   double* sm_d = smem;                                 // [NB*8][LDC]
   double* sm_w = smem + NB * 8 * LDC;                  // [TILE]
   SDev* sm_s = reinterpret_cast<SDev*>(sm_w + TILE);   // [S]
-  RowC* sm_r = reinterpret_cast<RowC*>(sm_s + P.S);    // [nrows][S]   (STAGED only)
+  RowC* sm_r = reinterpret_cast<RowC*>(sm_s + P.S);    // [S]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int zb = blockIdx.y;
-  const int64_t ncell = P.cell_end - P.cell_begin;
-  const int64_t ntile = (ncell + TILE - 1) / TILE;
+  const int nkb = (P.Nk + TILE - 1) / TILE;
+  const int64_t ntile = (int64_t)nkb * nrows;
+  const int64_t t_begin = ntile * blockIdx.x / gridDim.x, t_end = ntile * (blockIdx.x + 1) / gridDim.x;
   const int64_t lattice = (int64_t)P.Nmu * P.Nk;
   {
     const int nwords = P.S * (int)(sizeof(SDev) / sizeof(double));
@@ -487,100 +548,108 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
     for (int i = tid; i < nwords; i += TILE) dst[i] = src[i];
   }
   __syncthreads();
-  const int nwork = P.nwork[zb];
+  const int n_full = P.nwork[zb * 4 + 0], n_bias = P.nwork[zb * 4 + 1], n_alias = P.nwork[zb * 4 + 2];
   const int* work = P.work + zb * P.S;
 
   double acc[T][2];
 #pragma unroll
   for (int t = 0; t < T; ++t) acc[t][0] = acc[t][1] = 0.0;
 
-  const double nbar = P.nbar[zb], vol = P.vol[zb];
+  const double nbar = P.nbar[zb], vol2 = 2.0 * P.vol[zb];
+  int kb_cur = -1, ki = 0;
+  bool col_ok = false;
+  double k = 0.0, wcol = 0.0;
+  int hA = -1, hB = -1, hN = -1;
 
-  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
-    const int64_t cell0 = P.cell_begin + tile * TILE;
-    const int64_t cell = cell0 + tid;
-    const bool valid = cell < P.cell_end;
-    const int mi = valid ? (int)(cell / P.Nk) : 0;
-    const int ki = valid ? (int)(cell - (int64_t)mi * P.Nk) : 0;
-    const double k = __ldg(P.k + ki);
-    const RowC* myrow = nullptr;
-    double mu = 0.0, smu = 0.0;
-    if (STAGED) {
-      const int r0 = (int)(cell0 / P.Nk);
-      __syncthreads();  // every warp is done with the previous tile's rows
-      for (int t = tid; t < nrows * nwork; t += TILE) {
-        const int rs = t / nwork, s = work[t - rs * nwork];
-        const int r = min(r0 + rs, P.Nmu - 1);
-        if (sm_s[s].flags & SD_OWN) sm_r[rs * P.S + s] = row_consts(sm_s[s], P.flags, __ldg(P.mu + r), __ldg(P.smu + r));
-      }
-      __syncthreads();
-      myrow = sm_r + (valid ? mi - r0 : 0) * P.S;
-    } else {
-      mu = __ldg(P.mu + mi);
-      smu = __ldg(P.smu + mi);
+  for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    const int kb = (int)(tile / nrows);
+    const int row = row_lo + (int)(tile - (int64_t)kb * nrows);
+    if (kb != kb_cur) {  // new block of wavenumbers: new k, Simpson weight; the hints restart
+      kb_cur = kb;
+      ki = kb * TILE + tid;
+      col_ok = ki < P.Nk;
+      ki = col_ok ? ki : P.Nk - 1;
+      k = __ldg(P.k + ki);
+      wcol = (k * k) * __ldg(P.wk + ki);
+      hA = hB = hN = -1;
     }
-    int hA = -1, hB = -1, hN = -1;
-    double P0 = 1.0, Psrc = 1.0, lnP0 = 0.0;
+    const int64_t cell = (int64_t)row * P.Nk + ki;
+    const bool valid = col_ok && cell >= P.cell_begin && cell < P.cell_end;
+    __syncthreads();  // every warp is done with the previous tile's row constants
+    for (int t = tid; t <= n_full; t += TILE) {  // the fiducial and the fully evaluated points
+      const int s = work[t];
+      sm_r[s] = row_consts(sm_s[s], P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
+    }
+    __syncthreads();
+    if (!__any_sync(0xffffffffu, valid)) continue;  // (uniform per warp; the barriers above are per tile)
 #pragma unroll 4
     for (int p = 0; p < NB * 8; ++p) sm_d[p * LDC + tid] = 0.0;
-    for (int wi = 0; wi < nwork; ++wi) {
-      const int s = work[wi];
-      const SDev& sp = sm_s[s];
-      double lnP, Pobs;
-      if (sp.flags & SD_OWN) {
-        double err2, X;
-        if (STAGED) {
-          X = eval_x(sp, myrow[s], P.flags, k, hA, hB, hN, err2);
-        } else {
-          const RowC rc = row_consts(sp, P.flags, mu, smu);
-          X = eval_x(sp, rc, P.flags, k, hA, hB, hN, err2);
-        }
-        Pobs = 0.0;
-        if (sp.flags & SD_PSHOT) {
-          Pobs = X * fast_exp_neg(-err2) + sp.pshot;
-          lnP = fast_log(Pobs);
-        } else {
-          lnP = fast_log(X) - err2;
-          if (sp.flags & SD_SRC) Pobs = X * fast_exp_neg(-err2);
-        }
+    double Psrc = 1.0;
+    // ln P_obs (and P_obs where it is needed) from X and err^2, then the point's contribution to the derivatives
+    auto finish = [&](const SDev& sp, int s, double X, double err2) {
+      const int fl = sp.flags;
+      double lnP, Pobs = 0.0;
+      if (fl & SD_PSHOT) {
+        Pobs = X * fast_exp_neg(-err2) + sp.pshot;
+        lnP = fast_log(Pobs);
       } else {
-        Pobs = P0;
-        lnP = lnP0;
+        lnP = fast_log(X) - err2;
+        if (fl & SD_SRC) Pobs = X * fast_exp_neg(-err2);
       }
-      if (s == 0) {
-        P0 = Pobs;
-        lnP0 = lnP;
-      }
-      if (s == P.ps_src) Psrc = Pobs;
+      if (fl & SD_PSSRC) Psrc = Pobs;
       if ((P.materialize & CFP_MAT_LNP) && valid) P.lnp[((size_t)s * P.Z + zb) * lattice + cell] = lnP;
-      if (sp.par0 >= 0) {
-        sm_d[sp.par0 * LDC + tid] += sp.w0 * lnP;
+      const int par0 = sp.par0;
+      if (par0 >= 0) {
+        sm_d[par0 * LDC + tid] += sp.w0 * lnP;
         for (int j = sp.csr0; j < sp.csr1; ++j) {
           const int par = __ldg(P.st_par + j);
           if (!__ldg(P.dead + par * P.Z + zb)) sm_d[par * LDC + tid] += __ldg(P.st_w + j) * lnP;
         }
       }
+      return Pobs;
+    };
+    // the fiducial
+    double qf0, F0, W0, err20;
+    const double X0 = eval_x(sm_s[0], sm_r[0], P.flags, k, hA, hB, hN, err20, qf0, F0, W0);
+    const double P0 = finish(sm_s[0], 0, X0, err20);
+    int wi = 1;
+    // points with their own cosmology / AP factors: full evaluation
+    for (const int we = wi + n_full; wi < we; ++wi) {
+      const int s = work[wi];
+      double err2;
+      const double X = eval_x(sm_s[s], sm_r[s], P.flags, k, hA, hB, hN, err2);
+      finish(sm_s[s], s, X, err2);
+    }
+    // points that differ from the fiducial only in the bias: the table look-ups are the fiducial's
+    for (const int we = wi + n_bias; wi < we; ++wi) {
+      const int s = work[wi];
+      const double kaiser = fma(sm_s[s].bias, qf0, F0);
+      finish(sm_s[s], s, (kaiser * kaiser) * W0, err20);
+    }
+    // aliases of the fiducial in this bin
+    for (const int we = wi + n_alias; wi < we; ++wi) {
+      const int s = work[wi];
+      finish(sm_s[s], s, X0, err20);
     }
     // finish the derivatives of the cell
     for (int par = 0; par < P.npar; ++par) {
       const int pb = __ldg(P.ps_bin + par);
-      const double den = __ldg(P.st_den + par);
       double d;
       if (pb >= 0)
-        d = (pb == zb) ? 1.0 / Psrc : 0.0;  // spectro_cov.py:510-532
+        d = (pb == zb) ? fast_rcp(Psrc) : 0.0;  // spectro_cov.py:510-532
       else
-        d = sm_d[par * LDC + tid] / den;  // dead parameters accumulate nothing: exactly 0
+        d = sm_d[par * LDC + tid] * __ldg(P.st_rden + par);  // dead parameters accumulate nothing: exactly 0
       sm_d[par * LDC + tid] = d;
       if ((P.materialize & CFP_MAT_DERIVS) && valid) P.derivs[((size_t)par * P.Z + zb) * lattice + cell] = d;
     }
     {
       // effective volume on the fiducial spectrum and the quadrature weight of the cell
       const double npobs = nbar * P0;
-      const double r = npobs / (1.0 + npobs);
+      const double r = fast_div(npobs, 1.0 + npobs);
       const double veff = INV_8PI2 * r * r;  // spectro_cov.py:223-225
       if ((P.materialize & CFP_MAT_DERIVS) && valid) P.veff[(size_t)zb * lattice + cell] = veff;
       // cosmicfish.py:541: k^2 * 2 * V_survey * veff, times the Simpson weights of :510-511
-      sm_w[tid] = valid ? (k * k * 2.0 * vol * veff) * (__ldg(P.wmu + mi) * __ldg(P.wk + ki)) : 0.0;
+      sm_w[tid] = valid ? (vol2 * veff) * (__ldg(P.wmu + row) * wcol) : 0.0;
     }
     __syncwarp();
     // Gram update on the FP64 tensor cores: this warp's 32 cells, k-steps of 4 cells
@@ -804,7 +873,8 @@ struct cfp_spectro_plan {
   int64_t cell_begin = 0, cell_end = 0;
   double *k_d = nullptr, *mu_d = nullptr, *smu_d = nullptr, *wk_d = nullptr, *wmu_d = nullptr;
   double *scal_d = nullptr, *pnw_k_d = nullptr, *pnw_p_d = nullptr, *nbar_d = nullptr, *vol_d = nullptr;
-  double *st_w_d = nullptr, *st_den_d = nullptr, *zbin_d = nullptr;
+  double *st_w_d = nullptr, *st_den_d = nullptr, *st_rden_d = nullptr, *zbin_d = nullptr;
+  double kmin = 0.0, kmax = 0.0;
   int *alias_d = nullptr, *ps_bin_d = nullptr, *st_ptr_d = nullptr, *st_par_d = nullptr, *dead_d = nullptr;
   double *blk_d = nullptr, *blknw_d = nullptr, *dcoef_d = nullptr;
   SDev* sdev_d = nullptr;
@@ -927,6 +997,11 @@ extern "C" int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S
   SP_UP(double, pnw_k_h, (size_t)NC * nnw, pl->pnw_k_d);
   SP_UP(double, pnw_p_h, (size_t)NC * Z * nnw, pl->pnw_p_d);
   SP_UP(double, stden_h, (size_t)npar, pl->st_den_d);
+  std::vector<double> rden(npar);
+  for (int p = 0; p < npar; ++p) rden[p] = 1.0 / stden_h[p];
+  SP_UP(double, rden.data(), (size_t)npar, pl->st_rden_d);
+  pl->kmin = *std::min_element(k_h, k_h + Nk);
+  pl->kmax = *std::max_element(k_h, k_h + Nk);
   SP_UP(int, ps_bin_h, (size_t)npar, pl->ps_bin_d);
   SP_UP(double, nbar_h, (size_t)Z, pl->nbar_d);
   SP_UP(double, vol_h, (size_t)Z, pl->vol_d);
@@ -939,7 +1014,7 @@ extern "C" int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S
   SP_UP(double, nullptr, (size_t)NC * Z * (nnw - 1) * LIN_BLK, pl->blknw_d);
   SP_UP(SDev, nullptr, (size_t)Z * S, pl->sdev_d);
   SP_UP(int, nullptr, (size_t)Z * S, pl->work_d);
-  SP_UP(int, nullptr, (size_t)Z, pl->nwork_d);
+  SP_UP(int, nullptr, (size_t)Z * 4, pl->nwork_d);
   SP_UP(int, nullptr, (size_t)NC, pl->shared_d);
   SP_UP(double, nullptr, (size_t)NC * Z * 2 * maxncy, pl->dcoef_d);
   SP_UP(double, nullptr, (size_t)Z * npar * npar, pl->fisher_d);
@@ -971,26 +1046,17 @@ extern "C" int cfp_spectro_plan_set_slice(cfp_spectro_plan* plan, int64_t cell_b
 }
 
 template <int NB>
-static cudaError_t launch_fisher(const SpectroParams& P, dim3 grid, size_t smem, int nrows, cudaStream_t st) {
-  if (nrows > 0) {
-    cudaError_t e = cudaFuncSetAttribute(spectro_fisher_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return e;
-    spectro_fisher_kernel<NB, true><<<grid, TILE, smem, st>>>(P, nrows);
-  } else {
-    cudaError_t e = cudaFuncSetAttribute(spectro_fisher_kernel<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return e;
-    spectro_fisher_kernel<NB, false><<<grid, TILE, smem, st>>>(P, 0);
-  }
+static cudaError_t launch_fisher(const SpectroParams& P, dim3 grid, size_t smem, int row_lo, int nrows, cudaStream_t st) {
+  cudaError_t e =
+      cudaFuncSetAttribute(spectro_fisher_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  spectro_fisher_kernel<NB><<<grid, TILE, smem, st>>>(P, row_lo, nrows);
   return cudaGetLastError();
 }
 
-// nrows = mu rows whose constants are staged per tile (0: threads derive their own)
-static size_t fisher_smem(int nb, int S, int nrows) {
+static size_t fisher_smem(int nb, int S) {
   const int T = nb * (nb + 1) / 2;
-  return std::max((size_t)(nb * 8 * (TILE + LDPAD) + TILE) * sizeof(double) + (size_t)S * sizeof(SDev) +
-                      (size_t)nrows * S * sizeof(RowC),
+  return std::max((size_t)(nb * 8 * (TILE + LDPAD) + TILE) * sizeof(double) + (size_t)S * (sizeof(SDev) + sizeof(RowC)),
                   (size_t)(TILE / 32) * T * 64 * sizeof(double));
 }
 
@@ -1000,7 +1066,7 @@ static void spectro_fill_params(cfp_spectro_plan* pl, int materialize, SpectroPa
   P.cell_begin = pl->cell_begin, P.cell_end = pl->cell_end;
   P.k = pl->k_d, P.mu = pl->mu_d, P.smu = pl->smu_d, P.wk = pl->wk_d, P.wmu = pl->wmu_d;
   P.scal = pl->scal_d, P.alias = pl->alias_d, P.st_ptr = pl->st_ptr_d, P.st_par = pl->st_par_d;
-  P.st_w = pl->st_w_d, P.st_den = pl->st_den_d, P.ps_bin = pl->ps_bin_d, P.dead = pl->dead_d;
+  P.st_w = pl->st_w_d, P.st_den = pl->st_den_d, P.st_rden = pl->st_rden_d, P.kmin = pl->kmin, P.kmax = pl->kmax, P.ps_bin = pl->ps_bin_d, P.dead = pl->dead_d;
   P.nbar = pl->nbar_d, P.vol = pl->vol_d, P.blob = pl->bank->blob_d, P.desc = pl->bank->desc_d;
   P.n_tables = pl->bank->n_tables, P.tab_pl = pl->tab_pl, P.tab_f = pl->tab_f;
   P.blk = pl->blk_d, P.blknw = pl->blknw_d, P.sdev = pl->sdev_d, P.work = pl->work_d, P.nwork = pl->nwork_d;
@@ -1131,8 +1197,10 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
     CFP_CUDA(cfp_dev_alloc(ctx, (void**)&pl->veff_d, (size_t)pl->Z * lattice * sizeof(double)));
     allocated = true;
   }
-  const int64_t ncell = pl->cell_end - pl->cell_begin;
-  const int64_t ntile = std::max<int64_t>(1, (ncell + TILE - 1) / TILE);
+  // tiles = (blocks of TILE wavenumbers) x (mu rows the slice touches)
+  const int row_lo = (int)(pl->cell_begin / pl->Nk);
+  const int nrows = std::max(1, (int)((pl->cell_end + pl->Nk - 1) / pl->Nk) - row_lo);
+  const int64_t ntile = (int64_t)((pl->Nk + TILE - 1) / TILE) * nrows;
   const int T = pl->nb * (pl->nb + 1) / 2;
   // persistent grid: one wave of (resident CTAs per SM) x (SM count) CTAs, never more CTAs than tiles
   const int minb = fisher_min_blocks(pl->nb);
@@ -1161,14 +1229,11 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
   }
   CFP_CUDA(cudaEventRecord(pl->kev0, st));
   const dim3 grid(gx, pl->Z);
-  // a tile of TILE consecutive cells touches at most this many mu rows
-  int nrows = std::min(pl->Nmu, (TILE + pl->Nk - 2) / pl->Nk + 1);
-  if (nrows > MAX_STAGED_ROWS) nrows = 0;
-  const size_t smem = fisher_smem(pl->nb, pl->S, nrows);
+  const size_t smem = fisher_smem(pl->nb, pl->S);
   cudaError_t e = cudaSuccess;
 #define CFP_LAUNCH_NB(NBV)                                   \
   case NBV:                                                  \
-    e = launch_fisher<NBV>(P, grid, smem, nrows, st);        \
+    e = launch_fisher<NBV>(P, grid, smem, row_lo, nrows, st); \
     break;
   switch (pl->nb) {
     CFP_LAUNCH_NB(1)
@@ -1177,7 +1242,7 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
     CFP_LAUNCH_NB(4)
     CFP_LAUNCH_NB(5)
     default:
-      e = launch_fisher<6>(P, grid, smem, nrows, st);
+      e = launch_fisher<6>(P, grid, smem, row_lo, nrows, st);
       break;
   }
 #undef CFP_LAUNCH_NB
