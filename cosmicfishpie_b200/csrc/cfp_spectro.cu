@@ -348,49 +348,64 @@ __device__ __forceinline__ double fast_rsqrt(double x) {  // x > 0, normal
   return fma(y, e, y);
 }
 
-// Polynomial coefficients live in constant memory: a 64-bit literal costs two UMOV issue slots per use on
-// sm_100a (profiles/r1c: 45 UMOV per cell evaluation), a constant-bank operand costs none.
-__constant__ double CFP_EXP_C[14] = {
-    1.6059043836821613e-10, 2.0876756987868100e-09, 2.5052108385441720e-08, 2.7557319223985888e-07,
-    2.7557319223985893e-06, 2.4801587301587302e-05, 1.9841269841269841e-04, 1.3888888888888889e-03,
-    8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0};  // 1/13! ... 1/0!
-__constant__ double CFP_LOG_C[9] = {1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0,
-                                    1.0 / 9.0,  1.0 / 7.0,  1.0 / 5.0,  1.0 / 3.0};
-__constant__ double CFP_K[5] = {1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01,
-                                -1.90821492927058770002e-10, -700.0};  // log2(e), 1.5*2^52, -ln2_hi, -ln2_lo, clamp
+// Constants live in constant memory: a 64-bit literal costs two UMOV issue slots per use on sm_100a
+// (profiles/r1c: 45 UMOV per cell evaluation), a constant-bank operand costs one uniform load at most.
+// Table-driven versions for the lattice loops: shorter dependency chains and fewer constants than the pure
+// polynomial forms above (exp: 32-entry 2^(j/32) table + degree-6 polynomial; log: 64-entry (1/c, -ln(1/c)) table +
+// degree-7 log1p).  The tables live in shared memory, filled once per CTA by math_tables_fill.
+struct MathTab {
+  double e2[32];   // 2^(j/32)
+  double2 lg[64];  // {1/c_i, ln c_i},  c_i = 1 + (i + 1/2)/64
+};
 
-__device__ __forceinline__ double fast_exp_neg(double x) {  // x <= 0
-  x = fmax(x, CFP_K[4]);
-  double t = fma(x, CFP_K[0], CFP_K[1]);  // magic constant rounds x log2(e) to the nearest integer (low word)
-  const int n = __double2loint(t);
-  t -= CFP_K[1];
-  double r = fma(t, CFP_K[2], x);
-  r = fma(t, CFP_K[3], r);
-  double p = CFP_EXP_C[0];
-#pragma unroll
-  for (int i = 1; i < 14; ++i) p = fma(p, r, CFP_EXP_C[i]);
-  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+__device__ __forceinline__ void math_tables_fill(MathTab& t, int tid, int nthreads) {
+  for (int j = tid; j < 32; j += nthreads) t.e2[j] = exp2((double)j * (1.0 / 32.0));
+  for (int i = tid; i < 64; i += nthreads) {
+    const double rc = 1.0 / (1.0 + ((double)i + 0.5) * (1.0 / 64.0));
+    t.lg[i] = make_double2(rc, -log(rc));
+  }
 }
 
-__device__ __forceinline__ double fast_log(double x) {  // x > 0, normal
-  int hi = __double2hiint(x);
-  const int lo = __double2loint(x);
-  int e = (hi >> 20) - 1023;
-  hi = (hi & 0x000fffff) | 0x3ff00000;
-  const bool up = hi >= 0x3ff6a09f;  // mantissa >= sqrt(2): halve it
-  hi = up ? hi - 0x00100000 : hi;
-  e = up ? e + 1 : e;
-  const double m = __hiloint2double(hi, lo);  // [sqrt(1/2), sqrt(2))
-  const double f = fast_div(m - 1.0, m + 1.0);
-  const double s = f * f;
-  double p = CFP_LOG_C[0];
-#pragma unroll
-  for (int i = 1; i < 9; ++i) p = fma(p, s, CFP_LOG_C[i]);
-  p = p * s;  // atanh(f)/f - 1
+__constant__ double CFP_TEXP[9] = {46.166241308446828384,        // 32 / ln 2
+                                   6755399441055744.0,           // 1.5 * 2^52
+                                   -2.16608493865351192653e-02,  // -(ln 2 / 32) high part
+                                   -5.96317165397058656257e-12,  // -(ln 2 / 32) low part
+                                   1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, -700.0};
+__constant__ double CFP_TLOG[8] = {1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0,
+                                   6.93147180369123816490e-01, 1.90821492927058770002e-10, 0.0};
+
+__device__ __forceinline__ double tab_exp_neg(const MathTab& mt, double x) {  // x <= 0
+  x = x < CFP_TEXP[8] ? CFP_TEXP[8] : x;
+  double t = fma(x, CFP_TEXP[0], CFP_TEXP[1]);  // low word = round(32 x / ln 2) = 32 n + j
+  const int m = __double2loint(t);
+  t -= CFP_TEXP[1];
+  double r = fma(t, CFP_TEXP[2], x);
+  r = fma(t, CFP_TEXP[3], r);                   // |r| <= ln2/64
+  const double tj = mt.e2[m & 31];
+  double p = fma(CFP_TEXP[4], r, CFP_TEXP[5]);
+  p = fma(p, r, CFP_TEXP[6]);
+  p = fma(p, r, CFP_TEXP[7]);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  p *= tj;
+  return __hiloint2double(__double2hiint(p) + ((m >> 5) << 20), __double2loint(p));
+}
+
+__device__ __forceinline__ double tab_log(const MathTab& mt, double x) {  // x > 0, normal
+  const int hi = __double2hiint(x);
+  const int e = (hi >> 20) - 1023;
+  const double2 cl = mt.lg[(hi >> 14) & 63];
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));  // [1, 2)
+  const double t = fma(m, cl.x, -1.0);                                                   // |t| < 1/128
+  double p = fma(CFP_TLOG[0], t, CFP_TLOG[1]);
+  p = fma(p, t, CFP_TLOG[2]);
+  p = fma(p, t, CFP_TLOG[3]);
+  p = fma(p, t, CFP_TLOG[4]);
+  p = fma(p, t, -0.5);
+  const double r = fma(p, t * t, t);  // log1p(t)
   const double de = (double)e;
-  const double f2 = f + f;
-  // ln x = e ln2 + 2 f (1 + p)
-  return fma(de, -CFP_K[2], fma(f2, p, fma(de, -CFP_K[3], f2)));
+  return fma(de, CFP_TLOG[5], cl.y + fma(de, CFP_TLOG[6], r));
 }
 
 // ------------------------------------------------------------------ lattice evaluation
@@ -459,8 +474,8 @@ __device__ __forceinline__ RowC row_consts(const SDev& p, unsigned flags, double
 // X = (bterm + F)^2 W with  bterm = bias * qf (Q-bias factor),  F = f(k') fs8 mu'^2,
 // W = bao/s8^2 * dewiggled P(k') / FoG: a point that differs from the fiducial only in its bias re-uses
 // qf, F and W of the fiducial (eval_bias_only).
-__device__ __forceinline__ double eval_x(const SDev& p, const RowC& rc, unsigned flags, double k, int& hA, int& hB,
-                                         int& hN, double& err2, double& qf, double& F, double& W) {
+__device__ __forceinline__ double eval_x(const MathTab& mt, const SDev& p, const RowC& rc, unsigned flags, double k,
+                                         int& hA, int& hB, int& hN, double& err2, double& qf, double& F, double& W) {
   const double err = k * rc.errc;
   err2 = err * err;
   const double kap = k * rc.G;
@@ -493,7 +508,7 @@ __device__ __forceinline__ double eval_x(const SDev& p, const RowC& rc, unsigned
     hN = locate<LIN_BLK>(p.blkN, p.nN, kap, hN, lo);
     const double2 ys = __ldg(reinterpret_cast<const double2*>(p.blkN + (size_t)hN * LIN_BLK + 2));
     const double pnw = fma(ys.y, kap - lo, ys.x);
-    const double e = fast_exp_neg(-rc.sv2 * (kap * kap));
+    const double e = tab_exp_neg(mt, -rc.sv2 * (kap * kap));
     W = p.baos * fma(e, pdd - pnw, pnw);  // pdd e + pnw (1 - e)
     if (flags & CFP_SPF_FOG) {            // Lorentzian FoG, spectro_obs.py:639-676
       const double t = kap * rc.fogc;
@@ -506,10 +521,10 @@ __device__ __forceinline__ double eval_x(const SDev& p, const RowC& rc, unsigned
   return (kaiser * kaiser) * W;
 }
 
-__device__ __forceinline__ double eval_x(const SDev& p, const RowC& rc, unsigned flags, double k, int& hA, int& hB,
-                                         int& hN, double& err2) {
+__device__ __forceinline__ double eval_x(const MathTab& mt, const SDev& p, const RowC& rc, unsigned flags, double k,
+                                         int& hA, int& hB, int& hN, double& err2) {
   double qf, F, W;
-  return eval_x(p, rc, flags, k, hA, hB, hN, err2, qf, F, W);
+  return eval_x(mt, p, rc, flags, k, hA, hB, hN, err2, qf, F, W);
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -535,6 +550,8 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
   double* sm_w = smem + NB * 8 * LDC;                  // [TILE]
   SDev* sm_s = reinterpret_cast<SDev*>(sm_w + TILE);   // [S]
   RowC* sm_r = reinterpret_cast<RowC*>(sm_s + P.S);    // [S]
+  MathTab& mt = *reinterpret_cast<MathTab*>(sm_r + P.S);
+  math_tables_fill(mt, threadIdx.x, TILE);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int zb = blockIdx.y;
   const int nkb = (P.Nk + TILE - 1) / TILE;
@@ -590,11 +607,11 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
       const int fl = sp.flags;
       double lnP, Pobs = 0.0;
       if (fl & SD_PSHOT) {
-        Pobs = X * fast_exp_neg(-err2) + sp.pshot;
-        lnP = fast_log(Pobs);
+        Pobs = X * tab_exp_neg(mt, -err2) + sp.pshot;
+        lnP = tab_log(mt, Pobs);
       } else {
-        lnP = fast_log(X) - err2;
-        if (fl & SD_SRC) Pobs = X * fast_exp_neg(-err2);
+        lnP = tab_log(mt, X) - err2;
+        if (fl & SD_SRC) Pobs = X * tab_exp_neg(mt, -err2);
       }
       if (fl & SD_PSSRC) Psrc = Pobs;
       if ((P.materialize & CFP_MAT_LNP) && valid) P.lnp[((size_t)s * P.Z + zb) * lattice + cell] = lnP;
@@ -610,14 +627,14 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
     };
     // the fiducial
     double qf0, F0, W0, err20;
-    const double X0 = eval_x(sm_s[0], sm_r[0], P.flags, k, hA, hB, hN, err20, qf0, F0, W0);
+    const double X0 = eval_x(mt, sm_s[0], sm_r[0], P.flags, k, hA, hB, hN, err20, qf0, F0, W0);
     const double P0 = finish(sm_s[0], 0, X0, err20);
     int wi = 1;
     // points with their own cosmology / AP factors: full evaluation
     for (const int we = wi + n_full; wi < we; ++wi) {
       const int s = work[wi];
       double err2;
-      const double X = eval_x(sm_s[s], sm_r[s], P.flags, k, hA, hB, hN, err2);
+      const double X = eval_x(mt, sm_s[s], sm_r[s], P.flags, k, hA, hB, hN, err2);
       finish(sm_s[s], s, X, err2);
     }
     // points that differ from the fiducial only in the bias: the table look-ups are the fiducial's
@@ -741,9 +758,11 @@ struct CellWalk {
 __global__ void __launch_bounds__(TILE, 3) spectro_data_kernel(SpectroParams P, const double* __restrict__ shot_data,
                                                                double* __restrict__ data) {
   __shared__ SDev sp;
+  __shared__ MathTab mt;
   const int zb = blockIdx.y, tid = threadIdx.x;
   if (tid < (int)(sizeof(SDev) / sizeof(double)))
     reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S)[tid];
+  math_tables_fill(mt, tid, TILE);
   __syncthreads();
   const int64_t lattice = (int64_t)P.Nmu * P.Nk;
   const double extra = 1.0 / P.nbar[zb] + (shot_data ? shot_data[zb] : 0.0);
@@ -756,8 +775,8 @@ __global__ void __launch_bounds__(TILE, 3) spectro_data_kernel(SpectroParams P, 
       rc = row_consts(sp, P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
     }
     double err2;
-    const double X = eval_x(sp, rc, P.flags, __ldg(P.k + w.ki), hA, hB, hN, err2);
-    data[(size_t)zb * lattice + w.cell] = X * fast_exp_neg(-err2) + sp.pshot + extra;
+    const double X = eval_x(mt, sp, rc, P.flags, __ldg(P.k + w.ki), hA, hB, hN, err2);
+    data[(size_t)zb * lattice + w.cell] = X * tab_exp_neg(mt, -err2) + sp.pshot + extra;
   }
 }
 
@@ -773,9 +792,11 @@ __global__ void __launch_bounds__(TILE, 3) spectro_chi2_kernel(SpectroParams P, 
   __shared__ RowC rows[CHI_ROWS];
   __shared__ double wrow[CHI_ROWS];
   __shared__ double red[TILE / 32];
+  __shared__ MathTab mt;
   const int zb = blockIdx.y, s = s_begin + blockIdx.z, tid = threadIdx.x;
   if (tid < (int)(sizeof(SDev) / sizeof(double)))
     reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S + s)[tid];
+  math_tables_fill(mt, tid, TILE);
   __syncthreads();
   const int64_t lattice = (int64_t)P.Nmu * P.Nk;
   const double extra = 1.0 / P.nbar[zb] + shot[(size_t)s * P.Z + zb] + sp.pshot;
@@ -802,8 +823,8 @@ __global__ void __launch_bounds__(TILE, 3) spectro_chi2_kernel(SpectroParams P, 
       for (int r = 0; r < nr; ++r) {
         const double Pd = __ldg(dcol + (size_t)r * P.Nk);
         double err2;
-        const double X = eval_x(sp, rows[r], P.flags, k, hA, hB, hN, err2);
-        const double Pt = fma(X, fast_exp_neg(-err2), extra);
+        const double X = eval_x(mt, sp, rows[r], P.flags, k, hA, hB, hN, err2);
+        const double Pt = fma(X, tab_exp_neg(mt, -err2), extra);
         const double q = (Pd - Pt) * fast_rcp(Pd);
         colsum = fma(wrow[r], q * q, colsum);
       }
@@ -1056,7 +1077,8 @@ static cudaError_t launch_fisher(const SpectroParams& P, dim3 grid, size_t smem,
 
 static size_t fisher_smem(int nb, int S) {
   const int T = nb * (nb + 1) / 2;
-  return std::max((size_t)(nb * 8 * (TILE + LDPAD) + TILE) * sizeof(double) + (size_t)S * (sizeof(SDev) + sizeof(RowC)),
+  return std::max((size_t)(nb * 8 * (TILE + LDPAD) + TILE) * sizeof(double) + (size_t)S * (sizeof(SDev) + sizeof(RowC)) +
+                      sizeof(MathTab),
                   (size_t)(TILE / 32) * T * 64 * sizeof(double));
 }
 
