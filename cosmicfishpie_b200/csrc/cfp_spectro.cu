@@ -533,10 +533,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// Resident CTAs per SM the kernel is compiled for: 64 registers/thread (4 CTAs, 32 warps per SM) still fit the
-// evaluation without spills when the Gram tile is small; measured 1.83 -> 1.30 ms against 2 CTAs per SM.
-// (Two cells per thread were tried and lost to one cell per thread at higher occupancy: profiles/r1c.)
-constexpr int fisher_min_blocks(int nb) { return nb <= 2 ? 4 : (nb == 3 ? 3 : 2); }
+// Resident CTAs per SM the kernel is compiled for.  The loop is latency-bound (table look-ups, Horner chains), so
+// resident warps matter more than registers: measured on B200 for the 2-block Gram tile, 2 CTAs/SM 1.83 ms,
+// 3 CTAs 1.13 ms, 4 CTAs (64 registers) 0.97 ms, 5 CTAs (48 registers, ~90 B of spills that ptxas places around
+// the per-tile code, not the evaluation loop) 0.88 ms.  Shared memory (43 KB per CTA) stops at 5.
+constexpr int fisher_min_blocks(int nb) { return nb <= 2 ? 5 : (nb == 3 ? 3 : 2); }
 // The lattice of one bin is cut into tiles of TILE consecutive wavenumbers x ONE mu row; a CTA takes a contiguous
 // run of tiles in (k block, mu row) order, i.e. it walks down the rows of a k block.  Along that walk k' = k G(mu)
 // moves by a fraction of a table piece per step, so every thread keeps valid piece hints from tile to tile, and
@@ -785,7 +786,7 @@ __global__ void __launch_bounds__(TILE, 3) spectro_data_kernel(SpectroParams P, 
 // drifts by a fraction of a piece per step, so the piece hints of the three tables stay valid, loads of the data
 // lattice stay coalesced, and the row constants of the point (staged once per CTA) are broadcast reads.
 constexpr int CHI_ROWS = 256;  // mu rows staged at a time (12 KB of RowC + 2 KB of row weights)
-__global__ void __launch_bounds__(TILE, 3) spectro_chi2_kernel(SpectroParams P, const double* __restrict__ data,
+__global__ void __launch_bounds__(TILE, 5) spectro_chi2_kernel(SpectroParams P, const double* __restrict__ data,
                                                                const double* __restrict__ shot, int s_begin,
                                                                double* __restrict__ partial) {
   __shared__ SDev sp;
@@ -1144,7 +1145,7 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
   const int nkb = (pl->Nk + TILE - 1) / TILE;
   int gx = 1;
   {
-    const int64_t slots = 3 * (int64_t)ctx->sm_count;  // spectro_chi2_kernel: 3 resident CTAs per SM
+    const int64_t slots = 5 * (int64_t)ctx->sm_count;  // spectro_chi2_kernel: 5 resident CTAs per SM
     int64_t best = INT64_MAX;
     for (int g = 1; g <= std::min(nkb, 64); ++g) {
       const int64_t ctas = (int64_t)g * S * Z;
