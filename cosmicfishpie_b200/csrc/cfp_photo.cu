@@ -230,132 +230,223 @@ __global__ void __launch_bounds__(CLS_THREADS) photo_cls_kernel(ClsParams P) {
 }
 
 struct FishParams {
-  int S, Nl, Nb, npar, l_begin, l_end, ldb;
+  int S, Nl, Nb, npar, l_begin, l_end, ldb, zstride;
   const double* cls;  // [S][Nl][Nb][Nb]
   const double *ell, *noise, *sqrtfsky;
   const int* stp_ptr;   // CSR of the stencil per parameter: stencil points and weights
   const int* stp_s;
   const double* stp_w;
   const double* stden;  // [npar]
-  double* Y;          // scratch [Nl-1][npar][Nb*ldb]
+  const double* strden; // [npar] 1 / stden
+  double* Y;          // scratch [Nl-1][npar][zstride]
   double* Fl;         // [Nl-1][npar][npar]
 };
 
-// One CTA per multipole bin (left-edge index li).  All steps are data-parallel (no triangular-solve chains):
-//   1. A = C_l(fiducial) + N in shared memory, inverted in place by Gauss-Jordan (SPD, no pivoting needed;
+// One CTA (16 warps) per multipole bin (left-edge index li).  All steps are data-parallel:
+//   1. M_p = Phi dC_p for every parameter, streamed from the stencil's C_ell (one warp per (parameter, 8 rows),
+//      16 independent coalesced loads in flight per lane) straight into the buffer Z_p will replace
+//   2. A = C_l(fiducial) + N in shared memory, inverted in place by Gauss-Jordan (SPD, no pivoting needed;
 //      cond <= 2e4, the reference itself uses an explicit pinv)
-//   2. one WARP per parameter: M_p = Phi dC_p into a per-warp shared tile, Z_p = A^-1 M_p into shared memory
-//      (global scratch when all Z_p do not fit); warps run independently, so load latency is hidden across warps
-//   3. F_pq = w_l sum_ij Z_p[i][j] Z_q[j][i] = w_l Tr(dC_p Sigma^-1 dC_q Sigma^-1), one warp per (p,q)
-constexpr int FISH_THREADS = 256;
+//   3. Z_p = A^-1 M_p in place on the FP64 tensor cores (mma.m8n8k4), one warp per (parameter, 8 columns)
+//   4. F_pq = w_l sum_ij Z_p[i][j] Z_q[j][i] = w_l Tr(dC_p Sigma^-1 dC_q Sigma^-1) as a (npar x K)(K x npar) product
+//      over K = (i, j) on the tensor cores; warps split K, partial tiles are added in fixed warp order
+// The Z_p live in shared memory when they fit (ZSMEM), else in a global scratch.
+constexpr int FISH_THREADS = 512;
 constexpr int FISH_WARPS = FISH_THREADS / 32;
+constexpr int FISH_MAX_PT = 8;   // npar <= 64
 
-__global__ void __launch_bounds__(FISH_THREADS) photo_fisher_kernel(FishParams P, int z_in_smem) {
+template <int KTMAX, bool ZSMEM>  // KTMAX: k-steps of step 3 the kernel is unrolled for (Nb <= 4 KTMAX)
+__global__ void __launch_bounds__(FISH_THREADS) photo_fisher_kernel(FishParams P) {
   extern __shared__ double sm[];
   const int Nb = P.Nb, ld = P.ldb;
-  double* sA = sm;                                  // [Nb][ld]
-  double* sM = sA + Nb * ld;                        // [FISH_WARPS][Nb][ld]
-  double* sZ = sM + (size_t)FISH_WARPS * Nb * ld;   // [npar][Nb][ld] if z_in_smem
+  const int PT = (P.npar + 7) / 8;
+  double* sA = sm;                                   // [Nb][ld]
+  double* sR = sA + Nb * ld;                         // [FISH_WARPS][PT][64] cross-warp reduction of step 4
+  double* sZ = sR + FISH_WARPS * PT * 64;            // [npar][zstride] if ZSMEM
   const int li = P.l_begin + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (li >= P.l_end) return;
+  const int ps = P.zstride;  // doubles between consecutive Z_p (padded: conflict-free fragment loads below)
+  double* Z = ZSMEM ? sZ : (P.Y + (size_t)blockIdx.x * P.npar * ps);
   const double* C0 = P.cls + ((size_t)0 * P.Nl + li) * Nb * Nb;
-  for (int e = tid; e < Nb * Nb; e += blockDim.x) {
-    const int i = e / Nb, j = e % Nb;
+  for (int e = tid; e < Nb * Nb; e += FISH_THREADS) {
+    const int i = e / Nb, j = e - i * Nb;
     sA[i * ld + j] = C0[e] + ((i == j) ? P.noise[i] : 0.0);
   }
-  __syncthreads();
-  // in-place Gauss-Jordan inversion: every thread computes the new values of its (<= 16) elements from the
-  // old matrix into registers, the CTA synchronises, then they are written back
-  const int per = (Nb * Nb + blockDim.x - 1) / blockDim.x;  // uniform across the CTA (Nb <= 64 -> per <= 16)
-  int ei[16], ej[16];
+  // ---- 1. M_p = Phi dC_p (photo_cov.py:228); padding columns are zero ------------------------------------
+  const int RB = (Nb + 7) / 8;
+  for (int unit = warp; unit < P.npar * RB; unit += FISH_WARPS) {
+    const int p = unit / RB, i0 = (unit - p * RB) * 8;
+    const int q0 = P.stp_ptr[p], nq = P.stp_ptr[p + 1] - q0;
+    const double rden = P.strden[p];
+    double* Zp = Z + (size_t)p * ps;
+    if (nq <= 4) {
+      const double* src[4];
+      double wq[4];
 #pragma unroll
-  for (int it = 0; it < 16; ++it) {
-    const int e = tid + it * blockDim.x;
-    ei[it] = e / Nb;
-    ej[it] = e % Nb;
-  }
-  for (int k = 0; k < Nb; ++k) {
-    const double piv = 1.0 / sA[k * ld + k];
-    double v[16];
-#pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      const int e = tid + it * blockDim.x;
-      if (it < per && e < Nb * Nb) {
-        const int i = ei[it], j = ej[it];
-        const double aik = sA[i * ld + k], akj = sA[k * ld + j];
-        if (i == k)
-          v[it] = (j == k) ? piv : akj * piv;
-        else if (j == k)
-          v[it] = -aik * piv;
-        else
-          v[it] = sA[i * ld + j] - aik * (akj * piv);
+      for (int u = 0; u < 4; ++u) {
+        const bool on = u < nq;
+        src[u] = P.cls + ((size_t)(on ? P.stp_s[q0 + u] : 0) * P.Nl + li) * Nb * Nb;
+        wq[u] = on ? P.stp_w[q0 + u] : 0.0;
       }
-    }
-    __syncthreads();
+      for (int j = lane; j < ld; j += 32) {
+        const bool jok = j < Nb;
+        const int jj = jok ? j : Nb - 1;
 #pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      const int e = tid + it * blockDim.x;
-      if (it < per && e < Nb * Nb) sA[ei[it] * ld + ej[it]] = v[it];
-    }
-    __syncthreads();
-  }
-  double* Z = z_in_smem ? sZ : (P.Y + (size_t)blockIdx.x * P.npar * Nb * ld);
-  double* Mw = sM + (size_t)warp * Nb * ld;
-  // lane = column j (no integer division in the inner loops); Nb <= 64 -> at most two column passes
-  for (int p = warp; p < P.npar; p += FISH_WARPS) {
-    const int q0 = P.stp_ptr[p], q1 = P.stp_ptr[p + 1];
-    const double rden = P.stden[p];
-    for (int j = lane; j < Nb; j += 32)
-      for (int i = 0; i < Nb; ++i) {
-        double acc = 0.0;
-        for (int q = q0; q < q1; ++q)
-          acc += P.stp_w[q] * __ldg(P.cls + (((size_t)P.stp_s[q] * P.Nl + li) * Nb + i) * Nb + j);
-        Mw[i * ld + j] = (acc / rden) * P.sqrtfsky[i];
-      }
-    __syncwarp();
-    double* Zp = Z + (size_t)p * Nb * ld;
-    for (int j = lane; j < Nb; j += 32)
-      for (int i = 0; i < Nb; ++i) {
-        double a0 = 0.0, a1 = 0.0;
-        int k = 0;
-        for (; k + 1 < Nb; k += 2) {
-          a0 += sA[i * ld + k] * Mw[k * ld + j];
-          a1 += sA[i * ld + k + 1] * Mw[(k + 1) * ld + j];
+        for (int ih = 0; ih < 8; ih += 4) {
+          double v[4][4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int ii = min(i0 + ih + r, Nb - 1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u][r] = (u < nq) ? __ldg(src[u] + (size_t)ii * Nb + jj) : 0.0;
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int i = i0 + ih + r;
+            double acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc += wq[u] * v[u][r];
+            if (i < Nb) Zp[i * ld + j] = jok ? (acc * rden) * P.sqrtfsky[i] : 0.0;
+          }
         }
-        if (k < Nb) a0 += sA[i * ld + k] * Mw[k * ld + j];
-        Zp[i * ld + j] = a0 + a1;
       }
-    __syncwarp();
+    } else {
+      for (int j = lane; j < ld; j += 32)
+        for (int i = i0; i < min(i0 + 8, Nb); ++i) {
+          double acc = 0.0;
+          if (j < Nb)
+            for (int q = q0; q < q0 + nq; ++q)
+              acc += P.stp_w[q] * __ldg(P.cls + (((size_t)P.stp_s[q] * P.Nl + li) * Nb + i) * Nb + j);
+          Zp[i * ld + j] = (acc * rden) * P.sqrtfsky[i];
+        }
+    }
   }
   __syncthreads();
-  // F_l[p][q] = w_l sum_ij Z_p[i][j] Z_q[j][i]; cosmicfish.py:681-683, 704, 723.  One warp per (p,q) pair,
-  // pairs enumerated in triangular order, each warp advancing by FISH_WARPS pairs.
+  // ---- 2. in-place Gauss-Jordan inversion: every thread computes the new values of its (<= 8) elements from the
+  // old matrix into registers, the CTA synchronises, then they are written back
+  {
+    const int per = (Nb * Nb + FISH_THREADS - 1) / FISH_THREADS;  // uniform across the CTA (Nb <= 64 -> per <= 8)
+    int eo[8], ec[8], er[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int e = tid + it * FISH_THREADS;
+      const int i = e / Nb, j = e - i * Nb;
+      er[it] = (e < Nb * Nb) ? i : -1;
+      ec[it] = j;
+      eo[it] = i * ld + j;
+    }
+    for (int k = 0; k < Nb; ++k) {
+      const double piv = 1.0 / sA[k * ld + k];
+      double v[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        if (it < per && er[it] >= 0) {
+          const int i = er[it], j = ec[it];
+          const double aik = sA[i * ld + k], akj = sA[k * ld + j];
+          const double t = akj * piv;
+          double r = sA[eo[it]] - aik * t;
+          r = (j == k) ? -aik * piv : r;
+          r = (i == k) ? ((j == k) ? piv : t) : r;
+          v[it] = r;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        if (it < per && er[it] >= 0) sA[eo[it]] = v[it];
+      __syncthreads();
+    }
+  }
+  // ---- 3. Z_p = A^-1 M_p in place: one warp per (parameter, block of 8 columns) -----------------------
+  const int g = lane >> 2, tg = lane & 3;  // mma.m8n8k4 fragment coordinates
+  const int MT = (Nb + 7) / 8, KT = (Nb + 3) / 4;
+  for (int unit = warp; unit < P.npar * MT; unit += FISH_WARPS) {
+    const int p = unit / MT, nt = unit - p * MT;
+    double* Zp = Z + (size_t)p * ps;
+    const int jb = nt * 8 + g;
+    double bf[KTMAX];  // the 8 columns of M_p this warp replaces: all k-steps of the B operand
+#pragma unroll
+    for (int kt = 0; kt < KTMAX; ++kt) {
+      const int k = kt * 4 + tg;
+      bf[kt] = (kt < KT && k < Nb && jb < Nb) ? Zp[k * ld + jb] : 0.0;
+    }
+    __syncwarp();
+    for (int mt = 0; mt < MT; ++mt) {
+      const int i = mt * 8 + g;
+      const bool iok = i < Nb;
+      const double* arow = sA + (iok ? i : 0) * ld + tg;
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int kt = 0; kt < KTMAX; ++kt) {
+        const double av = (kt < KT && iok && kt * 4 + tg < Nb) ? arow[kt * 4] : 0.0;
+        if (kt < KT) dmma884(c0, c1, av, bf[kt]);
+      }
+      const int j = nt * 8 + tg * 2;
+      if (iok && j < ld) Zp[i * ld + j] = c0;
+      if (iok && j + 1 < ld) Zp[i * ld + j + 1] = c1;
+    }
+  }
+  __syncthreads();
+  // ---- 4. F_l[p][q] = w_l sum_ij Z_p[i][j] Z_q[j][i]  (cosmicfish.py:681-683, 704, 723) -------------------
   const double lc = 0.5 * P.ell[li] + 0.5 * P.ell[li + 1];
   const double wl = (lc + 0.5) * (P.ell[li + 1] - P.ell[li]);
   double* Fl = P.Fl + (size_t)blockIdx.x * P.npar * P.npar;
-  int pp = 0, qq = warp;
-  while (qq > pp) {
-    qq -= pp + 1;
-    ++pp;
-  }
-  while (pp < P.npar) {
-    const double* Zp = Z + (size_t)pp * Nb * ld;
-    const double* Zq = Z + (size_t)qq * Nb * ld;
-    double s = 0.0;
-    for (int j = lane; j < Nb; j += 32)
-      for (int i = 0; i < Nb; ++i) s += Zp[i * ld + j] * Zq[j * ld + i];
+  const int KS = (Nb * ld) / 4;  // ld is a multiple of 4: a k-step never straddles two rows i
+  // B operand: B[k = (i, j)][q] = Z_q[j][i]; per-lane bases of the (at most FISH_MAX_PT) parameter blocks
+  const double* zq[FISH_MAX_PT];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-      s *= wl;
-      Fl[pp * P.npar + qq] = s;
-      Fl[qq * P.npar + pp] = s;
+  for (int u = 0; u < FISH_MAX_PT; ++u) {
+    const int qb = u * 8 + g;
+    zq[u] = Z + (size_t)(qb < P.npar ? qb : 0) * ps;
+  }
+  for (int pt = 0; pt < PT; ++pt) {
+    const int pa = pt * 8 + g;
+    const bool pok = pa < P.npar;
+    const double* Za = Z + (size_t)(pok ? pa : 0) * ps + tg;
+    double c[FISH_MAX_PT][2];
+#pragma unroll
+    for (int u = 0; u < FISH_MAX_PT; ++u) c[u][0] = c[u][1] = 0.0;
+    // k-step ks covers elements e = 4 ks + tg of row i = e / ld; this warp takes ks = warp, warp + 16, ...
+    int i = (warp * 4) / ld, j0 = warp * 4 - i * ld;
+    for (int ks = warp; ks < KS; ks += FISH_WARPS) {
+      const int j = j0 + tg;
+      const double av = pok ? Za[ks * 4] : 0.0;
+      const bool jok = j < Nb;
+      const int off = (jok ? j : 0) * ld + i;
+#pragma unroll
+      for (int u = 0; u < FISH_MAX_PT; ++u) {
+        if (u <= pt) {
+          const double bv = (jok && u * 8 + g < P.npar) ? zq[u][off] : 0.0;
+          dmma884(c[u][0], c[u][1], av, bv);
+        }
+      }
+      j0 += FISH_WARPS * 4;
+      while (j0 >= ld) {
+        j0 -= ld;
+        ++i;
+      }
     }
-    qq += FISH_WARPS;
-    while (qq > pp) {
-      qq -= pp + 1;
-      ++pp;
+    // fixed-order reduction over the warps
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < FISH_MAX_PT; ++u)
+      if (u <= pt) {
+        sR[((size_t)warp * PT + u) * 64 + lane * 2 + 0] = c[u][0];
+        sR[((size_t)warp * PT + u) * 64 + lane * 2 + 1] = c[u][1];
+      }
+    __syncthreads();
+    for (int x = tid; x < (pt + 1) * 64; x += FISH_THREADS) {
+      const int u = x / 64, l = (x % 64) / 2, r = x % 2;
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < FISH_WARPS; ++w) sum += sR[((size_t)w * PT + u) * 64 + l * 2 + r];
+      const int pi = pt * 8 + (l >> 2), qi = u * 8 + (l & 3) * 2 + r;
+      if (pi < P.npar && qi < P.npar && qi <= pi) {
+        sum *= wl;
+        Fl[pi * P.npar + qi] = sum;
+        Fl[qi * P.npar + pi] = sum;
+      }
     }
   }
 }
@@ -465,13 +556,14 @@ __global__ void photo_add_noise_kernel(int Nl, int Nb, const double* __restrict_
 struct cfp_photo_plan {
   cfp_ctx* ctx = nullptr;
   const cfp_bank* bank = nullptr;
-  int S = 0, NC = 0, Nl = 0, Nz = 0, Nb = 0, npar = 0, nb = 0, ldz = 0, nz4 = 0, ldb = 0, tab_p = 0;
+  int S = 0, NC = 0, Nl = 0, Nz = 0, Nb = 0, npar = 0, nb = 0, ldz = 0, nz4 = 0, ldb = 0, zstride = 0, tab_p = 0;
   int l_begin = 0, l_end = 0;
   double dz = 0.0, kmax = 0.0;
   int *cosmo_of_s_d = nullptr, *kind_d = nullptr;
   double *ell_d = nullptr, *z_d = nullptr, *chi_d = nullptr, *hub_d = nullptr, *wlpref_d = nullptr, *ngal_d = nullptr;
   double *bias_d = nullptr, *ia_d = nullptr, *lmin_d = nullptr, *lmax_d = nullptr, *noise_d = nullptr;
-  double *sqrtfsky_d = nullptr, *stw_d = nullptr, *stden_d = nullptr, *wz_d = nullptr, *stp_w_d = nullptr;
+  double *sqrtfsky_d = nullptr, *stw_d = nullptr, *stden_d = nullptr, *strden_d = nullptr, *wz_d = nullptr;
+  double* stp_w_d = nullptr;
   int *stp_ptr_d = nullptr, *stp_s_d = nullptr;
   double *T_d = nullptr, *eff_d = nullptr, *U_d = nullptr, *V_d = nullptr, *cls_d = nullptr, *Y_d = nullptr;
   double *Fl_d = nullptr, *fisher_d = nullptr;
@@ -511,6 +603,7 @@ extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, 
               "NULL input array");
   CFP_REQUIRE(S >= 1 && NC >= 1 && Nl >= 2 && Nz >= 2 && Nb >= 1 && npar >= 1, "bad dimensions");
   CFP_REQUIRE(Nb <= MAX_PNB * 8, "more than 64 tomographic rows");
+  CFP_REQUIRE(npar <= FISH_MAX_PT * 8, "more than 64 parameters");
   CFP_REQUIRE(NC <= bank->n_cosmo, "NC exceeds the bank");
   CFP_REQUIRE(tab_p >= 0 && tab_p < bank->n_tables, "bad table slot");
   for (int s = 0; s < S; ++s) CFP_REQUIRE(cosmo_of_s_h[s] >= 0 && cosmo_of_s_h[s] < NC, "cosmology index out of range");
@@ -531,7 +624,12 @@ extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, 
     photo_free(pl);
     return CFP_ERR_INVALID;
   }
-  pl->ldb = Nb | 1;
+  // row stride of the Nb x Nb tiles and stride between the Z_p blocks: multiples of 4 that are 4 or 12 mod 16,
+  // so that the m8n8k4 fragment loads of photo_fisher_kernel hit 16 distinct 8-byte banks per half warp
+  pl->ldb = Nb;
+  while (pl->ldb % 16 != 4 && pl->ldb % 16 != 12) ++pl->ldb;
+  pl->zstride = Nb * pl->ldb;
+  while (pl->zstride % 16 != 4 && pl->zstride % 16 != 12) pl->zstride += 4;
   pl->dz = dz, pl->kmax = kmax;
   pl->l_begin = 0, pl->l_end = Nl - 1;
   std::vector<double> wz(ldz, 0.0);
@@ -552,6 +650,9 @@ extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, 
   PH_UP(double, sqrtfsky_h, (size_t)Nb, pl->sqrtfsky_d);
   PH_UP(double, stw_h, (size_t)npar * S, pl->stw_d);
   PH_UP(double, stden_h, (size_t)npar, pl->stden_d);
+  std::vector<double> strden(npar);
+  for (int p = 0; p < npar; ++p) strden[p] = 1.0 / stden_h[p];
+  PH_UP(double, strden.data(), (size_t)npar, pl->strden_d);
   PH_UP(double, wz.data(), (size_t)ldz, pl->wz_d);
   {
     std::vector<int> ptr(npar + 1, 0), ss;
@@ -577,7 +678,7 @@ extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, 
   PH_UP(double, nullptr, (size_t)S * pl->nb * 8 * ldz, pl->U_d);
   PH_UP(double, nullptr, (size_t)S * pl->nb * 8 * ldz, pl->V_d);
   PH_UP(double, nullptr, (size_t)S * Nl * Nb * Nb, pl->cls_d);
-  PH_UP(double, nullptr, (size_t)(Nl - 1) * 2 * npar * Nb * pl->ldb, pl->Y_d);
+  PH_UP(double, nullptr, (size_t)(Nl - 1) * npar * pl->zstride, pl->Y_d);
   PH_UP(double, nullptr, (size_t)(Nl - 1) * npar * npar, pl->Fl_d);
   PH_UP(double, nullptr, (size_t)npar * npar, pl->fisher_d);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -714,19 +815,27 @@ static int photo_run_fisher(cfp_photo_plan* pl, cudaStream_t st) {
   {
     FishParams P;
     P.S = pl->S, P.Nl = pl->Nl, P.Nb = pl->Nb, P.npar = pl->npar, P.l_begin = pl->l_begin, P.l_end = pl->l_end;
-    P.ldb = pl->ldb;
+    P.ldb = pl->ldb, P.zstride = pl->zstride;
     P.cls = pl->cls_d, P.ell = pl->ell_d, P.noise = pl->noise_d, P.sqrtfsky = pl->sqrtfsky_d;
     P.stp_ptr = pl->stp_ptr_d, P.stp_s = pl->stp_s_d, P.stp_w = pl->stp_w_d;
-    P.stden = pl->stden_d, P.Y = pl->Y_d, P.Fl = pl->Fl_d;
+    P.stden = pl->stden_d, P.strden = pl->strden_d, P.Y = pl->Y_d, P.Fl = pl->Fl_d;
     const int nbins = pl->l_end - pl->l_begin;
-    size_t smem = (size_t)(1 + FISH_WARPS) * pl->Nb * pl->ldb * sizeof(double);
-    const size_t zsm = (size_t)pl->npar * pl->Nb * pl->ldb * sizeof(double);
-    const int z_in_smem = (smem + zsm <= 220 * 1024) ? 1 : 0;
-    if (z_in_smem) smem += zsm;
-    CFP_CUDA(cudaFuncSetAttribute(photo_fisher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int PT = (pl->npar + 7) / 8;
+    size_t smem = ((size_t)pl->Nb * pl->ldb + (size_t)FISH_WARPS * PT * 64) * sizeof(double);
+    const size_t zsm = (size_t)pl->npar * pl->zstride * sizeof(double);
+    const bool zs = smem + zsm <= 220 * 1024;
+    if (zs) smem += zsm;
+    void (*kern)(FishParams) = nullptr;
+    if (pl->Nb <= 16)
+      kern = zs ? photo_fisher_kernel<4, true> : photo_fisher_kernel<4, false>;
+    else if (pl->Nb <= 32)
+      kern = zs ? photo_fisher_kernel<8, true> : photo_fisher_kernel<8, false>;
+    else
+      kern = zs ? photo_fisher_kernel<16, true> : photo_fisher_kernel<16, false>;
+    CFP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CFP_CUDA(cudaEventRecord(pl->kev[4], st));
     if (nbins > 0) {
-      photo_fisher_kernel<<<nbins, FISH_THREADS, smem, st>>>(P, z_in_smem);
+      kern<<<nbins, FISH_THREADS, smem, st>>>(P);
       ctx->launches++;
       CFP_CUDA(cudaGetLastError());
     }
