@@ -62,19 +62,29 @@ __global__ void __launch_bounds__(256) photo_eff_kernel(int NC, int Nb, int Nz, 
     sq[i] = v / sch[i % Nz];
   }
   __syncthreads();
+  // trapezoid increments of both integrals, computed by the whole CTA: sq <- t2, se <- t1
+  for (int i = threadIdx.x; i < Nb * Nz; i += blockDim.x)
+    se[i] = (i % Nz < Nz - 1) ? 0.5 * (sq[i + 1] + sq[i]) * dz : 0.0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < Nb * Nz; i += blockDim.x) sq[i] = se[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < Nb * Nz; i += blockDim.x)
+    se[i] = (i % Nz < Nz - 1) ? 0.5 * (sn[i + 1] + sn[i]) * dz : 0.0;
+  __syncthreads();
+  // the serial part (np.cumsum order, photo_obs.py:137-147) is two additions and one FMA per step
   for (int a = threadIdx.x; a < Nb; a += blockDim.x) {
     double* e = se + (size_t)a * Nz;
     if (kind[a] != 0) {
       for (int i = 0; i < Nz; ++i) e[i] = 0.0;
       continue;
     }
-    const double* n = sn + (size_t)a * Nz;
-    const double* q = sq + (size_t)a * Nz;
+    const double* t2 = sq + (size_t)a * Nz;
     double I1 = 0.0, I2 = 0.0;
     e[Nz - 1] = I1 - sch[Nz - 1] * I2;
+#pragma unroll 4
     for (int i = Nz - 2; i >= 0; --i) {
-      I1 = I1 + 0.5 * (n[i + 1] + n[i]) * dz;
-      I2 = I2 + 0.5 * (q[i + 1] + q[i]) * dz;
+      I1 = I1 + e[i];
+      I2 = I2 + t2[i];
       e[i] = I1 - sch[i] * I2;
     }
   }
@@ -451,12 +461,18 @@ __global__ void __launch_bounds__(FISH_THREADS) photo_fisher_kernel(FishParams P
   }
 }
 
-__global__ void photo_reduce_kernel(const double* __restrict__ Fl, int nbins, int n, double* __restrict__ F) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// F = sum over multipole bins in a FIXED tree: one warp per element, lane l adds bins l, l+32, ... in order, then a
+// butterfly over the lanes.  All bins of an element are fetched concurrently instead of one dependent chain.
+__global__ void __launch_bounds__(256) photo_reduce_kernel(const double* __restrict__ Fl, int nbins, int n,
+                                                           double* __restrict__ F) {
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (e >= n) return;
   double s = 0.0;
-  for (int l = 0; l < nbins; ++l) s += Fl[(size_t)l * n + e];
-  F[e] = s;
+  for (int l = lane; l < nbins; l += 32) s += Fl[(size_t)l * n + e];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) F[e] = s;
 }
 
 
@@ -841,7 +857,7 @@ static int photo_run_fisher(cfp_photo_plan* pl, cudaStream_t st) {
     }
     CFP_CUDA(cudaEventRecord(pl->kev[5], st));
     const int n = pl->npar * pl->npar;
-    photo_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(pl->Fl_d, nbins, n, pl->fisher_d);
+    photo_reduce_kernel<<<(n + 7) / 8, 256, 0, st>>>(pl->Fl_d, nbins, n, pl->fisher_d);
     ctx->launches++;
     CFP_CUDA(cudaGetLastError());
   }

@@ -98,7 +98,7 @@ struct SpectroParams {
   const double* blob;
   double* blk;            // [(c*Z+zb)*2+tab][maxint][CUBIC_BLK]
   double* blknw;          // [(c*Z+zb)][nnw-1][LIN_BLK]
-  const int* shared_knots;  // [NC]
+  int* shared_tmp;          // [Z][NC]: 1 if P_lin and f of the cosmology share their k-knots
   SDev* sdev;             // [Z][S]
   int* work;              // [Z][S] stencil points to visit per bin, in order
   int* nwork;             // [Z][4]: full, bias-only and alias points in the bin's work list (after the fiducial)
@@ -118,10 +118,18 @@ struct PrepParams {
   double* blk;
   const double *pnw_k, *pnw_p;
   double* blknw;
-  int* shared_knots;    // [NC] 1 if P_lin and f share their k-knots
 };
 
-__global__ void spectro_prepare_kernel(PrepParams P) {
+struct SpectroParams;
+__device__ void spectro_setup_block(const SpectroParams& P, int zb);
+
+// blockIdx.y = 0, 1, 2: piece tables of P_lin, f, P_nw for job blockIdx.x = (cosmology, bin);
+// blockIdx.y = 3: the per-bin setup (spectro_setup_block) for bin blockIdx.x -- one launch does both.
+__global__ void spectro_prepare_kernel(PrepParams P, const SpectroParams SP, int Zbins) {
+  if (blockIdx.y == 3) {
+    if ((int)blockIdx.x < Zbins) spectro_setup_block(SP, blockIdx.x);
+    return;
+  }
   const int job = blockIdx.x;  // (c*Z + zb)
   const int c = job / P.Z, zb = job % P.Z;
   const int tab = blockIdx.y;  // 0: P_lin, 1: f, 2: no-wiggle
@@ -140,14 +148,6 @@ __global__ void spectro_prepare_kernel(PrepParams P) {
   }
   const int64_t* d = P.desc + ((size_t)c * P.n_tables + P.tab[tab]) * CFP_BANK_DESC;
   const int nx = (int)d[0], ny = (int)d[1];
-  if (tab == 0 && zb == 0) {  // do P_lin(z,k) and f(z,k) share their k-knots? (one piece search serves both)
-    const int64_t* d2 = P.desc + ((size_t)c * P.n_tables + P.tab[1]) * CFP_BANK_DESC;
-    int same = (d2[1] == d[1]);
-    if (same)
-      for (int i = threadIdx.x; i < ny; i += blockDim.x) same &= (P.blob[d[3] + i] == P.blob[d2[3] + i]);
-    same = __syncthreads_and(same);
-    if (threadIdx.x == 0) P.shared_knots[c] = same;
-  }
   const double* tx = P.blob + d[2];
   const double* ty = P.blob + d[3];
   const double* cf = P.blob + d[4];
@@ -221,8 +221,31 @@ __global__ void spectro_prepare_kernel(PrepParams P) {
 
 // one thread per (z-bin, stencil point): derived scalars, table pointers, stencil feed; thread 0 of
 // each bin then builds the bin's work list
-__global__ void spectro_setup_kernel(SpectroParams P) {
-  const int zb = blockIdx.x;
+__device__ void spectro_setup_block(const SpectroParams& P, int zb) {
+  extern __shared__ int cls_sm[];                   // [S] unless in batch mode
+  const bool batch = (P.materialize & 16) != 0;     // bit 4: batch (likelihood) mode needs no work list
+  // do P_lin(z,k) and f(z,k) share their k-knots? (one piece search serves both)  Answered here from the bank
+  // itself, so that this block does not wait for the piece tables the other blocks of the launch are writing.
+  int* same = P.shared_tmp + zb * P.NC;
+  for (int c = threadIdx.x; c < P.NC; c += blockDim.x) {
+    const int64_t* dA = P.desc + ((size_t)c * P.n_tables + P.tab_pl) * CFP_BANK_DESC;
+    const int64_t* dB = P.desc + ((size_t)c * P.n_tables + P.tab_f) * CFP_BANK_DESC;
+    same[c] = (dA[1] == dB[1]);
+  }
+  __syncthreads();
+  {
+    // all (cosmology, knot) comparisons as one flat loop: independent loads, a mismatch clears the flag
+    int nk_max = 0;
+    for (int c = 0; c < P.NC; ++c)
+      nk_max = max(nk_max, (int)P.desc[((size_t)c * P.n_tables + P.tab_pl) * CFP_BANK_DESC + 1]);
+    for (int x = threadIdx.x; x < P.NC * nk_max; x += blockDim.x) {
+      const int c = x / nk_max, i = x - c * nk_max;
+      const int64_t* dA = P.desc + ((size_t)c * P.n_tables + P.tab_pl) * CFP_BANK_DESC;
+      const int64_t* dB = P.desc + ((size_t)c * P.n_tables + P.tab_f) * CFP_BANK_DESC;
+      if (i < (int)dA[1] && dA[1] == dB[1] && P.blob[dA[3] + i] != P.blob[dB[3] + i]) same[c] = 0;
+    }
+  }
+  __syncthreads();
   for (int s = threadIdx.x; s < P.S; s += blockDim.x) {
     const double* sc = P.scal + ((size_t)s * P.Z + zb) * CFP_SP_NSCAL;
     SDev o;
@@ -252,12 +275,12 @@ __global__ void spectro_setup_kernel(SpectroParams P) {
     o.nA = (int)dA[1] - 7;
     o.nB = (int)dB[1] - 7;
     o.nN = P.nnw - 1;
-    o.xminA = o.blkA[0];
-    o.xmaxA = o.blkA[(size_t)(o.nA - 1) * CUBIC_BLK + 1];
-    o.xminB = o.blkB[0];
-    o.xmaxB = o.blkB[(size_t)(o.nB - 1) * CUBIC_BLK + 1];
+    o.xminA = P.blob[dA[3] + 3];  // = lo of the first piece, hi of the last (fpbisp.f clamps to [t[3], t[n-4]])
+    o.xmaxA = P.blob[dA[3] + dA[1] - 4];
+    o.xminB = P.blob[dB[3] + 3];
+    o.xmaxB = P.blob[dB[3] + dB[1] - 4];
     o.baos = o.bao * o.invs8sq;
-    const bool shared = P.shared_knots[c] != 0;
+    const bool shared = P.shared_tmp[zb * P.NC + c] != 0;
     const bool own = (s == 0) || (P.alias[s * P.Z + zb] == s);
     o.flags = (own ? SD_OWN : 0) | ((o.A1 != 0.0 || o.A2 != 0.0) ? SD_QBIAS : 0) | (shared ? SD_SHARED_KNOTS : 0) |
               ((s == 0 || s == P.ps_src) ? SD_SRC : 0) | (o.pshot != 0.0 ? SD_PSHOT : 0) | (s == 0 ? SD_FID : 0) |
@@ -295,20 +318,20 @@ __global__ void spectro_setup_kernel(SpectroParams P) {
     o.csr0 = jj;
     o.csr1 = j1;
     P.sdev[(size_t)zb * P.S + s] = o;
+    if (!batch) {  // class of the point in the bin's work list (-1: not visited)
+      const bool needed = (s == P.ps_src) || (P.materialize & CFP_MAT_LNP) || (o.par0 >= 0);
+      cls_sm[s] = !needed ? -1 : (!(o.flags & SD_OWN) ? 2 : ((o.flags & SD_BIASONLY) ? 1 : 0));
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0 && !(P.materialize & 16)) {  // bit 4: batch (likelihood) mode needs no work list
+  if (threadIdx.x == 0 && !batch) {
     // work list of the bin: [fiducial | full evaluations | bias-only | aliases of the fiducial that feed a
     // derivative or are materialised]; the lattice loop runs one branch-free loop per class
     int n = 0, cnt[3] = {0, 0, 0};
     P.work[zb * P.S + n++] = 0;
     for (int cls = 0; cls < 3; ++cls)
-      for (int s = 1; s < P.S; ++s) {
-        const SDev& o = P.sdev[(size_t)zb * P.S + s];
-        const bool needed = (s == P.ps_src) || (P.materialize & CFP_MAT_LNP) || (o.par0 >= 0);
-        const int c = !(o.flags & SD_OWN) ? 2 : ((o.flags & SD_BIASONLY) ? 1 : 0);
-        if (needed && c == cls) P.work[zb * P.S + n++] = s, ++cnt[cls];
-      }
+      for (int s = 1; s < P.S; ++s)
+        if (cls_sm[s] == cls) P.work[zb * P.S + n++] = s, ++cnt[cls];
     P.nwork[zb * 4 + 0] = cnt[0];
     P.nwork[zb * 4 + 1] = cnt[1];
     P.nwork[zb * 4 + 2] = cnt[2];
@@ -707,13 +730,24 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
   }
 }
 
-__global__ void spectro_reduce_kernel(const double* __restrict__ partial, int ncta, int nb, int npar,
-                                      double* __restrict__ F) {
+// F[zb] = sum over the CTAs' partial tiles in a FIXED tree: warp w adds CTAs w, w+32, ... in order, then the 32
+// warp sums are added in warp order.  grid (Z, T*64/32), 1024 threads: lane = element, warp = CTA subset, so the
+// ~150 partials of an element are fetched by 32 independent loads at a time instead of one dependent chain.
+__global__ void __launch_bounds__(1024) spectro_reduce_kernel(const double* __restrict__ partial, int ncta, int nb,
+                                                              int npar, double* __restrict__ F) {
+  __shared__ double red[32][33];
   const int zb = blockIdx.x;
   const int T = nb * (nb + 1) / 2;
-  for (int e = threadIdx.x; e < T * 64; e += blockDim.x) {
-    double s = 0.0;
-    for (int c = 0; c < ncta; ++c) s += partial[((size_t)zb * ncta + c) * (T * 64) + e];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.y * 32 + lane;  // < T*64 (a multiple of 32)
+  double s = 0.0;
+  for (int c = warp; c < ncta; c += 32) s += partial[((size_t)zb * ncta + c) * (T * 64) + e];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0) {
+    s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) s += red[w][lane];
     // decode (tile, lane, r) -> (i, j)
     const int t = e / 64, l = (e % 64) / 2, r = e % 2;
     int ib = 0, acc = 0;
@@ -1037,7 +1071,7 @@ extern "C" int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S
   SP_UP(SDev, nullptr, (size_t)Z * S, pl->sdev_d);
   SP_UP(int, nullptr, (size_t)Z * S, pl->work_d);
   SP_UP(int, nullptr, (size_t)Z * 4, pl->nwork_d);
-  SP_UP(int, nullptr, (size_t)NC, pl->shared_d);
+  SP_UP(int, nullptr, (size_t)NC * Z, pl->shared_d);
   SP_UP(double, nullptr, (size_t)NC * Z * 2 * maxncy, pl->dcoef_d);
   SP_UP(double, nullptr, (size_t)Z * npar * npar, pl->fisher_d);
   // the uploads read caller-owned host memory asynchronously: finish them before returning
@@ -1093,7 +1127,7 @@ static void spectro_fill_params(cfp_spectro_plan* pl, int materialize, SpectroPa
   P.nbar = pl->nbar_d, P.vol = pl->vol_d, P.blob = pl->bank->blob_d, P.desc = pl->bank->desc_d;
   P.n_tables = pl->bank->n_tables, P.tab_pl = pl->tab_pl, P.tab_f = pl->tab_f;
   P.blk = pl->blk_d, P.blknw = pl->blknw_d, P.sdev = pl->sdev_d, P.work = pl->work_d, P.nwork = pl->nwork_d;
-  P.shared_knots = pl->shared_d;
+  P.shared_tmp = pl->shared_d;
   P.partial = pl->partial_d;
   P.lnp = pl->lnp_d, P.derivs = pl->derivs_d, P.veff = pl->veff_d;
 }
@@ -1106,11 +1140,9 @@ static int spectro_prepare(cfp_spectro_plan* pl, const SpectroParams& P, cudaStr
   pp.tab[0] = pl->tab_pl, pp.tab[1] = pl->tab_f;
   pp.zbin = pl->zbin_d, pp.dcoef = pl->dcoef_d, pp.blk = pl->blk_d;
   pp.pnw_k = pl->pnw_k_d, pp.pnw_p = pl->pnw_p_d, pp.blknw = pl->blknw_d;
-  pp.shared_knots = pl->shared_d;
-  spectro_prepare_kernel<<<dim3(pl->NC * pl->Z, 3), 128, 0, st>>>(pp);
-  ctx->launches++;
-  CFP_CUDA(cudaGetLastError());
-  spectro_setup_kernel<<<pl->Z, 64, 0, st>>>(P);
+  const size_t cls_bytes = (P.materialize & 16) ? 0 : (size_t)pl->S * sizeof(int);
+  CFP_REQUIRE(cls_bytes <= 40 * 1024, "too many stencil points for a Fisher work list (batch mode has no limit)");
+  spectro_prepare_kernel<<<dim3(pl->NC * pl->Z, 4), 128, cls_bytes, st>>>(pp, P, pl->Z);
   ctx->launches++;
   CFP_CUDA(cudaGetLastError());
   return CFP_OK;
@@ -1275,7 +1307,7 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
     return CFP_ERR_CUDA;
   }
   CFP_CUDA(cudaEventRecord(pl->kev1, st));
-  spectro_reduce_kernel<<<pl->Z, 256, 0, st>>>(pl->partial_d, gx, pl->nb, pl->npar, pl->fisher_d);
+  spectro_reduce_kernel<<<dim3(pl->Z, T * 2), 1024, 0, st>>>(pl->partial_d, gx, pl->nb, pl->npar, pl->fisher_d);
   ctx->launches++;
   CFP_CUDA(cudaGetLastError());
   CFP_CUDA(cudaEventRecord(ctx->ev1, st));
