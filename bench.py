@@ -44,11 +44,14 @@ PHOTO_SPEC = "Euclid-Photometric-13bins-lmax5000"
 SPECTRO_SPEC = "Euclid-Spectroscopic-ISTF-Pessimistic"
 NMU, NK = 129, 8193
 WORKLOAD = f"euclid_3x2pt_13bins_lmax5000_npar23 + gcsp_4bins_npar15_3PT_lattice{NMU}x{NK}"
-# FP64 operations per lattice-cell evaluation of spectro_fisher_kernel, counted once from ncu
-# (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on, DFMA = 2) -- see profiles/ and DESIGN.md
-F_CELL = 170.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one spectro_fisher_kernel launch (ncu --set full, profiles/r1c)
-TRAFFIC_BYTES = 2.22e6
+# FP64 operations spectro_fisher_kernel EXECUTES per lattice cell and bin, frozen from the ncu source-page counters of
+# the final kernel (predicated-on thread instructions, DADD + DMUL + 2 DFMA; profiles/r1d_*): a full evaluation of
+# P_obs of one stencil point incl. its log (F_FULL), a point that differs from the fiducial only in the bias and
+# re-uses its look-ups (F_LIGHT), and the per-cell epilogue (derivative scaling, V_eff, weights: F_FIXED).
+# 15 full + 2 light + fixed = 1525 measured on the bench workload.  The Gram update adds 128 flop per 8x8 tile (DMMA).
+F_FULL, F_LIGHT, F_FIXED = 94.3, 30.0, 50.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one spectro_fisher_kernel launch (ncu --set full, profiles/r1d)
+TRAFFIC_BYTES = 2.99e6
 
 
 def ext_dict(bank):
@@ -295,16 +298,30 @@ def run_gpu(args):
     if clk is not None:
         clk["window"] = "timed region + 0.6 s of the identical step loop"
     job = fm_sp._spectro_job
-    evals = int(sum(1 + np.count_nonzero(job.alias[1:, z]) for z in range(splan.Z))) * (ce - cb)
-    gram = 2.0 * (8 * splan.npar_pad if hasattr(splan, "npar_pad") else 8 * ((splan.npar + 7) // 8)) ** 2 / 2.0
-    flops = F_CELL * evals + gram * splan.Z * (ce - cb)
+    from cosmicfishpie_b200._lib import SP_BIAS
+    n_full = n_light = 0
+    for z in range(splan.Z):
+        own = [s_ for s_ in range(1, splan.S) if job.alias[s_, z] == s_]
+        other = [q for q in range(job.scal.shape[2]) if q != SP_BIAS]
+        light = [s_ for s_ in own if np.array_equal(job.scal[s_, z, other], job.scal[0, z, other])]
+        n_light += len(light)
+        n_full += 1 + len(own) - len(light)
+    ncell = ce - cb
+    evals = (n_full + n_light) * ncell
+    nb8 = (splan.npar + 7) // 8
+    gram = 128.0 * nb8 * (nb8 + 1) / 2
+    flops = (F_FULL * n_full + F_LIGHT * n_light + (F_FIXED + gram) * splan.Z) * ncell
     peak_dfma = ctx.peak_fp64(0)
     peak_dmma = ctx.peak_fp64(1)
     achieved = flops / (k_ms * 1e-3) / 1e12
     roof = {"bound": "fp64", "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s", "frac": achieved / peak_dfma,
             "traffic": TRAFFIC_BYTES if world == 1 else None, "kernel": "spectro_fisher_kernel", "kernel_ms": k_ms,
             "peak_source": "measured live: cfp_peak_fp64 DFMA microbenchmark (MEASURED_PEAKS.json has no FP64 entry)",
-            "peak_dmma_tflops": peak_dmma, "flop_per_cell_eval": F_CELL, "cell_evals": evals}
+            "peak_dmma_tflops": peak_dmma, "flop_per_full_eval": F_FULL, "flop_per_light_eval": F_LIGHT,
+            "flop_per_cell_fixed": F_FIXED + gram, "full_evals_per_cell": n_full, "light_evals_per_cell": n_light,
+            "cell_evals": evals,
+            "what": "FP64 operations the kernel executes (ncu-frozen per-evaluation counts x evaluations) / "
+                    "CUDA-event kernel time, against the DFMA rate measured live on this GPU"}
     # HBM view: the API-preserving mode writes derivs[npar][Z][cells] + veff[Z][cells] once
     with torch.cuda.stream(stream):
         flush.zero_()

@@ -35,7 +35,7 @@ EXPORTS = [
     "cfp_photo_plan_chi2", "cfp_spectro_plan_chi2", "cfp_cells_chi2", "cfp_wedge_chi2",
     "cfp_legendre_project", "cfp_legendre_covariance", "cfp_legendre_chi2",
     "cfp_bank_upload_rows", "cfp_host_alloc", "cfp_host_free", "cfp_spectro_plan_chi2_dev", "cfp_dev_upload",
-    "cfp_dev_release",
+    "cfp_dev_release", "cfp_photo_plan_create_zmap",
 ]
 
 
@@ -98,6 +98,9 @@ def load():
     lib.cfp_photo_plan_create.argtypes = [
         _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp, C.c_double, _dp, _dp, _dp,
         _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int, C.POINTER(_vp)]
+    lib.cfp_photo_plan_create_zmap.argtypes = [
+        _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp, C.c_double, _dp, _dp, _dp,
+        _ip, _dp, _dp, C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int, C.POINTER(_vp)]
     lib.cfp_photo_plan_destroy.argtypes = [_vp]
     lib.cfp_photo_plan_set_slice.argtypes = [_vp, C.c_int, C.c_int]
     lib.cfp_photo_plan_run.argtypes = [_vp, _vp]
@@ -235,18 +238,36 @@ def default_context(device: Optional[int] = None) -> Context:
     return _default_ctx[device]
 
 
+_PINNED_POOL = {}  # n_doubles -> [address, ...]: page-locking is slow (ms per call), so released blocks are kept
+_PINNED_POOL_MAX_BYTES = 1 << 30
+_pinned_pool_bytes = 0
+
+
 class PinnedBuffer:
-    """Page-locked host array of float64 (cfp_host_alloc) -- buffers that are uploaded again and again."""
+    """Page-locked host array of float64 (cfp_host_alloc) -- buffers that are uploaded again and again.
+    close() returns the block to a process-wide pool keyed by size (table rows of one bank all have one size)."""
 
     def __init__(self, ctx: Context, n_doubles: int):
-        self.ctx, self.ptr = ctx, _vp()
-        _check(ctx.lib.cfp_host_alloc(ctx.handle, int(n_doubles) * 8, C.byref(self.ptr)), "cfp_host_alloc")
-        self.array = np.ctypeslib.as_array(C.cast(self.ptr, _dp), shape=(int(n_doubles),))
+        global _pinned_pool_bytes
+        self.ctx, self.n = ctx, int(n_doubles)
+        free = _PINNED_POOL.get(self.n)
+        if free:
+            self.ptr = _vp(free.pop())
+            _pinned_pool_bytes -= self.n * 8
+        else:
+            self.ptr = _vp()
+            _check(ctx.lib.cfp_host_alloc(ctx.handle, self.n * 8, C.byref(self.ptr)), "cfp_host_alloc")
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, _dp), shape=(self.n,))
 
     def close(self):
+        global _pinned_pool_bytes
         if self.ptr:
             self.array = None
-            self.ctx.lib.cfp_host_free(None, self.ptr)
+            if _pinned_pool_bytes + self.n * 8 <= _PINNED_POOL_MAX_BYTES:
+                _PINNED_POOL.setdefault(self.n, []).append(self.ptr.value)
+                _pinned_pool_bytes += self.n * 8
+            else:
+                self.ctx.lib.cfp_host_free(None, self.ptr)
             self.ptr = _vp()
 
     def __del__(self):  # pragma: no cover
@@ -449,7 +470,7 @@ class SpectroPlan:
 
 class PhotoPlan:
     def __init__(self, ctx: Context, bank: Bank, *, cosmo_of_s, ell, z, dz, chi, hub, wlpref, kind, ngal, bias, ia,
-                 lmin, lmax, noise, sqrtfsky, stw, stden, kmax, tab_p=TAB_PNL):
+                 lmin, lmax, noise, sqrtfsky, stw, stden, kmax, tab_p=TAB_PNL, zmap=None):
         self.ctx, self.bank = ctx, bank
         self.cosmo_of_s = i32(cosmo_of_s)
         self.ell, self.z = f64(ell), f64(z)
@@ -461,15 +482,26 @@ class PhotoPlan:
         self.S, self.NC = self.cosmo_of_s.size, self.chi.shape[0]
         self.Nl, self.Nz, self.Nb, self.npar = self.ell.size, self.z.size, self.kind.size, self.stw.shape[0]
         assert self.chi.shape == (self.NC, self.Nz) and self.hub.shape == (self.NC, self.Nz)
-        assert self.ngal.shape == (self.Nb, self.Nz) and self.bias.shape == (self.S, self.Nb, self.Nz)
+        self.zmap = None if zmap is None else i32(zmap)
+        Kb = self.Nz if self.zmap is None else self.bias.shape[2]
+        assert self.ngal.shape == (self.Nb, self.Nz) and self.bias.shape == (self.S, self.Nb, Kb)
         assert self.ia.shape == (self.S, self.Nz) and self.stw.shape == (self.npar, self.S)
         self.handle = _vp()
-        _check(ctx.lib.cfp_photo_plan_create(
-            ctx.handle, bank.handle, self.S, self.NC, self.Nl, self.Nz, self.Nb, self.npar, _p(self.cosmo_of_s, _ip),
-            _p(self.ell), _p(self.z), float(dz), _p(self.chi), _p(self.hub), _p(self.wlpref), _p(self.kind, _ip),
-            _p(self.ngal), _p(self.bias), _p(self.ia), _p(self.lmin), _p(self.lmax), _p(self.noise),
-            _p(self.sqrtfsky), _p(self.stw), _p(self.stden), float(kmax), int(tab_p), C.byref(self.handle)),
-            "cfp_photo_plan_create")
+        if self.zmap is None:
+            _check(ctx.lib.cfp_photo_plan_create(
+                ctx.handle, bank.handle, self.S, self.NC, self.Nl, self.Nz, self.Nb, self.npar,
+                _p(self.cosmo_of_s, _ip), _p(self.ell), _p(self.z), float(dz), _p(self.chi), _p(self.hub),
+                _p(self.wlpref), _p(self.kind, _ip), _p(self.ngal), _p(self.bias), _p(self.ia), _p(self.lmin),
+                _p(self.lmax), _p(self.noise), _p(self.sqrtfsky), _p(self.stw), _p(self.stden), float(kmax), int(tab_p),
+                C.byref(self.handle)), "cfp_photo_plan_create")
+        else:  # bias on Kb samples per (point, row) + z -> sample map
+            assert self.zmap.shape == (self.Nz,)
+            _check(ctx.lib.cfp_photo_plan_create_zmap(
+                ctx.handle, bank.handle, self.S, self.NC, self.Nl, self.Nz, self.Nb, self.npar,
+                _p(self.cosmo_of_s, _ip), _p(self.ell), _p(self.z), float(dz), _p(self.chi), _p(self.hub),
+                _p(self.wlpref), _p(self.kind, _ip), _p(self.ngal), _p(self.bias), int(Kb), _p(self.zmap, _ip),
+                _p(self.ia), _p(self.lmin), _p(self.lmax), _p(self.noise), _p(self.sqrtfsky), _p(self.stw),
+                _p(self.stden), float(kmax), int(tab_p), C.byref(self.handle)), "cfp_photo_plan_create_zmap")
         self.h2d_bytes = sum(a.nbytes for a in (self.cosmo_of_s, self.ell, self.z, self.chi, self.hub, self.wlpref,
                                                 self.kind, self.ngal, self.bias, self.ia, self.lmin, self.lmax,
                                                 self.noise, self.sqrtfsky, self.stw, self.stden))

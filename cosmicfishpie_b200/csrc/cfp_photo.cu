@@ -125,8 +125,9 @@ __global__ void photo_window_kernel(int S, int Nb, int Nz, int ldz, int nrow_pad
                                     const int* __restrict__ kind, const double* __restrict__ z,
                                     const double* __restrict__ chi, const double* __restrict__ hub,
                                     const double* __restrict__ wlpref, const double* __restrict__ ngal,
-                                    const double* __restrict__ bias, const double* __restrict__ ia,
-                                    const double* __restrict__ eff, double* __restrict__ U, double* __restrict__ V) {
+                                    const double* __restrict__ bias, int Kb, const int* __restrict__ zmap,
+                                    const double* __restrict__ ia, const double* __restrict__ eff,
+                                    double* __restrict__ U, double* __restrict__ V) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t tot = (size_t)S * nrow_pad * ldz;
   if (idx >= tot) return;
@@ -145,7 +146,7 @@ __global__ void photo_window_kernel(int S, int Nb, int Nz, int ldz, int nrow_pad
       u = w / sh;
       v = wia / sh;
     } else {  // clustering row, photo_obs.py:542, 715-717
-      const double w = (ng * H) * bias[((size_t)s * Nb + a) * Nz + iz];
+      const double w = (ng * H) * bias[((size_t)s * Nb + a) * Kb + (zmap ? zmap[iz] : iz)];
       u = w / sh;
       v = 0.0;
     }
@@ -578,6 +579,8 @@ struct cfp_photo_plan {
   int *cosmo_of_s_d = nullptr, *kind_d = nullptr;
   double *ell_d = nullptr, *z_d = nullptr, *chi_d = nullptr, *hub_d = nullptr, *wlpref_d = nullptr, *ngal_d = nullptr;
   double *bias_d = nullptr, *ia_d = nullptr, *lmin_d = nullptr, *lmax_d = nullptr, *noise_d = nullptr;
+  int Kb = 0;             // bias samples per (point, row): Nz, or fewer with a z -> sample map
+  int* zmap_d = nullptr;  // [Nz] or NULL (identity)
   double *sqrtfsky_d = nullptr, *stw_d = nullptr, *stden_d = nullptr, *strden_d = nullptr, *wz_d = nullptr;
   double* stp_w_d = nullptr;
   int *stp_ptr_d = nullptr, *stp_s_d = nullptr;
@@ -606,6 +609,15 @@ static void photo_free(cfp_photo_plan* p) {
     pl->owned.push_back((void*)(dst));                         \
   } while (0)
 
+static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb, int npar,
+                                  const int32_t* cosmo_of_s_h, const double* ell_h, const double* z_h, double dz,
+                                  const double* chi_h, const double* hub_h, const double* wlpref_h,
+                                  const int32_t* kind_h, const double* ngal_h, const double* bias_h,
+                                  const double* ia_h, const double* lmin_h, const double* lmax_h,
+                                  const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
+                                  const double* stden_h, double kmax, int tab_p, int Kb, const int32_t* zmap_h,
+                                  cfp_photo_plan** out);
+
 extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb,
                                      int npar, const int32_t* cosmo_of_s_h, const double* ell_h, const double* z_h,
                                      double dz, const double* chi_h, const double* hub_h, const double* wlpref_h,
@@ -613,6 +625,34 @@ extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, 
                                      const double* ia_h, const double* lmin_h, const double* lmax_h,
                                      const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
                                      const double* stden_h, double kmax, int tab_p, cfp_photo_plan** out) {
+  return photo_plan_create_impl(ctx, bank, S, NC, Nl, Nz, Nb, npar, cosmo_of_s_h, ell_h, z_h, dz, chi_h, hub_h, wlpref_h,
+                                kind_h, ngal_h, bias_h, ia_h, lmin_h, lmax_h, noise_h, sqrtfsky_h, stw_h, stden_h, kmax,
+                                tab_p, Nz, nullptr, out);
+}
+
+extern "C" int cfp_photo_plan_create_zmap(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb,
+                                          int npar, const int32_t* cosmo_of_s_h, const double* ell_h,
+                                          const double* z_h, double dz, const double* chi_h, const double* hub_h,
+                                          const double* wlpref_h, const int32_t* kind_h, const double* ngal_h,
+                                          const double* bias_h, int Kb, const int32_t* zmap_h, const double* ia_h,
+                                          const double* lmin_h, const double* lmax_h, const double* noise_h,
+                                          const double* sqrtfsky_h, const double* stw_h, const double* stden_h,
+                                          double kmax, int tab_p, cfp_photo_plan** out) {
+  CFP_REQUIRE(Kb >= 1 && zmap_h != nullptr, "Kb >= 1 and a z map are required");
+  for (int i = 0; i < Nz; ++i) CFP_REQUIRE(zmap_h[i] >= 0 && zmap_h[i] < Kb, "z map entry out of range");
+  return photo_plan_create_impl(ctx, bank, S, NC, Nl, Nz, Nb, npar, cosmo_of_s_h, ell_h, z_h, dz, chi_h, hub_h, wlpref_h,
+                                kind_h, ngal_h, bias_h, ia_h, lmin_h, lmax_h, noise_h, sqrtfsky_h, stw_h, stden_h, kmax,
+                                tab_p, Kb, zmap_h, out);
+}
+
+static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb, int npar,
+                                  const int32_t* cosmo_of_s_h, const double* ell_h, const double* z_h, double dz,
+                                  const double* chi_h, const double* hub_h, const double* wlpref_h,
+                                  const int32_t* kind_h, const double* ngal_h, const double* bias_h,
+                                  const double* ia_h, const double* lmin_h, const double* lmax_h,
+                                  const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
+                                  const double* stden_h, double kmax, int tab_p, int Kb, const int32_t* zmap_h,
+                                  cfp_photo_plan** out) {
   CFP_REQUIRE(ctx && bank && out, "NULL ctx/bank/out");
   CFP_REQUIRE(cosmo_of_s_h && ell_h && z_h && chi_h && hub_h && wlpref_h && kind_h && ngal_h && bias_h && ia_h &&
                   lmin_h && lmax_h && noise_h && sqrtfsky_h && stw_h && stden_h,
@@ -658,7 +698,9 @@ extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, 
   PH_UP(double, hub_h, (size_t)NC * Nz, pl->hub_d);
   PH_UP(double, wlpref_h, (size_t)NC, pl->wlpref_d);
   PH_UP(double, ngal_h, (size_t)Nb * Nz, pl->ngal_d);
-  PH_UP(double, bias_h, (size_t)S * Nb * Nz, pl->bias_d);
+  pl->Kb = Kb;
+  PH_UP(double, bias_h, (size_t)S * Nb * Kb, pl->bias_d);
+  if (zmap_h) PH_UP(int, zmap_h, (size_t)Nz, pl->zmap_d);
   PH_UP(double, ia_h, (size_t)S * Nz, pl->ia_d);
   PH_UP(double, lmin_h, (size_t)Nb, pl->lmin_d);
   PH_UP(double, lmax_h, (size_t)Nb, pl->lmax_d);
@@ -782,7 +824,7 @@ static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
     const size_t tot = (size_t)pl->S * pl->nb * 8 * pl->ldz;
     photo_window_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
         pl->S, pl->Nb, pl->Nz, pl->ldz, pl->nb * 8, pl->cosmo_of_s_d, pl->kind_d, pl->z_d, pl->chi_d, pl->hub_d,
-        pl->wlpref_d, pl->ngal_d, pl->bias_d, pl->ia_d, pl->eff_d, pl->U_d, pl->V_d);
+        pl->wlpref_d, pl->ngal_d, pl->bias_d, pl->Kb, pl->zmap_d, pl->ia_d, pl->eff_d, pl->U_d, pl->V_d);
     ctx->launches++;
     CFP_CUDA(cudaGetLastError());
   }

@@ -302,7 +302,8 @@ class PhotoJob:
                 cp.update({k: float(v) for k, v in zip(ckeys, row)})
                 idx[u] = cs.add(cp)
             self.cosmo_of_s = idx[np.asarray(inv).ravel()]
-        self.bias = np.ones((B, Nb, Nz))
+        self.zmap = None  # bias sampled on the z grid, or on fewer samples + a z -> sample map (binned models)
+        self.bias = None
         self.ia = np.zeros((B, Nz))
         if "WL" in g.observables:
             ia = cfg.IAparams
@@ -324,20 +325,29 @@ class PhotoJob:
             model = bp["bias_model"]
             gc_rows = [a for a, (o, _) in enumerate(g.rows) if o == "GCph"]
             if model == "binned":
+                # piecewise constant in z: one sample per tomographic bin and a z -> bin map, not B*Nb*Nz doubles
                 edges = np.asarray(configuration.specs["z_bins_GCph"])
                 brang = list(configuration.specs["binrange_GCph"])
                 vals = np.stack([column(f"b{k}", bp[f"b{k}"]) for k in brang], axis=1)            # [B, nbins]
-                zi = np.clip(np.searchsorted(edges, g.z, side="right") - 1, 0, brang[-1] - 1)
-                self.bias[:, gc_rows, :] = vals[:, zi][:, None, :]
+                self.zmap = np.clip(np.searchsorted(edges, g.z, side="right") - 1, 0, brang[-1] - 1).astype(np.int32)
+                self.bias = np.empty((B, Nb, vals.shape[1]))
+                self.bias[:] = 1.0
+                self.bias[:, gc_rows, :] = vals[:, None, :]
             elif model == "binned_constant":
+                self.zmap = np.zeros(Nz, dtype=np.int32)
+                self.bias = np.ones((B, Nb, 1))
                 for a in gc_rows:
                     i = g.rows[a][1]
-                    self.bias[:, a, :] = column(f"b{i}", bp[f"b{i}"])[:, None]
+                    self.bias[:, a, 0] = column(f"b{i}", bp[f"b{i}"])
             else:
+                self.bias = np.ones((B, Nb, Nz))
                 pts = [dict(bp, **{k: float(matrix[s, col[k]]) for k in bp if k in col}) for s in range(B)]
                 for s, b in enumerate(pts):
                     for a in gc_rows:
                         self.bias[s, a] = nuis.gcph_bias(b, g.rows[a][1])(g.z)
+        if self.bias is None:
+            self.zmap = np.zeros(Nz, dtype=np.int32)
+            self.bias = np.ones((B, Nb, 1))
         self.chi = np.array([c.on_grid("comoving", g.z) for c in cs.cosmos])
         self.hub = np.array([c.on_grid("Hubble", g.z) for c in cs.cosmos])
         self.wlpref = np.array([(3.0 / 2.0) * c.scalar("Hubble", 0.0) ** 2.0 * c.scalar("Omegam_of_z", 0.0)
@@ -357,7 +367,7 @@ class PhotoJob:
                 cs.ctx or _lib.default_context(), cs.bank(), cosmo_of_s=self.cosmo_of_s, ell=g.ell, z=g.z, dz=g.dz,
                 chi=self.chi, hub=self.hub, wlpref=self.wlpref, kind=g.kind, ngal=self.ngal, bias=self.bias,
                 ia=self.ia, lmin=g.lmin, lmax=g.lmax, noise=g.noise, sqrtfsky=g.sqrtfsky, stw=self.stw,
-                stden=self.stden, kmax=g.kmax, tab_p=g.tab_p)
+                stden=self.stden, kmax=g.kmax, tab_p=g.tab_p, zmap=getattr(self, "zmap", None))
         return self._plan
 
     def run(self):

@@ -223,6 +223,17 @@ int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int
                           const double* lmax_h, const double* noise_h, const double* sqrtfsky_h,
                           const double* stw_h, const double* stden_h, double kmax, int tab_p,
                           cfp_photo_plan** out);
+
+/* The same with the galaxy bias given on Kb <= Nz samples per (point, row) and a map zmap_h[Nz] -> sample: the
+ * reference's `binned` model (nuisance.py:98-230) is constant inside each tomographic bin, so a batch of B
+ * likelihood points uploads B*Nb*n_bins doubles instead of B*Nb*Nz.  bias_h[S][Nb][Kb].                         */
+int cfp_photo_plan_create_zmap(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb, int npar,
+                               const int32_t* cosmo_of_s_h, const double* ell_h, const double* z_h, double dz,
+                               const double* chi_h, const double* hub_h, const double* wlpref_h,
+                               const int32_t* kind_h, const double* ngal_h, const double* bias_h, int Kb,
+                               const int32_t* zmap_h, const double* ia_h, const double* lmin_h, const double* lmax_h,
+                               const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
+                               const double* stden_h, double kmax, int tab_p, cfp_photo_plan** out);
 int cfp_photo_plan_destroy(cfp_photo_plan* plan);
 /* multi-GPU partition: this rank owns multipoles [l_begin, l_end) */
 int cfp_photo_plan_set_slice(cfp_photo_plan* plan, int l_begin, int l_end);
