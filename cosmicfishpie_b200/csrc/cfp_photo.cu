@@ -479,15 +479,66 @@ __global__ void __launch_bounds__(256) photo_reduce_kernel(const double* __restr
 
 // ---------------------------------------------------------------------------- likelihood
 constexpr int CHI_WARPS = 4;
+// row stride of the per-warp n x n tile: odd (conflict-free column walks) and >= n + 2: the lower triangle holds the
+// Cholesky factor of A, the strict upper triangle shifted by one column holds L_B / M transposed, column n+1 the
+// reciprocal diagonal
+__host__ __device__ constexpr int chi_ld(int nmax) { return (nmax + 2) | 1; }
+// doubles reserved per warp for the (i, j) pair list of the Cholesky trailing updates (2 bytes per pair)
+__host__ __device__ constexpr int chi_pairs_doubles(int nmax) { return (nmax * (nmax - 1) / 2 * 2 + 7) / 8 + 1; }
 
-// One warp per (point, multipole, block): q = tr(A^-1 B) + ln det A - lndetB - n, A = C_l(s) + N.
-// A is factorised (Cholesky) in shared memory, lane i then solves A y = b_i and keeps y_i.
+// One warp per (point, multipole, block): q = tr(A^-1 B) + ln det A - ln det B - n, A = C_l(s) + N, B = data
+// (photo_like.py:28-97).  With the Cholesky factors A = L L^T and B = L_B L_B^T (L_B is factorised ONCE per
+// (multipole, block) by the data pass and kept in global memory)
+//     tr(A^-1 B) = || L^-1 L_B ||_F^2 ,
+// i.e. after the factorisation of A one forward substitution per column of L_B, which starts at the column's
+// diagonal -- no backward substitution.  The trailing update of the factorisation is spread over all 32 lanes
+// (flat index over the trailing triangle), units whose quadrature weight is zero are skipped.
+__device__ __forceinline__ double chi_rsqrt(double x) {  // x > 0, normal: 1/sqrt(x) to ~1 ulp without the slow path
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  return fma(y, e, y);
+}
+
+// pairs[e] = (i << 8) | j of the strictly-lower-plus-diagonal elements with j >= 1, ordered by DEcreasing j: the
+// trailing triangle of elimination step k (rows/cols k+1 .. n-1) is the first (n-k-1)(n-k)/2 entries.
+__device__ __forceinline__ void chol_pairs_fill(unsigned short* __restrict__ pairs, int n, int lane) {
+  for (int j = n - 1; j >= 1; --j) {
+    const int m = n - 1 - j;               // columns already listed: n-1 .. j+1
+    const int base = m * (m + 1) / 2;      // their element count: sum_{c=j+1}^{n-1} (n - c)
+    for (int i = j + lane; i < n; i += 32) pairs[base + (i - j)] = (unsigned short)((i << 8) | j);
+  }
+}
+
+__device__ __forceinline__ void chol_warp(double* __restrict__ L, const unsigned short* __restrict__ pairs, int n,
+                                          int LD, int lane) {
+  for (int k = 0; k < n; ++k) {
+    const double a = L[k * LD + k];
+    const double rd = chi_rsqrt(a);
+    __syncwarp();
+    if (lane > k && lane < n) L[lane * LD + k] *= rd;
+    if (lane == k) L[k * LD + k] = a * rd;
+    __syncwarp();
+    const int m = n - k - 1;  // trailing triangle: rows/cols k+1 .. n-1, j <= i
+    const int cnt = m * (m + 1) / 2;
+    for (int e = lane; e < cnt; e += 32) {
+      const int ij = pairs[e];
+      const int i = ij >> 8, j = ij & 255;
+      L[i * LD + j] -= L[i * LD + k] * L[j * LD + k];
+    }
+    __syncwarp();  // the next pivot L[k+1][k+1] was updated by some other lane
+  }
+}
+
 __global__ void __launch_bounds__(CHI_WARPS * 32) photo_chi2_kernel(
     int S, int Nl, int Nb, int nblk, const int* __restrict__ blk_off, const int* __restrict__ blk_n,
-    const double* __restrict__ cls, const double* __restrict__ noise, const double* __restrict__ data,
-    const double* __restrict__ lndetB, int data_mode, int nmax, double* __restrict__ q) {
+    const double* __restrict__ cls, const double* __restrict__ noise, const double* __restrict__ wts,
+    double* __restrict__ LB, double* __restrict__ lndetB, int data_mode, int nmax, double* __restrict__ q) {
   extern __shared__ double chism[];
-  const int CHI_LD = nmax | 1;
+  const int CHI_LD = chi_ld(nmax);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t unit = (size_t)blockIdx.x * CHI_WARPS + warp;
   const size_t total = (size_t)S * Nl * nblk;
@@ -495,56 +546,54 @@ __global__ void __launch_bounds__(CHI_WARPS * 32) photo_chi2_kernel(
   const int b = (int)(unit % nblk);
   const int il = (int)((unit / nblk) % Nl);
   const int s = (int)(unit / ((size_t)nblk * Nl));
+  if (wts && wts[(size_t)b * Nl + il] == 0.0) {  // outside the block's multipole range
+    if (lane == 0) q[unit] = 0.0;
+    return;
+  }
   const int off = blk_off[b], n = blk_n[b];
-  double* L = chism + (size_t)warp * 2 * nmax * CHI_LD;
-  double* W = L + (size_t)nmax * CHI_LD;
+  double* L = chism + (size_t)warp * (nmax * CHI_LD + chi_pairs_doubles(nmax));
+  unsigned short* pairs = reinterpret_cast<unsigned short*>(L + (size_t)nmax * CHI_LD);
+  chol_pairs_fill(pairs, n, lane);
   const double* A = cls + ((size_t)s * Nl + il) * Nb * Nb;
-  const double* B = data + (size_t)il * Nb * Nb;
-  for (int e = lane; e < n * n; e += 32) {
-    const int i = e / n, j = e % n;
-    L[i * CHI_LD + j] = A[(size_t)(off + i) * Nb + off + j] + ((i == j) ? noise[off + i] : 0.0);
-    W[i * CHI_LD + j] = B[(size_t)(off + i) * Nb + off + j];
-  }
+  double* LBu = LB + ((size_t)il * nblk + b) * nmax * nmax;
+  // lower triangle <- A (+ noise); element (r, c) of L_B, r >= c, goes to L[c][r + 1] (the free upper triangle)
+#pragma unroll 4
+  for (int i = 0; i < n; ++i)
+    for (int j = lane; j <= i; j += 32) {
+      L[i * CHI_LD + j] = A[(size_t)(off + i) * Nb + off + j] + ((i == j) ? noise[off + i] : 0.0);
+      if (!data_mode) L[j * CHI_LD + i + 1] = LBu[i * nmax + j];
+    }
   __syncwarp();
-  double lndet = 0.0;
-  for (int k = 0; k < n; ++k) {
-    const double d = sqrt(L[k * CHI_LD + k]);
-    lndet += log(d);
-    __syncwarp();
-    if (lane > k && lane < n) L[lane * CHI_LD + k] /= d;
-    if (lane == k) L[k * CHI_LD + k] = d;
-    __syncwarp();
-    if (lane > k && lane < n) {
-      const double lik = L[lane * CHI_LD + k];
-      for (int j = k + 1; j <= lane; ++j) L[lane * CHI_LD + j] -= lik * L[j * CHI_LD + k];
-    }
-    __syncwarp();
-  }
+  chol_warp(L, pairs, n, CHI_LD, lane);
+  double lndet = (lane < n) ? log(L[lane * CHI_LD + lane]) : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lndet += __shfl_xor_sync(0xffffffffu, lndet, o);
   lndet *= 2.0;
-  double yi = 0.0;
-  if (lane < n) {
-    const int i = lane;
-    for (int r = 0; r < n; ++r) {  // forward: L m = b_i
-      double x = W[r * CHI_LD + i];
-      for (int k = 0; k < r; ++k) x -= L[r * CHI_LD + k] * W[k * CHI_LD + i];
-      W[r * CHI_LD + i] = x / L[r * CHI_LD + r];
-    }
-    for (int r = n - 1; r >= i; --r) {  // backward: L^T y = m, down to component i
-      double x = W[r * CHI_LD + i];
-      for (int k = r + 1; k < n; ++k) x -= L[k * CHI_LD + r] * W[k * CHI_LD + i];
-      x /= L[r * CHI_LD + r];
-      W[r * CHI_LD + i] = x;
-      if (r == i) yi = x;
+  if (data_mode) {  // setup pass on the data itself: keep ln det B and the factor L_B (upper triangle zero)
+    for (int i = 0; i < n; ++i)
+      for (int j = lane; j < n; j += 32) LBu[i * nmax + j] = (j <= i) ? L[i * CHI_LD + j] : 0.0;
+    if (lane == 0) q[unit] = lndet;
+    return;
+  }
+  // 1 / diagonal once, then lane i: M[:, i] = L^-1 L_B[:, i] from row i down (kept in row i of the upper triangle),
+  // accumulating |M|^2
+  if (lane < n) L[lane * CHI_LD + n + 1] = 1.0 / L[lane * CHI_LD + lane];
+  __syncwarp();
+  double tr = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    double* Mi = L + i * CHI_LD + 1;  // Mi[r] = M[r][i], r >= i
+    for (int r = i; r < n; ++r) {
+      double x = Mi[r];
+      const double* Lr = L + r * CHI_LD;
+      for (int k = i; k < r; ++k) x -= Lr[k] * Mi[k];
+      x *= Lr[n + 1];
+      Mi[r] = x;
+      tr += x * x;
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) yi += __shfl_xor_sync(0xffffffffu, yi, o);
-  if (lane == 0) {
-    if (data_mode)  // setup pass on the data itself: store ln det B
-      q[unit] = lndet;
-    else
-      q[unit] = yi + lndet - lndetB[(size_t)il * nblk + b] - (double)n;
-  }
+  for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+  if (lane == 0) q[unit] = tr + lndet - lndetB[(size_t)il * nblk + b] - (double)n;
 }
 
 __global__ void photo_chi2_reduce_kernel(int S, int Nl, int nblk, const double* __restrict__ q,
@@ -948,26 +997,27 @@ extern "C" int cfp_photo_plan_chi2(cfp_photo_plan* pl, const double* data_h, int
   }
   int nmax = 1;
   for (int b = 0; b < nblk; ++b) nmax = std::max(nmax, (int)blk_n_h[b]);
-  const size_t chi_smem = (size_t)CHI_WARPS * 2 * nmax * (nmax | 1) * sizeof(double);
+  const size_t chi_smem = (size_t)CHI_WARPS * (nmax * chi_ld(nmax) + chi_pairs_doubles(nmax)) * sizeof(double);
   if (cudaFuncSetAttribute(photo_chi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chi_smem) != cudaSuccess) {
     cfp_set_error("cfp_photo_plan_chi2: cannot reserve %zu B of shared memory", chi_smem);
     cleanup();
     return CFP_ERR_CUDA;
   }
   // ln det of the data blocks: the same kernel on a zero-noise "theory" = data
-  double* zero_d = nullptr;
+  double *zero_d = nullptr, *lb_d = nullptr;
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nb, &zero_d));
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nl * nblk * nmax * nmax, &lb_d));
   if (st != ctx->stream) cudaStreamSynchronize(ctx->stream);
   {
     const size_t units = (size_t)Nl * nblk;
     photo_chi2_kernel<<<(unsigned)((units + CHI_WARPS - 1) / CHI_WARPS), CHI_WARPS * 32, chi_smem, st>>>(
-        1, Nl, Nb, nblk, off_d, n_d, data_d, zero_d, data_d, nullptr, 1, nmax, lndet_d);
+        1, Nl, Nb, nblk, off_d, n_d, data_d, zero_d, w_d, lb_d, nullptr, 1, nmax, lndet_d);
     ctx->launches++;
   }
   {
     const size_t units = (size_t)S * Nl * nblk;
     photo_chi2_kernel<<<(unsigned)((units + CHI_WARPS - 1) / CHI_WARPS), CHI_WARPS * 32, chi_smem, st>>>(
-        S, Nl, Nb, nblk, off_d, n_d, pl->cls_d, pl->noise_d, data_d, lndet_d, 0, nmax, q_d);
+        S, Nl, Nb, nblk, off_d, n_d, pl->cls_d, pl->noise_d, w_d, lb_d, lndet_d, 0, nmax, q_d);
     ctx->launches++;
     photo_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Nl, nblk, q_d, w_d, chi2_d);
     ctx->launches++;
@@ -979,6 +1029,7 @@ extern "C" int cfp_photo_plan_chi2(cfp_photo_plan* pl, const double* data_h, int
   float ms = 0.f;
   if (e == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
   cfp_dev_free(ctx, zero_d);
+  cfp_dev_free(ctx, lb_d);
   cleanup();
 #undef CHI_TRY
   if (e != cudaSuccess) {
@@ -1034,9 +1085,10 @@ extern "C" int cfp_cells_chi2(cfp_ctx* ctx, int S, int Nl, int Nb, const double*
   cudaStream_t st = ctx->stream;
   int *off_d = nullptr, *n_d = nullptr;
   double *w_d = nullptr, *th_d = nullptr, *data_d = nullptr, *zero_d = nullptr, *lndet_d = nullptr, *q_d = nullptr, *chi2_d = nullptr;
+  double* lb_d = nullptr;
   auto cleanup = [&]() {
     for (void* q : {(void*)off_d, (void*)n_d, (void*)w_d, (void*)th_d, (void*)data_d, (void*)zero_d, (void*)lndet_d,
-                    (void*)q_d, (void*)chi2_d})
+                    (void*)q_d, (void*)chi2_d, (void*)lb_d})
       cfp_dev_free(ctx, q);
   };
   int rc;
@@ -1057,16 +1109,17 @@ extern "C" int cfp_cells_chi2(cfp_ctx* ctx, int S, int Nl, int Nb, const double*
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nl * nblk, &lndet_d));
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S * Nl * nblk, &q_d));
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d));
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nl * nblk * nmax * nmax, &lb_d));
 #undef CHI_TRY
-  const size_t chi_smem = (size_t)CHI_WARPS * 2 * nmax * (nmax | 1) * sizeof(double);
+  const size_t chi_smem = (size_t)CHI_WARPS * (nmax * chi_ld(nmax) + chi_pairs_doubles(nmax)) * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(photo_chi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chi_smem);
   if (e == cudaSuccess) {
     size_t units = (size_t)Nl * nblk;
     photo_chi2_kernel<<<(unsigned)((units + CHI_WARPS - 1) / CHI_WARPS), CHI_WARPS * 32, chi_smem, st>>>(
-        1, Nl, Nb, nblk, off_d, n_d, data_d, zero_d, data_d, nullptr, 1, nmax, lndet_d);
+        1, Nl, Nb, nblk, off_d, n_d, data_d, zero_d, w_d, lb_d, nullptr, 1, nmax, lndet_d);
     units = (size_t)S * Nl * nblk;
     photo_chi2_kernel<<<(unsigned)((units + CHI_WARPS - 1) / CHI_WARPS), CHI_WARPS * 32, chi_smem, st>>>(
-        S, Nl, Nb, nblk, off_d, n_d, th_d, zero_d, data_d, lndet_d, 0, nmax, q_d);
+        S, Nl, Nb, nblk, off_d, n_d, th_d, zero_d, w_d, lb_d, lndet_d, 0, nmax, q_d);
     photo_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Nl, nblk, q_d, w_d, chi2_d);
     ctx->launches += 3;
     e = cudaGetLastError();
