@@ -1,5 +1,6 @@
-"""Minimal workload for `ncu`: one GCsp Fisher (spectro_fisher_kernel), one 3x2pt Fisher (photo kernels) and one
-spectroscopic wedge-likelihood batch (spectro_chi2_kernel) on the bench configuration.
+"""Minimal workload for `ncu`: GCsp Fisher (spectro_fisher_kernel), 3x2pt Fisher (photo kernels), a spectroscopic
+wedge-likelihood batch (spectro_chi2_kernel) and a photometric likelihood batch (photo_chi2_kernel), each twice,
+on the bench configuration.
 Usage: python tools/ncu_driver.py [n_like_points]"""
 import os
 import sys
@@ -12,7 +13,7 @@ sys.path.insert(0, REPO)
 
 import bench  # noqa: E402
 from cosmicfishpie_b200 import toy_tables as tt  # noqa: E402
-from cosmicfishpie_b200.likelihood import SpectroLikelihood  # noqa: E402
+from cosmicfishpie_b200.likelihood import PhotometricLikelihood, SpectroLikelihood  # noqa: E402
 
 
 def main():
@@ -30,7 +31,13 @@ def main():
     mat = fid * (1.0 + 0.02 * np.random.default_rng(0).standard_normal((n_like, len(keys))))
     for _ in range(2):
         ll = like.loglike_batch(mat, keys=keys)
-    print("ok", float(np.sum(ll)))
+    plike = PhotometricLikelihood(cosmo_data=a)
+    pkeys = [k for k in a.freeparams if k not in bench.P7]
+    pfid = np.array([a.allparams[k] for k in pkeys])
+    pmat = pfid * (1.0 + 0.02 * np.random.default_rng(1).standard_normal((4 * n_like, len(pkeys))))
+    for _ in range(2):
+        pl = plike.loglike_batch(pmat, keys=pkeys)
+    print("ok", float(np.sum(ll)), float(np.sum(pl)))
 
 
 if __name__ == "__main__":
