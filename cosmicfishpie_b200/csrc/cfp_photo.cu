@@ -176,17 +176,14 @@ __global__ void __launch_bounds__(CLS_THREADS) photo_cls_kernel(ClsParams P) {
   constexpr int NT = NB * (NB + 1) / 2;
   extern __shared__ double smem[];
   const int rows = NB * 8;
-  double* sU = smem;
-  double* sV = smem + (size_t)rows * P.ldz;
+  double* sK = smem;  // [rows][ldz]: W + W^IA of the point (both multiply the same sqrt(P)/chi, photo_obs.py:905-919);
+                      // one staged array instead of two doubles the resident CTAs per SM
   const int s = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   {
     const double* gU = P.U + (size_t)s * rows * P.ldz;
     const double* gV = P.V + (size_t)s * rows * P.ldz;
-    for (int i = tid; i < rows * P.ldz; i += CLS_THREADS) {
-      sU[i] = gU[i];
-      sV[i] = gV[i];
-    }
+    for (int i = tid; i < rows * P.ldz; i += CLS_THREADS) sK[i] = gU[i] + gV[i];
   }
   __syncthreads();
   const int c = P.cosmo_of_s[s];
@@ -206,7 +203,7 @@ __global__ void __launch_bounds__(CLS_THREADS) photo_cls_kernel(ClsParams P) {
 #pragma unroll
       for (int ib = 0; ib < NB; ++ib) {
         const int off = (ib * 8 + g) * P.ldz + iz;
-        a[ib] = t * sU[off] + t * sV[off];  // photo_obs.py:905-919 (sqrtP*W + sqrtP_IA*W_IA)
+        a[ib] = t * sK[off];
       }
       int tt = 0;
 #pragma unroll
@@ -723,9 +720,9 @@ static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int
   int ldz = pl->nz4;
   while (!((ldz % 16) == 4 || (ldz % 16) == 12)) ldz += 4;  // conflict-free DMMA fragment loads
   pl->ldz = ldz;
-  if ((size_t)2 * pl->nb * 8 * ldz * sizeof(double) > 220 * 1024) {
+  if ((size_t)pl->nb * 8 * ldz * sizeof(double) > 220 * 1024) {
     cfp_set_error("cfp_photo_plan_create: Nb_pad x Nz = %d x %d does not fit the shared-memory tile of the C_ell kernel "
-                  "(limit 2*Nb_pad*Nz*8 B <= 220 KB)", pl->nb * 8, ldz);
+                  "(limit Nb_pad*Nz*8 B <= 220 KB)", pl->nb * 8, ldz);
     photo_free(pl);
     return CFP_ERR_INVALID;
   }
@@ -886,14 +883,17 @@ static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
     P.l_begin = all_ell ? 0 : pl->l_begin;
     P.l_end = all_ell ? pl->Nl : std::min(pl->l_end + 1, pl->Nl);
     const int nl = P.l_end - P.l_begin;
-    int lch = std::max(CLS_WARPS, (nl * pl->S + 2 * ctx->sm_count - 1) / (2 * ctx->sm_count));
+    const size_t smem = (size_t)pl->nb * 8 * pl->ldz * sizeof(double);
+    // multipoles per CTA: one wave of as many CTAs as fit beside their staged windows (at most 8 per SM)
+    const int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, (size_t)220 * 1024 / std::max<size_t>(smem, 1)));
+    const int slots = per_sm * ctx->sm_count;
+    int lch = std::max(CLS_WARPS, (nl * pl->S + slots - 1) / slots);
     lch = (lch + CLS_WARPS - 1) / CLS_WARPS * CLS_WARPS;
     P.lch = lch;
     P.cosmo_of_s = pl->cosmo_of_s_d, P.U = pl->U_d, P.V = pl->V_d, P.T = pl->T_d, P.wz = pl->wz_d;
     P.ell = pl->ell_d, P.lmin = pl->lmin_d, P.lmax = pl->lmax_d, P.cls = pl->cls_d;
     CFP_CUDA(cudaEventRecord(pl->kev[2], st));
     const dim3 grid((nl + lch - 1) / lch, pl->S);
-    const size_t smem = (size_t)2 * pl->nb * 8 * pl->ldz * sizeof(double);
     cudaError_t e = cudaSuccess;
     if (nl > 0) {
       switch (pl->nb) {
