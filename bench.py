@@ -153,7 +153,7 @@ def run_reference(args):
             "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": value, "unit": "Fisher/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Fisher/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    return line
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -341,10 +341,10 @@ def run_gpu(args):
     pplan.set_slice(0, nbins)
 
     if args.profile:
-        if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms_per_step, "kernel_ms": k_ms, "photo_kernel_ms": photo_ms,
-                              "roofline": roof}))
-        return
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return ({"profile_run": True, "ms_per_step": ms_per_step, "kernel_ms": k_ms, "photo_kernel_ms": photo_ms,
+                 "roofline": roof} if rank == 0 else None)
 
     # ---- end to end through the public API, from host tables -----------------------------------------
     from cosmicfishpie_b200 import cosmology as ccos
@@ -429,6 +429,7 @@ def run_gpu(args):
         cabi_step()
     t_cabi = (time.perf_counter() - t0) / n_e2e
 
+    line = None
     if rank == 0:
         cpu = None
         if world == 1 or True:
@@ -463,9 +464,9 @@ def run_gpu(args):
             "roofline": roof, "roofline_hbm": roof_hbm, "photo_kernel_ms": photo_ms, "cpu_baseline": cpu,
             "fisher_trace": float(np.trace(Ftot.fisher_matrix)),
         }
-        print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
+    return line
 
 
 def main():
@@ -477,10 +478,18 @@ def main():
     ap.add_argument("--profile", action="store_true",
                     help="resident-plan loop only (no e2e / CPU baseline): the command line used under ncu")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_gpu(args)
+    # The contract is ONE JSON line on stdout.  Libraries write banners to fd 1 (NCCL prints its version there):
+    # point fd 1 at stderr for the duration of the run and emit the result on the saved descriptor.
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference(args) if args.impl == "reference" else run_gpu(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_out, 1)
+    if line is not None:
+        os.write(1, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
