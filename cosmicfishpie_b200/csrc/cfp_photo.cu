@@ -7,9 +7,12 @@
 //   photo_window_kernel   per stencil point: W_a(z)/sqrt(H) and W^IA_a(z)/sqrt(H)   (photo_obs.py:514-722)
 //   photo_cls_kernel      C_l[a][b] = sum_z w_z K_a K_b, K_a = T W_a + T W^IA_a, as a batch of
 //                         (Nb x Nz)(Nz x Nb) SYRKs on mma.sync m8n8k4 f64 (DMMA)    (photo_obs.py:878-928)
-//   photo_fisher_kernel   per multipole bin: covariance, Cholesky, Y_p = L^-1 (Phi dC_p) L^-T and
-//                         F_pq += w_l sum_ij Y_p[ij] Y_q[ji]   (photo_cov.py:198-245, cosmicfish.py:643-744)
-//   photo_reduce_kernel   fixed-order sum over multipole bins.
+//   photo_fisher_kernel   per multipole bin: M_p = Phi dC_p streamed from the stencil's C_ell, Gauss-Jordan inverse
+//                         of the covariance, Z_p = A^-1 M_p and F_pq += w_l Tr(Z_p Z_q) on DMMA
+//                         (photo_cov.py:198-245, cosmicfish.py:643-744)
+//   photo_reduce_kernel   fixed-tree sum over multipole bins
+//   photo_chi2_kernel     likelihood: one warp per (point, multipole, block), Cholesky + one forward substitution,
+//                         tr(A^-1 B) = |L^-1 L_B|^2                                      (photo_like.py:28-97,180-256)
 #include <algorithm>
 #include <cmath>
 

@@ -1,20 +1,25 @@
 // Spectroscopic galaxy clustering: P_obs(k,mu,z) lattice, derivatives and Fisher reduction.
 //
 // Kernels (all FP64):
-//   spectro_prepare_kernel   per (cosmology, z-bin, table): contracts the bicubic B-spline of
-//                            P_lin(z,k) / f(z,k) with the z-basis at the bin redshift and converts
-//                            the resulting 1-D cubic B-spline to piecewise-polynomial (Taylor)
-//                            form per knot interval; converts the no-wiggle samples to
-//                            (value, slope) pairs.  Output lives in HBM, is a few MB and is read
-//                            by the main kernel through L1/L2.
-//   spectro_fisher_kernel    one CTA = one z-bin x 256-cell tiles of the (mu,k) lattice.  Each
-//                            thread evaluates ln P_obs of its cell at every stencil point
-//                            (AP remap, Kaiser, FoG, dewiggling, spec-z error), accumulates the
-//                            derivative stencils into a shared-memory tile d[par][cell], and each
-//                            warp contracts its 32 cells into the Gram matrix
-//                            F_ij += w d_i d_j with FP64 tensor-core MMAs (mma.sync m8n8k4 = DMMA;
-//                            tcgen05 has no f64 kind).  Per-CTA partial sums go to HBM.
-//   spectro_reduce_kernel    fixed-order sum of the CTA partials -> F[Z][npar][npar] (deterministic).
+//   spectro_prepare_kernel   blockIdx.y < 3, per (cosmology, z-bin, table): contracts the bicubic B-spline of
+//                            P_lin(z,k) / f(z,k) with the z-basis at the bin redshift and converts the resulting
+//                            1-D cubic B-spline to piecewise-polynomial (Taylor) form per knot interval; converts
+//                            the no-wiggle samples to (value, slope) pairs.  Output lives in HBM, is a few MB and
+//                            is read by the main kernel through L1/L2.
+//                            blockIdx.y == 3, per z-bin (spectro_setup_block): derived scalars, table pointers,
+//                            stencil feed of every (stencil point, bin) and the bin's work list by class.
+//   spectro_fisher_kernel    one CTA = one z-bin x a run of tiles (256 wavenumbers x one mu row) walked down the
+//                            mu rows of a k block.  Per tile a few threads stage the row constants of every
+//                            stencil point (the AP remap is linear in k along a row); each thread then evaluates
+//                            ln P_obs of its cell at every stencil point (Kaiser, FoG, dewiggling, spec-z error;
+//                            three table look-ups with hints that survive from tile to tile), accumulates the
+//                            derivative stencils into a shared-memory tile d[par][cell], and each warp contracts
+//                            its 32 cells into the Gram matrix F_ij += w d_i d_j with FP64 tensor-core MMAs
+//                            (mma.sync m8n8k4 = DMMA; tcgen05 has no f64 kind).  Per-CTA partials go to HBM.
+//   spectro_reduce_kernel    fixed-tree sum of the CTA partials -> F[Z][npar][npar] (deterministic).
+//   spectro_chi2_kernel      wedge likelihood of a batch of points: the same evaluation walking down mu columns
+//                            against a device-resident data lattice; spectro_data_kernel builds that lattice
+//                            from stencil point 0 when the caller has none.
 //
 // Reference semantics restated here: cosmicfishpie/LSSsurvey/spectro_obs.py:342-933,
 // spectro_cov.py:207-228,481-532, fishermatrix/derivatives.py:93-207, cosmicfish.py:495-542.
