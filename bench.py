@@ -407,7 +407,7 @@ def run_gpu(args):
 
     Lp = PhotometricLikelihood(cosmo_data=fm_ph)
     kp = [k for k in fm_ph.freeparams if k not in P7]
-    like_photo = like_block(Lp, kp, fm_ph.allparams, 8192, 0.02)
+    like_photo = like_block(Lp, kp, fm_ph.allparams, 16384, 0.02)
     Ls = SpectroLikelihood(cosmoFM_data=fm_sp)
     ks = [k for k in fm_sp.freeparams if k.startswith("lnbg")]
     like_spectro = like_block(Ls, ks, fm_sp.allparams, 256, 0.01)

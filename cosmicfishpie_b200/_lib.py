@@ -35,7 +35,7 @@ EXPORTS = [
     "cfp_photo_plan_chi2", "cfp_spectro_plan_chi2", "cfp_cells_chi2", "cfp_wedge_chi2",
     "cfp_legendre_project", "cfp_legendre_covariance", "cfp_legendre_chi2",
     "cfp_bank_upload_rows", "cfp_host_alloc", "cfp_host_free", "cfp_spectro_plan_chi2_dev", "cfp_dev_upload",
-    "cfp_dev_release", "cfp_photo_plan_create_zmap",
+    "cfp_dev_release", "cfp_photo_plan_create_zmap", "cfp_ctx_aux_stream",
 ]
 
 
@@ -68,6 +68,8 @@ def load():
     lib.cfp_ctx_create.argtypes = [C.c_int, C.POINTER(_vp)]
     lib.cfp_ctx_destroy.argtypes = [_vp]
     lib.cfp_ctx_sync.argtypes = [_vp]
+    lib.cfp_ctx_aux_stream.argtypes = [_vp]
+    lib.cfp_ctx_aux_stream.restype = _vp
     lib.cfp_ctx_launch_count.argtypes = [_vp]
     lib.cfp_ctx_launch_count.restype = C.c_int64
     lib.cfp_ctx_last_run_ms.argtypes = [_vp]
@@ -153,6 +155,11 @@ class Context:
 
     def sync(self):
         _check(self.lib.cfp_ctx_sync(self.handle), "cfp_ctx_sync")
+
+    @property
+    def aux_stream(self) -> int:
+        """Handle of the context's second stream (pass as `stream=`)."""
+        return int(self.lib.cfp_ctx_aux_stream(self.handle) or 0)
 
     @property
     def launches(self) -> int:

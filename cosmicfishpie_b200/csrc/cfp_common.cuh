@@ -32,6 +32,7 @@ struct cfp_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux = nullptr;  // second stream for callers that overlap a running batch with the next one's uploads
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
   double last_ms = 0.0;

@@ -32,6 +32,7 @@ extern "C" int cfp_ctx_create(int device, cfp_ctx** out) {
   CFP_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
   CFP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CFP_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
   CFP_CUDA(cudaEventCreate(&ctx->ev0));
   CFP_CUDA(cudaEventCreate(&ctx->ev1));
   // Arena for every device buffer of banks and plans: a private stream-ordered pool that keeps what it
@@ -58,6 +59,8 @@ extern "C" int cfp_ctx_destroy(cfp_ctx* ctx) {
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+  cudaStreamSynchronize(ctx->aux);
+  cudaStreamDestroy(ctx->aux);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return CFP_OK;
@@ -69,6 +72,8 @@ extern "C" int cfp_ctx_sync(cfp_ctx* ctx) {
   CFP_CUDA(cudaStreamSynchronize(ctx->stream));
   return CFP_OK;
 }
+
+extern "C" void* cfp_ctx_aux_stream(cfp_ctx* ctx) { return ctx ? (void*)ctx->aux : nullptr; }
 
 extern "C" int64_t cfp_ctx_launch_count(const cfp_ctx* ctx) { return ctx ? ctx->launches : -1; }
 

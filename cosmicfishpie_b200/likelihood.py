@@ -247,10 +247,30 @@ class PhotometricLikelihood(Likelihood, NautilusMixin):
         off, n, w = self._blocks()
         out = np.empty(matrix.shape[0])
         chunk = 4096
-        for i in range(0, matrix.shape[0], chunk):
-            job = photo_mod.PhotoJob.from_matrix(self.cosmo_theory, names, matrix[i:i + chunk])
-            out[i:i + chunk] = job.plan().chi2(off, n, w, data=self._data_full)
+        spans = [(i, min(i + chunk, matrix.shape[0])) for i in range(0, matrix.shape[0], chunk)]
+        if len(spans) == 1:
+            job = photo_mod.PhotoJob.from_matrix(self.cosmo_theory, names, matrix)
+            out[:] = job.plan().chi2(off, n, w, data=self._data_full)
             job.close()
+            return out
+        # software pipeline over the chunks: chunk i's kernels run on the context's second stream from a worker thread
+        # (ctypes releases the GIL while it waits) while this thread assembles and uploads chunk i+1
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(job, a, b):
+            plan = job.plan()
+            out[a:b] = plan.chi2(off, n, w, data=self._data_full, stream=plan.ctx.aux_stream)
+            job.close()
+
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = None
+            for a, b in spans:
+                job = photo_mod.PhotoJob.from_matrix(self.cosmo_theory, names, matrix[a:b])
+                job.plan()  # create + H2D now, on the context stream
+                if pending is not None:
+                    pending.result()
+                pending = pool.submit(run, job, a, b)
+            pending.result()
         return out
 
     def chi2_batch(self, param_dicts) -> np.ndarray:

@@ -48,6 +48,10 @@ int cfp_ctx_create(int device, cfp_ctx** out);
 int cfp_ctx_destroy(cfp_ctx* ctx);
 int cfp_ctx_sync(cfp_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+/* A second stream owned by the context, for the `stream` argument of the *_run / *_chi2 entry points: a caller can
+ * run one batch there (from a worker thread) while it creates the next plan -- whose uploads use the context's own
+ * stream -- and so overlap PCIe with compute.  The library itself never launches on it.                          */
+void* cfp_ctx_aux_stream(cfp_ctx* ctx);
 int64_t cfp_ctx_launch_count(const cfp_ctx* ctx);
 /* device time [ms] of the last *_run call, measured with CUDA events on the launch stream */
 double cfp_ctx_last_run_ms(const cfp_ctx* ctx);

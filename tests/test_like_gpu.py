@@ -152,3 +152,18 @@ def test_spectro_legendre_matches_reference(spectro_fm):
     assert np.max(np.abs(chi2[1:] - ref[1:]) / ref[1:]) < 1e-7
     th = like.compute_theory(dicts[2])
     assert abs(like.compute_chi2(th) - ref[2]) / ref[2] < 1e-7
+
+
+def test_photo_batch_pipeline_equals_single_chunks(photo_fm):
+    """Batches longer than one chunk run as a two-stage pipeline (worker thread + second stream): same numbers as
+    the chunks evaluated one by one."""
+    from cosmicfishpie_b200.likelihood import PhotometricLikelihood
+
+    like = PhotometricLikelihood(cosmo_data=photo_fm)
+    keys = ["b1", "b5", "AIA", "etaIA"]
+    fid = np.array([photo_fm.allparams[k] for k in keys])
+    mat = fid * (1 + 0.02 * np.random.default_rng(11).standard_normal((4096 + 700, len(keys))))
+    whole = like.loglike_batch(mat, keys=keys)
+    parts = np.concatenate([like.loglike_batch(mat[:4096], keys=keys), like.loglike_batch(mat[4096:], keys=keys)])
+    assert np.array_equal(whole, parts)
+    assert np.all(np.isfinite(whole)) and whole.max() <= 1e-9

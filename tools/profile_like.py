@@ -28,7 +28,7 @@ def main():
     b.compute()
     buf = io.StringIO()
     for name, like, keys, allp, B in (
-            ("photo", PhotometricLikelihood(cosmo_data=a), [k for k in a.freeparams if k not in bench.P7], a.allparams, 8192),
+            ("photo", PhotometricLikelihood(cosmo_data=a), [k for k in a.freeparams if k not in bench.P7], a.allparams, 16384),
             ("spectro", SpectroLikelihood(cosmoFM_data=b), [k for k in b.freeparams if k.startswith("lnbg")], b.allparams, 256)):
         fid = np.array([allp[k] for k in keys])
         mat = fid * (1.0 + 0.02 * np.random.default_rng(0).standard_normal((B, len(keys))))
