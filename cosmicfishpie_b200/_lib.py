@@ -213,7 +213,13 @@ class Context:
 
     def legendre_chi2(self, pl_data, pl_theory, icov) -> np.ndarray:
         pl_data, pl_theory, icov = f64(pl_data), f64(pl_theory), f64(icov)
-        S, Nk, Z = pl_theory.shape[:3]
+        S, Nk, Z, nl = pl_theory.shape
+        if nl > 3 or pl_data.shape != (Nk, Z, nl) or icov.shape != (Nk, Z, nl, nl):
+            raise ValueError("legendre_chi2: expected P_ell (Nk, Nz, n<=3) and an inverse covariance (Nk, Nz, n, n)")
+        if nl < 3:  # the kernel contracts three multipoles: pad with zeros (contributes nothing)
+            pd, pt, ic = np.zeros((Nk, Z, 3)), np.zeros((S, Nk, Z, 3)), np.zeros((Nk, Z, 3, 3))
+            pd[..., :nl], pt[..., :nl], ic[..., :nl, :nl] = pl_data, pl_theory, icov
+            pl_data, pl_theory, icov = pd, pt, ic
         out = np.empty(S)
         _check(self.lib.cfp_legendre_chi2(self.handle, S, Nk, Z, _p(pl_data), _p(pl_theory), _p(icov), _p(out)),
                "cfp_legendre_chi2")

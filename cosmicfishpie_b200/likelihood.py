@@ -287,6 +287,12 @@ class PhotometricLikelihood(Likelihood, NautilusMixin):
 
 
 # ------------------------------------------------------------------------------------- spectroscopic
+def _device_of(fm):
+    """options["device"] of a FisherMatrix; duck-typed stand-ins (the reference's own tests use bare objects with
+    only the grids) have no settings and get the default device."""
+    return (getattr(fm, "settings", None) or {}).get("device") if fm is not None else None
+
+
 def observable_Pgg(theory_spectro, cosmoFM, nuisance_shot=None):
     """P_obs + 1/nbar + shot on the (z, mu, k) lattice (reference: spectro_like.py:25-41)."""
     z_bins = cosmoFM.pk_cov.global_z_bin_mids
@@ -301,7 +307,7 @@ def observable_Pgg(theory_spectro, cosmoFM, nuisance_shot=None):
 
 def compute_wedge_chi2(P_obs_data, P_obs_theory, cosmoFM_data):
     """Reference: spectro_like.py:143-189 (device reduction, Simpson weights of the lattice)."""
-    ctx = _lib.default_context(cosmoFM_data.settings.get("device"))
+    ctx = _lib.default_context(_device_of(cosmoFM_data))
     k, mu = cosmoFM_data.Pk_kgrid, cosmoFM_data.Pk_mugrid
     return float(ctx.wedge_chi2(np.asarray(P_obs_theory)[None], P_obs_data, k, simpson_weights(k), simpson_weights(mu),
                                 cosmoFM_data.pk_cov.volume_survey_array)[0])
@@ -329,13 +335,13 @@ def _legendre_weights(mugrid):
 
 def legendre_Pgg(obs_Pgg, cosmoFM):
     """Multipoles P_ell(k, z), ell = 0,2,4, shape (Nk, Nz, 3) (reference: spectro_like.py:48-56)."""
-    ctx = _lib.default_context(cosmoFM.settings.get("device"))
+    ctx = _lib.default_context(_device_of(cosmoFM))
     return ctx.legendre_project(np.asarray(obs_Pgg)[None], _legendre_weights(cosmoFM.Pk_mugrid))[0]
 
 
 def compute_covariance_legendre(P_ell, cosmoFM):
     """k-bin integrated Gaussian covariance of the multipoles and its inverse (reference: spectro_like.py:69-122)."""
-    ctx = _lib.default_context(cosmoFM.settings.get("device"))
+    ctx = _lib.default_context(_device_of(cosmoFM))
     if P_ell.shape[0] != len(cosmoFM.Pk_kgrid):
         raise ValueError("k_grid and P_ell have different lengths in k")
     return ctx.legendre_covariance(P_ell, cosmoFM.Pk_kgrid, cosmoFM.pk_cov.volume_survey_array, _M3J_REF)
@@ -343,7 +349,7 @@ def compute_covariance_legendre(P_ell, cosmoFM):
 
 def compute_chi2_legendre(P_ell_data, P_ell_theory, inv_covariance, cosmoFM=None):
     """Reference: spectro_like.py:125-140."""
-    ctx = _lib.default_context(None if cosmoFM is None else cosmoFM.settings.get("device"))
+    ctx = _lib.default_context(_device_of(cosmoFM))
     return float(ctx.legendre_chi2(P_ell_data, np.asarray(P_ell_theory)[None], inv_covariance)[0])
 
 
