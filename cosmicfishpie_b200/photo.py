@@ -102,12 +102,18 @@ _LUM_CACHE = {}
 
 
 def _lumratio_table(extdir):
+    """<L>(z)/L*(z) table of the eNLA model: `lumratio_file.dat` of `external_data_dir` (nuisance.py:193-230); the
+    package's own data directory ships the same table as .npy.  None if the directory has no such file -- the
+    reference then uses a ratio of 1 (with a warning)."""
     if extdir not in _LUM_CACHE:
+        here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
         txt = os.path.join(extdir or "", "lumratio_file.dat")
         if extdir and os.path.isfile(txt):
             _LUM_CACHE[extdir] = np.loadtxt(txt)
+        elif extdir is None or os.path.abspath(extdir) == here:
+            _LUM_CACHE[extdir] = np.load(os.path.join(here, "lumratio.npy"))
         else:
-            _LUM_CACHE[extdir] = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "lumratio.npy"))
+            _LUM_CACHE[extdir] = None
     return _LUM_CACHE[extdir]
 
 
@@ -123,7 +129,10 @@ class PhotoNuisance:
                              max(sp["z_bins_WL"][-1], sp["z_bins_GCph"][-1]) + 1, 50 * self.settings["accuracy"])
         if "WL" in self.observables:
             lum = _lumratio_table(self.settings.get("external_data_dir"))
-            self.lumratio = interp1d(lum[:, 0], lum[:, 1], kind="linear")
+            if lum is None:  # nuisance.py:220-228
+                self.lumratio = lambda z: np.ones_like(z) if hasattr(z, "__len__") else 1.0
+            else:
+                self.lumratio = interp1d(lum[:, 0], lum[:, 1], kind="linear")
             self._lum_z = self.lumratio(self.z)
 
     def gcph_bias(self, biaspars, ibin=1):
@@ -147,13 +156,16 @@ class PhotoNuisance:
     def IA(self, IApars, cosmo):
         if IApars["IA_model"] != "eNLA":
             raise ValueError("only the eNLA intrinsic alignment model exists")
-        Om = cosmo.scalar("Omegam_of_z", 0.0)
+        # memoised accessors of this package's cosmology facade; any object with the reference's
+        # `Omegam_of_z` / `growth` methods works too
+        Om = cosmo.scalar("Omegam_of_z", 0.0) if hasattr(cosmo, "scalar") else cosmo.Omegam_of_z(0.0)
         piv = self.settings["pivot_z_IA"]
         z = self.z
         CIA = 0.0134 * (1 + piv)
         fac = -IApars["AIA"] * CIA * Om
         z_dep = (1 + z) / (1 + piv)
-        win = fac * z_dep ** IApars["etaIA"] * ((self._lum_z ** IApars["betaIA"]) / (cosmo.on_grid("growth", z).flatten()))
+        growth = cosmo.on_grid("growth", z) if hasattr(cosmo, "on_grid") else np.asarray(cosmo.growth(z))
+        win = fac * z_dep ** IApars["etaIA"] * ((self._lum_z ** IApars["betaIA"]) / (growth.flatten()))
         return InterpolatedUnivariateSpline(z, win, k=1)
 
 
