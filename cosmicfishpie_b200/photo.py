@@ -493,15 +493,27 @@ class PhotoCov:
         return noisy
 
     def get_covmat(self, noisy_cls):
-        """Per-multipole covariance (C + N)/sqrt(f_sky) as an array [Nl][Nb][Nb]; column order `cov_cols`
-        (the reference returns a list of pandas DataFrames with the same values, photo_cov.py:198-245)."""
+        """Per-multipole covariance (C + N)/sqrt(f_sky) as the reference returns it: a list of Nl pandas DataFrames
+        indexed by the tomographic rows (photo_cov.py:198-245).  `np.array(covmat)` is the [Nl][Nb][Nb] array."""
+        import pandas as pd
+
         cols = self.grid.cols
         self.cov_cols = cols
         cov = np.empty((len(noisy_cls["ells"]), len(cols), len(cols)))
         for a, ca in enumerate(cols):
             for b, cb in enumerate(cols):
                 cov[:, a, b] = noisy_cls[ca + "x" + cb] / self.grid.sqrtfsky[a]
-        return cov
+        return [pd.DataFrame(m, index=cols, columns=cols) for m in cov]
+
+    def __getattr__(self, name):
+        # the reference's FisherMatrix.compute() leaves cls / noisy_cls / covmat / derivs on photo_LSS; here they are
+        # produced on first access (the Fisher matrix itself never needs them on the host)
+        if name in ("cls", "noisy_cls", "covmat") and "_job" in self.__dict__:
+            self.compute_covmat()
+            return self.__dict__[name]
+        if name == "derivs" and "_job" in self.__dict__:
+            return self.compute_derivs()
+        raise AttributeError(name)
 
     # --- the whole job ---------------------------------------------------------------------------
     def _freeparams(self, freeparams=None):

@@ -517,6 +517,16 @@ class SpectroDerivs:
         self.fiducial_obj = fiducial_spectro_obj
         self.z_array = np.asarray(z_array)
         self.pk_kmesh, self.pk_mumesh = pk_kmesh, pk_mumesh
+        # The device works on a separable (mu, k) lattice.  A np.meshgrid pair maps onto it directly; any other
+        # broadcastable pair (the reference evaluates whatever it is given) is evaluated on the lattice of its
+        # distinct k and mu values and gathered back.
+        kk, mm = np.asarray(pk_kmesh, dtype=float), np.asarray(pk_mumesh, dtype=float)
+        if kk.ndim == 2 and kk.shape == mm.shape and np.all(kk == kk[0:1, :]) and np.all(mm == mm[:, 0:1]):
+            self._kgrid, self._mugrid, self._gather = kk[0, :], mm[:, 0], None
+        else:
+            kb, mb = np.broadcast_arrays(kk, mm)
+            self._kgrid, self._mugrid = np.unique(kb), np.unique(mb)
+            self._gather = (np.searchsorted(self._mugrid, mb), np.searchsorted(self._kgrid, kb))
         self.freeparams = None
         self.stencil = stencil
         self.config = configuration if configuration is not None else fiducial_spectro_obj.config
@@ -528,17 +538,17 @@ class SpectroDerivs:
         """{"z_bins": z_array, i: ln P_obs lattice} at an arbitrary parameter point (spectro_cov.py:481-508)."""
         cfg = self.fiducial_obj._cfg
         self.pobs = SpectroJob._point(allpars, cfg, self.fiducial_obj.cosmo_set)
-        lat = _evaluate_lattice([self.pobs], list(self.z_array), self.pk_kmesh[0, :], self.pk_mumesh[:, 0])
+        lat = _evaluate_lattice([self.pobs], list(self.z_array), self._kgrid, self._mugrid)
         out = {"z_bins": self.z_array}
         for i in range(len(self.z_array)):
-            out[i] = lat[0, i]
+            out[i] = lat[0, i] if self._gather is None else lat[0, i][self._gather]
         return out
 
     def build_job(self, cov: SpectroCov, freeparams=None) -> SpectroJob:
         if freeparams:
             self.freeparams = freeparams
-        self.job = SpectroJob(self.fiducial_obj, cov, self.z_array, self.pk_kmesh[0, :], self.pk_mumesh[:, 0],
-                              self.freeparams, self.stencil)
+        self.job = SpectroJob(self.fiducial_obj, cov, self.z_array, self._kgrid, self._mugrid, self.freeparams,
+                              self.stencil)
         return self.job
 
     def compute_derivs(self, freeparams=dict(), cov: Optional[SpectroCov] = None):
@@ -550,10 +560,11 @@ class SpectroDerivs:
             self.build_job(cov)
         plan = self.job.run(materialize=_lib.MAT_DERIVS)
         _, _, D, V = plan.fetch(derivs=True)
-        self.veff = V
+        g = self._gather
+        self.veff = V if g is None else np.array([v[g] for v in V])
         derivs = {}
         for ip, par in enumerate(self.job.parnames):
-            d = {i: D[ip, i] for i in range(len(self.z_array))}
+            d = {i: (D[ip, i] if g is None else D[ip, i][g]) for i in range(len(self.z_array))}
             if self.job.ps_bin[ip] < 0:
                 d = {"z_bins": self.z_array, **d}
             derivs[par] = d
