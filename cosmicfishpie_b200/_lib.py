@@ -35,7 +35,7 @@ EXPORTS = [
     "cfp_photo_plan_chi2", "cfp_spectro_plan_chi2", "cfp_cells_chi2", "cfp_wedge_chi2",
     "cfp_legendre_project", "cfp_legendre_covariance", "cfp_legendre_chi2",
     "cfp_bank_upload_rows", "cfp_host_alloc", "cfp_host_free", "cfp_spectro_plan_chi2_dev", "cfp_dev_upload",
-    "cfp_dev_release", "cfp_photo_plan_create_zmap", "cfp_ctx_aux_stream",
+    "cfp_dev_release", "cfp_photo_plan_create_zmap", "cfp_ctx_aux_stream", "cfp_photo_plan_create_ex",
 ]
 
 
@@ -103,6 +103,10 @@ def load():
     lib.cfp_photo_plan_create_zmap.argtypes = [
         _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp, C.c_double, _dp, _dp, _dp,
         _ip, _dp, _dp, C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int, C.POINTER(_vp)]
+    lib.cfp_photo_plan_create_ex.argtypes = [
+        _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp, C.c_double, _dp, _dp, _dp,
+        _ip, C.c_int, _ip, _dp, _dp, C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int,
+        C.POINTER(_vp)]
     lib.cfp_photo_plan_destroy.argtypes = [_vp]
     lib.cfp_photo_plan_set_slice.argtypes = [_vp, C.c_int, C.c_int]
     lib.cfp_photo_plan_run.argtypes = [_vp, _vp]
@@ -483,7 +487,7 @@ class SpectroPlan:
 
 class PhotoPlan:
     def __init__(self, ctx: Context, bank: Bank, *, cosmo_of_s, ell, z, dz, chi, hub, wlpref, kind, ngal, bias, ia,
-                 lmin, lmax, noise, sqrtfsky, stw, stden, kmax, tab_p=TAB_PNL, zmap=None):
+                 lmin, lmax, noise, sqrtfsky, stw, stden, kmax, tab_p=TAB_PNL, zmap=None, win_of_s=None):
         self.ctx, self.bank = ctx, bank
         self.cosmo_of_s = i32(cosmo_of_s)
         self.ell, self.z = f64(ell), f64(z)
@@ -497,10 +501,22 @@ class PhotoPlan:
         assert self.chi.shape == (self.NC, self.Nz) and self.hub.shape == (self.NC, self.Nz)
         self.zmap = None if zmap is None else i32(zmap)
         Kb = self.Nz if self.zmap is None else self.bias.shape[2]
-        assert self.ngal.shape == (self.Nb, self.Nz) and self.bias.shape == (self.S, self.Nb, Kb)
+        self.win_of_s = None if win_of_s is None else i32(win_of_s)
+        NW = 1 if self.win_of_s is None else self.ngal.shape[0]
+        assert self.ngal.shape == ((self.Nb, self.Nz) if self.win_of_s is None else (NW, self.Nb, self.Nz))
+        assert self.bias.shape == (self.S, self.Nb, Kb)
         assert self.ia.shape == (self.S, self.Nz) and self.stw.shape == (self.npar, self.S)
         self.handle = _vp()
-        if self.zmap is None:
+        if self.win_of_s is not None:  # several sets of n(z) windows (photo-z parameters vary between points)
+            assert self.win_of_s.shape == (self.S,)
+            _check(ctx.lib.cfp_photo_plan_create_ex(
+                ctx.handle, bank.handle, self.S, self.NC, self.Nl, self.Nz, self.Nb, self.npar,
+                _p(self.cosmo_of_s, _ip), _p(self.ell), _p(self.z), float(dz), _p(self.chi), _p(self.hub),
+                _p(self.wlpref), _p(self.kind, _ip), int(NW), _p(self.win_of_s, _ip), _p(self.ngal), _p(self.bias),
+                int(Kb), _p(self.zmap, _ip), _p(self.ia), _p(self.lmin), _p(self.lmax), _p(self.noise),
+                _p(self.sqrtfsky), _p(self.stw), _p(self.stden), float(kmax), int(tab_p), C.byref(self.handle)),
+                "cfp_photo_plan_create_ex")
+        elif self.zmap is None:
             _check(ctx.lib.cfp_photo_plan_create(
                 ctx.handle, bank.handle, self.S, self.NC, self.Nl, self.Nz, self.Nb, self.npar,
                 _p(self.cosmo_of_s, _ip), _p(self.ell), _p(self.z), float(dz), _p(self.chi), _p(self.hub),

@@ -48,11 +48,15 @@ __global__ void photo_sqrtp_kernel(const double* __restrict__ blob, const int64_
 // one CTA per cosmology: eff = I1 - chi * I2 with backward cumulative trapezoids (sequential in z like
 // np.cumsum).  n_i(z) and n_i(z)/chi(z) are staged in shared memory by the whole CTA first, so the serial
 // 200-step recurrence of each lensing row runs on shared-memory operands only.
-__global__ void __launch_bounds__(256) photo_eff_kernel(int NC, int Nb, int Nz, const int* __restrict__ kind,
-                                                        const double* __restrict__ ngal, const double* __restrict__ chi,
-                                                        double dz, double* __restrict__ eff) {
+__global__ void __launch_bounds__(256) photo_eff_kernel(int NP, int Nb, int Nz, const int* __restrict__ kind,
+                                                        const int* __restrict__ pair_c, const int* __restrict__ pair_w,
+                                                        const double* __restrict__ ngal_all,
+                                                        const double* __restrict__ chi, double dz,
+                                                        double* __restrict__ eff) {
   extern __shared__ double effsm[];  // chi[Nz], n[Nb][Nz], q[Nb][Nz], e[Nb][Nz]
-  const int c = blockIdx.x;
+  // one CTA per (cosmology, n(z) window set) pair that occurs among the stencil points
+  const int c = pair_c ? pair_c[blockIdx.x] : blockIdx.x;
+  const double* ngal = ngal_all + (size_t)(pair_w ? pair_w[blockIdx.x] : 0) * Nb * Nz;
   double* sch = effsm;
   double* sn = sch + Nz;
   double* sq = sn + (size_t)Nb * Nz;
@@ -92,17 +96,20 @@ __global__ void __launch_bounds__(256) photo_eff_kernel(int NC, int Nb, int Nz, 
     }
   }
   __syncthreads();
-  double* out = eff + (size_t)c * Nb * Nz;
+  double* out = eff + (size_t)blockIdx.x * Nb * Nz;
   for (int i = threadIdx.x; i < Nb * Nz; i += blockDim.x) out[i] = se[i];
 }
 
 // fallback for grids whose rows do not fit in shared memory: one thread per (cosmology, row), global operands
-__global__ void photo_eff_kernel_global(int NC, int Nb, int Nz, const int* __restrict__ kind,
-                                        const double* __restrict__ ngal, const double* __restrict__ chi, double dz,
+__global__ void photo_eff_kernel_global(int NP, int Nb, int Nz, const int* __restrict__ kind,
+                                        const int* __restrict__ pair_c, const int* __restrict__ pair_w,
+                                        const double* __restrict__ ngal_all, const double* __restrict__ chi, double dz,
                                         double* __restrict__ eff) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= NC * Nb) return;
-  const int c = idx / Nb, a = idx % Nb;
+  if (idx >= NP * Nb) return;
+  const int pr = idx / Nb, a = idx % Nb;
+  const int c = pair_c ? pair_c[pr] : pr;
+  const double* ngal = ngal_all + (size_t)(pair_w ? pair_w[pr] : 0) * Nb * Nz;
   double* e = eff + (size_t)idx * Nz;
   if (kind[a] != 0) {
     for (int i = 0; i < Nz; ++i) e[i] = 0.0;
@@ -125,6 +132,7 @@ __global__ void photo_eff_kernel_global(int NC, int Nb, int Nz, const int* __res
 
 // U[s][a][z] = W_a/sqrt(H), V[s][a][z] = W^IA_a/sqrt(H), rows padded to ldz
 __global__ void photo_window_kernel(int S, int Nb, int Nz, int ldz, int nrow_pad, const int* __restrict__ cosmo_of_s,
+                                    const int* __restrict__ win_of_s, const int* __restrict__ pair_of_s,
                                     const int* __restrict__ kind, const double* __restrict__ z,
                                     const double* __restrict__ chi, const double* __restrict__ hub,
                                     const double* __restrict__ wlpref, const double* __restrict__ ngal,
@@ -142,9 +150,10 @@ __global__ void photo_window_kernel(int S, int Nb, int Nz, int ldz, int nrow_pad
     const int c = cosmo_of_s[s];
     const double H = hub[(size_t)c * Nz + iz];
     const double sh = sqrt(H);
-    const double ng = ngal[(size_t)a * Nz + iz];
+    const double ng = ngal[((size_t)(win_of_s ? win_of_s[s] : 0) * Nb + a) * Nz + iz];
+    const int pr = pair_of_s ? pair_of_s[s] : c;  // (cosmology, window set) pair: row of the efficiency table
     if (kind[a] == 0) {  // lensing row, photo_obs.py:584-590
-      const double w = wlpref[c] * (1.0 + z[iz]) * chi[(size_t)c * Nz + iz] * eff[((size_t)c * Nb + a) * Nz + iz];
+      const double w = wlpref[c] * (1.0 + z[iz]) * chi[(size_t)c * Nz + iz] * eff[((size_t)pr * Nb + a) * Nz + iz];
       const double wia = ng * ia[(size_t)s * Nz + iz] * H;
       u = w / sh;
       v = wia / sh;
@@ -628,6 +637,8 @@ struct cfp_photo_plan {
   int *cosmo_of_s_d = nullptr, *kind_d = nullptr;
   double *ell_d = nullptr, *z_d = nullptr, *chi_d = nullptr, *hub_d = nullptr, *wlpref_d = nullptr, *ngal_d = nullptr;
   double *bias_d = nullptr, *ia_d = nullptr, *lmin_d = nullptr, *lmax_d = nullptr, *noise_d = nullptr;
+  int NW = 1, NP = 0;     // n(z) window sets; (cosmology, window set) pairs among the stencil points
+  int *win_of_s_d = nullptr, *pair_of_s_d = nullptr, *pair_c_d = nullptr, *pair_w_d = nullptr;
   int Kb = 0;             // bias samples per (point, row): Nz, or fewer with a z -> sample map
   int* zmap_d = nullptr;  // [Nz] or NULL (identity)
   double *sqrtfsky_d = nullptr, *stw_d = nullptr, *stden_d = nullptr, *strden_d = nullptr, *wz_d = nullptr;
@@ -665,7 +676,7 @@ static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int
                                   const double* ia_h, const double* lmin_h, const double* lmax_h,
                                   const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
                                   const double* stden_h, double kmax, int tab_p, int Kb, const int32_t* zmap_h,
-                                  cfp_photo_plan** out);
+                                  int NW, const int32_t* win_of_s_h, cfp_photo_plan** out);
 
 extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb,
                                      int npar, const int32_t* cosmo_of_s_h, const double* ell_h, const double* z_h,
@@ -676,7 +687,7 @@ extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, 
                                      const double* stden_h, double kmax, int tab_p, cfp_photo_plan** out) {
   return photo_plan_create_impl(ctx, bank, S, NC, Nl, Nz, Nb, npar, cosmo_of_s_h, ell_h, z_h, dz, chi_h, hub_h, wlpref_h,
                                 kind_h, ngal_h, bias_h, ia_h, lmin_h, lmax_h, noise_h, sqrtfsky_h, stw_h, stden_h, kmax,
-                                tab_p, Nz, nullptr, out);
+                                tab_p, Nz, nullptr, 1, nullptr, out);
 }
 
 extern "C" int cfp_photo_plan_create_zmap(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb,
@@ -691,7 +702,27 @@ extern "C" int cfp_photo_plan_create_zmap(cfp_ctx* ctx, const cfp_bank* bank, in
   for (int i = 0; i < Nz; ++i) CFP_REQUIRE(zmap_h[i] >= 0 && zmap_h[i] < Kb, "z map entry out of range");
   return photo_plan_create_impl(ctx, bank, S, NC, Nl, Nz, Nb, npar, cosmo_of_s_h, ell_h, z_h, dz, chi_h, hub_h, wlpref_h,
                                 kind_h, ngal_h, bias_h, ia_h, lmin_h, lmax_h, noise_h, sqrtfsky_h, stw_h, stden_h, kmax,
-                                tab_p, Kb, zmap_h, out);
+                                tab_p, Kb, zmap_h, 1, nullptr, out);
+}
+
+extern "C" int cfp_photo_plan_create_ex(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb,
+                                        int npar, const int32_t* cosmo_of_s_h, const double* ell_h, const double* z_h,
+                                        double dz, const double* chi_h, const double* hub_h, const double* wlpref_h,
+                                        const int32_t* kind_h, int NW, const int32_t* win_of_s_h,
+                                        const double* ngal_h, const double* bias_h, int Kb, const int32_t* zmap_h,
+                                        const double* ia_h, const double* lmin_h, const double* lmax_h,
+                                        const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
+                                        const double* stden_h, double kmax, int tab_p, cfp_photo_plan** out) {
+  CFP_REQUIRE(NW >= 1 && (NW == 1 || win_of_s_h != nullptr), "NW >= 1, and a window index per point when NW > 1");
+  if (win_of_s_h)
+    for (int s = 0; s < S; ++s) CFP_REQUIRE(win_of_s_h[s] >= 0 && win_of_s_h[s] < NW, "window index out of range");
+  if (zmap_h) {
+    CFP_REQUIRE(Kb >= 1, "Kb >= 1");
+    for (int i = 0; i < Nz; ++i) CFP_REQUIRE(zmap_h[i] >= 0 && zmap_h[i] < Kb, "z map entry out of range");
+  }
+  return photo_plan_create_impl(ctx, bank, S, NC, Nl, Nz, Nb, npar, cosmo_of_s_h, ell_h, z_h, dz, chi_h, hub_h, wlpref_h,
+                                kind_h, ngal_h, bias_h, ia_h, lmin_h, lmax_h, noise_h, sqrtfsky_h, stw_h, stden_h, kmax,
+                                tab_p, zmap_h ? Kb : Nz, zmap_h, NW, win_of_s_h, out);
 }
 
 static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb, int npar,
@@ -701,7 +732,7 @@ static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int
                                   const double* ia_h, const double* lmin_h, const double* lmax_h,
                                   const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
                                   const double* stden_h, double kmax, int tab_p, int Kb, const int32_t* zmap_h,
-                                  cfp_photo_plan** out) {
+                                  int NW, const int32_t* win_of_s_h, cfp_photo_plan** out) {
   CFP_REQUIRE(ctx && bank && out, "NULL ctx/bank/out");
   CFP_REQUIRE(cosmo_of_s_h && ell_h && z_h && chi_h && hub_h && wlpref_h && kind_h && ngal_h && bias_h && ia_h &&
                   lmin_h && lmax_h && noise_h && sqrtfsky_h && stw_h && stden_h,
@@ -746,7 +777,29 @@ static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int
   PH_UP(double, chi_h, (size_t)NC * Nz, pl->chi_d);
   PH_UP(double, hub_h, (size_t)NC * Nz, pl->hub_d);
   PH_UP(double, wlpref_h, (size_t)NC, pl->wlpref_d);
-  PH_UP(double, ngal_h, (size_t)Nb * Nz, pl->ngal_d);
+  PH_UP(double, ngal_h, (size_t)NW * Nb * Nz, pl->ngal_d);
+  pl->NW = NW;
+  {
+    // distinct (cosmology, window set) pairs among the stencil points: one lensing-efficiency table each
+    std::vector<int> pair_of_s(S), pair_c, pair_w;
+    for (int s = 0; s < S; ++s) {
+      const int c = cosmo_of_s_h[s], w = win_of_s_h ? win_of_s_h[s] : 0;
+      int p = 0;
+      for (; p < (int)pair_c.size(); ++p)
+        if (pair_c[p] == c && pair_w[p] == w) break;
+      if (p == (int)pair_c.size()) pair_c.push_back(c), pair_w.push_back(w);
+      pair_of_s[s] = p;
+    }
+    if (NW == 1) {  // keep the plain layout: pair index = cosmology index, every cosmology has a table
+      pl->NP = NC;
+    } else {
+      pl->NP = (int)pair_c.size();
+      PH_UP(int, win_of_s_h, (size_t)S, pl->win_of_s_d);
+      PH_UP(int, pair_of_s.data(), (size_t)S, pl->pair_of_s_d);
+      PH_UP(int, pair_c.data(), pair_c.size(), pl->pair_c_d);
+      PH_UP(int, pair_w.data(), pair_w.size(), pl->pair_w_d);
+    }
+  }
   pl->Kb = Kb;
   PH_UP(double, bias_h, (size_t)S * Nb * Kb, pl->bias_d);
   if (zmap_h) PH_UP(int, zmap_h, (size_t)Nz, pl->zmap_d);
@@ -781,7 +834,7 @@ static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int
     PH_UP(double, ww.data(), ww.size(), pl->stp_w_d);
   }
   PH_UP(double, nullptr, (size_t)NC * Nl * Nz, pl->T_d);
-  PH_UP(double, nullptr, (size_t)NC * Nb * Nz, pl->eff_d);
+  PH_UP(double, nullptr, (size_t)pl->NP * Nb * Nz, pl->eff_d);
   PH_UP(double, nullptr, (size_t)S * pl->nb * 8 * ldz, pl->U_d);
   PH_UP(double, nullptr, (size_t)S * pl->nb * 8 * ldz, pl->V_d);
   PH_UP(double, nullptr, (size_t)S * Nl * Nb * Nb, pl->cls_d);
@@ -859,12 +912,12 @@ static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
     if (esm <= 200 * 1024) {
       if (esm > 48 * 1024)
         CFP_CUDA(cudaFuncSetAttribute(photo_eff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
-      photo_eff_kernel<<<pl->NC, 256, esm, st>>>(pl->NC, pl->Nb, pl->Nz, pl->kind_d, pl->ngal_d, pl->chi_d, pl->dz,
-                                                pl->eff_d);
+      photo_eff_kernel<<<pl->NP, 256, esm, st>>>(pl->NP, pl->Nb, pl->Nz, pl->kind_d, pl->pair_c_d, pl->pair_w_d,
+                                                pl->ngal_d, pl->chi_d, pl->dz, pl->eff_d);
     } else {
-      const int tot = pl->NC * pl->Nb;
-      photo_eff_kernel_global<<<(tot + 63) / 64, 64, 0, st>>>(pl->NC, pl->Nb, pl->Nz, pl->kind_d, pl->ngal_d, pl->chi_d,
-                                                             pl->dz, pl->eff_d);
+      const int tot = pl->NP * pl->Nb;
+      photo_eff_kernel_global<<<(tot + 63) / 64, 64, 0, st>>>(pl->NP, pl->Nb, pl->Nz, pl->kind_d, pl->pair_c_d,
+                                                             pl->pair_w_d, pl->ngal_d, pl->chi_d, pl->dz, pl->eff_d);
     }
     ctx->launches++;
     CFP_CUDA(cudaGetLastError());
@@ -872,7 +925,8 @@ static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
   {
     const size_t tot = (size_t)pl->S * pl->nb * 8 * pl->ldz;
     photo_window_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
-        pl->S, pl->Nb, pl->Nz, pl->ldz, pl->nb * 8, pl->cosmo_of_s_d, pl->kind_d, pl->z_d, pl->chi_d, pl->hub_d,
+        pl->S, pl->Nb, pl->Nz, pl->ldz, pl->nb * 8, pl->cosmo_of_s_d, pl->win_of_s_d, pl->pair_of_s_d, pl->kind_d,
+        pl->z_d, pl->chi_d, pl->hub_d,
         pl->wlpref_d, pl->ngal_d, pl->bias_d, pl->Kb, pl->zmap_d, pl->ia_d, pl->eff_d, pl->U_d, pl->V_d);
     ctx->launches++;
     CFP_CUDA(cudaGetLastError());

@@ -245,10 +245,16 @@ class PhotoJob:
         # (IA parameters, cosmology) window and each distinct bias row once
         ia_memo, bias_memo = {}, {}
         per_bin_bias = cfg.Photobiasparams.get("bias_model") == "binned_constant"
+        win_sets, win_index = [fid_photo], {tuple(fid_photo.items()): 0}
+        self.win_of_s = np.zeros(S, dtype=np.int32)
         for s, ap in enumerate(points):
             photopars = {k: ap[k] for k in fid_photo}
-            if photopars != fid_photo:
-                raise NotImplementedError("photo-z parameters cannot be varied per stencil point yet")
+            if photopars != fid_photo:  # a stencil point of a photo-z parameter: its own n_i(z) windows
+                key = tuple(photopars.items())
+                if key not in win_index:
+                    win_index[key] = len(win_sets)
+                    win_sets.append(photopars)
+                self.win_of_s[s] = win_index[key]
             cp = {k: ap[k] for k in cfg.fiducialparams}
             c = cs.add(cp)
             self.cosmo_of_s[s] = c
@@ -276,6 +282,10 @@ class PhotoJob:
         win = galaxy_photo_dist(fid_photo, configuration)
         self.window = win
         self.ngal = _ngal_rows(win, g)
+        if len(win_sets) > 1:
+            self.ngal = np.stack([_ngal_rows(galaxy_photo_dist(pp, configuration), g) for pp in win_sets])
+        else:
+            self.win_of_s = None
         self.stw, self.stden = np.asarray(stw, float), np.asarray(stden, float)
         self.NC = NC
         self._plan = None
@@ -379,7 +389,8 @@ class PhotoJob:
                 cs.ctx or _lib.default_context(), cs.bank(), cosmo_of_s=self.cosmo_of_s, ell=g.ell, z=g.z, dz=g.dz,
                 chi=self.chi, hub=self.hub, wlpref=self.wlpref, kind=g.kind, ngal=self.ngal, bias=self.bias,
                 ia=self.ia, lmin=g.lmin, lmax=g.lmax, noise=g.noise, sqrtfsky=g.sqrtfsky, stw=self.stw,
-                stden=self.stden, kmax=g.kmax, tab_p=g.tab_p, zmap=getattr(self, "zmap", None))
+                stden=self.stden, kmax=g.kmax, tab_p=g.tab_p, zmap=getattr(self, "zmap", None),
+                win_of_s=getattr(self, "win_of_s", None))
         return self._plan
 
     def run(self):

@@ -238,6 +238,17 @@ int cfp_photo_plan_create_zmap(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC
                                const int32_t* zmap_h, const double* ia_h, const double* lmin_h, const double* lmax_h,
                                const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
                                const double* stden_h, double kmax, int tab_p, cfp_photo_plan** out);
+
+/* The general form: NW sets of tomographic n_i(z) windows (ngal_h[NW][Nb][Nz]) with one index per stencil point
+ * (win_of_s_h[S], NULL when NW == 1) -- stencil points that vary a photo-z parameter carry their own windows
+ * (photo_cov.py:116-160 builds a new GalaxyPhotoDist per parameter point); zmap_h may be NULL (bias_h[S][Nb][Nz]). */
+int cfp_photo_plan_create_ex(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb, int npar,
+                             const int32_t* cosmo_of_s_h, const double* ell_h, const double* z_h, double dz,
+                             const double* chi_h, const double* hub_h, const double* wlpref_h, const int32_t* kind_h,
+                             int NW, const int32_t* win_of_s_h, const double* ngal_h, const double* bias_h, int Kb,
+                             const int32_t* zmap_h, const double* ia_h, const double* lmin_h, const double* lmax_h,
+                             const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
+                             const double* stden_h, double kmax, int tab_p, cfp_photo_plan** out);
 int cfp_photo_plan_destroy(cfp_photo_plan* plan);
 /* multi-GPU partition: this rank owns multipoles [l_begin, l_end) */
 int cfp_photo_plan_set_slice(cfp_photo_plan* plan, int l_begin, int l_end);
