@@ -52,27 +52,27 @@ class FisherMatrix:
             IMbiaspars=IMbiaspars, PShotpars=PShotpars, surveyName=surveyName, cosmoModel=cosmoModel,
             latexnames=latexnames)
         self.config = cfg
-        self.settings = copy.deepcopy(cfg.settings)
-        self.specs = copy.deepcopy(cfg.specs)
-        self.fiducialcosmopars = copy.deepcopy(cfg.fiducialparams)
+        self.settings = cfg.settings  # the Config instance is private to this object: no second copy needed
+        self.specs = cfg.specs
+        self.fiducialcosmopars = dict(cfg.fiducialparams)
         self.fiducialparams = self.fiducialcosmopars
         self.fiducialcosmo = cfg.fiducialcosmo
-        self.photopars = copy.deepcopy(cfg.photoparams)
-        self.photobiaspars = copy.deepcopy(cfg.Photobiasparams)
-        self.IApars = copy.deepcopy(cfg.IAparams)
-        self.Spectrobiaspars = copy.deepcopy(cfg.Spectrobiasparams)
+        self.photopars = dict(cfg.photoparams)
+        self.photobiaspars = dict(cfg.Photobiasparams)
+        self.IApars = dict(cfg.IAparams)
+        self.Spectrobiaspars = dict(cfg.Spectrobiasparams)
         self.Spectrobiasparams = self.Spectrobiaspars
-        self.Spectrononlinpars = copy.deepcopy(cfg.Spectrononlinearparams)
+        self.Spectrononlinpars = dict(cfg.Spectrononlinearparams)
         self.Spectrononlinearparams = self.Spectrononlinpars
-        self.IMbiaspars = copy.deepcopy(cfg.IMbiasparams)
+        self.IMbiaspars = dict(cfg.IMbiasparams)
         self.IMbiasparams = self.IMbiaspars
-        self.PShotpars = copy.deepcopy(cfg.PShotparams)
+        self.PShotpars = dict(cfg.PShotparams)
         self.PShotparams = self.PShotpars
-        self.observables = copy.deepcopy(cfg.obs)
+        self.observables = list(cfg.obs)
         self.obs = self.observables
         self.input_type = cfg.input_type
         self.external = cfg.external
-        self.freeparams = copy.deepcopy(cfg.freeparams)
+        self.freeparams = dict(cfg.freeparams)
         self.latex_names = cfg.latex_names
         allpars = {}
         for d in (self.fiducialcosmopars, self.photobiaspars, self.photopars, self.IApars, self.Spectrobiaspars,

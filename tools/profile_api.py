@@ -38,6 +38,25 @@ def main():
     step("both")
     step("both")
     buf = io.StringIO()
+    # wall-clock phases (no profiler): constructor | host preparation of the job | H2D + kernels + D2H | file export
+    for which, make in (("photo", bench.make_photo_fm), ("spectro", bench.make_spectro_fm)):
+        acc = {"ctor": 0.0, "host_prep": 0.0, "device": 0.0, "export": 0.0, "close": 0.0}
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fm = make(bank, tmp)
+            t1 = time.perf_counter()
+            fm.compute()
+            t2 = time.perf_counter()
+            job = fm.photo_LSS._job if which == "photo" else fm._spectro_job
+            job.close()
+            job.cosmo_set.bank().close()
+            t3 = time.perf_counter()
+            acc["ctor"] += t1 - t0
+            acc["host_prep"] += fm.timings["host_prep_s"]
+            acc["device"] += fm.timings["device_s"]
+            acc["export"] += (t2 - t1) - fm.timings["compute_s"]
+            acc["close"] += t3 - t2
+        buf.write(f"==== {which} phases, ms per forecast: " + ", ".join(f"{k} {1e3 * v / n:.2f}" for k, v in acc.items()) + "\n")
     for which in ("photo", "spectro"):
         t0 = time.perf_counter()
         for _ in range(n):
