@@ -438,7 +438,7 @@ def run_gpu(args):
         jp.close()
         js.close()
         p1, p2 = jp.plan(), js.plan()
-        p1.run()
+        p1.run(stream=ctx.aux_stream)  # the two probes are independent: second stream of the context
         p2.run()
         p1.fetch()
         p2.fetch()

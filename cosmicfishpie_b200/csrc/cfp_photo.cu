@@ -649,10 +649,15 @@ struct cfp_photo_plan {
   bool ran = false;
   cudaStream_t last_st = nullptr;  // stream of the most recent run (the pool releases on the context stream)
   cudaEvent_t kev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // begin / end of this plan's most recent run or chi2 call, on the stream it ran on: fetch waits on run1 (plans of
+  // one context may run concurrently on different streams, a context-wide event would be the wrong one)
+  cudaEvent_t run0 = nullptr, run1 = nullptr;
   std::vector<void*> owned;
 };
 
 static void photo_free(cfp_photo_plan* p) {
+  if (p->run0) cudaEventDestroy(p->run0);
+  if (p->run1) cudaEventDestroy(p->run1);
   for (auto& e : p->kev)
     if (e) cudaEventDestroy(e);
   for (void* q : p->owned) cfp_dev_free(p->ctx, q);
@@ -882,12 +887,16 @@ extern "C" int cfp_photo_plan_run(cfp_photo_plan* pl, void* stream) {
   cfp_ctx* ctx = pl->ctx;
   CFP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  CFP_CUDA(cudaEventRecord(ctx->ev0, st));
+  if (!pl->run0) {
+    CFP_CUDA(cudaEventCreate(&pl->run0));
+    CFP_CUDA(cudaEventCreate(&pl->run1));
+  }
+  CFP_CUDA(cudaEventRecord(pl->run0, st));
   int rc = photo_run_cls(pl, st, false);
   if (rc != CFP_OK) return rc;
   rc = photo_run_fisher(pl, st);
   if (rc != CFP_OK) return rc;
-  CFP_CUDA(cudaEventRecord(ctx->ev1, st));
+  CFP_CUDA(cudaEventRecord(pl->run1, st));
   pl->ran = true;
   return CFP_OK;
 }
@@ -1046,7 +1055,11 @@ extern "C" int cfp_photo_plan_chi2(cfp_photo_plan* pl, const double* data_h, int
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S * Nl * nblk, &q_d));
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d));
   if (st != ctx->stream) cudaStreamSynchronize(ctx->stream);  // uploads ran on the context stream
-  cudaEventRecord(ctx->ev0, st);
+  if (!pl->run0) {
+    cudaEventCreate(&pl->run0);
+    cudaEventCreate(&pl->run1);
+  }
+  cudaEventRecord(pl->run0, st);
   CHI_TRY(photo_run_cls(pl, st, true));
   if (!data_h) {
     photo_add_noise_kernel<<<(Nl * Nb * Nb + 255) / 256, 256, 0, st>>>(Nl, Nb, pl->cls_d, pl->noise_d, data_d);
@@ -1079,12 +1092,12 @@ extern "C" int cfp_photo_plan_chi2(cfp_photo_plan* pl, const double* data_h, int
     photo_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Nl, nblk, q_d, w_d, chi2_d);
     ctx->launches++;
   }
-  cudaEventRecord(ctx->ev1, st);
+  cudaEventRecord(pl->run1, st);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(chi2_h, chi2_d, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   float ms = 0.f;
-  if (e == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+  if (e == cudaSuccess && cudaEventElapsedTime(&ms, pl->run0, pl->run1) == cudaSuccess) ctx->last_ms = ms;
   cfp_dev_free(ctx, zero_d);
   cfp_dev_free(ctx, lb_d);
   cleanup();
@@ -1116,9 +1129,9 @@ extern "C" int cfp_photo_plan_fetch(cfp_photo_plan* pl, double* fisher_h, double
   }
   cfp_ctx* ctx = pl->ctx;
   CFP_CUDA(cudaSetDevice(ctx->device));
-  CFP_CUDA(cudaEventSynchronize(ctx->ev1));
+  CFP_CUDA(cudaEventSynchronize(pl->run1));
   float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+  if (cudaEventElapsedTime(&ms, pl->run0, pl->run1) == cudaSuccess) ctx->last_ms = ms;
   if (fisher_h)
     CFP_CUDA(cudaMemcpy(fisher_h, pl->fisher_d, (size_t)pl->npar * pl->npar * sizeof(double), cudaMemcpyDeviceToHost));
   if (cls_h)

@@ -945,10 +945,15 @@ struct cfp_spectro_plan {
   bool ran = false;
   cudaStream_t last_st = nullptr;  // stream of the most recent run (the pool releases on the context stream)
   cudaEvent_t kev0 = nullptr, kev1 = nullptr;
+  // begin / end of this plan's most recent run or chi2 call, on the stream it ran on: fetch waits on run1 (plans of
+  // one context may run concurrently on different streams, a context-wide event would be the wrong one)
+  cudaEvent_t run0 = nullptr, run1 = nullptr;
   std::vector<void*> owned;
 };
 
 static void spectro_free(cfp_spectro_plan* p) {
+  if (p->run0) cudaEventDestroy(p->run0);
+  if (p->run1) cudaEventDestroy(p->run1);
   if (p->kev0) cudaEventDestroy(p->kev0);
   if (p->kev1) cudaEventDestroy(p->kev1);
   for (void* q : p->owned) cfp_dev_free(p->ctx, q);
@@ -1209,7 +1214,11 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S * Z * gx, &part_d));
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d));
   if (st != ctx->stream) cudaStreamSynchronize(ctx->stream);
-  cudaEventRecord(ctx->ev0, st);
+  if (!pl->run0) {
+    cudaEventCreate(&pl->run0);
+    cudaEventCreate(&pl->run1);
+  }
+  cudaEventRecord(pl->run0, st);
   SpectroParams P;
   spectro_fill_params(pl, 16, P);
   CHI_TRY(spectro_prepare(pl, P, st));
@@ -1226,12 +1235,12 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
   }
   spectro_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Z * gx, part_d, chi2_d);
   ctx->launches++;
-  cudaEventRecord(ctx->ev1, st);
+  cudaEventRecord(pl->run1, st);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(chi2_h, chi2_d, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   float ms = 0.f;
-  if (e == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+  if (e == cudaSuccess && cudaEventElapsedTime(&ms, pl->run0, pl->run1) == cudaSuccess) ctx->last_ms = ms;
   cleanup();
 #undef CHI_TRY
   if (e != cudaSuccess) {
@@ -1276,7 +1285,11 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
   // pool allocations are ordered on the context stream; a caller's stream must not start before them
   if (allocated && st != ctx->stream) CFP_CUDA(cudaStreamSynchronize(ctx->stream));
   pl->last_st = st;
-  CFP_CUDA(cudaEventRecord(ctx->ev0, st));
+  if (!pl->run0) {
+    CFP_CUDA(cudaEventCreate(&pl->run0));
+    CFP_CUDA(cudaEventCreate(&pl->run1));
+  }
+  CFP_CUDA(cudaEventRecord(pl->run0, st));
   SpectroParams P;
   spectro_fill_params(pl, materialize, P);
   {
@@ -1315,7 +1328,7 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
   spectro_reduce_kernel<<<dim3(pl->Z, T * 2), 1024, 0, st>>>(pl->partial_d, gx, pl->nb, pl->npar, pl->fisher_d);
   ctx->launches++;
   CFP_CUDA(cudaGetLastError());
-  CFP_CUDA(cudaEventRecord(ctx->ev1, st));
+  CFP_CUDA(cudaEventRecord(pl->run1, st));
   pl->ran = true;
   return CFP_OK;
 }
@@ -1342,9 +1355,9 @@ extern "C" int cfp_spectro_plan_fetch(cfp_spectro_plan* pl, double* fisher_h, do
   }
   cfp_ctx* ctx = pl->ctx;
   CFP_CUDA(cudaSetDevice(ctx->device));
-  CFP_CUDA(cudaEventSynchronize(ctx->ev1));
+  CFP_CUDA(cudaEventSynchronize(pl->run1));
   float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+  if (cudaEventElapsedTime(&ms, pl->run0, pl->run1) == cudaSuccess) ctx->last_ms = ms;
   const size_t lattice = (size_t)pl->Nmu * pl->Nk;
   if (fisher_h)
     CFP_CUDA(cudaMemcpy(fisher_h, pl->fisher_d, (size_t)pl->Z * pl->npar * pl->npar * sizeof(double), cudaMemcpyDeviceToHost));

@@ -153,3 +153,27 @@ def test_spectro_slices_sum_to_full_fisher(spectro_fm):
         acc += plan.fetch()[0]
     plan.set_slice(0, ncell)
     assert np.max(np.abs(acc - full)) <= 1e-11 * np.max(np.abs(full))
+
+
+def test_two_plans_on_two_streams(spectro_fm, extfiles, tmp_path):
+    """Plans of one context running concurrently on the context's two streams: each fetch waits for its own plan and
+    returns what the serial run returns."""
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    o = base_options(tmp_path, survey_name_photo="Euclid-Photometric-ISTF-Pessimistic", survey_name_spectro=False,
+                     ell_sampling=30)
+    photo_fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={p: 0.01 for p in P7[:3]}, options=o,
+                            observables=["WL", "GCph"], extfiles=extfiles)
+    photo_fm.compute()
+    pp, sp = photo_fm.photo_LSS._job.plan(), spectro_fm._spectro_job.plan()
+    assert pp.ctx is sp.ctx
+    pp.run()
+    sp.run()
+    want_p, want_s = pp.fetch()[0], sp.fetch()[0]
+    for _ in range(5):
+        sp.run()                          # the long lattice kernel first, on the context stream
+        pp.run(stream=pp.ctx.aux_stream)  # the short photometric kernels on the second stream
+        got_p = pp.fetch()[0]             # must wait for pp, not for whichever plan ran last on the context
+        got_s = sp.fetch()[0]
+        assert np.array_equal(got_p, want_p) and np.array_equal(got_s, want_s)
