@@ -430,7 +430,7 @@ def run_gpu(args):
     like_photo = like_block(Lp, kp, fm_ph.allparams, 16384, 0.02)
     Ls = SpectroLikelihood(cosmoFM_data=fm_sp)
     ks = [k for k in fm_sp.freeparams if k.startswith("lnbg")]
-    like_spectro = like_block(Ls, ks, fm_sp.allparams, 256, 0.01)
+    like_spectro = like_block(Ls, ks, fm_sp.allparams, 2048, 0.01)
 
     # ---- C ABI only: plan_create from host buffers + run + fetch -------------------------------------
     def cabi_step():

@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "cfp_common.cuh"
 
@@ -820,30 +821,50 @@ __global__ void __launch_bounds__(TILE, 3) spectro_data_kernel(SpectroParams P, 
   }
 }
 
-// grid (gx, Z, S): partial[s][zb][cta] = sum over this CTA's cells of w (P_d - P_t)^2 / P_d^2.
+// Wedge chi^2 of a batch of points.  grid (gx, chunks): a chunk is up to CHI_CH points of ONE bin whose scalar blocks
+// differ only in the galaxy bias (a sampler that draws nuisance parameters around cosmologies of the bank produces
+// exactly that): the table look-ups, exp and FoG of a cell are evaluated once per chunk -- X = (b q + F)^2 W, see
+// eval_x -- and each member point costs a handful of FP64 operations.
+// partial[s][zb][cta] = sum over this CTA's cells of w (P_d - P_t)^2 / P_d^2.
 // A CTA owns blocks of TILE consecutive k and walks DOWN the mu rows of each block: along a column k' = k G(mu)
 // drifts by a fraction of a piece per step, so the piece hints of the three tables stay valid, loads of the data
-// lattice stay coalesced, and the row constants of the point (staged once per CTA) are broadcast reads.
+// lattice stay coalesced, and the row constants of the chunk (staged once per CTA) are broadcast reads.
 constexpr int CHI_ROWS = 256;  // mu rows staged at a time (12 KB of RowC + 2 KB of row weights)
-__global__ void __launch_bounds__(TILE, 5) spectro_chi2_kernel(SpectroParams P, const double* __restrict__ data,
-                                                               const double* __restrict__ shot, int s_begin,
+constexpr int CHI_CH = 8;      // points per chunk (one accumulator each in registers)
+__global__ void __launch_bounds__(TILE, 4) spectro_chi2_kernel(SpectroParams P, const double* __restrict__ data,
+                                                               const double* __restrict__ shot,
+                                                               const int* __restrict__ ch_zb,
+                                                               const int* __restrict__ ch_off,
+                                                               const int* __restrict__ ch_cnt,
+                                                               const int* __restrict__ mem_s,
                                                                double* __restrict__ partial) {
   __shared__ SDev sp;
   __shared__ RowC rows[CHI_ROWS];
   __shared__ double wrow[CHI_ROWS];
-  __shared__ double red[TILE / 32];
+  __shared__ double red[CHI_CH][TILE / 32];
+  __shared__ double mb[CHI_CH], mx[CHI_CH];  // bias and additive noise of the member points
+  __shared__ int ms[CHI_CH];
   __shared__ MathTab mt;
-  const int zb = blockIdx.y, s = s_begin + blockIdx.z, tid = threadIdx.x;
+  const int tid = threadIdx.x;
+  const int zb = ch_zb[blockIdx.y], off = ch_off[blockIdx.y], cnt = ch_cnt[blockIdx.y];
+  const int s0 = mem_s[off];  // representative: every member shares its block except the bias
   if (tid < (int)(sizeof(SDev) / sizeof(double)))
-    reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S + s)[tid];
+    reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S + s0)[tid];
   math_tables_fill(mt, tid, TILE);
   __syncthreads();
+  if (tid < CHI_CH) {
+    const int sj = mem_s[off + min(tid, cnt - 1)];
+    ms[tid] = sj;
+    mb[tid] = P.sdev[(size_t)zb * P.S + sj].bias;
+    mx[tid] = 1.0 / P.nbar[zb] + shot[(size_t)sj * P.Z + zb] + sp.pshot;
+  }
   const int64_t lattice = (int64_t)P.Nmu * P.Nk;
-  const double extra = 1.0 / P.nbar[zb] + shot[(size_t)s * P.Z + zb] + sp.pshot;
   const double pref = 2.0 * P.vol[zb] * INV_8PI2;  // spectro_like.py:162-178
   const double* __restrict__ dz = data + (size_t)zb * lattice;
   const int nkb = (P.Nk + TILE - 1) / TILE;
-  double acc = 0.0;
+  double acc[CHI_CH];
+#pragma unroll
+  for (int j = 0; j < CHI_CH; ++j) acc[j] = 0.0;
   for (int r0 = 0; r0 < P.Nmu; r0 += CHI_ROWS) {
     const int nr = min(CHI_ROWS, P.Nmu - r0);
     __syncthreads();
@@ -859,27 +880,37 @@ __global__ void __launch_bounds__(TILE, 5) spectro_chi2_kernel(SpectroParams P, 
       const double wcol = __ldg(P.wk + ki) * (k * k);
       const double* __restrict__ dcol = dz + (size_t)r0 * P.Nk + ki;
       int hA = -1, hB = -1, hN = -1;
-      double colsum = 0.0;
       for (int r = 0; r < nr; ++r) {
         const double Pd = __ldg(dcol + (size_t)r * P.Nk);
-        double err2;
-        const double X = eval_x(mt, sp, rows[r], P.flags, k, hA, hB, hN, err2);
-        const double Pt = fma(X, tab_exp_neg(mt, -err2), extra);
-        const double q = (Pd - Pt) * fast_rcp(Pd);
-        colsum = fma(wrow[r], q * q, colsum);
+        double err2, qf, F, W;
+        eval_x(mt, sp, rows[r], P.flags, k, hA, hB, hN, err2, qf, F, W);
+        const double We = W * tab_exp_neg(mt, -err2);
+        const double rPd = fast_rcp(Pd);
+        const double w = wrow[r] * wcol;
+#pragma unroll
+        for (int j = 0; j < CHI_CH; ++j)
+          if (j < cnt) {
+            const double kaiser = fma(mb[j], qf, F);
+            const double Pt = fma(kaiser * kaiser, We, mx[j]);
+            const double q = (Pd - Pt) * rPd;
+            acc[j] = fma(w, q * q, acc[j]);
+          }
       }
-      acc = fma(wcol, colsum, acc);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((tid & 31) == 0) red[tid >> 5] = acc;
+  for (int j = 0; j < CHI_CH; ++j) {
+    double a = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((tid & 31) == 0) red[j][tid >> 5] = a;
+  }
   __syncthreads();
-  if (tid == 0) {
+  if (tid < cnt) {
     double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < TILE / 32; ++w) t += red[w];
-    partial[((size_t)s * P.Z + zb) * gridDim.x + blockIdx.x] = t;
+    for (int w = 0; w < TILE / 32; ++w) t += red[tid][w];
+    partial[((size_t)ms[tid] * P.Z + zb) * gridDim.x + blockIdx.x] = t;
   }
 }
 
@@ -944,6 +975,7 @@ struct cfp_spectro_plan {
   double *lnp_d = nullptr, *derivs_d = nullptr, *veff_d = nullptr;
   bool ran = false;
   cudaStream_t last_st = nullptr;  // stream of the most recent run (the pool releases on the context stream)
+  std::vector<double> scal_h;      // host copy of the scalar blocks (the likelihood groups points by them)
   cudaEvent_t kev0 = nullptr, kev1 = nullptr;
   // begin / end of this plan's most recent run or chi2 call, on the stream it ran on: fetch waits on run1 (plans of
   // one context may run concurrently on different streams, a context-wide event would be the wrong one)
@@ -1059,6 +1091,7 @@ extern "C" int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S
   SP_UP(double, wk_h, (size_t)Nk, pl->wk_d);
   SP_UP(double, wmu_h, (size_t)Nmu, pl->wmu_d);
   SP_UP(double, scal_h, (size_t)S * Z * CFP_SP_NSCAL, pl->scal_d);
+  pl->scal_h.assign(scal_h, scal_h + (size_t)S * Z * CFP_SP_NSCAL);
   SP_UP(int, alias_h, (size_t)S * Z, pl->alias_d);
   SP_UP(double, pnw_k_h, (size_t)NC * nnw, pl->pnw_k_d);
   SP_UP(double, pnw_p_h, (size_t)NC * Z * nnw, pl->pnw_p_d);
@@ -1181,23 +1214,74 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
   const int S = pl->S, Z = pl->Z;
   const size_t lattice = (size_t)pl->Nmu * pl->Nk;
   const int64_t ntile = (int64_t)((lattice + TILE - 1) / TILE);
-  // CTAs per (point, bin): each takes every gx-th block of TILE wavenumbers.  Pick the split that needs the
-  // fewest (waves of resident CTAs) x (blocks per CTA), i.e. fills the GPU for small batches and avoids a
-  // ragged last wave for large ones.
+  // Chunks: per bin, points whose scalar blocks are identical except for the bias are evaluated together (up to
+  // CHI_CH per chunk).  Grouping by a hash of the block bytes, verified against the group's representative.
+  std::vector<int> ch_zb, ch_off, ch_cnt, mem_s;
+  {
+    const double* sc = pl->scal_h.data();
+    auto key_equal = [&](int a, int b, int zb) {
+      const double* x = sc + ((size_t)a * Z + zb) * CFP_SP_NSCAL;
+      const double* y = sc + ((size_t)b * Z + zb) * CFP_SP_NSCAL;
+      for (int q = 0; q < CFP_SP_NSCAL; ++q)
+        if (q != CFP_SP_BIAS && std::memcmp(x + q, y + q, sizeof(double)) != 0) return false;
+      return true;
+    };
+    std::vector<std::pair<uint64_t, int>> order(S);
+    for (int zb = 0; zb < Z; ++zb) {
+      for (int sidx = 0; sidx < S; ++sidx) {
+        const double* x = sc + ((size_t)sidx * Z + zb) * CFP_SP_NSCAL;
+        uint64_t h = 1469598103934665603ull;  // FNV-1a over the 8-byte words of the block, bias excluded
+        for (int q = 0; q < CFP_SP_NSCAL; ++q) {
+          if (q == CFP_SP_BIAS) continue;
+          uint64_t w;
+          std::memcpy(&w, x + q, sizeof(w));
+          h = (h ^ w) * 1099511628211ull;
+        }
+        order[sidx] = {h, sidx};
+      }
+      std::sort(order.begin(), order.end());
+      int i = 0;
+      while (i < S) {
+        // members of the hash run that really equal its first element form one group; the others (collisions,
+        // never seen in practice) become singletons
+        const int rep = order[i].second;
+        int j = i;
+        std::vector<int> same, other;
+        while (j < S && order[j].first == order[i].first) {
+          (key_equal(order[j].second, rep, zb) ? same : other).push_back(order[j].second);
+          ++j;
+        }
+        for (size_t o = 0; o < same.size(); o += CHI_CH) {
+          ch_zb.push_back(zb), ch_off.push_back((int)mem_s.size());
+          ch_cnt.push_back((int)std::min<size_t>(CHI_CH, same.size() - o));
+          mem_s.insert(mem_s.end(), same.begin() + o, same.begin() + o + ch_cnt.back());
+        }
+        for (int sidx : other) ch_zb.push_back(zb), ch_off.push_back((int)mem_s.size()), ch_cnt.push_back(1), mem_s.push_back(sidx);
+        i = j;
+      }
+    }
+  }
+  const int nch = (int)ch_zb.size();
+  // CTAs per chunk: each takes every gx-th block of TILE wavenumbers.  Pick the split that needs the fewest
+  // (waves of resident CTAs) x (blocks per CTA), i.e. fills the GPU for small batches and avoids a ragged last wave
+  // for large ones.
   const int nkb = (pl->Nk + TILE - 1) / TILE;
   int gx = 1;
   {
-    const int64_t slots = 5 * (int64_t)ctx->sm_count;  // spectro_chi2_kernel: 5 resident CTAs per SM
+    const int64_t slots = 4 * (int64_t)ctx->sm_count;  // spectro_chi2_kernel: 4 resident CTAs per SM
     int64_t best = INT64_MAX;
     for (int g = 1; g <= std::min(nkb, 64); ++g) {
-      const int64_t ctas = (int64_t)g * S * Z;
+      const int64_t ctas = (int64_t)g * nch;
       const int64_t cost = ((ctas + slots - 1) / slots) * ((nkb + g - 1) / g);
       if (cost < best) best = cost, gx = g;
     }
   }
+  int *ch_zb_d = nullptr, *ch_off_d = nullptr, *ch_cnt_d = nullptr, *mem_s_d = nullptr;
   double *data_d = nullptr, *shot_d = nullptr, *sd_d = nullptr, *part_d = nullptr, *chi2_d = nullptr;
   auto cleanup = [&]() {
-    for (void* q : {(void*)data_d, (void*)shot_d, (void*)sd_d, (void*)part_d, (void*)chi2_d}) cfp_dev_free(ctx, q);
+    for (void* q : {(void*)data_d, (void*)shot_d, (void*)sd_d, (void*)part_d, (void*)chi2_d, (void*)ch_zb_d, (void*)ch_off_d,
+                    (void*)ch_cnt_d, (void*)mem_s_d})
+      cfp_dev_free(ctx, q);
   };
   int rc;
 #define CHI_TRY(x)      \
@@ -1213,7 +1297,11 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
   if (shot_data_h) CHI_TRY(cfp_upload(ctx, shot_data_h, (size_t)Z, &sd_d));
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S * Z * gx, &part_d));
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d));
-  if (st != ctx->stream) cudaStreamSynchronize(ctx->stream);
+  CHI_TRY(cfp_upload(ctx, ch_zb.data(), ch_zb.size(), &ch_zb_d));
+  CHI_TRY(cfp_upload(ctx, ch_off.data(), ch_off.size(), &ch_off_d));
+  CHI_TRY(cfp_upload(ctx, ch_cnt.data(), ch_cnt.size(), &ch_cnt_d));
+  CHI_TRY(cfp_upload(ctx, mem_s.data(), mem_s.size(), &mem_s_d));
+  CFP_CUDA(cudaStreamSynchronize(ctx->stream));  // the chunk lists are host temporaries
   if (!pl->run0) {
     cudaEventCreate(&pl->run0);
     cudaEventCreate(&pl->run1);
@@ -1228,9 +1316,10 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
     ctx->launches++;
   }
   const double* data_use = data_dev ? data_dev : data_d;
-  for (int s0 = 0; s0 < S; s0 += 32768) {
-    const int ns = std::min(32768, S - s0);
-    spectro_chi2_kernel<<<dim3(gx, Z, ns), TILE, 0, st>>>(P, data_use, shot_d, s0, part_d);
+  for (int c0 = 0; c0 < nch; c0 += 65535) {
+    const int nc = std::min(65535, nch - c0);
+    spectro_chi2_kernel<<<dim3(gx, nc), TILE, 0, st>>>(P, data_use, shot_d, ch_zb_d + c0, ch_off_d + c0, ch_cnt_d + c0,
+                                                      mem_s_d, part_d);
     ctx->launches++;
   }
   spectro_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Z * gx, part_d, chi2_d);
