@@ -830,8 +830,10 @@ __global__ void __launch_bounds__(TILE, 3) spectro_data_kernel(SpectroParams P, 
 // drifts by a fraction of a piece per step, so the piece hints of the three tables stay valid, loads of the data
 // lattice stay coalesced, and the row constants of the chunk (staged once per CTA) are broadcast reads.
 constexpr int CHI_ROWS = 256;  // mu rows staged at a time (12 KB of RowC + 2 KB of row weights)
-constexpr int CHI_CH = 8;      // points per chunk (one accumulator each in registers)
-__global__ void __launch_bounds__(TILE, 4) spectro_chi2_kernel(SpectroParams P, const double* __restrict__ data,
+constexpr int CHI_CH = 16;     // points per chunk of a group (one accumulator each in registers)
+// CH = 1 (points that share their block with nobody: 5 CTAs/SM) or CHI_CH (3 CTAs/SM)
+template <int CH, int MINB>
+__global__ void __launch_bounds__(TILE, MINB) spectro_chi2_kernel(SpectroParams P, const double* __restrict__ data,
                                                                const double* __restrict__ shot,
                                                                const int* __restrict__ ch_zb,
                                                                const int* __restrict__ ch_off,
@@ -841,9 +843,9 @@ __global__ void __launch_bounds__(TILE, 4) spectro_chi2_kernel(SpectroParams P, 
   __shared__ SDev sp;
   __shared__ RowC rows[CHI_ROWS];
   __shared__ double wrow[CHI_ROWS];
-  __shared__ double red[CHI_CH][TILE / 32];
-  __shared__ double mb[CHI_CH], mx[CHI_CH];  // bias and additive noise of the member points
-  __shared__ int ms[CHI_CH];
+  __shared__ double red[CH][TILE / 32];
+  __shared__ double mb[CH], mx[CH];  // bias and additive noise of the member points
+  __shared__ int ms[CH];
   __shared__ MathTab mt;
   const int tid = threadIdx.x;
   const int zb = ch_zb[blockIdx.y], off = ch_off[blockIdx.y], cnt = ch_cnt[blockIdx.y];
@@ -852,7 +854,7 @@ __global__ void __launch_bounds__(TILE, 4) spectro_chi2_kernel(SpectroParams P, 
     reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S + s0)[tid];
   math_tables_fill(mt, tid, TILE);
   __syncthreads();
-  if (tid < CHI_CH) {
+  if (tid < CH) {
     const int sj = mem_s[off + min(tid, cnt - 1)];
     ms[tid] = sj;
     mb[tid] = P.sdev[(size_t)zb * P.S + sj].bias;
@@ -862,9 +864,9 @@ __global__ void __launch_bounds__(TILE, 4) spectro_chi2_kernel(SpectroParams P, 
   const double pref = 2.0 * P.vol[zb] * INV_8PI2;  // spectro_like.py:162-178
   const double* __restrict__ dz = data + (size_t)zb * lattice;
   const int nkb = (P.Nk + TILE - 1) / TILE;
-  double acc[CHI_CH];
+  double acc[CH];
 #pragma unroll
-  for (int j = 0; j < CHI_CH; ++j) acc[j] = 0.0;
+  for (int j = 0; j < CH; ++j) acc[j] = 0.0;
   for (int r0 = 0; r0 < P.Nmu; r0 += CHI_ROWS) {
     const int nr = min(CHI_ROWS, P.Nmu - r0);
     __syncthreads();
@@ -888,7 +890,7 @@ __global__ void __launch_bounds__(TILE, 4) spectro_chi2_kernel(SpectroParams P, 
         const double rPd = fast_rcp(Pd);
         const double w = wrow[r] * wcol;
 #pragma unroll
-        for (int j = 0; j < CHI_CH; ++j)
+        for (int j = 0; j < CH; ++j)
           if (j < cnt) {
             const double kaiser = fma(mb[j], qf, F);
             const double Pt = fma(kaiser * kaiser, We, mx[j]);
@@ -899,7 +901,7 @@ __global__ void __launch_bounds__(TILE, 4) spectro_chi2_kernel(SpectroParams P, 
     }
   }
 #pragma unroll
-  for (int j = 0; j < CHI_CH; ++j) {
+  for (int j = 0; j < CH; ++j) {
     double a = acc[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -1216,7 +1218,7 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
   const int64_t ntile = (int64_t)((lattice + TILE - 1) / TILE);
   // Chunks: per bin, points whose scalar blocks are identical except for the bias are evaluated together (up to
   // CHI_CH per chunk).  Grouping by a hash of the block bytes, verified against the group's representative.
-  std::vector<int> ch_zb, ch_off, ch_cnt, mem_s;
+  std::vector<int> ch_zb, ch_off, ch_cnt, mem_s, one_zb, one_off;
   {
     const double* sc = pl->scal_h.data();
     auto key_equal = [&](int a, int b, int zb) {
@@ -1252,26 +1254,35 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
           ++j;
         }
         for (size_t o = 0; o < same.size(); o += CHI_CH) {
-          ch_zb.push_back(zb), ch_off.push_back((int)mem_s.size());
-          ch_cnt.push_back((int)std::min<size_t>(CHI_CH, same.size() - o));
-          mem_s.insert(mem_s.end(), same.begin() + o, same.begin() + o + ch_cnt.back());
+          const int c = (int)std::min<size_t>(CHI_CH, same.size() - o);
+          auto& Z_ = c == 1 ? one_zb : ch_zb;
+          auto& O_ = c == 1 ? one_off : ch_off;
+          Z_.push_back(zb), O_.push_back((int)mem_s.size());
+          if (c > 1) ch_cnt.push_back(c);
+          mem_s.insert(mem_s.end(), same.begin() + o, same.begin() + o + c);
         }
-        for (int sidx : other) ch_zb.push_back(zb), ch_off.push_back((int)mem_s.size()), ch_cnt.push_back(1), mem_s.push_back(sidx);
+        for (int sidx : other) one_zb.push_back(zb), one_off.push_back((int)mem_s.size()), mem_s.push_back(sidx);
         i = j;
       }
     }
   }
-  const int nch = (int)ch_zb.size();
+  // chunk list = [groups of 2..CHI_CH points | single points]; the two parts run as two launches
+  const int n_grp = (int)ch_zb.size(), n_one = (int)one_zb.size();
+  ch_zb.insert(ch_zb.end(), one_zb.begin(), one_zb.end());
+  ch_off.insert(ch_off.end(), one_off.begin(), one_off.end());
+  ch_cnt.insert(ch_cnt.end(), (size_t)n_one, 1);
+  const int nch = n_grp + n_one;
   // CTAs per chunk: each takes every gx-th block of TILE wavenumbers.  Pick the split that needs the fewest
   // (waves of resident CTAs) x (blocks per CTA), i.e. fills the GPU for small batches and avoids a ragged last wave
   // for large ones.
   const int nkb = (pl->Nk + TILE - 1) / TILE;
   int gx = 1;
   {
-    const int64_t slots = 4 * (int64_t)ctx->sm_count;  // spectro_chi2_kernel: 4 resident CTAs per SM
+    // resident CTAs: 3 per SM for the group kernel, 5 for the single-point kernel
+    const int64_t slots = (n_grp >= n_one ? 3 : 5) * (int64_t)ctx->sm_count;
     int64_t best = INT64_MAX;
     for (int g = 1; g <= std::min(nkb, 64); ++g) {
-      const int64_t ctas = (int64_t)g * nch;
+      const int64_t ctas = (int64_t)g * std::max(n_grp, n_one);
       const int64_t cost = ((ctas + slots - 1) / slots) * ((nkb + g - 1) / g);
       if (cost < best) best = cost, gx = g;
     }
@@ -1316,10 +1327,16 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
     ctx->launches++;
   }
   const double* data_use = data_dev ? data_dev : data_d;
-  for (int c0 = 0; c0 < nch; c0 += 65535) {
+  for (int c0 = 0; c0 < n_grp; c0 += 65535) {
+    const int nc = std::min(65535, n_grp - c0);
+    spectro_chi2_kernel<CHI_CH, 3><<<dim3(gx, nc), TILE, 0, st>>>(P, data_use, shot_d, ch_zb_d + c0, ch_off_d + c0,
+                                                                 ch_cnt_d + c0, mem_s_d, part_d);
+    ctx->launches++;
+  }
+  for (int c0 = n_grp; c0 < nch; c0 += 65535) {
     const int nc = std::min(65535, nch - c0);
-    spectro_chi2_kernel<<<dim3(gx, nc), TILE, 0, st>>>(P, data_use, shot_d, ch_zb_d + c0, ch_off_d + c0, ch_cnt_d + c0,
-                                                      mem_s_d, part_d);
+    spectro_chi2_kernel<1, 5><<<dim3(gx, nc), TILE, 0, st>>>(P, data_use, shot_d, ch_zb_d + c0, ch_off_d + c0,
+                                                            ch_cnt_d + c0, mem_s_d, part_d);
     ctx->launches++;
   }
   spectro_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Z * gx, part_d, chi2_d);
