@@ -103,6 +103,10 @@ F3 = {"Omegam": 0.01, "h": 0.01, "w0": 0.01}
     ("gcsp_var_dzdep", dict(SMALL), {"spec_sigma_dz_type": "z-dependent", "spec_sigma_dz": 0.001}, None),
     ("gcsp_var_nlcosmo", dict(SMALL, fix_cosmo_nl_terms=False), {}, None),
     ("gcsp_var_qbias", dict(SMALL), {}, "Euclid-Spectroscopic-ISTF-Pessimistic-Qbias"),
+    ("gcsp_var_sigmapv", dict(SMALL), {"nonlinear_parametrization": dict(
+        rescale_sigmap=True, rescale_sigmav=True, default=None,
+        rescale_sigma_pv={f"sigma{c}_{i}": 1.0 for c in "pv" for i in (1, 2, 3, 4)})},
+     "Euclid-Spectroscopic-ISTF-Pessimistic-sigma_pv"),
 ])
 def test_spectro_oracle_variants_bit_exact(obank, tag, settings, spec_over, yaml_name):
     from cosmicfishpie_b200 import toy_tables as tt
@@ -117,7 +121,12 @@ def test_spectro_oracle_variants_bit_exact(obank, tag, settings, spec_over, yaml
     fp = dict(F3)
     for k in list(bias) + list(ps):
         fp.setdefault(k, 1e-4)
-    r = spectro_fisher(obank, sp, settings, dict(tt.FIDUCIAL), bias, ps, {}, fp, max_z_bins=2, return_all=True)
+    nonlin = {}
+    if sp.get("nonlinear_model", "default") == "rescale_sigma_pv":  # config.py:722-732
+        nonlin = dict(sp["nonlinear_parametrization"]["rescale_sigma_pv"])
+        for k in nonlin:
+            fp.setdefault(k, 0.01)
+    r = spectro_fisher(obank, sp, settings, dict(tt.FIDUCIAL), bias, ps, nonlin, fp, max_z_bins=2, return_all=True)
     g = golden(tag)
     assert r["param_names"] == list(g["param_names"])
     assert np.array_equal(r["fisher"], g["fisher"])

@@ -28,6 +28,11 @@ CASES.update({
     "gcsp_var_nlcosmo": dict(free=F3, opts=dict(SMALL, fix_cosmo_nl_terms=False), mzb=2),
     "gcsp_var_qbias": dict(free=F3, opts=dict(SMALL, survey_name_spectro="Euclid-Spectroscopic-ISTF-Pessimistic-Qbias"),
                            mzb=2),
+    # per-bin rescaling of sigma_p / sigma_v as free parameters
+    "gcsp_var_sigmapv": dict(free=F3, opts=dict(SMALL, survey_name_spectro="Euclid-Spectroscopic-ISTF-Pessimistic-sigma_pv"),
+                             mzb=2, specs={"nonlinear_parametrization": dict(
+                                 rescale_sigmap=True, rescale_sigmav=True, default=None,
+                                 rescale_sigma_pv={f"sigma{c}_{i}": 1.0 for c in "pv" for i in (1, 2, 3, 4)})}),
 })
 
 

@@ -231,6 +231,12 @@ GCSP_VARIANTS = {
     "gcsp_var_dzdep": dict(options_extra=dict(SMALL), specifications={"spec_sigma_dz_type": "z-dependent", "spec_sigma_dz": 0.001}),
     "gcsp_var_nlcosmo": dict(options_extra=dict(SMALL, fix_cosmo_nl_terms=False)),
     "gcsp_var_qbias": dict(options_extra=dict(SMALL, specs_dir=MYSPECS), spectro_yaml="Euclid-Spectroscopic-ISTF-Pessimistic-Qbias"),
+    # per-bin rescaling of sigma_p and sigma_v as free parameters (reference's own sigma_pv specification): 19 parameters
+    # with max_z_bins=2 -> three 8-row blocks in the Gram kernel
+    "gcsp_var_sigmapv": dict(options_extra=dict(SMALL, specs_dir=MYSPECS), spectro_yaml="Euclid-Spectroscopic-ISTF-Pessimistic-sigma_pv",
+                             specifications={"nonlinear_parametrization": dict(
+                                 rescale_sigmap=True, rescale_sigmav=True, default=None,
+                                 rescale_sigma_pv={f"sigma{c}_{i}": 1.0 for c in "pv" for i in (1, 2, 3, 4)})}),
 }
 PHOTO_VARIANTS = {
     "photo_var_linear_pk": dict(obs=["WL", "GCph"], free={"Omegam": 0.01, "h": 0.01}, options_extra={"ell_sampling": 16, "nonlinear": False}),
