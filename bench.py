@@ -12,10 +12,14 @@ Boltzmann tables, cosmicfishpie_b200/toy_tables.py) in the reference's `external
 
 Numbers in the JSON line
   value      combined Fisher matrices / s with every input resident in HBM (plans uploaded, device timing by
-             CUDA events on the launch stream, L2 flushed between steps)
-  e2e        the same metric through the public API `FisherMatrix(...).compute()` from HOST tables: spline
-             fitting, per-job host preparation, H2D of the table bank and job arrays, kernels, D2H of the
-             Fisher matrices and file export are all inside the timed region (what a reference user times)
+             CUDA events on the launch stream, L2 flushed between steps); N GPUs: N independent forecasts per
+             step (weak scaling), `strong_scaling` = one forecast sharded over the GPUs + NCCL all-reduce.  The
+             two probes of a forecast run on two streams; the timed steps' results are checked against the API run
+  e2e        the same metric through the public API `FisherMatrix(...).compute()` from HOST tables: per-job host
+             preparation, pinned H2D of the table bank and job arrays, kernels, D2H of the Fisher matrices and
+             file export inside the timed region; the spline facades of the cached tables are reused between
+             steps (`e2e_cold` re-fits them every step, which is what the reference does per Fisher matrix)
+  likelihood batched log-likelihood evaluations / s through `loglike_batch` (photometric 3x2pt, spectroscopic wedges)
   cabi_e2e   through the C ABI only (cfp_*_plan_create from host buffers + run + fetch)
   roofline   dominant kernel (spectro_fisher_kernel) against the measured FP64 DFMA peak of this GPU; the
              HBM view of the API-preserving (materialising) mode is in `roofline_hbm`
