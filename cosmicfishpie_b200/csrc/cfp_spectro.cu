@@ -28,6 +28,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <math_constants.h>
+
 #include "cfp_common.cuh"
 
 namespace {
@@ -638,9 +640,11 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
       double lnP, Pobs = 0.0;
       if (fl & SD_PSHOT) {
         Pobs = X * tab_exp_neg(mt, -err2) + sp.pshot;
-        lnP = tab_log(mt, Pobs);
+        lnP = Pobs > 0.0 ? tab_log(mt, Pobs) : CUDART_NAN;
       } else {
-        lnP = tab_log(mt, X) - err2;
+        // a spectrum that is not positive (tables ending inside the lattice: the degree-1 no-wiggle spline
+        // extrapolates below zero) has no logarithm: NaN, as numpy gives the reference (spectro_obs.py:913-933)
+        lnP = X > 0.0 ? tab_log(mt, X) - err2 : CUDART_NAN;
         if (fl & SD_SRC) Pobs = X * tab_exp_neg(mt, -err2);
       }
       if (fl & SD_PSSRC) Psrc = Pobs;
