@@ -70,3 +70,26 @@ def test_photo_5pt_vs_oracle(bank3, tmp_path):
     assert list(F.get_param_names()) == ref["param_names"]
     scale = np.sqrt(np.outer(np.diag(ref["fisher"]), np.diag(ref["fisher"])))
     assert np.max(np.abs(F.fisher_matrix - ref["fisher"]) / scale) < 1e-8
+
+
+def test_photo_accuracy_2_vs_oracle(bank3, tmp_path):
+    """accuracy = 2 doubles the redshift and multipole sampling (400 z, 200 multipoles): other tile shapes in the
+    window, C_ell and Fisher kernels than any golden case."""
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+    from oracle.cosmo import Bank
+    from oracle.photo import default_photo_bias, finish_photo_specs, photo_fisher
+
+    o = base_options(tmp_path, accuracy=2, survey_name_photo="Euclid-Photometric-ISTF-Pessimistic", survey_name_spectro=False)
+    fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"Omegam": 0.01, "h": 0.01}, options=o,
+                      observables=["GCph"], extfiles=ext_of(bank3))
+    F = fm.compute()
+    assert fm.photo_LSS.grid.zsamp == 400 and fm.photo_LSS.grid.ellsamp == 200
+    sp = finish_photo_specs(yaml.safe_load(open(os.path.join(SPECDIR, "Euclid-Photometric-ISTF-Pessimistic.yaml")))["specifications"])
+    lum = np.load(os.path.join(REPO, "cosmicfishpie_b200", "data", "lumratio.npy"))
+    ob = Bank(bank3, tt.FIDUCIAL, tt.COSMO_KEYS, eps_values=EPS)
+    ref = photo_fisher(ob, sp, {"accuracy": 2}, ["GCph"], dict(tt.FIDUCIAL), dict(sp["photo_z_params"]), {},
+                       default_photo_bias(sp), dict(fm.config.freeparams), lum)
+    assert list(F.get_param_names()) == ref["param_names"]
+    scale = np.sqrt(np.outer(np.diag(ref["fisher"]), np.diag(ref["fisher"])))
+    assert np.max(np.abs(F.fisher_matrix - ref["fisher"]) / scale) < 1e-9
