@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libcfp_b200.so")
 # mirror of include/cfp_b200.h -----------------------------------------------------------------
 ABI_VERSION = 1
 BANK_DESC = 5
-TAB_PLIN, TAB_PNL, TAB_F, TAB_D, NTAB = 0, 1, 2, 3, 4
+TAB_PLIN, TAB_PNL, TAB_F, TAB_D, TAB_PLIN_CB, TAB_PNL_CB, TAB_F_CB, NTAB = 0, 1, 2, 3, 4, 5, 6, 7
 (SP_Z, SP_COSMO, SP_QPAR, SP_QPER, SP_HUBBLE, SP_DZ, SP_BIAS, SP_A1, SP_A2, SP_SIGMAP, SP_I0, SP_I1, SP_I2,
  SP_SVRESCALE, SP_FS8, SP_INVS8SQ, SP_KHFAC, SP_PSHOT, SP_NSCAL) = range(19)
 SPF_AP, SPF_FOG, SPF_LINEAR, SPF_KH_BEFORE_ERR = 1, 2, 4, 8

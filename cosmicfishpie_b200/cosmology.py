@@ -38,8 +38,14 @@ DEFAULT_FILE_NAMES = {  # config.py:289-304
     "s8_z": "sigma8-z",
     "z_arr": "z_values_list",
     "k_arr": "k_values_list",
+    "fcb_zk": "fcb_GrowthRate-zk",
+    "Plcb_zk": "Plincb-zk",
+    "Pnlcb_zk": "Pnonlincb-zk",
+    "s8cb_z": "sigma8cb-z",
 }
 _KEYMAP = {"z": "z_arr", "k": "k_arr", "H": "H_z", "s8": "s8_z", "D": "D_zk", "f": "f_zk", "Pl": "Pl_zk", "Pnl": "Pnl_zk"}
+# cold dark matter + baryon tables, read when GCsp_Tracer / GCph_Tracer is "clustering" (cosmology.py:1240-1245)
+_KEYMAP_CB = {"s8cb": "s8cb_z", "fcb": "fcb_zk", "Plcb": "Plcb_zk", "Pnlcb": "Pnlcb_zk"}
 
 
 def round_decimals_up(number: float) -> float:
@@ -74,17 +80,22 @@ def folder_for(cosmopars, fiducial, external) -> str:
 _TABLE_CACHE: Dict[tuple, dict] = {}
 
 
-def load_tables(external: dict, folder: str) -> dict:
-    """Raw arrays of one folder, cached per (source, folder)."""
+def load_tables(external: dict, folder: str, cb: bool = False) -> dict:
+    """Raw arrays of one folder, cached per (source, folder); `cb` adds the cdm+baryon tables."""
     if "tables" in external and external["tables"] is not None:
-        return external["tables"][folder]
-    key = (os.path.abspath(external["directory"]), folder)
+        t = external["tables"][folder]
+        if cb:
+            missing = [k for k in _KEYMAP_CB if k not in t]
+            if missing:
+                raise FileNotFoundError(f"tracer 'clustering' needs the cb tables {missing} in folder {folder}")
+        return t
+    key = (os.path.abspath(external["directory"]), folder, bool(cb))
     if key in _TABLE_CACHE:
         return _TABLE_CACHE[key]
     names = dict(DEFAULT_FILE_NAMES)
     names.update({k: v for k, v in (external.get("file_names") or {}).items() if v is not None})
     out = {}
-    for short, long in _KEYMAP.items():
+    for short, long in {**_KEYMAP, **(_KEYMAP_CB if cb else {})}.items():
         path = None
         for base in (folder, external.get("fiducial_folder", "fiducial_eps_0")):  # fiducial fallback for grids/H
             hits = glob.glob(os.path.join(external["directory"], base, names[long] + ".*"))
@@ -147,7 +158,8 @@ class cosmo_functions:
         self.cosmopars = cosmopars
         self.fiducialcosmopars = config.fiducialparams
         self.folder = folder_for(cosmopars, self.fiducialcosmopars, self.external)
-        t = load_tables(self.external, self.folder)
+        self.cb_files_on = "clustering" in (self.settings.get("GCsp_Tracer"), self.settings.get("GCph_Tracer"))
+        t = load_tables(self.external, self.folder, cb=self.cb_files_on)
         pkf = rf = kf = 1.0
         if self.external.get("k-units") == "h/Mpc":  # cosmology.py:1438-1444
             pkf = (1 / cosmopars["h"]) ** 3
@@ -171,6 +183,13 @@ class cosmo_functions:
             "Pk_nl": _LazySpline(zg, kg, pkf * np.asarray(t["Pnl"], float)),
         }
         self.s8_of_z = InterpolatedUnivariateSpline(zg, np.asarray(t["s8"], float).flatten())
+        if self.cb_files_on:  # cosmology.py:1508-1531
+            self._lazy.update({
+                "f_growthrate_cb_zk": _LazySpline(zg, kg, t["fcb"]),
+                "Pk_cb_l": _LazySpline(zg, kg, pkf * np.asarray(t["Plcb"], float)),
+                "Pk_cb_nl": _LazySpline(zg, kg, pkf * np.asarray(t["Pnlcb"], float)),
+            })
+            self.s8_cb_of_z = InterpolatedUnivariateSpline(zg, np.asarray(t["s8cb"], float).flatten())
         self.results = self  # reference code reaches splines through `.results`
         self._nw_cache = {}
 
@@ -214,19 +233,26 @@ class cosmo_functions:
         return self.com_dist(z)
 
     def matpow(self, z, k, nonlinear=False, tracer="matter"):
+        if tracer == "clustering":  # cosmology.py:1715-1716, 1741-1758
+            return (self.Pk_cb_nl if nonlinear else self.Pk_cb_l)(z, k, grid=False)
         return (self.Pk_nl if nonlinear else self.Pk_l)(z, k, grid=False)
 
     def f_growthrate(self, z, k=None, gamma=False, tracer="matter"):
+        if tracer == "clustering":  # cosmology.py:1937-1939
+            return self.f_growthrate_cb_zk(z, 0.0001 if k is None else k, grid=False)
         return self.f_growthrate_zk(z, 0.0001 if k is None else k, grid=False)
 
     def growth(self, z, k=None):
         return self.D_growth_zk(z, 0.0001 if k is None else k, grid=False)
 
     def sigma8_of_z(self, z, tracer="matter"):
-        return self.s8_of_z(z)
+        return self.s8_cb_of_z(z) if tracer == "clustering" else self.s8_of_z(z)  # cosmology.py:1851-1857
+
+    def sigma8_cb_of_z(self, z):
+        return self.s8_cb_of_z(z)
 
     def fsigma8_of_z(self, z, k=None, gamma=False, tracer="matter"):
-        return self.f_growthrate(z, k) * self.sigma8_of_z(z)
+        return self.f_growthrate(z, k, gamma, tracer=tracer) * self.sigma8_of_z(z, tracer=tracer)
 
     def Omegam_of_z(self, z):
         return (self.cosmopars["Omegam"] * (1 + z) ** 3) / self.E_hubble(z) ** 2
@@ -234,10 +260,10 @@ class cosmo_functions:
     def SigmaMG(self, z, k):
         return np.array(1)
 
-    def nonwiggle_table(self, z, nonlinear=False):
+    def nonwiggle_table(self, z, nonlinear=False, tracer="matter"):
         """Knots and coefficients of the degree-1 no-wiggle spline at redshift z
         (Savitzky-Golay smoothing in ln k, cosmology.py:1760-1813)."""
-        key = (float(z), bool(nonlinear))
+        key = (float(z), bool(nonlinear), tracer == "clustering")
         if key not in self._nw_cache:
             s = self.settings
             h = self.cosmopars["h"]
@@ -245,7 +271,8 @@ class cosmo_functions:
                              s["savgol_internalsamples"])
             dlnk = np.mean(lk[1:] - lk[0:-1])
             n_sg = int(np.round(s["savgol_width"] / np.log(1 + dlnk)))
-            lp = InterpolatedUnivariateSpline(lk, np.log(self.matpow(z, np.exp(lk), nonlinear=nonlinear).flatten()), k=1)
+            lp = InterpolatedUnivariateSpline(
+                lk, np.log(self.matpow(z, np.exp(lk), nonlinear=nonlinear, tracer=tracer).flatten()), k=1)
             sg = savgol_filter(lp(lk), n_sg, s["savgol_polyorder"])
             spl = InterpolatedUnivariateSpline(np.exp(lk), np.exp(sg), k=1)
             t, c, _ = spl._eval_args
@@ -254,12 +281,15 @@ class cosmo_functions:
         return self._nw_cache[key]
 
     def nonwiggle_pow(self, z, k, nonlinear=False, tracer="matter"):
-        return self.nonwiggle_table(z, nonlinear)[2](k)
+        return self.nonwiggle_table(z, nonlinear, tracer)[2](k)
 
     # --- device export -----------------------------------------------------------------------
     def bank_row(self, slots=None):
         """Bicubic (tx, ty, c) per table slot of include/cfp_b200.h; `slots` limits which tables are fitted."""
-        names = {_lib.TAB_PLIN: "Pk_l", _lib.TAB_PNL: "Pk_nl", _lib.TAB_F: "f_growthrate_zk", _lib.TAB_D: "D_growth_zk"}
+        names = {_lib.TAB_PLIN: "Pk_l", _lib.TAB_PNL: "Pk_nl", _lib.TAB_F: "f_growthrate_zk", _lib.TAB_D: "D_growth_zk",
+                 _lib.TAB_PLIN_CB: "Pk_cb_l", _lib.TAB_PNL_CB: "Pk_cb_nl", _lib.TAB_F_CB: "f_growthrate_cb_zk"}
+        if not self.cb_files_on:
+            names = {k: v for k, v in names.items() if k < _lib.TAB_PLIN_CB}
         row = [None] * _lib.NTAB
         for slot, name in names.items():
             if slots is None or slot in slots:
@@ -293,7 +323,8 @@ def cached_cosmo(cosmopars, config) -> "cosmo_functions":
     src = id(ext["tables"]) if ext.get("tables") is not None else os.path.abspath(ext["directory"])
     key = (src, tuple(sorted((k, v) for k, v in cosmopars.items())), tuple(sorted(config.fiducialparams.items())),
            tuple(ext["paramnames"]), tuple(ext["eps_values"]), ext.get("k-units"), ext.get("r-units"),
-           st["savgol_internalkmin"], st["savgol_internalsamples"], st["savgol_width"], st["savgol_polyorder"])
+           st["savgol_internalkmin"], st["savgol_internalsamples"], st["savgol_width"], st["savgol_polyorder"],
+           st.get("GCsp_Tracer"), st.get("GCph_Tracer"))
     hit = _COSMO_CACHE.get(key)
     if hit is not None and hit[0] is ext.get("tables"):  # identity check: id() values can be recycled
         return hit[1]

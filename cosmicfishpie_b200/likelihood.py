@@ -512,7 +512,8 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
                 cs.ctx or _lib.default_context(), cs.bank(), k=fm.Pk_kgrid, mu=fm.Pk_mugrid, wk=wk, wmu=wmu,
                 scal=scal[i0:i0 + S], alias=np.tile(np.arange(S, dtype=np.int32)[:, None], (1, Z)), pnw_k=pk, pnw_p=pp,
                 stw=np.zeros((1, S)), stden=np.ones(1), ps_bin=np.array([-1], np.int32), ps_src=0, nbar=nbar,
-                vol=fm.pk_cov.volume_survey_array, flags=fid_obs.flags())
+                vol=fm.pk_cov.volume_survey_array, flags=fid_obs.flags(),
+                tab_plin=spectro_mod.table_slots(fm.settings)[0], tab_f=spectro_mod.table_slots(fm.settings)[1])
             out[i0:i0 + S] = plan.chi2(shot[i0:i0 + S], data_dev=self._data_on_device(plan.ctx))
             plan.close()
         return out
@@ -538,7 +539,8 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
                 alias=np.tile(np.arange(S, dtype=np.int32)[:, None], (1, Z)), pnw_k=pk, pnw_p=pp, stw=np.zeros((1, S)),
                 stden=np.ones(1), ps_bin=np.array([-1], np.int32), ps_src=0,
                 nbar=np.array([fm.pk_cov.n_density(z) for z in zs]), vol=fm.pk_cov.volume_survey_array,
-                flags=pts[0].flags())
+                flags=pts[0].flags(), tab_plin=spectro_mod.table_slots(fm.settings)[0],
+                tab_f=spectro_mod.table_slots(fm.settings)[1])
             out[i0:i0 + chunk] = plan.chi2(np.array(shots), data_dev=self._data_on_device(plan.ctx))
             plan.close()
         return out

@@ -152,9 +152,9 @@ class ComputeGalSpectro:
         self.specs = dict(configuration.specs)
         self.settings = configuration.settings
         self.s8terms = self.settings["bfs8terms"]
-        self.tracer = self.settings["GCsp_Tracer"]
-        if self.tracer != "matter":
-            raise NotImplementedError("GCsp_Tracer='clustering' (cb tables) is not supported")
+        self.tracer = self.settings["GCsp_Tracer"]  # "matter" | "clustering" (cdm+baryon tables), spectro_obs.py:164
+        if self.tracer not in ("matter", "clustering"):
+            raise ValueError("GCsp_Tracer must be 'matter' or 'clustering'")
         self.fiducial_cosmopars = dict(cfg.fiducialparams if fiducial_cosmopars is None else fiducial_cosmopars)
         if self.fiducial_cosmopars != cfg.fiducialparams:
             raise AttributeError("fiducial_cosmopars not equal to the configuration's fiducialparams")
@@ -254,7 +254,7 @@ class ComputeGalSpectro:
             self.nuisance.gcsp_rescale_sigmapv_at_z(z, sigma_key="sigmav") if self.rescale_sigmav else 1.0
         )
         if self.s8terms:
-            s8 = float(self.cosmo.scalar("sigma8_of_z", z))
+            s8 = float(self.cosmo.scalar("sigma8_cb_of_z" if self.tracer == "clustering" else "sigma8_of_z", z))
             b[_lib.SP_FS8], b[_lib.SP_INVS8SQ] = s8, 1.0 / s8**2
         else:
             b[_lib.SP_FS8], b[_lib.SP_INVS8SQ] = 1.0, 1.0
@@ -292,10 +292,17 @@ class ComputeGalSpectro:
         return out.reshape(shape)
 
 
+def table_slots(settings):
+    """Bank slots of P_lin(z,k) and f(z,k) of the GCsp tracer (spectro_obs.py:628-630, 780)."""
+    if settings["GCsp_Tracer"] == "clustering":
+        return _lib.TAB_PLIN_CB, _lib.TAB_F_CB
+    return _lib.TAB_PLIN, _lib.TAB_F
+
+
 def _cosmo_set_of(cfg) -> CosmoSet:
     cs = cfg.__dict__.get("_cosmo_set")
     if cs is None:
-        cs = CosmoSet(cfg, slots=(_lib.TAB_PLIN, _lib.TAB_F))
+        cs = CosmoSet(cfg, slots=table_slots(cfg.settings))
         cfg.__dict__["_cosmo_set"] = cs
     return cs
 
@@ -309,7 +316,7 @@ def _pnw_arrays(cosmo_set: CosmoSet, zs, used):
     pp = np.ones((NC, Z, nnw))
     for c in sorted(used):
         for j, z in enumerate(zs):
-            kk, vv, _ = cosmo_set.cosmos[c].nonwiggle_table(z)
+            kk, vv, _ = cosmo_set.cosmos[c].nonwiggle_table(z, tracer=cosmo_set.config.settings["GCsp_Tracer"])
             pk[c] = kk
             pp[c, j] = vv
     return pk, pp
@@ -328,7 +335,7 @@ def _evaluate_lattice(points: List[ComputeGalSpectro], zs, kgrid, mugrid) -> np.
         cs.ctx or _lib.default_context(), cs.bank(), k=kgrid, mu=mugrid, wk=np.zeros_like(kgrid),
         wmu=np.zeros_like(mugrid), scal=scal, alias=alias, pnw_k=pk, pnw_p=pp, stw=np.zeros((1, S)),
         stden=np.ones(1), ps_bin=np.array([-1], dtype=np.int32), ps_src=0, nbar=np.zeros(Z), vol=np.zeros(Z),
-        flags=points[0].flags())
+        flags=points[0].flags(), tab_plin=table_slots(points[0].settings)[0], tab_f=table_slots(points[0].settings)[1])
     plan.run(materialize=_lib.MAT_LNP)
     _, lnp, _, _ = plan.fetch(lnp=True)
     plan.close()
@@ -464,6 +471,7 @@ class SpectroJob:
         self.nbar = np.array([cov.n_density(z) for z in self.zmids])
         self.vol = np.array([cov.volume_survey(i) for i in range(Z)])
         self.flags = fiducial_obs.flags()
+        self.tabs = table_slots(fiducial_obs.settings)
         self.cosmo_set = cs
         self._plan = None
 
@@ -484,7 +492,8 @@ class SpectroJob:
             self._plan = _lib.SpectroPlan(
                 cs.ctx or _lib.default_context(), cs.bank(), k=self.kgrid, mu=self.mugrid, wk=self.wk, wmu=self.wmu,
                 scal=self.scal, alias=self.alias, pnw_k=self.pnw_k, pnw_p=self.pnw_p, stw=self.stw, stden=self.stden,
-                ps_bin=self.ps_bin, ps_src=self.ps_src, nbar=self.nbar, vol=self.vol, flags=self.flags)
+                ps_bin=self.ps_bin, ps_src=self.ps_src, nbar=self.nbar, vol=self.vol, flags=self.flags,
+                tab_plin=self.tabs[0], tab_f=self.tabs[1])
         return self._plan
 
     def run(self, materialize=0):

@@ -53,6 +53,12 @@ FILE_STEMS = {
     "f": "f_GrowthRate-zk",
     "Pl": "Plin-zk",
     "Pnl": "Pnonlin-zk",
+    # cold dark matter + baryon ("clustering" tracer) tables, read only when a tracer setting asks for them
+    # (config.py:289-304, cosmology.py:1240-1245,1352-1368)
+    "s8cb": "sigma8cb-z",
+    "fcb": "fcb_GrowthRate-zk",
+    "Plcb": "Plincb-zk",
+    "Pnlcb": "Pnonlincb-zk",
 }
 
 
@@ -108,7 +114,12 @@ def make_tables(pars: Dict[str, float], zg: np.ndarray, kg: np.ndarray) -> Dict[
     Pl = Dzk**2 * P0[None, :]
     D2 = kg[None, :] ** 3 * Pl / (2.0 * np.pi**2)
     Pnl = Pl * (1.0 + D2**1.2 / (1.0 + 0.3 * D2**0.6))
-    return {"z": zg, "k": kg, "H": H, "s8": s8 * Dz, "D": Dzk, "f": fzk, "Pl": Pl, "Pnl": Pnl}
+    # "clustering" (cb) variants: a smooth scale-dependent boost of the spectra and of the growth rate, as massive
+    # neutrinos would leave between total matter and cdm+baryons
+    boost = (1.0 + 0.015 * kg / (kg + 0.1))[None, :]
+    return {"z": zg, "k": kg, "H": H, "s8": s8 * Dz, "D": Dzk, "f": fzk, "Pl": Pl, "Pnl": Pnl,
+            "s8cb": 1.004 * s8 * Dz, "fcb": fzk * (1.0 + 0.003 * kg / (kg + 0.05))[None, :], "Plcb": Pl * boost**2,
+            "Pnlcb": Pnl * boost**2}
 
 
 def eps_string(eps: float) -> str:

@@ -78,7 +78,10 @@ int cfp_peak_fp64(cfp_ctx* ctx, int kind, double* tflops_out);
 #define CFP_TAB_PNL 1
 #define CFP_TAB_F 2
 #define CFP_TAB_D 3
-#define CFP_NTAB 4
+#define CFP_TAB_PLIN_CB 4 /* cdm+baryon ("clustering" tracer) spectra and growth rate, cosmology.py:1508-1531 */
+#define CFP_TAB_PNL_CB 5
+#define CFP_TAB_F_CB 6
+#define CFP_NTAB 7
 
 int cfp_bank_upload(cfp_ctx* ctx, const double* blob_h, size_t n_doubles, const int64_t* desc_h,
                     int n_cosmo, int n_tables, cfp_bank** out);

@@ -75,6 +75,11 @@ class Cosmo:
         self.s8_of_z = InterpolatedUnivariateSpline(self.zgrid, np.asarray(tables["s8"]).flatten())
         self.Pk_l = RectBivariateSpline(self.zgrid, self.kgrid, pkf * np.asarray(tables["Pl"]), kx=3, ky=3)
         self.Pk_nl = RectBivariateSpline(self.zgrid, self.kgrid, pkf * np.asarray(tables["Pnl"]), kx=3, ky=3)
+        if "Plcb" in tables:  # cdm+baryon ("clustering" tracer) tables, cosmology.py:1508-1531
+            self.f_growthrate_cb_zk = RectBivariateSpline(self.zgrid, self.kgrid, tables["fcb"], kx=3, ky=3)
+            self.s8_cb_of_z = InterpolatedUnivariateSpline(self.zgrid, np.asarray(tables["s8cb"]).flatten())
+            self.Pk_cb_l = RectBivariateSpline(self.zgrid, self.kgrid, pkf * np.asarray(tables["Plcb"]), kx=3, ky=3)
+            self.Pk_cb_nl = RectBivariateSpline(self.zgrid, self.kgrid, pkf * np.asarray(tables["Pnlcb"]), kx=3, ky=3)
 
     # accessors, cosmology.py:1616-1977 -------------------------------------------------
     def Hubble(self, z):
@@ -89,26 +94,30 @@ class Cosmo:
     def comoving(self, z):
         return self.com_dist(z)
 
-    def matpow(self, z, k, nonlinear=False):
+    def matpow(self, z, k, nonlinear=False, tracer="matter"):
+        if tracer == "clustering":  # cosmology.py:1715-1716
+            return (self.Pk_cb_nl if nonlinear else self.Pk_cb_l)(z, k, grid=False)
         return (self.Pk_nl if nonlinear else self.Pk_l)(z, k, grid=False)
 
-    def f_growthrate(self, z, k=None):
+    def f_growthrate(self, z, k=None, tracer="matter"):
+        if tracer == "clustering":  # cosmology.py:1937-1939
+            return self.f_growthrate_cb_zk(z, 0.0001 if k is None else k, grid=False)
         return self.f_growthrate_zk(z, 0.0001 if k is None else k, grid=False)
 
     def growth(self, z, k=None):
         return self.D_growth_zk(z, 0.0001 if k is None else k, grid=False)
 
-    def sigma8_of_z(self, z):
-        return self.s8_of_z(z)
+    def sigma8_of_z(self, z, tracer="matter"):
+        return self.s8_cb_of_z(z) if tracer == "clustering" else self.s8_of_z(z)  # cosmology.py:1851-1857
 
-    def fsigma8_of_z(self, z, k=None):
-        return self.f_growthrate(z, k) * self.sigma8_of_z(z)
+    def fsigma8_of_z(self, z, k=None, tracer="matter"):
+        return self.f_growthrate(z, k, tracer=tracer) * self.sigma8_of_z(z, tracer=tracer)
 
     def Omegam_of_z(self, z):
         # cosmology.py:1904-1905 (external branch)
         return (self.cosmopars["Omegam"] * (1 + z) ** 3) / self.E_hubble(z) ** 2
 
-    def nonwiggle_table(self, z, nonlinear=False):
+    def nonwiggle_table(self, z, nonlinear=False, tracer="matter"):
         """(k_samples, P_nw samples) of the degree-1 spline of cosmology.py:1790-1812."""
         s = self.settings
         unitsf = self.cosmopars["h"]
@@ -118,13 +127,13 @@ class Cosmo:
         dlnk = np.mean(logk[1:] - logk[0:-1])
         n_savgol = int(np.round(s["savgol_width"] / np.log(1 + dlnk)))
         intp_p = InterpolatedUnivariateSpline(
-            logk, np.log(self.matpow(z, np.exp(logk), nonlinear=nonlinear).flatten()), k=1
+            logk, np.log(self.matpow(z, np.exp(logk), nonlinear=nonlinear, tracer=tracer).flatten()), k=1
         )
         pow_sg = savgol_filter(intp_p(logk), n_savgol, s["savgol_polyorder"])
         return np.exp(logk), np.exp(pow_sg)
 
-    def nonwiggle_pow(self, z, k, nonlinear=False):
-        kk, pp = self.nonwiggle_table(z, nonlinear)
+    def nonwiggle_pow(self, z, k, nonlinear=False, tracer="matter"):
+        kk, pp = self.nonwiggle_table(z, nonlinear, tracer)
         return InterpolatedUnivariateSpline(kk, pp, k=1)(k)
 
 

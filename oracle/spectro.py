@@ -103,6 +103,7 @@ class GalSpectro:
         self.nuis = SpectroNuisance(specs, spectrobiaspars, nonlinpars)
         self.k_grid = np.logspace(np.log10(0.001), np.log10(5), 1024)  # :261-263
         self.linear = s["GCsp_linear"]
+        self.tracer = s["GCsp_Tracer"]  # spectro_obs.py:164
         par = specs.get("nonlinear_parametrization", {"default": ""}) or {}
         self.rescale_sigmap = par.get("rescale_sigmap", False)
         self.rescale_sigmav = par.get("rescale_sigmav", False)
@@ -145,9 +146,9 @@ class GalSpectro:
     def kaiser(self, z, k, mu):
         b = self.nuis.bias_at_z(z) * self.nuis.kscale(k)
         if self.s["bfs8terms"]:
-            f = self.cosmo.fsigma8_of_z(z, k)
+            f = self.cosmo.fsigma8_of_z(z, k, tracer=self.tracer)  # spectro_obs.py:628-630
         else:
-            f = self.cosmo.f_growthrate(z, k)
+            f = self.cosmo.f_growthrate(z, k, tracer=self.tracer)
         return b + f * mu**2
 
     def moments(self, z, m):
@@ -180,9 +181,9 @@ class GalSpectro:
 
     def dewiggled(self, z, k, mu):
         g = 0 if self.linear else self.sigmav(z, mu) ** 2
-        den = self.cosmo.sigma8_of_z(z) ** 2 if self.s["bfs8terms"] else 1
-        pdd = self.cosmo.matpow(z, k) / den
-        pnw = self.cosmo.nonwiggle_pow(z, k) / den
+        den = self.cosmo.sigma8_of_z(z, tracer=self.tracer) ** 2 if self.s["bfs8terms"] else 1  # spectro_obs.py:778-807
+        pdd = self.cosmo.matpow(z, k, tracer=self.tracer) / den
+        pnw = self.cosmo.nonwiggle_pow(z, k, tracer=self.tracer) / den
         return pdd * np.exp(-g * k**2) + pnw * (1 - np.exp(-g * k**2))
 
     def observed_Pgg(self, z, k, mu):

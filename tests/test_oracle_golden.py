@@ -103,6 +103,7 @@ F3 = {"Omegam": 0.01, "h": 0.01, "w0": 0.01}
     ("gcsp_var_dzdep", dict(SMALL), {"spec_sigma_dz_type": "z-dependent", "spec_sigma_dz": 0.001}, None),
     ("gcsp_var_nlcosmo", dict(SMALL, fix_cosmo_nl_terms=False), {}, None),
     ("gcsp_var_qbias", dict(SMALL), {}, "Euclid-Spectroscopic-ISTF-Pessimistic-Qbias"),
+    ("gcsp_var_clustering", dict(SMALL, GCsp_Tracer="clustering", bfs8terms=True), {}, None),
     ("gcsp_var_sigmapv", dict(SMALL), {"nonlinear_parametrization": dict(
         rescale_sigmap=True, rescale_sigmav=True, default=None,
         rescale_sigma_pv={f"sigma{c}_{i}": 1.0 for c in "pv" for i in (1, 2, 3, 4)})},

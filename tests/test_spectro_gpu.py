@@ -28,6 +28,8 @@ CASES.update({
     "gcsp_var_nlcosmo": dict(free=F3, opts=dict(SMALL, fix_cosmo_nl_terms=False), mzb=2),
     "gcsp_var_qbias": dict(free=F3, opts=dict(SMALL, survey_name_spectro="Euclid-Spectroscopic-ISTF-Pessimistic-Qbias"),
                            mzb=2),
+    # cdm+baryon ("clustering") tracer tables
+    "gcsp_var_clustering": dict(free=F3, opts=dict(SMALL, GCsp_Tracer="clustering", bfs8terms=True), mzb=2),
     # per-bin rescaling of sigma_p / sigma_v as free parameters
     "gcsp_var_sigmapv": dict(free=F3, opts=dict(SMALL, survey_name_spectro="Euclid-Spectroscopic-ISTF-Pessimistic-sigma_pv"),
                              mzb=2, specs={"nonlinear_parametrization": dict(

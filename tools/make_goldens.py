@@ -41,7 +41,7 @@ def quiet():
 
 def bank_dir():
     d = os.path.join(SCRATCH, "bank")
-    if not os.path.isdir(os.path.join(d, "fiducial_eps_0")):
+    if not os.path.isfile(os.path.join(d, "fiducial_eps_0", "Plincb-zk.txt")):  # (cb tables were added later)
         tt.write_bank(d, eps_values=(0.01,))
     return d
 
@@ -233,6 +233,8 @@ GCSP_VARIANTS = {
     "gcsp_var_qbias": dict(options_extra=dict(SMALL, specs_dir=MYSPECS), spectro_yaml="Euclid-Spectroscopic-ISTF-Pessimistic-Qbias"),
     # per-bin rescaling of sigma_p and sigma_v as free parameters (reference's own sigma_pv specification): 19 parameters
     # with max_z_bins=2 -> three 8-row blocks in the Gram kernel
+    # cdm+baryon tracer: P_cb, f_cb, sigma8_cb tables (the theta-theta moments stay on total matter, spectro_obs.py:748-752)
+    "gcsp_var_clustering": dict(options_extra=dict(SMALL, GCsp_Tracer="clustering", bfs8terms=True)),
     "gcsp_var_sigmapv": dict(options_extra=dict(SMALL, specs_dir=MYSPECS), spectro_yaml="Euclid-Spectroscopic-ISTF-Pessimistic-sigma_pv",
                              specifications={"nonlinear_parametrization": dict(
                                  rescale_sigmap=True, rescale_sigmav=True, default=None,
