@@ -36,6 +36,7 @@ EXPORTS = [
     "cfp_legendre_project", "cfp_legendre_covariance", "cfp_legendre_chi2",
     "cfp_bank_upload_rows", "cfp_host_alloc", "cfp_host_free", "cfp_spectro_plan_chi2_dev", "cfp_dev_upload",
     "cfp_dev_release", "cfp_photo_plan_create_zmap", "cfp_ctx_aux_stream", "cfp_photo_plan_create_ex",
+    "cfp_photo_plan_set_gc_table",
 ]
 
 
@@ -107,6 +108,7 @@ def load():
         _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp, C.c_double, _dp, _dp, _dp,
         _ip, C.c_int, _ip, _dp, _dp, C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int,
         C.POINTER(_vp)]
+    lib.cfp_photo_plan_set_gc_table.argtypes = [_vp, C.c_int]
     lib.cfp_photo_plan_destroy.argtypes = [_vp]
     lib.cfp_photo_plan_set_slice.argtypes = [_vp, C.c_int, C.c_int]
     lib.cfp_photo_plan_run.argtypes = [_vp, _vp]
@@ -487,7 +489,7 @@ class SpectroPlan:
 
 class PhotoPlan:
     def __init__(self, ctx: Context, bank: Bank, *, cosmo_of_s, ell, z, dz, chi, hub, wlpref, kind, ngal, bias, ia,
-                 lmin, lmax, noise, sqrtfsky, stw, stden, kmax, tab_p=TAB_PNL, zmap=None, win_of_s=None):
+                 lmin, lmax, noise, sqrtfsky, stw, stden, kmax, tab_p=TAB_PNL, zmap=None, win_of_s=None, tab_pg=None):
         self.ctx, self.bank = ctx, bank
         self.cosmo_of_s = i32(cosmo_of_s)
         self.ell, self.z = f64(ell), f64(z)
@@ -531,6 +533,8 @@ class PhotoPlan:
                 _p(self.wlpref), _p(self.kind, _ip), _p(self.ngal), _p(self.bias), int(Kb), _p(self.zmap, _ip),
                 _p(self.ia), _p(self.lmin), _p(self.lmax), _p(self.noise), _p(self.sqrtfsky), _p(self.stw),
                 _p(self.stden), float(kmax), int(tab_p), C.byref(self.handle)), "cfp_photo_plan_create_zmap")
+        if tab_pg is not None and int(tab_pg) != int(tab_p):  # clustering rows on another spectrum (cdm+baryons)
+            _check(ctx.lib.cfp_photo_plan_set_gc_table(self.handle, int(tab_pg)), "cfp_photo_plan_set_gc_table")
         self.h2d_bytes = sum(a.nbytes for a in (self.cosmo_of_s, self.ell, self.z, self.chi, self.hub, self.wlpref,
                                                 self.kind, self.ngal, self.bias, self.ia, self.lmin, self.lmax,
                                                 self.noise, self.sqrtfsky, self.stw, self.stden))

@@ -177,13 +177,15 @@ struct ClsParams {
   int S, Nl, Nz, Nb, nb, ldz, nz4, lch, l_begin, l_end;
   const int* cosmo_of_s;
   const double *U, *V;   // [S][nb*8][ldz]
-  const double* T;       // [NC][Nl][Nz]
+  const double* T;       // [NC][Nl][Nz] sqrt(P)/chi of the lensing rows
+  const double* Tg;      // the same for the clustering rows (another table when GCph_Tracer = 'clustering', else = T)
+  const int* kind;       // [Nb] 0 = lensing row, 1 = clustering row
   const double* wz;      // [nz4] trapezoid weights (zero padded)
   const double *ell, *lmin, *lmax;
   double* cls;           // [S][Nl][Nb][Nb]
 };
 
-template <int NB>
+template <int NB, bool TWO>  // TWO: the clustering rows use their own sqrt(P) table (GCph_Tracer = 'clustering')
 __global__ void __launch_bounds__(CLS_THREADS) photo_cls_kernel(ClsParams P) {
   constexpr int NT = NB * (NB + 1) / 2;
   extern __shared__ double smem[];
@@ -202,20 +204,29 @@ __global__ void __launch_bounds__(CLS_THREADS) photo_cls_kernel(ClsParams P) {
   const int l0 = P.l_begin + blockIdx.x * P.lch;
   const int l1 = min(l0 + P.lch, P.l_end);
   const int g = lane >> 2, tg = lane & 3;
+  // which sqrt(P) table each of this lane's rows multiplies (photo_obs.py:483-507: GCph uses its tracer's spectrum)
+  bool gc_row[NB];
+#pragma unroll
+  for (int ib = 0; ib < NB; ++ib) {
+    const int row = ib * 8 + g;
+    gc_row[ib] = TWO && row < P.Nb && P.kind[row] != 0;
+  }
   for (int il = l0 + warp; il < l1; il += CLS_WARPS) {
     const double* Trow = P.T + ((size_t)c * P.Nl + il) * P.Nz;
+    const double* Tgrow = P.Tg + ((size_t)c * P.Nl + il) * P.Nz;
     double acc[NT][2];
 #pragma unroll
     for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
     for (int z0 = 0; z0 < P.nz4; z0 += 4) {
       const int iz = z0 + tg;
       const double t = (iz < P.Nz) ? __ldg(Trow + iz) : 0.0;
+      const double t_gc = TWO ? ((iz < P.Nz) ? __ldg(Tgrow + iz) : 0.0) : t;
       const double w = P.wz[iz];
       double a[NB];
 #pragma unroll
       for (int ib = 0; ib < NB; ++ib) {
         const int off = (ib * 8 + g) * P.ldz + iz;
-        a[ib] = t * sK[off];
+        a[ib] = ((TWO && gc_row[ib]) ? t_gc : t) * sK[off];
       }
       int tt = 0;
 #pragma unroll
@@ -632,6 +643,8 @@ struct cfp_photo_plan {
   cfp_ctx* ctx = nullptr;
   const cfp_bank* bank = nullptr;
   int S = 0, NC = 0, Nl = 0, Nz = 0, Nb = 0, npar = 0, nb = 0, ldz = 0, nz4 = 0, ldb = 0, zstride = 0, tab_p = 0;
+  int tab_pg = 0;          // table of the clustering rows (= tab_p unless GCph_Tracer = 'clustering')
+  double* Tg_d = nullptr;  // its sqrt(P)/chi table (owned only when tab_pg != tab_p)
   int l_begin = 0, l_end = 0;
   double dz = 0.0, kmax = 0.0;
   int *cosmo_of_s_d = nullptr, *kind_d = nullptr;
@@ -754,6 +767,7 @@ static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int
   cfp_photo_plan* pl = new cfp_photo_plan();
   pl->ctx = ctx, pl->bank = bank;
   pl->S = S, pl->NC = NC, pl->Nl = Nl, pl->Nz = Nz, pl->Nb = Nb, pl->npar = npar, pl->tab_p = tab_p;
+  pl->tab_pg = tab_p;
   pl->nb = (Nb + 7) / 8;
   pl->nz4 = (Nz + 3) / 4 * 4;
   int ldz = pl->nz4;
@@ -863,6 +877,22 @@ extern "C" int cfp_photo_plan_destroy(cfp_photo_plan* plan) {
   return CFP_OK;
 }
 
+extern "C" int cfp_photo_plan_set_gc_table(cfp_photo_plan* plan, int tab_p_gc) {
+  CFP_REQUIRE(plan != nullptr, "plan is NULL");
+  CFP_REQUIRE(tab_p_gc >= 0 && tab_p_gc < plan->bank->n_tables, "bad table slot");
+  for (int c = 0; c < plan->NC; ++c)
+    CFP_REQUIRE(plan->bank->desc(c, tab_p_gc)[0] >= 8, "cosmology lacks the clustering power spectrum table");
+  cfp_ctx* ctx = plan->ctx;
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  if (tab_p_gc != plan->tab_p && !plan->Tg_d) {
+    CFP_CUDA(cfp_dev_alloc(ctx, (void**)&plan->Tg_d, (size_t)plan->NC * plan->Nl * plan->Nz * sizeof(double)));
+    plan->owned.push_back((void*)plan->Tg_d);
+    CFP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  plan->tab_pg = tab_p_gc;
+  return CFP_OK;
+}
+
 extern "C" int cfp_photo_plan_set_slice(cfp_photo_plan* plan, int l_begin, int l_end) {
   CFP_REQUIRE(plan != nullptr, "plan is NULL");
   CFP_REQUIRE(l_begin >= 0 && l_begin <= l_end && l_end <= plan->Nl - 1, "slice out of range");
@@ -873,9 +903,15 @@ extern "C" int cfp_photo_plan_set_slice(cfp_photo_plan* plan, int l_begin, int l
 
 template <int NB>
 static cudaError_t launch_cls(const ClsParams& P, dim3 grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(photo_cls_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  photo_cls_kernel<NB><<<grid, CLS_THREADS, smem, st>>>(P);
+  if (P.Tg != P.T) {
+    cudaError_t e = cudaFuncSetAttribute(photo_cls_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    photo_cls_kernel<NB, true><<<grid, CLS_THREADS, smem, st>>>(P);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(photo_cls_kernel<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    photo_cls_kernel<NB, false><<<grid, CLS_THREADS, smem, st>>>(P);
+  }
   return cudaGetLastError();
 }
 
@@ -914,6 +950,13 @@ static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
         pl->chi_d, pl->kmax, pl->T_d);
     ctx->launches++;
     CFP_CUDA(cudaGetLastError());
+    if (pl->tab_pg != pl->tab_p) {
+      photo_sqrtp_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(
+          pl->bank->blob_d, pl->bank->desc_d, pl->bank->n_tables, pl->tab_pg, pl->NC, pl->Nl, pl->Nz, pl->ell_d,
+          pl->z_d, pl->chi_d, pl->kmax, pl->Tg_d);
+      ctx->launches++;
+      CFP_CUDA(cudaGetLastError());
+    }
   }
   CFP_CUDA(cudaEventRecord(pl->kev[1], st));
   {
@@ -957,6 +1000,7 @@ static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
     lch = (lch + CLS_WARPS - 1) / CLS_WARPS * CLS_WARPS;
     P.lch = lch;
     P.cosmo_of_s = pl->cosmo_of_s_d, P.U = pl->U_d, P.V = pl->V_d, P.T = pl->T_d, P.wz = pl->wz_d;
+    P.Tg = pl->tab_pg != pl->tab_p ? pl->Tg_d : pl->T_d, P.kind = pl->kind_d;
     P.ell = pl->ell_d, P.lmin = pl->lmin_d, P.lmax = pl->lmax_d, P.cls = pl->cls_d;
     CFP_CUDA(cudaEventRecord(pl->kev[2], st));
     const dim3 grid((nl + lch - 1) / lch, pl->S);

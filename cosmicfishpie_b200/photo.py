@@ -209,8 +209,13 @@ class _PhotoGrid:
         self.sqrtfsky = np.array([np.sqrt(sp["fsky_" + o]) for o, _ in self.rows])  # photo_cov.py:228
         self.kmax = float(sp["kmax"])
         self.tab_p = _lib.TAB_PNL if st["nonlinear"] else _lib.TAB_PLIN
-        if st["GCph_Tracer"] != "matter":
-            raise NotImplementedError("GCph_Tracer='clustering' (cb tables) is not supported")
+        # sqrt(P) of the clustering rows is taken on the tracer's spectrum (photo_obs.py:483-507)
+        if st["GCph_Tracer"] == "clustering":
+            self.tab_pg = _lib.TAB_PNL_CB if st["nonlinear"] else _lib.TAB_PLIN_CB
+        elif st["GCph_Tracer"] == "matter":
+            self.tab_pg = self.tab_p
+        else:
+            raise ValueError("GCph_Tracer must be 'matter' or 'clustering'")
         if st["activateMG"] or st["external_activateMG"]:
             raise NotImplementedError("modified-gravity Sigma(z,k) is not supported")
 
@@ -390,7 +395,7 @@ class PhotoJob:
                 chi=self.chi, hub=self.hub, wlpref=self.wlpref, kind=g.kind, ngal=self.ngal, bias=self.bias,
                 ia=self.ia, lmin=g.lmin, lmax=g.lmax, noise=g.noise, sqrtfsky=g.sqrtfsky, stw=self.stw,
                 stden=self.stden, kmax=g.kmax, tab_p=g.tab_p, zmap=getattr(self, "zmap", None),
-                win_of_s=getattr(self, "win_of_s", None))
+                win_of_s=getattr(self, "win_of_s", None), tab_pg=g.tab_pg)
         return self._plan
 
     def run(self):
@@ -407,7 +412,11 @@ class PhotoJob:
 def _cosmo_set_of(cfg) -> CosmoSet:
     cs = cfg.__dict__.get("_cosmo_set")
     if cs is None:
-        cs = CosmoSet(cfg, slots=(_lib.TAB_PNL if cfg.settings["nonlinear"] else _lib.TAB_PLIN,))
+        nl = cfg.settings["nonlinear"]
+        slots = [_lib.TAB_PNL if nl else _lib.TAB_PLIN]
+        if cfg.settings["GCph_Tracer"] == "clustering":
+            slots.append(_lib.TAB_PNL_CB if nl else _lib.TAB_PLIN_CB)
+        cs = CosmoSet(cfg, slots=tuple(slots))
         cfg.__dict__["_cosmo_set"] = cs
     return cs
 

@@ -252,6 +252,11 @@ int cfp_photo_plan_create_ex(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, 
                              const int32_t* zmap_h, const double* ia_h, const double* lmin_h, const double* lmax_h,
                              const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
                              const double* stden_h, double kmax, int tab_p, cfp_photo_plan** out);
+
+/* Table slot of the spectrum the CLUSTERING rows use when it differs from tab_p (GCph_Tracer = "clustering":
+ * photo_obs.py:483-507 evaluates sqrt(P) of GCph on the cdm+baryon spectrum, lensing rows stay on total matter).
+ * Call between create and run.                                                                                    */
+int cfp_photo_plan_set_gc_table(cfp_photo_plan* plan, int tab_p_gc);
 int cfp_photo_plan_destroy(cfp_photo_plan* plan);
 /* multi-GPU partition: this rank owns multipoles [l_begin, l_end) */
 int cfp_photo_plan_set_slice(cfp_photo_plan* plan, int l_begin, int l_end);

@@ -213,8 +213,11 @@ class Cls:
         idx = np.where(kappa < self.specs["kmax"])
         el, zi = idx
         p = np.sqrt(self.cosmo.matpow(self.z[zi], kappa[el, zi], nonlinear=self.s["nonlinear"])) / self.chi[zi]
-        for k in ("WL", "WL_IA", "GCph"):  # Sigma_MG == 1 and tracer == matter on this path
+        for k in ("WL", "WL_IA", "GCph"):  # Sigma_MG == 1 on this path
             self.sqrtPell[k][zi, el] = p
+        if self.s["GCph_Tracer"] == "clustering":  # photo_obs.py:499-509: GCph on the cdm+baryon spectrum
+            self.sqrtPell["GCph"][zi, el] = np.sqrt(self.cosmo.matpow(
+                self.z[zi], kappa[el, zi], nonlinear=self.s["nonlinear"], tracer="clustering")) / self.chi[zi]
 
     def compute_kernels(self):
         z = self.z

@@ -138,6 +138,7 @@ def test_spectro_oracle_variants_bit_exact(obank, tag, settings, spec_over, yaml
     ("photo_var_linear_pk", ["WL", "GCph"], {"Omegam": 0.01, "h": 0.01}, {"ell_sampling": 16, "nonlinear": False}, {}),
     ("photo_var_sqrtbias", ["GCph"], {"sigma8": 0.01}, {"ell_sampling": 16}, {"ph_bias_model": "sqrt"}),
     ("photo_var_gcfirst", ["GCph", "WL"], {"Omegam": 0.01}, {"ell_sampling": 12, "pivot_z_IA": 0.3}, {}),
+    ("photo_var_clustering", ["WL", "GCph"], {"Omegam": 0.01, "h": 0.01}, {"ell_sampling": 12, "GCph_Tracer": "clustering"}, {}),
     ("photo_var_photoz", ["WL", "GCph"], {"Omegam": 0.01, "sigma_b": 0.02, "zb": 0.002, "fout": 0.02},
      {"ell_sampling": 12}, {}),
 ])

@@ -23,6 +23,9 @@ CASES.update({  # goldens: tools/make_goldens.py PHOTO_VARIANTS
     "photo_var_sqrtbias": dict(obs=["GCph"], free={"sigma8": 0.01}, opts={"ell_sampling": 16},
                                specs={"ph_bias_model": "sqrt"}),
     "photo_var_gcfirst": dict(obs=["GCph", "WL"], free={"Omegam": 0.01}, opts={"ell_sampling": 12, "pivot_z_IA": 0.3}),
+    # GCph on the cdm+baryon ("clustering") spectrum, lensing on total matter
+    "photo_var_clustering": dict(obs=["WL", "GCph"], free={"Omegam": 0.01, "h": 0.01},
+                                 opts={"ell_sampling": 12, "GCph_Tracer": "clustering"}),
     # photo-z parameters free: their stencil points carry their own n_i(z) windows and lensing efficiencies
     "photo_var_photoz": dict(obs=["WL", "GCph"], free={"Omegam": 0.01, "sigma_b": 0.02, "zb": 0.002, "fout": 0.02},
                              opts={"ell_sampling": 12}),

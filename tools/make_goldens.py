@@ -244,6 +244,9 @@ PHOTO_VARIANTS = {
     "photo_var_linear_pk": dict(obs=["WL", "GCph"], free={"Omegam": 0.01, "h": 0.01}, options_extra={"ell_sampling": 16, "nonlinear": False}),
     "photo_var_sqrtbias": dict(obs=["GCph"], free={"sigma8": 0.01}, options_extra={"ell_sampling": 16}, specifications={"ph_bias_model": "sqrt"}),
     "photo_var_gcfirst": dict(obs=["GCph", "WL"], free={"Omegam": 0.01}, options_extra={"ell_sampling": 12, "pivot_z_IA": 0.3}),
+    # GCph on the cdm+baryon spectrum, lensing on total matter
+    "photo_var_clustering": dict(obs=["WL", "GCph"], free={"Omegam": 0.01, "h": 0.01},
+                                 options_extra={"ell_sampling": 12, "GCph_Tracer": "clustering"}),
     # photo-z parameters as free parameters: each of their stencil points has its own n_i(z) windows (zb has fiducial 0:
     # absolute step)
     "photo_var_photoz": dict(obs=["WL", "GCph"], free={"Omegam": 0.01, "sigma_b": 0.02, "zb": 0.002, "fout": 0.02},
