@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -34,7 +35,7 @@ struct cfp_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t aux = nullptr;  // second stream for callers that overlap a running batch with the next one's uploads
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int64_t launches = 0;
+  std::atomic<int64_t> launches{0};  // plans of one context may be driven from two host threads (pipelined batches)
   double last_ms = 0.0;
   cudaMemPool_t pool = nullptr;  // stream-ordered arena: plan create/destroy never reach the driver allocator
 };

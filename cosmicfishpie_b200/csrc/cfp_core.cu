@@ -75,7 +75,7 @@ extern "C" int cfp_ctx_sync(cfp_ctx* ctx) {
 
 extern "C" void* cfp_ctx_aux_stream(cfp_ctx* ctx) { return ctx ? (void*)ctx->aux : nullptr; }
 
-extern "C" int64_t cfp_ctx_launch_count(const cfp_ctx* ctx) { return ctx ? ctx->launches : -1; }
+extern "C" int64_t cfp_ctx_launch_count(const cfp_ctx* ctx) { return ctx ? ctx->launches.load() : -1; }
 
 extern "C" double cfp_ctx_last_run_ms(const cfp_ctx* ctx) { return ctx ? ctx->last_ms : -1.0; }
 
