@@ -435,6 +435,8 @@ def run_gpu(args):
     Ls = SpectroLikelihood(cosmoFM_data=fm_sp)
     ks = [k for k in fm_sp.freeparams if k.startswith("lnbg")]
     like_spectro = like_block(Ls, ks, fm_sp.allparams, 2048, 0.01)
+    Ll = SpectroLikelihood(cosmoFM_data=fm_sp, leg_flag="legendre")
+    like_legendre = like_block(Ll, ks, fm_sp.allparams, 2048, 0.01)
 
     # ---- C ABI only: plan_create from host buffers + run + fetch -------------------------------------
     def cabi_step():
@@ -482,6 +484,7 @@ def run_gpu(args):
             "cabi_e2e": {"value": world / t_cabi, "unit": "Fisher/s", "s_per_step": t_cabi,
                          "what": "cfp_*_plan_create(host buffers) + run + fetch, table bank resident"},
             "likelihood": {"photo_3x2pt_13bins": like_photo, "spectro_wedges_129x8193": like_spectro,
+                           "spectro_legendre_129x8193": like_legendre,
                            "scaling": "weak", "what": "loglike_batch through the public API (host prep + H2D + kernels + "
                                                       "D2H), nuisance parameters drawn around the fiducial"},
             "gpu_launches": int(launches_timed),

@@ -36,7 +36,7 @@ EXPORTS = [
     "cfp_legendre_project", "cfp_legendre_covariance", "cfp_legendre_chi2",
     "cfp_bank_upload_rows", "cfp_host_alloc", "cfp_host_free", "cfp_spectro_plan_chi2_dev", "cfp_dev_upload",
     "cfp_dev_release", "cfp_photo_plan_create_zmap", "cfp_ctx_aux_stream", "cfp_photo_plan_create_ex",
-    "cfp_photo_plan_set_gc_table",
+    "cfp_photo_plan_set_gc_table", "cfp_spectro_plan_chi2_legendre",
 ]
 
 
@@ -86,6 +86,7 @@ def load():
     lib.cfp_host_alloc.argtypes = [_vp, C.c_size_t, C.POINTER(_vp)]
     lib.cfp_host_free.argtypes = [_vp, _vp]
     lib.cfp_spectro_plan_chi2_dev.argtypes = [_vp, _vp, _dp, _dp, _vp]
+    lib.cfp_spectro_plan_chi2_legendre.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp, _vp]
     lib.cfp_dev_upload.argtypes = [_vp, _dp, C.c_size_t, C.POINTER(_vp)]
     lib.cfp_dev_release.argtypes = [_vp, _vp]
     lib.cfp_bank_eval.argtypes = [_vp, _vp, C.c_int, C.c_int, _dp, _dp, C.c_size_t, _dp]
@@ -462,6 +463,18 @@ class SpectroPlan:
             return out
         _check(self.ctx.lib.cfp_spectro_plan_chi2(self.handle, _p(data), _p(shot), _p(sd), _p(out),
                                                   _vp(stream) if stream else None), "cfp_spectro_plan_chi2")
+        return out
+
+    def chi2_legendre(self, pl_data, icov, lw, shot, stream: int = 0) -> np.ndarray:
+        """Multipole chi^2 of every point of the plan: data multipoles (Nk, Z, 3), their inverse covariance
+        (Nk, Z, 3, 3), Legendre weights (3, Nmu), shot noise (S, Z)  (cfp_spectro_plan_chi2_legendre)."""
+        pl_data, icov, lw, shot = f64(pl_data), f64(icov), f64(lw), f64(shot)
+        assert pl_data.shape == (self.Nk, self.Z, 3) and icov.shape == (self.Nk, self.Z, 3, 3)
+        assert lw.shape == (3, self.Nmu) and shot.shape == (self.S, self.Z)
+        out = np.empty(self.S)
+        _check(self.ctx.lib.cfp_spectro_plan_chi2_legendre(self.handle, _p(pl_data), _p(icov), _p(lw), _p(shot), _p(out),
+                                                           _vp(stream) if stream else None),
+               "cfp_spectro_plan_chi2_legendre")
         return out
 
     def fetch(self, lnp=False, derivs=False):

@@ -920,6 +920,99 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_chi2_kernel(SpectroParams 
   }
 }
 
+// Legendre-multipole chi^2 of a batch of points, fused (reference: spectro_like.py:48-56, 125-140, 192-233): a thread
+// owns one wavenumber, walks down the mu rows accumulating P_l(k) = sum_mu lw_l(mu) P_t(k, mu) for l = 0, 2, 4 of up
+// to LEG_CH points that share everything but the bias, then contracts (P_l,data - P_l)^T C^-1 (P_l,data - P_l) with
+// the 3x3 inverse covariance of its (k, bin).  The theory lattices never exist in memory.
+// partial[s][zb][cta] = this CTA's share of chi2[s].  Requires Nmu <= CHI_ROWS (all rows staged at once).
+constexpr int LEG_CH = 4;
+__global__ void __launch_bounds__(TILE, 4) spectro_legendre_chi2_kernel(
+    SpectroParams P, const double* __restrict__ pl_data /*[Nk][Z][3]*/, const double* __restrict__ icov /*[Nk][Z][9]*/,
+    const double* __restrict__ lw /*[3][Nmu]*/, const double* __restrict__ shot, const int* __restrict__ ch_zb,
+    const int* __restrict__ ch_off, const int* __restrict__ ch_cnt, const int* __restrict__ mem_s,
+    double* __restrict__ partial) {
+  __shared__ SDev sp;
+  __shared__ RowC rows[CHI_ROWS];
+  __shared__ double slw[3][CHI_ROWS];
+  __shared__ double red[LEG_CH][TILE / 32];
+  __shared__ double mb[LEG_CH], mx[LEG_CH];
+  __shared__ int ms[LEG_CH];
+  __shared__ MathTab mt;
+  const int tid = threadIdx.x;
+  const int zb = ch_zb[blockIdx.y], off = ch_off[blockIdx.y], cnt = ch_cnt[blockIdx.y];
+  const int s0 = mem_s[off];
+  if (tid < (int)(sizeof(SDev) / sizeof(double)))
+    reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S + s0)[tid];
+  math_tables_fill(mt, tid, TILE);
+  __syncthreads();
+  if (tid < LEG_CH) {
+    const int sj = mem_s[off + min(tid, cnt - 1)];
+    ms[tid] = sj;
+    mb[tid] = P.sdev[(size_t)zb * P.S + sj].bias;
+    mx[tid] = 1.0 / P.nbar[zb] + shot[(size_t)sj * P.Z + zb] + sp.pshot;
+  }
+  for (int r = tid; r < P.Nmu; r += TILE) {
+    rows[r] = row_consts(sp, P.flags, __ldg(P.mu + r), __ldg(P.smu + r));
+    slw[0][r] = lw[r], slw[1][r] = lw[P.Nmu + r], slw[2][r] = lw[2 * P.Nmu + r];
+  }
+  __syncthreads();
+  const int nkb = (P.Nk + TILE - 1) / TILE;
+  double acc[LEG_CH];
+#pragma unroll
+  for (int j = 0; j < LEG_CH; ++j) acc[j] = 0.0;
+  for (int kb = blockIdx.x; kb < nkb; kb += gridDim.x) {
+    const int ki = kb * TILE + tid;
+    if (ki >= P.Nk) continue;
+    const double k = __ldg(P.k + ki);
+    int hA = -1, hB = -1, hN = -1;
+    double a0[LEG_CH], a2[LEG_CH], a4[LEG_CH];
+#pragma unroll
+    for (int j = 0; j < LEG_CH; ++j) a0[j] = a2[j] = a4[j] = 0.0;
+    for (int r = 0; r < P.Nmu; ++r) {
+      double err2, qf, F, W;
+      eval_x(mt, sp, rows[r], P.flags, k, hA, hB, hN, err2, qf, F, W);
+      const double We = W * tab_exp_neg(mt, -err2);
+      const double w0 = slw[0][r], w2 = slw[1][r], w4 = slw[2][r];
+#pragma unroll
+      for (int j = 0; j < LEG_CH; ++j)
+        if (j < cnt) {
+          const double kaiser = fma(mb[j], qf, F);
+          const double Pt = fma(kaiser * kaiser, We, mx[j]);
+          a0[j] = fma(w0, Pt, a0[j]);
+          a2[j] = fma(w2, Pt, a2[j]);
+          a4[j] = fma(w4, Pt, a4[j]);
+        }
+    }
+    const double* pd = pl_data + ((size_t)ki * P.Z + zb) * 3;
+    const double* M = icov + ((size_t)ki * P.Z + zb) * 9;
+    const double p0 = __ldg(pd), p2 = __ldg(pd + 1), p4 = __ldg(pd + 2);
+    double m[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) m[e] = __ldg(M + e);
+#pragma unroll
+    for (int j = 0; j < LEG_CH; ++j)
+      if (j < cnt) {
+        const double d0 = p0 - a0[j], d1 = p2 - a2[j], d2 = p4 - a4[j];
+        acc[j] += d0 * (m[0] * d0 + m[1] * d1 + m[2] * d2) + d1 * (m[3] * d0 + m[4] * d1 + m[5] * d2) +
+                  d2 * (m[6] * d0 + m[7] * d1 + m[8] * d2);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < LEG_CH; ++j) {
+    double a = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((tid & 31) == 0) red[j][tid >> 5] = a;
+  }
+  __syncthreads();
+  if (tid < cnt) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < TILE / 32; ++w) t += red[tid][w];
+    partial[((size_t)ms[tid] * P.Z + zb) * gridDim.x + blockIdx.x] = t;
+  }
+}
+
 // stand-alone wedge chi^2 on given lattices: grid (gx, Z, S)
 __global__ void __launch_bounds__(TILE) wedge_chi2_kernel(int Z, int Nmu, int Nk, const double* __restrict__ theory,
                                                           const double* __restrict__ data, const double* __restrict__ k,
@@ -1197,6 +1290,64 @@ static int spectro_prepare(cfp_spectro_plan* pl, const SpectroParams& P, cudaStr
   return CFP_OK;
 }
 
+// Chunks of a likelihood batch: per bin, points whose scalar blocks are identical except for the bias are evaluated
+// together (up to `chunk` per chunk).  Grouping by a hash of the block bytes, verified against the group's
+// representative.  Chunk list = [groups of 2..chunk points | single points] (n_grp, n_one of each).
+static void spectro_build_chunks(const cfp_spectro_plan* pl, int chunk, std::vector<int>& ch_zb, std::vector<int>& ch_off,
+                                 std::vector<int>& ch_cnt, std::vector<int>& mem_s, int& n_grp, int& n_one) {
+  const int S = pl->S, Z = pl->Z;
+  std::vector<int> one_zb, one_off;
+  const double* sc = pl->scal_h.data();
+  auto key_equal = [&](int a, int b, int zb) {
+    const double* x = sc + ((size_t)a * Z + zb) * CFP_SP_NSCAL;
+    const double* y = sc + ((size_t)b * Z + zb) * CFP_SP_NSCAL;
+    for (int q = 0; q < CFP_SP_NSCAL; ++q)
+      if (q != CFP_SP_BIAS && std::memcmp(x + q, y + q, sizeof(double)) != 0) return false;
+    return true;
+  };
+  std::vector<std::pair<uint64_t, int>> order(S);
+  for (int zb = 0; zb < Z; ++zb) {
+    for (int sidx = 0; sidx < S; ++sidx) {
+      const double* x = sc + ((size_t)sidx * Z + zb) * CFP_SP_NSCAL;
+      uint64_t h = 1469598103934665603ull;  // FNV-1a over the 8-byte words of the block, bias excluded
+      for (int q = 0; q < CFP_SP_NSCAL; ++q) {
+        if (q == CFP_SP_BIAS) continue;
+        uint64_t w;
+        std::memcpy(&w, x + q, sizeof(w));
+        h = (h ^ w) * 1099511628211ull;
+      }
+      order[sidx] = {h, sidx};
+    }
+    std::sort(order.begin(), order.end());
+    int i = 0;
+    while (i < S) {
+      // members of the hash run that really equal its first element form one group; the others (collisions, never
+      // seen in practice) become singletons
+      const int rep = order[i].second;
+      int j = i;
+      std::vector<int> same, other;
+      while (j < S && order[j].first == order[i].first) {
+        (key_equal(order[j].second, rep, zb) ? same : other).push_back(order[j].second);
+        ++j;
+      }
+      for (size_t o = 0; o < same.size(); o += chunk) {
+        const int c = (int)std::min<size_t>(chunk, same.size() - o);
+        auto& Z_ = c == 1 ? one_zb : ch_zb;
+        auto& O_ = c == 1 ? one_off : ch_off;
+        Z_.push_back(zb), O_.push_back((int)mem_s.size());
+        if (c > 1) ch_cnt.push_back(c);
+        mem_s.insert(mem_s.end(), same.begin() + o, same.begin() + o + c);
+      }
+      for (int sidx : other) one_zb.push_back(zb), one_off.push_back((int)mem_s.size()), mem_s.push_back(sidx);
+      i = j;
+    }
+  }
+  n_grp = (int)ch_zb.size(), n_one = (int)one_zb.size();
+  ch_zb.insert(ch_zb.end(), one_zb.begin(), one_zb.end());
+  ch_off.insert(ch_off.end(), one_off.begin(), one_off.end());
+  ch_cnt.insert(ch_cnt.end(), (size_t)n_one, 1);
+}
+
 static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const double* data_dev, const double* shot_h,
                              const double* shot_data_h, double* chi2_h, void* stream);
 
@@ -1220,61 +1371,9 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
   const int S = pl->S, Z = pl->Z;
   const size_t lattice = (size_t)pl->Nmu * pl->Nk;
   const int64_t ntile = (int64_t)((lattice + TILE - 1) / TILE);
-  // Chunks: per bin, points whose scalar blocks are identical except for the bias are evaluated together (up to
-  // CHI_CH per chunk).  Grouping by a hash of the block bytes, verified against the group's representative.
-  std::vector<int> ch_zb, ch_off, ch_cnt, mem_s, one_zb, one_off;
-  {
-    const double* sc = pl->scal_h.data();
-    auto key_equal = [&](int a, int b, int zb) {
-      const double* x = sc + ((size_t)a * Z + zb) * CFP_SP_NSCAL;
-      const double* y = sc + ((size_t)b * Z + zb) * CFP_SP_NSCAL;
-      for (int q = 0; q < CFP_SP_NSCAL; ++q)
-        if (q != CFP_SP_BIAS && std::memcmp(x + q, y + q, sizeof(double)) != 0) return false;
-      return true;
-    };
-    std::vector<std::pair<uint64_t, int>> order(S);
-    for (int zb = 0; zb < Z; ++zb) {
-      for (int sidx = 0; sidx < S; ++sidx) {
-        const double* x = sc + ((size_t)sidx * Z + zb) * CFP_SP_NSCAL;
-        uint64_t h = 1469598103934665603ull;  // FNV-1a over the 8-byte words of the block, bias excluded
-        for (int q = 0; q < CFP_SP_NSCAL; ++q) {
-          if (q == CFP_SP_BIAS) continue;
-          uint64_t w;
-          std::memcpy(&w, x + q, sizeof(w));
-          h = (h ^ w) * 1099511628211ull;
-        }
-        order[sidx] = {h, sidx};
-      }
-      std::sort(order.begin(), order.end());
-      int i = 0;
-      while (i < S) {
-        // members of the hash run that really equal its first element form one group; the others (collisions,
-        // never seen in practice) become singletons
-        const int rep = order[i].second;
-        int j = i;
-        std::vector<int> same, other;
-        while (j < S && order[j].first == order[i].first) {
-          (key_equal(order[j].second, rep, zb) ? same : other).push_back(order[j].second);
-          ++j;
-        }
-        for (size_t o = 0; o < same.size(); o += CHI_CH) {
-          const int c = (int)std::min<size_t>(CHI_CH, same.size() - o);
-          auto& Z_ = c == 1 ? one_zb : ch_zb;
-          auto& O_ = c == 1 ? one_off : ch_off;
-          Z_.push_back(zb), O_.push_back((int)mem_s.size());
-          if (c > 1) ch_cnt.push_back(c);
-          mem_s.insert(mem_s.end(), same.begin() + o, same.begin() + o + c);
-        }
-        for (int sidx : other) one_zb.push_back(zb), one_off.push_back((int)mem_s.size()), mem_s.push_back(sidx);
-        i = j;
-      }
-    }
-  }
-  // chunk list = [groups of 2..CHI_CH points | single points]; the two parts run as two launches
-  const int n_grp = (int)ch_zb.size(), n_one = (int)one_zb.size();
-  ch_zb.insert(ch_zb.end(), one_zb.begin(), one_zb.end());
-  ch_off.insert(ch_off.end(), one_off.begin(), one_off.end());
-  ch_cnt.insert(ch_cnt.end(), (size_t)n_one, 1);
+  std::vector<int> ch_zb, ch_off, ch_cnt, mem_s;
+  int n_grp = 0, n_one = 0;
+  spectro_build_chunks(pl, CHI_CH, ch_zb, ch_off, ch_cnt, mem_s, n_grp, n_one);
   const int nch = n_grp + n_one;
   // CTAs per chunk: each takes every gx-th block of TILE wavenumbers.  Pick the split that needs the fewest
   // (waves of resident CTAs) x (blocks per CTA), i.e. fills the GPU for small batches and avoids a ragged last wave
@@ -1355,6 +1454,90 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
 #undef CHI_TRY
   if (e != cudaSuccess) {
     cfp_set_error("cfp_spectro_plan_chi2: %s", cudaGetErrorString(e));
+    return CFP_ERR_CUDA;
+  }
+  return CFP_OK;
+}
+
+extern "C" int cfp_spectro_plan_chi2_legendre(cfp_spectro_plan* pl, const double* pl_data_h, const double* icov_h,
+                                              const double* lw_h, const double* shot_h, double* chi2_h, void* stream) {
+  CFP_REQUIRE(pl && pl_data_h && icov_h && lw_h && shot_h && chi2_h, "NULL argument");
+  CFP_REQUIRE(pl->Nmu <= CHI_ROWS, "the fused multipole path stages every mu row at once (Nmu <= 256)");
+  cfp_ctx* ctx = pl->ctx;
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const int S = pl->S, Z = pl->Z, Nk = pl->Nk;
+  std::vector<int> ch_zb, ch_off, ch_cnt, mem_s;
+  int n_grp = 0, n_one = 0;
+  spectro_build_chunks(pl, LEG_CH, ch_zb, ch_off, ch_cnt, mem_s, n_grp, n_one);
+  const int nch = n_grp + n_one;
+  const int nkb = (Nk + TILE - 1) / TILE;
+  int gx = 1;
+  {
+    const int64_t slots = 4 * (int64_t)ctx->sm_count;
+    int64_t best = INT64_MAX;
+    for (int g = 1; g <= std::min(nkb, 64); ++g) {
+      const int64_t cost = (((int64_t)g * nch + slots - 1) / slots) * ((nkb + g - 1) / g);
+      if (cost < best) best = cost, gx = g;
+    }
+  }
+  int *ch_zb_d = nullptr, *ch_off_d = nullptr, *ch_cnt_d = nullptr, *mem_s_d = nullptr;
+  double *pd_d = nullptr, *ic_d = nullptr, *lw_d = nullptr, *shot_d = nullptr, *part_d = nullptr, *chi2_d = nullptr;
+  auto cleanup = [&]() {
+    for (void* q : {(void*)pd_d, (void*)ic_d, (void*)lw_d, (void*)shot_d, (void*)part_d, (void*)chi2_d, (void*)ch_zb_d,
+                    (void*)ch_off_d, (void*)ch_cnt_d, (void*)mem_s_d})
+      cfp_dev_free(ctx, q);
+  };
+  int rc;
+#define LEG_TRY(x)      \
+  do {                  \
+    rc = (x);           \
+    if (rc != CFP_OK) { \
+      cleanup();        \
+      return rc;        \
+    }                   \
+  } while (0)
+  LEG_TRY(cfp_upload(ctx, pl_data_h, (size_t)Nk * Z * 3, &pd_d));
+  LEG_TRY(cfp_upload(ctx, icov_h, (size_t)Nk * Z * 9, &ic_d));
+  LEG_TRY(cfp_upload(ctx, lw_h, (size_t)3 * pl->Nmu, &lw_d));
+  LEG_TRY(cfp_upload(ctx, shot_h, (size_t)S * Z, &shot_d));
+  LEG_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S * Z * gx, &part_d));
+  LEG_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d));
+  LEG_TRY(cfp_upload(ctx, ch_zb.data(), ch_zb.size(), &ch_zb_d));
+  LEG_TRY(cfp_upload(ctx, ch_off.data(), ch_off.size(), &ch_off_d));
+  LEG_TRY(cfp_upload(ctx, ch_cnt.data(), ch_cnt.size(), &ch_cnt_d));
+  LEG_TRY(cfp_upload(ctx, mem_s.data(), mem_s.size(), &mem_s_d));
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    cleanup();
+    cfp_set_error("cfp_spectro_plan_chi2_legendre: upload failed");
+    return CFP_ERR_CUDA;
+  }
+  if (!pl->run0) {
+    cudaEventCreate(&pl->run0);
+    cudaEventCreate(&pl->run1);
+  }
+  cudaEventRecord(pl->run0, st);
+  SpectroParams P;
+  spectro_fill_params(pl, 16, P);
+  LEG_TRY(spectro_prepare(pl, P, st));
+  for (int c0 = 0; c0 < nch; c0 += 65535) {
+    const int nc = std::min(65535, nch - c0);
+    spectro_legendre_chi2_kernel<<<dim3(gx, nc), TILE, 0, st>>>(P, pd_d, ic_d, lw_d, shot_d, ch_zb_d + c0, ch_off_d + c0,
+                                                               ch_cnt_d + c0, mem_s_d, part_d);
+    ctx->launches++;
+  }
+  spectro_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Z * gx, part_d, chi2_d);
+  ctx->launches++;
+  cudaEventRecord(pl->run1, st);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(chi2_h, chi2_d, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  if (e == cudaSuccess && cudaEventElapsedTime(&ms, pl->run0, pl->run1) == cudaSuccess) ctx->last_ms = ms;
+  cleanup();
+#undef LEG_TRY
+  if (e != cudaSuccess) {
+    cfp_set_error("cfp_spectro_plan_chi2_legendre: %s", cudaGetErrorString(e));
     return CFP_ERR_CUDA;
   }
   return CFP_OK;

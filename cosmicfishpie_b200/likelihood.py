@@ -439,6 +439,25 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
         lw = _legendre_weights(fm.Pk_mugrid)
         inv_n = np.array([1 / fm.pk_cov.n_density(z) for z in zs])
         out = np.empty(len(param_dicts))
+        if fm.Pk_musamp <= 256:  # fused: the theory lattices are never materialised
+            for i0 in range(0, len(param_dicts), 4096):
+                pts, shots = zip(*[_spectro_point(p, fm) for p in param_dicts[i0:i0 + 4096]])
+                cs = pts[0].cosmo_set
+                S, Z = len(pts), len(zs)
+                scal = np.array([[p.scalar_block(z) for z in zs] for p in pts])
+                used = {int(c) for c in scal[:, :, _lib.SP_COSMO].ravel()}
+                pk, pp = spectro_mod._pnw_arrays(cs, zs, set() if pts[0].linear_switch else used)
+                tabs = spectro_mod.table_slots(fm.settings)
+                plan = _lib.SpectroPlan(
+                    cs.ctx or _lib.default_context(), cs.bank(), k=fm.Pk_kgrid, mu=fm.Pk_mugrid,
+                    wk=simpson_weights(fm.Pk_kgrid), wmu=simpson_weights(fm.Pk_mugrid), scal=scal,
+                    alias=np.tile(np.arange(S, dtype=np.int32)[:, None], (1, Z)), pnw_k=pk, pnw_p=pp,
+                    stw=np.zeros((1, S)), stden=np.ones(1), ps_bin=np.array([-1], np.int32), ps_src=0,
+                    nbar=1.0 / inv_n, vol=fm.pk_cov.volume_survey_array, flags=pts[0].flags(), tab_plin=tabs[0],
+                    tab_f=tabs[1])
+                out[i0:i0 + S] = plan.chi2_legendre(self.data_obs, self._inv_cov_legendre, lw, np.array(shots))
+                plan.close()
+            return out
         lattice_bytes = 8 * len(zs) * fm.Pk_musamp * fm.Pk_ksamp
         chunk = max(1, min(512, int(2**30 // lattice_bytes)))
         for i0 in range(0, len(param_dicts), chunk):
@@ -451,9 +470,9 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
     def chi2_matrix(self, names, matrix) -> np.ndarray:
         """Array fast path of the wedge chi^2 for a batch given as a matrix: per-point scalar blocks are assembled
         from one cached block per (cosmology, bin) plus the nuisance columns, no Python object per point."""
-        if self.leg_flag != "wedges":
-            return self.chi2_batch([dict(zip(names, row)) for row in matrix])
         fm = self.cosmo_theory
+        if self.leg_flag != "wedges" and fm.Pk_musamp > 256:  # the fused multipole kernel stages <= 256 mu rows
+            return self.chi2_batch([dict(zip(names, row)) for row in matrix])
         fid_obs = fm.pk_obs_fid
         cs = fid_obs.cosmo_set
         zs = list(fm.pk_cov.global_z_bin_mids)
@@ -514,7 +533,11 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
                 stw=np.zeros((1, S)), stden=np.ones(1), ps_bin=np.array([-1], np.int32), ps_src=0, nbar=nbar,
                 vol=fm.pk_cov.volume_survey_array, flags=fid_obs.flags(),
                 tab_plin=spectro_mod.table_slots(fm.settings)[0], tab_f=spectro_mod.table_slots(fm.settings)[1])
-            out[i0:i0 + S] = plan.chi2(shot[i0:i0 + S], data_dev=self._data_on_device(plan.ctx))
+            if self.leg_flag == "wedges":
+                out[i0:i0 + S] = plan.chi2(shot[i0:i0 + S], data_dev=self._data_on_device(plan.ctx))
+            else:
+                out[i0:i0 + S] = plan.chi2_legendre(self.data_obs, self._inv_cov_legendre, _legendre_weights(fm.Pk_mugrid),
+                                                    shot[i0:i0 + S])
             plan.close()
         return out
 

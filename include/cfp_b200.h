@@ -302,6 +302,13 @@ int cfp_spectro_plan_chi2(cfp_spectro_plan* plan, const double* data_h, const do
  * thousands of batches against ONE data vector, which therefore crosses PCIe once, not once per batch. */
 int cfp_spectro_plan_chi2_dev(cfp_spectro_plan* plan, const double* data_d, const double* shot_h, double* chi2_h,
                               void* stream);
+
+/* Legendre multipoles (replaces legendre_Pgg + compute_chi2_legendre over a batch, spectro_like.py:48-56,125-140,
+ * 192-233), fused: chi2[s] = sum_{k,z} d^T C^-1 d,  d_l = P_l,data(k,z) - sum_mu lw_l(mu) P_t(s; k, mu, z), l = 0,2,4.
+ *   pl_data_h[Nk][Z][3], icov_h[Nk][Z][3][3] (cfp_legendre_covariance), lw_h[3][Nmu] = (2l+1) * Simpson weight * L_l(mu),
+ *   shot_h[S][Z].  Nmu <= 256.                                                                                    */
+int cfp_spectro_plan_chi2_legendre(cfp_spectro_plan* plan, const double* pl_data_h, const double* icov_h,
+                                   const double* lw_h, const double* shot_h, double* chi2_h, void* stream);
 int cfp_dev_upload(cfp_ctx* ctx, const double* src_h, size_t n_doubles, double** out_d);
 int cfp_dev_release(cfp_ctx* ctx, double* p_d);
 

@@ -152,6 +152,13 @@ def test_spectro_legendre_matches_reference(spectro_fm):
     assert np.max(np.abs(chi2[1:] - ref[1:]) / ref[1:]) < 1e-7
     th = like.compute_theory(dicts[2])
     assert abs(like.compute_chi2(th) - ref[2]) / ref[2] < 1e-7
+    # the array fast path (fused multipole kernel, points grouped by shared blocks) against the point-by-point route
+    keys = ["lnbg_1", "lnbg_2", "lnbg_3", "lnbg_4", "Ps_2"]
+    fid = np.array([allp[k] for k in keys])
+    mat = fid + np.array([0.01, 0.01, 0.01, 0.01, 5.0]) * np.random.default_rng(2).standard_normal((21, len(keys)))
+    fast = like.chi2_matrix(keys, mat)
+    slow = np.array([like.compute_chi2(like.compute_theory(dict(zip(keys, row)))) for row in mat[:5]])
+    assert np.max(np.abs(fast[:5] - slow) / slow) < 1e-9
 
 
 def test_photo_batch_pipeline_equals_single_chunks(photo_fm):
