@@ -11,8 +11,8 @@ fused kernel, which never writes the per-parameter lattices to HBM; touching eit
 kernel in materialising mode.
 
 Extra options understood here (all optional, defaults reproduce the reference):
-  options["stencil"]   "3PT" (default) | "5PT" | "4PT_FWD"  -- the reference ignores
-                       settings["derivatives"] and always uses 3PT, so a separate key is used
+  options["stencil"]   "3PT" (default) | "5PT" | "4PT_FWD" | "STEM" (photometric probes only)  -- the reference
+                       ignores settings["derivatives"] and always uses 3PT, so a separate key is used
   options["device"]    CUDA device index (default LOCAL_RANK or 0)
 """
 from __future__ import annotations

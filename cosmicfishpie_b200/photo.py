@@ -550,22 +550,25 @@ class PhotoCov:
 
     def build_job(self, freeparams=None) -> PhotoJob:
         fp = self._freeparams(freeparams)
-        pts, den = stencils.get(self.stencil)
+        ext_eps = (self._cfg.external or {}).get("eps_values") if self.stencil == "STEM" else None
         points = [dict(self.allparsfid)]
         rows, stden = [], np.ones(len(fp))
+        self._offsets = []
         for ip, par in enumerate(fp):
-            h = stencils.stepsize(self.allparsfid[par], fp[par])
-            stden[ip] = den * h
-            row = {}
-            for m, w in pts:
-                if m == 0:
+            offs, stden[ip] = stencils.offsets_and_weights(self.stencil, self.allparsfid[par], fp[par], ext_eps)
+            row, used = {}, []
+            for off, w in offs:
+                if off == 0:
                     row[0] = row.get(0, 0.0) + w
+                    used.append((0, off))
                     continue
                 ap = dict(self.allparsfid)  # flat {name: number}
-                ap[par] = ap[par] + m * h
+                ap[par] = ap[par] + off
                 points.append(ap)
                 row[len(points) - 1] = w
+                used.append((len(points) - 1, off))
             rows.append(row)
+            self._offsets.append(used)
         stw = np.zeros((len(fp), len(points)))
         for ip, row in enumerate(rows):
             for s, w in row.items():
@@ -594,10 +597,27 @@ class PhotoCov:
             F = cdist.allreduce_numpy(F)
             plan.set_slice(0, nbins)
             plan.run()  # every rank keeps the full C_ell set for compute_covmat()/compute_derivs()
+        if self.stencil == "STEM":
+            self._check_stem_residuals()
         t2 = time()
         self.timings = {"host_prep_s": t1 - t0, "device_s": t2 - t1}
         self.fisher = F
         return F
+
+    def _check_stem_residuals(self):
+        """derivatives.py:402-419 trims the outermost points while the straight-line fit of any C_ell leaves a sum of
+        squared residuals above an ABSOLUTE 1e-3.  The device stencil uses all points: verify that the reference
+        would have, too (spectra <= 1e-4 cannot fail this), and refuse loudly otherwise."""
+        cl = self._all_cls()
+        for par, used in zip(self.parnames, self._offsets):
+            x = np.array([off for _, off in used])
+            y = np.array([cl[s] for s, _ in used])
+            w, den = stencils.slope_weights(x)
+            slope = np.tensordot(w, y, axes=(0, 0)) / den
+            fit = np.mean(y, axis=0) + (x - np.mean(x)).reshape((-1,) + (1,) * (y.ndim - 1)) * slope
+            if np.max(np.sum((y - fit) ** 2, axis=0)) > stencils.STEM_THRESHOLD:
+                raise NotImplementedError(f"SteM derivative of {par}: the fit residual exceeds {stencils.STEM_THRESHOLD}; "
+                                          "the reference would trim the stencil per multipole, which is not supported")
 
     def _all_cls(self):
         if self._job is None:

@@ -421,6 +421,8 @@ class SpectroJob:
         self.freeparams = dict(freeparams)
         self.parnames = list(self.freeparams)
         self.fiducial_allpars = fiducial_obs.fiducial_allpars
+        if stencil == "STEM":  # derivatives.py:427
+            raise ValueError("STEM derivative not availabe for spectropscopic probes yet!")
         pts, den = stencils.get(stencil)
         cs = fiducial_obs.cosmo_set
         fid_all = self.fiducial_allpars

@@ -316,6 +316,40 @@ class PhotoCov:
         return cov
 
 
+def _stem_derivative(pc, par, eps_values, threshold=1.0e-3, numstem=11):
+    """derivatives.derivative_stem with external tables (derivatives.py:348-441): straight-line fit through the
+    observable at fid*(1 +- eps) for every tabulated eps; the outermost points are dropped while the fit residual
+    exceeds an ABSOLUTE 1e-3 (never, for angular spectra of order 1e-5 and below).  Restated as written, including
+    the trimmed fit pairing the shortened abscissae with the FIRST ordinates (:410-413)."""
+    fid = pc.allparsfid
+    eps_v = np.array(eps_values)
+    d_eps = np.concatenate([-eps_v[::-1], eps_v])
+    stepsize = fid[par] * d_eps if fid[par] != 0.0 else d_eps
+    obs_mod = []
+    for step in stepsize:
+        ap = copy.deepcopy(fid)
+        ap[par] = ap[par] + step
+        obs_mod.append(pc.getcls(ap))
+    dpar = {"ells": obs_mod[0]["ells"]}
+    for key in obs_mod[0]:
+        if key == "ells":
+            continue
+        temp = []
+        for ind in range(len(dpar["ells"])):
+            residuals, counter, tempstep = 1000, 0, stepsize
+            while residuals > threshold:
+                fit = np.polyfit(tempstep, [obs_mod[i][key][ind] for i in range(len(tempstep))], 1, full=True)
+                residuals = fit[1]
+                if residuals > threshold:
+                    tempstep = tempstep[1:-1]
+                counter += 1
+                if numstem - counter < 3:
+                    raise RuntimeError(f"{par} derivative could not converge")
+            temp.append(fit[0][0])
+        dpar[key] = np.array(temp)
+    return dpar
+
+
 def photo_fisher(bank, specs, settings, observables, fiducial_cosmopars, photopars, IApars, biaspars,
                  freeparams, lumratio_table, return_all=False, stencil="3PT"):
     """FisherMatrix.compute() photo branch (cosmicfish.py:225-251, 643-744)."""
@@ -329,6 +363,9 @@ def photo_fisher(bank, specs, settings, observables, fiducial_cosmopars, photopa
     for par in freeparams:  # derivatives.py:131-207
         fid = pc.allparsfid
         step = fid[par] * freeparams[par] if fid[par] != 0.0 else freeparams[par]
+        if stencil == "STEM":
+            derivs[par] = _stem_derivative(pc, par, bank.eps_values)
+            continue
         from .spectro import STENCILS
 
         pts, den = STENCILS[stencil]

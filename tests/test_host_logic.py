@@ -161,6 +161,28 @@ def test_photo_job_assembly(extfiles, tmp_path):
     assert np.array_equal(job.ia[s_b3], job.ia[0]) and not np.array_equal(job.ia[-1], job.ia[0])
 
 
+def test_photo_stem_job_assembly(tmp_path):
+    """SteM with external tables: every free parameter (nuisance included) is stepped by +-eps for every tabulated eps,
+    cosmological points resolve to their own table folders, and the stencil rows hold the least-squares weights."""
+    from cosmicfishpie_b200 import photo
+    from cosmicfishpie_b200 import toy_tables as tt
+
+    eps = (0.01, 0.02, 0.03)
+    ext = {"tables": tt.make_bank(eps_values=eps, pars=("Omegam",)), "directory": "<memory>", "paramnames": list(tt.COSMO_KEYS),
+           "folder_paramnames": list(tt.COSMO_KEYS), "k-units": "1/Mpc", "r-units": "Mpc", "eps_values": list(eps)}
+    fm = make_fm(ext, tmp_path, ["WL"], {"Omegam": 0.01}, stencil="STEM", ell_sampling=8)
+    pc = photo.PhotoCov(fm.fiducialcosmopars, fm.photopars, fm.IApars, fm.photobiaspars, configuration=fm, stencil="STEM")
+    job = pc.build_job(fm.freeparams)
+    npar = 1 + 3
+    assert job.stw.shape == (npar, 1 + 6 * npar) and job.NC == 7
+    assert sorted(job.cosmo_of_s[1:7]) == [1, 2, 3, 4, 5, 6] and set(job.cosmo_of_s[7:]) == {0}
+    x = tt.FIDUCIAL["Omegam"] * np.array([-0.03, -0.02, -0.01, 0.01, 0.02, 0.03])
+    assert np.allclose(job.stw[0, 1:7], x, rtol=1e-14, atol=1e-18) and np.isclose(job.stden[0], np.sum(x * x), rtol=1e-14)
+    assert np.all(job.stw[0, 7:] == 0) and np.all(job.stw[:, 0] == 0)
+    assert [pc.points[s]["Omegam"] for s in range(1, 7)] == [tt.FIDUCIAL["Omegam"] + o for o in
+                                                            tt.FIDUCIAL["Omegam"] * np.array([-0.03, -0.02, -0.01, 0.01, 0.02, 0.03])]
+
+
 def test_stencils_are_exact_on_polynomials():
     from cosmicfishpie_b200 import stencils
 
@@ -173,6 +195,27 @@ def test_stencils_are_exact_on_polynomials():
     assert stencils.stepsize(0.32, 0.01) == 0.32 * 0.01 and stencils.stepsize(0.0, 0.01) == 0.01
     with pytest.raises(ValueError):
         stencils.get("POLY")
+
+
+def test_stem_stencil_is_the_least_squares_slope():
+    """derivatives.py:356-419: the SteM derivative is np.polyfit(steps, f, 1)[0]; as a fixed linear stencil it must
+    give the same slope, on the external (+-eps_values) and on the 11-point abscissae."""
+    from cosmicfishpie_b200 import stencils
+
+    rng = np.random.default_rng(11)
+    for fid, ext in ((0.32, (0.01, 0.02, 0.03)), (0.0, (0.01, 0.02, 0.03)), (-1.0, None), (0.0, None)):
+        offs, den = stencils.offsets_and_weights("STEM", fid, 0.01, ext)
+        x = np.array([o for o, _ in offs])
+        assert len(x) == (6 if ext else 11)
+        scale = fid if fid != 0.0 else 1.0
+        want = (np.concatenate([-np.array(ext)[::-1], ext]) if ext else np.linspace(-0.05, 0.05, 11)) * scale
+        assert np.array_equal(x, want)
+        y = 2.0e-6 * (1 + 3.0 * x + 40.0 * x * x) + 1e-12 * rng.standard_normal(len(x))
+        got = sum(w * yi for (_, w), yi in zip(offs, y)) / den
+        assert np.isclose(got, np.polyfit(x, y, 1)[0], rtol=1e-11)
+    # the classic stencils through the same interface: offsets m*h, denominator D*h
+    offs, den = stencils.offsets_and_weights("3PT", 0.32, 0.01)
+    assert offs == [(0.32 * 0.01, 1.0), (-(0.32 * 0.01), -1.0)] and den == 2.0 * (0.32 * 0.01)
 
 
 def test_fisher_container_roundtrip_and_add(tmp_path):

@@ -170,6 +170,30 @@ def test_photo_oracle_variants_bit_exact(obank, tag, obs, free, settings, spec_o
     assert np.array_equal(r["fisher"], g["fisher"])
 
 
+def test_photo_oracle_stem_bit_exact():
+    """SteM derivatives: the reference's derivative engine run on its own getcls with +-1, 2, 3 % tables, its
+    einsum assembly for the matrix (tools/make_goldens.py::photo_stem)."""
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.cosmo import Bank
+    from oracle.photo import default_photo_bias, finish_photo_specs, photo_fisher
+
+    g = golden("photo_stem")
+    eps = tuple(g["eps_values"])
+    ob = Bank(tt.make_bank(eps_values=eps, pars=("Omegam", "h")), tt.FIDUCIAL, tt.COSMO_KEYS, eps_values=eps)
+    sp = finish_photo_specs(yaml.safe_load(open(os.path.join(SPECDIR, "Euclid-Photometric-ISTF-Pessimistic.yaml")))["specifications"])
+    lum = np.load(os.path.join(REPO, "cosmicfishpie_b200", "data", "lumratio.npy"))
+    bias, ia = default_photo_bias(sp), dict(sp["IA_params"])
+    fp = {"Omegam": 0.01, "h": 0.01}
+    fp.update({k: sp["vary_ph_bias"] for k in bias if k != "bias_model"})
+    fp.update({k: sp["vary_IA_pars"] for k in ia if k != "IA_model"})
+    r = photo_fisher(ob, sp, {"ell_sampling": 10}, ["WL", "GCph"], dict(tt.FIDUCIAL), dict(sp["photo_z_params"]), ia, bias,
+                     fp, lum, return_all=True, stencil="STEM")
+    assert r["param_names"] == list(g["param_names"])
+    for par in ("Omegam", "b3", "AIA"):
+        assert np.array_equal(np.array([r["derivs"][par][k] for k in g["cl_keys"]]), g["dcl__" + par])
+    assert np.array_equal(r["fisher"], g["fisher"])
+
+
 LIKE_PHOTO = {"fid": {}, "nuis": {"b1": 1.02, "b7": 0.985, "AIA": 1.04, "etaIA": 0.97, "betaIA": 1.01},
               "cosmo": {"Omegam": 1.01}, "both": {"h": 0.99, "b3": 1.03, "AIA": 0.95}}
 LIKE_SPECTRO = {"fid": {}, "nuis": {"lnbg_1": 1.01, "lnbg_4": 0.99}, "cosmo": {"h": 1.01},

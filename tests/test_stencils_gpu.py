@@ -72,6 +72,43 @@ def test_photo_5pt_vs_oracle(bank3, tmp_path):
     assert np.max(np.abs(F.fisher_matrix - ref["fisher"]) / scale) < 1e-8
 
 
+def test_photo_stem_vs_reference_golden(tmp_path):
+    """SteM derivatives against the reference's own derivative engine and einsum assembly (golden photo_stem):
+    6-point straight-line fits through the +-1, 2, 3 % tables for all 15 parameters of a 3x2pt forecast."""
+    from conftest import golden
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    g = golden("photo_stem")
+    eps = tuple(float(e) for e in g["eps_values"])
+    ext = ext_of(tt.make_bank(eps_values=eps, pars=("Omegam", "h")))
+    ext["eps_values"] = list(eps)
+    o = base_options(tmp_path, stencil="STEM", ell_sampling=10, survey_name_photo="Euclid-Photometric-ISTF-Pessimistic",
+                     survey_name_spectro=False)
+    fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"Omegam": 0.01, "h": 0.01}, options=o,
+                      observables=["WL", "GCph"], extfiles=ext)
+    F = fm.compute()
+    assert list(F.get_param_names()) == list(g["param_names"])
+    assert fm.photo_LSS._job.stw.shape == (15, 1 + 15 * 6)
+    scale = np.sqrt(np.outer(np.diag(g["fisher"]), np.diag(g["fisher"])))
+    assert np.max(np.abs(F.fisher_matrix - g["fisher"]) / scale) < 1e-6      # north_star tolerance on Fisher elements
+    assert np.max(np.abs(np.array(F.get_confidence_bounds()) / g["sigma"] - 1)) < 1e-4
+    d = fm.photo_LSS.compute_derivs()
+    for par in ("Omegam", "b3", "AIA"):
+        got = np.array([d[par][k] for k in g["cl_keys"]])
+        assert np.max(np.abs(got - g["dcl__" + par])) <= 1e-9 * np.max(np.abs(g["dcl__" + par]))
+
+
+def test_spectro_refuses_stem(bank3, tmp_path):
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"h": 0.01}, options=base_options(tmp_path, stencil="STEM"),
+                      observables=["GCsp"], extfiles=ext_of(bank3))
+    with pytest.raises(ValueError, match="STEM derivative not availabe"):  # derivatives.py:427
+        fm.compute(max_z_bins=1)
+
+
 def test_photo_accuracy_2_vs_oracle(bank3, tmp_path):
     """accuracy = 2 doubles the redshift and multipole sampling (400 z, 200 multipoles): other tile shapes in the
     window, C_ell and Fisher kernels than any golden case."""

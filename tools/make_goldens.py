@@ -270,6 +270,52 @@ for _n in list(GCSP_VARIANTS) + list(PHOTO_VARIANTS):
     CASES[_n] = _make_variant(_n)
 
 
+STEM_EPS = (0.01, 0.02, 0.03)
+
+
+@case
+def photo_stem():
+    """SteM derivatives (derivatives.py:348-441): no production caller of the reference selects them
+    (PhotoCov.compute_derivs hard-wires 3PT), so the derivative engine is driven directly on the reference's own
+    getcls, and its own einsum Fisher assembly turns the result into a matrix.  With external tables the stencil is
+    +-eps for every eps in extfiles["eps_values"], for every free parameter (nuisance included)."""
+    import cosmicfishpie.configs.config as cfg
+    import cosmicfishpie.fishermatrix.cosmicfish as cff
+    import cosmicfishpie.fishermatrix.derivatives as fishderiv
+    import cosmicfishpie.LSSsurvey.photo_cov as photo_cov
+    import cosmicfishpie.LSSsurvey.photo_obs as photo_obs
+
+    d = os.path.join(SCRATCH, "bank_stem")
+    pars = ("Omegam", "h")
+    if not os.path.isdir(os.path.join(d, "h_mn_eps_3p0E-02")):
+        tt.write_bank(d, eps_values=STEM_EPS, pars=pars)
+    ext = tt.extfiles_for(d, eps_values=STEM_EPS, pars=pars)
+    obs = ["WL", "GCph"]
+    o = base_options("photo_stem", spectro=False, photo=True, ell_sampling=10)
+    t0 = time.time()
+    with quiet():
+        fm = cff.FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"Omegam": 0.01, "h": 0.01}, options=o,
+                              specifications={}, observables=obs, extfiles=ext, cosmoModel="w0waCDM", surveyName="Euclid")
+        fid = photo_obs.ComputeCls(fm.fiducialcosmopars, fm.photopars, fm.IApars, fm.photobiaspars)
+        lss = photo_cov.PhotoCov(fm.fiducialcosmopars, fm.photopars, fm.IApars, fm.photobiaspars, fiducial_Cls=fid)
+        noisy, covmat = lss.compute_covmat()
+        eng = fishderiv.derivatives(lss.getcls, lss.allparsfid, derivatives_type="STEM", observables_type=obs,
+                                    external_settings=cfg.external)
+        derivs = eng.result
+        F = fm.photo_LSS_fishermatrix_einsum(noisy_cls=noisy, covmat=covmat, derivs=derivs)
+    wall = time.time() - t0
+    F = np.array(F)
+    out = {"fisher": F, "param_names": np.array(list(fm.freeparams.keys())),
+           "sigma": np.sqrt(np.diag(np.linalg.inv(F))), "wall_s": wall, "eps_values": np.array(STEM_EPS)}
+    keys = [k for k in lss.cls if k != "ells"]
+    out["ells"] = np.array(lss.cls["ells"])
+    out["cl_keys"] = np.array(keys)
+    for par in ("Omegam", "b3", "AIA"):
+        out["dcl__" + par] = np.array([derivs[par][k] for k in keys])
+    np.savez_compressed(os.path.join(GOLD, "photo_stem.npz"), **out)
+    print(f"photo_stem: npar={len(out['param_names'])} wall={wall:.2f}s F00={out['fisher'][0,0]:.10e}")
+
+
 LIKE_POINTS_PHOTO = {
     "fid": {},
     "nuis": {"b1": 1.02, "b7": 0.985, "AIA": 1.04, "etaIA": 0.97, "betaIA": 1.01},     # multiplicative shifts
