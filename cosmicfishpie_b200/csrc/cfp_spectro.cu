@@ -53,7 +53,7 @@ struct alignas(16) SDev {
   double w0;                         // weight of this point in the derivative of parameter par0
   int flags, par0;                   // SD_*; parameter fed with weight w0 (-1: none)
   int csr0, csr1;                    // further (parameter, weight) pairs in the CSR arrays
-  int nB, pad0;
+  int nB, sidx;                      // sidx: index of the point in the job's stencil (shared memory holds work order)
   double xminB, xmaxB;
   // row-constant inputs and the rest
   double rqpar, rqper, dzH, A1, A2, sigmap, I0, I12, svr2, fs8, invs8sq, khfac, bao, pshot;
@@ -109,7 +109,8 @@ struct SpectroParams {
   int* shared_tmp;          // [Z][NC]: 1 if P_lin and f of the cosmology share their k-knots
   SDev* sdev;             // [Z][S]
   int* work;              // [Z][S] stencil points to visit per bin, in order
-  int* nwork;             // [Z][4]: full, bias-only and alias points in the bin's work list (after the fiducial)
+  int* nwork;             // [Z][4]: full, bias-only and alias points in the bin's work list (after the fiducial);
+                          //         [3] = how many of the full points, listed first, take the specialised loop
   double* partial;        // [Z][gridDim.x][T*64]
   double *lnp, *derivs, *veff;
 };
@@ -254,6 +255,8 @@ __device__ void spectro_setup_block(const SpectroParams& P, int zb) {
     }
   }
   __syncthreads();
+  const int c_fid = (int)P.scal[(size_t)zb * CFP_SP_NSCAL + CFP_SP_COSMO];
+  const int nA_fid = (int)P.desc[((size_t)c_fid * P.n_tables + P.tab_pl) * CFP_BANK_DESC + 1] - 7;
   for (int s = threadIdx.x; s < P.S; s += blockDim.x) {
     const double* sc = P.scal + ((size_t)s * P.Z + zb) * CFP_SP_NSCAL;
     SDev o;
@@ -301,7 +304,7 @@ __device__ void spectro_setup_block(const SpectroParams& P, int zb) {
         if (q != CFP_SP_BIAS) same = same && (sc[q] == s0[q]);
       if (same) o.flags |= SD_BIASONLY;
     }
-    o.pad0 = 0;
+    o.sidx = s;
     {
       // k' = k khfac sqrt(mu^2 rqpar^2 + (1 - mu^2) rqper^2) lies between k khfac min(rq) and k khfac max(rq)
       const double gmin = o.khfac * fmin(o.rqpar, o.rqper) * (1.0 - 1e-12);
@@ -328,22 +331,29 @@ __device__ void spectro_setup_block(const SpectroParams& P, int zb) {
     P.sdev[(size_t)zb * P.S + s] = o;
     if (!batch) {  // class of the point in the bin's work list (-1: not visited)
       const bool needed = (s == P.ps_src) || (P.materialize & CFP_MAT_LNP) || (o.par0 >= 0);
-      cls_sm[s] = !needed ? -1 : (!(o.flags & SD_OWN) ? 2 : ((o.flags & SD_BIASONLY) ? 1 : 0));
+      // a "plain" full point is what a forecast consists of almost entirely: non-linear spectrum with FoG, tables on
+      // shared knots covering the whole lattice, no Q-bias, no shot-noise term, feeds exactly one parameter and
+      // nobody reads its P_obs -- eval_x_plain / the first loop of the lattice kernel carry none of those branches
+      const bool plain = !(P.flags & CFP_SPF_LINEAR) && (P.flags & CFP_SPF_FOG) &&
+                         (o.flags & (SD_SHARED_KNOTS | SD_NOCLAMP)) == (SD_SHARED_KNOTS | SD_NOCLAMP) &&
+                         !(o.flags & (SD_QBIAS | SD_PSHOT | SD_SRC | SD_PSSRC)) && o.par0 >= 0 && o.csr0 == o.csr1 &&
+                         o.nA == nA_fid;  // (a piece hint of the fiducial's table is a valid index of this one)
+      cls_sm[s] = !needed ? -1 : (!(o.flags & SD_OWN) ? 3 : ((o.flags & SD_BIASONLY) ? 2 : (plain ? 0 : 1)));
     }
   }
   __syncthreads();
   if (threadIdx.x == 0 && !batch) {
-    // work list of the bin: [fiducial | full evaluations | bias-only | aliases of the fiducial that feed a
-    // derivative or are materialised]; the lattice loop runs one branch-free loop per class
-    int n = 0, cnt[3] = {0, 0, 0};
+    // work list of the bin: [fiducial | full evaluations, plain ones first | bias-only | aliases of the fiducial
+    // that feed a derivative or are materialised]; the lattice loop runs one branch-free loop per class
+    int n = 0, cnt[4] = {0, 0, 0, 0};
     P.work[zb * P.S + n++] = 0;
-    for (int cls = 0; cls < 3; ++cls)
+    for (int cls = 0; cls < 4; ++cls)
       for (int s = 1; s < P.S; ++s)
         if (cls_sm[s] == cls) P.work[zb * P.S + n++] = s, ++cnt[cls];
-    P.nwork[zb * 4 + 0] = cnt[0];
-    P.nwork[zb * 4 + 1] = cnt[1];
-    P.nwork[zb * 4 + 2] = cnt[2];
-    P.nwork[zb * 4 + 3] = n;
+    P.nwork[zb * 4 + 0] = cnt[0] + cnt[1];
+    P.nwork[zb * 4 + 1] = cnt[2];
+    P.nwork[zb * 4 + 2] = cnt[3];
+    P.nwork[zb * 4 + 3] = cnt[0];
   }
 }
 
@@ -459,7 +469,7 @@ __device__ __forceinline__ int locate(const double* __restrict__ blk, int n, dou
     lo = __ldg(blk + (size_t)j * STRIDE);
     return j;
   }
-  j = hint;
+  j = min(hint, n - 1);  // (a hint carried over from a table with more pieces)
   b = __ldg(reinterpret_cast<const double2*>(blk + (size_t)j * STRIDE));
   while (x >= b.y && j < n - 1) {
     ++j;
@@ -471,6 +481,18 @@ __device__ __forceinline__ int locate(const double* __restrict__ blk, int n, dou
   }
   lo = b.x;
   return j;
+}
+
+// The same with a hint that is known to be a valid index and almost always right (the walk down a mu column moves
+// k' by a fraction of a piece per step): one load, two compares, the search only off the common path.
+template <int STRIDE>
+__device__ __forceinline__ int locate_near(const double* __restrict__ blk, int n, double x, int hint, double& lo) {
+  const double2 b = __ldg(reinterpret_cast<const double2*>(blk + (size_t)hint * STRIDE));
+  if (x >= b.x && x < b.y) {
+    lo = b.x;
+    return hint;
+  }
+  return locate<STRIDE>(blk, n, x, hint, lo);
 }
 
 __device__ __forceinline__ double cubic_at(const double* __restrict__ blk, int j, double u) {
@@ -558,6 +580,28 @@ __device__ __forceinline__ double eval_x(const MathTab& mt, const SDev& p, const
   return eval_x(mt, p, rc, flags, k, hA, hB, hN, err2, qf, F, W);
 }
 
+// eval_x of a "plain" point (see spectro_setup_block): the same operations in the same order, without the
+// configuration branches; hA and hN are valid indices (the fiducial of the tile was evaluated first).
+__device__ __forceinline__ double eval_x_plain(const MathTab& mt, const SDev& p, const RowC& rc, double k, int& hA,
+                                               int& hN, double& err2) {
+  const double err = k * rc.errc;
+  err2 = err * err;
+  const double kap = k * rc.G;
+  double lo;
+  hA = locate_near<CUBIC_BLK>(p.blkA, p.nA, kap, hA, lo);
+  const double u = kap - lo;
+  const double pdd = cubic_at(p.blkA, hA, u);
+  const double F = cubic_at(p.blkB, hA, u) * rc.fmu2;
+  hN = locate_near<LIN_BLK>(p.blkN, p.nN, kap, hN, lo);
+  const double2 ys = __ldg(reinterpret_cast<const double2*>(p.blkN + (size_t)hN * LIN_BLK + 2));
+  const double pnw = fma(ys.y, kap - lo, ys.x);
+  const double e = tab_exp_neg(mt, -rc.sv2 * (kap * kap));
+  const double t = kap * rc.fogc;
+  const double W = fast_div(p.baos * fma(e, pdd - pnw, pnw), fma(t, t, 1.0));
+  const double kaiser = p.bias + F;  // = fma(bias, 1, F)
+  return (kaiser * kaiser) * W;
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
@@ -580,9 +624,9 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
   extern __shared__ __align__(16) double smem[];
   double* sm_d = smem;                                 // [NB*8][LDC]
   double* sm_w = smem + NB * 8 * LDC;                  // [TILE]
-  SDev* sm_s = reinterpret_cast<SDev*>(sm_w + TILE);   // [S]
-  RowC* sm_r = reinterpret_cast<RowC*>(sm_s + P.S);    // [S]
-  MathTab& mt = *reinterpret_cast<MathTab*>(sm_r + P.S);
+  MathTab& mt = *reinterpret_cast<MathTab*>(sm_w + TILE);  // (at a compile-time offset: no address arithmetic in the loops)
+  SDev* sm_s = reinterpret_cast<SDev*>(&mt + 1);       // [S], in work-list order
+  RowC* sm_r = reinterpret_cast<RowC*>(sm_s + P.S);    // [S], likewise
   math_tables_fill(mt, threadIdx.x, TILE);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int zb = blockIdx.y;
@@ -590,15 +634,22 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
   const int64_t ntile = (int64_t)nkb * nrows;
   const int64_t t_begin = ntile * blockIdx.x / gridDim.x, t_end = ntile * (blockIdx.x + 1) / gridDim.x;
   const int64_t lattice = (int64_t)P.Nmu * P.Nk;
+  const int n_full = P.nwork[zb * 4 + 0], n_bias = P.nwork[zb * 4 + 1], n_alias = P.nwork[zb * 4 + 2];
+  // lnP lattices are written by the general loop only
+  const int n_plain = (P.materialize & CFP_MAT_LNP) ? 0 : P.nwork[zb * 4 + 3];
   {
-    const int nwords = P.S * (int)(sizeof(SDev) / sizeof(double));
+    // the points of the bin, staged in the ORDER OF THE WORK LIST: the loops below walk sm_s / sm_r linearly
+    constexpr int W = (int)(sizeof(SDev) / sizeof(double));
+    const int* work = P.work + zb * P.S;
+    const int nwords = (1 + n_full + n_bias + n_alias) * W;
     const double* src = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S);
     double* dst = reinterpret_cast<double*>(sm_s);
-    for (int i = tid; i < nwords; i += TILE) dst[i] = src[i];
+    for (int i = tid; i < nwords; i += TILE) {
+      const int t = i / W;
+      dst[i] = src[(size_t)work[t] * W + (i - t * W)];
+    }
   }
   __syncthreads();
-  const int n_full = P.nwork[zb * 4 + 0], n_bias = P.nwork[zb * 4 + 1], n_alias = P.nwork[zb * 4 + 2];
-  const int* work = P.work + zb * P.S;
 
   double acc[T][2];
 #pragma unroll
@@ -625,17 +676,15 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
     const int64_t cell = (int64_t)row * P.Nk + ki;
     const bool valid = col_ok && cell >= P.cell_begin && cell < P.cell_end;
     __syncthreads();  // every warp is done with the previous tile's row constants
-    for (int t = tid; t <= n_full; t += TILE) {  // the fiducial and the fully evaluated points
-      const int s = work[t];
-      sm_r[s] = row_consts(sm_s[s], P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
-    }
+    for (int t = tid; t <= n_full; t += TILE)  // the fiducial and the fully evaluated points
+      sm_r[t] = row_consts(sm_s[t], P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
     __syncthreads();
     if (!__any_sync(0xffffffffu, valid)) continue;  // (uniform per warp; the barriers above are per tile)
 #pragma unroll 4
     for (int p = 0; p < NB * 8; ++p) sm_d[p * LDC + tid] = 0.0;
     double Psrc = 1.0;
     // ln P_obs (and P_obs where it is needed) from X and err^2, then the point's contribution to the derivatives
-    auto finish = [&](const SDev& sp, int s, double X, double err2) {
+    auto finish = [&](const SDev& sp, double X, double err2) {
       const int fl = sp.flags;
       double lnP, Pobs = 0.0;
       if (fl & SD_PSHOT) {
@@ -648,7 +697,7 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
         if (fl & SD_SRC) Pobs = X * tab_exp_neg(mt, -err2);
       }
       if (fl & SD_PSSRC) Psrc = Pobs;
-      if ((P.materialize & CFP_MAT_LNP) && valid) P.lnp[((size_t)s * P.Z + zb) * lattice + cell] = lnP;
+      if ((P.materialize & CFP_MAT_LNP) && valid) P.lnp[((size_t)sp.sidx * P.Z + zb) * lattice + cell] = lnP;
       const int par0 = sp.par0;
       if (par0 >= 0) {
         sm_d[par0 * LDC + tid] += sp.w0 * lnP;
@@ -662,26 +711,30 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
     // the fiducial
     double qf0, F0, W0, err20;
     const double X0 = eval_x(mt, sm_s[0], sm_r[0], P.flags, k, hA, hB, hN, err20, qf0, F0, W0);
-    const double P0 = finish(sm_s[0], 0, X0, err20);
-    int wi = 1;
-    // points with their own cosmology / AP factors: full evaluation
-    for (const int we = wi + n_full; wi < we; ++wi) {
-      const int s = work[wi];
+    const double P0 = finish(sm_s[0], X0, err20);
+    const SDev* sp = sm_s + 1;
+    const RowC* rp = sm_r + 1;
+    // points with their own cosmology / AP factors: full evaluation; the plain ones (all of them in a forecast
+    // but the one the shot-noise derivatives read) first, in the loop without configuration branches
+    for (int i = n_plain; i > 0; --i, ++sp, ++rp) {
       double err2;
-      const double X = eval_x(mt, sm_s[s], sm_r[s], P.flags, k, hA, hB, hN, err2);
-      finish(sm_s[s], s, X, err2);
+      const double X = eval_x_plain(mt, *sp, *rp, k, hA, hN, err2);
+      const double lnP = X > 0.0 ? tab_log(mt, X) - err2 : CUDART_NAN;
+      sm_d[sp->par0 * LDC + tid] += sp->w0 * lnP;
+    }
+    if (n_plain > 0) hB = hA;  // (shared knots)
+    for (int i = n_full - n_plain; i > 0; --i, ++sp, ++rp) {
+      double err2;
+      const double X = eval_x(mt, *sp, *rp, P.flags, k, hA, hB, hN, err2);
+      finish(*sp, X, err2);
     }
     // points that differ from the fiducial only in the bias: the table look-ups are the fiducial's
-    for (const int we = wi + n_bias; wi < we; ++wi) {
-      const int s = work[wi];
-      const double kaiser = fma(sm_s[s].bias, qf0, F0);
-      finish(sm_s[s], s, (kaiser * kaiser) * W0, err20);
+    for (int i = n_bias; i > 0; --i, ++sp) {
+      const double kaiser = fma(sp->bias, qf0, F0);
+      finish(*sp, (kaiser * kaiser) * W0, err20);
     }
     // aliases of the fiducial in this bin
-    for (const int we = wi + n_alias; wi < we; ++wi) {
-      const int s = work[wi];
-      finish(sm_s[s], s, X0, err20);
-    }
+    for (int i = n_alias; i > 0; --i, ++sp) finish(*sp, X0, err20);
     // finish the derivatives of the cell
     for (int par = 0; par < P.npar; ++par) {
       const int pb = __ldg(P.ps_bin + par);
