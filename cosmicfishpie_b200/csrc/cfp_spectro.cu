@@ -67,7 +67,8 @@ enum {
   SD_BIASONLY = 32,     // differs from the fiducial only in the galaxy bias: re-uses the fiducial's table look-ups
   SD_FID = 64,          // stencil point 0
   SD_PSSRC = 128,       // the point whose P_obs feeds d lnP / d Ps_i
-  SD_NOCLAMP = 256      // k' of the whole lattice lies inside the knot range of both tables: no clamping needed
+  SD_NOCLAMP = 256,     // k' of the whole lattice lies inside the knot range of both tables: no clamping needed
+  SD_PLAIN = 512        // eval_x_plain applies (see spectro_setup_block)
 };
 
 // What one (stencil point, z-bin) needs per mu ROW of the lattice: with the Alcock-Paczynski remap
@@ -109,8 +110,9 @@ struct SpectroParams {
   int* shared_tmp;          // [Z][NC]: 1 if P_lin and f of the cosmology share their k-knots
   SDev* sdev;             // [Z][S]
   int* work;              // [Z][S] stencil points to visit per bin, in order
-  int* nwork;             // [Z][4]: full, bias-only and alias points in the bin's work list (after the fiducial);
-                          //         [3] = how many of the full points, listed first, take the specialised loop
+  int* nwork;             // [Z][8]: 0 full, 1 bias-only, 2 alias points in the bin's work list (after the fiducial);
+                          //         3: how many of the full points, listed first, are plain (the specialised loop);
+                          //         5: the fiducial is plain as far as its evaluation goes
   double* partial;        // [Z][gridDim.x][T*64]
   double *lnp, *derivs, *veff;
 };
@@ -328,17 +330,25 @@ __device__ void spectro_setup_block(const SpectroParams& P, int zb) {
       }
     o.csr0 = jj;
     o.csr1 = j1;
+    {
+      // a "plain" evaluation is what a forecast or a likelihood batch consists of almost entirely: non-linear spectrum
+      // with FoG, tables on shared knots covering the whole lattice, no Q-bias, no shot-noise term -- eval_x_plain
+      // carries none of those branches
+      const bool plain_eval = !(P.flags & CFP_SPF_LINEAR) && (P.flags & CFP_SPF_FOG) &&
+                              (o.flags & (SD_SHARED_KNOTS | SD_NOCLAMP)) == (SD_SHARED_KNOTS | SD_NOCLAMP) &&
+                              !(o.flags & (SD_QBIAS | SD_PSHOT)) &&
+                              o.nA == nA_fid;  // (a piece hint of the fiducial's table is a valid index of this one)
+      if (plain_eval) o.flags |= SD_PLAIN;
+    }
     P.sdev[(size_t)zb * P.S + s] = o;
     if (!batch) {  // class of the point in the bin's work list (-1: not visited)
       const bool needed = (s == P.ps_src) || (P.materialize & CFP_MAT_LNP) || (o.par0 >= 0);
-      // a "plain" full point is what a forecast consists of almost entirely: non-linear spectrum with FoG, tables on
-      // shared knots covering the whole lattice, no Q-bias, no shot-noise term, feeds exactly one parameter and
-      // nobody reads its P_obs -- eval_x_plain / the first loop of the lattice kernel carry none of those branches
-      const bool plain = !(P.flags & CFP_SPF_LINEAR) && (P.flags & CFP_SPF_FOG) &&
-                         (o.flags & (SD_SHARED_KNOTS | SD_NOCLAMP)) == (SD_SHARED_KNOTS | SD_NOCLAMP) &&
-                         !(o.flags & (SD_QBIAS | SD_PSHOT | SD_SRC | SD_PSSRC)) && o.par0 >= 0 && o.csr0 == o.csr1 &&
-                         o.nA == nA_fid;  // (a piece hint of the fiducial's table is a valid index of this one)
+      const bool plain_eval = (o.flags & SD_PLAIN) != 0;
+      // a plain POINT of the Fisher work list also feeds exactly one parameter and nobody reads its P_obs.  (A third loop for the plain point whose P_obs
+      // the shot-noise derivatives read was measured slower: 0.813 vs 0.789 ms, register allocation.)
+      const bool plain = plain_eval && o.par0 >= 0 && o.csr0 == o.csr1 && !(o.flags & (SD_SRC | SD_PSSRC));
       cls_sm[s] = !needed ? -1 : (!(o.flags & SD_OWN) ? 3 : ((o.flags & SD_BIASONLY) ? 2 : (plain ? 0 : 1)));
+      if (s == 0) P.nwork[zb * 8 + 5] = plain_eval ? 1 : 0;
     }
   }
   __syncthreads();
@@ -350,10 +360,10 @@ __device__ void spectro_setup_block(const SpectroParams& P, int zb) {
     for (int cls = 0; cls < 4; ++cls)
       for (int s = 1; s < P.S; ++s)
         if (cls_sm[s] == cls) P.work[zb * P.S + n++] = s, ++cnt[cls];
-    P.nwork[zb * 4 + 0] = cnt[0] + cnt[1];
-    P.nwork[zb * 4 + 1] = cnt[2];
-    P.nwork[zb * 4 + 2] = cnt[3];
-    P.nwork[zb * 4 + 3] = cnt[0];
+    P.nwork[zb * 8 + 0] = cnt[0] + cnt[1];
+    P.nwork[zb * 8 + 1] = cnt[2];
+    P.nwork[zb * 8 + 2] = cnt[3];
+    P.nwork[zb * 8 + 3] = cnt[0];
   }
 }
 
@@ -583,23 +593,45 @@ __device__ __forceinline__ double eval_x(const MathTab& mt, const SDev& p, const
 // eval_x of a "plain" point (see spectro_setup_block): the same operations in the same order, without the
 // configuration branches; hA and hN are valid indices (the fiducial of the tile was evaluated first).
 __device__ __forceinline__ double eval_x_plain(const MathTab& mt, const SDev& p, const RowC& rc, double k, int& hA,
-                                               int& hN, double& err2) {
+                                               int& hN, double& err2, double& F, double& W) {
   const double err = k * rc.errc;
   err2 = err * err;
   const double kap = k * rc.G;
-  double lo;
-  hA = locate_near<CUBIC_BLK>(p.blkA, p.nA, kap, hA, lo);
-  const double u = kap - lo;
-  const double pdd = cubic_at(p.blkA, hA, u);
-  const double F = cubic_at(p.blkB, hA, u) * rc.fmu2;
-  hN = locate_near<LIN_BLK>(p.blkN, p.nN, kap, hN, lo);
-  const double2 ys = __ldg(reinterpret_cast<const double2*>(p.blkN + (size_t)hN * LIN_BLK + 2));
-  const double pnw = fma(ys.y, kap - lo, ys.x);
+  // The hints are almost always right (the walk down a mu column moves k' by a fraction of a piece per step), so
+  // every record is fetched AT THE HINT before any bound is checked: one round trip to the tables per evaluation
+  // instead of bounds -> coefficients; a wrong hint takes the search and fetches again.
+  const double2* ra = reinterpret_cast<const double2*>(p.blkA + (size_t)hA * CUBIC_BLK);
+  const double2* rb = reinterpret_cast<const double2*>(p.blkB + (size_t)hA * CUBIC_BLK);
+  const double2* rn = reinterpret_cast<const double2*>(p.blkN + (size_t)hN * LIN_BLK);
+  double2 bA = __ldg(ra), a01 = __ldg(ra + 1), a23 = __ldg(ra + 2);
+  double2 f01 = __ldg(rb + 1), f23 = __ldg(rb + 2);
+  double2 bN = __ldg(rn), ys = __ldg(rn + 1);
+  if (!(kap >= bA.x && kap < bA.y)) {
+    hA = locate<CUBIC_BLK>(p.blkA, p.nA, kap, hA, bA.x);
+    ra = reinterpret_cast<const double2*>(p.blkA + (size_t)hA * CUBIC_BLK);
+    rb = reinterpret_cast<const double2*>(p.blkB + (size_t)hA * CUBIC_BLK);
+    a01 = __ldg(ra + 1), a23 = __ldg(ra + 2);
+    f01 = __ldg(rb + 1), f23 = __ldg(rb + 2);
+  }
+  if (!(kap >= bN.x && kap < bN.y)) {
+    hN = locate<LIN_BLK>(p.blkN, p.nN, kap, hN, bN.x);
+    ys = __ldg(reinterpret_cast<const double2*>(p.blkN + (size_t)hN * LIN_BLK + 2));
+  }
+  const double u = kap - bA.x;
+  const double pdd = a01.x + u * (a01.y + u * (a23.x + u * a23.y));
+  F = (f01.x + u * (f01.y + u * (f23.x + u * f23.y))) * rc.fmu2;
+  const double pnw = fma(ys.y, kap - bN.x, ys.x);
   const double e = tab_exp_neg(mt, -rc.sv2 * (kap * kap));
   const double t = kap * rc.fogc;
-  const double W = fast_div(p.baos * fma(e, pdd - pnw, pnw), fma(t, t, 1.0));
+  W = fast_div(p.baos * fma(e, pdd - pnw, pnw), fma(t, t, 1.0));
   const double kaiser = p.bias + F;  // = fma(bias, 1, F)
   return (kaiser * kaiser) * W;
+}
+
+__device__ __forceinline__ double eval_x_plain(const MathTab& mt, const SDev& p, const RowC& rc, double k, int& hA,
+                                               int& hN, double& err2) {
+  double F, W;
+  return eval_x_plain(mt, p, rc, k, hA, hN, err2, F, W);
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -632,11 +664,15 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
   const int zb = blockIdx.y;
   const int nkb = (P.Nk + TILE - 1) / TILE;
   const int64_t ntile = (int64_t)nkb * nrows;
+  // equal runs of tiles per CTA.  (Weighting the nearly empty tiles of a ragged last block of wavenumbers -- Nk = 8193
+  // leaves one column -- by their busy warps was measured slower: such a tile is no shorter in latency.)
   const int64_t t_begin = ntile * blockIdx.x / gridDim.x, t_end = ntile * (blockIdx.x + 1) / gridDim.x;
   const int64_t lattice = (int64_t)P.Nmu * P.Nk;
-  const int n_full = P.nwork[zb * 4 + 0], n_bias = P.nwork[zb * 4 + 1], n_alias = P.nwork[zb * 4 + 2];
+  const int n_full = P.nwork[zb * 8 + 0], n_bias = P.nwork[zb * 8 + 1], n_alias = P.nwork[zb * 8 + 2];
   // lnP lattices are written by the general loop only
-  const int n_plain = (P.materialize & CFP_MAT_LNP) ? 0 : P.nwork[zb * 4 + 3];
+  const bool special = !(P.materialize & CFP_MAT_LNP);
+  const int n_plain = special ? P.nwork[zb * 8 + 3] : 0;
+  const bool fid_plain = P.nwork[zb * 8 + 5] != 0;
   {
     // the points of the bin, staged in the ORDER OF THE WORK LIST: the loops below walk sm_s / sm_r linearly
     constexpr int W = (int)(sizeof(SDev) / sizeof(double));
@@ -679,7 +715,7 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
     for (int t = tid; t <= n_full; t += TILE)  // the fiducial and the fully evaluated points
       sm_r[t] = row_consts(sm_s[t], P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
     __syncthreads();
-    if (!__any_sync(0xffffffffu, valid)) continue;  // (uniform per warp; the barriers above are per tile)
+    if (__any_sync(0xffffffffu, valid)) {  // (uniform per warp; the barriers are per tile)
 #pragma unroll 4
     for (int p = 0; p < NB * 8; ++p) sm_d[p * LDC + tid] = 0.0;
     double Psrc = 1.0;
@@ -710,7 +746,14 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
     };
     // the fiducial
     double qf0, F0, W0, err20;
-    const double X0 = eval_x(mt, sm_s[0], sm_r[0], P.flags, k, hA, hB, hN, err20, qf0, F0, W0);
+    double X0;
+    if (fid_plain && hA >= 0 && hN >= 0) {  // (the first tile of a block of wavenumbers has no hints yet)
+      qf0 = 1.0;
+      X0 = eval_x_plain(mt, sm_s[0], sm_r[0], k, hA, hN, err20, F0, W0);
+      hB = hA;
+    } else {
+      X0 = eval_x(mt, sm_s[0], sm_r[0], P.flags, k, hA, hB, hN, err20, qf0, F0, W0);
+    }
     const double P0 = finish(sm_s[0], X0, err20);
     const SDev* sp = sm_s + 1;
     const RowC* rp = sm_r + 1;
@@ -774,6 +817,7 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
         }
     }
     __syncwarp();
+    }  // any valid cell in this warp's part of the tile
   }
   // cross-warp reduction in fixed order, then one partial per CTA
   __syncthreads();
@@ -921,6 +965,7 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_chi2_kernel(SpectroParams 
   const double pref = 2.0 * P.vol[zb] * INV_8PI2;  // spectro_like.py:162-178
   const double* __restrict__ dz = data + (size_t)zb * lattice;
   const int nkb = (P.Nk + TILE - 1) / TILE;
+  const bool plain = (sp.flags & SD_PLAIN) != 0;
   double acc[CH];
 #pragma unroll
   for (int j = 0; j < CH; ++j) acc[j] = 0.0;
@@ -942,7 +987,12 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_chi2_kernel(SpectroParams 
       for (int r = 0; r < nr; ++r) {
         const double Pd = __ldg(dcol + (size_t)r * P.Nk);
         double err2, qf, F, W;
-        eval_x(mt, sp, rows[r], P.flags, k, hA, hB, hN, err2, qf, F, W);
+        if (plain && hA >= 0) {  // (every row of a column but the first)
+          qf = 1.0;
+          eval_x_plain(mt, sp, rows[r], k, hA, hN, err2, F, W);
+        } else {
+          eval_x(mt, sp, rows[r], P.flags, k, hA, hB, hN, err2, qf, F, W);
+        }
         const double We = W * tab_exp_neg(mt, -err2);
         const double rPd = fast_rcp(Pd);
         const double w = wrow[r] * wcol;
@@ -1023,7 +1073,7 @@ __global__ void __launch_bounds__(TILE, 4) spectro_legendre_chi2_kernel(
     for (int j = 0; j < LEG_CH; ++j) a0[j] = a2[j] = a4[j] = 0.0;
     for (int r = 0; r < P.Nmu; ++r) {
       double err2, qf, F, W;
-      eval_x(mt, sp, rows[r], P.flags, k, hA, hB, hN, err2, qf, F, W);
+      eval_x(mt, sp, rows[r], P.flags, k, hA, hB, hN, err2, qf, F, W);  // (eval_x_plain measured no faster here)
       const double We = W * tab_exp_neg(mt, -err2);
       const double w0 = slw[0][r], w2 = slw[1][r], w4 = slw[2][r];
 #pragma unroll
@@ -1265,7 +1315,7 @@ extern "C" int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S
   SP_UP(double, nullptr, (size_t)NC * Z * (nnw - 1) * LIN_BLK, pl->blknw_d);
   SP_UP(SDev, nullptr, (size_t)Z * S, pl->sdev_d);
   SP_UP(int, nullptr, (size_t)Z * S, pl->work_d);
-  SP_UP(int, nullptr, (size_t)Z * 4, pl->nwork_d);
+  SP_UP(int, nullptr, (size_t)Z * 8, pl->nwork_d);
   SP_UP(int, nullptr, (size_t)NC * Z, pl->shared_d);
   SP_UP(double, nullptr, (size_t)NC * Z * 2 * maxncy, pl->dcoef_d);
   SP_UP(double, nullptr, (size_t)Z * npar * npar, pl->fisher_d);
