@@ -1116,6 +1116,243 @@ __global__ void __launch_bounds__(TILE, 4) spectro_legendre_chi2_kernel(
   }
 }
 
+// ------------------------------------------------------------------ likelihood of a large group through its moments
+// Members of a group differ only in the galaxy bias b and in the additive noise m, and the theory is a polynomial in
+// them: P_t,j - P_t,0 = (b_j^2 - b_0^2) a + (b_j - b_0) c + (m_j - m_0) with a = qf^2 We, c = 2 qf F We per cell and
+// member 0 the group's reference.  Both likelihoods are quadratic in P_t, so chi2_j = v^T M v with
+// v = (b_j^2 - b_0^2, b_j - b_0, m_j - m_0, 1) and a 4x4 matrix M summed over the lattice ONCE per group and bin --
+// a nuisance-parameter batch of thousands of points costs one lattice pass per bin instead of one per 16 (wedges) or
+// 4 (multipoles) points.  The residual of the reference member is formed exactly as the direct kernels form it, so
+// a member equal to the reference (v = (0,0,0,1)) gets the direct kernel's value; the others differ from it by
+// rounding only (tests/test_like_gpu.py compares the two paths).
+// mom[(group * gridDim.x + cta) * MOM_N + e]: coefficients of v_i v_j, i <= j, in row-major order of (i, j).
+constexpr int MOM_N = 10;
+constexpr int MOM_MIN = 4;  // smaller groups take the direct kernels
+
+template <int N>
+__device__ __forceinline__ void block_sum_store(double (&acc)[N], double (*red)[TILE / 32], double* __restrict__ out) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double a = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((tid & 31) == 0) red[j][tid >> 5] = a;
+  }
+  __syncthreads();
+  if (tid < N) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < TILE / 32; ++w) t += red[tid][w];
+    out[tid] = t;
+  }
+}
+
+__global__ void __launch_bounds__(TILE, 3) spectro_wedge_moments_kernel(SpectroParams P, const double* __restrict__ data,
+                                                                        const double* __restrict__ shot,
+                                                                        const int* __restrict__ g_zb,
+                                                                        const int* __restrict__ g_off,
+                                                                        const int* __restrict__ mem_s,
+                                                                        double* __restrict__ mom) {
+  __shared__ SDev sp;
+  __shared__ RowC rows[CHI_ROWS];
+  __shared__ double wrow[CHI_ROWS];
+  __shared__ double red[MOM_N][TILE / 32];
+  __shared__ MathTab mt;
+  const int tid = threadIdx.x;
+  const int zb = g_zb[blockIdx.y], s0 = mem_s[g_off[blockIdx.y]];
+  if (tid < (int)(sizeof(SDev) / sizeof(double)))
+    reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S + s0)[tid];
+  math_tables_fill(mt, tid, TILE);
+  __syncthreads();
+  const double b0 = sp.bias, m0 = 1.0 / P.nbar[zb] + shot[(size_t)s0 * P.Z + zb] + sp.pshot;
+  const int64_t lattice = (int64_t)P.Nmu * P.Nk;
+  const double pref = 2.0 * P.vol[zb] * INV_8PI2;  // spectro_like.py:162-178
+  const double* __restrict__ dz = data + (size_t)zb * lattice;
+  const int nkb = (P.Nk + TILE - 1) / TILE;
+  const bool plain = (sp.flags & SD_PLAIN) != 0;
+  double acc[MOM_N];
+#pragma unroll
+  for (int j = 0; j < MOM_N; ++j) acc[j] = 0.0;
+  for (int r0 = 0; r0 < P.Nmu; r0 += CHI_ROWS) {
+    const int nr = min(CHI_ROWS, P.Nmu - r0);
+    __syncthreads();
+    for (int r = tid; r < nr; r += TILE) {
+      rows[r] = row_consts(sp, P.flags, __ldg(P.mu + r0 + r), __ldg(P.smu + r0 + r));
+      wrow[r] = __ldg(P.wmu + r0 + r) * pref;
+    }
+    __syncthreads();
+    for (int kb = blockIdx.x; kb < nkb; kb += gridDim.x) {
+      const int ki = kb * TILE + tid;
+      if (ki >= P.Nk) continue;
+      const double k = __ldg(P.k + ki);
+      const double wcol = __ldg(P.wk + ki) * (k * k);
+      const double* __restrict__ dcol = dz + (size_t)r0 * P.Nk + ki;
+      int hA = -1, hB = -1, hN = -1;
+      for (int r = 0; r < nr; ++r) {
+        const double Pd = __ldg(dcol + (size_t)r * P.Nk);
+        double err2, qf, F, W;
+        if (plain && hA >= 0) {
+          qf = 1.0;
+          eval_x_plain(mt, sp, rows[r], k, hA, hN, err2, F, W);
+        } else {
+          eval_x(mt, sp, rows[r], P.flags, k, hA, hB, hN, err2, qf, F, W);
+        }
+        const double We = W * tab_exp_neg(mt, -err2);
+        const double rPd = fast_rcp(Pd);
+        const double w = wrow[r] * wcol;
+        const double kaiser = fma(b0, qf, F);
+        const double Pt = fma(kaiser * kaiser, We, m0);
+        const double g3 = (Pd - Pt) * rPd;  // the reference member's term, as spectro_chi2_kernel forms it
+        const double qw = qf * We;
+        const double g0 = -(qf * qw) * rPd, g1 = -(2.0 * (F * qw)) * rPd, g2 = -rPd;
+        const double w0 = w * g0, w1 = w * g1, w2 = w * g2;
+        acc[0] = fma(w0, g0, acc[0]);
+        acc[1] = fma(w0, g1, acc[1]);
+        acc[2] = fma(w0, g2, acc[2]);
+        acc[3] = fma(w0, g3, acc[3]);
+        acc[4] = fma(w1, g1, acc[4]);
+        acc[5] = fma(w1, g2, acc[5]);
+        acc[6] = fma(w1, g3, acc[6]);
+        acc[7] = fma(w2, g2, acc[7]);
+        acc[8] = fma(w2, g3, acc[8]);
+        acc[9] = fma(w * g3, g3, acc[9]);
+      }
+    }
+  }
+  // coefficients of v_i v_j: the off-diagonal ones count twice
+  acc[1] *= 2.0, acc[2] *= 2.0, acc[3] *= 2.0, acc[5] *= 2.0, acc[6] *= 2.0, acc[8] *= 2.0;
+  block_sum_store(acc, red, mom + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * MOM_N);
+}
+
+// The same for the Legendre multipoles (see spectro_legendre_chi2_kernel): a thread owns a wavenumber, accumulates
+// over the mu rows the multipoles of a, c and of the reference member's spectrum, and adds G^T C^-1 G of its (k, bin)
+// with G = [-a_l, -c_l, -sum_mu lw_l, P_l,data - P_l,0] (3 x 4).
+__global__ void __launch_bounds__(TILE, 3) spectro_legendre_moments_kernel(
+    SpectroParams P, const double* __restrict__ pl_data /*[Nk][Z][3]*/, const double* __restrict__ icov /*[Nk][Z][9]*/,
+    const double* __restrict__ lw /*[3][Nmu]*/, const double* __restrict__ shot, const int* __restrict__ g_zb,
+    const int* __restrict__ g_off, const int* __restrict__ mem_s, double* __restrict__ mom) {
+  __shared__ SDev sp;
+  __shared__ RowC rows[CHI_ROWS];
+  __shared__ double slw[3][CHI_ROWS];
+  __shared__ double red[MOM_N][TILE / 32];
+  __shared__ double lwsum[3];
+  __shared__ MathTab mt;
+  const int tid = threadIdx.x;
+  const int zb = g_zb[blockIdx.y], s0 = mem_s[g_off[blockIdx.y]];
+  if (tid < (int)(sizeof(SDev) / sizeof(double)))
+    reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S + s0)[tid];
+  math_tables_fill(mt, tid, TILE);
+  __syncthreads();
+  for (int r = tid; r < P.Nmu; r += TILE) {
+    rows[r] = row_consts(sp, P.flags, __ldg(P.mu + r), __ldg(P.smu + r));
+#pragma unroll
+    for (int l = 0; l < 3; ++l) slw[l][r] = __ldg(lw + (size_t)l * P.Nmu + r);
+  }
+  __syncthreads();
+  if (tid < 3) {  // multipoles of the additive noise: m sum_mu lw_l(mu), summed in row order as the direct kernel does
+    double t = 0.0;
+    for (int r = 0; r < P.Nmu; ++r) t += slw[tid][r];
+    lwsum[tid] = t;
+  }
+  __syncthreads();
+  const double b0 = sp.bias, m0 = 1.0 / P.nbar[zb] + shot[(size_t)s0 * P.Z + zb] + sp.pshot;
+  const bool plain = (sp.flags & SD_PLAIN) != 0;
+  const int nkb = (P.Nk + TILE - 1) / TILE;
+  double acc[MOM_N];
+#pragma unroll
+  for (int j = 0; j < MOM_N; ++j) acc[j] = 0.0;
+  for (int kb = blockIdx.x; kb < nkb; kb += gridDim.x) {
+    const int ki = kb * TILE + tid;
+    if (ki >= P.Nk) continue;
+    const double k = __ldg(P.k + ki);
+    int hA = -1, hB = -1, hN = -1;
+    double A[3] = {0.0, 0.0, 0.0}, C[3] = {0.0, 0.0, 0.0}, R[3] = {0.0, 0.0, 0.0};
+    for (int r = 0; r < P.Nmu; ++r) {
+      double err2, qf, F, W;
+      if (plain && hA >= 0) {
+        qf = 1.0;
+        eval_x_plain(mt, sp, rows[r], k, hA, hN, err2, F, W);
+      } else {
+        eval_x(mt, sp, rows[r], P.flags, k, hA, hB, hN, err2, qf, F, W);
+      }
+      const double We = W * tab_exp_neg(mt, -err2);
+      const double kaiser = fma(b0, qf, F);
+      const double Pt = fma(kaiser * kaiser, We, m0);  // the reference member, as spectro_legendre_chi2_kernel forms it
+      const double qw = qf * We;
+      const double a = qf * qw, c = 2.0 * (F * qw);
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        const double wl = slw[l][r];
+        A[l] = fma(wl, a, A[l]);
+        C[l] = fma(wl, c, C[l]);
+        R[l] = fma(wl, Pt, R[l]);
+      }
+    }
+    const double* pd = pl_data + ((size_t)ki * P.Z + zb) * 3;
+    const double* M = icov + ((size_t)ki * P.Z + zb) * 9;
+    double m[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) m[e] = __ldg(M + e);
+    double g[4][3], t[4][3];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      g[0][l] = -A[l];
+      g[1][l] = -C[l];
+      g[2][l] = -lwsum[l];
+      g[3][l] = __ldg(pd + l) - R[l];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)  // t_j = C^-1 g_j
+#pragma unroll
+      for (int l = 0; l < 3; ++l) t[j][l] = m[l * 3 + 0] * g[j][0] + m[l * 3 + 1] * g[j][1] + m[l * 3 + 2] * g[j][2];
+    int e = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = i; j < 4; ++j) {
+        double q = g[i][0] * t[j][0] + g[i][1] * t[j][1] + g[i][2] * t[j][2];
+        if (j != i) q += g[j][0] * t[i][0] + g[j][1] * t[i][1] + g[j][2] * t[i][2];
+        acc[e++] += q;
+      }
+  }
+  block_sum_store(acc, red, mom + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * MOM_N);
+}
+
+// chi2 of every member of the moment groups: block = group; the group's moments are summed over its CTAs in order,
+// then a thread per member evaluates v^T M v.  Written where the direct kernels write (slot 0 of the member's
+// (point, bin) partials, zeros in the other slots), so that one reduction serves both paths.
+__global__ void __launch_bounds__(128) spectro_moments_apply_kernel(SpectroParams P, const double* __restrict__ shot,
+                                                                    const int* __restrict__ g_zb,
+                                                                    const int* __restrict__ g_off,
+                                                                    const int* __restrict__ g_cnt,
+                                                                    const int* __restrict__ mem_s,
+                                                                    const double* __restrict__ mom, int gx_mom,
+                                                                    double* __restrict__ partial, int gx_part) {
+  __shared__ double c[MOM_N];
+  const int g = blockIdx.x, zb = g_zb[g], off = g_off[g], cnt = g_cnt[g];
+  if (threadIdx.x < MOM_N) {
+    double t = 0.0;
+    for (int cta = 0; cta < gx_mom; ++cta) t += mom[((size_t)g * gx_mom + cta) * MOM_N + threadIdx.x];
+    c[threadIdx.x] = t;
+  }
+  __syncthreads();
+  const int s0 = mem_s[off];
+  const SDev* sd = P.sdev + (size_t)zb * P.S;
+  const double b0 = sd[s0].bias, base = 1.0 / P.nbar[zb], ps = sd[s0].pshot;
+  const double m0 = base + shot[(size_t)s0 * P.Z + zb] + ps;
+  for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+    const int s = mem_s[off + j];
+    const double b = sd[s].bias, mj = base + shot[(size_t)s * P.Z + zb] + ps;
+    const double v0 = (b - b0) * (b + b0), v1 = b - b0, v2 = mj - m0;
+    const double chi = c[9] + v0 * (c[3] + v0 * c[0] + v1 * c[1] + v2 * c[2]) + v1 * (c[6] + v1 * c[4] + v2 * c[5]) +
+                       v2 * (c[8] + v2 * c[7]);
+    double* out = partial + ((size_t)s * P.Z + zb) * gx_part;
+    out[0] = chi;
+    for (int q = 1; q < gx_part; ++q) out[q] = 0.0;
+  }
+}
+
 // stand-alone wedge chi^2 on given lattices: grid (gx, Z, S)
 __global__ void __launch_bounds__(TILE) wedge_chi2_kernel(int Z, int Nmu, int Nk, const double* __restrict__ theory,
                                                           const double* __restrict__ data, const double* __restrict__ k,
@@ -1459,6 +1696,38 @@ extern "C" int cfp_spectro_plan_chi2(cfp_spectro_plan* pl, const double* data_h,
   return spectro_chi2_impl(pl, data_h, nullptr, shot_h, shot_data_h, chi2_h, stream);
 }
 
+// The groups of a batch as the likelihood entry points launch them: [groups of >= MOM_MIN members (moment kernels) |
+// smaller groups (one chunk each for the direct kernels) | single points].  CFP_NO_MOMENTS=1 sends every group through
+// the direct kernels in chunks of `chunk` (tests compare the two paths).
+static void spectro_build_groups(const cfp_spectro_plan* pl, int chunk, std::vector<int>& zb, std::vector<int>& off,
+                                 std::vector<int>& cnt, std::vector<int>& mem_s, int& n_mom, int& n_grp, int& n_one) {
+  const char* env = std::getenv("CFP_NO_MOMENTS");
+  if (env && env[0] == '1') {
+    n_mom = 0;
+    spectro_build_chunks(pl, chunk, zb, off, cnt, mem_s, n_grp, n_one);
+    return;
+  }
+  std::vector<int> gz, go, gc;
+  int ng = 0;
+  spectro_build_chunks(pl, INT_MAX, gz, go, gc, mem_s, ng, n_one);
+  n_mom = n_grp = 0;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < ng; ++i)
+      if ((gc[i] >= MOM_MIN) == (pass == 0)) {
+        zb.push_back(gz[i]), off.push_back(go[i]), cnt.push_back(gc[i]);
+        ++(pass == 0 ? n_mom : n_grp);
+      }
+  zb.insert(zb.end(), gz.begin() + ng, gz.end());
+  off.insert(off.end(), go.begin() + ng, go.end());
+  cnt.insert(cnt.end(), gc.begin() + ng, gc.end());
+}
+
+// CTAs per moment group: fill the GPU (3 resident CTAs per SM), at most one per block of wavenumbers
+static int moments_grid_x(const cfp_ctx* ctx, int n_mom, int nkb) {
+  const int64_t slots = 3 * (int64_t)ctx->sm_count;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(nkb, slots / std::max(n_mom, 1)));
+}
+
 extern "C" int cfp_spectro_plan_chi2_dev(cfp_spectro_plan* pl, const double* data_d, const double* shot_h,
                                          double* chi2_h, void* stream) {
   CFP_REQUIRE(data_d != nullptr, "data_d is NULL");
@@ -1475,9 +1744,9 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
   const size_t lattice = (size_t)pl->Nmu * pl->Nk;
   const int64_t ntile = (int64_t)((lattice + TILE - 1) / TILE);
   std::vector<int> ch_zb, ch_off, ch_cnt, mem_s;
-  int n_grp = 0, n_one = 0;
-  spectro_build_chunks(pl, CHI_CH, ch_zb, ch_off, ch_cnt, mem_s, n_grp, n_one);
-  const int nch = n_grp + n_one;
+  int n_mom = 0, n_grp = 0, n_one = 0;
+  spectro_build_groups(pl, CHI_CH, ch_zb, ch_off, ch_cnt, mem_s, n_mom, n_grp, n_one);
+  const int nch = n_mom + n_grp + n_one;
   // CTAs per chunk: each takes every gx-th block of TILE wavenumbers.  Pick the split that needs the fewest
   // (waves of resident CTAs) x (blocks per CTA), i.e. fills the GPU for small batches and avoids a ragged last wave
   // for large ones.
@@ -1494,10 +1763,11 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
     }
   }
   int *ch_zb_d = nullptr, *ch_off_d = nullptr, *ch_cnt_d = nullptr, *mem_s_d = nullptr;
-  double *data_d = nullptr, *shot_d = nullptr, *sd_d = nullptr, *part_d = nullptr, *chi2_d = nullptr;
+  double *data_d = nullptr, *shot_d = nullptr, *sd_d = nullptr, *part_d = nullptr, *chi2_d = nullptr, *mom_d = nullptr;
+  const int gxm = moments_grid_x(ctx, n_mom, nkb);
   auto cleanup = [&]() {
     for (void* q : {(void*)data_d, (void*)shot_d, (void*)sd_d, (void*)part_d, (void*)chi2_d, (void*)ch_zb_d, (void*)ch_off_d,
-                    (void*)ch_cnt_d, (void*)mem_s_d})
+                    (void*)ch_cnt_d, (void*)mem_s_d, (void*)mom_d})
       cfp_dev_free(ctx, q);
   };
   int rc;
@@ -1514,6 +1784,7 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
   if (shot_data_h) CHI_TRY(cfp_upload(ctx, shot_data_h, (size_t)Z, &sd_d));
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S * Z * gx, &part_d));
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d));
+  if (n_mom) CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)n_mom * gxm * MOM_N, &mom_d));
   CHI_TRY(cfp_upload(ctx, ch_zb.data(), ch_zb.size(), &ch_zb_d));
   CHI_TRY(cfp_upload(ctx, ch_off.data(), ch_off.size(), &ch_off_d));
   CHI_TRY(cfp_upload(ctx, ch_cnt.data(), ch_cnt.size(), &ch_cnt_d));
@@ -1533,13 +1804,23 @@ static int spectro_chi2_impl(cfp_spectro_plan* pl, const double* data_h, const d
     ctx->launches++;
   }
   const double* data_use = data_dev ? data_dev : data_d;
-  for (int c0 = 0; c0 < n_grp; c0 += 65535) {
-    const int nc = std::min(65535, n_grp - c0);
+  for (int c0 = 0; c0 < n_mom; c0 += 65535) {
+    const int nc = std::min(65535, n_mom - c0);
+    spectro_wedge_moments_kernel<<<dim3(gxm, nc), TILE, 0, st>>>(P, data_use, shot_d, ch_zb_d + c0, ch_off_d + c0, mem_s_d,
+                                                                mom_d + (size_t)c0 * gxm * MOM_N);
+    ctx->launches++;
+  }
+  if (n_mom) {
+    spectro_moments_apply_kernel<<<n_mom, 128, 0, st>>>(P, shot_d, ch_zb_d, ch_off_d, ch_cnt_d, mem_s_d, mom_d, gxm, part_d, gx);
+    ctx->launches++;
+  }
+  for (int c0 = n_mom; c0 < n_mom + n_grp; c0 += 65535) {
+    const int nc = std::min(65535, n_mom + n_grp - c0);
     spectro_chi2_kernel<CHI_CH, 3><<<dim3(gx, nc), TILE, 0, st>>>(P, data_use, shot_d, ch_zb_d + c0, ch_off_d + c0,
                                                                  ch_cnt_d + c0, mem_s_d, part_d);
     ctx->launches++;
   }
-  for (int c0 = n_grp; c0 < nch; c0 += 65535) {
+  for (int c0 = n_mom + n_grp; c0 < nch; c0 += 65535) {
     const int nc = std::min(65535, nch - c0);
     spectro_chi2_kernel<1, 5><<<dim3(gx, nc), TILE, 0, st>>>(P, data_use, shot_d, ch_zb_d + c0, ch_off_d + c0,
                                                             ch_cnt_d + c0, mem_s_d, part_d);
@@ -1571,24 +1852,26 @@ extern "C" int cfp_spectro_plan_chi2_legendre(cfp_spectro_plan* pl, const double
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   const int S = pl->S, Z = pl->Z, Nk = pl->Nk;
   std::vector<int> ch_zb, ch_off, ch_cnt, mem_s;
-  int n_grp = 0, n_one = 0;
-  spectro_build_chunks(pl, LEG_CH, ch_zb, ch_off, ch_cnt, mem_s, n_grp, n_one);
-  const int nch = n_grp + n_one;
+  int n_mom = 0, n_grp = 0, n_one = 0;
+  spectro_build_groups(pl, LEG_CH, ch_zb, ch_off, ch_cnt, mem_s, n_mom, n_grp, n_one);
+  const int nch = n_mom + n_grp + n_one, ndir = n_grp + n_one;
   const int nkb = (Nk + TILE - 1) / TILE;
+  const int gxm = moments_grid_x(ctx, n_mom, nkb);
   int gx = 1;
   {
     const int64_t slots = 4 * (int64_t)ctx->sm_count;
     int64_t best = INT64_MAX;
     for (int g = 1; g <= std::min(nkb, 64); ++g) {
-      const int64_t cost = (((int64_t)g * nch + slots - 1) / slots) * ((nkb + g - 1) / g);
+      const int64_t cost = (((int64_t)g * std::max(ndir, 1) + slots - 1) / slots) * ((nkb + g - 1) / g);
       if (cost < best) best = cost, gx = g;
     }
   }
   int *ch_zb_d = nullptr, *ch_off_d = nullptr, *ch_cnt_d = nullptr, *mem_s_d = nullptr;
   double *pd_d = nullptr, *ic_d = nullptr, *lw_d = nullptr, *shot_d = nullptr, *part_d = nullptr, *chi2_d = nullptr;
+  double* mom_d = nullptr;
   auto cleanup = [&]() {
     for (void* q : {(void*)pd_d, (void*)ic_d, (void*)lw_d, (void*)shot_d, (void*)part_d, (void*)chi2_d, (void*)ch_zb_d,
-                    (void*)ch_off_d, (void*)ch_cnt_d, (void*)mem_s_d})
+                    (void*)ch_off_d, (void*)ch_cnt_d, (void*)mem_s_d, (void*)mom_d})
       cfp_dev_free(ctx, q);
   };
   int rc;
@@ -1606,6 +1889,7 @@ extern "C" int cfp_spectro_plan_chi2_legendre(cfp_spectro_plan* pl, const double
   LEG_TRY(cfp_upload(ctx, shot_h, (size_t)S * Z, &shot_d));
   LEG_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S * Z * gx, &part_d));
   LEG_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d));
+  if (n_mom) LEG_TRY(cfp_upload<double>(ctx, nullptr, (size_t)n_mom * gxm * MOM_N, &mom_d));
   LEG_TRY(cfp_upload(ctx, ch_zb.data(), ch_zb.size(), &ch_zb_d));
   LEG_TRY(cfp_upload(ctx, ch_off.data(), ch_off.size(), &ch_off_d));
   LEG_TRY(cfp_upload(ctx, ch_cnt.data(), ch_cnt.size(), &ch_cnt_d));
@@ -1623,7 +1907,17 @@ extern "C" int cfp_spectro_plan_chi2_legendre(cfp_spectro_plan* pl, const double
   SpectroParams P;
   spectro_fill_params(pl, 16, P);
   LEG_TRY(spectro_prepare(pl, P, st));
-  for (int c0 = 0; c0 < nch; c0 += 65535) {
+  for (int c0 = 0; c0 < n_mom; c0 += 65535) {
+    const int nc = std::min(65535, n_mom - c0);
+    spectro_legendre_moments_kernel<<<dim3(gxm, nc), TILE, 0, st>>>(P, pd_d, ic_d, lw_d, shot_d, ch_zb_d + c0, ch_off_d + c0,
+                                                                   mem_s_d, mom_d + (size_t)c0 * gxm * MOM_N);
+    ctx->launches++;
+  }
+  if (n_mom) {
+    spectro_moments_apply_kernel<<<n_mom, 128, 0, st>>>(P, shot_d, ch_zb_d, ch_off_d, ch_cnt_d, mem_s_d, mom_d, gxm, part_d, gx);
+    ctx->launches++;
+  }
+  for (int c0 = n_mom; c0 < nch; c0 += 65535) {
     const int nc = std::min(65535, nch - c0);
     spectro_legendre_chi2_kernel<<<dim3(gx, nc), TILE, 0, st>>>(P, pd_d, ic_d, lw_d, shot_d, ch_zb_d + c0, ch_off_d + c0,
                                                                ch_cnt_d + c0, mem_s_d, part_d);

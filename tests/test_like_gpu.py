@@ -174,3 +174,38 @@ def test_photo_batch_pipeline_equals_single_chunks(photo_fm):
     parts = np.concatenate([like.loglike_batch(mat[:4096], keys=keys), like.loglike_batch(mat[4096:], keys=keys)])
     assert np.array_equal(whole, parts)
     assert np.all(np.isfinite(whole)) and whole.max() <= 1e-9
+
+
+@pytest.mark.parametrize("flag", ["wedges", "legendre"])
+def test_spectro_moment_path_equals_direct_kernels(spectro_fm, monkeypatch, flag):
+    """Groups of >= 4 points that differ only in bias and shot noise are evaluated through the moments of the group
+    (one lattice pass per bin); CFP_NO_MOMENTS=1 sends the same batch through the direct kernels.  The two agree to
+    rounding, a member equal to the group's reference exactly, and the fiducial's chi2 stays (numerically) zero."""
+    from cosmicfishpie_b200 import likelihood as lk
+
+    like = lk.SpectroLikelihood(cosmoFM_data=spectro_fm, leg_flag=flag)
+    keys = ["h", "lnbg_1", "lnbg_2", "lnbg_3", "lnbg_4", "Ps_1", "Ps_3"]
+    fid = np.array([spectro_fm.allparams[k] for k in keys])
+    rng = np.random.default_rng(31)
+    mat = np.tile(fid, (150, 1))
+    mat[1:, 1:5] += 0.02 * rng.standard_normal((149, 4))
+    mat[1:, 5:] = rng.uniform(0.0, 60.0, size=(149, 2))
+    mat[100:, 0] = fid[0] * 1.01       # a second cosmology of the bank: its own groups
+    mat[148:, 0] = fid[0] * 0.99       # ... and a group of 2 (direct kernels either way)
+    mom = like.chi2_matrix(keys, mat)
+    monkeypatch.setenv("CFP_NO_MOMENTS", "1")
+    direct = like.chi2_matrix(keys, mat)
+    monkeypatch.delenv("CFP_NO_MOMENTS")
+    assert mom[0] < 1e-15 and direct[0] < 1e-15
+    tol = 1e-11 if flag == "wedges" else 1e-8  # (the 3x3 multipole covariances are ill-conditioned, cond ~ 1e6)
+    # the group of two takes the direct kernels either way (the split of the lattice over CTAs may differ)
+    assert np.max(np.abs(mom[148:] - direct[148:]) / direct[148:]) < 1e-12
+    assert np.max(np.abs(mom[1:] - direct[1:]) / direct[1:]) < tol
+    # a large, bias-only batch (what bench.py times) stays finite and ordered like the direct evaluation
+    big = np.tile(fid, (1500, 1))
+    big[:, 1:5] *= 1 + 0.01 * rng.standard_normal((1500, 4))
+    a = like.chi2_matrix(keys, big)
+    monkeypatch.setenv("CFP_NO_MOMENTS", "1")
+    b = like.chi2_matrix(keys, big[:64])
+    monkeypatch.delenv("CFP_NO_MOMENTS")
+    assert np.all(np.isfinite(a)) and np.max(np.abs(a[:64] - b) / b) < tol
