@@ -434,9 +434,9 @@ def run_gpu(args):
     like_photo = like_block(Lp, kp, fm_ph.allparams, 16384, 0.02)
     Ls = SpectroLikelihood(cosmoFM_data=fm_sp)
     ks = [k for k in fm_sp.freeparams if k.startswith("lnbg")]
-    like_spectro = like_block(Ls, ks, fm_sp.allparams, 2048, 0.01)
+    like_spectro = like_block(Ls, ks, fm_sp.allparams, 16384, 0.01)
     Ll = SpectroLikelihood(cosmoFM_data=fm_sp, leg_flag="legendre")
-    like_legendre = like_block(Ll, ks, fm_sp.allparams, 2048, 0.01)
+    like_legendre = like_block(Ll, ks, fm_sp.allparams, 16384, 0.01)
 
     # ---- C ABI only: plan_create from host buffers + run + fetch -------------------------------------
     def cabi_step():

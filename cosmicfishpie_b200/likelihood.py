@@ -499,7 +499,8 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
                                                 spectrononlinearpars=fm.Spectrononlinpars, PShotpars=fm.PShotpars,
                                                 configuration=fm, cosmo_set=cs)
             base[c] = np.array([obs.scalar_block(z) for z in zs])
-        scal = np.stack([base[c] for c in cosmo_of_s])  # [B, Z, NSCAL]
+        cu, cinv = np.unique(cosmo_of_s, return_inverse=True)
+        scal = np.stack([base[c] for c in cu])[np.asarray(cinv).ravel()]  # [B, Z, NSCAL]
         nu = fid_obs.nuisance
         for zb, z in enumerate(zs):
             b = nu.gcsp_zvalue_to_zindex(z)

@@ -29,7 +29,10 @@ def main():
     buf = io.StringIO()
     for name, like, keys, allp, B in (
             ("photo", PhotometricLikelihood(cosmo_data=a), [k for k in a.freeparams if k not in bench.P7], a.allparams, 16384),
-            ("spectro", SpectroLikelihood(cosmoFM_data=b), [k for k in b.freeparams if k.startswith("lnbg")], b.allparams, 2048)):
+            ("spectro", SpectroLikelihood(cosmoFM_data=b), [k for k in b.freeparams if k.startswith("lnbg")], b.allparams, 2048),
+            ("spectro 16k", SpectroLikelihood(cosmoFM_data=b), [k for k in b.freeparams if k.startswith("lnbg")], b.allparams, 16384),
+            ("legendre 16k", SpectroLikelihood(cosmoFM_data=b, leg_flag="legendre"),
+             [k for k in b.freeparams if k.startswith("lnbg")], b.allparams, 16384)):
         fid = np.array([allp[k] for k in keys])
         mat = fid * (1.0 + 0.02 * np.random.default_rng(0).standard_normal((B, len(keys))))
         like.loglike_batch(mat, keys=keys)
