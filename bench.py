@@ -49,12 +49,13 @@ SPECTRO_SPEC = "Euclid-Spectroscopic-ISTF-Pessimistic"
 NMU, NK = 129, 8193
 WORKLOAD = f"euclid_3x2pt_13bins_lmax5000_npar23 + gcsp_4bins_npar15_3PT_lattice{NMU}x{NK}"
 # FP64 operations spectro_fisher_kernel EXECUTES per lattice cell and bin, frozen from the ncu source-page counters of
-# the final kernel (predicated-on thread instructions, DADD + DMUL + 2 DFMA; profiles/r1d_*): a full evaluation of
+# the final kernel (predicated-on thread instructions, DADD + DMUL + 2 DFMA; profiles/r1e_*): a full evaluation of
 # P_obs of one stencil point incl. its log (F_FULL), a point that differs from the fiducial only in the bias and
 # re-uses its look-ups (F_LIGHT), and the per-cell epilogue (derivative scaling, V_eff, weights: F_FIXED).
-# 15 full + 2 light + fixed = 1525 measured on the bench workload.  The Gram update adds 128 flop per 8x8 tile (DMMA).
-F_FULL, F_LIGHT, F_FIXED = 94.3, 30.0, 50.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one spectro_fisher_kernel launch (ncu --set full, profiles/r1d)
+# 15 full + 2 light + fixed = 1510 measured on the bench workload (DFMA 2.551e9, DMUL 0.903e9, DADD 0.379e9 thread
+# instructions per launch).  The Gram update adds 128 flop per 8x8 tile (DMMA).
+F_FULL, F_LIGHT, F_FIXED = 93.35, 30.0, 50.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one spectro_fisher_kernel launch (ncu --set full, profiles/r1e)
 TRAFFIC_BYTES = 2.99e6
 
 

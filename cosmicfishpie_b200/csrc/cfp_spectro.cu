@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
   double* sm_w = smem + NB * 8 * LDC;                  // [TILE]
   MathTab& mt = *reinterpret_cast<MathTab*>(sm_w + TILE);  // (at a compile-time offset: no address arithmetic in the loops)
   SDev* sm_s = reinterpret_cast<SDev*>(&mt + 1);       // [S], in work-list order
-  RowC* sm_r = reinterpret_cast<RowC*>(sm_s + P.S);    // [S], likewise
+  RowC* const sm_r0 = reinterpret_cast<RowC*>(sm_s + P.S);  // [ROWS][S], likewise
   math_tables_fill(mt, threadIdx.x, TILE);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int zb = blockIdx.y;
@@ -697,9 +697,15 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
   double k = 0.0, wcol = 0.0;
   int hA = -1, hB = -1, hN = -1;
 
-  for (int64_t tile = t_begin; tile < t_end; ++tile) {
-    const int kb = (int)(tile / nrows);
-    const int row = row_lo + (int)(tile - (int64_t)kb * nrows);
+#ifndef CFP_X_ROWS
+#define CFP_X_ROWS 2
+#endif
+  constexpr int ROWS = CFP_X_ROWS;  // mu rows (tiles of one block of wavenumbers) per pair of barriers
+  for (int64_t tile0 = t_begin; tile0 < t_end;) {
+    const int kb = (int)(tile0 / nrows);
+    const int row0 = (int)(tile0 - (int64_t)kb * nrows);
+    const int nr = (int)min((int64_t)min(ROWS, nrows - row0), t_end - tile0);
+    tile0 += nr;
     if (kb != kb_cur) {  // new block of wavenumbers: new k, Simpson weight; the hints restart
       kb_cur = kb;
       ki = kb * TILE + tid;
@@ -709,12 +715,17 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
       wcol = (k * k) * __ldg(P.wk + ki);
       hA = hB = hN = -1;
     }
+    __syncthreads();  // every warp is done with the previous rows' constants
+    for (int idx = tid; idx < nr * (n_full + 1); idx += TILE) {  // the fiducial and the fully evaluated points
+      const int rr = idx / (n_full + 1), t = idx - rr * (n_full + 1);
+      sm_r0[rr * P.S + t] = row_consts(sm_s[t], P.flags, __ldg(P.mu + row_lo + row0 + rr), __ldg(P.smu + row_lo + row0 + rr));
+    }
+    __syncthreads();
+    for (int rr = 0; rr < nr; ++rr) {
+    const int row = row_lo + row0 + rr;
+    const RowC* const sm_r = sm_r0 + rr * P.S;
     const int64_t cell = (int64_t)row * P.Nk + ki;
     const bool valid = col_ok && cell >= P.cell_begin && cell < P.cell_end;
-    __syncthreads();  // every warp is done with the previous tile's row constants
-    for (int t = tid; t <= n_full; t += TILE)  // the fiducial and the fully evaluated points
-      sm_r[t] = row_consts(sm_s[t], P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
-    __syncthreads();
     if (__any_sync(0xffffffffu, valid)) {  // (uniform per warp; the barriers are per tile)
 #pragma unroll 4
     for (int p = 0; p < NB * 8; ++p) sm_d[p * LDC + tid] = 0.0;
@@ -818,6 +829,7 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
     }
     __syncwarp();
     }  // any valid cell in this warp's part of the tile
+    }  // rows of the group
   }
   // cross-warp reduction in fixed order, then one partial per CTA
   __syncthreads();
@@ -1594,7 +1606,7 @@ static cudaError_t launch_fisher(const SpectroParams& P, dim3 grid, size_t smem,
 
 static size_t fisher_smem(int nb, int S) {
   const int T = nb * (nb + 1) / 2;
-  return std::max((size_t)(nb * 8 * (TILE + LDPAD) + TILE) * sizeof(double) + (size_t)S * (sizeof(SDev) + sizeof(RowC)) +
+  return std::max((size_t)(nb * 8 * (TILE + LDPAD) + TILE) * sizeof(double) + (size_t)S * (sizeof(SDev) + CFP_X_ROWS * sizeof(RowC)) +
                       sizeof(MathTab),
                   (size_t)(TILE / 32) * T * 64 * sizeof(double));
 }
