@@ -294,6 +294,10 @@ int cfp_photo_plan_chi2(cfp_photo_plan* plan, const double* data_h, int nblk, co
  * with the plan's Simpson weights, volumes and number densities.
  *   data_h[Z][Nmu][Nk] : data spectra including noise, or NULL = stencil point 0 + 1/nbar_z + shot_data_h[z]
  *   shot_h[S][Z], shot_data_h[Z] (may be NULL = 0)
+ * Points of a bin whose scalar blocks differ only in the galaxy bias are evaluated together: groups of >= 4 through
+ * the ten lattice moments of the group (one pass over the lattice per group and bin, chi2 = v^T M v per member),
+ * smaller groups in one pass of the direct kernel.  Environment CFP_NO_MOMENTS=1 (read per call) disables the moment
+ * path; the same applies to cfp_spectro_plan_chi2_legendre.
  */
 int cfp_spectro_plan_chi2(cfp_spectro_plan* plan, const double* data_h, const double* shot_h,
                           const double* shot_data_h, double* chi2_h, void* stream);
