@@ -634,81 +634,21 @@ __device__ __forceinline__ double eval_x_plain(const MathTab& mt, const SDev& p,
   return eval_x_plain(mt, p, rc, k, hA, hN, err2, F, W);
 }
 
-// Two plain points at once: all fourteen records are requested before any bound is checked, ONE (rare) branch repairs
-// wrong hints, and the arithmetic of the two points is a single basic block the scheduler can interleave.
-__device__ __forceinline__ void eval_x_plain2(const MathTab& mt, const SDev& p0, const RowC& r0, const SDev& p1,
-                                              const RowC& r1, double k, int& hA, int& hN, double& X0, double& e0,
-                                              double& X1, double& e1) {
-  const double k0 = k * r0.G, k1 = k * r1.G;
-  const double2* a0 = reinterpret_cast<const double2*>(p0.blkA + (size_t)hA * CUBIC_BLK);
-  const double2* b0 = reinterpret_cast<const double2*>(p0.blkB + (size_t)hA * CUBIC_BLK);
-  const double2* n0 = reinterpret_cast<const double2*>(p0.blkN + (size_t)hN * LIN_BLK);
-  const double2* a1 = reinterpret_cast<const double2*>(p1.blkA + (size_t)hA * CUBIC_BLK);
-  const double2* b1 = reinterpret_cast<const double2*>(p1.blkB + (size_t)hA * CUBIC_BLK);
-  const double2* n1 = reinterpret_cast<const double2*>(p1.blkN + (size_t)hN * LIN_BLK);
-  double2 bA0 = __ldg(a0), bA1 = __ldg(a1), bN0 = __ldg(n0), bN1 = __ldg(n1);
-  double2 a01 = __ldg(a0 + 1), a23 = __ldg(a0 + 2), f01 = __ldg(b0 + 1), f23 = __ldg(b0 + 2), ys0 = __ldg(n0 + 1);
-  double2 c01 = __ldg(a1 + 1), c23 = __ldg(a1 + 2), g01 = __ldg(b1 + 1), g23 = __ldg(b1 + 2), ys1 = __ldg(n1 + 1);
-  const bool ok = (k0 >= bA0.x && k0 < bA0.y) && (k1 >= bA1.x && k1 < bA1.y) && (k0 >= bN0.x && k0 < bN0.y) &&
-                  (k1 >= bN1.x && k1 < bN1.y);
-  if (!ok) {
-    int h = locate<CUBIC_BLK>(p0.blkA, p0.nA, k0, hA, bA0.x);
-    a0 = reinterpret_cast<const double2*>(p0.blkA + (size_t)h * CUBIC_BLK);
-    b0 = reinterpret_cast<const double2*>(p0.blkB + (size_t)h * CUBIC_BLK);
-    a01 = __ldg(a0 + 1), a23 = __ldg(a0 + 2), f01 = __ldg(b0 + 1), f23 = __ldg(b0 + 2);
-    h = locate<CUBIC_BLK>(p1.blkA, p1.nA, k1, h, bA1.x);
-    a1 = reinterpret_cast<const double2*>(p1.blkA + (size_t)h * CUBIC_BLK);
-    b1 = reinterpret_cast<const double2*>(p1.blkB + (size_t)h * CUBIC_BLK);
-    c01 = __ldg(a1 + 1), c23 = __ldg(a1 + 2), g01 = __ldg(b1 + 1), g23 = __ldg(b1 + 2);
-    hA = h;
-    h = locate<LIN_BLK>(p0.blkN, p0.nN, k0, hN, bN0.x);
-    ys0 = __ldg(reinterpret_cast<const double2*>(p0.blkN + (size_t)h * LIN_BLK + 2));
-    h = locate<LIN_BLK>(p1.blkN, p1.nN, k1, h, bN1.x);
-    ys1 = __ldg(reinterpret_cast<const double2*>(p1.blkN + (size_t)h * LIN_BLK + 2));
-    hN = h;
-  }
-  {
-    const double err = k * r0.errc;
-    e0 = err * err;
-    const double u = k0 - bA0.x;
-    const double pdd = a01.x + u * (a01.y + u * (a23.x + u * a23.y));
-    const double F = (f01.x + u * (f01.y + u * (f23.x + u * f23.y))) * r0.fmu2;
-    const double pnw = fma(ys0.y, k0 - bN0.x, ys0.x);
-    const double e = tab_exp_neg(mt, -r0.sv2 * (k0 * k0));
-    const double t = k0 * r0.fogc;
-    const double W = fast_div(p0.baos * fma(e, pdd - pnw, pnw), fma(t, t, 1.0));
-    const double kaiser = p0.bias + F;
-    X0 = (kaiser * kaiser) * W;
-  }
-  {
-    const double err = k * r1.errc;
-    e1 = err * err;
-    const double u = k1 - bA1.x;
-    const double pdd = c01.x + u * (c01.y + u * (c23.x + u * c23.y));
-    const double F = (g01.x + u * (g01.y + u * (g23.x + u * g23.y))) * r1.fmu2;
-    const double pnw = fma(ys1.y, k1 - bN1.x, ys1.x);
-    const double e = tab_exp_neg(mt, -r1.sv2 * (k1 * k1));
-    const double t = k1 * r1.fogc;
-    const double W = fast_div(p1.baos * fma(e, pdd - pnw, pnw), fma(t, t, 1.0));
-    const double kaiser = p1.bias + F;
-    X1 = (kaiser * kaiser) * W;
-  }
-}
-
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
 
-// Resident CTAs per SM the kernel is compiled for.  The loop is latency-bound (table look-ups, Horner chains), so
-// resident warps matter more than registers: measured on B200 for the 2-block Gram tile, 2 CTAs/SM 1.83 ms,
-// 3 CTAs 1.13 ms, 4 CTAs (64 registers) 0.97 ms, 5 CTAs (48 registers, ~90 B of spills that ptxas places around
-// the per-tile code, not the evaluation loop) 0.88 ms.  Shared memory (43 KB per CTA) stops at 5.
-#ifndef CFP_X_MINB
-#define CFP_X_MINB 5
-#endif
-constexpr int fisher_min_blocks(int nb) { return nb <= 2 ? CFP_X_MINB : (nb == 3 ? 3 : 2); }
+// Resident CTAs per SM the kernel is compiled for.  The loop is latency-bound (table look-ups, Horner chains).
+// Measured on B200 for the 2-block Gram tile before the plain-point loop: 2 CTAs/SM 1.83 ms, 3 CTAs 1.13 ms, 4 CTAs
+// (64 registers) 0.97 ms, 5 CTAs (48 registers, spills around the per-tile code) 0.88 ms; with the plain-point loop
+// 4 and 5 CTAs tie (0.782 / 0.785 ms) and 3 CTAs lose (0.859).  Evaluating two stencil points per iteration (all
+// records requested up front, one repair branch, one basic block of arithmetic) was slower at every occupancy:
+// 1.34 ms (5 CTAs, spills), 1.06 (4), 1.00 (3), 1.16 (2 CTAs, 128 registers, no spills).  Shared memory (44 KB per
+// CTA) stops at 5.
+constexpr int fisher_min_blocks(int nb) { return nb <= 2 ? 5 : (nb == 3 ? 3 : 2); }
+constexpr int FISHER_ROWS = 2;  // mu rows per pair of barriers (1: 0.785 ms, 2: 0.776, 3: 0.772 and 1.1 KB more shared memory)
 // The lattice of one bin is cut into tiles of TILE consecutive wavenumbers x ONE mu row; a CTA takes a contiguous
 // run of tiles in (k block, mu row) order, i.e. it walks down the rows of a k block.  Along that walk k' = k G(mu)
 // moves by a fraction of a table piece per step, so every thread keeps valid piece hints from tile to tile, and
@@ -761,10 +701,7 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
   double k = 0.0, wcol = 0.0;
   int hA = -1, hB = -1, hN = -1;
 
-#ifndef CFP_X_ROWS
-#define CFP_X_ROWS 2
-#endif
-  constexpr int ROWS = CFP_X_ROWS;  // mu rows (tiles of one block of wavenumbers) per pair of barriers
+  constexpr int ROWS = FISHER_ROWS;  // mu rows (tiles of one block of wavenumbers) per pair of barriers
   for (int64_t tile0 = t_begin; tile0 < t_end;) {
     const int kb = (int)(tile0 / nrows);
     const int row0 = (int)(tile0 - (int64_t)kb * nrows);
@@ -834,21 +771,7 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
     const RowC* rp = sm_r + 1;
     // points with their own cosmology / AP factors: full evaluation; the plain ones (all of them in a forecast
     // but the one the shot-noise derivatives read) first, in the loop without configuration branches
-#ifndef CFP_X_PAIR
-#define CFP_X_PAIR 0
-#endif
-    int i = n_plain;
-#if CFP_X_PAIR
-    for (; i >= 2; i -= 2, sp += 2, rp += 2) {
-      double X0p, e0p, X1p, e1p;
-      eval_x_plain2(mt, sp[0], rp[0], sp[1], rp[1], k, hA, hN, X0p, e0p, X1p, e1p);
-      const double l0 = X0p > 0.0 ? tab_log(mt, X0p) - e0p : CUDART_NAN;
-      const double l1 = X1p > 0.0 ? tab_log(mt, X1p) - e1p : CUDART_NAN;
-      sm_d[sp[0].par0 * LDC + tid] += sp[0].w0 * l0;
-      sm_d[sp[1].par0 * LDC + tid] += sp[1].w0 * l1;
-    }
-#endif
-    for (; i > 0; --i, ++sp, ++rp) {
+    for (int i = n_plain; i > 0; --i, ++sp, ++rp) {
       double err2;
       const double X = eval_x_plain(mt, *sp, *rp, k, hA, hN, err2);
       const double lnP = X > 0.0 ? tab_log(mt, X) - err2 : CUDART_NAN;
@@ -1684,7 +1607,7 @@ static cudaError_t launch_fisher(const SpectroParams& P, dim3 grid, size_t smem,
 
 static size_t fisher_smem(int nb, int S) {
   const int T = nb * (nb + 1) / 2;
-  return std::max((size_t)(nb * 8 * (TILE + LDPAD) + TILE) * sizeof(double) + (size_t)S * (sizeof(SDev) + CFP_X_ROWS * sizeof(RowC)) +
+  return std::max((size_t)(nb * 8 * (TILE + LDPAD) + TILE) * sizeof(double) + (size_t)S * (sizeof(SDev) + FISHER_ROWS * sizeof(RowC)) +
                       sizeof(MathTab),
                   (size_t)(TILE / 32) * T * 64 * sizeof(double));
 }
