@@ -65,6 +65,9 @@ class Nuisance:
     def vectorized_gcsp_bias_at_z(self, z):
         return self._spectro.vectorized_gcsp_bias_at_z(z)
 
+    def gcsp_bias_interp(self):
+        return self._spectro.gcsp_bias_interp()
+
     def gcsp_rescale_sigmapv_at_z(self, z, sigma_key="sigmap"):
         return self._spectro.gcsp_rescale_sigmapv_at_z(z, sigma_key=sigma_key)
 

@@ -98,6 +98,12 @@ class SpectroNuisance:
     def gcsp_bias_at_z(self, z):
         return self.gcsp_bias_at_zm()[self.gcsp_zvalue_to_zindex(z) - 1]
 
+    def gcsp_bias_interp(self):
+        """Degree-1 spline through the per-bin biases at the bin centres (nuisance.py:327-344)."""
+        from scipy.interpolate import InterpolatedUnivariateSpline
+
+        return InterpolatedUnivariateSpline(self.gcsp_zbins_mids(), self.gcsp_bias_at_zm(), k=1)
+
     def vectorized_gcsp_bias_at_z(self, z):
         return np.vectorize(self.gcsp_bias_at_z)(z)
 
@@ -197,9 +203,7 @@ class ComputeGalSpectro:
         self.kh_rescaling_bug = self.settings["kh_rescaling_bug"]
         self.kh_rescaling_beforespecerr_bug = self.settings["kh_rescaling_beforespecerr_bug"]
         self.bias_samples = bias_samples
-        self.use_bias_funcs = use_bias_funcs
-        if use_bias_funcs:
-            raise NotImplementedError("use_bias_funcs=True is not supported")
+        self.use_bias_funcs = use_bias_funcs  # per-bin biases interpolated linearly in z (spectro_obs.py:568-572)
 
     # --- cheap host scalars (same formulas as the reference) ----------------------------------
     def qparallel(self, z):
@@ -244,7 +248,10 @@ class ComputeGalSpectro:
         b[_lib.SP_QPER] = self.qperpendicular(z)
         b[_lib.SP_HUBBLE] = self.cosmo.scalar("Hubble", z)
         b[_lib.SP_DZ] = self.dz_err if self.dz_type == "constant" else self.dz_err * (1 + z)
-        b[_lib.SP_BIAS] = self.nuisance.gcsp_bias_at_z(z)
+        if self.use_bias_funcs:
+            b[_lib.SP_BIAS] = float(self.nuisance.gcsp_bias_interp()(z))
+        else:
+            b[_lib.SP_BIAS] = self.nuisance.gcsp_bias_at_z(z)
         b[_lib.SP_A1], b[_lib.SP_A2] = self.nuisance.qbias_coeffs()
         if not self.linear_switch:
             m0, m1, m2 = (self.P_ThetaTheta_Moments(z, m) for m in (0, 1, 2))
@@ -268,27 +275,27 @@ class ComputeGalSpectro:
     def observed_Pgg(self, z, k, mu, b_i=None):
         """P_obs(z; k, mu) for a separable mesh (k, mu from np.meshgrid) or any broadcastable pair of
         arrays; evaluated by the CUDA lattice kernel (reference: spectro_obs.py:845-911)."""
-        if b_i is not None:
-            raise NotImplementedError("b_i override is not supported")
-        return np.exp(self.lnpobs_gg(z, k, mu))
+        return np.exp(self.lnpobs_gg(z, k, mu, b_i=b_i))
 
     def lnpobs_gg(self, z, k, mu, b_i=None):
-        if b_i is not None:
-            raise NotImplementedError("b_i override is not supported")
+        """ln P_obs; `b_i` (a number) replaces the whole bias term b(z) b(k) of the Kaiser factor
+        (spectro_obs.py:617-618).  Arrays of b_i are not supported."""
+        if b_i is not None and np.ndim(b_i) != 0:
+            raise NotImplementedError("b_i must be a number")
         k = np.asarray(k, dtype=float)
         mu = np.asarray(mu, dtype=float)
         kb, mb = np.broadcast_arrays(k, mu)
         shape = kb.shape
         if kb.ndim == 2 and np.all(kb == kb[0:1, :]) and np.all(mb == mb[:, 0:1]):
             kg, mg = kb[0, :], mb[:, 0]  # meshgrid layout (Nmu, Nk)
-            out = _evaluate_lattice([self], [float(z)], kg, mg)[0, 0]
+            out = _evaluate_lattice([self], [float(z)], kg, mg, b_i=b_i)[0, 0]
             return out.reshape(shape)
         flat_k, flat_m = kb.ravel(), mb.ravel()
         out = np.empty(flat_k.size)
         # generic point list: one lattice row per distinct mu keeps the kernel's separable layout
         for m in np.unique(flat_m):
             sel = flat_m == m
-            out[sel] = _evaluate_lattice([self], [float(z)], flat_k[sel], np.array([m]))[0, 0, 0]
+            out[sel] = _evaluate_lattice([self], [float(z)], flat_k[sel], np.array([m]), b_i=b_i)[0, 0, 0]
         return out.reshape(shape)
 
 
@@ -322,11 +329,14 @@ def _pnw_arrays(cosmo_set: CosmoSet, zs, used):
     return pk, pp
 
 
-def _evaluate_lattice(points: List[ComputeGalSpectro], zs, kgrid, mugrid) -> np.ndarray:
-    """ln P_obs [S][Z][Nmu][Nk] of several parameter points (no derivatives)."""
+def _evaluate_lattice(points: List[ComputeGalSpectro], zs, kgrid, mugrid, b_i=None) -> np.ndarray:
+    """ln P_obs [S][Z][Nmu][Nk] of several parameter points (no derivatives); b_i: a number replacing the bias term."""
     cs = points[0].cosmo_set
     S, Z = len(points), len(zs)
     scal = np.array([[p.scalar_block(z) for z in zs] for p in points])
+    if b_i is not None:
+        scal[:, :, _lib.SP_BIAS] = float(b_i)
+        scal[:, :, _lib.SP_A1] = scal[:, :, _lib.SP_A2] = 0.0
     alias = np.tile(np.arange(S, dtype=np.int32)[:, None], (1, Z))
     linear = points[0].linear_switch
     used = {p.cosmo_index for p in points}

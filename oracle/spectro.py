@@ -94,7 +94,8 @@ class SpectroNuisance:
 class GalSpectro:
     """spectro_obs.py ComputeGalSpectro for the gg spectrum."""
 
-    def __init__(self, cosmo, fidcosmo, specs, settings, spectrobiaspars, nonlinpars):
+    def __init__(self, cosmo, fidcosmo, specs, settings, spectrobiaspars, nonlinpars, use_bias_funcs=False):
+        self.use_bias_funcs = use_bias_funcs  # spectro_obs.py:568-572
         self.cosmo, self.fid = cosmo, fidcosmo
         self.specs = specs
         s = dict(DEFAULT_SETTINGS)
@@ -143,8 +144,17 @@ class GalSpectro:
             return 1
         return 1 / (self.qper(z) ** 2 * self.qpar(z))
 
-    def kaiser(self, z, k, mu):
-        b = self.nuis.bias_at_z(z) * self.nuis.kscale(k)
+    def kaiser(self, z, k, mu, b_i=None):
+        """spectro_obs.py:585-634; b_i replaces the whole bias term, use_bias_funcs interpolates the per-bin biases
+        linearly in z (nuisance.py:327-344)."""
+        if b_i is not None:
+            b = b_i
+        elif self.use_bias_funcs:
+            from scipy.interpolate import InterpolatedUnivariateSpline
+
+            b = InterpolatedUnivariateSpline(self.nuis.zmids, self.nuis.bias_at_zm(), k=1)(z) * self.nuis.kscale(k)
+        else:
+            b = self.nuis.bias_at_z(z) * self.nuis.kscale(k)
         if self.s["bfs8terms"]:
             f = self.cosmo.fsigma8_of_z(z, k, tracer=self.tracer)  # spectro_obs.py:628-630
         else:
@@ -186,7 +196,7 @@ class GalSpectro:
         pnw = self.cosmo.nonwiggle_pow(z, k, tracer=self.tracer) / den
         return pdd * np.exp(-g * k**2) + pnw * (1 - np.exp(-g * k**2))
 
-    def observed_Pgg(self, z, k, mu):
+    def observed_Pgg(self, z, k, mu, b_i=None):
         """spectro_obs.py:845-911."""
         if self.s["kh_rescaling_beforespecerr_bug"]:
             k = self.k_units_change(k)
@@ -195,7 +205,7 @@ class GalSpectro:
             err = self.spec_err_z(z, k, mu)
             k = self.k_units_change(k)
         k, mu = self.kmu_ap(z, k, mu)
-        return self.bao(z) * (self.kaiser(z, k, mu) ** 2) * self.dewiggled(z, k, mu) * self.fog(z, k, mu) * (err**2) + 0
+        return self.bao(z) * (self.kaiser(z, k, mu, b_i) ** 2) * self.dewiggled(z, k, mu) * self.fog(z, k, mu) * (err**2) + 0
 
     def lnpobs_gg(self, z, k, mu):
         return np.log(self.observed_Pgg(z, k, mu))

@@ -183,6 +183,27 @@ def test_photo_stem_job_assembly(tmp_path):
                                                             tt.FIDUCIAL["Omegam"] * np.array([-0.03, -0.02, -0.01, 0.01, 0.02, 0.03])]
 
 
+def test_spectro_bias_overrides_on_the_host(extfiles, tmp_path):
+    """use_bias_funcs=True puts the z-interpolated bias into the scalar block (the oracle's kaiser term at the same
+    z), the default the per-bin constant; the block is all the device sees of the bias."""
+    from cosmicfishpie_b200 import _lib, spectro
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.spectro import SpectroNuisance
+
+    fm = make_fm(extfiles, tmp_path, ["GCsp"], {"h": 0.01})
+    plain = spectro.ComputeGalSpectro(dict(tt.FIDUCIAL), configuration=fm)
+    funcs = spectro.ComputeGalSpectro(dict(tt.FIDUCIAL), configuration=fm, use_bias_funcs=True)
+    nu = SpectroNuisance(fm.specs, dict(fm.Spectrobiaspars), {})
+    zm, bm = nu.zmids, nu.bias_at_zm()
+    for z in (1.0, 1.13, 1.47, 1.65):
+        assert plain.scalar_block(z)[_lib.SP_BIAS] == nu.bias_at_z(z)
+        want = np.interp(z, zm, bm)
+        assert np.isclose(funcs.scalar_block(z)[_lib.SP_BIAS], want, rtol=1e-14)
+    other = [q for q in range(_lib.SP_NSCAL) if q != _lib.SP_BIAS]
+    assert np.array_equal(plain.scalar_block(1.13)[other], funcs.scalar_block(1.13)[other])
+    assert funcs.scalar_block(1.13)[_lib.SP_BIAS] != plain.scalar_block(1.13)[_lib.SP_BIAS]
+
+
 def test_stencils_are_exact_on_polynomials():
     from cosmicfishpie_b200 import stencils
 

@@ -194,6 +194,26 @@ def test_photo_oracle_stem_bit_exact():
     assert np.array_equal(r["fisher"], g["fisher"])
 
 
+def test_spectro_oracle_bias_overrides_bit_exact(obank):
+    """observed_Pgg with b_i and with use_bias_funcs=True, between the bin centres (golden gcsp_kat_bias)."""
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.spectro import DEFAULT_SETTINGS, GalSpectro
+
+    g = golden("gcsp_kat_bias")
+    sp = _spectro_specs()
+    bias = dict(sp["sp_bias_parametrization"]["linear_log"])
+    cp = dict(tt.FIDUCIAL)
+    cp["h"] = tt.FIDUCIAL["h"] * 1.01
+    fid = obank.cosmo(dict(tt.FIDUCIAL))
+    kk, mm = np.meshgrid(g["k"], g["mu"])
+    plain = GalSpectro(obank.cosmo(cp), fid, sp, dict(DEFAULT_SETTINGS), bias, {})
+    funcs = GalSpectro(obank.cosmo(cp), fid, sp, dict(DEFAULT_SETTINGS), bias, {}, use_bias_funcs=True)
+    for i, z in enumerate(g["z"]):
+        assert np.array_equal(plain.observed_Pgg(z, kk, mm), g["pgg_default"][i])
+        assert np.array_equal(plain.observed_Pgg(z, kk, mm, b_i=float(g["b_i"])), g["pgg_b_i"][i])
+        assert np.array_equal(funcs.observed_Pgg(z, kk, mm), g["pgg_bias_funcs"][i])
+
+
 LIKE_PHOTO = {"fid": {}, "nuis": {"b1": 1.02, "b7": 0.985, "AIA": 1.04, "etaIA": 0.97, "betaIA": 1.01},
               "cosmo": {"Omegam": 1.01}, "both": {"h": 0.99, "b3": 1.03, "AIA": 0.95}}
 LIKE_SPECTRO = {"fid": {}, "nuis": {"lnbg_1": 1.01, "lnbg_4": 0.99}, "cosmo": {"h": 1.01},

@@ -193,6 +193,35 @@ def gcsp_small():
 
 
 @case
+def gcsp_kat_bias():
+    """Known-answer lattices of ComputeGalSpectro.observed_Pgg with the two bias overrides no Fisher path uses:
+    b_i (a number replacing the whole bias term, spectro_obs.py:617-618) and use_bias_funcs=True (per-bin biases
+    interpolated linearly in z, nuisance.py:327-344), at redshifts between the bin centres."""
+    import cosmicfishpie.fishermatrix.cosmicfish as cff
+    import cosmicfishpie.LSSsurvey.spectro_obs as spobs
+
+    ext = tt.extfiles_for(bank_dir())
+    with quiet():
+        fm = cff.FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"h": 0.01}, options=base_options("gcsp_kat_bias"),
+                              specifications={}, observables=["GCsp"], extfiles=ext, cosmoModel="w0waCDM", surveyName="Euclid")
+        cp = dict(tt.FIDUCIAL)
+        cp["h"] = tt.FIDUCIAL["h"] * 1.01
+        k = np.linspace(0.002, 0.3, 48)
+        mu = np.linspace(0.0, 1.0, 7)
+        kk, mm = np.meshgrid(k, mu)
+        plain = spobs.ComputeGalSpectro(cp, fiducial_cosmopars=dict(tt.FIDUCIAL))
+        funcs = spobs.ComputeGalSpectro(cp, fiducial_cosmopars=dict(tt.FIDUCIAL), use_bias_funcs=True)
+        zs = np.array([1.0, 1.13, 1.47, 1.65])
+        out = {"k": k, "mu": mu, "z": zs, "b_i": np.array(1.7),
+               "pgg_default": np.array([plain.observed_Pgg(z, kk, mm) for z in zs]),
+               "pgg_b_i": np.array([plain.observed_Pgg(z, kk, mm, b_i=1.7) for z in zs]),
+               "lnp_b_i": np.array([plain.lnpobs_gg(z, kk, mm, b_i=1.7) for z in zs]),
+               "pgg_bias_funcs": np.array([funcs.observed_Pgg(z, kk, mm) for z in zs])}
+    np.savez_compressed(os.path.join(GOLD, "gcsp_kat_bias.npz"), **out)
+    print("gcsp_kat_bias:", out["pgg_default"][1, 3, 5], out["pgg_b_i"][1, 3, 5], out["pgg_bias_funcs"][1, 3, 5])
+
+
+@case
 def wl_cfg2():
     """BASELINE cfg2 analogue: WL only, 5 cosmo + 3 IA."""
     run_photo("wl_cfg2", ["WL"], {p: 0.01 for p in PARS7[:5]}, save_derivs=("Omegam", "AIA", "etaIA"))
