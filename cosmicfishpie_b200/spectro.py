@@ -542,7 +542,9 @@ class SpectroDerivs:
         # broadcastable pair (the reference evaluates whatever it is given) is evaluated on the lattice of its
         # distinct k and mu values and gathered back.
         kk, mm = np.asarray(pk_kmesh, dtype=float), np.asarray(pk_mumesh, dtype=float)
-        if kk.ndim == 2 and kk.shape == mm.shape and np.all(kk == kk[0:1, :]) and np.all(mm == mm[:, 0:1]):
+        # (broadcast views, what FisherMatrix.set_pk_settings passes, are separable by construction: no 2 x Nmu x Nk scan)
+        if kk.ndim == 2 and kk.shape == mm.shape and (
+                (kk.strides[0] == 0 and mm.strides[1] == 0) or (np.all(kk == kk[0:1, :]) and np.all(mm == mm[:, 0:1]))):
             self._kgrid, self._mugrid, self._gather = kk[0, :], mm[:, 0], None
         else:
             kb, mb = np.broadcast_arrays(kk, mm)
