@@ -191,6 +191,51 @@ class FisherMatrix:
         self._materialise_spectro()
         return self._lazy["veff"]
 
+    def compute_binned_derivs(self, z_arr):
+        """{par: {"z_bins": z_arr, i: d ln P_obs / d par on the (mu, k) lattice}} for the given bin centres
+        (cosmicfish.py:383-405): the lattice kernel in materialising mode."""
+        from . import spectro as spectro_mod
+
+        self.pk_deriv = spectro_mod.SpectroDerivs(
+            z_arr, self.Pk_kmesh, self.Pk_mumesh, fiducial_spectro_obj=self.pk_obs_fid,
+            bias_samples=getattr(self, "obs_spectrum", ["g", "g"]),
+            configuration=self, stencil=self.stencil)
+        return self.pk_deriv.compute_derivs(freeparams=self.freeparams)
+
+    def fish_integrand(self, zi, k, mu, pi, pj):
+        """k^2 2 V_survey V_eff dlnP/dpi dlnP/dpj on the lattice (cosmicfish.py:514-542), from the materialised
+        derivative and effective-volume lattices of the device run."""
+        return k**2 * 2 * self.pk_cov.volume_survey(zi) * self.veff_arr[zi] * self.derivs_dict[pi][zi] * self.derivs_dict[pj][zi]
+
+    def fisher_integral(self, integrand):
+        """Simpson over mu, then over k, of a user-supplied lattice (cosmicfish.py:495-512).  A convenience for
+        inspecting single elements; compute() never calls it -- the fused kernel does the same sum with the same
+        weights on the device."""
+        from .quadrature import simpson_weights
+
+        integrand = np.asarray(integrand, dtype=float)
+        return float(simpson_weights(self.Pk_kgrid) @ (simpson_weights(self.Pk_mugrid) @ integrand))
+
+    def fisher_calculation(self, zi, p_i, p_j):
+        """One element of the Fisher matrix of bin zi (cosmicfish.py:472-493)."""
+        return self.fisher_integral(self.fish_integrand(zi, self.Pk_kmesh, self.Pk_mumesh, p_i, p_j))
+
+    def recap_options(self):
+        """Print the selected options (cosmicfish.py:1004-1050)."""
+        if self.settings["feedback"] > 1:
+            print("\n----------RECAP OF SELECTED OPTIONS--------\n\nSettings:")
+            for key in self.settings:
+                print("   " + key + ": {}".format(self.settings[key]))
+            print("\nSpecifications:")
+            for key in self.specs:
+                print("   " + key + ": {}".format(self.specs[key]))
+            for title, d in (("Cosmological parameters:", self.fiducialcosmopars), ("Photometric parameters:", self.photopars),
+                             ("IA parameters:", self.IApars), ("Bias parameters:", self.photobiaspars),
+                             ("SpectroBias parameters:", self.Spectrobiaspars), ("Shot noise parameters:", self.PShotpars)):
+                print(title)
+                for key in d:
+                    print("   " + key + ": {}".format(d[key]))
+
     def pk_LSS_Fisher(self, nbins):
         """Per-bin Fisher matrices [nbins][npar][npar] (cosmicfish.py:407-443), from the fused kernel."""
         return np.array(self.pk_fisher_per_bin[:nbins])

@@ -204,6 +204,18 @@ def test_spectro_bias_overrides_on_the_host(extfiles, tmp_path):
     assert funcs.scalar_block(1.13)[_lib.SP_BIAS] != plain.scalar_block(1.13)[_lib.SP_BIAS]
 
 
+def test_fisher_integral_is_scipy_simpson(extfiles, tmp_path):
+    """FisherMatrix.fisher_integral (cosmicfish.py:495-512): Simpson over mu then k, even sample counts included."""
+    from scipy.integrate import simpson
+
+    for nmu, nk in ((9, 65), (8, 64)):
+        fm = make_fm(extfiles, tmp_path, ["GCsp"], {"h": 0.01}, spectro_Pk_k_samples=nk, spectro_Pk_mu_samples=nmu)
+        fm.set_pk_settings()
+        lat = np.random.default_rng(nk).standard_normal((nmu, nk))
+        want = simpson(simpson(lat, x=fm.Pk_mumesh[:, 0], axis=0), x=fm.Pk_kmesh[0, :])
+        assert np.isclose(fm.fisher_integral(lat), want, rtol=1e-13)
+
+
 def test_stencils_are_exact_on_polynomials():
     from cosmicfishpie_b200 import stencils
 
