@@ -68,6 +68,15 @@ class Nuisance:
     def gcsp_bias_interp(self):
         return self._spectro.gcsp_bias_interp()
 
+    def gcsp_bias_at_zi(self, zi):
+        return self._spectro.gcsp_bias_at_zi(zi)
+
+    def gcsp_bias_kscale(self, k, z=None):
+        return self._spectro.gcsp_bias_kscale(k, z)
+
+    def vectorized_gcsp_rescale_sigmapv_at_z(self, z, sigma_key="sigmap"):
+        return self._spectro.vectorized_gcsp_rescale_sigmapv_at_z(z, sigma_key=sigma_key)
+
     def gcsp_rescale_sigmapv_at_z(self, z, sigma_key="sigmap"):
         return self._spectro.gcsp_rescale_sigmapv_at_z(z, sigma_key=sigma_key)
 

@@ -60,6 +60,17 @@ class GalaxyPhotoDist:
         powv = np.array([e**self.ngamma for e in expo.ravel()]).reshape(expo.shape)
         return (z / self.z0_p) ** 2 * np.exp(-powv)
 
+    def n_i(self, z, i, obs="GCph"):
+        """dN/dz restricted to tomographic bin i, no photo-z errors (photo_window.py:85-110)."""
+        zb = self.z_bins_WL if obs == "WL" else self.z_bins_GCph
+        nb = self.n_bins_WL if obs == "WL" else self.n_bins_GCph
+        if i == 0 or i > nb:
+            return None
+        z = np.atleast_1d(z)
+        out = self.dNdz(z)
+        out[~((z <= zb[i]) & (z >= zb[i - 1]))] = 0.0
+        return out
+
     def ngal_photoz(self, z, i, obs):
         if obs == "GCph":
             zb = self.z_bins_GCph

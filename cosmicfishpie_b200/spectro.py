@@ -107,6 +107,20 @@ class SpectroNuisance:
     def vectorized_gcsp_bias_at_z(self, z):
         return np.vectorize(self.gcsp_bias_at_z)(z)
 
+    def gcsp_bias_at_zi(self, zi):
+        """Bias of the bin with (1-based) index zi (nuisance.py:268-283)."""
+        return self.gcsp_bias_at_zm()[zi - 1]
+
+    def gcsp_bias_kscale(self, k, z=None):
+        """Scale dependence of the bias: (1 + k^2 A2) / (1 + k A1) for the Q-bias model, else 1 (nuisance.py:306-325)."""
+        if k is not None and self.sp_bias_model == "linear_Qbias":
+            a1, a2 = self.qbias_coeffs()
+            return (1 + k**2 * a2) / (1 + k * a1)
+        return 1
+
+    def vectorized_gcsp_rescale_sigmapv_at_z(self, z, sigma_key="sigmap"):
+        return np.vectorize(lambda zz: self.gcsp_rescale_sigmapv_at_z(zz, sigma_key=sigma_key))(z)
+
     def qbias_coeffs(self):
         if self.sp_bias_model == "linear_Qbias":
             return self.Spectrobiasparams.get("A1", 0.0), self.Spectrobiasparams.get("A2", 0.0)
@@ -214,6 +228,51 @@ class ComputeGalSpectro:
 
     def BAO_term(self, z):
         return 1 / (self.qperpendicular(z) ** 2 * self.qparallel(z)) if self.APbool else 1
+
+    # coordinate maps of the lattice (spectro_obs.py:386-506): closed-form host helpers for inspection -- the lattice
+    # kernel folds them into per-(point, mu row) constants (RowC in csrc/cfp_spectro.cu) and never calls these
+    def kpar(self, z, k, mu):
+        return k * mu * (1 / self.qparallel(z))
+
+    def kper(self, z, k, mu):
+        return k * np.sqrt(1 - mu**2) * (1 / self.qperpendicular(z))
+
+    def k_units_change(self, k):
+        if self.kh_rescaling_bug:
+            return k * (self.cosmo.cosmopars["h"] / self.fiducialcosmo.cosmopars["h"])
+        return k
+
+    def kmu_alc_pac(self, z, k, mu):
+        if not self.APbool:
+            return k, mu
+        kap = np.sqrt(self.kpar(z, k, mu) ** 2 + self.kper(z, k, mu) ** 2)
+        return kap, self.kpar(z, k, mu) / kap
+
+    def spec_err_z(self, z, k, mu):
+        dz = self.dz_err if self.dz_type == "constant" else self.dz_err * (1 + z)
+        err = dz * (1 / self.cosmo.scalar("Hubble", z)) * self.kpar(z, k, mu)
+        return np.exp(-(1 / 2) * err**2)
+
+    def sigmavNL(self, zz, mu):
+        """Damping scale of the BAO wiggles (spectro_obs.py:699-722)."""
+        if self.linear_switch:
+            return 0
+        f0, f1, f2 = (self.P_ThetaTheta_Moments(zz, m) for m in (0, 1, 2))
+        sv = np.sqrt(f0 + 2 * mu**2 * f1 + mu**2 * f2)
+        if self.rescale_sigmav:
+            sv = sv * self.nuisance.gcsp_rescale_sigmapv_at_z(zz, sigma_key="sigmav")
+        return sv
+
+    def observed_P_ij(self, z, k, mu, bsi="g", bsj="g"):
+        """Galaxy auto-spectrum through the lattice kernel (spectro_obs.py:913-933 for bias samples g, g)."""
+        if (bsi, bsj) != ("g", "g"):
+            raise NotImplementedError("only the galaxy auto-spectrum is in scope")
+        return self.observed_Pgg(z, k, mu)
+
+    def lnpobs_ij(self, z, k, mu, bsi="g", bsj="g"):
+        if (bsi, bsj) != ("g", "g"):
+            raise NotImplementedError("only the galaxy auto-spectrum is in scope")
+        return self.lnpobs_gg(z, k, mu)
 
     def P_ThetaTheta_Moments(self, zz, moment=0):
         c = self.fiducialcosmo if self.fix_cosmo_nl_terms else self.cosmo

@@ -204,6 +204,34 @@ def test_spectro_bias_overrides_on_the_host(extfiles, tmp_path):
     assert funcs.scalar_block(1.13)[_lib.SP_BIAS] != plain.scalar_block(1.13)[_lib.SP_BIAS]
 
 
+def test_spectro_coordinate_helpers_equal_oracle(extfiles, toy_bank, tmp_path):
+    """kpar / kper / kmu_alc_pac / spec_err_z / sigmavNL / BAO_term of ComputeGalSpectro (spectro_obs.py:342-535,
+    699-722) against the oracle's (bit-exact on the reference goldens), at a shifted cosmology."""
+    from cosmicfishpie_b200 import spectro
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.cosmo import Bank
+    from oracle.spectro import DEFAULT_SETTINGS, GalSpectro
+
+    fm = make_fm(extfiles, tmp_path, ["GCsp"], {"h": 0.01})
+    cp = dict(tt.FIDUCIAL)
+    cp["Omegam"] = tt.FIDUCIAL["Omegam"] * 1.01
+    mine = spectro.ComputeGalSpectro(cp, fiducial_cosmopars=dict(tt.FIDUCIAL), configuration=fm)
+    ob = Bank(toy_bank, tt.FIDUCIAL, tt.COSMO_KEYS)
+    ref = GalSpectro(ob.cosmo(cp), ob.cosmo(dict(tt.FIDUCIAL)), fm.specs, dict(DEFAULT_SETTINGS),
+                     dict(fm.Spectrobiaspars), {})
+    kk, mm = np.meshgrid(np.linspace(0.002, 0.3, 31), np.linspace(0.0, 1.0, 7))
+    for z in (1.0, 1.33):
+        assert np.allclose(mine.kpar(z, kk, mm), ref.kpar(z, kk, mm), rtol=1e-15, atol=0)
+        assert np.allclose(mine.kper(z, kk, mm), ref.kper(z, kk, mm), rtol=1e-15, atol=0)
+        ka, ma = mine.kmu_alc_pac(z, kk, mm)
+        kb, mb = ref.kmu_ap(z, kk, mm)
+        assert np.allclose(ka, kb, rtol=1e-15, atol=0) and np.allclose(ma, mb, rtol=1e-15, atol=1e-300)
+        assert np.allclose(mine.spec_err_z(z, kk, mm), ref.spec_err_z(z, kk, mm), rtol=1e-15, atol=0)
+        assert np.allclose(mine.sigmavNL(z, mm), ref.sigmav(z, mm), rtol=1e-13, atol=0)
+        assert np.isclose(mine.BAO_term(z), ref.bao(z), rtol=1e-15)
+    assert mine.k_units_change(kk) is kk
+
+
 def test_fisher_integral_is_scipy_simpson(extfiles, tmp_path):
     """FisherMatrix.fisher_integral (cosmicfish.py:495-512): Simpson over mu then k, even sample counts included."""
     from scipy.integrate import simpson
