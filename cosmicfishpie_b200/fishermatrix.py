@@ -269,8 +269,18 @@ class FisherMatrix:
         return self.photo_LSS.compute_derivs()
 
     def photo_LSS_fishermatrix_einsum(self, noisy_cls=None, covmat=None, derivs=None, lss_obj=None):
-        """Kept for API compatibility (cosmicfish.py:643-744): the Fisher of the configured job."""
+        """The Fisher matrix of the configured photometric job (cosmicfish.py:544-744).  The device assembles
+        covariance, derivatives and trace in one pass from the job's own stencil, so the arguments are accepted only
+        when they are what `lss_obj.compute_covmat()` / `compute_derivs()` returned; anything else (say, derivatives
+        from another scheme) is refused instead of being silently ignored -- select the scheme with
+        options["stencil"]."""
         obj = lss_obj if lss_obj is not None else self.photo_LSS
+        own = getattr(obj, "__dict__", {})
+        for name, given in (("noisy_cls", noisy_cls), ("covmat", covmat), ("derivs", derivs)):
+            if given is not None and given is not own.get(name):
+                raise NotImplementedError(
+                    f"photo_LSS_fishermatrix: a user-supplied `{name}` is not supported; the Fisher matrix is assembled "
+                    "on the device from the configured job (options['stencil'] selects the derivative scheme)")
         return obj.compute_fisher(self.freeparams)
 
     photo_LSS_fishermatrix = photo_LSS_fishermatrix_einsum
