@@ -470,6 +470,14 @@ class SpectroCov:
             cov = np.zeros_like(cov)
         return cov
 
+    def cov(self, ibin, k, mu):
+        """Covariance of the clustering spectrum in bin ibin (spectro_cov.py:230-252), restated as written: the
+        reference hands the bin INDEX to veff(), which expects a redshift."""
+        zmid = self.global_z_bin_mids[ibin]
+        veffS = self.veff(ibin, k, mu) * self.volume_survey(ibin)
+        pobs = self.pk_obs.observed_Pgg(zmid, k, mu)
+        return (2 * (2 * np.pi) ** 3 / veffS) * pobs**2 * (1 / k) ** 3
+
     def noisy_P_ij(self, z, k, mu, si="g", sj="g"):
         if not (si == "g" and sj == "g"):
             raise NotImplementedError("only the galaxy auto-spectrum is in scope")
