@@ -56,7 +56,7 @@ WORKLOAD = f"euclid_3x2pt_13bins_lmax5000_npar23 + gcsp_4bins_npar15_3PT_lattice
 # instructions per launch).  The Gram update adds 128 flop per 8x8 tile (DMMA).
 F_FULL, F_LIGHT, F_FIXED = 93.35, 30.0, 50.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one spectro_fisher_kernel launch (ncu --set full, profiles/r1e)
-TRAFFIC_BYTES = 2.99e6
+TRAFFIC_BYTES = 3.24e6  # 2.99 MB read + 0.25 MB written
 
 
 def ext_dict(bank):
