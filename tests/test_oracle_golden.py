@@ -258,3 +258,70 @@ def test_spectro_likelihood_oracle_bit_exact(obank):
         assert L.wedge_chi2(th) == g["chi2_wedges"][i]
         assert L.legendre_chi2(pld, L.legendre(th), icov) == g["chi2_legendre"][i]
     # the backend-free known answer of the reference's own test (tests/spectro_like_test.py:60-73): 5/(4 pi^2)
+
+
+# ---------------------------------------------------------------- the workloads bench.py times (round-2 goldens)
+FINE = {"spectro_Pk_k_samples": 8193, "spectro_Pk_mu_samples": 129}
+
+
+def test_spectro_oracle_fine_lattice_bit_exact(obank):
+    """GCsp on the bench lattice (129 x 8193, 15 parameters): golden gcsp_cfg4_fine of the unmodified reference."""
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.spectro import spectro_fisher
+
+    sp = _spectro_specs()
+    bias = dict(sp["sp_bias_parametrization"]["linear_log"])
+    ps = dict(sp["shot_noise_parametrization"]["constant"])
+    fp = {p: 0.01 for p in P7}
+    fp.update({k: 1e-4 for k in list(bias) + list(ps)})
+    r = spectro_fisher(obank, sp, dict(FINE), dict(tt.FIDUCIAL), bias, ps, {}, fp, return_all=True)
+    g = golden("gcsp_cfg4_fine")
+    assert r["param_names"] == list(g["param_names"])
+    assert np.array_equal(r["fisher"], g["fisher"])
+    assert np.array_equal(r["fisher_per_bin"], g["fisher_per_bin"])
+    assert np.array_equal(np.array([x[::8, ::64] for x in r["lnp_fid"]]), g["lnpobs_fid_strided"])
+    assert np.array_equal(np.array([x[::8, ::64] for x in r["veff"]]), g["veff_strided"])
+    for par in ("Omegam", "wa", "lnbg_2", "Ps_4"):
+        d = np.array([(np.asarray(r["derivs"][par][i]) * np.ones((129, 8193)))[::8, ::64] for i in range(4)])
+        assert np.array_equal(d, g["deriv_strided__" + par]), par
+
+
+def test_photo_likelihood_oracle_cfg3_bit_exact(obank):
+    """13+13-bin photometric likelihood (golden like_photo_cfg3): data cells and a third of the stored points."""
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.likelihood import PhotoLikelihood
+    from oracle.photo import default_photo_bias, finish_photo_specs
+
+    sp = finish_photo_specs(yaml.safe_load(open(os.path.join(SPECDIR, "Euclid-Photometric-13bins-lmax5000.yaml")))["specifications"])
+    lum = np.load(os.path.join(REPO, "cosmicfishpie_b200", "data", "lumratio.npy"))
+    bias, ia = default_photo_bias(sp), dict(sp["IA_params"])
+    L = PhotoLikelihood(obank, sp, None, ["WL", "GCph"], dict(tt.FIDUCIAL), dict(sp["photo_z_params"]), ia, bias, lum)
+    g = golden("like_photo_cfg3")
+    for k in ("Cell_LL", "Cell_GG", "Cell_GL"):
+        assert np.array_equal(L.data[k], g[k])
+    keys = [str(k) for k in g["keys"]]
+    for i in list(range(0, 40, 3)):
+        assert L.loglike(dict(zip(keys, g["points"][i]))) == g["loglike"][i], i
+
+
+def test_spectro_likelihood_oracle_fine_bit_exact(obank):
+    """Spectroscopic likelihood on the 129 x 8193 lattice (golden like_spectro_fine): data, multipoles and six points."""
+    from cosmicfishpie_b200 import toy_tables as tt
+    from oracle.likelihood import SpectroLikelihoodOracle
+
+    sp = _spectro_specs()
+    bias = dict(sp["sp_bias_parametrization"]["linear_log"])
+    ps = dict(sp["shot_noise_parametrization"]["constant"])
+    L = SpectroLikelihoodOracle(obank, sp, dict(FINE), dict(tt.FIDUCIAL), bias, ps, {})
+    g = golden("like_spectro_fine")
+    assert np.array_equal(L.data[:, ::8, ::64], g["data_strided"])
+    pld = L.legendre(L.data)
+    cov, icov = L.legendre_cov(pld)
+    assert np.array_equal(pld[::64], g["pl_data_strided"]) and np.array_equal(cov[::64], g["cov_strided"])
+    keys = [str(k) for k in g["keys"]]
+    for i in (0, 3, 9, 14, 18, 21):
+        th = L.theory(dict(zip(keys, g["points"][i])))
+        if i == 9:
+            assert np.array_equal(th[:, ::8, ::64], g["theory_9_strided"])
+        assert L.wedge_chi2(th) == g["chi2_wedges"][i], i
+        assert L.legendre_chi2(pld, L.legendre(th), icov) == g["chi2_legendre"][i], i

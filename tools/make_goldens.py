@@ -419,6 +419,158 @@ def like_spectro():
     print("like_spectro wedges:", dict(zip(names, w)), "legendre:", dict(zip(names, lg)))
 
 
+# ------------------------------------------------------------------ the workloads bench.py times (round 2)
+FINE = {"spectro_Pk_k_samples": 8193, "spectro_Pk_mu_samples": 129}
+FINE_KSTRIDE, FINE_MUSTRIDE = 64, 8
+
+
+@case
+def gcsp_cfg4_fine():
+    """BASELINE cfg4 as bench.py runs it: GCsp, 4 bins, 7 cosmological + 4 lnbg + 4 Ps parameters, 129 x 8193
+    lattice.  Lattices are stored every 64th wavenumber and every 8th mu row."""
+    import cosmicfishpie.fishermatrix.cosmicfish as cff
+
+    ext = tt.extfiles_for(bank_dir())
+    o = base_options("gcsp_cfg4_fine", spectro=True, photo=False, **FINE)
+    t0 = time.time()
+    with quiet():
+        fm = cff.FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={p: 0.01 for p in PARS7}, options=o,
+                              specifications={}, observables=["GCsp"], extfiles=ext, cosmoModel="w0waCDM",
+                              surveyName="Euclid")
+        F = fm.compute()
+    wall = time.time() - t0
+    out = fisher_payload(F, fm)
+    out["wall_s"] = wall
+    out["zmids"] = np.array(fm.zmids)
+    sl = (slice(None, None, FINE_MUSTRIDE), slice(None, None, FINE_KSTRIDE))
+    out["veff_strided"] = np.array([v[sl] for v in fm.veff_arr])
+    lnp = np.array([fm.pk_obs_fid.lnpobs_gg(z, fm.Pk_kmesh, fm.Pk_mumesh)[sl] for z in fm.zmids])
+    out["lnpobs_fid_strided"] = lnp
+    for par in fm.freeparams:
+        out["deriv_strided__" + par] = np.array(
+            [(np.asarray(fm.derivs_dict[par][i]) * np.ones((129, 8193)))[sl] for i in range(len(fm.zmids))])
+    out["fisher_per_bin"] = np.array([fm.fisher_per_bin(i) for i in range(len(fm.zmids))])
+    np.savez_compressed(os.path.join(GOLD, "gcsp_cfg4_fine.npz"), **out)
+    print(f"gcsp_cfg4_fine: npar={len(out['param_names'])} wall={wall:.1f}s F00={out['fisher'][0,0]:.10e}")
+
+
+def _bank_steps(rng, n, pars=PARS7):
+    """n cosmologies of the bank: one parameter each at fiducial*(1 +- 0.01) (wa: +-0.01 absolute)."""
+    rows = []
+    for _ in range(n):
+        p = pars[rng.integers(len(pars))]
+        sgn = 1.0 if rng.integers(2) else -1.0
+        rows.append((p, tt.FIDUCIAL[p] * (1 + 0.01 * sgn) if tt.FIDUCIAL[p] != 0 else 0.01 * sgn))
+    return rows
+
+
+@case
+def like_photo_cfg3():
+    """Photometric likelihood on the bench workload (3x2pt, 13+13 bins, lmax 5000): 40 points -- the fiducial,
+    a group that varies only the galaxy biases, a group that varies biases and IA, and 24 points on cosmologies of the
+    bank with their own nuisance draws.  The parameter matrix is stored with the fixture."""
+    from cosmicfishpie.likelihood.photo_like import PhotometricLikelihood
+
+    fm = run_photo("_tmp_like_photo_cfg3", ["WL", "GCph"], {p: 0.01 for p in PARS7},
+                   options_extra={"specs_dir": MYSPECS}, photo_yaml="Euclid-Photometric-13bins-lmax5000")
+    os.remove(os.path.join(GOLD, "_tmp_like_photo_cfg3.npz"))
+    with quiet():
+        like = PhotometricLikelihood(cosmo_data=fm)
+    allp = dict(fm.allparams)
+    bkeys = [f"b{i}" for i in range(1, 14)]
+    ikeys = ["AIA", "betaIA", "etaIA"]
+    keys = PARS7 + bkeys + ikeys
+    fid = np.array([allp[k] for k in keys])
+    rng = np.random.default_rng(2024)
+    mat = np.tile(fid, (40, 1))
+    nb, ni = len(bkeys), len(ikeys)
+    mat[1:9, 7:7 + nb] *= 1 + 0.02 * rng.standard_normal((8, nb))
+    mat[9:16, 7:7 + nb] *= 1 + 0.02 * rng.standard_normal((7, nb))
+    mat[9:16, 7 + nb:] *= 1 + 0.03 * rng.standard_normal((7, ni))
+    for r, (p, v) in zip(range(16, 40), _bank_steps(rng, 24)):
+        mat[r, keys.index(p)] = v
+        mat[r, 7:7 + nb] *= 1 + 0.02 * rng.standard_normal(nb)
+        if r % 2:
+            mat[r, 7 + nb:] *= 1 + 0.03 * rng.standard_normal(ni)
+    vals = []
+    t0 = time.time()
+    for row in mat:
+        with quiet():
+            vals.append(like.loglike(param_dict=dict(zip(keys, row))))
+    out = {k: np.array(v) for k, v in like.data_obs.items()}
+    out.update(keys=np.array(keys), points=mat, loglike=np.array(vals), wall_per_point_s=(time.time() - t0) / len(mat))
+    np.savez_compressed(os.path.join(GOLD, "like_photo_cfg3.npz"), **out)
+    print("like_photo_cfg3:", vals[:3], "...", out["wall_per_point_s"], "s/point")
+
+
+@case
+def like_spectro_fine():
+    """Spectroscopic likelihood on the bench lattice (129 x 8193): wedges and Legendre multipoles at 22 points --
+    groups of 4-7 points that share a cosmology and differ in lnbg_i / Ps_i (the moment kernels' case), plus single
+    points.  The parameter matrix is stored with the fixture."""
+    import cosmicfishpie.fishermatrix.cosmicfish as cff
+    from cosmicfishpie.likelihood import spectro_like as sl
+
+    ext = tt.extfiles_for(bank_dir())
+    o = base_options("_tmp_like_spectro_fine", spectro=True, photo=False, **FINE)
+    with quiet():
+        # a forecast object without the derivative pass: the likelihood needs the fiducial observable and covariance
+        fm = cff.FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={p: 0.01 for p in PARS7}, options=o,
+                              specifications={}, observables=["GCsp"], extfiles=ext, cosmoModel="w0waCDM",
+                              surveyName="Euclid")
+        # the prelude of FisherMatrix.compute (cosmicfish.py:262-290) without its derivative pass
+        import cosmicfishpie.LSSsurvey.spectro_cov as spec_cov
+        import cosmicfishpie.LSSsurvey.spectro_obs as spec_obs
+        fm.set_pk_settings()
+        fm.obs_spectrum = ["g", "g"]
+        fm.pk_obs_fid = spec_obs.ComputeGalSpectro(cosmopars=fm.fiducialcosmopars, fiducial_cosmopars=fm.fiducialcosmopars,
+                                                   spectrobiaspars=fm.Spectrobiaspars, spectrononlinearpars=fm.Spectrononlinpars,
+                                                   IMbiaspars=fm.IMbiaspars, PShotpars=fm.PShotpars, configuration=fm)
+        fm.pk_cov = spec_cov.SpectroCov(fm.fiducialcosmopars, fiducial_specobs=fm.pk_obs_fid, bias_samples=fm.obs_spectrum,
+                                        configuration=fm)
+        fm.zmids = fm.pk_cov.inter_z_bin_mids
+    fm.pk_cov.volume_survey_array = np.array([fm.pk_cov.volume_survey(i) for i in range(len(fm.zmids))])
+    with quiet():
+        data = sl.observable_Pgg(fm.pk_cov, fm)
+        pl_data = sl.legendre_Pgg(data, fm)
+        cov, icov = sl.compute_covariance_legendre(pl_data, fm)
+    allp = dict(fm.allparams)
+    keys = PARS7 + [f"lnbg_{i}" for i in range(1, 5)] + [f"Ps_{i}" for i in range(1, 5)]
+    fid = np.array([allp[k] for k in keys])
+    rng = np.random.default_rng(77)
+    mat = np.tile(fid, (22, 1))
+
+    def nuis(rows, shot=True):
+        mat[rows, 7:11] += 0.01 * rng.standard_normal((len(rows), 4))
+        if shot:
+            mat[rows, 11:15] = rng.uniform(0.0, 50.0, size=(len(rows), 4))
+
+    nuis(list(range(1, 8)))                       # 7 points on the fiducial cosmology (+ the fiducial itself)
+    mat[8:13, keys.index("h")] = tt.FIDUCIAL["h"] * 1.01
+    nuis(list(range(8, 13)))                      # group of 5
+    mat[13:17, keys.index("Omegam")] = tt.FIDUCIAL["Omegam"] * 0.99
+    nuis(list(range(13, 17)), shot=False)         # group of 4, biases only
+    for r, (p, v) in zip(range(17, 22), [("w0", -1.01), ("wa", 0.01), ("sigma8", tt.FIDUCIAL["sigma8"] * 1.01),
+                                         ("ns", tt.FIDUCIAL["ns"] * 0.99), ("Omegab", tt.FIDUCIAL["Omegab"] * 1.01)]):
+        mat[r, keys.index(p)] = v                 # single points
+    nuis([17, 19, 21])
+    w, lg = [], []
+    t0 = time.time()
+    sl2 = (slice(None), slice(None, None, FINE_MUSTRIDE), slice(None, None, FINE_KSTRIDE))
+    out = {"data_strided": data[sl2], "pl_data_strided": pl_data[::FINE_KSTRIDE], "cov_strided": cov[::FINE_KSTRIDE]}
+    for i, row in enumerate(mat):
+        with quiet():
+            th = sl.compute_theory_spectro(dict(zip(keys, row)), fm, "wedges")
+            w.append(sl.compute_wedge_chi2(data, th, fm))
+            lg.append(sl.compute_chi2_legendre(pl_data, sl.legendre_Pgg(th, fm), icov))
+        if i == 9:
+            out["theory_9_strided"] = th[sl2]
+    out.update(keys=np.array(keys), points=mat, chi2_wedges=np.array(w), chi2_legendre=np.array(lg),
+               wall_per_point_s=(time.time() - t0) / len(mat))
+    np.savez_compressed(os.path.join(GOLD, "like_spectro_fine.npz"), **out)
+    print("like_spectro_fine wedges:", w[:4], "legendre:", lg[:4], out["wall_per_point_s"], "s/point")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     os.makedirs(SCRATCH, exist_ok=True)
