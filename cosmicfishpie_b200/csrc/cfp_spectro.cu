@@ -83,6 +83,19 @@ struct RowC {
   double pad;
 };
 
+// Plan of the pair kernel (spectro_fisher_pairs_kernel) for one bin, built by spectro_setup_block: which stencil
+// point every lane group evaluates.  q = sign * 8 + slot; slots 0..6: parameters whose two stencil points need a full
+// evaluation each (weights +1 / -1); slot 7: the bin's bias-only pair (or the fiducial twice).
+struct PairPlan {
+  int ok;        // the pair kernel applies to this bin (otherwise spectro_fisher_kernel runs it)
+  int ps_sel;    // P_obs the shot-noise derivative divides by: 0 fiducial, 1 / 2 the + / - point of slot 7
+  int pt[16];    // stencil point of q
+  int par[9];    // parameter of slot 0..7; [8]: the bin's shot-noise parameter; -1: none
+  int pad;
+  double coef[8];  // 1 / stencil denominator of the slot's parameter (0: unused slot)
+  double bias0;    // galaxy bias of the fiducial
+};
+
 struct SpectroParams {
   int S, Z, Nmu, Nk, npar, nb, nnw, NC;
   unsigned flags;
@@ -115,6 +128,7 @@ struct SpectroParams {
                           //         5: the fiducial is plain as far as its evaluation goes
   double* partial;        // [Z][gridDim.x][T*64]
   double *lnp, *derivs, *veff;
+  PairPlan* pairs;        // [Z]
 };
 
 // ------------------------------------------------------------------ prepare
@@ -364,6 +378,70 @@ __device__ void spectro_setup_block(const SpectroParams& P, int zb) {
     P.nwork[zb * 8 + 1] = cnt[2];
     P.nwork[zb * 8 + 2] = cnt[3];
     P.nwork[zb * 8 + 3] = cnt[0];
+    // Can the pair kernel take this bin?  A 3PT forecast of plain points: at most 7 parameters with a fully evaluated
+    // +/- pair, one bias-only +/- pair, nothing else but the point the shot-noise derivatives read.
+    const SDev* sd = P.sdev + (size_t)zb * P.S;
+    PairPlan pp;
+    bool ok = P.materialize == 0 && P.nwork[zb * 8 + 5] != 0 && P.npar <= MAX_NB * 8;
+    pp.ps_sel = 0;
+    pp.pad = 0;
+    pp.bias0 = sd[0].bias;
+    int have[16];
+    for (int q = 0; q < 16; ++q) pp.pt[q] = 0, have[q] = 0;
+    for (int a = 0; a < 9; ++a) pp.par[a] = -1;
+    for (int a = 0; a < 8; ++a) pp.coef[a] = 0.0;
+    int nslot = 0;
+    for (int s = 1; s < P.S && ok; ++s) {
+      const int c = cls_sm[s];
+      if (c < 0) continue;
+      const SDev& o = sd[s];
+      if (c == 3) {  // an alias of the fiducial: only as the point the shot-noise derivatives read
+        if (!(s == P.ps_src && o.par0 < 0)) ok = false;
+        continue;
+      }
+      if (c == 1 || !(o.flags & SD_PLAIN) || o.par0 < 0 || o.csr0 != o.csr1 || (o.w0 != 1.0 && o.w0 != -1.0)) {
+        ok = false;
+        break;
+      }
+      int slot = -1;
+      if (c == 2) {
+        slot = 7;
+        if (pp.par[7] >= 0 && pp.par[7] != o.par0) ok = false;
+      } else {
+        for (int a = 0; a < nslot; ++a)
+          if (pp.par[a] == o.par0) slot = a;
+        if (slot < 0) {
+          if (nslot == 7) {
+            ok = false;
+            break;
+          }
+          slot = nslot++;
+        }
+      }
+      const int q = (o.w0 == 1.0 ? 0 : 8) + slot;
+      if (have[q]) ok = false;
+      have[q] = 1;
+      pp.pt[q] = s;
+      pp.par[slot] = o.par0;
+      pp.coef[slot] = P.st_rden[o.par0];
+      if (s == P.ps_src) {
+        if (c == 2)
+          pp.ps_sel = (o.w0 == 1.0) ? 1 : 2;
+        else
+          ok = false;
+      }
+    }
+    for (int a = 0; a < 8; ++a)
+      if (have[a] != have[8 + a]) ok = false;
+    for (int par = 0; par < P.npar; ++par)
+      if (P.ps_bin[par] == zb) {
+        if (pp.par[8] >= 0) ok = false;
+        pp.par[8] = par;
+      }
+    pp.ok = ok ? 1 : 0;
+    P.pairs[zb] = pp;
+  } else if (threadIdx.x == 0) {
+    P.pairs[zb].ok = 0;
   }
 }
 
@@ -663,6 +741,7 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
   MathTab& mt = *reinterpret_cast<MathTab*>(sm_w + TILE);  // (at a compile-time offset: no address arithmetic in the loops)
   SDev* sm_s = reinterpret_cast<SDev*>(&mt + 1);       // [S], in work-list order
   RowC* const sm_r0 = reinterpret_cast<RowC*>(sm_s + P.S);  // [ROWS][S], likewise
+  if (P.pairs[blockIdx.y].ok) return;  // (uniform) spectro_fisher_pairs_kernel takes this bin
   math_tables_fill(mt, threadIdx.x, TILE);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int zb = blockIdx.y;
@@ -854,9 +933,11 @@ __global__ void __launch_bounds__(TILE, MINB) spectro_fisher_kernel(SpectroParam
 // warp sums are added in warp order.  grid (Z, T*64/32), 1024 threads: lane = element, warp = CTA subset, so the
 // ~150 partials of an element are fetched by 32 independent loads at a time instead of one dependent chain.
 __global__ void __launch_bounds__(1024) spectro_reduce_kernel(const double* __restrict__ partial, int ncta, int nb,
-                                                              int npar, double* __restrict__ F) {
+                                                              int npar, const PairPlan* __restrict__ pairs,
+                                                              double* __restrict__ F) {
   __shared__ double red[32][33];
   const int zb = blockIdx.x;
+  if (pairs[zb].ok) return;  // spectro_reduce_pairs_kernel writes this bin
   const int T = nb * (nb + 1) / 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.y * 32 + lane;  // < T*64 (a multiple of 32)
@@ -884,6 +965,244 @@ __global__ void __launch_bounds__(1024) spectro_reduce_kernel(const double* __re
   }
 }
 
+
+// ---------------------------------------------------------------------------- pair kernel
+// spectro_fisher_pairs_kernel: the Fisher lattice pass of a plain 3PT forecast (PairPlan.ok), organised around the
+// fragment layout of the FP64 tensor-core MMA instead of around a shared-memory derivative tile.
+//
+//   lane = (slot = lane >> 2, cell = lane & 3).  A warp owns four neighbouring wavenumbers and walks DOWN their mu
+//   column.  Lane (slot, cell) evaluates the +/- stencil pair of parameter `slot` at its cell and forms
+//   d_slot = (ln P+ - ln P-) / (2h) from ONE division and an atanh series (ln(X+/X-) = 2 atanh((X+ - X-)/(X+ + X-)),
+//   |t| ~ 1e-2: five terms are exact to rounding) -- no logarithm, no exponent extraction.  That value IS the lane's
+//   element of the A fragment (8 parameters x 4 cells) of mma.m8n8k4.f64, and times the cell weight its element of
+//   the B fragment: the Gram update F_ij += w d_i d_j needs no transposition through shared memory and no barrier.
+//   Slot 7 carries the bin's bias-only pair, which shares every table look-up with the fiducial; its lanes also
+//   derive P_obs of the fiducial (effective volume, quadrature weight) and the shot-noise derivative 1 / P_obs, and
+//   hand them to the other lanes of their cell by shuffles.
+//   Along a mu column k' = k G(mu) drifts by a fraction of a table piece, so the piece records (P_lin and f cubics,
+//   no-wiggle line) of both stencil points live in REGISTERS and are re-fetched only when k' leaves the piece:
+//   the steady state issues no global load at all.  The row constants of the 16 (sign, slot) points for every mu row
+//   of the slice are staged once per CTA in shared memory ([row][q], 48-byte records: conflict-free 128-bit loads).
+// Work: tasks = (segment of rows) x (group of 4 wavenumbers), dealt round-robin to the warps of the grid in a fixed
+// order (deterministic partial sums); partial[zb][cta][3 tiles][64].
+constexpr int PK_WARPS = 8;
+constexpr int PK_THREADS = PK_WARPS * 32;
+constexpr int PK_MAXROWS = 136;  // mu rows staged at once (16 x 48 B each)
+
+struct PRec {  // piece records of one stencil point at the lane's k': a_i are pre-multiplied by bao / sigma8^2
+  double loA, hiA, a0, a1, a2, a3, f0, f1, f2, f3;
+  double loN, hiN, c0, sl;  // no-wiggle line c0 + sl k' (pre-multiplied likewise); +-inf bounds at the table ends
+};
+
+__device__ __forceinline__ void pair_fetch_cubic(PRec& r, const SDev& sp, double kap, int& h) {
+  double lo;
+  h = locate<CUBIC_BLK>(sp.blkA, sp.nA, kap, h, lo);
+  const double2* ra = reinterpret_cast<const double2*>(sp.blkA + (size_t)h * CUBIC_BLK);
+  const double2* rb = reinterpret_cast<const double2*>(sp.blkB + (size_t)h * CUBIC_BLK);
+  const double2 b = __ldg(ra), a01 = __ldg(ra + 1), a23 = __ldg(ra + 2), f01 = __ldg(rb + 1), f23 = __ldg(rb + 2);
+  r.loA = b.x, r.hiA = b.y;
+  r.a0 = a01.x * sp.baos, r.a1 = a01.y * sp.baos, r.a2 = a23.x * sp.baos, r.a3 = a23.y * sp.baos;
+  r.f0 = f01.x, r.f1 = f01.y, r.f2 = f23.x, r.f3 = f23.y;
+}
+
+__device__ __forceinline__ void pair_fetch_line(PRec& r, const SDev& sp, double kap, int& h) {
+  double lo;
+  h = locate<LIN_BLK>(sp.blkN, sp.nN, kap, h, lo);
+  const double2* rn = reinterpret_cast<const double2*>(sp.blkN + (size_t)h * LIN_BLK);
+  const double2 b = __ldg(rn), ys = __ldg(rn + 1);
+  // degree-1 spline with extrapolation: the end pieces extend to infinity
+  r.loN = (h == 0) ? -CUDART_INF : b.x;
+  r.hiN = (h == sp.nN - 1) ? CUDART_INF : b.y;
+  r.sl = ys.y * sp.baos;
+  r.c0 = fma(-ys.y, b.x, ys.x) * sp.baos;  // y + slope (k' - lo) = (y - slope lo) + slope k'
+}
+
+// numerator N = (b + f mu'^2)^2 * dewiggled P * bao/s8^2 and FoG denominator of X = N / den; err2 as in eval_x
+__device__ __forceinline__ void pair_eval(const MathTab& mt, const PRec& r, const RowC& rc, double k, double kap,
+                                          double bias, double& N, double& den, double& err2, double& F, double& dw) {
+  const double err = k * rc.errc;
+  err2 = err * err;
+  const double u = kap - r.loA;
+  const double pdd = fma(u, fma(u, fma(u, r.a3, r.a2), r.a1), r.a0);
+  F = fma(u, fma(u, fma(u, r.f3, r.f2), r.f1), r.f0) * rc.fmu2;
+  const double pnw = fma(r.sl, kap, r.c0);
+  const double e = tab_exp_neg(mt, -rc.sv2 * (kap * kap));
+  dw = fma(e, pdd - pnw, pnw);
+  const double t = kap * rc.fogc;
+  den = fma(t, t, 1.0);
+  const double kaiser = bias + F;
+  N = (kaiser * kaiser) * dw;
+}
+
+__constant__ double CFP_ATANH[5] = {1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0};
+
+__global__ void __launch_bounds__(PK_THREADS, 2)
+    spectro_fisher_pairs_kernel(SpectroParams P, int row_lo, int nrows, int srows, int nseg, double* __restrict__ partial) {
+  const int zb = blockIdx.y;
+  if (!P.pairs[zb].ok) return;  // (uniform: the general kernel takes this bin)
+  extern __shared__ __align__(16) double smem[];
+  RowC* const sm_rows = reinterpret_cast<RowC*>(smem);                   // [srows][16]
+  MathTab& mt = *reinterpret_cast<MathTab*>(sm_rows + (size_t)srows * 16);
+  SDev* const sm_pt = reinterpret_cast<SDev*>(&mt + 1);                   // [16]
+  PairPlan& plan = *reinterpret_cast<PairPlan*>(sm_pt + 16);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = lane >> 2, cell = lane & 3;
+  if (tid < (int)(sizeof(PairPlan) / sizeof(int))) reinterpret_cast<int*>(&plan)[tid] = reinterpret_cast<const int*>(P.pairs + zb)[tid];
+  math_tables_fill(mt, tid, PK_THREADS);
+  __syncthreads();
+  {
+    constexpr int W = (int)(sizeof(SDev) / sizeof(double));
+    const double* src = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S);
+    double* dst = reinterpret_cast<double*>(sm_pt);
+    for (int i = tid; i < 16 * W; i += PK_THREADS) {
+      const int q = i / W;
+      dst[i] = src[(size_t)plan.pt[q] * W + (i - q * W)];
+    }
+  }
+  __syncthreads();
+  const SDev& spA = sm_pt[slot];
+  const SDev& spB = sm_pt[8 + slot];
+  const double biasA = spA.bias, biasB = spB.bias;
+  const double coef = plan.coef[slot];
+  const double bias0 = plan.bias0;
+  const int ps_sel = plan.ps_sel;
+  const bool has_ps = plan.par[8] >= 0;
+  const double nbar = P.nbar[zb], vol2 = 2.0 * P.vol[zb];
+  const int nquad = (P.Nk + 3) >> 2;
+  double acc[3][2];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) acc[t][0] = acc[t][1] = 0.0;
+
+  for (int r_base = 0; r_base < nrows; r_base += srows) {
+    const int nr = min(srows, nrows - r_base);
+    __syncthreads();
+    for (int i = tid; i < nr * 16; i += PK_THREADS) {
+      const int rr = i >> 4, q = i & 15;
+      const int row = row_lo + r_base + rr;
+      RowC rc = row_consts(sm_pt[q], P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
+      if (q == 7) rc.pad = __ldg(P.wmu + row);
+      sm_rows[i] = rc;
+    }
+    __syncthreads();
+    const int segs = (nr == nrows) ? nseg : 1;  // (a slice staged in several pieces is not cut further)
+    const int seglen = (nr + segs - 1) / segs;
+    const int ntask = nquad * segs;
+    for (int task = blockIdx.x * PK_WARPS + warp; task < ntask; task += gridDim.x * PK_WARPS) {
+      const int seg = task / nquad, quad = task - seg * nquad;
+      const int r0 = seg * seglen, r1 = min(nr, r0 + seglen);
+      int ki = quad * 4 + cell;
+      const bool col_ok = ki < P.Nk;
+      ki = col_ok ? ki : P.Nk - 1;
+      const double k = __ldg(P.k + ki);
+      const double wcol = (k * k) * __ldg(P.wk + ki);
+      PRec A, B;
+      A.loA = A.loN = B.loA = B.loN = CUDART_INF;  // nothing fetched yet
+      A.hiA = A.hiN = B.hiA = B.hiN = -CUDART_INF;
+      A.a0 = A.a1 = A.a2 = A.a3 = A.f0 = A.f1 = A.f2 = A.f3 = A.c0 = A.sl = 0.0;
+      B.a0 = B.a1 = B.a2 = B.a3 = B.f0 = B.f1 = B.f2 = B.f3 = B.c0 = B.sl = 0.0;
+      int hAa = -1, hAn = -1, hBa = -1, hBn = -1;
+      const RowC* rcp = sm_rows + (size_t)r0 * 16 + slot;
+      int64_t cellidx = (int64_t)(row_lo + r_base + r0) * P.Nk + ki;
+      for (int r = r0; r < r1; ++r, rcp += 16, cellidx += P.Nk) {
+        const RowC& rcA = rcp[0];
+        const RowC& rcB = rcp[8];
+        const double kapA = k * rcA.G, kapB = k * rcB.G;
+        if (!(kapA >= A.loA && kapA < A.hiA)) pair_fetch_cubic(A, spA, kapA, hAa);
+        if (!(kapA >= A.loN && kapA < A.hiN)) pair_fetch_line(A, spA, kapA, hAn);
+        if (!(kapB >= B.loA && kapB < B.hiA)) pair_fetch_cubic(B, spB, kapB, hBa);
+        if (!(kapB >= B.loN && kapB < B.hiN)) pair_fetch_line(B, spB, kapB, hBn);
+        double NA, denA, e2A, FA, dwA, NB, denB, e2B, FB, dwB;
+        pair_eval(mt, A, rcA, k, kapA, biasA, NA, denA, e2A, FA, dwA);
+        pair_eval(mt, B, rcB, k, kapB, biasB, NB, denB, e2B, FB, dwB);
+        // d = (ln P+ - ln P-) / (2h),  ln P = ln(N / den) - err2
+        const double num = NA * denB, dnm = NB * denA;
+        const double t = fast_div(num - dnm, num + dnm);
+        const double t2 = t * t;
+        double p = fma(CFP_ATANH[0], t2, CFP_ATANH[1]);
+        p = fma(p, t2, CFP_ATANH[2]);
+        p = fma(p, t2, CFP_ATANH[3]);
+        p = fma(p, t2, CFP_ATANH[4]);
+        double lnr = fma(p * t2, t + t, t + t);
+        if (!(fabs(t) < 0.03)) {  // a step too large for the series (or a spectrum that is not positive: NaN below)
+          lnr = (num > 0.0 && dnm > 0.0) ? tab_log(mt, num) - tab_log(mt, dnm) : CUDART_NAN;
+        }
+        // a spectrum that is not positive has no logarithm: NaN, as numpy gives the reference (spectro_obs.py:913-933)
+        double d = (num > 0.0 && dnm > 0.0) ? (lnr - (e2A - e2B)) * coef : CUDART_NAN;
+        double w = 0.0, dps = 0.0;
+        if (slot == 7) {
+          // fiducial spectrum from the pair's shared look-ups: effective volume, quadrature weight, 1 / P_obs
+          const double rden = fast_rcp(denA);
+          const double kaiser0 = bias0 + FA;
+          const double N0 = (kaiser0 * kaiser0) * dwA;
+          const double e = tab_exp_neg(mt, -e2A) * rden;
+          const double P0 = N0 * e;
+          if (has_ps) dps = fast_rcp(ps_sel == 0 ? P0 : (ps_sel == 1 ? NA : NB) * e);  // spectro_cov.py:510-532
+          const double npobs = nbar * P0;
+          const double rr = fast_div(npobs, 1.0 + npobs);
+          const double veff = INV_8PI2 * rr * rr;  // spectro_cov.py:223-225
+          const bool valid = col_ok && cellidx >= P.cell_begin && cellidx < P.cell_end;
+          // cosmicfish.py:541: k^2 * 2 * V_survey * veff, times the Simpson weights of :510-511
+          w = valid ? (vol2 * veff) * (rcA.pad * wcol) : 0.0;
+        }
+        w = __shfl_sync(0xffffffffu, w, 28 + cell);
+        dps = __shfl_sync(0xffffffffu, dps, 28 + cell);
+        const double a1 = (slot == 0) ? dps : 0.0;
+        const double b0 = w * d, b1 = w * a1;
+        dmma884(acc[0][0], acc[0][1], d, b0);
+        dmma884(acc[1][0], acc[1][1], a1, b0);
+        dmma884(acc[2][0], acc[2][1], a1, b1);
+      }
+    }
+  }
+  // cross-warp reduction in fixed order, then one partial per CTA
+  __syncthreads();
+  double* red = smem;  // [PK_WARPS][3][64]
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    red[(warp * 3 + t) * 64 + lane * 2 + 0] = acc[t][0];
+    red[(warp * 3 + t) * 64 + lane * 2 + 1] = acc[t][1];
+  }
+  __syncthreads();
+  double* out = partial + ((size_t)zb * gridDim.x + blockIdx.x) * 192;
+  for (int e = tid; e < 192; e += PK_THREADS) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int w = 0; w < PK_WARPS; ++w) sacc += red[w * 192 + e];
+    out[e] = sacc;
+  }
+}
+
+// F[zb] of the bins the pair kernel took: internal order (slots 0..7, shot noise) -> parameters, zeros elsewhere.
+// One CTA per bin, one thread per element of the lower triangle; the CTA partials are summed in a fixed order.
+__global__ void __launch_bounds__(256) spectro_reduce_pairs_kernel(const double* __restrict__ partial, int ncta,
+                                                                   int npar, const PairPlan* __restrict__ pairs,
+                                                                   double* __restrict__ F) {
+  const int zb = blockIdx.x;
+  const PairPlan& plan = pairs[zb];
+  if (!plan.ok) return;
+  __shared__ int inv[MAX_NB * 8];
+  for (int p = threadIdx.x; p < npar; p += blockDim.x) {
+    int a = -1;
+    for (int q = 0; q < 9; ++q)
+      if (plan.par[q] == p) a = q;
+    inv[p] = a;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < npar * npar; e += blockDim.x) {
+    const int i = e / npar, j = e - i * npar;
+    if (j > i) continue;
+    const int ai = inv[i], aj = inv[j];
+    double s = 0.0;
+    if (ai >= 0 && aj >= 0) {
+      const int hi = max(ai, aj), lo = min(ai, aj);
+      const int t = hi < 8 ? 0 : (lo < 8 ? 1 : 2);
+      const int el = t * 64 + ((hi & 7) * 4 + ((lo & 7) >> 1)) * 2 + (lo & 1);
+      for (int c = 0; c < ncta; ++c) s += partial[((size_t)zb * ncta + c) * 192 + el];
+    }
+    F[((size_t)zb * npar + i) * npar + j] = s;
+    F[((size_t)zb * npar + j) * npar + i] = s;
+  }
+}
 
 // ---------------------------------------------------------------------------- likelihood (wedges)
 // Grid-stride walk over the lattice that keeps (mu index, k index) incrementally -- no 64-bit division per
@@ -1425,6 +1744,11 @@ struct cfp_spectro_plan {
   int *work_d = nullptr, *nwork_d = nullptr, *shared_d = nullptr;
   double *partial_d = nullptr, *fisher_d = nullptr;
   double *lnp_d = nullptr, *derivs_d = nullptr, *veff_d = nullptr;
+  PairPlan* pairs_d = nullptr;     // [Z] plan of the pair kernel per bin (written by the setup block of every run)
+  double* partial2_d = nullptr;    // [Z][grid2_x][192] partials of the pair kernel
+  int grid2_x = 0;
+  int pair_state = 0;              // bins the pair kernel takes when nothing is materialised: 0 unknown, 1 all, 2 none, 3 some
+  int last_mat = -1;
   bool ran = false;
   cudaStream_t last_st = nullptr;  // stream of the most recent run (the pool releases on the context stream)
   std::vector<double> scal_h;      // host copy of the scalar blocks (the likelihood groups points by them)
@@ -1445,6 +1769,7 @@ static void spectro_free(cfp_spectro_plan* p) {
   cfp_dev_free(p->ctx, p->derivs_d);
   cfp_dev_free(p->ctx, p->veff_d);
   cfp_dev_free(p->ctx, p->partial_d);
+  cfp_dev_free(p->ctx, p->partial2_d);
   delete p;
 }
 
@@ -1569,6 +1894,7 @@ extern "C" int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S
   SP_UP(int, nullptr, (size_t)NC * Z, pl->shared_d);
   SP_UP(double, nullptr, (size_t)NC * Z * 2 * maxncy, pl->dcoef_d);
   SP_UP(double, nullptr, (size_t)Z * npar * npar, pl->fisher_d);
+  SP_UP(PairPlan, nullptr, (size_t)Z, pl->pairs_d);
   // the uploads read caller-owned host memory asynchronously: finish them before returning
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
     cfp_set_error("cfp_spectro_plan_create: upload failed");
@@ -1625,6 +1951,7 @@ static void spectro_fill_params(cfp_spectro_plan* pl, int materialize, SpectroPa
   P.shared_tmp = pl->shared_d;
   P.partial = pl->partial_d;
   P.lnp = pl->lnp_d, P.derivs = pl->derivs_d, P.veff = pl->veff_d;
+  P.pairs = pl->pairs_d;
 }
 
 static int spectro_prepare(cfp_spectro_plan* pl, const SpectroParams& P, cudaStream_t st) {
@@ -1974,10 +2301,15 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
   const int nrows = std::max(1, (int)((pl->cell_end + pl->Nk - 1) / pl->Nk) - row_lo);
   const int64_t ntile = (int64_t)((pl->Nk + TILE - 1) / TILE) * nrows;
   const int T = pl->nb * (pl->nb + 1) / 2;
+  // which kernel: the pair kernel takes the bins of a plain 3PT forecast (decided on the device by the setup block
+  // of each run; the host learns the answer at the first fetch and then skips the launches that would do nothing)
+  static const bool no_pairs = std::getenv("CFP_NO_PAIRS") != nullptr;
+  const bool try_pairs = materialize == 0 && !no_pairs && pl->pair_state != 2;
+  const bool run_general = !(try_pairs && pl->pair_state == 1);
   // persistent grid: one wave of (resident CTAs per SM) x (SM count) CTAs, never more CTAs than tiles
   const int minb = fisher_min_blocks(pl->nb);
   int gx = (int)std::min<int64_t>(ntile, std::max(1, (ctx->sm_count * minb + pl->Z - 1) / pl->Z));
-  if (gx != pl->grid_x) {
+  if (run_general && gx != pl->grid_x) {
     if (pl->partial_d && pl->last_st && pl->last_st != ctx->stream) CFP_CUDA(cudaStreamSynchronize(pl->last_st));
     cfp_dev_free(ctx, pl->partial_d);
     pl->partial_d = nullptr;
@@ -1985,16 +2317,27 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
     pl->grid_x = gx;
     allocated = true;
   }
+  const int nquad = (pl->Nk + 3) / 4;
+  const int gx2 = std::max(1, std::min((nquad + PK_WARPS - 1) / PK_WARPS, (ctx->sm_count * 2) / pl->Z));
+  if (try_pairs && gx2 != pl->grid2_x) {
+    if (pl->partial2_d && pl->last_st && pl->last_st != ctx->stream) CFP_CUDA(cudaStreamSynchronize(pl->last_st));
+    cfp_dev_free(ctx, pl->partial2_d);
+    pl->partial2_d = nullptr;
+    CFP_CUDA(cfp_dev_alloc(ctx, (void**)&pl->partial2_d, (size_t)pl->Z * gx2 * 192 * sizeof(double)));
+    pl->grid2_x = gx2;
+    allocated = true;
+  }
   // pool allocations are ordered on the context stream; a caller's stream must not start before them
   if (allocated && st != ctx->stream) CFP_CUDA(cudaStreamSynchronize(ctx->stream));
   pl->last_st = st;
+  pl->last_mat = materialize;
   if (!pl->run0) {
     CFP_CUDA(cudaEventCreate(&pl->run0));
     CFP_CUDA(cudaEventCreate(&pl->run1));
   }
   CFP_CUDA(cudaEventRecord(pl->run0, st));
   SpectroParams P;
-  spectro_fill_params(pl, materialize, P);
+  spectro_fill_params(pl, try_pairs ? 0 : (materialize | (no_pairs || pl->pair_state == 2 ? 32 : 0)), P);
   {
     int rc = spectro_prepare(pl, P, st);
     if (rc != CFP_OK) return rc;
@@ -2004,32 +2347,64 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
     CFP_CUDA(cudaEventCreate(&pl->kev1));
   }
   CFP_CUDA(cudaEventRecord(pl->kev0, st));
-  const dim3 grid(gx, pl->Z);
-  const size_t smem = fisher_smem(pl->nb, pl->S);
   cudaError_t e = cudaSuccess;
+  if (try_pairs) {
+    // rows staged at once, and how finely the rows are cut into tasks: enough tasks for an even deal to the warps
+    const int srows = std::min(nrows, PK_MAXROWS);
+    const int nwarps = gx2 * PK_WARPS;
+    int nseg = 1;
+    double best = 0.0;
+    for (int c = 1; c <= 4 && c <= nrows; ++c) {
+      const int64_t tasks = (int64_t)nquad * c;
+      const double eff = (double)tasks / (double)(((tasks + nwarps - 1) / nwarps) * nwarps);
+      if (eff > best + 0.02) best = eff, nseg = c;
+    }
+    const size_t smem2 = std::max((size_t)srows * 16 * sizeof(RowC), (size_t)PK_WARPS * 192 * sizeof(double)) + sizeof(MathTab) +
+                         16 * sizeof(SDev) + sizeof(PairPlan);
+    e = cudaFuncSetAttribute(spectro_fisher_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e == cudaSuccess) {
+      spectro_fisher_pairs_kernel<<<dim3(gx2, pl->Z), PK_THREADS, smem2, st>>>(P, row_lo, nrows, srows, nseg, pl->partial2_d);
+      ctx->launches++;
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+      cfp_set_error("spectro_fisher_pairs_kernel launch: %s", cudaGetErrorString(e));
+      return CFP_ERR_CUDA;
+    }
+  }
+  if (run_general) {
+    const dim3 grid(gx, pl->Z);
+    const size_t smem = fisher_smem(pl->nb, pl->S);
 #define CFP_LAUNCH_NB(NBV)                                   \
   case NBV:                                                  \
     e = launch_fisher<NBV>(P, grid, smem, row_lo, nrows, st); \
     break;
-  switch (pl->nb) {
-    CFP_LAUNCH_NB(1)
-    CFP_LAUNCH_NB(2)
-    CFP_LAUNCH_NB(3)
-    CFP_LAUNCH_NB(4)
-    CFP_LAUNCH_NB(5)
-    default:
-      e = launch_fisher<6>(P, grid, smem, row_lo, nrows, st);
-      break;
-  }
+    switch (pl->nb) {
+      CFP_LAUNCH_NB(1)
+      CFP_LAUNCH_NB(2)
+      CFP_LAUNCH_NB(3)
+      CFP_LAUNCH_NB(4)
+      CFP_LAUNCH_NB(5)
+      default:
+        e = launch_fisher<6>(P, grid, smem, row_lo, nrows, st);
+        break;
+    }
 #undef CFP_LAUNCH_NB
-  ctx->launches++;
-  if (e != cudaSuccess) {
-    cfp_set_error("spectro_fisher_kernel launch: %s", cudaGetErrorString(e));
-    return CFP_ERR_CUDA;
+    ctx->launches++;
+    if (e != cudaSuccess) {
+      cfp_set_error("spectro_fisher_kernel launch: %s", cudaGetErrorString(e));
+      return CFP_ERR_CUDA;
+    }
   }
   CFP_CUDA(cudaEventRecord(pl->kev1, st));
-  spectro_reduce_kernel<<<dim3(pl->Z, T * 2), 1024, 0, st>>>(pl->partial_d, gx, pl->nb, pl->npar, pl->fisher_d);
-  ctx->launches++;
+  if (run_general) {
+    spectro_reduce_kernel<<<dim3(pl->Z, T * 2), 1024, 0, st>>>(pl->partial_d, gx, pl->nb, pl->npar, pl->pairs_d, pl->fisher_d);
+    ctx->launches++;
+  }
+  if (try_pairs) {
+    spectro_reduce_pairs_kernel<<<pl->Z, 256, 0, st>>>(pl->partial2_d, gx2, pl->npar, pl->pairs_d, pl->fisher_d);
+    ctx->launches++;
+  }
   CFP_CUDA(cudaGetLastError());
   CFP_CUDA(cudaEventRecord(pl->run1, st));
   pl->ran = true;
@@ -2061,6 +2436,14 @@ extern "C" int cfp_spectro_plan_fetch(cfp_spectro_plan* pl, double* fisher_h, do
   CFP_CUDA(cudaEventSynchronize(pl->run1));
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, pl->run0, pl->run1) == cudaSuccess) ctx->last_ms = ms;
+  if (pl->last_mat == 0 && pl->pair_state == 0) {
+    // which bins the pair kernel took (the setup block decided): later runs skip the launch that would do nothing
+    std::vector<PairPlan> pp(pl->Z);
+    CFP_CUDA(cudaMemcpy(pp.data(), pl->pairs_d, (size_t)pl->Z * sizeof(PairPlan), cudaMemcpyDeviceToHost));
+    int n_ok = 0;
+    for (const PairPlan& q : pp) n_ok += q.ok ? 1 : 0;
+    pl->pair_state = n_ok == pl->Z ? 1 : (n_ok == 0 ? 2 : 3);
+  }
   const size_t lattice = (size_t)pl->Nmu * pl->Nk;
   if (fisher_h)
     CFP_CUDA(cudaMemcpy(fisher_h, pl->fisher_d, (size_t)pl->Z * pl->npar * pl->npar * sizeof(double), cudaMemcpyDeviceToHost));
