@@ -967,31 +967,43 @@ __global__ void __launch_bounds__(1024) spectro_reduce_kernel(const double* __re
 
 
 // ---------------------------------------------------------------------------- pair kernel
-// spectro_fisher_pairs_kernel: the Fisher lattice pass of a plain 3PT forecast (PairPlan.ok), organised around the
-// fragment layout of the FP64 tensor-core MMA instead of around a shared-memory derivative tile.
+// The Fisher lattice pass of a plain 3PT forecast (PairPlan.ok), organised around the fragment layout of the FP64
+// tensor-core MMA instead of around a shared-memory derivative tile.  Two kernels:
 //
+// spectro_weights_kernel (pre-pass, thread = cell walking down a mu column): the fiducial spectrum of every cell ->
+//   effective volume x quadrature weight w, and the shot-noise derivative 1 / P_obs; {w, dps} pairs to HBM
+//   (16 B per cell, read back once by the pair kernel while still L2-resident).
+//
+// spectro_fisher_pairs_kernel:
 //   lane = (slot = lane >> 2, cell = lane & 3).  A warp owns four neighbouring wavenumbers and walks DOWN their mu
 //   column.  Lane (slot, cell) evaluates the +/- stencil pair of parameter `slot` at its cell and forms
 //   d_slot = (ln P+ - ln P-) / (2h) from ONE division and an atanh series (ln(X+/X-) = 2 atanh((X+ - X-)/(X+ + X-)),
 //   |t| ~ 1e-2: five terms are exact to rounding) -- no logarithm, no exponent extraction.  That value IS the lane's
 //   element of the A fragment (8 parameters x 4 cells) of mma.m8n8k4.f64, and times the cell weight its element of
 //   the B fragment: the Gram update F_ij += w d_i d_j needs no transposition through shared memory and no barrier.
-//   Slot 7 carries the bin's bias-only pair, which shares every table look-up with the fiducial; its lanes also
-//   derive P_obs of the fiducial (effective volume, quadrature weight) and the shot-noise derivative 1 / P_obs, and
-//   hand them to the other lanes of their cell by shuffles.
 //   Along a mu column k' = k G(mu) drifts by a fraction of a table piece, so the piece records (P_lin and f cubics,
 //   no-wiggle line) of both stencil points live in REGISTERS and are re-fetched only when k' leaves the piece:
-//   the steady state issues no global load at all.  The row constants of the 16 (sign, slot) points for every mu row
-//   of the slice are staged once per CTA in shared memory ([row][q], 48-byte records: conflict-free 128-bit loads).
+//   the steady state issues no table load at all.  The row constants of the 16 (sign, slot) points for every mu row
+//   of the slice are staged once per CTA in shared memory ([row][q], 48-byte records: conflict-free 128-bit loads),
+//   already multiplied out so that every mu-dependent factor is one FMA in k^2 or k'.
 // Work: tasks = (segment of rows) x (group of 4 wavenumbers), dealt round-robin to the warps of the grid in a fixed
-// order (deterministic partial sums); partial[zb][cta][3 tiles][64].
-constexpr int PK_WARPS = 8;
-constexpr int PK_THREADS = PK_WARPS * 32;
+// order (deterministic partial sums); one CTA per SM; partial[zb][cta][80].
 constexpr int PK_MAXROWS = 136;  // mu rows staged at once (16 x 48 B each)
+constexpr int WG_ROWS = 16;      // mu rows per CTA of the weights pre-pass
 
-struct PRec {  // piece records of one stencil point at the lane's k': a_i are pre-multiplied by bao / sigma8^2
-  double loA, hiA, a0, a1, a2, a3, f0, f1, f2, f3;
-  double loN, hiN, c0, sl;  // no-wiggle line c0 + sl k' (pre-multiplied likewise); +-inf bounds at the table ends
+struct RowP {    // row constants of the pair kernel, per (row, q)
+  double G;      // k' / k
+  double fmu2;   // fs8 mu'^2
+  double errc2;  // (err / k)^2:  err^2 = k^2 errc2
+  double nsvg;   // -sv2 G^2:     dewiggling exponent = k^2 nsvg
+  double fg2;    // (G fogc)^2:   FoG denominator = 1 + k^2 fg2
+  double pad;
+};
+
+struct PRec {  // piece records of one stencil point at the lane's k': a_i, c0, sl are pre-multiplied by bao / sigma8^2
+  double loA, a0, a1, a2, a3, f0, f1, f2, f3;
+  double loN, c0, sl;  // no-wiggle line c0 + sl k'
+  unsigned wA, wN;     // high words of the piece widths: k' - lo is inside the piece if its high word is smaller
 };
 
 __device__ __forceinline__ void pair_fetch_cubic(PRec& r, const SDev& sp, double kap, int& h) {
@@ -1000,7 +1012,8 @@ __device__ __forceinline__ void pair_fetch_cubic(PRec& r, const SDev& sp, double
   const double2* ra = reinterpret_cast<const double2*>(sp.blkA + (size_t)h * CUBIC_BLK);
   const double2* rb = reinterpret_cast<const double2*>(sp.blkB + (size_t)h * CUBIC_BLK);
   const double2 b = __ldg(ra), a01 = __ldg(ra + 1), a23 = __ldg(ra + 2), f01 = __ldg(rb + 1), f23 = __ldg(rb + 2);
-  r.loA = b.x, r.hiA = b.y;
+  r.loA = b.x;
+  r.wA = (unsigned)__double2hiint(b.y - b.x);
   r.a0 = a01.x * sp.baos, r.a1 = a01.y * sp.baos, r.a2 = a23.x * sp.baos, r.a3 = a23.y * sp.baos;
   r.f0 = f01.x, r.f1 = f01.y, r.f2 = f23.x, r.f3 = f23.y;
 }
@@ -1010,38 +1023,110 @@ __device__ __forceinline__ void pair_fetch_line(PRec& r, const SDev& sp, double 
   h = locate<LIN_BLK>(sp.blkN, sp.nN, kap, h, lo);
   const double2* rn = reinterpret_cast<const double2*>(sp.blkN + (size_t)h * LIN_BLK);
   const double2 b = __ldg(rn), ys = __ldg(rn + 1);
-  // degree-1 spline with extrapolation: the end pieces extend to infinity
-  r.loN = (h == 0) ? -CUDART_INF : b.x;
-  r.hiN = (h == sp.nN - 1) ? CUDART_INF : b.y;
+  // degree-1 spline with extrapolation: the end pieces extend (practically) to infinity
+  const double lo_v = (h == 0) ? -1e300 : b.x, hi_v = (h == sp.nN - 1) ? 1e300 : b.y;
+  r.loN = lo_v;
+  r.wN = (unsigned)__double2hiint(hi_v - lo_v);
   r.sl = ys.y * sp.baos;
   r.c0 = fma(-ys.y, b.x, ys.x) * sp.baos;  // y + slope (k' - lo) = (y - slope lo) + slope k'
 }
 
-// numerator N = (b + f mu'^2)^2 * dewiggled P * bao/s8^2 and FoG denominator of X = N / den; err2 as in eval_x
-__device__ __forceinline__ void pair_eval(const MathTab& mt, const PRec& r, const RowC& rc, double k, double kap,
-                                          double bias, double& N, double& den, double& err2, double& F, double& dw) {
-  const double err = k * rc.errc;
-  err2 = err * err;
-  const double u = kap - r.loA;
+// exp(x), x <= 0: tab_exp_neg with the clamp done on the high word in the integer pipe (for x <= 0 the high word
+// grows with |x| as an unsigned integer) and the polynomial in Estrin form (dependency chain 4 instead of 6)
+__device__ __forceinline__ double pair_exp_neg(const MathTab& mt, double x) {
+  x = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC085E000u), __double2loint(x));  // >= -700 (about)
+  double t = fma(x, CFP_TEXP[0], CFP_TEXP[1]);  // low word = round(32 x / ln 2) = 32 n + j
+  const int m = __double2loint(t);
+  t -= CFP_TEXP[1];
+  double r = fma(t, CFP_TEXP[2], x);
+  r = fma(t, CFP_TEXP[3], r);                   // |r| <= ln2/64
+  const double tj = mt.e2[m & 31];
+  const double r2 = r * r;
+  const double q0 = r + 1.0;
+  const double q1 = fma(r, CFP_TEXP[7], 0.5);
+  const double q2 = fma(r, CFP_TEXP[5], CFP_TEXP[6]);
+  double p = fma(CFP_TEXP[4], r2, q2);
+  p = fma(p, r2, q1);
+  p = fma(p, r2, q0);
+  p *= tj;
+  return __hiloint2double(__double2hiint(p) + ((m >> 5) << 20), __double2loint(p));
+}
+
+// numerator N = (b + f mu'^2)^2 * dewiggled P * bao/s8^2 and FoG denominator of X = N / den
+__device__ __forceinline__ void pair_eval(const MathTab& mt, const PRec& r, const RowP& rc, double k2, double kap,
+                                          double u, double bias, double& N, double& den) {
   const double pdd = fma(u, fma(u, fma(u, r.a3, r.a2), r.a1), r.a0);
-  F = fma(u, fma(u, fma(u, r.f3, r.f2), r.f1), r.f0) * rc.fmu2;
+  const double pf = fma(u, fma(u, fma(u, r.f3, r.f2), r.f1), r.f0);
   const double pnw = fma(r.sl, kap, r.c0);
-  const double e = tab_exp_neg(mt, -rc.sv2 * (kap * kap));
-  dw = fma(e, pdd - pnw, pnw);
-  const double t = kap * rc.fogc;
-  den = fma(t, t, 1.0);
-  const double kaiser = bias + F;
+  const double e = pair_exp_neg(mt, k2 * rc.nsvg);
+  const double dw = fma(e, pdd - pnw, pnw);
+  den = fma(k2, rc.fg2, 1.0);
+  const double kaiser = fma(pf, rc.fmu2, bias);
   N = (kaiser * kaiser) * dw;
 }
 
-__constant__ double CFP_ATANH[5] = {1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0};
+__constant__ double CFP_ATANH[4] = {1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0};
 
-__global__ void __launch_bounds__(PK_THREADS, 2)
-    spectro_fisher_pairs_kernel(SpectroParams P, int row_lo, int nrows, int srows, int nseg, double* __restrict__ partial) {
+// {w, dps}[zb][row - row_lo][k]: quadrature weight x 2 V veff of the cell on the fiducial spectrum, and the
+// shot-noise derivative 1 / P_obs (0 if the bin has no shot-noise parameter).  grid (k blocks, Z, row segments).
+__global__ void __launch_bounds__(TILE) spectro_weights_kernel(SpectroParams P, int row_lo, int nrows,
+                                                               double2* __restrict__ wd) {
+  const int zb = blockIdx.y;
+  if (!P.pairs[zb].ok) return;
+  __shared__ SDev sp;
+  __shared__ RowC rows[WG_ROWS];
+  __shared__ MathTab mt;
+  const int tid = threadIdx.x;
+  if (tid < (int)(sizeof(SDev) / sizeof(double)))
+    reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S)[tid];
+  math_tables_fill(mt, tid, TILE);
+  __syncthreads();
+  const int r0 = blockIdx.z * WG_ROWS, nr = min(WG_ROWS, nrows - r0);
+  if (tid < nr) rows[tid] = row_consts(sp, P.flags, __ldg(P.mu + row_lo + r0 + tid), __ldg(P.smu + row_lo + r0 + tid));
+  __syncthreads();
+  const int ki = blockIdx.x * TILE + tid;
+  const int ldk = ((P.Nk + 3) >> 2) << 2;  // rows padded to whole groups of four wavenumbers (zero weight)
+  if (ki >= P.Nk) {
+    if (ki < ldk)
+      for (int r = 0; r < nr; ++r) wd[((size_t)zb * nrows + (r0 + r)) * ldk + ki] = make_double2(0.0, 0.0);
+    return;
+  }
+  const PairPlan& plan = P.pairs[zb];
+  const int ps_sel = plan.ps_sel;
+  const bool has_ps = plan.par[8] >= 0;
+  const double bsrc = ps_sel == 0 ? sp.bias : P.sdev[(size_t)zb * P.S + plan.pt[(ps_sel == 1 ? 0 : 8) + 7]].bias;
+  const double nbar = P.nbar[zb], vol2 = 2.0 * P.vol[zb];
+  const double k = __ldg(P.k + ki);
+  const double wcol = (k * k) * __ldg(P.wk + ki);
+  int hA = -1, hB = -1, hN = -1;
+  for (int r = 0; r < nr; ++r) {
+    const int row = row_lo + r0 + r;
+    double err2, qf, F, W;
+    const double X0 = eval_x(mt, sp, rows[r], P.flags, k, hA, hB, hN, err2, qf, F, W);
+    const double e = tab_exp_neg(mt, -err2);
+    const double P0 = X0 * e;
+    const double ks = fma(bsrc, qf, F);
+    const double Psrc = ps_sel == 0 ? P0 : ((ks * ks) * W) * e;
+    const double npobs = nbar * P0;
+    const double rr = fast_div(npobs, 1.0 + npobs);
+    const double veff = INV_8PI2 * rr * rr;  // spectro_cov.py:223-225
+    const int64_t cell = (int64_t)row * P.Nk + ki;
+    const bool valid = cell >= P.cell_begin && cell < P.cell_end;
+    // cosmicfish.py:541: k^2 * 2 * V_survey * veff, times the Simpson weights of :510-511
+    const double w = valid ? (vol2 * veff) * (__ldg(P.wmu + row) * wcol) : 0.0;
+    wd[((size_t)zb * nrows + (r0 + r)) * ldk + ki] = make_double2(w, has_ps ? fast_rcp(Psrc) : 0.0);  // spectro_cov.py:510-532
+  }
+}
+
+template <int PK_WARPS>
+__global__ void __launch_bounds__(PK_WARPS * 32, 1)
+    spectro_fisher_pairs_kernel(SpectroParams P, int row_lo, int nrows, int srows, int nseg,
+                                const double2* __restrict__ wd, double* __restrict__ partial) {
+  constexpr int PK_THREADS = PK_WARPS * 32;
   const int zb = blockIdx.y;
   if (!P.pairs[zb].ok) return;  // (uniform: the general kernel takes this bin)
   extern __shared__ __align__(16) double smem[];
-  RowC* const sm_rows = reinterpret_cast<RowC*>(smem);                   // [srows][16]
+  RowP* const sm_rows = reinterpret_cast<RowP*>(smem);                   // [srows][16]
   MathTab& mt = *reinterpret_cast<MathTab*>(sm_rows + (size_t)srows * 16);
   SDev* const sm_pt = reinterpret_cast<SDev*>(&mt + 1);                   // [16]
   PairPlan& plan = *reinterpret_cast<PairPlan*>(sm_pt + 16);
@@ -1064,14 +1149,11 @@ __global__ void __launch_bounds__(PK_THREADS, 2)
   const SDev& spB = sm_pt[8 + slot];
   const double biasA = spA.bias, biasB = spB.bias;
   const double coef = plan.coef[slot];
-  const double bias0 = plan.bias0;
-  const int ps_sel = plan.ps_sel;
-  const bool has_ps = plan.par[8] >= 0;
-  const double nbar = P.nbar[zb], vol2 = 2.0 * P.vol[zb];
   const int nquad = (P.Nk + 3) >> 2;
-  double acc[3][2];
-#pragma unroll
-  for (int t = 0; t < 3; ++t) acc[t][0] = acc[t][1] = 0.0;
+  const int ldk = nquad << 2;
+  // Gram accumulators: the 8 x 8 tile of the slots on the tensor cores; the shot-noise row F[8][slot] and F[8][8]
+  // as two scalar FMAs per lane (only one row of a second tile would be non-zero)
+  double acc0 = 0.0, acc1 = 0.0, acc8 = 0.0, acc88 = 0.0;
 
   for (int r_base = 0; r_base < nrows; r_base += srows) {
     const int nr = min(srows, nrows - r_base);
@@ -1079,9 +1161,12 @@ __global__ void __launch_bounds__(PK_THREADS, 2)
     for (int i = tid; i < nr * 16; i += PK_THREADS) {
       const int rr = i >> 4, q = i & 15;
       const int row = row_lo + r_base + rr;
-      RowC rc = row_consts(sm_pt[q], P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
-      if (q == 7) rc.pad = __ldg(P.wmu + row);
-      sm_rows[i] = rc;
+      const RowC rc = row_consts(sm_pt[q], P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
+      RowP rp;
+      rp.G = rc.G, rp.fmu2 = rc.fmu2, rp.errc2 = rc.errc * rc.errc, rp.nsvg = -rc.sv2 * (rc.G * rc.G);
+      const double gf = rc.G * rc.fogc;
+      rp.fg2 = gf * gf, rp.pad = 0.0;
+      sm_rows[i] = rp;
     }
     __syncthreads();
     const int segs = (nr == nrows) ? nseg : 1;  // (a slice staged in several pieces is not cut further)
@@ -1090,84 +1175,87 @@ __global__ void __launch_bounds__(PK_THREADS, 2)
     for (int task = blockIdx.x * PK_WARPS + warp; task < ntask; task += gridDim.x * PK_WARPS) {
       const int seg = task / nquad, quad = task - seg * nquad;
       const int r0 = seg * seglen, r1 = min(nr, r0 + seglen);
-      int ki = quad * 4 + cell;
-      const bool col_ok = ki < P.Nk;
-      ki = col_ok ? ki : P.Nk - 1;
-      const double k = __ldg(P.k + ki);
-      const double wcol = (k * k) * __ldg(P.wk + ki);
+      const int kcol = quad * 4 + cell;  // (columns beyond the lattice carry zero weight in wd)
+      const double k = __ldg(P.k + min(kcol, P.Nk - 1));
+      const double k2 = k * k;
       PRec A, B;
-      A.loA = A.loN = B.loA = B.loN = CUDART_INF;  // nothing fetched yet
-      A.hiA = A.hiN = B.hiA = B.hiN = -CUDART_INF;
+      A.loA = A.loN = B.loA = B.loN = 0.0;
+      A.wA = A.wN = B.wA = B.wN = 0u;  // nothing fetched yet
       A.a0 = A.a1 = A.a2 = A.a3 = A.f0 = A.f1 = A.f2 = A.f3 = A.c0 = A.sl = 0.0;
       B.a0 = B.a1 = B.a2 = B.a3 = B.f0 = B.f1 = B.f2 = B.f3 = B.c0 = B.sl = 0.0;
       int hAa = -1, hAn = -1, hBa = -1, hBn = -1;
-      const RowC* rcp = sm_rows + (size_t)r0 * 16 + slot;
-      int64_t cellidx = (int64_t)(row_lo + r_base + r0) * P.Nk + ki;
-      for (int r = r0; r < r1; ++r, rcp += 16, cellidx += P.Nk) {
-        const RowC& rcA = rcp[0];
-        const RowC& rcB = rcp[8];
+      const RowP* rcp = sm_rows + (size_t)r0 * 16 + slot;
+      const double2* wdp = wd + ((size_t)zb * nrows + (r_base + r0)) * ldk + kcol;
+      // The loop is software-pipelined by one row: iteration r evaluates the pair of row r and FINISHES row r - 1
+      // (division, series, Gram update), so that the serial tail of one row overlaps the table polynomials and
+      // exponentials of the next in one basic block; {w, dps} of a row are requested one iteration before their use.
+      // The first iteration finishes a dummy row of zero weight, the last one (r == r1) re-evaluates row r1 - 1.
+      double num_p = 1.0, dnm_p = 1.0, ed_p = 0.0;
+      double2 wv_p = make_double2(0.0, 0.0);
+      for (int r = r0; r <= r1; ++r) {
+        const double2 wv = __ldg(wdp);
+        const RowP& rcA = rcp[0];
+        const RowP& rcB = rcp[8];
         const double kapA = k * rcA.G, kapB = k * rcB.G;
-        if (!(kapA >= A.loA && kapA < A.hiA)) pair_fetch_cubic(A, spA, kapA, hAa);
-        if (!(kapA >= A.loN && kapA < A.hiN)) pair_fetch_line(A, spA, kapA, hAn);
-        if (!(kapB >= B.loA && kapB < B.hiA)) pair_fetch_cubic(B, spB, kapB, hBa);
-        if (!(kapB >= B.loN && kapB < B.hiN)) pair_fetch_line(B, spB, kapB, hBn);
-        double NA, denA, e2A, FA, dwA, NB, denB, e2B, FB, dwB;
-        pair_eval(mt, A, rcA, k, kapA, biasA, NA, denA, e2A, FA, dwA);
-        pair_eval(mt, B, rcB, k, kapB, biasB, NB, denB, e2B, FB, dwB);
-        // d = (ln P+ - ln P-) / (2h),  ln P = ln(N / den) - err2
-        const double num = NA * denB, dnm = NB * denA;
-        const double t = fast_div(num - dnm, num + dnm);
-        const double t2 = t * t;
-        double p = fma(CFP_ATANH[0], t2, CFP_ATANH[1]);
-        p = fma(p, t2, CFP_ATANH[2]);
-        p = fma(p, t2, CFP_ATANH[3]);
-        p = fma(p, t2, CFP_ATANH[4]);
-        double lnr = fma(p * t2, t + t, t + t);
-        if (!(fabs(t) < 0.03)) {  // a step too large for the series (or a spectrum that is not positive: NaN below)
-          lnr = (num > 0.0 && dnm > 0.0) ? tab_log(mt, num) - tab_log(mt, dnm) : CUDART_NAN;
+        double uA = kapA - A.loA, uB = kapB - B.loA;
+        const double vA = kapA - A.loN, vB = kapB - B.loN;
+        // inside the pieces held in registers?  (high words compared as unsigned integers: a negative or too large
+        // offset fails; so does, harmlessly, one within 2^-20 of the piece's upper end)
+        const bool okA = (unsigned)__double2hiint(uA) < A.wA, okAn = (unsigned)__double2hiint(vA) < A.wN;
+        const bool okB = (unsigned)__double2hiint(uB) < B.wA, okBn = (unsigned)__double2hiint(vB) < B.wN;
+        if (!(okA && okAn && okB && okBn)) {
+          if (!okA) pair_fetch_cubic(A, spA, kapA, hAa), uA = kapA - A.loA;
+          if (!okAn) pair_fetch_line(A, spA, kapA, hAn);
+          if (!okB) pair_fetch_cubic(B, spB, kapB, hBa), uB = kapB - B.loA;
+          if (!okBn) pair_fetch_line(B, spB, kapB, hBn);
         }
-        // a spectrum that is not positive has no logarithm: NaN, as numpy gives the reference (spectro_obs.py:913-933)
-        double d = (num > 0.0 && dnm > 0.0) ? (lnr - (e2A - e2B)) * coef : CUDART_NAN;
-        double w = 0.0, dps = 0.0;
-        if (slot == 7) {
-          // fiducial spectrum from the pair's shared look-ups: effective volume, quadrature weight, 1 / P_obs
-          const double rden = fast_rcp(denA);
-          const double kaiser0 = bias0 + FA;
-          const double N0 = (kaiser0 * kaiser0) * dwA;
-          const double e = tab_exp_neg(mt, -e2A) * rden;
-          const double P0 = N0 * e;
-          if (has_ps) dps = fast_rcp(ps_sel == 0 ? P0 : (ps_sel == 1 ? NA : NB) * e);  // spectro_cov.py:510-532
-          const double npobs = nbar * P0;
-          const double rr = fast_div(npobs, 1.0 + npobs);
-          const double veff = INV_8PI2 * rr * rr;  // spectro_cov.py:223-225
-          const bool valid = col_ok && cellidx >= P.cell_begin && cellidx < P.cell_end;
-          // cosmicfish.py:541: k^2 * 2 * V_survey * veff, times the Simpson weights of :510-511
-          w = valid ? (vol2 * veff) * (rcA.pad * wcol) : 0.0;
+        double NA, denA, NB, denB;
+        pair_eval(mt, A, rcA, k2, kapA, uA, biasA, NA, denA);
+        pair_eval(mt, B, rcB, k2, kapB, uB, biasB, NB, denB);
+        const double ed = k2 * (rcA.errc2 - rcB.errc2);  // err+^2 - err-^2
+        // ---- finish the previous row: d = (ln P+ - ln P-) / (2h),  ln P = ln(N / den) - err^2
+        {
+          const double t = (num_p - dnm_p) * fast_rcp(num_p + dnm_p);
+          const double t2 = t * t;
+          double p = fma(CFP_ATANH[0], t2, CFP_ATANH[1]);
+          p = fma(p, t2, CFP_ATANH[2]);
+          p = fma(p, t2, CFP_ATANH[3]);
+          double lnr = fma(p * t2, t + t, t + t);
+          // the series needs |t| < 0.03 (t^10 / 11 < 1e-16 relative) and both spectra positive (sign bits clear)
+          if (!(fabs(t) < 0.03 && (__double2hiint(num_p) | __double2hiint(dnm_p)) >= 0)) {
+            // a spectrum that is not positive has no logarithm: NaN, as numpy gives the reference (spectro_obs.py:913-933)
+            lnr = (num_p > 0.0 && dnm_p > 0.0) ? tab_log(mt, num_p) - tab_log(mt, dnm_p) : CUDART_NAN;
+          }
+          const double d = (lnr - ed_p) * coef;
+          const double b0 = wv_p.x * d;
+          dmma884(acc0, acc1, d, b0);
+          acc8 = fma(wv_p.y, b0, acc8);
+          acc88 = fma(wv_p.y * wv_p.y, wv_p.x, acc88);
         }
-        w = __shfl_sync(0xffffffffu, w, 28 + cell);
-        dps = __shfl_sync(0xffffffffu, dps, 28 + cell);
-        const double a1 = (slot == 0) ? dps : 0.0;
-        const double b0 = w * d, b1 = w * a1;
-        dmma884(acc[0][0], acc[0][1], d, b0);
-        dmma884(acc[1][0], acc[1][1], a1, b0);
-        dmma884(acc[2][0], acc[2][1], a1, b1);
+        num_p = NA * denB, dnm_p = NB * denA, ed_p = ed, wv_p = wv;
+        if (r + 1 < r1) rcp += 16, wdp += ldk;  // (the extra iteration stays on the last row)
       }
+      // (what is still carried here is the duplicate evaluation of the last row: dropped)
     }
   }
-  // cross-warp reduction in fixed order, then one partial per CTA
+  // the shot-noise row: sum over the four cells of a slot
+  acc8 += __shfl_xor_sync(0xffffffffu, acc8, 1);
+  acc8 += __shfl_xor_sync(0xffffffffu, acc8, 2);
+  acc88 += __shfl_xor_sync(0xffffffffu, acc88, 1);
+  acc88 += __shfl_xor_sync(0xffffffffu, acc88, 2);
+  // cross-warp reduction in fixed order, then one partial per CTA: [tile 0: 64][F[8][slot]: 8][F[8][8]: 1]
   __syncthreads();
-  double* red = smem;  // [PK_WARPS][3][64]
-#pragma unroll
-  for (int t = 0; t < 3; ++t) {
-    red[(warp * 3 + t) * 64 + lane * 2 + 0] = acc[t][0];
-    red[(warp * 3 + t) * 64 + lane * 2 + 1] = acc[t][1];
-  }
+  double* red = smem;  // [PK_WARPS][80]
+  red[warp * 80 + lane * 2 + 0] = acc0;
+  red[warp * 80 + lane * 2 + 1] = acc1;
+  if (cell == 0) red[warp * 80 + 64 + slot] = acc8;
+  if (lane == 0) red[warp * 80 + 72] = acc88;
   __syncthreads();
-  double* out = partial + ((size_t)zb * gridDim.x + blockIdx.x) * 192;
-  for (int e = tid; e < 192; e += PK_THREADS) {
+  double* out = partial + ((size_t)zb * gridDim.x + blockIdx.x) * 80;
+  for (int e = tid; e < 73; e += PK_THREADS) {
     double sacc = 0.0;
 #pragma unroll
-    for (int w = 0; w < PK_WARPS; ++w) sacc += red[w * 192 + e];
+    for (int w = 0; w < PK_WARPS; ++w) sacc += red[w * 80 + e];
     out[e] = sacc;
   }
 }
@@ -1195,9 +1283,9 @@ __global__ void __launch_bounds__(256) spectro_reduce_pairs_kernel(const double*
     double s = 0.0;
     if (ai >= 0 && aj >= 0) {
       const int hi = max(ai, aj), lo = min(ai, aj);
-      const int t = hi < 8 ? 0 : (lo < 8 ? 1 : 2);
-      const int el = t * 64 + ((hi & 7) * 4 + ((lo & 7) >> 1)) * 2 + (lo & 1);
-      for (int c = 0; c < ncta; ++c) s += partial[((size_t)zb * ncta + c) * 192 + el];
+      // [tile of the 8 slots: fragment order][F[8][slot]][F[8][8]]
+      const int el = hi < 8 ? (hi * 4 + (lo >> 1)) * 2 + (lo & 1) : (lo < 8 ? 64 + lo : 72);
+      for (int c = 0; c < ncta; ++c) s += partial[((size_t)zb * ncta + c) * 80 + el];
     }
     F[((size_t)zb * npar + i) * npar + j] = s;
     F[((size_t)zb * npar + j) * npar + i] = s;
@@ -1745,8 +1833,9 @@ struct cfp_spectro_plan {
   double *partial_d = nullptr, *fisher_d = nullptr;
   double *lnp_d = nullptr, *derivs_d = nullptr, *veff_d = nullptr;
   PairPlan* pairs_d = nullptr;     // [Z] plan of the pair kernel per bin (written by the setup block of every run)
-  double* partial2_d = nullptr;    // [Z][grid2_x][192] partials of the pair kernel
-  int grid2_x = 0;
+  double* partial2_d = nullptr;    // [Z][grid2_x][80] partials of the pair kernel
+  double2* wd_d = nullptr;         // [Z][rows of the slice][Nk] {weight, shot-noise derivative} of the weights pre-pass
+  int grid2_x = 0, wd_rows = 0;
   int pair_state = 0;              // bins the pair kernel takes when nothing is materialised: 0 unknown, 1 all, 2 none, 3 some
   int last_mat = -1;
   bool ran = false;
@@ -1770,6 +1859,7 @@ static void spectro_free(cfp_spectro_plan* p) {
   cfp_dev_free(p->ctx, p->veff_d);
   cfp_dev_free(p->ctx, p->partial_d);
   cfp_dev_free(p->ctx, p->partial2_d);
+  cfp_dev_free(p->ctx, p->wd_d);
   delete p;
 }
 
@@ -2318,13 +2408,17 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
     allocated = true;
   }
   const int nquad = (pl->Nk + 3) / 4;
-  const int gx2 = std::max(1, std::min((nquad + PK_WARPS - 1) / PK_WARPS, (ctx->sm_count * 2) / pl->Z));
-  if (try_pairs && gx2 != pl->grid2_x) {
+  static const int pk_warps = std::getenv("CFP_PK_WARPS") ? std::atoi(std::getenv("CFP_PK_WARPS")) : 16;
+  const int gx2 = std::max(1, std::min((nquad + pk_warps - 1) / pk_warps, ctx->sm_count / pl->Z));
+  if (try_pairs && (gx2 != pl->grid2_x || nrows != pl->wd_rows)) {
     if (pl->partial2_d && pl->last_st && pl->last_st != ctx->stream) CFP_CUDA(cudaStreamSynchronize(pl->last_st));
     cfp_dev_free(ctx, pl->partial2_d);
-    pl->partial2_d = nullptr;
-    CFP_CUDA(cfp_dev_alloc(ctx, (void**)&pl->partial2_d, (size_t)pl->Z * gx2 * 192 * sizeof(double)));
+    cfp_dev_free(ctx, pl->wd_d);
+    pl->partial2_d = nullptr, pl->wd_d = nullptr;
+    CFP_CUDA(cfp_dev_alloc(ctx, (void**)&pl->partial2_d, (size_t)pl->Z * gx2 * 80 * sizeof(double)));
+    CFP_CUDA(cfp_dev_alloc(ctx, (void**)&pl->wd_d, (size_t)pl->Z * nrows * (4 * nquad) * sizeof(double2)));
     pl->grid2_x = gx2;
+    pl->wd_rows = nrows;
     allocated = true;
   }
   // pool allocations are ordered on the context stream; a caller's stream must not start before them
@@ -2351,7 +2445,7 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
   if (try_pairs) {
     // rows staged at once, and how finely the rows are cut into tasks: enough tasks for an even deal to the warps
     const int srows = std::min(nrows, PK_MAXROWS);
-    const int nwarps = gx2 * PK_WARPS;
+    const int nwarps = gx2 * pk_warps;
     int nseg = 1;
     double best = 0.0;
     for (int c = 1; c <= 4 && c <= nrows; ++c) {
@@ -2359,14 +2453,34 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
       const double eff = (double)tasks / (double)(((tasks + nwarps - 1) / nwarps) * nwarps);
       if (eff > best + 0.02) best = eff, nseg = c;
     }
-    const size_t smem2 = std::max((size_t)srows * 16 * sizeof(RowC), (size_t)PK_WARPS * 192 * sizeof(double)) + sizeof(MathTab) +
+    spectro_weights_kernel<<<dim3((pl->Nk + TILE - 1) / TILE, pl->Z, (nrows + WG_ROWS - 1) / WG_ROWS), TILE, 0, st>>>(
+        P, row_lo, nrows, pl->wd_d);
+    ctx->launches++;
+    const size_t smem2 = std::max((size_t)srows * 16 * sizeof(RowP), (size_t)pk_warps * 80 * sizeof(double)) + sizeof(MathTab) +
                          16 * sizeof(SDev) + sizeof(PairPlan);
-    e = cudaFuncSetAttribute(spectro_fisher_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    if (e == cudaSuccess) {
-      spectro_fisher_pairs_kernel<<<dim3(gx2, pl->Z), PK_THREADS, smem2, st>>>(P, row_lo, nrows, srows, nseg, pl->partial2_d);
-      ctx->launches++;
-      e = cudaGetLastError();
+#define CFP_LAUNCH_PK(WV)                                                                                             \
+  case WV:                                                                                                            \
+    e = cudaFuncSetAttribute(spectro_fisher_pairs_kernel<WV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
+    if (e == cudaSuccess)                                                                                             \
+      spectro_fisher_pairs_kernel<WV><<<dim3(gx2, pl->Z), WV * 32, smem2, st>>>(P, row_lo, nrows, srows, nseg,         \
+                                                                               pl->wd_d, pl->partial2_d);             \
+    break;
+    switch (pk_warps) {
+      CFP_LAUNCH_PK(12)
+      CFP_LAUNCH_PK(20)
+      CFP_LAUNCH_PK(24)
+      CFP_LAUNCH_PK(28)
+      CFP_LAUNCH_PK(32)
+      default:
+        e = cudaFuncSetAttribute(spectro_fisher_pairs_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e == cudaSuccess)
+          spectro_fisher_pairs_kernel<16><<<dim3(gx2, pl->Z), 16 * 32, smem2, st>>>(P, row_lo, nrows, srows, nseg, pl->wd_d,
+                                                                                    pl->partial2_d);
+        break;
     }
+#undef CFP_LAUNCH_PK
+    ctx->launches++;
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
       cfp_set_error("spectro_fisher_pairs_kernel launch: %s", cudaGetErrorString(e));
       return CFP_ERR_CUDA;
