@@ -308,6 +308,7 @@ class cosmo_functions:
 
 
 _COSMO_CACHE: Dict[tuple, tuple] = {}
+_COSMO_CACHE_MAX = 256  # fitted cosmologies kept (oldest evicted first)
 
 
 def clear_caches():
@@ -330,6 +331,8 @@ def cached_cosmo(cosmopars, config) -> "cosmo_functions":
         return hit[1]
     c = cosmo_functions(dict(cosmopars), config.input_type, config)
     _COSMO_CACHE[key] = (ext.get("tables"), c)
+    while len(_COSMO_CACHE) > _COSMO_CACHE_MAX:  # a sampler that moves in cosmology would grow this without bound
+        _COSMO_CACHE.pop(next(iter(_COSMO_CACHE)))
     return c
 
 
@@ -363,9 +366,26 @@ class CosmoSet:
     def __len__(self):
         return len(self.cosmos)
 
+    def begin_batch(self, limit: int = 64):
+        """Called by the likelihoods before a batch indexes into the set: once more than `limit` cosmologies have
+        accumulated (a sampler that varies cosmological parameters adds one per distinct point) the set is cut back
+        to the fiducial and the device bank released, so host and device memory stay bounded over a long run."""
+        if len(self.cosmos) > limit:
+            if self._bank is not None:
+                self._bank.close()
+                self._bank = None
+            self.cosmos = self.cosmos[:1]
+            self._by_key = {k: v for k, v in self._by_key.items() if v == 0}
+
+    def context(self) -> _lib.Context:
+        """The device context every bank, plan and likelihood helper of this job uses: options["device"]
+        (default: LOCAL_RANK or 0), created on first use."""
+        if self.ctx is None:
+            self.ctx = _lib.default_context((getattr(self.config, "settings", None) or {}).get("device"))
+        return self.ctx
+
     def bank(self) -> _lib.Bank:
         if self._bank is None:
-            if self.ctx is None:
-                self.ctx = _lib.default_context()
-            self._bank = _lib.Bank.from_rows(self.ctx, [c.packed_row(self.ctx, self.slots) for c in self.cosmos])
+            ctx = self.context()
+            self._bank = _lib.Bank.from_rows(ctx, [c.packed_row(ctx, self.slots) for c in self.cosmos])
         return self._bank

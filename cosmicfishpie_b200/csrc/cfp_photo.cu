@@ -11,7 +11,7 @@
 //                         of the covariance, Z_p = A^-1 M_p and F_pq += w_l Tr(Z_p Z_q) on DMMA
 //                         (photo_cov.py:198-245, cosmicfish.py:643-744)
 //   photo_reduce_kernel   fixed-tree sum over multipole bins
-//   photo_chi2_kernel     likelihood: one warp per (point, multipole, block), Cholesky + one forward substitution,
+//   photo_chi2_reg_kernel likelihood: one warp per (point, multipole), register-resident Cholesky fused with the forward substitution,
 //                         tr(A^-1 B) = |L^-1 L_B|^2                                      (photo_like.py:28-97,180-256)
 #include <algorithm>
 #include <cmath>
@@ -498,21 +498,6 @@ __global__ void __launch_bounds__(256) photo_reduce_kernel(const double* __restr
 
 
 // ---------------------------------------------------------------------------- likelihood
-constexpr int CHI_WARPS = 4;
-// row stride of the per-warp n x n tile: odd (conflict-free column walks) and >= n + 2: the lower triangle holds the
-// Cholesky factor of A, the strict upper triangle shifted by one column holds L_B / M transposed, column n+1 the
-// reciprocal diagonal
-__host__ __device__ constexpr int chi_ld(int nmax) { return (nmax + 2) | 1; }
-// doubles reserved per warp for the (i, j) pair list of the Cholesky trailing updates (2 bytes per pair)
-__host__ __device__ constexpr int chi_pairs_doubles(int nmax) { return (nmax * (nmax - 1) / 2 * 2 + 7) / 8 + 1; }
-
-// One warp per (point, multipole, block): q = tr(A^-1 B) + ln det A - ln det B - n, A = C_l(s) + N, B = data
-// (photo_like.py:28-97).  With the Cholesky factors A = L L^T and B = L_B L_B^T (L_B is factorised ONCE per
-// (multipole, block) by the data pass and kept in global memory)
-//     tr(A^-1 B) = || L^-1 L_B ||_F^2 ,
-// i.e. after the factorisation of A one forward substitution per column of L_B, which starts at the column's
-// diagonal -- no backward substitution.  The trailing update of the factorisation is spread over all 32 lanes
-// (flat index over the trailing triangle), units whose quadrature weight is zero are skipped.
 __device__ __forceinline__ double chi_rsqrt(double x) {  // x > 0, normal: 1/sqrt(x) to ~1 ulp without the slow path
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -523,110 +508,223 @@ __device__ __forceinline__ double chi_rsqrt(double x) {  // x > 0, normal: 1/sqr
   return fma(y, e, y);
 }
 
-// pairs[e] = (i << 8) | j of the strictly-lower-plus-diagonal elements with j >= 1, ordered by DEcreasing j: the
-// trailing triangle of elimination step k (rows/cols k+1 .. n-1) is the first (n-k-1)(n-k)/2 entries.
-__device__ __forceinline__ void chol_pairs_fill(unsigned short* __restrict__ pairs, int n, int lane) {
-  for (int j = n - 1; j >= 1; --j) {
-    const int m = n - 1 - j;               // columns already listed: n-1 .. j+1
-    const int base = m * (m + 1) / 2;      // their element count: sum_{c=j+1}^{n-1} (n - c)
-    for (int i = j + lane; i < n; i += 32) pairs[base + (i - j)] = (unsigned short)((i << 8) | j);
-  }
-}
+// One warp per (point, multipole) takes every block of the chi^2 in turn.  Lane j owns ROW j of the (lower) matrix
+// A = C_l + N and COLUMN j of the data factor L_B, both in registers (static indices only: the loops are unrolled
+// for a compile-time bound N >= n).  Right-looking Cholesky: at step k the pivot is broadcast by a shuffle, every
+// lane scales its element of column k, the column goes through a 2 x 32-double shared-memory buffer (one store,
+// then 128-bit broadcast loads) and is used TWICE per loaded value: for the trailing update of A and for the forward
+// substitution M = L^-1 L_B, which is fused into the same sweep -- tr(A^-1 B) = |M|_F^2 accumulates as the columns
+// are finalised.  No pair lists, one warp barrier per pivot.
+// A block that is the LEADING sub-block of another one (3x2pt: the lensing block inside the full matrix) costs
+// nothing: the Cholesky factor, L_B and M of a leading block are the leading blocks of the big ones, so its
+// tr and ln det are partial sums of the same sweep.
+struct ChiBlocks {
+  int nblk;
+  int off[8], n[8];
+  int parent[8];  // block whose leading sub-block this one is (-1: none)
+  int child[8];   // the block that is this one's leading sub-block (-1: none)
+};
 
-__device__ __forceinline__ void chol_warp(double* __restrict__ L, const unsigned short* __restrict__ pairs, int n,
-                                          int LD, int lane) {
-  for (int k = 0; k < n; ++k) {
-    const double a = L[k * LD + k];
-    const double rd = chi_rsqrt(a);
-    __syncwarp();
-    if (lane > k && lane < n) L[lane * LD + k] *= rd;
-    if (lane == k) L[k * LD + k] = a * rd;
-    __syncwarp();
-    const int m = n - k - 1;  // trailing triangle: rows/cols k+1 .. n-1, j <= i
-    const int cnt = m * (m + 1) / 2;
-    for (int e = lane; e < cnt; e += 32) {
-      const int ij = pairs[e];
-      const int i = ij >> 8, j = ij & 255;
-      L[i * LD + j] -= L[i * LD + k] * L[j * LD + k];
+template <int N, bool DATA>
+__device__ __forceinline__ void chol_trace(const double* __restrict__ A, int lda, const double* __restrict__ noise,
+                                           const double* __restrict__ LB, int ldb, int n, int nlead,
+                                           double* col /* not __restrict__: the barriers must order its loads */,
+                                           int lane, double& tr, double& tr_lead, double& lndet, double& lndet_lead,
+                                           double* __restrict__ LBout) {
+  double a[N];
+  const bool in = lane < n;
+  const double nz = (noise && in) ? noise[lane] : 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i)  // row `lane` of the symmetric matrix read as column `lane`: coalesced; beyond n: identity
+    a[i] = (i < n && in) ? A[(size_t)i * lda + lane] + (i == lane ? nz : 0.0) : (i == lane ? 1.0 : 0.0);
+  double diag = 1.0;
+  // ---- pass 1: right-looking Cholesky; column k (scaled) is left in shared memory col[k][0..31], with 1 / L_kk in
+  // its diagonal slot
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    if (k < n) {  // (uniform)
+      const double akk = __shfl_sync(0xffffffffu, a[k], k);
+      const double rd = chi_rsqrt(akk);
+      const double ljk = a[k] * rd;  // lane j > k: L[j][k]; lane k: L[k][k]
+      a[k] = ljk;
+      if (lane == k) diag = ljk;
+      double* cb = col + k * 32;
+      cb[lane] = (lane == k) ? rd : ljk;
+      __syncwarp();
+      const double nl = -ljk;
+      int i = k + 1;
+      if (i & 1) {
+        if (i < N) a[i] = fma(nl, cb[i], a[i]);
+        ++i;
+      }
+#pragma unroll
+      for (; i + 1 < N; i += 2) {
+        const double2 c = *reinterpret_cast<const double2*>(cb + i);
+        a[i] = fma(nl, c.x, a[i]);
+        a[i + 1] = fma(nl, c.y, a[i + 1]);
+      }
     }
-    __syncwarp();  // the next pivot L[k+1][k+1] was updated by some other lane
   }
+  const double lg = in ? log(diag) : 0.0;
+  double l_all = lg, l_lead = (lane < nlead) ? lg : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    l_all += __shfl_xor_sync(0xffffffffu, l_all, o);
+    l_lead += __shfl_xor_sync(0xffffffffu, l_lead, o);
+  }
+  lndet = 2.0 * l_all;
+  lndet_lead = 2.0 * l_lead;
+  tr = tr_lead = 0.0;
+  if constexpr (DATA) {
+    if (in) {  // keep the factor: row `lane`, upper triangle zero
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        if (k < n) LBout[(size_t)lane * ldb + k] = (k <= lane) ? a[k] : 0.0;
+    }
+  } else {
+  // ---- pass 2: M = L^-1 L_B by columns (lane c owns column c of L_B, zero above the diagonal), the columns of L
+  // read back from shared memory; tr(A^-1 B) = |M|_F^2 accumulates as the rows are finalised
+#pragma unroll
+  for (int i = 0; i < N; ++i) a[i] = (i < n && in) ? LB[(size_t)i * ldb + lane] : 0.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    if (k >= n) break;
+    {
+      __syncwarp();  // (also keeps the scheduler from hoisting the broadcast loads of every later step up here)
+      const double* cb = col + k * 32;
+      const double xk = a[k] * cb[k];  // M[k][lane], final
+      const double x2 = xk * xk;
+      tr += x2;
+      if (k < nlead && lane < nlead) tr_lead += x2;
+      const double nx = -xk;
+      int i = k + 1;
+      if (i & 1) {
+        if (i < N) a[i] = fma(nx, cb[i], a[i]);
+        ++i;
+      }
+#pragma unroll
+      for (; i + 1 < N; i += 2) {
+        const double2 c = *reinterpret_cast<const double2*>(cb + i);
+        a[i] = fma(nx, c.x, a[i]);
+        a[i + 1] = fma(nx, c.y, a[i + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tr += __shfl_xor_sync(0xffffffffu, tr, o);
+    tr_lead += __shfl_xor_sync(0xffffffffu, tr_lead, o);
+  }
+  }
+  __syncwarp();  // (the next block of this warp overwrites col)
 }
 
-__global__ void __launch_bounds__(CHI_WARPS * 32) photo_chi2_kernel(
-    int S, int Nl, int Nb, int nblk, const int* __restrict__ blk_off, const int* __restrict__ blk_n,
-    const double* __restrict__ cls, const double* __restrict__ noise, const double* __restrict__ wts,
-    double* __restrict__ LB, double* __restrict__ lndetB, int data_mode, int nmax, double* __restrict__ q) {
-  extern __shared__ double chism[];
-  const int CHI_LD = chi_ld(nmax);
+// NQ: the kernel is compiled for blocks of at most 4 NQ rows (registers: the largest instantiation counts)
+template <bool DATA, int NQ>
+__device__ __forceinline__ void chol_dispatch(int n, const double* A, int lda, const double* noise, const double* LB,
+                                              int ldb, int nlead, double* col, int lane, double& tr, double& tr_lead,
+                                              double& lndet, double& lndet_lead, double* LBout) {
+#define CHOL_CASE(Q)                                                                                               \
+  if constexpr (Q < NQ) {                                                                                          \
+    if (n <= 4 * Q) {                                                                                              \
+      chol_trace<4 * Q, DATA>(A, lda, noise, LB, ldb, n, nlead, col, lane, tr, tr_lead, lndet, lndet_lead, LBout); \
+      return;                                                                                                      \
+    }                                                                                                              \
+  }
+  CHOL_CASE(1)
+  CHOL_CASE(2)
+  CHOL_CASE(3)
+  CHOL_CASE(4)
+  CHOL_CASE(5)
+  CHOL_CASE(6)
+  CHOL_CASE(7)
+#undef CHOL_CASE
+  chol_trace<4 * NQ, DATA>(A, lda, noise, LB, ldb, n, nlead, col, lane, tr, tr_lead, lndet, lndet_lead, LBout);
+}
+
+constexpr int CHR_WARPS = 4;
+// q[s][l][b] = tr(A^-1 B) + ln det A - ln det B - n  (photo_like.py:28-97); DATA: q[l][b] = ln det B, LB = chol(B)
+// resident CTAs per SM the kernel is compiled for: caps the registers near 2 N + 40 (without a cap the scheduler hoists
+// the broadcast loads of the whole substitution pass and takes 255)
+constexpr int chr_min_blocks(int nq) { return nq <= 2 ? 8 : (nq <= 4 ? 7 : (nq <= 5 ? 5 : 4)); }
+template <bool DATA, int NQ>
+__global__ void __launch_bounds__(CHR_WARPS * 32, chr_min_blocks(NQ)) photo_chi2_reg_kernel(
+    int S, int Nl, int Nb, ChiBlocks B, const double* __restrict__ cls, const double* __restrict__ noise,
+    const double* __restrict__ wts, double* __restrict__ LB, const double* __restrict__ lndetB, int nmax,
+    double* __restrict__ q) {
+  __shared__ __align__(16) double colbuf[CHR_WARPS][4 * NQ * 32];  // per warp: the columns of L, [k][row]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t unit = (size_t)blockIdx.x * CHI_WARPS + warp;
-  const size_t total = (size_t)S * Nl * nblk;
-  if (unit >= total) return;
-  const int b = (int)(unit % nblk);
-  const int il = (int)((unit / nblk) % Nl);
-  const int s = (int)(unit / ((size_t)nblk * Nl));
-  if (wts && wts[(size_t)b * Nl + il] == 0.0) {  // outside the block's multipole range
-    if (lane == 0) q[unit] = 0.0;
-    return;
-  }
-  const int off = blk_off[b], n = blk_n[b];
-  double* L = chism + (size_t)warp * (nmax * CHI_LD + chi_pairs_doubles(nmax));
-  unsigned short* pairs = reinterpret_cast<unsigned short*>(L + (size_t)nmax * CHI_LD);
-  chol_pairs_fill(pairs, n, lane);
-  const double* A = cls + ((size_t)s * Nl + il) * Nb * Nb;
-  double* LBu = LB + ((size_t)il * nblk + b) * nmax * nmax;
-  // lower triangle <- A (+ noise); element (r, c) of L_B, r >= c, goes to L[c][r + 1] (the free upper triangle)
-#pragma unroll 4
-  for (int i = 0; i < n; ++i)
-    for (int j = lane; j <= i; j += 32) {
-      L[i * CHI_LD + j] = A[(size_t)(off + i) * Nb + off + j] + ((i == j) ? noise[off + i] : 0.0);
-      if (!data_mode) L[j * CHI_LD + i + 1] = LBu[i * nmax + j];
+  const size_t unit = (size_t)blockIdx.x * CHR_WARPS + warp;
+  if (unit >= (size_t)S * Nl) return;
+  const int il = (int)(unit % Nl), s = (int)(unit / Nl);
+  const double* Afull = cls + ((size_t)s * Nl + il) * Nb * Nb;
+  for (int b = 0; b < B.nblk; ++b) {
+    const size_t qi = ((size_t)s * Nl + il) * B.nblk + b;
+    const bool live = wts[(size_t)b * Nl + il] != 0.0;  // inside the block's multipole range
+    if (!live) {
+      if (lane == 0) q[qi] = 0.0;
+      continue;
     }
-  __syncwarp();
-  chol_warp(L, pairs, n, CHI_LD, lane);
-  double lndet = (lane < n) ? log(L[lane * CHI_LD + lane]) : 0.0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) lndet += __shfl_xor_sync(0xffffffffu, lndet, o);
-  lndet *= 2.0;
-  if (data_mode) {  // setup pass on the data itself: keep ln det B and the factor L_B (upper triangle zero)
-    for (int i = 0; i < n; ++i)
-      for (int j = lane; j < n; j += 32) LBu[i * nmax + j] = (j <= i) ? L[i * CHI_LD + j] : 0.0;
-    if (lane == 0) q[unit] = lndet;
-    return;
-  }
-  // 1 / diagonal once, then lane i: M[:, i] = L^-1 L_B[:, i] from row i down (kept in row i of the upper triangle),
-  // accumulating |M|^2
-  if (lane < n) L[lane * CHI_LD + n + 1] = 1.0 / L[lane * CHI_LD + lane];
-  __syncwarp();
-  double tr = 0.0;
-  for (int i = lane; i < n; i += 32) {
-    double* Mi = L + i * CHI_LD + 1;  // Mi[r] = M[r][i], r >= i
-    for (int r = i; r < n; ++r) {
-      double x = Mi[r];
-      const double* Lr = L + r * CHI_LD;
-      for (int k = i; k < r; ++k) x -= Lr[k] * Mi[k];
-      x *= Lr[n + 1];
-      Mi[r] = x;
-      tr += x * x;
+    const int off = B.off[b], n = B.n[b];
+    double* LBu = LB + ((size_t)il * B.nblk + b) * nmax * nmax;
+    double tr, trl, ld, ldl;
+    if (DATA) {
+      chol_dispatch<true, NQ>(n, Afull + (size_t)off * Nb + off, Nb, nullptr, nullptr, nmax, 0, colbuf[warp], lane, tr, trl,
+                              ld, ldl, LBu);
+      if (lane == 0) q[qi] = ld;
+      continue;
+    }
+    const int par = B.parent[b];
+    if (par >= 0 && wts[(size_t)par * Nl + il] != 0.0) continue;  // written together with the parent
+    int ch = B.child[b];
+    if (ch >= 0 && wts[(size_t)ch * Nl + il] == 0.0) ch = -1;
+    chol_dispatch<false, NQ>(n, Afull + (size_t)off * Nb + off, Nb, noise + off, LBu, nmax, ch >= 0 ? B.n[ch] : 0,
+                             colbuf[warp], lane, tr, trl, ld, ldl, nullptr);
+    if (lane == 0) {
+      q[qi] = tr + ld - lndetB[(size_t)il * B.nblk + b] - (double)n;
+      if (ch >= 0) q[qi - b + ch] = trl + ldl - lndetB[(size_t)il * B.nblk + ch] - (double)B.n[ch];
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
-  if (lane == 0) q[unit] = tr + lndet - lndetB[(size_t)il * nblk + b] - (double)n;
 }
 
-__global__ void photo_chi2_reduce_kernel(int S, int Nl, int nblk, const double* __restrict__ q,
-                                         const double* __restrict__ w, double* __restrict__ chi2) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// parent / child maps of the blocks: d is a leading sub-block of c if they start at the same row and d is smaller
+static ChiBlocks chi_blocks(int nblk, const int32_t* off, const int32_t* n) {
+  ChiBlocks B;
+  B.nblk = nblk;
+  for (int b = 0; b < 8; ++b) B.off[b] = B.n[b] = 0, B.parent[b] = B.child[b] = -1;
+  for (int b = 0; b < nblk; ++b) B.off[b] = off[b], B.n[b] = n[b];
+  for (int d = 0; d < nblk; ++d)
+    for (int c = 0; c < nblk; ++c)
+      if (c != d && off[c] == off[d] && n[c] > n[d] && B.child[c] < 0 && B.parent[d] < 0 && B.parent[c] < 0) {
+        B.parent[d] = c;
+        B.child[c] = d;
+      }
+  return B;
+}
+
+// data pass (ln det B, L_B) + theory pass + multipole sum
+static cudaError_t photo_launch_chi2(cfp_ctx* ctx, cudaStream_t st, int S, int Nl, int Nb, int nblk, const int32_t* off_h,
+                                     const int32_t* n_h, int nmax, const double* theory_d, const double* noise_d,
+                                     const double* data_d, const double* w_d, double* lb_d, double* lndet_d, double* q_d,
+                                     double* chi2_d);
+
+// chi2[s] = sum over (multipole, block) of w q, one warp per point: lanes stride over the point's contiguous q row
+// (coalesced), fixed-order shuffle tree
+__global__ void __launch_bounds__(128) photo_chi2_reduce_kernel(int S, int Nl, int nblk, const double* __restrict__ q,
+                                                                const double* __restrict__ w, double* __restrict__ chi2) {
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= S) return;
+  const double* qs = q + (size_t)s * Nl * nblk;
   double acc = 0.0;
-  for (int b = 0; b < nblk; ++b)
-    for (int l = 0; l < Nl; ++l) {
-      const double wl = w[(size_t)b * Nl + l];
-      if (wl != 0.0) acc += wl * q[((size_t)s * Nl + l) * nblk + b];
-    }
-  chi2[s] = acc;
+  for (int e = lane; e < Nl * nblk; e += 32) {
+    const int l = e / nblk, b = e - l * nblk;
+    const double wl = w[(size_t)b * Nl + l];
+    if (wl != 0.0) acc += wl * qs[e];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) chi2[s] = acc;
 }
 
 __global__ void photo_add_noise_kernel(int Nl, int Nb, const double* __restrict__ cls0, const double* __restrict__ noise,
@@ -637,6 +735,43 @@ __global__ void photo_add_noise_kernel(int Nl, int Nb, const double* __restrict_
   data[e] = cls0[e] + ((ij / Nb == ij % Nb) ? noise[ij / Nb] : 0.0);
 }
 
+}  // namespace
+
+namespace {
+cudaError_t photo_launch_chi2(cfp_ctx* ctx, cudaStream_t st, int S, int Nl, int Nb, int nblk, const int32_t* off_h,
+                              const int32_t* n_h, int nmax, const double* theory_d, const double* noise_d,
+                              const double* data_d, const double* w_d, double* lb_d, double* lndet_d, double* q_d,
+                              double* chi2_d) {
+  const ChiBlocks B = chi_blocks(nblk, off_h, n_h);
+  const unsigned g_data = (unsigned)(((size_t)Nl + CHR_WARPS - 1) / CHR_WARPS);
+  const unsigned g_th = (unsigned)(((size_t)S * Nl + CHR_WARPS - 1) / CHR_WARPS);
+#define CHI_LAUNCH(Q)                                                                                                  \
+  case Q:                                                                                                              \
+    photo_chi2_reg_kernel<true, Q><<<g_data, CHR_WARPS * 32, 0, st>>>(1, Nl, Nb, B, data_d, nullptr, w_d, lb_d, nullptr, \
+                                                                      nmax, lndet_d);                                  \
+    photo_chi2_reg_kernel<false, Q><<<g_th, CHR_WARPS * 32, 0, st>>>(S, Nl, Nb, B, theory_d, noise_d, w_d, lb_d,        \
+                                                                     lndet_d, nmax, q_d);                              \
+    break;
+  switch ((nmax + 3) / 4) {
+    CHI_LAUNCH(1)
+    CHI_LAUNCH(2)
+    CHI_LAUNCH(3)
+    CHI_LAUNCH(4)
+    CHI_LAUNCH(5)
+    CHI_LAUNCH(6)
+    CHI_LAUNCH(7)
+    default:
+      photo_chi2_reg_kernel<true, 8><<<g_data, CHR_WARPS * 32, 0, st>>>(1, Nl, Nb, B, data_d, nullptr, w_d, lb_d, nullptr, nmax,
+                                                                        lndet_d);
+      photo_chi2_reg_kernel<false, 8><<<g_th, CHR_WARPS * 32, 0, st>>>(S, Nl, Nb, B, theory_d, noise_d, w_d, lb_d, lndet_d,
+                                                                       nmax, q_d);
+      break;
+  }
+#undef CHI_LAUNCH
+  photo_chi2_reduce_kernel<<<(S + 3) / 4, 128, 0, st>>>(S, Nl, nblk, q_d, w_d, chi2_d);
+  ctx->launches += 3;
+  return cudaGetLastError();
+}
 }  // namespace
 
 struct cfp_photo_plan {
@@ -1111,33 +1246,14 @@ extern "C" int cfp_photo_plan_chi2(cfp_photo_plan* pl, const double* data_h, int
   }
   int nmax = 1;
   for (int b = 0; b < nblk; ++b) nmax = std::max(nmax, (int)blk_n_h[b]);
-  const size_t chi_smem = (size_t)CHI_WARPS * (nmax * chi_ld(nmax) + chi_pairs_doubles(nmax)) * sizeof(double);
-  if (cudaFuncSetAttribute(photo_chi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chi_smem) != cudaSuccess) {
-    cfp_set_error("cfp_photo_plan_chi2: cannot reserve %zu B of shared memory", chi_smem);
-    cleanup();
-    return CFP_ERR_CUDA;
-  }
-  // ln det of the data blocks: the same kernel on a zero-noise "theory" = data
   double *zero_d = nullptr, *lb_d = nullptr;
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nb, &zero_d));
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nl * nblk * nmax * nmax, &lb_d));
   if (st != ctx->stream) cudaStreamSynchronize(ctx->stream);
-  {
-    const size_t units = (size_t)Nl * nblk;
-    photo_chi2_kernel<<<(unsigned)((units + CHI_WARPS - 1) / CHI_WARPS), CHI_WARPS * 32, chi_smem, st>>>(
-        1, Nl, Nb, nblk, off_d, n_d, data_d, zero_d, w_d, lb_d, nullptr, 1, nmax, lndet_d);
-    ctx->launches++;
-  }
-  {
-    const size_t units = (size_t)S * Nl * nblk;
-    photo_chi2_kernel<<<(unsigned)((units + CHI_WARPS - 1) / CHI_WARPS), CHI_WARPS * 32, chi_smem, st>>>(
-        S, Nl, Nb, nblk, off_d, n_d, pl->cls_d, pl->noise_d, w_d, lb_d, lndet_d, 0, nmax, q_d);
-    ctx->launches++;
-    photo_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Nl, nblk, q_d, w_d, chi2_d);
-    ctx->launches++;
-  }
+  // ln det and Cholesky factor of the data blocks, then every (point, multipole), then the multipole sums
+  cudaError_t e = photo_launch_chi2(ctx, st, S, Nl, Nb, nblk, blk_off_h, blk_n_h, nmax, pl->cls_d, pl->noise_d, data_d, w_d,
+                                    lb_d, lndet_d, q_d, chi2_d);
   cudaEventRecord(pl->run1, st);
-  cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(chi2_h, chi2_d, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   float ms = 0.f;
@@ -1225,19 +1341,8 @@ extern "C" int cfp_cells_chi2(cfp_ctx* ctx, int S, int Nl, int Nb, const double*
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d));
   CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nl * nblk * nmax * nmax, &lb_d));
 #undef CHI_TRY
-  const size_t chi_smem = (size_t)CHI_WARPS * (nmax * chi_ld(nmax) + chi_pairs_doubles(nmax)) * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(photo_chi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chi_smem);
-  if (e == cudaSuccess) {
-    size_t units = (size_t)Nl * nblk;
-    photo_chi2_kernel<<<(unsigned)((units + CHI_WARPS - 1) / CHI_WARPS), CHI_WARPS * 32, chi_smem, st>>>(
-        1, Nl, Nb, nblk, off_d, n_d, data_d, zero_d, w_d, lb_d, nullptr, 1, nmax, lndet_d);
-    units = (size_t)S * Nl * nblk;
-    photo_chi2_kernel<<<(unsigned)((units + CHI_WARPS - 1) / CHI_WARPS), CHI_WARPS * 32, chi_smem, st>>>(
-        S, Nl, Nb, nblk, off_d, n_d, th_d, zero_d, w_d, lb_d, lndet_d, 0, nmax, q_d);
-    photo_chi2_reduce_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, Nl, nblk, q_d, w_d, chi2_d);
-    ctx->launches += 3;
-    e = cudaGetLastError();
-  }
+  cudaError_t e = photo_launch_chi2(ctx, st, S, Nl, Nb, nblk, blk_off_h, blk_n_h, nmax, th_d, zero_d, data_d, w_d, lb_d, lndet_d,
+                                    q_d, chi2_d);
   if (e == cudaSuccess) e = cudaMemcpyAsync(chi2_h, chi2_d, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cleanup();

@@ -989,7 +989,7 @@ __global__ void __launch_bounds__(1024) spectro_reduce_kernel(const double* __re
 // Work: tasks = (segment of rows) x (group of 4 wavenumbers), dealt round-robin to the warps of the grid in a fixed
 // order (deterministic partial sums); one CTA per SM; partial[zb][cta][80].
 constexpr int PK_MAXROWS = 136;  // mu rows staged at once (16 x 48 B each)
-constexpr int WG_ROWS = 16;      // mu rows per CTA of the weights pre-pass
+constexpr int WG_ROWS = 64;      // most mu rows a CTA of the weights pre-pass walks
 
 struct RowP {    // row constants of the pair kernel, per (row, q)
   double G;      // k' / k
@@ -1045,7 +1045,9 @@ __device__ __forceinline__ double pair_exp_neg(const MathTab& mt, double x) {
   const double q0 = r + 1.0;
   const double q1 = fma(r, CFP_TEXP[7], 0.5);
   const double q2 = fma(r, CFP_TEXP[5], CFP_TEXP[6]);
-  double p = fma(CFP_TEXP[4], r2, q2);
+  // (1/720 with a zero low word: the r^6 term is below 2e-15, 20 mantissa bits are plenty, and a constant without
+  // low word is an immediate operand instead of a constant-bank load)
+  double p = fma(__hiloint2double(0x3F56C16C, 0), r2, q2);
   p = fma(p, r2, q1);
   p = fma(p, r2, q0);
   p *= tj;
@@ -1068,21 +1070,32 @@ __device__ __forceinline__ void pair_eval(const MathTab& mt, const PRec& r, cons
 __constant__ double CFP_ATANH[4] = {1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0};
 
 // {w, dps}[zb][row - row_lo][k]: quadrature weight x 2 V veff of the cell on the fiducial spectrum, and the
-// shot-noise derivative 1 / P_obs (0 if the bin has no shot-noise parameter).  grid (k blocks, Z, row segments).
-__global__ void __launch_bounds__(TILE) spectro_weights_kernel(SpectroParams P, int row_lo, int nrows,
+// shot-noise derivative 1 / P_obs (0 if the bin has no shot-noise parameter).  grid (k blocks, Z, row segments);
+// a thread walks down `seglen` rows of its wavenumber with the fiducial's piece records in registers.
+__global__ void __launch_bounds__(TILE) spectro_weights_kernel(SpectroParams P, int row_lo, int nrows, int seglen,
                                                                double2* __restrict__ wd) {
   const int zb = blockIdx.y;
   if (!P.pairs[zb].ok) return;
   __shared__ SDev sp;
-  __shared__ RowC rows[WG_ROWS];
+  __shared__ RowP rows[WG_ROWS];
+  __shared__ double wmu[WG_ROWS];
   __shared__ MathTab mt;
   const int tid = threadIdx.x;
   if (tid < (int)(sizeof(SDev) / sizeof(double)))
     reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S)[tid];
   math_tables_fill(mt, tid, TILE);
   __syncthreads();
-  const int r0 = blockIdx.z * WG_ROWS, nr = min(WG_ROWS, nrows - r0);
-  if (tid < nr) rows[tid] = row_consts(sp, P.flags, __ldg(P.mu + row_lo + r0 + tid), __ldg(P.smu + row_lo + r0 + tid));
+  const int r0 = blockIdx.z * seglen, nr = min(seglen, nrows - r0);
+  if (tid < nr) {
+    const int row = row_lo + r0 + tid;
+    const RowC rc = row_consts(sp, P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
+    RowP rp;
+    rp.G = rc.G, rp.fmu2 = rc.fmu2, rp.errc2 = rc.errc * rc.errc, rp.nsvg = -rc.sv2 * (rc.G * rc.G);
+    const double gf = rc.G * rc.fogc;
+    rp.fg2 = gf * gf, rp.pad = 0.0;
+    rows[tid] = rp;
+    wmu[tid] = __ldg(P.wmu + row);
+  }
   __syncthreads();
   const int ki = blockIdx.x * TILE + tid;
   const int ldk = ((P.Nk + 3) >> 2) << 2;  // rows padded to whole groups of four wavenumbers (zero weight)
@@ -1094,27 +1107,43 @@ __global__ void __launch_bounds__(TILE) spectro_weights_kernel(SpectroParams P, 
   const PairPlan& plan = P.pairs[zb];
   const int ps_sel = plan.ps_sel;
   const bool has_ps = plan.par[8] >= 0;
-  const double bsrc = ps_sel == 0 ? sp.bias : P.sdev[(size_t)zb * P.S + plan.pt[(ps_sel == 1 ? 0 : 8) + 7]].bias;
+  const double bias0 = sp.bias;
+  const double bsrc = ps_sel == 0 ? bias0 : P.sdev[(size_t)zb * P.S + plan.pt[(ps_sel == 1 ? 0 : 8) + 7]].bias;
   const double nbar = P.nbar[zb], vol2 = 2.0 * P.vol[zb];
   const double k = __ldg(P.k + ki);
-  const double wcol = (k * k) * __ldg(P.wk + ki);
-  int hA = -1, hB = -1, hN = -1;
-  for (int r = 0; r < nr; ++r) {
-    const int row = row_lo + r0 + r;
-    double err2, qf, F, W;
-    const double X0 = eval_x(mt, sp, rows[r], P.flags, k, hA, hB, hN, err2, qf, F, W);
-    const double e = tab_exp_neg(mt, -err2);
-    const double P0 = X0 * e;
-    const double ks = fma(bsrc, qf, F);
-    const double Psrc = ps_sel == 0 ? P0 : ((ks * ks) * W) * e;
+  const double k2 = k * k;
+  const double wcol = k2 * __ldg(P.wk + ki);
+  PRec A;
+  A.loA = A.loN = 0.0;
+  A.wA = A.wN = 0u;
+  A.a0 = A.a1 = A.a2 = A.a3 = A.f0 = A.f1 = A.f2 = A.f3 = A.c0 = A.sl = 0.0;
+  int hA = -1, hN = -1;
+  double2* out = wd + ((size_t)zb * nrows + r0) * ldk + ki;
+  int64_t cell = (int64_t)(row_lo + r0) * P.Nk + ki;
+  for (int r = 0; r < nr; ++r, out += ldk, cell += P.Nk) {
+    const RowP& rc = rows[r];
+    const double kap = k * rc.G;
+    double u = kap - A.loA;
+    const double v = kap - A.loN;
+    if (!((unsigned)__double2hiint(u) < A.wA)) pair_fetch_cubic(A, sp, kap, hA), u = kap - A.loA;
+    if (!((unsigned)__double2hiint(v) < A.wN)) pair_fetch_line(A, sp, kap, hN);
+    const double pdd = fma(u, fma(u, fma(u, A.a3, A.a2), A.a1), A.a0);
+    const double F = fma(u, fma(u, fma(u, A.f3, A.f2), A.f1), A.f0) * rc.fmu2;
+    const double pnw = fma(A.sl, kap, A.c0);
+    const double dw = fma(pair_exp_neg(mt, k2 * rc.nsvg), pdd - pnw, pnw);
+    // X e^{-err^2} / FoG denominator
+    const double damp = pair_exp_neg(mt, -(k2 * rc.errc2)) * fast_rcp(fma(k2, rc.fg2, 1.0));
+    const double k0 = bias0 + F;
+    const double P0 = ((k0 * k0) * dw) * damp;
+    const double ks = bsrc + F;
+    const double Psrc = ((ks * ks) * dw) * damp;  // (= P0 unless the bias pair's point is the source)
     const double npobs = nbar * P0;
-    const double rr = fast_div(npobs, 1.0 + npobs);
+    const double rr = npobs * fast_rcp(1.0 + npobs);
     const double veff = INV_8PI2 * rr * rr;  // spectro_cov.py:223-225
-    const int64_t cell = (int64_t)row * P.Nk + ki;
     const bool valid = cell >= P.cell_begin && cell < P.cell_end;
     // cosmicfish.py:541: k^2 * 2 * V_survey * veff, times the Simpson weights of :510-511
-    const double w = valid ? (vol2 * veff) * (__ldg(P.wmu + row) * wcol) : 0.0;
-    wd[((size_t)zb * nrows + (r0 + r)) * ldk + ki] = make_double2(w, has_ps ? fast_rcp(Psrc) : 0.0);  // spectro_cov.py:510-532
+    const double w = valid ? (vol2 * veff) * (wmu[r] * wcol) : 0.0;
+    *out = make_double2(w, has_ps ? fast_rcp(Psrc) : 0.0);  // spectro_cov.py:510-532
   }
 }
 
@@ -1217,7 +1246,8 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 1)
         {
           const double t = (num_p - dnm_p) * fast_rcp(num_p + dnm_p);
           const double t2 = t * t;
-          double p = fma(CFP_ATANH[0], t2, CFP_ATANH[1]);
+          // (1/9 and 1/7 truncated to a zero low word -- immediates; their terms are below 1e-13 and 1e-10 of t)
+          double p = fma(__hiloint2double(0x3FBC71C7, 0), t2, __hiloint2double(0x3FC24925, 0));
           p = fma(p, t2, CFP_ATANH[2]);
           p = fma(p, t2, CFP_ATANH[3]);
           double lnr = fma(p * t2, t + t, t + t);
@@ -1261,10 +1291,11 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 1)
 }
 
 // F[zb] of the bins the pair kernel took: internal order (slots 0..7, shot noise) -> parameters, zeros elsewhere.
-// One CTA per bin, one thread per element of the lower triangle; the CTA partials are summed in a fixed order.
-__global__ void __launch_bounds__(256) spectro_reduce_pairs_kernel(const double* __restrict__ partial, int ncta,
-                                                                   int npar, const PairPlan* __restrict__ pairs,
-                                                                   double* __restrict__ F) {
+// grid (Z); one warp per element of the lower triangle, lanes over the CTA partials (fixed order: lane l adds CTAs
+// l, l + 32, ..., then a shuffle tree).
+__global__ void __launch_bounds__(1024) spectro_reduce_pairs_kernel(const double* __restrict__ partial, int ncta,
+                                                                    int npar, const PairPlan* __restrict__ pairs,
+                                                                    double* __restrict__ F) {
   const int zb = blockIdx.x;
   const PairPlan& plan = pairs[zb];
   if (!plan.ok) return;
@@ -1276,7 +1307,8 @@ __global__ void __launch_bounds__(256) spectro_reduce_pairs_kernel(const double*
     inv[p] = a;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < npar * npar; e += blockDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int e = warp; e < npar * npar; e += nwarp) {
     const int i = e / npar, j = e - i * npar;
     if (j > i) continue;
     const int ai = inv[i], aj = inv[j];
@@ -1285,10 +1317,14 @@ __global__ void __launch_bounds__(256) spectro_reduce_pairs_kernel(const double*
       const int hi = max(ai, aj), lo = min(ai, aj);
       // [tile of the 8 slots: fragment order][F[8][slot]][F[8][8]]
       const int el = hi < 8 ? (hi * 4 + (lo >> 1)) * 2 + (lo & 1) : (lo < 8 ? 64 + lo : 72);
-      for (int c = 0; c < ncta; ++c) s += partial[((size_t)zb * ncta + c) * 80 + el];
+      for (int c = lane; c < ncta; c += 32) s += partial[((size_t)zb * ncta + c) * 80 + el];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     }
-    F[((size_t)zb * npar + i) * npar + j] = s;
-    F[((size_t)zb * npar + j) * npar + i] = s;
+    if (lane == 0) {
+      F[((size_t)zb * npar + i) * npar + j] = s;
+      F[((size_t)zb * npar + j) * npar + i] = s;
+    }
   }
 }
 
@@ -2054,7 +2090,7 @@ static int spectro_prepare(cfp_spectro_plan* pl, const SpectroParams& P, cudaStr
   pp.pnw_k = pl->pnw_k_d, pp.pnw_p = pl->pnw_p_d, pp.blknw = pl->blknw_d;
   const size_t cls_bytes = (P.materialize & 16) ? 0 : (size_t)pl->S * sizeof(int);
   CFP_REQUIRE(cls_bytes <= 40 * 1024, "too many stencil points for a Fisher work list (batch mode has no limit)");
-  spectro_prepare_kernel<<<dim3(pl->NC * pl->Z, 4), 128, cls_bytes, st>>>(pp, P, pl->Z);
+  spectro_prepare_kernel<<<dim3(pl->NC * pl->Z, 4), 512, cls_bytes, st>>>(pp, P, pl->Z);
   ctx->launches++;
   CFP_CUDA(cudaGetLastError());
   return CFP_OK;
@@ -2453,8 +2489,14 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
       const double eff = (double)tasks / (double)(((tasks + nwarps - 1) / nwarps) * nwarps);
       if (eff > best + 0.02) best = eff, nseg = c;
     }
-    spectro_weights_kernel<<<dim3((pl->Nk + TILE - 1) / TILE, pl->Z, (nrows + WG_ROWS - 1) / WG_ROWS), TILE, 0, st>>>(
-        P, row_lo, nrows, pl->wd_d);
+    {
+      // row segments: as many as keep the grid within ONE wave of resident CTAs (3 per SM), at most WG_ROWS rows each
+      const int kb = (pl->Nk + TILE - 1) / TILE;
+      const int wsegs = std::min(nrows, std::max((nrows + WG_ROWS - 1) / WG_ROWS, (ctx->sm_count * 3) / (kb * pl->Z)));
+      const int wlen = (nrows + wsegs - 1) / wsegs;
+      spectro_weights_kernel<<<dim3((pl->Nk + TILE - 1) / TILE, pl->Z, wsegs), TILE, 0, st>>>(P, row_lo, nrows, wlen,
+                                                                                            pl->wd_d);
+    }
     ctx->launches++;
     const size_t smem2 = std::max((size_t)srows * 16 * sizeof(RowP), (size_t)pk_warps * 80 * sizeof(double)) + sizeof(MathTab) +
                          16 * sizeof(SDev) + sizeof(PairPlan);
@@ -2516,7 +2558,7 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
     ctx->launches++;
   }
   if (try_pairs) {
-    spectro_reduce_pairs_kernel<<<pl->Z, 256, 0, st>>>(pl->partial2_d, gx2, pl->npar, pl->pairs_d, pl->fisher_d);
+    spectro_reduce_pairs_kernel<<<pl->Z, 1024, 0, st>>>(pl->partial2_d, gx2, pl->npar, pl->pairs_d, pl->fisher_d);
     ctx->launches++;
   }
   CFP_CUDA(cudaGetLastError());

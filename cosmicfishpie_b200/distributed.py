@@ -44,20 +44,74 @@ def shard(fm, rank: int, world: int):
     return fm
 
 
-def allreduce_numpy(a: np.ndarray) -> np.ndarray:
-    """Sum a host array over all ranks (NCCL: staged through the current CUDA device; gloo: CPU)."""
+def allreduce_numpy(a: np.ndarray, device=None) -> np.ndarray:
+    """Sum a host array over all ranks (NCCL: staged through CUDA device `device`, default LOCAL_RANK --
+    the device of the cfp context, not torch's current device; gloo: CPU)."""
     if not is_distributed():
         return a
+    import os
+
     import torch
     import torch.distributed as dist
 
     t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
     if dist.get_backend() == "nccl":
-        t = t.cuda()
+        dev = int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device)
+        t = t.cuda(dev)
         dist.all_reduce(t)
         return t.cpu().numpy()
     dist.all_reduce(t)
     return t.numpy()
+
+
+def allreduce_plan_result(plan, shape) -> bool:
+    """Sum the Fisher result buffer of a cfp plan over all ranks IN PLACE on the device (one NCCL all-reduce over
+    NVLink on the plan's own device buffer).  Returns False when there is nothing to do on the device
+    (single process, or a gloo group: the caller then reduces the fetched host array)."""
+    if not is_distributed():
+        return False
+    import torch
+    import torch.distributed as dist
+
+    if dist.get_backend() != "nccl":
+        return False
+    ctx = plan.ctx
+    ctx.sync()  # the plan ran on the context's stream, the collective runs on torch's
+    t = device_view(plan.fisher_device_ptr(), shape, ctx.device)
+    with torch.cuda.device(ctx.device):
+        dist.all_reduce(t)
+        torch.cuda.current_stream().synchronize()
+    return True
+
+
+def barrier():
+    if is_distributed():
+        import torch.distributed as dist
+
+        dist.barrier()
+
+
+def allgather_numpy(a: np.ndarray, device=None) -> np.ndarray:
+    """Concatenate equally shaped 1-D host arrays of all ranks in rank order (NCCL all_gather staged through the
+    cfp device, or gloo on the host).  Used by the sharded likelihood batches."""
+    if not is_distributed():
+        return a
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+    world = dist.get_world_size()
+    if dist.get_backend() == "nccl":
+        dev = int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device)
+        t = t.cuda(dev)
+        out = torch.empty(world * t.numel(), dtype=torch.float64, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy()
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    return torch.cat(parts).numpy()
 
 
 class _DevArray:

@@ -160,9 +160,11 @@ class FisherMatrix:
         plan = job.plan()
         plan.set_slice(*cdist.split_range(self.Pk_ksamp * self.Pk_musamp, rank, world))
         plan.run(materialize=0)
+        # partial Fisher matrices of the slices: one all-reduce on the plan's own device buffer (NCCL), then one D2H
+        reduced = world > 1 and cdist.allreduce_plan_result(plan, (plan.Z, plan.npar, plan.npar))
         Fz, _, _, _ = plan.fetch()
-        if world > 1:
-            Fz = cdist.allreduce_numpy(Fz)
+        if world > 1 and not reduced:
+            Fz = cdist.allreduce_numpy(Fz, device=getattr(getattr(plan, "ctx", None), "device", None))  # (gloo group, or no process group at all: no-op)
         plan.set_slice(0, self.Pk_ksamp * self.Pk_musamp)
         t2 = time()
         self.timings.update(host_prep_s=t1 - t0, device_s=t2 - t1,
@@ -308,16 +310,28 @@ class FisherMatrix:
         cols = list(self.freeparams)
         os.makedirs(self.settings["results_dir"], exist_ok=True)
         root = self.settings["results_dir"] + "/" + self.cf_version + "_" + self.settings["outroot"] + "_" + obstring + "_FM"
-        with open(root + self.settings["fishermatrix_file_extension"], "w") as f:
-            f.write("#" + " ".join(["", *cols]) + "\n")
-            for row in np.asarray(fishmat):
-                f.write("\t".join(repr(float(v)) for v in row) + "\n")
-        with open(root + ".paramnames", "w") as f:
-            f.write("#\n#\n# This file contains the parameter names for a derived Fisher matrix.\n#\n")
-            for par in cols:
-                f.write(str(par) + "    " + str(self.latex_names.get(par, str(par))) + "    "
-                        + "{:.6f}".format(self.allparams[par]) + "\n")
+        # Under torchrun every rank holds the same reduced matrix and runs this method.  Files are written to a
+        # rank-private temporary name and moved into place atomically, so a rank can never read another rank's
+        # half-written file; the result object of every rank is built from the text it wrote itself (repr round-trip,
+        # exactly what re-reading the file gives).
+        rank = (self._shard if self._shard is not None else cdist.rank_world())[0]
+        tag = ".tmp%d_%d" % (rank, os.getpid())
+
+        def write_atomic(path, text):
+            with open(path + tag, "w") as f:
+                f.write(text)
+            os.replace(path + tag, path)
+
+        fm_text = "#" + " ".join(["", *cols]) + "\n" + "".join(
+            "\t".join(repr(float(v)) for v in row) + "\n" for row in np.atleast_2d(np.asarray(fishmat)))
+        pn_text = "#\n#\n# This file contains the parameter names for a derived Fisher matrix.\n#\n" + "".join(
+            str(par) + "    " + str(self.latex_names.get(par, str(par))) + "    " + "{:.6f}".format(self.allparams[par]) + "\n"
+            for par in cols)
+        write_atomic(root + self.settings["fishermatrix_file_extension"], fm_text)
+        write_atomic(root + ".paramnames", pn_text)
         out = fm.fisher_matrix(file_name=root + ".txt")
+        if rank != 0 and cdist.is_distributed():
+            return out  # the specification files are rank 0's business
         git = self._git_version()
         with open(root + "_specs.dat", "w") as f:
             f.write("**Git version commit: %s \n" % git)

@@ -240,14 +240,21 @@ class PhotometricLikelihood(Likelihood, NautilusMixin):
         return float(ctx.cells_chi2(self._full_from_cells(theory_obs)[None], self._data_full, off, n, w)[0])
 
     def chi2_matrix(self, names, matrix) -> np.ndarray:
-        known = set(self.cosmo_theory.fiducialcosmopars) | set(self.cosmo_theory.IApars) | set(self.cosmo_theory.photobiaspars)
+        fmt = self.cosmo_theory
+        known = set(fmt.fiducialcosmopars) | set(fmt.IApars) | set(fmt.photobiaspars) | set(fmt.photopars)
         keep = [i for i, n in enumerate(names) if n in known]  # unused parameters are ignored, as in the reference
         names = [names[i] for i in keep]
         matrix = np.ascontiguousarray(np.atleast_2d(matrix)[:, keep])
+        if any(n in fmt.photopars for n in names):
+            # photo-z parameters change the n_i(z) windows of a point (photo_like.py compute_theory updates photopars):
+            # the array fast path has one window set per job, so these batches go point by point
+            return self.chi2_batch([dict(zip(names, row)) for row in matrix])
         off, n, w = self._blocks()
         out = np.empty(matrix.shape[0])
         chunk = 4096
         spans = [(i, min(i + chunk, matrix.shape[0])) for i in range(0, matrix.shape[0], chunk)]
+        # (between batches, never between the pipelined chunks of one: a running chunk holds the bank)
+        photo_mod._cosmo_set_of(photo_mod._cfg_of(fmt)[1]).begin_batch()
         if len(spans) == 1:
             job = photo_mod.PhotoJob.from_matrix(self.cosmo_theory, names, matrix)
             out[:] = job.plan().chi2(off, n, w, data=self._data_full)
@@ -449,7 +456,7 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
                 pk, pp = spectro_mod._pnw_arrays(cs, zs, set() if pts[0].linear_switch else used)
                 tabs = spectro_mod.table_slots(fm.settings)
                 plan = _lib.SpectroPlan(
-                    cs.ctx or _lib.default_context(), cs.bank(), k=fm.Pk_kgrid, mu=fm.Pk_mugrid,
+                    cs.context(), cs.bank(), k=fm.Pk_kgrid, mu=fm.Pk_mugrid,
                     wk=simpson_weights(fm.Pk_kgrid), wmu=simpson_weights(fm.Pk_mugrid), scal=scal,
                     alias=np.tile(np.arange(S, dtype=np.int32)[:, None], (1, Z)), pnw_k=pk, pnw_p=pp,
                     stw=np.zeros((1, S)), stden=np.ones(1), ps_bin=np.array([-1], np.int32), ps_src=0,
@@ -475,6 +482,7 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
             return self.chi2_batch([dict(zip(names, row)) for row in matrix])
         fid_obs = fm.pk_obs_fid
         cs = fid_obs.cosmo_set
+        cs.begin_batch()
         zs = list(fm.pk_cov.global_z_bin_mids)
         matrix = np.atleast_2d(np.asarray(matrix, dtype=float))
         B, Z = matrix.shape[0], len(zs)
@@ -529,7 +537,7 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
         for i0 in range(0, B, chunk):
             S = min(chunk, B - i0)
             plan = _lib.SpectroPlan(
-                cs.ctx or _lib.default_context(), cs.bank(), k=fm.Pk_kgrid, mu=fm.Pk_mugrid, wk=wk, wmu=wmu,
+                cs.context(), cs.bank(), k=fm.Pk_kgrid, mu=fm.Pk_mugrid, wk=wk, wmu=wmu,
                 scal=scal[i0:i0 + S], alias=np.tile(np.arange(S, dtype=np.int32)[:, None], (1, Z)), pnw_k=pk, pnw_p=pp,
                 stw=np.zeros((1, S)), stden=np.ones(1), ps_bin=np.array([-1], np.int32), ps_src=0, nbar=nbar,
                 vol=fm.pk_cov.volume_survey_array, flags=fid_obs.flags(),
@@ -558,7 +566,7 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
             used = {int(c) for c in scal[:, :, _lib.SP_COSMO].ravel()}
             pk, pp = spectro_mod._pnw_arrays(cs, zs, set() if pts[0].linear_switch else used)
             plan = _lib.SpectroPlan(
-                cs.ctx or _lib.default_context(), cs.bank(), k=fm.Pk_kgrid, mu=fm.Pk_mugrid,
+                cs.context(), cs.bank(), k=fm.Pk_kgrid, mu=fm.Pk_mugrid,
                 wk=simpson_weights(fm.Pk_kgrid), wmu=simpson_weights(fm.Pk_mugrid), scal=scal,
                 alias=np.tile(np.arange(S, dtype=np.int32)[:, None], (1, Z)), pnw_k=pk, pnw_p=pp, stw=np.zeros((1, S)),
                 stden=np.ones(1), ps_bin=np.array([-1], np.int32), ps_src=0,

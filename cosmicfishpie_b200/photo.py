@@ -402,7 +402,7 @@ class PhotoJob:
         if self._plan is None:
             g, cs = self.grid, self.cosmo_set
             self._plan = _lib.PhotoPlan(
-                cs.ctx or _lib.default_context(), cs.bank(), cosmo_of_s=self.cosmo_of_s, ell=g.ell, z=g.z, dz=g.dz,
+                cs.context(), cs.bank(), cosmo_of_s=self.cosmo_of_s, ell=g.ell, z=g.z, dz=g.dz,
                 chi=self.chi, hub=self.hub, wlpref=self.wlpref, kind=g.kind, ngal=self.ngal, bias=self.bias,
                 ia=self.ia, lmin=g.lmin, lmax=g.lmax, noise=g.noise, sqrtfsky=g.sqrtfsky, stw=self.stw,
                 stden=self.stden, kmax=g.kmax, tab_p=g.tab_p, zmap=getattr(self, "zmap", None),
@@ -603,9 +603,11 @@ class PhotoCov:
         nbins = plan.Nl - 1
         plan.set_slice(*cdist.split_range(nbins, rank, world))
         plan.run()
+        reduced = world > 1 and cdist.allreduce_plan_result(plan, (plan.npar, plan.npar))  # NCCL, in place on the device
         F, _, _ = plan.fetch()
         if world > 1:
-            F = cdist.allreduce_numpy(F)
+            if not reduced:
+                F = cdist.allreduce_numpy(F, device=getattr(getattr(plan, "ctx", None), "device", None))
             plan.set_slice(0, nbins)
             plan.run()  # every rank keeps the full C_ell set for compute_covmat()/compute_derivs()
         if self.stencil == "STEM":

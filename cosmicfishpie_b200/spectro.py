@@ -401,7 +401,7 @@ def _evaluate_lattice(points: List[ComputeGalSpectro], zs, kgrid, mugrid, b_i=No
     used = {p.cosmo_index for p in points}
     pk, pp = _pnw_arrays(cs, zs, set() if linear else used)
     plan = _lib.SpectroPlan(
-        cs.ctx or _lib.default_context(), cs.bank(), k=kgrid, mu=mugrid, wk=np.zeros_like(kgrid),
+        cs.context(), cs.bank(), k=kgrid, mu=mugrid, wk=np.zeros_like(kgrid),
         wmu=np.zeros_like(mugrid), scal=scal, alias=alias, pnw_k=pk, pnw_p=pp, stw=np.zeros((1, S)),
         stden=np.ones(1), ps_bin=np.array([-1], dtype=np.int32), ps_src=0, nbar=np.zeros(Z), vol=np.zeros(Z),
         flags=points[0].flags(), tab_plin=table_slots(points[0].settings)[0], tab_f=table_slots(points[0].settings)[1])
@@ -569,7 +569,7 @@ class SpectroJob:
         if self._plan is None:
             cs = self.cosmo_set
             self._plan = _lib.SpectroPlan(
-                cs.ctx or _lib.default_context(), cs.bank(), k=self.kgrid, mu=self.mugrid, wk=self.wk, wmu=self.wmu,
+                cs.context(), cs.bank(), k=self.kgrid, mu=self.mugrid, wk=self.wk, wmu=self.wmu,
                 scal=self.scal, alias=self.alias, pnw_k=self.pnw_k, pnw_p=self.pnw_p, stw=self.stw, stden=self.stden,
                 ps_bin=self.ps_bin, ps_src=self.ps_src, nbar=self.nbar, vol=self.vol, flags=self.flags,
                 tab_plin=self.tabs[0], tab_f=self.tabs[1])

@@ -53,5 +53,30 @@ def main():
                 print(f"{label}: {flag} {keys[0]}.. B={B}: device ms {np.mean(t):.3f}  sum loglike {np.sum(ll):.12e}")
 
 
+def photo():
+    """device time of photometric likelihood chunks (13+13 bins): python tools/ab_kernel.py label photo [B]"""
+    from cosmicfishpie_b200.likelihood import PhotometricLikelihood
+    import time
+
+    label = sys.argv[1]
+    B = int(sys.argv[3]) if len(sys.argv) > 3 else 8192
+    tmp = tempfile.mkdtemp(prefix="cfp_ab_")
+    fm = bench.make_photo_fm(tt.make_bank(eps_values=(0.01,)), tmp)
+    fm.compute()
+    like = PhotometricLikelihood(cosmo_data=fm)
+    keys = [k for k in fm.freeparams if k not in bench.P7]
+    fid = np.array([fm.allparams[k] for k in keys])
+    mat = fid * (1.0 + 0.02 * np.random.default_rng(1).standard_normal((B, len(keys))))
+    ll = like.loglike_batch(mat, keys=keys)
+    ctx = fm.ctx
+    t0 = time.perf_counter()
+    ll = like.loglike_batch(mat, keys=keys)
+    dt = time.perf_counter() - t0
+    print(f"{label}: photo likelihood B={B}: {B / dt:.0f} evals/s wall, device ms of the last chunk {ctx.last_run_ms:.3f}, sum {np.sum(ll):.12e}")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[2] == "photo":
+        photo()
+    else:
+        main()
