@@ -36,7 +36,8 @@ EXPORTS = [
     "cfp_legendre_project", "cfp_legendre_covariance", "cfp_legendre_chi2",
     "cfp_bank_upload_rows", "cfp_host_alloc", "cfp_host_free", "cfp_spectro_plan_chi2_dev", "cfp_dev_upload",
     "cfp_dev_release", "cfp_photo_plan_create_zmap", "cfp_ctx_aux_stream", "cfp_photo_plan_create_ex",
-    "cfp_photo_plan_set_gc_table", "cfp_spectro_plan_chi2_legendre",
+    "cfp_photo_plan_set_gc_table", "cfp_spectro_plan_chi2_legendre", "cfp_spectro_plan_kernel_ms_part",
+    "cfp_math_selftest",
 ]
 
 
@@ -78,6 +79,10 @@ def load():
     lib.cfp_peak_fp64.argtypes = [_vp, C.c_int, _dp]
     lib.cfp_spectro_plan_kernel_ms.argtypes = [_vp]
     lib.cfp_spectro_plan_kernel_ms.restype = C.c_double
+    lib.cfp_spectro_plan_kernel_ms_part.argtypes = [_vp, C.c_int]
+    lib.cfp_spectro_plan_kernel_ms_part.restype = C.c_double
+    lib.cfp_math_selftest.argtypes = [_vp, C.c_int, _dp, C.c_int, _dp]
+    lib.cfp_math_selftest.restype = C.c_int
     lib.cfp_photo_plan_kernel_ms.argtypes = [_vp, C.c_int]
     lib.cfp_photo_plan_kernel_ms.restype = C.c_double
     lib.cfp_bank_upload.argtypes = [_vp, _dp, C.c_size_t, _lp, C.c_int, C.c_int, C.POINTER(_vp)]
@@ -175,6 +180,13 @@ class Context:
     @property
     def last_run_ms(self) -> float:
         return float(self.lib.cfp_ctx_last_run_ms(self.handle))
+
+    def math_selftest(self, which: int, x) -> np.ndarray:
+        """f(x) on the device for the lattice loops' FP64 functions (cfp_math_selftest)."""
+        x = f64(x).ravel()
+        y = np.empty_like(x)
+        _check(self.lib.cfp_math_selftest(self.handle, int(which), _p(x), x.size, _p(y)), "cfp_math_selftest")
+        return y
 
     def peak_fp64(self, kind: int) -> float:
         """Measured FP64 TFLOP/s: kind 0 = DFMA, 1 = DMMA."""
@@ -443,8 +455,9 @@ class SpectroPlan:
         _check(self.ctx.lib.cfp_spectro_plan_run(self.handle, int(materialize), _vp(stream) if stream else None),
                "cfp_spectro_plan_run")
 
-    def kernel_ms(self) -> float:
-        return float(self.ctx.lib.cfp_spectro_plan_kernel_ms(self.handle))
+    def kernel_ms(self, part: int = 0) -> float:
+        """Device time of the lattice pass of the last run: 0 whole pass, 1 weights pre-pass, 2 main kernel."""
+        return float(self.ctx.lib.cfp_spectro_plan_kernel_ms_part(self.handle, int(part)))
 
     def fisher_device_ptr(self) -> int:
         return int(self.ctx.lib.cfp_spectro_plan_fisher_d(self.handle) or 0)

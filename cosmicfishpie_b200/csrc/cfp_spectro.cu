@@ -1290,6 +1290,28 @@ __global__ void __launch_bounds__(PK_WARPS * 32, 1)
   }
 }
 
+// ---------------------------------------------------------------------------- math self-test
+// y[i] = f(x[i]) for the branch-free FP64 functions of the lattice loops (tests sweep their stated domains against libm)
+__global__ void math_selftest_kernel(int which, int n, const double* __restrict__ x, double* __restrict__ y) {
+  __shared__ MathTab mt;
+  math_tables_fill(mt, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  double r;
+  switch (which) {
+    case 0: r = tab_exp_neg(mt, v); break;
+    case 1: r = tab_log(mt, v); break;
+    case 2: r = fast_rcp(v); break;
+    case 3: r = fast_rsqrt(v); break;
+    case 4: r = fast_div(1.0, v); break;
+    case 5: r = pair_exp_neg(mt, v); break;
+    default: r = CUDART_NAN; break;
+  }
+  y[i] = r;
+}
+
 // F[zb] of the bins the pair kernel took: internal order (slots 0..7, shot noise) -> parameters, zeros elsewhere.
 // grid (Z); one warp per element of the lower triangle, lanes over the CTA partials (fixed order: lane l adds CTAs
 // l, l + 32, ..., then a shuffle tree).
@@ -1874,10 +1896,11 @@ struct cfp_spectro_plan {
   int grid2_x = 0, wd_rows = 0;
   int pair_state = 0;              // bins the pair kernel takes when nothing is materialised: 0 unknown, 1 all, 2 none, 3 some
   int last_mat = -1;
+  bool mid_recorded = false;       // kevm was recorded by the last run (the pair kernel ran)
   bool ran = false;
   cudaStream_t last_st = nullptr;  // stream of the most recent run (the pool releases on the context stream)
   std::vector<double> scal_h;      // host copy of the scalar blocks (the likelihood groups points by them)
-  cudaEvent_t kev0 = nullptr, kev1 = nullptr;
+  cudaEvent_t kev0 = nullptr, kev1 = nullptr, kevm = nullptr;  // lattice pass begin / end, and between pre-pass and main kernel
   // begin / end of this plan's most recent run or chi2 call, on the stream it ran on: fetch waits on run1 (plans of
   // one context may run concurrently on different streams, a context-wide event would be the wrong one)
   cudaEvent_t run0 = nullptr, run1 = nullptr;
@@ -1889,6 +1912,7 @@ static void spectro_free(cfp_spectro_plan* p) {
   if (p->run1) cudaEventDestroy(p->run1);
   if (p->kev0) cudaEventDestroy(p->kev0);
   if (p->kev1) cudaEventDestroy(p->kev1);
+  if (p->kevm) cudaEventDestroy(p->kevm);
   for (void* q : p->owned) cfp_dev_free(p->ctx, q);
   cfp_dev_free(p->ctx, p->lnp_d);
   cfp_dev_free(p->ctx, p->derivs_d);
@@ -2475,8 +2499,10 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
   if (!pl->kev0) {
     CFP_CUDA(cudaEventCreate(&pl->kev0));
     CFP_CUDA(cudaEventCreate(&pl->kev1));
+    CFP_CUDA(cudaEventCreate(&pl->kevm));
   }
   CFP_CUDA(cudaEventRecord(pl->kev0, st));
+  pl->mid_recorded = false;
   cudaError_t e = cudaSuccess;
   if (try_pairs) {
     // rows staged at once, and how finely the rows are cut into tasks: enough tasks for an even deal to the warps
@@ -2496,6 +2522,8 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
       const int wlen = (nrows + wsegs - 1) / wsegs;
       spectro_weights_kernel<<<dim3((pl->Nk + TILE - 1) / TILE, pl->Z, wsegs), TILE, 0, st>>>(P, row_lo, nrows, wlen,
                                                                                             pl->wd_d);
+      cudaEventRecord(pl->kevm, st);
+      pl->mid_recorded = true;
     }
     ctx->launches++;
     const size_t smem2 = std::max((size_t)srows * 16 * sizeof(RowP), (size_t)pk_warps * 80 * sizeof(double)) + sizeof(MathTab) +
@@ -2574,6 +2602,38 @@ extern "C" double cfp_spectro_plan_kernel_ms(cfp_spectro_plan* pl) {
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, pl->kev0, pl->kev1) != cudaSuccess) return -1.0;
   return ms;
+}
+
+extern "C" int cfp_math_selftest(cfp_ctx* ctx, int which, const double* x_h, int n, double* y_h) {
+  CFP_REQUIRE(ctx && x_h && y_h && n >= 1 && which >= 0 && which <= 5, "bad argument");
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  double *x_d = nullptr, *y_d = nullptr;
+  int rc = cfp_upload<double>(ctx, x_h, (size_t)n, &x_d);
+  if (rc == CFP_OK) rc = cfp_upload<double>(ctx, nullptr, (size_t)n, &y_d);
+  if (rc == CFP_OK) {
+    math_selftest_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(which, n, x_d, y_d);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(y_h, y_d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      cfp_set_error("cfp_math_selftest: %s", cudaGetErrorString(e));
+      rc = CFP_ERR_CUDA;
+    }
+  }
+  cfp_dev_free(ctx, x_d);
+  cfp_dev_free(ctx, y_d);
+  return rc;
+}
+
+extern "C" double cfp_spectro_plan_kernel_ms_part(cfp_spectro_plan* pl, int which) {
+  if (which == 0) return cfp_spectro_plan_kernel_ms(pl);
+  if (!pl || !pl->ran || !pl->kev1 || !pl->mid_recorded || which < 0 || which > 2) return -1.0;
+  cudaSetDevice(pl->ctx->device);
+  if (cudaEventSynchronize(pl->kev1) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  const cudaError_t e = which == 1 ? cudaEventElapsedTime(&ms, pl->kev0, pl->kevm) : cudaEventElapsedTime(&ms, pl->kevm, pl->kev1);
+  return e == cudaSuccess ? (double)ms : -1.0;
 }
 
 extern "C" const double* cfp_spectro_plan_fisher_d(const cfp_spectro_plan* plan) {

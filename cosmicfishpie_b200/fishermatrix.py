@@ -99,17 +99,43 @@ class FisherMatrix:
     def compute(self, max_z_bins=None):
         """Compute the Fisher matrix of the configured observables; returns a `fisher_matrix` object
         (re-read from the exported text file, like the reference) or None when `outroot` is empty."""
+        return self._finish(self._launch(max_z_bins))
+
+    def _launch(self, max_z_bins=None):
+        """Host preparation, H2D and the (asynchronous) kernel launches of this forecast; `_finish` collects."""
         t0 = time()
         if "GCph" in self.observables or "WL" in self.observables:
-            finalFisher = self._compute_photo()
+            state = ("photo", self._launch_photo())
         elif "GCsp" in self.observables:
-            finalFisher = self._compute_spectro(max_z_bins)
+            state = ("spectro", self._launch_spectro(max_z_bins))
         else:
             raise AttributeError("Observables list not defined properly")
+        return (t0,) + state
+
+    def _finish(self, launched):
+        t0, kind, st = launched
+        finalFisher = self._finish_photo(st) if kind == "photo" else self._finish_spectro(st)
         t1 = time()
         self.timings["compute_s"] = t1 - t0
         self.fisher_array = finalFisher
         return self.export_fisher(finalFisher, totaltime=t1 - t0)
+
+    @staticmethod
+    def compute_many(forecasts, max_z_bins=None):
+        """A batch of forecasts (FisherMatrix objects, any mix of probes) as a two-stage pipeline: the kernels of a
+        forecast run asynchronously while the host prepares and uploads the next one; results are collected one
+        forecast late.  Returns the list of results in order -- the same objects `compute()` returns.
+        (The reference has no batch entry: every forecast is one blocking `compute()`; SURVEY 8e names batches of
+        forecasts -- many fiducials or survey specifications -- as the unit that fills a GPU.)"""
+        out, pending = [], None
+        for f in forecasts:
+            launched = f._launch(max_z_bins)
+            if pending is not None:
+                out.append(pending[0]._finish(pending[1]))
+            pending = (f, launched)
+        if pending is not None:
+            out.append(pending[0]._finish(pending[1]))
+        return out
 
     # --- spectro ------------------------------------------------------------------------------
     def set_pk_settings(self):
@@ -135,7 +161,7 @@ class FisherMatrix:
                 if ibin > nmax:
                     self.freeparams.pop(key)
 
-    def _compute_spectro(self, max_z_bins=None):
+    def _launch_spectro(self, max_z_bins=None):
         t0 = time()
         self.set_pk_settings()
         self.obs_spectrum = ["g", "g"]
@@ -160,6 +186,10 @@ class FisherMatrix:
         plan = job.plan()
         plan.set_slice(*cdist.split_range(self.Pk_ksamp * self.Pk_musamp, rank, world))
         plan.run(materialize=0)
+        return plan, world, t0, t1
+
+    def _finish_spectro(self, st):
+        plan, world, t0, t1 = st
         # partial Fisher matrices of the slices: one all-reduce on the plan's own device buffer (NCCL), then one D2H
         reduced = world > 1 and cdist.allreduce_plan_result(plan, (plan.Z, plan.npar, plan.npar))
         Fz, _, _, _ = plan.fetch()
@@ -174,6 +204,9 @@ class FisherMatrix:
         self.pk_fisher_per_bin = Fz
         self._lazy.clear()
         return np.sum(Fz, axis=0)
+
+    def _compute_spectro(self, max_z_bins=None):
+        return self._finish_spectro(self._launch_spectro(max_z_bins))
 
     def _materialise_spectro(self):
         if "derivs" not in self._lazy:
@@ -246,7 +279,7 @@ class FisherMatrix:
         return np.array(self.pk_fisher_per_bin[ibin])
 
     # --- photo --------------------------------------------------------------------------------
-    def _compute_photo(self):
+    def _launch_photo(self):
         from . import photo as photo_mod
 
         t0 = time()
@@ -258,13 +291,20 @@ class FisherMatrix:
                                             stencil=self.stencil)
         t1 = time()
         shard = self._shard if self._shard is not None else cdist.rank_world()
-        F = self.photo_LSS.compute_fisher(self.freeparams, shard=shard)
+        return self.photo_LSS.launch_fisher(self.freeparams, shard=shard), t0, t1
+
+    def _finish_photo(self, st):
+        launched, t0, t1 = st
+        F = self.photo_LSS.finish_fisher(launched)
         t2 = time()
         plan = self.photo_LSS._job.plan()
         self.timings.update(host_prep_s=self.photo_LSS.timings.get("host_prep_s", t1 - t0),
                             device_s=self.photo_LSS.timings.get("device_s", t2 - t1),
                             kernel_ms=getattr(getattr(plan, "ctx", None), "last_run_ms", float("nan")))
         return F
+
+    def _compute_photo(self):
+        return self._finish_photo(self._launch_photo())
 
     @property
     def photo_derivs(self):
@@ -329,7 +369,19 @@ class FisherMatrix:
             for par in cols)
         write_atomic(root + self.settings["fishermatrix_file_extension"], fm_text)
         write_atomic(root + ".paramnames", pn_text)
-        out = fm.fisher_matrix(file_name=root + ".txt")
+        arr = np.atleast_2d(np.asarray(fishmat, dtype=float))
+        if arr.any(axis=1).all() and arr.any(axis=0).all():
+            # what re-reading the two files gives (repr round-trips exactly, fiducials carry six decimals), without
+            # parsing them back
+            out = fm.fisher_matrix(fisher_matrix=arr, param_names=cols,
+                                   param_names_latex=[str(self.latex_names.get(p, str(p))) for p in cols],
+                                   fiducial=[float("{:.6f}".format(self.allparams[p])) for p in cols])
+            out.file_name = root + ".txt"
+            out.path = os.path.abspath(out.file_name)
+            out.name = os.path.splitext(os.path.basename(out.file_name))[0]
+            out.indir = os.path.dirname(out.path)
+        else:  # all-zero rows / columns are deleted on reading (analysis/fisher_matrix.py:261-268): take that route
+            out = fm.fisher_matrix(file_name=root + ".txt")
         if rank != 0 and cdist.is_distributed():
             return out  # the specification files are rank 0's business
         git = self._git_version()

@@ -74,10 +74,27 @@ class Likelihood(ABC):
         """chi^2 of every row of `matrix` [B, len(names)]; subclasses override this with an array fast path."""
         return self.chi2_batch([dict(zip(names, row)) for row in matrix])
 
-    def loglike_batch(self, param_matrix, prior=None, keys: Optional[Iterable[str]] = None) -> np.ndarray:
-        """log-likelihood of every row of `param_matrix` [B, ndim]; columns named by `prior.keys` or `keys`."""
+    def loglike_batch(self, param_matrix, prior=None, keys: Optional[Iterable[str]] = None, shard: bool = False) -> np.ndarray:
+        """log-likelihood of every row of `param_matrix` [B, ndim]; columns named by `prior.keys` or `keys`.
+
+        `shard=True` under torch.distributed (one process per GPU): every rank holds the same matrix, evaluates a
+        contiguous slice of the points on its own GPU and ONE all-gather (NCCL over NVLink; gloo on CPU) hands every
+        rank the full vector -- the points are independent, so this is the only exchange."""
         names = list(keys) if keys is not None else list(getattr(prior, "keys"))
         pm = np.atleast_2d(np.asarray(param_matrix, dtype=float))
+        if shard:
+            from . import distributed as cdist
+
+            rank, world = cdist.rank_world()
+            if world > 1:
+                B = pm.shape[0]
+                per = (B + world - 1) // world  # equal slices (the last ranks may run past the end: padded below)
+                lo, hi = min(B, rank * per), min(B, (rank + 1) * per)
+                local = np.full(per, np.nan)
+                if hi > lo:
+                    local[: hi - lo] = -0.5 * self.chi2_matrix(names, pm[lo:hi])
+                dev = (getattr(self.cosmo_theory, "settings", None) or {}).get("device")
+                return cdist.allgather_numpy(local, device=dev)[:B]
         return -0.5 * self.chi2_matrix(names, pm)
 
 
@@ -97,7 +114,7 @@ class NautilusMixin:
 
         kw = dict(sampler_kwargs or {})
         kw.pop("pool", None)  # never fork after CUDA initialisation: batches go to the GPU instead
-        sampler = Sampler(prior, lambda x: self.loglike_batch(x, prior=prior), vectorized=True, pass_dict=False, **kw)
+        sampler = Sampler(prior, lambda x: self.loglike_batch(x, prior=prior, shard=True), vectorized=True, pass_dict=False, **kw)
         sampler.run(**dict(run_kwargs or {}))
         return sampler
 
@@ -486,48 +503,7 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
         zs = list(fm.pk_cov.global_z_bin_mids)
         matrix = np.atleast_2d(np.asarray(matrix, dtype=float))
         B, Z = matrix.shape[0], len(zs)
-        col = {n: i for i, n in enumerate(names)}
-
-        def column(key, fid):
-            return matrix[:, col[key]] if key in col else np.full(B, float(fid))
-
-        ckeys = [k for k in fm.fiducialcosmopars if k in col]
-        cosmo_of_s = np.zeros(B, dtype=np.int64)
-        if ckeys:
-            uniq, inv = np.unique(matrix[:, [col[k] for k in ckeys]], axis=0, return_inverse=True)
-            idx = np.empty(len(uniq), dtype=np.int64)
-            for u, row in enumerate(uniq):
-                cp = dict(fm.fiducialcosmopars)
-                cp.update({k: float(v) for k, v in zip(ckeys, row)})
-                idx[u] = cs.add(cp)
-            cosmo_of_s = idx[np.asarray(inv).ravel()]
-        base = {}
-        for c in np.unique(cosmo_of_s):
-            obs = spectro_mod.ComputeGalSpectro(cs.cosmos[c].cosmopars, spectrobiaspars=fm.Spectrobiaspars,
-                                                spectrononlinearpars=fm.Spectrononlinpars, PShotpars=fm.PShotpars,
-                                                configuration=fm, cosmo_set=cs)
-            base[c] = np.array([obs.scalar_block(z) for z in zs])
-        cu, cinv = np.unique(cosmo_of_s, return_inverse=True)
-        scal = np.stack([base[c] for c in cu])[np.asarray(cinv).ravel()]  # [B, Z, NSCAL]
-        nu = fid_obs.nuisance
-        for zb, z in enumerate(zs):
-            b = nu.gcsp_zvalue_to_zindex(z)
-            key = nu.sp_bias_root + nu.sp_bias_sample + "_" + str(b)
-            vals = column(key, fm.Spectrobiaspars[key])
-            scal[:, zb, _lib.SP_BIAS] = np.exp(vals) if nu.sp_bias_model == "linear_log" else vals
-            if fid_obs.rescale_sigmap and not fid_obs.linear_switch:
-                k2 = "sigmap_" + str(b)
-                scal[:, zb, _lib.SP_SIGMAP] = np.sqrt(scal[:, zb, _lib.SP_I2]) * column(k2, fm.Spectrononlinpars.get(k2, 1.0))
-            if fid_obs.rescale_sigmav:
-                k2 = "sigmav_" + str(b)
-                scal[:, zb, _lib.SP_SVRESCALE] = column(k2, fm.Spectrononlinpars.get(k2, 1.0))
-        if nu.sp_bias_model == "linear_Qbias":
-            scal[:, :, _lib.SP_A1] = column("A1", fm.Spectrobiaspars.get("A1", 0.0))[:, None]
-            scal[:, :, _lib.SP_A2] = column("A2", fm.Spectrobiaspars.get("A2", 0.0))[:, None]
-        shot = np.zeros((B, Z))
-        for i, key in enumerate(fm.PShotpars.keys()):
-            if i < Z:
-                shot[:, i] = column(key, fm.PShotpars[key])
+        scal, shot, cosmo_of_s = spectro_mod.scalar_blocks_from_matrix(fm, fid_obs, zs, names, matrix)
         used = {int(c) for c in np.unique(cosmo_of_s)}
         pk, pp = spectro_mod._pnw_arrays(cs, zs, set() if fid_obs.linear_switch else used)
         wk, wmu = simpson_weights(fm.Pk_kgrid), simpson_weights(fm.Pk_mugrid)

@@ -322,8 +322,8 @@ class PhotoJob:
         B, Nz, Nb = matrix.shape[0], g.zsamp, len(g.rows)
         col = {n: i for i, n in enumerate(names)}
         for n in names:
-            if n in cfg.photoparams:
-                raise NotImplementedError("photo-z parameters cannot be varied per point yet")
+            if n in cfg.photoparams and np.any(matrix[:, col[n]] != float(cfg.photoparams[n])):
+                raise NotImplementedError("photo-z parameters cannot be varied per point by the array path")
 
         def column(key, fid):
             return matrix[:, col[key]] if key in col else np.full(B, float(fid))
@@ -333,11 +333,11 @@ class PhotoJob:
         self.cosmo_of_s = np.zeros(B, dtype=np.int32)
         if ckeys:
             sub = matrix[:, [col[k] for k in ckeys]]
-            uniq, inv = np.unique(sub, axis=0, return_inverse=True)
+            uniq, first, inv = np.unique(sub, axis=0, return_index=True, return_inverse=True)
             idx = np.empty(len(uniq), dtype=np.int32)
-            for u, row in enumerate(uniq):
+            for u in np.argsort(first):  # cosmologies enter the set in the order of their first appearance
                 cp = dict(cfg.fiducialparams)
-                cp.update({k: float(v) for k, v in zip(ckeys, row)})
+                cp.update({k: float(v) for k, v in zip(ckeys, uniq[u])})
                 idx[u] = cs.add(cp)
             self.cosmo_of_s = idx[np.asarray(inv).ravel()]
         self.zmap = None  # bias sampled on the z grid, or on fewer samples + a z -> sample map (binned models)
@@ -586,13 +586,27 @@ class PhotoCov:
                 stw[ip, s] = w
         self.parnames = list(fp)
         self.points = points
-        self._job = PhotoJob(self.configuration, points, stw, stden)
+        cfg = self._cfg
+        if self.stencil != "STEM" and not any(k in cfg.photoparams for k in fp):
+            # stencil points as rows of a matrix: windows, IA and bias assembled with array operations (the photo-z
+            # parameters, whose stencil points need their own n_i(z) windows, take the point-by-point constructor)
+            names = [k for k, v in self.allparsfid.items() if isinstance(v, (int, float, np.floating, np.integer))
+                     and not isinstance(v, bool)]
+            mat = np.array([[ap[k] for k in names] for ap in points], dtype=float)
+            self._job = PhotoJob.from_matrix(self.configuration, names, mat)
+            self._job.stw, self._job.stden = np.asarray(stw, float), np.asarray(stden, float)
+        else:
+            self._job = PhotoJob(self.configuration, points, stw, stden)
         self._cls_all = None
         return self._job
 
     def compute_fisher(self, freeparams=None, shard=(0, 1)) -> np.ndarray:
         """Fisher matrix of the job; `shard=(rank, world)` restricts this process to its slice of the
         multipole bins and all-reduces the partial sums (cosmicfishpie_b200.distributed)."""
+        return self.finish_fisher(self.launch_fisher(freeparams, shard))
+
+    def launch_fisher(self, freeparams=None, shard=(0, 1)):
+        """Host preparation, H2D and the asynchronous kernel launches; `finish_fisher` collects the result."""
         from . import distributed as cdist
 
         t0 = time()
@@ -603,6 +617,12 @@ class PhotoCov:
         nbins = plan.Nl - 1
         plan.set_slice(*cdist.split_range(nbins, rank, world))
         plan.run()
+        return plan, world, nbins, t0, t1
+
+    def finish_fisher(self, launched) -> np.ndarray:
+        from . import distributed as cdist
+
+        plan, world, nbins, t0, t1 = launched
         reduced = world > 1 and cdist.allreduce_plan_result(plan, (plan.npar, plan.npar))  # NCCL, in place on the device
         F, _, _ = plan.fetch()
         if world > 1:

@@ -373,6 +373,79 @@ def _cosmo_set_of(cfg) -> CosmoSet:
     return cs
 
 
+
+def _base_blocks(fid_obs: "ComputeGalSpectro", cs: CosmoSet, c: int, zs) -> np.ndarray:
+    """[Z][NSCAL] scalar blocks of cosmology `c` of the set with the configuration's FIDUCIAL nuisance values.
+    Everything in them that is not a nuisance value derives from the cached Boltzmann tables (H, D_A, sigma8, the
+    theta-theta moments at the bin centres), so the array is cached on the cosmology facade, keyed by what else enters
+    (bin centres, switches, redshift-error model, fiducial nuisance values)."""
+    cosmo = cs.cosmos[c]
+    key = (tuple(float(z) for z in zs), fid_obs.flags(), fid_obs.s8terms, fid_obs.tracer, fid_obs.fix_cosmo_nl_terms,
+           fid_obs.kh_rescaling_bug, fid_obs.dz_err, fid_obs.dz_type, fid_obs.rescale_sigmap, fid_obs.rescale_sigmav,
+           tuple(fid_obs.fiducial_spectrobiaspars.items()), tuple(fid_obs.fiducial_spectrononlinearpars.items()),
+           tuple(np.asarray(fid_obs.nuisance.sp_zbins).tolist()), fid_obs.nuisance.sp_bias_model)
+    cache = cosmo.__dict__.setdefault("_sp_base_cache", {})
+    hit = cache.get(key)
+    if hit is None or hit[0] is not fid_obs.fiducialcosmo:  # identity check: the fiducial facade enters q_par, q_perp
+        obs = ComputeGalSpectro(cosmo.cosmopars, spectrobiaspars=fid_obs.fiducial_spectrobiaspars,
+                                spectrononlinearpars=fid_obs.fiducial_spectrononlinearpars,
+                                PShotpars=fid_obs.fiducial_PShotpars, configuration=fid_obs.config, cosmo_set=cs)
+        arr = np.array([obs.scalar_block(z) for z in zs])
+        arr.setflags(write=False)
+        hit = (fid_obs.fiducialcosmo, arr)
+        cache[key] = hit
+    out = hit[1].copy()
+    out[:, _lib.SP_COSMO] = c
+    return out
+
+
+def scalar_blocks_from_matrix(fm, fid_obs: "ComputeGalSpectro", zs, names, matrix):
+    """Scalar blocks [B][Z][NSCAL], additive shot noise [B][Z] and bank index [B] of a batch of parameter points given
+    as a matrix [B, len(names)] -- stencil points of a Fisher job or points of a likelihood batch.  One cached block per
+    (cosmology, bin) plus the nuisance columns: no Python object per point.  Unlisted parameters stay fiducial."""
+    cs = fid_obs.cosmo_set
+    matrix = np.atleast_2d(np.asarray(matrix, dtype=float))
+    B, Z = matrix.shape[0], len(zs)
+    col = {n: i for i, n in enumerate(names)}
+
+    def column(key, fid):
+        return matrix[:, col[key]] if key in col else np.full(B, float(fid))
+
+    ckeys = [k for k in fm.fiducialcosmopars if k in col]
+    cosmo_of_s = np.zeros(B, dtype=np.int64)
+    if ckeys:
+        uniq, first, inv = np.unique(matrix[:, [col[k] for k in ckeys]], axis=0, return_index=True, return_inverse=True)
+        idx = np.empty(len(uniq), dtype=np.int64)
+        for u in np.argsort(first):  # cosmologies enter the set in the order of their first appearance
+            cp = dict(fm.fiducialcosmopars)
+            cp.update({k: float(v) for k, v in zip(ckeys, uniq[u])})
+            idx[u] = cs.add(cp)
+        cosmo_of_s = idx[np.asarray(inv).ravel()]
+    cu, cinv = np.unique(cosmo_of_s, return_inverse=True)
+    scal = np.stack([_base_blocks(fid_obs, cs, int(c), zs) for c in cu])[np.asarray(cinv).ravel()]  # [B, Z, NSCAL]
+    nu = fid_obs.nuisance
+    for zb, z in enumerate(zs):
+        b = nu.gcsp_zvalue_to_zindex(z)
+        if "linear" in nu.sp_bias_model:
+            key = nu.sp_bias_root + nu.sp_bias_sample + "_" + str(b)
+            vals = column(key, fm.Spectrobiaspars[key])
+            scal[:, zb, _lib.SP_BIAS] = np.exp(vals) if nu.sp_bias_model == "linear_log" else vals
+        if fid_obs.rescale_sigmap and not fid_obs.linear_switch:
+            k2 = "sigmap_" + str(b)
+            scal[:, zb, _lib.SP_SIGMAP] = np.sqrt(scal[:, zb, _lib.SP_I2]) * column(k2, fm.Spectrononlinpars.get(k2, 1.0))
+        if fid_obs.rescale_sigmav:
+            k2 = "sigmav_" + str(b)
+            scal[:, zb, _lib.SP_SVRESCALE] = column(k2, fm.Spectrononlinpars.get(k2, 1.0))
+    if nu.sp_bias_model == "linear_Qbias":
+        scal[:, :, _lib.SP_A1] = column("A1", fm.Spectrobiaspars.get("A1", 0.0))[:, None]
+        scal[:, :, _lib.SP_A2] = column("A2", fm.Spectrobiaspars.get("A2", 0.0))[:, None]
+    shot = np.zeros((B, Z))
+    for i, key in enumerate(fm.PShotpars.keys()):
+        if i < Z:
+            shot[:, i] = column(key, fm.PShotpars[key])
+    return scal, shot, cosmo_of_s
+
+
 def _pnw_arrays(cosmo_set: CosmoSet, zs, used):
     """No-wiggle knots/values [NC][nnw], [NC][Z][nnw]; rows of unused cosmologies are left as ones."""
     nnw = cosmo_set.config.settings["savgol_internalsamples"]
@@ -503,8 +576,7 @@ class SpectroJob:
         pts, den = stencils.get(stencil)
         cs = fiducial_obs.cosmo_set
         fid_all = self.fiducial_allpars
-        points = [fiducial_obs]        # s = 0
-        point_pars = [dict(fid_all)]
+        point_pars = [dict(fid_all)]   # s = 0: the fiducial
         npar = len(self.parnames)
         stw_rows, stden, ps_bin = [], np.ones(npar), -np.ones(npar, dtype=np.int32)
         last_eval, ps_src = None, None
@@ -528,19 +600,29 @@ class SpectroJob:
                     continue
                 ap = dict(fid_all)  # flat {name: number}
                 ap[par] = ap[par] + m * h
-                points.append(self._point(ap, cfg, cs))
                 point_pars.append(ap)
-                row[len(points) - 1] = w
-                last_eval = len(points) - 1
+                row[len(point_pars) - 1] = w
+                last_eval = len(point_pars) - 1
             stw_rows.append(row)
-        self.points, self.point_pars = points, point_pars
-        S, Z = len(points), len(self.zmids)
+        self.point_pars = point_pars
+        self._cfg, self._points = cfg, None
+        S, Z = len(point_pars), len(self.zmids)
         self.stw = np.zeros((npar, S))
         for ip, row in enumerate(stw_rows):
             for s, w in row.items():
                 self.stw[ip, s] = w
         self.stden, self.ps_bin, self.ps_src = stden, ps_bin, (0 if ps_src is None else ps_src)
-        self.scal = np.array([[p.scalar_block(z) for z in self.zmids] for p in points])
+        if fiducial_obs.use_bias_funcs:
+            self.scal = np.array([[p.scalar_block(z) for z in self.zmids] for p in self.points])
+        else:
+            # every stencil point as a row of a matrix: one cached block per (cosmology, bin) + the nuisance columns
+            from types import SimpleNamespace
+
+            names = list(fid_all)
+            mat = np.array([[ap[k] for k in names] for ap in point_pars], dtype=float)
+            view = SimpleNamespace(fiducialcosmopars=cfg.fiducialparams, Spectrobiaspars=cfg.Spectrobiasparams,
+                                   Spectrononlinpars=cfg.Spectrononlinearparams, PShotpars={})
+            self.scal, _, _ = scalar_blocks_from_matrix(view, fiducial_obs, self.zmids, names, mat)
         # a stencil point whose block equals the fiducial's in a bin reuses the fiducial lattice there
         same = np.all(self.scal == self.scal[0:1], axis=2)
         self.alias = np.where(same, 0, np.arange(S)[:, None]).astype(np.int32)
@@ -553,6 +635,14 @@ class SpectroJob:
         self.tabs = table_slots(fiducial_obs.settings)
         self.cosmo_set = cs
         self._plan = None
+
+    @property
+    def points(self):
+        """ComputeGalSpectro object of every stencil point (built on demand: the job itself works on the matrix of
+        their parameter values)."""
+        if self._points is None:
+            self._points = [self.fid] + [self._point(ap, self._cfg, self.fid.cosmo_set) for ap in self.point_pars[1:]]
+        return self._points
 
     @staticmethod
     def _point(allpars, cfg, cs):

@@ -186,6 +186,13 @@ int cfp_spectro_plan_run(cfp_spectro_plan* plan, int materialize, void* stream);
 /* Device time [ms] of the fused lattice/derivative/Fisher kernel alone in the last run (CUDA events on
  * the launch stream around that one launch); synchronises. */
 double cfp_spectro_plan_kernel_ms(cfp_spectro_plan* plan);
+/* Parts of the lattice pass of the last run: 0 = the whole pass (as above), 1 = the weights pre-pass, 2 = the main
+ * kernel (spectro_fisher_pairs_kernel); -1 when the last run did not take the pair kernels. */
+double cfp_spectro_plan_kernel_ms_part(cfp_spectro_plan* plan, int which);
+/* Test hook: y[i] = f(x[i]) on the device for the branch-free FP64 functions of the lattice loops, so that tests can
+ * sweep their stated domains against libm.  which: 0 exp(x), x <= 0 (table version); 1 log(x), x > 0 normal;
+ * 2 1/x; 3 1/sqrt(x); 4 1/x by division; 5 exp(x), x <= 0 (pair-kernel version).  Host buffers. */
+int cfp_math_selftest(cfp_ctx* ctx, int which, const double* x_h, int n, double* y_h);
 /* Device pointer of the result F[Z][npar][npar] (valid until the plan is destroyed). */
 const double* cfp_spectro_plan_fisher_d(const cfp_spectro_plan* plan);
 /* Copy results to the host (synchronises). Any pointer may be NULL. */

@@ -117,3 +117,60 @@ def test_two_rank_sharded_compute_sums_to_single_rank(tmp_path):
     assert np.allclose(F0, full, rtol=1e-12)
     nb = 21 - 1
     assert np.allclose(P0, np.sum(np.sin(0.1 * np.arange(nb) + 1.0)) * _pattern(P0.shape[0]), rtol=1e-12)
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cosmicfishpie_b200.likelihood import Likelihood
+
+    class Toy(Likelihood):
+        """chi2 = sum of squares of the row: every rank must only ever see its own slice."""
+
+        def __init__(self):
+            self.cosmo_theory = None
+            self.seen = []
+
+        def compute_data(self):
+            return None
+
+        def compute_theory(self, p):
+            return None
+
+        def compute_chi2(self, t):
+            return 0.0
+
+        def chi2_batch(self, dicts):
+            raise AssertionError("the array path is the one under test")
+
+        def chi2_matrix(self, names, matrix):
+            self.seen.append(matrix.shape[0])
+            return np.sum(np.asarray(matrix) ** 2, axis=1)
+
+    like = Toy()
+    mat = np.arange(7 * 3, dtype=float).reshape(7, 3)  # 7 points over 2 ranks: slices of 4 and 3
+    ll = like.loglike_batch(mat, keys=["a", "b", "c"], shard=True)
+    q.put((rank, ll, like.seen))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_loglike_batch_gathers_every_point():
+    """loglike_batch(shard=True): contiguous slices per rank, one all-gather, every rank gets the full vector."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=90) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = -0.5 * np.sum(np.arange(21, dtype=float).reshape(7, 3) ** 2, axis=1)
+    for rank, ll, seen in res:
+        assert np.array_equal(ll, expect)
+        assert seen == ([4] if rank == 0 else [3])

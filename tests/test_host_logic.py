@@ -155,7 +155,8 @@ def test_photo_job_assembly(extfiles, tmp_path):
     assert np.all(g.lmax[:10] == 1500) and np.all(g.lmax[10:] == 750)
     # b3 step changes only the bias window inside bin 3
     s_b3 = 1 + 2 * (2 + 2)
-    diff = np.nonzero(np.any(job.bias[s_b3] != job.bias[0], axis=0))[0]
+    bias = job.bias if getattr(job, "zmap", None) is None else job.bias[:, :, job.zmap]  # (per-bin samples + z -> bin map)
+    diff = np.nonzero(np.any(bias[s_b3] != bias[0], axis=0))[0]
     zb = fm.specs["z_bins_GCph"]
     assert np.all((g.z[diff] >= zb[2]) & (g.z[diff] < zb[3]))
     assert np.array_equal(job.ia[s_b3], job.ia[0]) and not np.array_equal(job.ia[-1], job.ia[0])

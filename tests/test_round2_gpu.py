@@ -1,0 +1,169 @@
+"""GPU tests added in round 2: device math functions swept over their domains, photo-z parameters in the batched
+likelihood, the pipelined batch entry, options["device"], and the NCCL paths on two GPUs (skipped on one)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import REPO, base_options
+
+pytestmark = pytest.mark.gpu
+
+P7 = ["Omegam", "Omegab", "h", "ns", "sigma8", "w0", "wa"]
+
+
+def ulp_err(y, ref):
+    return np.max(np.abs(y - ref) / (np.abs(ref) * np.finfo(float).eps))
+
+
+def test_device_math_functions_match_libm():
+    """tab_exp_neg / pair_exp_neg on [-700, 0], tab_log / fast_rcp / fast_rsqrt / fast_div on positive normal numbers
+    (csrc/cfp_spectro.cu: their stated domains), against numpy's libm: a few ulp."""
+    from cosmicfishpie_b200 import _lib
+
+    ctx = _lib.default_context()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([-np.logspace(-300, np.log10(700.0), 200000), -rng.uniform(0, 40, 200000), [0.0, -1e-320, -700.0]])
+    for which in (0, 5):
+        y = ctx.math_selftest(which, x)
+        assert ulp_err(y, np.exp(x)) < 4.0, which
+    assert ctx.math_selftest(5, np.array([-1e4, -1e300]))[0] < 1e-300  # clamped, not garbage
+    pos = np.concatenate([10.0 ** rng.uniform(-300, 300, 400000), 1.0 + rng.uniform(-1e-3, 1e-3, 1000),
+                          [np.finfo(float).tiny, 1.0, 2.0, 0.5, 1e308]])
+    y = ctx.math_selftest(1, pos)
+    ref = np.log(pos)
+    nz = ref != 0
+    assert np.max(np.abs(y[nz] - ref[nz]) / np.maximum(np.abs(ref[nz]), 1e-3)) < 4 * np.finfo(float).eps * 1e3 / 1e3 + 1e-15
+    mid = 10.0 ** rng.uniform(-150, 150, 400000)  # 1/x and 1/sqrt(x) stay normal
+    assert ulp_err(ctx.math_selftest(2, mid), 1.0 / mid) < 2.0
+    assert ulp_err(ctx.math_selftest(3, mid), 1.0 / np.sqrt(mid)) < 3.0
+    assert ulp_err(ctx.math_selftest(4, mid), 1.0 / mid) < 2.0
+
+
+@pytest.fixture(scope="module")
+def photo_fm(extfiles, tmp_path_factory):
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    o = base_options(tmp_path_factory.mktemp("r2p"), survey_name_photo="Euclid-Photometric-ISTF-Pessimistic",
+                     survey_name_spectro=False, ell_sampling=24)
+    fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"Omegam": 0.01, "h": 0.01}, options=o,
+                      observables=["WL", "GCph"], extfiles=extfiles)
+    fm.compute()
+    return fm
+
+
+def test_loglike_batch_honours_photoz_parameters(photo_fm):
+    """photo-z parameters must not be dropped by the array path (photo_like.py compute_theory updates them)."""
+    from cosmicfishpie_b200.likelihood import PhotometricLikelihood
+
+    like = PhotometricLikelihood(cosmo_data=photo_fm)
+    keys = ["b2", "AIA", "sigma_b", "zb"]
+    fid = np.array([photo_fm.allparams[k] for k in keys])
+    mat = np.tile(fid, (4, 1))
+    mat[1, 2] *= 1.05
+    mat[2, 3] += 0.004
+    mat[3] = fid * np.array([1.02, 0.97, 1.0, 1.0]) + np.array([0, 0, 0.002, 0.001])
+    batch = like.loglike_batch(mat, keys=keys)
+    single = np.array([like.loglike(param_dict=dict(zip(keys, r))) for r in mat])
+    assert abs(batch[0]) < 1e-7 and np.all(batch[1:] < -1e-3)  # the photo-z shifts are felt
+    assert np.max(np.abs(batch[1:] - single[1:]) / np.abs(single[1:])) < 1e-10
+
+
+def test_compute_many_equals_compute(extfiles, tmp_path):
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    def make(obs, i):
+        if obs == "GCsp":
+            o = base_options(tmp_path / f"s{i}", spectro_Pk_k_samples=257, spectro_Pk_mu_samples=17)
+        else:
+            o = base_options(tmp_path / f"p{i}", survey_name_photo="Euclid-Photometric-ISTF-Pessimistic",
+                             survey_name_spectro=False, ell_sampling=16)
+        return FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"Omegam": 0.01, "w0": 0.01}, options=o,
+                            observables=["GCsp"] if obs == "GCsp" else ["WL", "GCph"], extfiles=extfiles)
+
+    order = ["GCsp", "photo", "photo", "GCsp"]
+    many = FisherMatrix.compute_many([make(o, i) for i, o in enumerate(order)])
+    for i, o in enumerate(order):
+        one = make(o, 10 + i).compute()
+        assert list(one.get_param_names()) == list(many[i].get_param_names())
+        assert np.array_equal(one.fisher_matrix, many[i].fisher_matrix)
+
+
+def test_device_option_reaches_the_plans(extfiles, tmp_path):
+    """options['device'] must select the device of banks, plans and likelihood helpers."""
+    import torch
+
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    dev = torch.cuda.device_count() - 1
+    o = base_options(tmp_path, spectro_Pk_k_samples=129, spectro_Pk_mu_samples=9, device=dev)
+    fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"h": 0.01}, options=o, observables=["GCsp"],
+                      extfiles=extfiles)
+    fm.compute()
+    assert fm.ctx.device == dev and fm._spectro_job.plan().ctx.device == dev
+    assert fm._spectro_job.cosmo_set.context().device == dev
+
+
+TWO_GPU_SCRIPT = r'''
+import os, sys, tempfile
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["CFP_REPO"])
+rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+from cosmicfishpie_b200 import toy_tables as tt
+from cosmicfishpie_b200.fishermatrix import FisherMatrix
+from cosmicfishpie_b200 import distributed as cdist
+from cosmicfishpie_b200.likelihood import SpectroLikelihood
+bank = tt.make_bank(eps_values=(0.01,))
+ext = {"tables": bank, "directory": "<memory>", "paramnames": list(tt.COSMO_KEYS), "folder_paramnames": list(tt.COSMO_KEYS),
+       "k-units": "1/Mpc", "r-units": "Mpc", "eps_values": [0.01]}
+tmp = tempfile.mkdtemp(prefix="cfp_2gpu_%d_" % rank)
+def make(shard):
+    o = {"accuracy": 1, "feedback": 0, "code": "external", "outroot": "t", "results_dir": tmp, "survey_name": "Euclid",
+         "cosmo_model": "w0waCDM", "derivatives": "3PT", "survey_name_spectro": "Euclid-Spectroscopic-ISTF-Pessimistic",
+         "survey_name_photo": False, "spectro_Pk_k_samples": 1025, "spectro_Pk_mu_samples": 33}
+    fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"Omegam": 0.01, "h": 0.01, "w0": 0.01}, options=o,
+                      observables=["GCsp"], extfiles=ext)
+    if not shard:
+        cdist.shard(fm, 0, 1)
+    return fm
+F_sharded = make(True).compute().fisher_matrix      # lattice cells split over the ranks + NCCL all-reduce in place
+fm1 = make(False)
+F_single = fm1.compute().fisher_matrix              # the whole lattice on this rank
+err = float(np.max(np.abs(F_sharded - F_single) / np.abs(F_single)))
+like = SpectroLikelihood(cosmoFM_data=fm1)
+keys = ["lnbg_1", "lnbg_2", "Ps_3"]
+fid = np.array([fm1.allparams[k] for k in keys])
+mat = fid + np.array([0.01, 0.01, 5.0]) * np.random.default_rng(3).standard_normal((37, 3))
+a = like.loglike_batch(mat, keys=keys, shard=True)
+b = like.loglike_batch(mat, keys=keys)
+gerr = float(np.max(np.abs(a - b) / np.abs(b)))
+if rank == 0:
+    print("RESULT", err, gerr, flush=True)
+dist.destroy_process_group()
+'''
+
+
+def test_two_gpu_sharded_fisher_and_gathered_likelihood(tmp_path):
+    """The NCCL paths on real hardware: a forecast whose lattice is split over two GPUs and all-reduced in place on
+    the plan's device buffer equals the single-GPU result to 1e-12; a sharded likelihood batch gathered over the
+    ranks equals the unsharded one."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "two_gpu.py"
+    script.write_text(TWO_GPU_SCRIPT)
+    env = dict(os.environ, CFP_REPO=REPO)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)], env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESULT")][0].split()
+    assert float(line[1]) < 1e-12 and float(line[2]) < 1e-12, line
