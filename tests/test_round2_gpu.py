@@ -26,16 +26,19 @@ def test_device_math_functions_match_libm():
     ctx = _lib.default_context()
     rng = np.random.default_rng(0)
     x = np.concatenate([-np.logspace(-300, np.log10(700.0), 200000), -rng.uniform(0, 40, 200000), [0.0, -1e-320, -700.0]])
+    x = np.maximum(x, -700.0)  # (the functions clamp below -700: exp(-700) ~ 1e-304 stands in for anything smaller)
     for which in (0, 5):
         y = ctx.math_selftest(which, x)
-        assert ulp_err(y, np.exp(x)) < 4.0, which
-    assert ctx.math_selftest(5, np.array([-1e4, -1e300]))[0] < 1e-300  # clamped, not garbage
+        assert ulp_err(y, np.exp(x)) < 3.0, which  # measured on B200: 1.96 ulp
+    assert np.all(ctx.math_selftest(5, np.array([-1e4, -1e300])) < 1e-300)  # clamped, not garbage
+    assert np.all(ctx.math_selftest(0, np.array([-1e4, -1e300])) < 1e-300)
     pos = np.concatenate([10.0 ** rng.uniform(-300, 300, 400000), 1.0 + rng.uniform(-1e-3, 1e-3, 1000),
                           [np.finfo(float).tiny, 1.0, 2.0, 0.5, 1e308]])
     y = ctx.math_selftest(1, pos)
     ref = np.log(pos)
-    nz = ref != 0
-    assert np.max(np.abs(y[nz] - ref[nz]) / np.maximum(np.abs(ref[nz]), 1e-3)) < 4 * np.finfo(float).eps * 1e3 / 1e3 + 1e-15
+    big = np.abs(ref) > 0.5
+    assert np.max(np.abs(y[big] - ref[big]) / np.abs(ref[big])) < 4 * np.finfo(float).eps
+    assert np.max(np.abs(y[~big] - ref[~big])) < 4e-16  # near 1 the absolute error counts (measured: 7e-17)
     mid = 10.0 ** rng.uniform(-150, 150, 400000)  # 1/x and 1/sqrt(x) stay normal
     assert ulp_err(ctx.math_selftest(2, mid), 1.0 / mid) < 2.0
     assert ulp_err(ctx.math_selftest(3, mid), 1.0 / np.sqrt(mid)) < 3.0
