@@ -128,14 +128,30 @@ class FisherMatrix:
         (The reference has no batch entry: every forecast is one blocking `compute()`; SURVEY 8e names batches of
         forecasts -- many fiducials or survey specifications -- as the unit that fills a GPU.)"""
         out, pending = [], None
+
+        def collect(f, launched):
+            out.append(f._finish(launched))
+            f.release_device()  # a batch keeps at most two forecasts' buffers on the device
+
         for f in forecasts:
             launched = f._launch(max_z_bins)
             if pending is not None:
-                out.append(pending[0]._finish(pending[1]))
+                collect(*pending)
             pending = (f, launched)
         if pending is not None:
-            out.append(pending[0]._finish(pending[1]))
+            collect(*pending)
         return out
+
+    def release_device(self):
+        """Return this forecast's device buffers (plan, table bank) to the context's pool.  Everything that needs them
+        later (`derivs_dict`, `veff_arr`, `photo_derivs`, likelihoods built on this object) re-creates them on demand."""
+        job = getattr(getattr(self, "photo_LSS", None), "_job", None) or self._spectro_job
+        if job is not None:
+            job.close()
+            cs = getattr(job, "cosmo_set", None)
+            if cs is not None and cs._bank is not None:
+                cs._bank.close()
+                cs._bank = None
 
     # --- spectro ------------------------------------------------------------------------------
     def set_pk_settings(self):
@@ -414,7 +430,8 @@ class FisherMatrix:
                                             "backend": "cosmicfishpie_b200"},
                                "options": _jsonify(self.settings), "specifications": _jsonify(self.specs),
                                "fiducialpars": _jsonify(self.fiducialcosmopars),
-                               "freepars": _jsonify(self.freeparams), "allparams": _jsonify(self.allparams)}, indent=2)
+                               "freepars": _jsonify(self.freeparams), "allparams": _jsonify(self.allparams)})
+            # (no indent: the C-accelerated encoder only handles the compact form; same content as the reference's file)
             with open(root + "_specs.json", "w") as jf:  # one write instead of one per token
                 jf.write(text)
         except Exception:  # best effort, like the reference

@@ -170,3 +170,43 @@ def test_two_gpu_sharded_fisher_and_gathered_likelihood(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESULT")][0].split()
     assert float(line[1]) < 1e-12 and float(line[2]) < 1e-12, line
+
+
+def test_nautilus_sampler_driver_joint_likelihood(extfiles, tmp_path, monkeypatch):
+    """The YAML-style driver of the reference (likelihood/sampler.py:86-261) over the vectorised GPU likelihoods, run
+    end to end against the stand-in `nautilus` of tools/_stubs: joint photometric + spectroscopic likelihood, chain and
+    metadata files as the reference writes them, every proposed batch evaluated by ONE loglike_batch call."""
+    monkeypatch.syspath_prepend(os.path.join(REPO, "tools", "_stubs"))
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.sampler import NautilusSampler, load_chain_metadata
+
+    cfg = {
+        "name": "t1", "fiducial": dict(tt.FIDUCIAL), "observables": ["WL", "GCph", "GCsp"], "extfiles": extfiles,
+        "options": {"accuracy": 1, "feedback": 0, "code": "external", "survey_name": "Euclid", "cosmo_model": "w0waCDM",
+                    "survey_name_photo": "Euclid-Photometric-ISTF-Pessimistic",
+                    "survey_name_spectro": "Euclid-Spectroscopic-ISTF-Pessimistic", "ell_sampling": 12,
+                    "spectro_Pk_k_samples": 129, "spectro_Pk_mu_samples": 9},
+        "priors": {"b3": [1.2, 1.5], "AIA": {"type": "gaussian", "loc": 1.72, "scale": 0.05}, "lnbg_2": [0.40, 0.46],
+                   "Ps_1": [0.0, 30.0], "not_a_parameter": [0, 1]},
+        "sampler_settings": {"n_live": 16, "n_networks": 1, "n_batch": 16, "pool": 4},
+    }
+    s = NautilusSampler(cfg, base_dir=str(tmp_path))
+    assert s.prior_chosen.keys == ["b3", "AIA", "lnbg_2", "Ps_1"]
+    naut = s.run()
+    assert naut.vectorized and naut.pool is None and naut.n_calls == 3  # three batches, three vectorised calls
+    chain, fid, meta, labels = load_chain_metadata(os.path.join(str(tmp_path), "chains", "chains_t1"))
+    data = np.loadtxt(chain)
+    assert data.shape == (48, 4 + 2) and open(chain).readline().strip() == "# loglike weights b3 AIA lnbg_2 Ps_1"
+    assert set(fid) == {"b3", "AIA", "lnbg_2", "Ps_1"} and labels["b3"] == "$b_{3}$"
+    for key in ("name", "start_time", "finish_time", "elapsed_time", "evidence_log_z", "chain_file", "priors",
+                "sampler_settings", "observables", "cosmo_model", "survey_name", "code", "cosmo_fiducial_params"):
+        assert key in meta, key
+    # the chain's log-likelihoods are the joint likelihood: photo + spectro, point by point
+    ph, sp = s.likelihood.parts
+    keys = s.prior_chosen.keys
+    for row in data[:3]:
+        d = dict(zip(keys, row[:4]))
+        assert abs(ph.loglike(param_dict=d) + sp.loglike(param_dict=d) - row[5]) <= 1e-9 * abs(row[5])
+    assert np.isclose(np.sum(data[:, 4]), 1.0)
+    # a finished run is not repeated: metadata refresh only
+    assert s.run() is None
