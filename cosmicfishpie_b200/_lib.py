@@ -37,7 +37,7 @@ EXPORTS = [
     "cfp_bank_upload_rows", "cfp_host_alloc", "cfp_host_free", "cfp_spectro_plan_chi2_dev", "cfp_dev_upload",
     "cfp_dev_release", "cfp_photo_plan_create_zmap", "cfp_ctx_aux_stream", "cfp_photo_plan_create_ex",
     "cfp_photo_plan_set_gc_table", "cfp_spectro_plan_chi2_legendre", "cfp_spectro_plan_kernel_ms_part",
-    "cfp_math_selftest",
+    "cfp_math_selftest", "cfp_spectro_plan_terms", "cfp_photo_plan_fetch_windows", "cfp_photo_fisher",
 ]
 
 
@@ -81,6 +81,9 @@ def load():
     lib.cfp_spectro_plan_kernel_ms.restype = C.c_double
     lib.cfp_spectro_plan_kernel_ms_part.argtypes = [_vp, C.c_int]
     lib.cfp_spectro_plan_kernel_ms_part.restype = C.c_double
+    lib.cfp_spectro_plan_terms.argtypes = [_vp, C.c_int, _dp]
+    lib.cfp_photo_plan_fetch_windows.argtypes = [_vp, _dp, _dp]
+    lib.cfp_photo_fisher.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
     lib.cfp_math_selftest.argtypes = [_vp, C.c_int, _dp, C.c_int, _dp]
     lib.cfp_math_selftest.restype = C.c_int
     lib.cfp_photo_plan_kernel_ms.argtypes = [_vp, C.c_int]
@@ -187,6 +190,16 @@ class Context:
         y = np.empty_like(x)
         _check(self.lib.cfp_math_selftest(self.handle, int(which), _p(x), x.size, _p(y)), "cfp_math_selftest")
         return y
+
+    def photo_fisher(self, cov, dC, ell) -> np.ndarray:
+        """cov [Nl][Nb][Nb], dC [npar][Nl][Nb][Nb], ell [Nl] -> F [npar][npar]  (cfp_photo_fisher)."""
+        cov, dC, ell = f64(cov), f64(dC), f64(ell)
+        npar, Nl, Nb = dC.shape[0], dC.shape[1], dC.shape[2]
+        if cov.shape != (Nl, Nb, Nb) or dC.shape[3] != Nb or ell.shape != (Nl,):
+            raise ValueError("photo_fisher: expected cov (Nl, Nb, Nb), dC (npar, Nl, Nb, Nb), ell (Nl,)")
+        out = np.empty((npar, npar))
+        _check(self.lib.cfp_photo_fisher(self.handle, Nl, Nb, npar, _p(cov), _p(dC), _p(ell), _p(out)), "cfp_photo_fisher")
+        return out
 
     def peak_fp64(self, kind: int) -> float:
         """Measured FP64 TFLOP/s: kind 0 = DFMA, 1 = DMMA."""
@@ -462,6 +475,12 @@ class SpectroPlan:
     def fisher_device_ptr(self) -> int:
         return int(self.ctx.lib.cfp_spectro_plan_fisher_d(self.handle) or 0)
 
+    def terms(self, s: int = 0) -> np.ndarray:
+        """[5][Z][Nmu][Nk]: Kaiser term, FoG factor, de-wiggled spectrum, redshift-error factor, P_obs of stencil point s."""
+        out = np.empty((5, self.Z, self.Nmu, self.Nk))
+        _check(self.ctx.lib.cfp_spectro_plan_terms(self.handle, int(s), _p(out)), "cfp_spectro_plan_terms")
+        return out
+
     def chi2(self, shot, data=None, shot_data=None, stream: int = 0, data_dev=None) -> np.ndarray:
         """Wedge chi^2 of every point of the plan against `data` (default: point 0 + noise)."""
         shot = f64(shot)
@@ -576,6 +595,12 @@ class PhotoPlan:
 
     def fisher_device_ptr(self) -> int:
         return int(self.ctx.lib.cfp_photo_plan_fisher_d(self.handle) or 0)
+
+    def fetch_windows(self):
+        """(U, V) [S][Nb][Nz]: W_a / sqrt(H) and W^IA_a / sqrt(H) of the last run."""
+        U, V = np.empty((self.S, self.Nb, self.Nz)), np.empty((self.S, self.Nb, self.Nz))
+        _check(self.ctx.lib.cfp_photo_plan_fetch_windows(self.handle, _p(U), _p(V)), "cfp_photo_plan_fetch_windows")
+        return U, V
 
     def chi2(self, blk_off, blk_n, blk_w, data=None, stream: int = 0) -> np.ndarray:
         """chi^2 of every point of the plan; blocks of tomographic rows with per-multipole weights."""

@@ -708,6 +708,75 @@ static cudaError_t photo_launch_chi2(cfp_ctx* ctx, cudaStream_t st, int S, int N
                                      const double* data_d, const double* w_d, double* lb_d, double* lndet_d, double* q_d,
                                      double* chi2_d);
 
+// ---- Fisher matrix from caller-supplied arrays (the reference's seam photo_LSS_fishermatrix_einsum(noisy_cls,
+// covmat, derivs), cosmicfish.py:643-744): per multipole bin l (left edge), A = covmat[l], Z_p = A^-1 dC_p[l],
+// F_pq(l) = w_l Tr(Z_p Z_q), w_l = (l_centre + 1/2) (l_{i+1} - l_i).  One CTA per bin; A^-1 by Gauss-Jordan with
+// partial pivoting in shared memory (the reference takes the pseudo-inverse; the matrices are non-singular), the Z_p
+// of all parameters in global scratch.  Not a hot path: the forecast itself runs photo_fisher_kernel on the stencil.
+__global__ void __launch_bounds__(256) photo_fisher_user_kernel(int Nl, int Nb, int npar, const double* __restrict__ cov,
+                                                                const double* __restrict__ dC, const double* __restrict__ ell,
+                                                                double* __restrict__ Zs, double* __restrict__ Fl) {
+  extern __shared__ double fsm[];
+  const int l = blockIdx.x, tid = threadIdx.x, n = Nb, ld = 2 * n;
+  double* aug = fsm;  // [n][2n]: (A | I) -> (I | A^-1)
+  __shared__ int piv;
+  for (int e = tid; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    aug[i * ld + j] = cov[((size_t)l * n + i) * n + j];
+    aug[i * ld + n + j] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    if (tid == 0) {
+      int best = k;
+      double bv = fabs(aug[k * ld + k]);
+      for (int i = k + 1; i < n; ++i)
+        if (fabs(aug[i * ld + k]) > bv) bv = fabs(aug[i * ld + k]), best = i;
+      piv = best;
+    }
+    __syncthreads();
+    if (piv != k)
+      for (int j = tid; j < ld; j += blockDim.x) {
+        const double t = aug[k * ld + j];
+        aug[k * ld + j] = aug[piv * ld + j];
+        aug[piv * ld + j] = t;
+      }
+    __syncthreads();
+    const double d = 1.0 / aug[k * ld + k];
+    __syncthreads();
+    for (int j = tid; j < ld; j += blockDim.x) aug[k * ld + j] *= d;
+    __syncthreads();
+    for (int e = tid; e < n * ld; e += blockDim.x) {
+      const int i = e / ld, j = e - i * ld;
+      if (i != k && j != k) aug[i * ld + j] -= aug[i * ld + k] * aug[k * ld + j];
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x)
+      if (i != k) aug[i * ld + k] = 0.0;
+    __syncthreads();
+  }
+  // Z_p = A^-1 dC_p
+  double* Z = Zs + (size_t)l * npar * n * n;
+  for (int e = tid; e < npar * n * n; e += blockDim.x) {
+    const int p = e / (n * n), ij = e - p * n * n, i = ij / n, j = ij - i * n;
+    const double* D = dC + (((size_t)p * Nl + l) * n) * n;
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) acc += aug[i * ld + n + k] * D[(size_t)k * n + j];
+    Z[e] = acc;
+  }
+  __syncthreads();
+  const double lc = 0.5 * (ell[l] + ell[l + 1]);
+  const double w = (lc + 0.5) * (ell[l + 1] - ell[l]);
+  for (int e = tid; e < npar * npar; e += blockDim.x) {
+    const int p = e / npar, q = e - p * npar;
+    const double *Zp = Z + (size_t)p * n * n, *Zq = Z + (size_t)q * n * n;
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) acc += Zp[i * n + j] * Zq[j * n + i];
+    Fl[(size_t)l * npar * npar + e] = w * acc;
+  }
+}
+
 // chi2[s] = sum over (multipole, block) of w q, one warp per point: lanes stride over the point's contiguous q row
 // (coalesced), fixed-order shuffle tree
 __global__ void __launch_bounds__(128) photo_chi2_reduce_kernel(int S, int Nl, int nblk, const double* __restrict__ q,
@@ -1352,3 +1421,59 @@ extern "C" int cfp_cells_chi2(cfp_ctx* ctx, int S, int Nl, int Nb, const double*
   }
   return CFP_OK;
 }
+
+extern "C" int cfp_photo_fisher(cfp_ctx* ctx, int Nl, int Nb, int npar, const double* cov_h, const double* dC_h,
+                                const double* ell_h, double* fisher_h) {
+  CFP_REQUIRE(ctx && cov_h && dC_h && ell_h && fisher_h, "NULL argument");
+  CFP_REQUIRE(Nl >= 2 && Nb >= 1 && Nb <= 64 && npar >= 1, "bad dimensions (at most 64 tomographic rows)");
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int nbins = Nl - 1;
+  double *cov_d = nullptr, *dC_d = nullptr, *ell_d = nullptr, *Z_d = nullptr, *Fl_d = nullptr, *F_d = nullptr;
+  int rc = cfp_upload<double>(ctx, cov_h, (size_t)Nl * Nb * Nb, &cov_d);
+  if (rc == CFP_OK) rc = cfp_upload<double>(ctx, dC_h, (size_t)npar * Nl * Nb * Nb, &dC_d);
+  if (rc == CFP_OK) rc = cfp_upload<double>(ctx, ell_h, (size_t)Nl, &ell_d);
+  if (rc == CFP_OK) rc = cfp_upload<double>(ctx, nullptr, (size_t)nbins * npar * Nb * Nb, &Z_d);
+  if (rc == CFP_OK) rc = cfp_upload<double>(ctx, nullptr, (size_t)nbins * npar * npar, &Fl_d);
+  if (rc == CFP_OK) rc = cfp_upload<double>(ctx, nullptr, (size_t)npar * npar, &F_d);
+  if (rc == CFP_OK) {
+    const size_t smem = (size_t)Nb * 2 * Nb * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(photo_fisher_user_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      photo_fisher_user_kernel<<<nbins, 256, smem, st>>>(Nl, Nb, npar, cov_d, dC_d, ell_d, Z_d, Fl_d);
+      photo_reduce_kernel<<<(npar * npar + 7) / 8, 256, 0, st>>>(Fl_d, nbins, npar * npar, F_d);
+      ctx->launches += 2;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(fisher_h, F_d, (size_t)npar * npar * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      cfp_set_error("cfp_photo_fisher: %s", cudaGetErrorString(e));
+      rc = CFP_ERR_CUDA;
+    }
+  }
+  for (void* q : {(void*)cov_d, (void*)dC_d, (void*)ell_d, (void*)Z_d, (void*)Fl_d, (void*)F_d}) cfp_dev_free(ctx, q);
+  return rc;
+}
+
+extern "C" int cfp_photo_plan_fetch_windows(cfp_photo_plan* pl, double* U_h, double* V_h) {
+  CFP_REQUIRE(pl && U_h && V_h, "NULL argument");
+  if (!pl->ran) {
+    cfp_set_error("cfp_photo_plan_fetch_windows: plan has not been run");
+    return CFP_ERR_STATE;
+  }
+  CFP_CUDA(cudaSetDevice(pl->ctx->device));
+  CFP_CUDA(cudaEventSynchronize(pl->run1));
+  const int nrow_pad = pl->nb * 8;
+  std::vector<double> tmp((size_t)pl->S * nrow_pad * pl->ldz);
+  for (int which = 0; which < 2; ++which) {
+    CFP_CUDA(cudaMemcpy(tmp.data(), which == 0 ? pl->U_d : pl->V_d, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    double* dst = which == 0 ? U_h : V_h;
+    for (int s = 0; s < pl->S; ++s)
+      for (int a = 0; a < pl->Nb; ++a)
+        for (int z = 0; z < pl->Nz; ++z)
+          dst[((size_t)s * pl->Nb + a) * pl->Nz + z] = tmp[((size_t)s * nrow_pad + a) * pl->ldz + z];
+  }
+  return CFP_OK;
+}
+

@@ -1400,6 +1400,44 @@ __global__ void __launch_bounds__(TILE, 3) spectro_data_kernel(SpectroParams P, 
   }
 }
 
+// The factors of P_obs of stencil point `s` as separate lattices (the reference's accessors kaiserTerm, FingersOfGod,
+// dewiggled_pdd, spec_err_z and observed_Pgg: spectro_obs.py:476-506, 584-676, 811-911), evaluated with the same
+// table look-ups and row constants as the fused kernels.  out[t][zb][cell], t = 0 Kaiser term  b(z) q(k') + f(k') mu'^2
+// [x sigma8], 1 Fingers-of-God factor, 2 de-wiggled spectrum [/ sigma8^2], 3 redshift-error factor exp(-err^2 / 2),
+// 4 P_obs.
+__global__ void __launch_bounds__(TILE, 3) spectro_terms_kernel(SpectroParams P, int s, double* __restrict__ out) {
+  __shared__ SDev sp;
+  __shared__ MathTab mt;
+  const int zb = blockIdx.y, tid = threadIdx.x;
+  if (tid < (int)(sizeof(SDev) / sizeof(double)))
+    reinterpret_cast<double*>(&sp)[tid] = reinterpret_cast<const double*>(P.sdev + (size_t)zb * P.S + s)[tid];
+  math_tables_fill(mt, tid, TILE);
+  __syncthreads();
+  const int64_t lattice = (int64_t)P.Nmu * P.Nk;
+  const size_t plane = (size_t)P.Z * lattice;
+  int hA = -1, hB = -1, hN = -1, row = -1;
+  RowC rc;
+  const int64_t stride = (int64_t)gridDim.x * TILE;
+  for (CellWalk w((int64_t)blockIdx.x * TILE + tid, stride, P.Nk); w.cell < lattice; w.next(stride, P.Nk)) {
+    if (w.mi != row) {
+      row = w.mi;
+      rc = row_consts(sp, P.flags, __ldg(P.mu + row), __ldg(P.smu + row));
+    }
+    const double k = __ldg(P.k + w.ki);
+    double err2, qf, F, W;
+    const double X = eval_x(mt, sp, rc, P.flags, k, hA, hB, hN, err2, qf, F, W);
+    const double kap = k * rc.G;
+    const double t = kap * rc.fogc;
+    const double fogden = ((P.flags & CFP_SPF_FOG) && !(P.flags & CFP_SPF_LINEAR)) ? fma(t, t, 1.0) : 1.0;
+    const size_t o = (size_t)zb * lattice + w.cell;
+    out[0 * plane + o] = fma(sp.bias, qf, F);
+    out[1 * plane + o] = 1.0 / fogden;
+    out[2 * plane + o] = (W * fogden) / sp.bao;  // W = bao / s8^2 * dewiggled / FoG denominator
+    out[3 * plane + o] = exp(-0.5 * err2);       // P_obs carries its square, exp(-err^2)
+    out[4 * plane + o] = X * tab_exp_neg(mt, -err2) + sp.pshot;
+  }
+}
+
 // Wedge chi^2 of a batch of points.  grid (gx, chunks): a chunk is up to CHI_CH points of ONE bin whose scalar blocks
 // differ only in the galaxy bias (a sampler that draws nuisance parameters around cosmologies of the bank produces
 // exactly that): the table look-ups, exp and FoG of a cell are evaluated once per chunk -- X = (b q + F)^2 W, see
@@ -2602,6 +2640,34 @@ extern "C" double cfp_spectro_plan_kernel_ms(cfp_spectro_plan* pl) {
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, pl->kev0, pl->kev1) != cudaSuccess) return -1.0;
   return ms;
+}
+
+extern "C" int cfp_spectro_plan_terms(cfp_spectro_plan* pl, int s, double* terms_h) {
+  CFP_REQUIRE(pl && terms_h, "NULL argument");
+  CFP_REQUIRE(s >= 0 && s < pl->S, "stencil point out of range");
+  cfp_ctx* ctx = pl->ctx;
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t n = (size_t)5 * pl->Z * pl->Nmu * pl->Nk;
+  double* out_d = nullptr;
+  CFP_CUDA(cfp_dev_alloc(ctx, (void**)&out_d, n * sizeof(double)));
+  SpectroParams P;
+  spectro_fill_params(pl, 16, P);  // (batch mode: scalar blocks and piece tables, no work list)
+  int rc = spectro_prepare(pl, P, st);
+  if (rc == CFP_OK) {
+    const int gx = std::max(1, std::min((int)(((size_t)pl->Nmu * pl->Nk + TILE - 1) / TILE), (ctx->sm_count * 3) / pl->Z + 1));
+    spectro_terms_kernel<<<dim3(gx, pl->Z), TILE, 0, st>>>(P, s, out_d);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(terms_h, out_d, n * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      cfp_set_error("cfp_spectro_plan_terms: %s", cudaGetErrorString(e));
+      rc = CFP_ERR_CUDA;
+    }
+  }
+  cfp_dev_free(ctx, out_d);
+  return rc;
 }
 
 extern "C" int cfp_math_selftest(cfp_ctx* ctx, int which, const double* x_h, int n, double* y_h) {

@@ -327,19 +327,34 @@ class FisherMatrix:
         return self.photo_LSS.compute_derivs()
 
     def photo_LSS_fishermatrix_einsum(self, noisy_cls=None, covmat=None, derivs=None, lss_obj=None):
-        """The Fisher matrix of the configured photometric job (cosmicfish.py:544-744).  The device assembles
-        covariance, derivatives and trace in one pass from the job's own stencil, so the arguments are accepted only
-        when they are what `lss_obj.compute_covmat()` / `compute_derivs()` returned; anything else (say, derivatives
-        from another scheme) is refused instead of being silently ignored -- select the scheme with
-        options["stencil"]."""
-        obj = lss_obj if lss_obj is not None else self.photo_LSS
+        """The Fisher matrix of a photometric probe (cosmicfish.py:544-744).
+
+        Called without arrays (or with the very objects `lss_obj.compute_covmat()` / `compute_derivs()` returned) the
+        configured job is assembled in one device pass from its own stencil.  Called with the caller's own arrays --
+        `noisy_cls` (for its "ells"), `covmat` (one matrix or DataFrame per multipole) and `derivs`
+        ({parameter: {"X ixY j": dC/dtheta (Nl,)}}, from any derivative scheme) -- the reference's assembly
+        sum_l (l_c + 1/2) dl Tr(dC_p S^-1 dC_q S^-1) with left-edge arrays runs on the device on exactly those arrays
+        (cfp_photo_fisher)."""
+        obj = lss_obj if lss_obj is not None else getattr(self, "photo_LSS", None)
         own = getattr(obj, "__dict__", {})
-        for name, given in (("noisy_cls", noisy_cls), ("covmat", covmat), ("derivs", derivs)):
-            if given is not None and given is not own.get(name):
-                raise NotImplementedError(
-                    f"photo_LSS_fishermatrix: a user-supplied `{name}` is not supported; the Fisher matrix is assembled "
-                    "on the device from the configured job (options['stencil'] selects the derivative scheme)")
-        return obj.compute_fisher(self.freeparams)
+        given = {"noisy_cls": noisy_cls, "covmat": covmat, "derivs": derivs}
+        if all(v is None or v is own.get(k) for k, v in given.items()):
+            return obj.compute_fisher(self.freeparams)
+        if covmat is None and obj is not None:
+            noisy_cls, covmat = obj.compute_covmat()
+        if derivs is None and obj is not None:
+            derivs = obj.compute_derivs()
+        if noisy_cls is None or covmat is None or derivs is None:
+            raise ValueError("photo_LSS_fishermatrix: pass noisy_cls, covmat and derivs (or an lss_obj to take them from)")
+        cols = []
+        for o in self.observables:  # cosmicfish.py:686-691
+            if o in ("GCph", "WL"):
+                cols.extend(f"{o} {i + 1}" for i in range(len(self.specs["z_bins_" + o]) - 1))
+        cov = np.array([np.asarray(c, dtype=float) for c in covmat])
+        dC = np.array([[[np.asarray(derivs[par][f"{a}x{b}"], dtype=float) for b in cols] for a in cols]
+                       for par in self.freeparams])                      # [npar][Nb][Nb][Nl]
+        dC = np.ascontiguousarray(np.transpose(dC, (0, 3, 1, 2)))        # [npar][Nl][Nb][Nb]
+        return self.ctx.photo_fisher(cov, dC, np.asarray(noisy_cls["ells"], dtype=float))
 
     photo_LSS_fishermatrix = photo_LSS_fishermatrix_einsum
 

@@ -477,6 +477,53 @@ class ComputeCls:
 
     computecls = computecls_vectorized = lambda self: (self.compute_all(), self.result)[1]
 
+    # --- radial kernels and single spectra (photo_obs.py:514-615, 878-928), from the device run ------------------
+    def _windows(self):
+        if getattr(self, "_win", None) is None:
+            allpars = {**self.cosmopars, **self.IApars, **self.biaspars, **self.photopars}
+            job = PhotoJob(self.configuration, [allpars], np.zeros((1, 1)), np.ones(1), self.cosmo_set)
+            plan = job.run()
+            U, V = plan.fetch_windows()
+            sqrtH = np.sqrt(self.cosmo_set.cosmos[job.cosmo_of_s[0]].on_grid("Hubble", self.grid.z))
+            bias = job.bias[0] if getattr(job, "zmap", None) is None else job.bias[0][:, job.zmap]
+            job.close()
+            self._win = (U[0] * sqrtH[None, :], V[0] * sqrtH[None, :], bias)
+        return self._win
+
+    def _row(self, obs, i):
+        try:
+            return self.grid.rows.index((obs, int(i)))
+        except ValueError:
+            raise ValueError(f"{obs} bin {i} is not part of this job") from None
+
+    def _at(self, z, values):
+        """Values on the job's z grid; other redshifts through a cubic interpolant of the grid values (the device
+        integrates on the grid; the reference evaluates its closed forms wherever asked)."""
+        z = np.asarray(z, dtype=float)
+        if z.shape == self.z.shape and np.array_equal(z, self.z):
+            return values.copy()
+        from scipy.interpolate import interp1d
+
+        return interp1d(self.z, values, kind="cubic")(z)
+
+    def lensing_kernel(self, z, i):
+        """(W_i^WL, W_i^IA)(z): lensing efficiency term and intrinsic-alignment term of bin i (photo_obs.py:558-615)."""
+        U, V, _ = self._windows()
+        a = self._row("WL", i)
+        return self._at(z, U[a]), self._at(z, V[a])
+
+    def galaxy_kernel(self, z, i):
+        """n_i(z) H(z) of clustering bin i -- without the galaxy bias, as in the reference (photo_obs.py:514-556)."""
+        U, _, bias = self._windows()
+        a = self._row("GCph", i)
+        return self._at(z, U[a] / bias[a])
+
+    def clsintegral(self, obs1, bin1, obs2, bin2):
+        """C_ell of one pair of tomographic rows (photo_obs.py:878-928) from the device's Limber contraction."""
+        if self.result is None:
+            self.compute_all()
+        return self.result[f"{obs1} {bin1}x{obs2} {bin2}"]
+
 
 class PhotoCov:
     """C_ell cache, noise, covariance and the Fisher of the photometric probes

@@ -286,6 +286,40 @@ class ComputeGalSpectro:
             sp *= self.nuisance.gcsp_rescale_sigmapv_at_z(zz, sigma_key="sigmap")
         return sp
 
+    # --- the factors of P_obs on a lattice, evaluated by the device (cfp_spectro_plan_terms) ----------------------
+    def _terms(self, z, k, mu, b_i=None):
+        """[5][Nmu][Nk] at redshift z for a separable (k, mu) mesh: Kaiser, FoG, de-wiggled, spec-z error, P_obs."""
+        k, mu = np.asarray(k, dtype=float), np.asarray(mu, dtype=float)
+        kb, mb = np.broadcast_arrays(k, mu)
+        if not (kb.ndim == 2 and np.all(kb == kb[0:1, :]) and np.all(mb == mb[:, 0:1])):
+            raise NotImplementedError("the term accessors take a separable mesh (k, mu from np.meshgrid)")
+        return _evaluate_terms(self, float(z), kb[0, :], mb[:, 0], b_i=b_i)
+
+    def kaiserTerm(self, z, k, mu, b_i=None, just_rsd=False, bias_sample="g"):
+        """b(z) b(k) + f(z, k) mu^2 at the (k, mu) given -- like the reference's accessor, which `observed_Pgg` calls
+        with the already AP-distorted coordinates (spectro_obs.py:584-637); `just_rsd`: 1 + (f / b) mu^2."""
+        if bias_sample != "g":
+            raise NotImplementedError("only the galaxy sample is in scope")
+        kaiser = self._terms(z, k, mu, b_i=b_i)[0]
+        if just_rsd:
+            rsd = self._terms(z, k, mu, b_i=0.0)[0]  # f mu^2
+            return 1 + rsd / (kaiser - rsd)
+        return kaiser
+
+    def FingersOfGod(self, z, k, mu, mode="Lorentz"):
+        """1 / (1 + (k mu sigma_p)^2) (spectro_obs.py:639-676; 1 when FoG is switched off or the model is linear)."""
+        if mode != "Lorentz":
+            raise NotImplementedError("only the Lorentzian damping exists in the Fisher path")
+        return self._terms(z, k, mu)[1]
+
+    def dewiggled_pdd(self, z, k, mu):
+        """P_lin e^{-g} + P_nw (1 - e^{-g}), g = sigma_v^2(mu) k^2, normalised like the reference (spectro_obs.py:811-843)."""
+        return self._terms(z, k, mu)[2]
+
+    def spec_err_lattice(self, z, k, mu):
+        """exp(-err^2 / 2) on the lattice: `spec_err_z` of the reference evaluated by the device."""
+        return self._terms(z, k, mu)[3]
+
     def flags(self) -> int:
         f = 0
         if self.APbool:
@@ -482,6 +516,27 @@ def _evaluate_lattice(points: List[ComputeGalSpectro], zs, kgrid, mugrid, b_i=No
     _, lnp, _, _ = plan.fetch(lnp=True)
     plan.close()
     return lnp
+
+
+def _evaluate_terms(point: ComputeGalSpectro, z: float, kgrid, mugrid, b_i=None) -> np.ndarray:
+    """[5][Nmu][Nk] factors of P_obs of one parameter point at redshift z (cfp_spectro_plan_terms)."""
+    cs = point.cosmo_set
+    scal = np.array([[point.scalar_block(z)]])
+    if b_i is not None:
+        scal[:, :, _lib.SP_BIAS] = float(b_i)
+        scal[:, :, _lib.SP_A1] = scal[:, :, _lib.SP_A2] = 0.0
+    # the reference's accessors take (k, mu) as given (observed_Pgg hands them the AP-distorted values): no remap here
+    scal[:, :, _lib.SP_KHFAC] = 1.0
+    flags = point.flags() & ~_lib.SPF_AP
+    pk, pp = _pnw_arrays(cs, [z], set() if point.linear_switch else {point.cosmo_index})
+    plan = _lib.SpectroPlan(
+        cs.context(), cs.bank(), k=kgrid, mu=mugrid, wk=np.zeros_like(kgrid), wmu=np.zeros_like(mugrid), scal=scal,
+        alias=np.zeros((1, 1), dtype=np.int32), pnw_k=pk, pnw_p=pp, stw=np.zeros((1, 1)), stden=np.ones(1),
+        ps_bin=np.array([-1], dtype=np.int32), ps_src=0, nbar=np.zeros(1), vol=np.zeros(1), flags=flags,
+        tab_plin=table_slots(point.settings)[0], tab_f=table_slots(point.settings)[1])
+    out = plan.terms(0)[:, 0]
+    plan.close()
+    return out
 
 
 class SpectroCov:
@@ -723,6 +778,23 @@ class SpectroDerivs:
         for i in range(len(self.z_array)):
             out[i] = lat[0, i] if self._gather is None else lat[0, i][self._gather]
         return out
+
+    def exact_derivs(self, par):
+        """Analytic derivative of ln P_obs w.r.t. a shot-noise parameter Ps_i: delta_{i, bin} / P_obs, with P_obs of the
+        LAST evaluated stencil point (spectro_cov.py:510-532); None for any other parameter -- the
+        `special_deriv_function` signature of the derivative engine.  Read from the device job's derivative lattices."""
+        if "Ps" not in par:
+            return None
+        if getattr(self, "derivs", None) is None or par not in self.derivs:
+            self.compute_derivs()
+        if par not in self.derivs:
+            return None
+        return {"z_bins": self.z_array, **{i: self.derivs[par][i] for i in range(len(self.z_array))}}
+
+    def kronecker_bins(self, par):
+        """[delta_{i, bin of par}] over the bins (spectro_cov.py:534-561)."""
+        ib = int(par.split("_")[-1]) - 1
+        return np.array([1.0 if i == ib else 0.0 for i in range(len(self.z_array))])
 
     def build_job(self, cov: SpectroCov, freeparams=None) -> SpectroJob:
         if freeparams:

@@ -189,6 +189,11 @@ double cfp_spectro_plan_kernel_ms(cfp_spectro_plan* plan);
 /* Parts of the lattice pass of the last run: 0 = the whole pass (as above), 1 = the weights pre-pass, 2 = the main
  * kernel (spectro_fisher_pairs_kernel); -1 when the last run did not take the pair kernels. */
 double cfp_spectro_plan_kernel_ms_part(cfp_spectro_plan* plan, int which);
+/* The factors of P_obs of stencil point s as separate lattices, terms_h[5][Z][Nmu][Nk] (host): 0 Kaiser term, 1
+ * Fingers-of-God factor, 2 de-wiggled spectrum, 3 redshift-error factor, 4 P_obs.  Replaces ComputeGalSpectro.kaiserTerm /
+ * FingersOfGod / dewiggled_pdd / spec_err_z / observed_Pgg (cosmicfishpie/LSSsurvey/spectro_obs.py:476-506, 584-676,
+ * 811-911) evaluated on a lattice. */
+int cfp_spectro_plan_terms(cfp_spectro_plan* plan, int s, double* terms_h);
 /* Test hook: y[i] = f(x[i]) on the device for the branch-free FP64 functions of the lattice loops, so that tests can
  * sweep their stated domains against libm.  which: 0 exp(x), x <= 0 (table version); 1 log(x), x > 0 normal;
  * 2 1/x; 3 1/sqrt(x); 4 1/x by division; 5 exp(x), x <= 0 (pair-kernel version).  Host buffers. */
@@ -273,6 +278,16 @@ int cfp_photo_plan_run(cfp_photo_plan* plan, void* stream);
 /* Device time [ms] of one kernel of the last run: which = 0 Limber table, 1 C_ell contraction (DMMA),
  * 2 Cholesky/trace Fisher; synchronises. */
 double cfp_photo_plan_kernel_ms(cfp_photo_plan* plan, int which);
+/* Radial kernels of the last run on the plan's z grid, [S][Nb][Nz] each (host): U = W_a / sqrt(H) (lensing efficiency
+ * term or galaxy kernel x bias), V = W^IA_a / sqrt(H).  Replaces ComputeCls.lensing_kernel / galaxy_kernel
+ * (cosmicfishpie/LSSsurvey/photo_obs.py:514-615) at the grid redshifts. */
+int cfp_photo_plan_fetch_windows(cfp_photo_plan* plan, double* U_h, double* V_h);
+/* Fisher matrix from caller-supplied arrays -- the reference's seam photo_LSS_fishermatrix_einsum(noisy_cls, covmat,
+ * derivs), cosmicfishpie/fishermatrix/cosmicfish.py:643-744: cov_h[Nl][Nb][Nb] (the covariance matrices), dC_h[npar][Nl][Nb][Nb]
+ * (derivatives of the spectra), ell_h[Nl] (bin edges) -> fisher_h[npar][npar] = sum over the Nl - 1 bins of
+ * (l_centre + 1/2) dl Tr(cov^-1 dC_p cov^-1 dC_q), left-edge arrays.  Host buffers, Nb <= 64. */
+int cfp_photo_fisher(cfp_ctx* ctx, int Nl, int Nb, int npar, const double* cov_h, const double* dC_h, const double* ell_h,
+                     double* fisher_h);
 const double* cfp_photo_plan_fisher_d(const cfp_photo_plan* plan);
 /* fisher_h[npar][npar], cls_h[S][Nl][Nb][Nb] (signal only, no noise), sqrtp_h[NC][Nl][Nz] */
 int cfp_photo_plan_fetch(cfp_photo_plan* plan, double* fisher_h, double* cls_h, double* sqrtp_h);

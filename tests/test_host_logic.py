@@ -233,19 +233,6 @@ def test_spectro_coordinate_helpers_equal_oracle(extfiles, toy_bank, tmp_path):
     assert mine.k_units_change(kk) is kk
 
 
-def test_photo_fishermatrix_refuses_foreign_derivatives(extfiles, tmp_path):
-    """photo_LSS_fishermatrix(noisy_cls, covmat, derivs) of the reference assembles whatever it is given; here the
-    device assembles the configured job, so foreign inputs are refused loudly, not ignored."""
-    from cosmicfishpie_b200 import photo
-
-    fm = make_fm(extfiles, tmp_path, ["WL"], {"Omegam": 0.01})
-    pc = photo.PhotoCov(fm.fiducialcosmopars, fm.photopars, fm.IApars, fm.photobiaspars, configuration=fm)
-    with pytest.raises(NotImplementedError, match="derivs"):
-        fm.photo_LSS_fishermatrix(derivs={"Omegam": {}}, lss_obj=pc)
-    with pytest.raises(NotImplementedError, match="covmat"):
-        fm.photo_LSS_fishermatrix_einsum(covmat=[], lss_obj=pc)
-
-
 def test_fisher_integral_is_scipy_simpson(extfiles, tmp_path):
     """FisherMatrix.fisher_integral (cosmicfish.py:495-512): Simpson over mu then k, even sample counts included."""
     from scipy.integrate import simpson

@@ -210,3 +210,102 @@ def test_nautilus_sampler_driver_joint_likelihood(extfiles, tmp_path, monkeypatc
     assert np.isclose(np.sum(data[:, 4]), 1.0)
     # a finished run is not repeated: metadata refresh only
     assert s.run() is None
+
+
+def test_einsum_seam_accepts_user_arrays(photo_fm):
+    """SURVEY 8b seam (4): photo_LSS_fishermatrix_einsum(noisy_cls, covmat, derivs) on the CALLER's arrays
+    (cosmicfish.py:643-744) -- here the job's own covariance and derivatives passed as copies, and derivatives from the
+    `derivatives` engine driven with a user callable: both must give the forecast's matrix."""
+    from cosmicfishpie_b200.derivatives import derivatives
+
+    fm = photo_fm
+    lss = fm.photo_LSS
+    F_job = fm.fisher_array
+    noisy, covmat = lss.compute_covmat()
+    derivs = lss.compute_derivs()
+    cov_copy = [np.array(c, dtype=float) for c in covmat]
+    der_copy = {p: {k: np.array(v) for k, v in d.items()} for p, d in derivs.items()}
+    F_user = fm.photo_LSS_fishermatrix_einsum(noisy_cls=dict(noisy), covmat=cov_copy, derivs=der_copy)
+    assert np.max(np.abs(F_user - F_job) / np.abs(F_job)) < 1e-9
+    # numpy restatement of the reference's einsum assembly on the same arrays
+    ells = noisy["ells"]
+    cols = list(covmat[0].columns)
+    lc, dl = 0.5 * (ells[1:] + ells[:-1]), np.diff(ells)
+    inv = np.linalg.pinv(np.array(cov_copy))
+    der = np.array([[[der_copy[p][f"{a}x{b}"] for b in cols] for a in cols] for p in fm.freeparams])
+    ref = np.zeros((len(fm.freeparams),) * 2)
+    for li in range(len(lc)):
+        d = der[:, :, :, li]
+        m2 = np.einsum("ij,pjk,kl->pil", inv[li], d, inv[li])
+        ref += np.einsum("pij,qji->pq", d, m2) * (lc[li] + 0.5) * dl[li]
+    assert np.max(np.abs(F_user - ref) / np.abs(ref)) < 1e-9
+    # the derivative engine on a USER callable (host route) and on the package's own getcls (device route)
+    free2 = {"Omegam": 0.01, "AIA": fm.freeparams["AIA"]}
+    calls = []
+
+    def my_observable(pars):
+        calls.append(dict(pars))
+        return lss.getcls(pars)
+
+    d_host = derivatives(my_observable, lss.allparsfid, freeparams=free2, observables_type=["WL", "GCph"]).result
+    d_dev = derivatives(lss.getcls, lss.allparsfid, freeparams=free2, observables_type=["WL", "GCph"]).result
+    assert len(calls) == 4
+    for p in free2:
+        for key in ("WL 1xWL 1", "WL 3xGCph 5", "GCph 10xGCph 10"):
+            ref_d = derivs[p][key]
+            assert np.allclose(d_host[p][key], ref_d, rtol=1e-9, atol=1e-22), (p, key)
+            assert np.allclose(d_dev[p][key], ref_d, rtol=1e-12, atol=1e-25), (p, key)
+        assert np.array_equal(d_host[p]["ells"], ells)
+
+
+def test_term_accessors_match_the_oracle(extfiles, tmp_path, toy_bank):
+    """SURVEY 8b seams: kaiserTerm / FingersOfGod / dewiggled_pdd (spectro_obs.py:584-676, 811-843), lensing_kernel /
+    galaxy_kernel / clsintegral (photo_obs.py:514-615, 878-928) and SpectroDerivs.exact_derivs (spectro_cov.py:510-532),
+    evaluated by the device, against the oracle's restatement of the same reference functions."""
+    import yaml
+
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+    from oracle.cosmo import Bank
+    from oracle.spectro import DEFAULT_SETTINGS, GalSpectro
+
+    o = base_options(tmp_path, spectro_Pk_k_samples=65, spectro_Pk_mu_samples=9)
+    fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"h": 0.01}, options=o, observables=["GCsp"], extfiles=extfiles)
+    fm.compute()
+    cp = dict(tt.FIDUCIAL, h=tt.FIDUCIAL["h"] * 1.01)
+    from cosmicfishpie_b200.spectro import ComputeGalSpectro
+
+    obs = ComputeGalSpectro(cp, fiducial_cosmopars=dict(tt.FIDUCIAL), configuration=fm)
+    sp = yaml.safe_load(open(os.path.join(REPO, "cosmicfishpie_b200", "data", "specs",
+                                          "Euclid-Spectroscopic-ISTF-Pessimistic.yaml")))["specifications"]
+    ob = Bank(toy_bank, tt.FIDUCIAL, tt.COSMO_KEYS)
+    ref = GalSpectro(ob.cosmo(cp), ob.cosmo(dict(tt.FIDUCIAL)), sp, dict(DEFAULT_SETTINGS),
+                     dict(sp["sp_bias_parametrization"]["linear_log"]), {})
+    z = 1.2
+    k, mu = fm.Pk_kmesh, fm.Pk_mumesh
+    for name, oname in (("kaiserTerm", "kaiser"), ("FingersOfGod", "fog"), ("dewiggled_pdd", "dewiggled")):
+        got, want = getattr(obs, name)(z, k, mu), getattr(ref, oname)(z, k, mu)
+        assert np.max(np.abs(got - want) / np.abs(want)) < 1e-12, name
+    assert np.max(np.abs(obs.spec_err_lattice(z, k, mu) - ref.spec_err_z(z, k, mu))) < 1e-14
+    bterm = ref.nuis.bias_at_z(z)
+    rsd = obs.kaiserTerm(z, k, mu, just_rsd=True)   # 1 + (f / b) mu^2
+    assert np.max(np.abs(rsd - (1 + (ref.kaiser(z, k, mu) - bterm) / bterm))) < 1e-12
+    # exact shot-noise derivative: delta_{i,bin} / P_obs of the last evaluated stencil point
+    ex = fm.pk_deriv.exact_derivs("Ps_2")
+    assert fm.pk_deriv.exact_derivs("h") is None and np.all(ex[0] == 0) and np.all(ex[1] > 0)
+    assert np.array_equal(ex[1], fm.derivs_dict["Ps_2"][1])
+    # photometric kernels
+    po = base_options(tmp_path / "p", survey_name_photo="Euclid-Photometric-ISTF-Pessimistic", survey_name_spectro=False,
+                      ell_sampling=12)
+    fp = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"Omegam": 0.01}, options=po, observables=["WL", "GCph"],
+                      extfiles=extfiles)
+    fp.compute()
+    cl = fp.photo_obs_fid
+    Wwl, Wia = cl.lensing_kernel(cl.z, 4)
+    Wgc = cl.galaxy_kernel(cl.z, 7)
+    assert Wwl.shape == cl.z.shape and np.all(Wwl >= 0) and Wwl[5] > 0 and np.all(Wia <= 0) and np.all(Wgc >= 0)
+    # W^GC = n_i(z) H(z) without bias (photo_obs.py:542): check against the window object and the Hubble table
+    H = fp.fiducialcosmo.on_grid("Hubble", cl.z)
+    assert np.allclose(Wgc, cl.window.norm_ngal_photoz(cl.z, 7, "GCph") * H, rtol=1e-12, atol=1e-300)
+    cl.compute_all()
+    assert np.array_equal(cl.clsintegral("WL", 2, "GCph", 5), cl.result["WL 2xGCph 5"])
