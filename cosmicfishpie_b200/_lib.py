@@ -38,6 +38,7 @@ EXPORTS = [
     "cfp_dev_release", "cfp_photo_plan_create_zmap", "cfp_ctx_aux_stream", "cfp_photo_plan_create_ex",
     "cfp_photo_plan_set_gc_table", "cfp_spectro_plan_chi2_legendre", "cfp_spectro_plan_kernel_ms_part",
     "cfp_math_selftest", "cfp_spectro_plan_terms", "cfp_photo_plan_fetch_windows", "cfp_photo_fisher",
+    "cfp_fisher_batch_post", "cfp_fisher_batch_add",
 ]
 
 
@@ -84,6 +85,8 @@ def load():
     lib.cfp_spectro_plan_terms.argtypes = [_vp, C.c_int, _dp]
     lib.cfp_photo_plan_fetch_windows.argtypes = [_vp, _dp, _dp]
     lib.cfp_photo_fisher.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
+    lib.cfp_fisher_batch_post.argtypes = [_vp, C.c_int, C.c_int, _dp, C.c_int, _ip, C.c_double, _dp, _dp, _dp]
+    lib.cfp_fisher_batch_add.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
     lib.cfp_math_selftest.argtypes = [_vp, C.c_int, _dp, C.c_int, _dp]
     lib.cfp_math_selftest.restype = C.c_int
     lib.cfp_photo_plan_kernel_ms.argtypes = [_vp, C.c_int]
@@ -199,6 +202,27 @@ class Context:
             raise ValueError("photo_fisher: expected cov (Nl, Nb, Nb), dC (npar, Nl, Nb, Nb), ell (Nl,)")
         out = np.empty((npar, npar))
         _check(self.lib.cfp_photo_fisher(self.handle, Nl, Nb, npar, _p(cov), _p(dC), _p(ell), _p(out)), "cfp_photo_fisher")
+        return out
+
+    def fisher_batch_post(self, F, keep=None, coef=1.0):
+        """F [B][n][n] -> (sigma [B][n], marginal [B][m][m] or None, fom [B] or None)  (cfp_fisher_batch_post)."""
+        F = f64(F)
+        B, n = F.shape[0], F.shape[1]
+        keep = None if keep is None else i32(keep)
+        m = 0 if keep is None else keep.size
+        sigma = np.empty((B, n))
+        marg = np.empty((B, m, m)) if m else None
+        fom = np.empty(B) if m else None
+        _check(self.lib.cfp_fisher_batch_post(self.handle, B, n, _p(F), m, _p(keep, _ip), float(coef), _p(sigma),
+                                              _p(marg), _p(fom)), "cfp_fisher_batch_post")
+        return sigma, marg, fom
+
+    def fisher_batch_add(self, a, b, map_a, map_b, n_out) -> np.ndarray:
+        a, b = f64(a), f64(b)
+        out = np.empty((a.shape[0], n_out, n_out))
+        _check(self.lib.cfp_fisher_batch_add(self.handle, a.shape[0], a.shape[1], b.shape[1], int(n_out),
+                                             _p(i32(map_a), _ip), _p(i32(map_b), _ip), _p(a), _p(b), _p(out)),
+               "cfp_fisher_batch_add")
         return out
 
     def peak_fp64(self, kind: int) -> float:

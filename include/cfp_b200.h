@@ -366,6 +366,21 @@ int cfp_legendre_covariance(cfp_ctx* ctx, int Nk, int Z, const double* pl_h, con
 int cfp_legendre_chi2(cfp_ctx* ctx, int S, int Nk, int Z, const double* pl_data_h, const double* pl_theory_h,
                       const double* icov_h, double* chi2_h);
 
+/* ---- batched Fisher-matrix post-processing ------------------------------------------------------
+ * B symmetric positive-definite matrices of n <= 64 parameters in one launch.
+ * cfp_fisher_batch_post: sigma_h[B][n] = coef * sqrt(diag(F^-1))  (fisher_matrix.get_confidence_bounds,
+ *   cosmicfishpie/analysis/fisher_matrix.py:705-733, coef = sqrt(2) erfinv(confidence level)); with m > 0 also the
+ *   Fisher matrix marginalised onto the parameters keep_h[m]: marg_h[B][m][m] = ((F^-1)[keep][keep])^-1
+ *   (analysis/fisher_operations.py:177-237) and fom_h[B] = sqrt(det marg) (for m = 2, e.g. (w0, wa): the dark-energy
+ *   figure of merit).  A matrix that is not positive definite gives NaN.
+ * cfp_fisher_batch_add: out_h[B][n_out][n_out] = a_h[b] scattered through map_a_h[na] + b_h[b] scattered through
+ *   map_b_h[nb] -- the sum over the union of parameters of fisher_matrix.__add__ (analysis/fisher_matrix.py:462-548),
+ *   the name -> index maps being the caller's.  Host buffers. */
+int cfp_fisher_batch_post(cfp_ctx* ctx, int B, int n, const double* fisher_h, int m, const int32_t* keep_h, double coef,
+                          double* sigma_h, double* marg_h, double* fom_h);
+int cfp_fisher_batch_add(cfp_ctx* ctx, int B, int na, int nb, int n_out, const int32_t* map_a_h, const int32_t* map_b_h,
+                         const double* a_h, const double* b_h, double* out_h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -309,3 +309,53 @@ def test_term_accessors_match_the_oracle(extfiles, tmp_path, toy_bank):
     assert np.allclose(Wgc, cl.window.norm_ngal_photoz(cl.z, 7, "GCph") * H, rtol=1e-12, atol=1e-300)
     cl.compute_all()
     assert np.array_equal(cl.clsintegral("WL", 2, "GCph", 5), cl.result["WL 2xGCph 5"])
+
+
+def test_batched_fisher_postprocessing_on_device():
+    """sums, marginal bounds, marginalised matrices and figures of merit of thousands of Fisher matrices in
+    one launch each, against numpy and against the result container's own CPU methods
+    (analysis/fisher_matrix.py:462-548, 705-733; analysis/fisher_operations.py:177-272)."""
+    from cosmicfishpie_b200 import fisher_operations as fo
+    from cosmicfishpie_b200.fisher_matrix import fisher_matrix
+
+    rng = np.random.default_rng(5)
+    B, n = 3000, 23
+    A = rng.standard_normal((B, n, 3 * n))
+    scale = 10.0 ** rng.uniform(-2, 3, size=(1, n))
+    F = np.einsum("bik,bjk->bij", A, A) * scale[:, :, None] * scale[:, None, :]  # SPD, rows of very different size
+    names = [f"p{i}" for i in range(n)]
+    names[5], names[6] = "w0", "wa"
+    sigma = fo.batch_confidence_bounds(F)
+    inv = np.linalg.inv(F)
+    from cosmicfishpie_b200.fisher_matrix import confidence_coefficient
+
+    ref_sigma = confidence_coefficient(0.6827) * np.sqrt(np.diagonal(inv, axis1=1, axis2=2))
+    assert sigma.shape == (B, n) and np.max(np.abs(sigma / ref_sigma - 1)) < 1e-9  # (north_star asks 1e-4 on sigma)
+    s2, marg, fom = fo.batch_marginalise(F, names, ["wa", "p2", "w0"])
+    ref_marg = np.linalg.inv(inv[:, [6, 2, 5]][:, :, [6, 2, 5]])
+    assert np.max(np.abs(marg - ref_marg) / np.abs(ref_marg).max(axis=(1, 2), keepdims=True)) < 1e-9
+    assert np.allclose(fom, np.sqrt(np.linalg.det(ref_marg)), rtol=1e-9)
+    assert np.allclose(fo.batch_figure_of_merit(F, names), 1 / np.sqrt(np.linalg.det(inv[:, 5:7, 5:7])), rtol=1e-9)
+    # the single-matrix interface of the reference's module and the container's CPU methods
+    f0 = fisher_matrix(fisher_matrix=F[0], param_names=names)
+    assert np.allclose(sigma[0], f0.get_confidence_bounds(), rtol=1e-10)
+    m0 = fo.marginalise(f0, ["w0", "wa"])
+    assert m0.param_names == ["w0", "wa"] and m0.name.endswith("_marginal")
+    assert np.allclose(m0.fisher_matrix, np.linalg.inv(inv[0][5:7, 5:7]), rtol=1e-9)
+    over = fo.marginalise_over(f0, ["p0", "p1"])
+    assert over.param_names == names[2:] and np.allclose(over.get_confidence_bounds(), f0.get_confidence_bounds()[2:], rtol=1e-8)
+    # sums over the union of parameters
+    nb = 15
+    Bm = np.einsum("bik,bjk->bij", A[:64, :nb], A[:64, :nb])
+    nb_names = names[:7] + [f"q{i}" for i in range(nb - 7)]
+    la = [fisher_matrix(fisher_matrix=F[b], param_names=names) for b in range(64)]
+    lb = [fisher_matrix(fisher_matrix=Bm[b], param_names=nb_names) for b in range(64)]
+    sums = fo.batch_add(la, lb)
+    for b in (0, 17, 63):
+        ref = la[b] + lb[b]
+        assert sums[b].param_names == ref.param_names and np.array_equal(sums[b].fisher_matrix, ref.fisher_matrix)
+    # a matrix that is not positive definite
+    bad = F[:2].copy()
+    bad[1] = -bad[1]
+    s = fo.batch_confidence_bounds(bad)
+    assert np.all(np.isfinite(s[0])) and np.all(np.isnan(s[1]))
