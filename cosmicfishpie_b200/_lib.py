@@ -38,7 +38,7 @@ EXPORTS = [
     "cfp_dev_release", "cfp_photo_plan_create_zmap", "cfp_ctx_aux_stream", "cfp_photo_plan_create_ex",
     "cfp_photo_plan_set_gc_table", "cfp_spectro_plan_chi2_legendre", "cfp_spectro_plan_kernel_ms_part",
     "cfp_math_selftest", "cfp_spectro_plan_terms", "cfp_photo_plan_fetch_windows", "cfp_photo_fisher",
-    "cfp_fisher_batch_post", "cfp_fisher_batch_add",
+    "cfp_fisher_batch_post", "cfp_fisher_batch_add", "cfp_bank_combine",
 ]
 
 
@@ -87,6 +87,7 @@ def load():
     lib.cfp_photo_fisher.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
     lib.cfp_fisher_batch_post.argtypes = [_vp, C.c_int, C.c_int, _dp, C.c_int, _ip, C.c_double, _dp, _dp, _dp]
     lib.cfp_fisher_batch_add.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
+    lib.cfp_bank_combine.argtypes = [_vp, _vp, C.c_int, _dp, C.POINTER(_vp)]
     lib.cfp_math_selftest.argtypes = [_vp, C.c_int, _dp, C.c_int, _dp]
     lib.cfp_math_selftest.restype = C.c_int
     lib.cfp_photo_plan_kernel_ms.argtypes = [_vp, C.c_int]
@@ -435,6 +436,20 @@ class Bank:
         self.handle = _vp()
         _check(ctx.lib.cfp_bank_upload(ctx.handle, _p(self.blob), self.blob.size, _p(desc, _lp), n_cosmo, NTAB,
                                        C.byref(self.handle)), "cfp_bank_upload")
+
+    def combined(self, W) -> "Bank":
+        """A new bank: this bank's rows followed by len(W) rows combined on the device, row m = sum_c W[m][c] * row_c
+        (cfp_bank_combine): emulated cosmologies without host fits."""
+        W = f64(W)
+        assert W.ndim == 2 and W.shape[1] == self.n_cosmo
+        out = Bank.__new__(Bank)
+        out.ctx, out.rows, out.blob, out.desc = self.ctx, [], None, None
+        out.n_cosmo = self.n_cosmo + W.shape[0]
+        out.nbytes = W.nbytes
+        out.handle = _vp()
+        _check(self.ctx.lib.cfp_bank_combine(self.ctx.handle, self.handle, W.shape[0], _p(W), C.byref(out.handle)),
+               "cfp_bank_combine")
+        return out
 
     def eval(self, cosmo: int, table: int, z, k) -> np.ndarray:
         z, k = np.broadcast_arrays(f64(z), f64(k))

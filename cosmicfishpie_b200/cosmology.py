@@ -157,9 +157,16 @@ class cosmo_functions:
         self.external = config.external
         self.cosmopars = cosmopars
         self.fiducialcosmopars = config.fiducialparams
-        self.folder = folder_for(cosmopars, self.fiducialcosmopars, self.external)
         self.cb_files_on = "clustering" in (self.settings.get("GCsp_Tracer"), self.settings.get("GCph_Tracer"))
-        t = load_tables(self.external, self.folder, cb=self.cb_files_on)
+        emulator = self.external.get("emulator")
+        if emulator is not None and not emulator.is_node(cosmopars):
+            # a cosmology between the tabulated ones: its tables from the bank's emulator (cosmicfishpie_b200/bank.py)
+            # instead of the reference's snap to the nearest folder (cosmology.py:1375-1421)
+            t = emulator.tables_at(cosmopars)
+            self.folder = "<emulated>"
+        else:
+            self.folder = folder_for(cosmopars, self.fiducialcosmopars, self.external)
+            t = load_tables(self.external, self.folder, cb=self.cb_files_on)
         pkf = rf = kf = 1.0
         if self.external.get("k-units") == "h/Mpc":  # cosmology.py:1438-1444
             pkf = (1 / cosmopars["h"]) ** 3
@@ -325,7 +332,7 @@ def cached_cosmo(cosmopars, config) -> "cosmo_functions":
     key = (src, tuple(sorted((k, v) for k, v in cosmopars.items())), tuple(sorted(config.fiducialparams.items())),
            tuple(ext["paramnames"]), tuple(ext["eps_values"]), ext.get("k-units"), ext.get("r-units"),
            st["savgol_internalkmin"], st["savgol_internalsamples"], st["savgol_width"], st["savgol_polyorder"],
-           st.get("GCsp_Tracer"), st.get("GCph_Tracer"))
+           st.get("GCsp_Tracer"), st.get("GCph_Tracer"), id(ext.get("emulator")))
     hit = _COSMO_CACHE.get(key)
     if hit is not None and hit[0] is ext.get("tables"):  # identity check: id() values can be recycled
         return hit[1]

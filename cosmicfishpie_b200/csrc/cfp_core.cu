@@ -193,6 +193,97 @@ extern "C" int cfp_bank_upload_rows(cfp_ctx* ctx, const double* const* rows_h, c
   return CFP_OK;
 }
 
+// out[m][e] = sum_c W[m][c] base[c][e] over the coefficient ranges of a row; knot ranges are copied from row 0.
+// is_knot[e] flags the knot elements of a row (all rows share one layout).
+__global__ void cfp_bank_combine_kernel(int NC, int M, size_t row_len, const double* __restrict__ base,
+                                        const double* __restrict__ W, const unsigned char* __restrict__ is_knot,
+                                        double* __restrict__ out) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (e >= row_len) return;
+  double acc;
+  if (is_knot[e]) {
+    acc = base[e];
+  } else {
+    acc = 0.0;
+    for (int c = 0; c < NC; ++c) {
+      const double w = W[(size_t)m * NC + c];
+      if (w != 0.0) acc = fma(w, base[(size_t)c * row_len + e], acc);
+    }
+  }
+  out[(size_t)m * row_len + e] = acc;
+}
+
+extern "C" int cfp_bank_combine(cfp_ctx* ctx, const cfp_bank* base, int M, const double* W_h, cfp_bank** out) {
+  CFP_REQUIRE(ctx && base && W_h && out && M >= 1, "bad argument");
+  *out = nullptr;
+  const int NC = base->n_cosmo, NT = base->n_tables;
+  CFP_REQUIRE(base->n % (size_t)NC == 0, "the rows of the base bank differ in length");
+  const size_t row_len = base->n / (size_t)NC;
+  // every row must have the layout of row 0 (same tables on the same knots): descriptors equal up to the row offset
+  std::vector<unsigned char> is_knot(row_len, 0);
+  for (int c = 0; c < NC; ++c)
+    for (int t = 0; t < NT; ++t) {
+      const int64_t* d = base->desc(c, t);
+      const int64_t* d0 = base->desc(0, t);
+      const int64_t shift = (int64_t)((size_t)c * row_len);
+      CFP_REQUIRE(d[0] == d0[0] && d[1] == d0[1], "the rows of the base bank differ in table shapes");
+      if (d0[0] == 0 && d0[1] == 0) continue;
+      CFP_REQUIRE(d[2] - shift == d0[2] && d[3] - shift == d0[3] && d[4] - shift == d0[4],
+                  "the rows of the base bank differ in layout");
+      if (c == 0) {
+        for (int64_t i = 0; i < d0[0]; ++i) is_knot[(size_t)(d0[2] + i)] = 1;
+        for (int64_t i = 0; i < d0[1]; ++i) is_knot[(size_t)(d0[3] + i)] = 1;
+      }
+    }
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cfp_bank* b = new cfp_bank();
+  b->ctx = ctx;
+  b->n_cosmo = NC + M;
+  b->n_tables = NT;
+  b->n = (size_t)(NC + M) * row_len;
+  b->desc_h.resize((size_t)(NC + M) * NT * CFP_BANK_DESC);
+  for (int c = 0; c < NC + M; ++c)
+    for (int t = 0; t < NT; ++t) {
+      const int64_t* d0 = base->desc(0, t);
+      int64_t* d = &b->desc_h[((size_t)c * NT + t) * CFP_BANK_DESC];
+      d[0] = d0[0], d[1] = d0[1];
+      const int64_t shift = (int64_t)((size_t)c * row_len);
+      d[2] = d0[2] + shift, d[3] = d0[3] + shift, d[4] = d0[4] + shift;
+      if (d0[0] == 0 && d0[1] == 0) d[2] = d[3] = d[4] = 0;
+    }
+  double* W_d = nullptr;
+  unsigned char* k_d = nullptr;
+  cudaError_t e = cfp_dev_alloc(ctx, (void**)&b->blob_d, b->n * sizeof(double));
+  int rc = e == cudaSuccess ? cfp_upload(ctx, W_h, (size_t)M * NC, &W_d) : CFP_ERR_CUDA;
+  if (rc == CFP_OK) rc = cfp_upload(ctx, is_knot.data(), row_len, &k_d);
+  if (rc == CFP_OK) rc = cfp_upload(ctx, b->desc_h.data(), b->desc_h.size(), &b->desc_d);
+  if (rc == CFP_OK) {
+    e = cudaMemcpyAsync(b->blob_d, base->blob_d, base->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+      cfp_bank_combine_kernel<<<dim3((unsigned)((row_len + 255) / 256), M), 256, 0, ctx->stream>>>(
+          NC, M, row_len, base->blob_d, W_d, k_d, b->blob_d + base->n);
+      ctx->launches++;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      cfp_set_error("cfp_bank_combine: %s", cudaGetErrorString(e));
+      rc = CFP_ERR_CUDA;
+    }
+  }
+  cfp_dev_free(ctx, W_d);
+  cfp_dev_free(ctx, k_d);
+  if (rc != CFP_OK) {
+    cfp_dev_free(ctx, b->blob_d);
+    cfp_dev_free(ctx, b->desc_d);
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return CFP_OK;
+}
+
 extern "C" int cfp_bank_free(cfp_ctx* ctx, cfp_bank* bank) {
   if (!bank) return CFP_OK;
   cfp_ctx* owner = bank->ctx ? bank->ctx : ctx;

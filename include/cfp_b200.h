@@ -366,6 +366,14 @@ int cfp_legendre_covariance(cfp_ctx* ctx, int Nk, int Z, const double* pl_h, con
 int cfp_legendre_chi2(cfp_ctx* ctx, int S, int Nk, int Z, const double* pl_data_h, const double* pl_theory_h,
                       const double* icov_h, double* chi2_h);
 
+/* Cosmology emulation on the device: a new bank = the NC rows of `base` followed by M rows whose bicubic
+ * coefficient arrays are the weighted sums sum_c W_h[m][c] * row_c (knots copied).  Interpolating-spline fitting is
+ * linear in the table values, so with the weights of a Taylor / interpolation scheme over tabulated cosmologies
+ * (cosmicfishpie_b200/bank.py) row NC + m is the table set of the emulated cosmology m, built without any host fit or
+ * H2D of tables -- where the reference snaps an off-grid cosmology to the nearest folder
+ * (cosmicfishpie/cosmology/cosmology.py:1375-1421).  All rows of `base` must share table shapes and knots. */
+int cfp_bank_combine(cfp_ctx* ctx, const cfp_bank* base, int M, const double* W_h, cfp_bank** out);
+
 /* ---- batched Fisher-matrix post-processing ------------------------------------------------------
  * B symmetric positive-definite matrices of n <= 64 parameters in one launch.
  * cfp_fisher_batch_post: sigma_h[B][n] = coef * sqrt(diag(F^-1))  (fisher_matrix.get_confidence_bounds,

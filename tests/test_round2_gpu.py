@@ -361,3 +361,72 @@ def test_batched_fisher_postprocessing_on_device():
     bad[1] = -bad[1]
     s = fo.batch_confidence_bounds(bad)
     assert np.all(np.isfinite(s[0])) and np.all(np.isnan(s[1]))
+
+
+def test_emulated_cosmology_likelihood_and_device_combine(extfiles, toy_bank, tmp_path):
+    """with the bank's emulator a likelihood batch moves CONTINUOUSLY in cosmology.  (1) parity at the
+    bank nodes: the same numbers as without the emulator; (2) off the nodes: against a likelihood fed with the toy
+    model's EXACT tables of each point (stated interpolation error); (3) cfp_bank_combine: the bicubic rows combined on
+    the device equal the host fit of the combined tables."""
+    from cosmicfishpie_b200 import _lib
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.bank import TaylorEmulator
+    from cosmicfishpie_b200.cosmology import cached_cosmo
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+    from cosmicfishpie_b200.likelihood import SpectroLikelihood
+
+    emu = TaylorEmulator(toy_bank, tt.FIDUCIAL, tt.COSMO_KEYS, 0.01)
+    zg, kg = toy_bank["fiducial_eps_0"]["z"], toy_bank["fiducial_eps_0"]["k"]
+
+    class Exact:  # stands in for the emulator: the toy model evaluated at the point itself
+        is_node = staticmethod(lambda theta: False)
+        tables_at = staticmethod(lambda theta: tt.make_tables({k: theta[k] for k in tt.COSMO_KEYS}, zg, kg))
+
+    def make(ext, sub):
+        fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"h": 0.01, "Omegam": 0.01},
+                          options=base_options(tmp_path / sub, spectro_Pk_k_samples=257, spectro_Pk_mu_samples=17),
+                          observables=["GCsp"], extfiles=ext)
+        fm.compute()
+        return fm, SpectroLikelihood(cosmoFM_data=fm)
+
+    fm_plain, like_plain = make(extfiles, "a")
+    fm_emu, like_emu = make(dict(extfiles, emulator=emu), "b")
+    fm_exact, like_exact = make(dict(extfiles, emulator=Exact()), "c")
+    keys = ["Omegam", "h", "sigma8", "w0", "lnbg_1", "lnbg_3"]
+    fid = np.array([fm_emu.allparams[k] for k in keys])
+    # (1) bank nodes
+    nodes = np.tile(fid, (5, 1))
+    nodes[1, 0] *= 1.01
+    nodes[2, 1] *= 0.99
+    nodes[3, 2] *= 1.01
+    nodes[4, 3] *= 0.99
+    nodes[:, 4:] += 0.01
+    a, b = like_emu.loglike_batch(nodes, keys=keys), like_plain.loglike_batch(nodes, keys=keys)
+    assert np.max(np.abs(a - b) / np.abs(b)) < 1e-12
+    # (2) between the nodes, several parameters at once
+    rng = np.random.default_rng(21)
+    pts = np.tile(fid, (12, 1))
+    pts[:, :4] *= 1 + 0.008 * rng.uniform(-1, 1, size=(12, 4))
+    pts[:, 4:] += 0.01 * rng.standard_normal((12, 2))
+    got, want = like_emu.loglike_batch(pts, keys=keys), like_exact.loglike_batch(pts, keys=keys)
+    rel = np.abs(got - want) / np.abs(want)
+    assert np.all(np.isfinite(got)) and np.max(rel) < 0.05, rel      # stated error of the diagonal expansion
+    snapped = like_plain.loglike_batch(np.where(np.arange(6) < 4, np.round(pts / fid / 0.01) * 0.01 * fid, pts), keys=keys)
+    assert np.median(rel) < 0.1 * np.median(np.abs(snapped - want) / np.abs(want))  # ... and far better than snapping
+    # (3) device combination of bank rows == host fit of the combined tables
+    cs = fm_emu._spectro_job.cosmo_set
+    base_pars = [dict(tt.FIDUCIAL)] + [p for _, p in list(tt.stencil_points(dict(tt.FIDUCIAL), (0.01,)))[1:]]
+    rows = [cached_cosmo(p, fm_emu.config).packed_row(cs.context(), (_lib.TAB_PLIN, _lib.TAB_F)) for p in base_pars]
+    base = _lib.Bank.from_rows(cs.context(), rows)
+    theta = dict(tt.FIDUCIAL, Omegam=0.3223, h=0.6725, ns=0.9633, wa=0.004)
+    W = emu.weight_matrix([theta], [f for f, _ in tt.stencil_points(dict(tt.FIDUCIAL), (0.01,))])
+    comb = base.combined(W)
+    zq, kq = rng.uniform(0.9, 1.8, 500), 10 ** rng.uniform(-3, -0.7, 500)
+    host = cached_cosmo(theta, fm_emu.config)
+    for slot, spl in ((_lib.TAB_PLIN, host.Pk_l), (_lib.TAB_F, host.f_growthrate_zk)):
+        dev = comb.eval(len(base_pars), slot, zq, kq)
+        ref = spl(zq, kq, grid=False)
+        assert np.max(np.abs(dev - ref) / np.abs(ref)) < 1e-11, slot
+        assert np.array_equal(comb.eval(3, slot, zq, kq), base.eval(3, slot, zq, kq))  # the base rows are carried over
+    comb.close()
+    base.close()
