@@ -58,10 +58,14 @@ WORKLOAD = f"euclid_3x2pt_13bins_lmax5000_npar23 + gcsp_4bins_npar15_3PT_lattice
 # instructions, DADD + DMUL + 2 DFMA; profiles/r2_*): per warp step of spectro_fisher_pairs_kernel (four cells x
 # eight parameter slots: 32 lanes x [2 evaluations + the pair's finishing]) plus its one DMMA.8x8x4 (512 flop), and per
 # cell of the spectro_weights_kernel pre-pass.  warp steps = Z x ceil(Nk / 4) x rows (+1 per task: pipeline fill).
-F_PAIR_STEP = 32 * 125.0 + 512.0
-F_WEIGHT_CELL = 118.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one spectro_fisher_pairs_kernel launch (ncu --set full, profiles/r2)
-TRAFFIC_BYTES = 0.42e6
+# Measured on the bench forecast (profiles/r2f_kernels.md): 4.4594e9 vector flop in 1 073 676 warp steps, 4.6034e8 in
+# 4 227 588 cells of the pre-pass.
+F_PAIR_STEP = 4153.4 + 512.0
+F_WEIGHT_CELL = 108.9
+# dram__bytes_read.sum + dram__bytes_write.sum of one spectro_fisher_pairs_kernel launch: `ncu --set full` with its
+# default cache flush before the kernel, i.e. the 67.7 MB {weight, 1/P} pairs of the pre-pass come from HBM (profiles/
+# r2b); in the running step they are still L2-resident and the kernel touches 0.41 MB of HBM (--cache-control none)
+TRAFFIC_BYTES = 70.9e6
 
 
 def ext_dict(bank):
@@ -465,7 +469,7 @@ def run_gpu(args):
         p5.run(materialize=0, stream=sptr)
         t5.append(p5.kernel_ms(0))
     five_pt = {"gcsp_5pt_lattice_pass_ms": float(np.mean(t5)), "stencil_points": int(p5.S),
-               "what": "GCsp 129x8193 with the 5-point stencil (39 stencil points instead of 23): device time of the "
+               "what": "GCsp 129x8193 with the 5-point stencil (45 stencil points instead of 23): device time of the "
                        "lattice pass (general kernel; oracle-pinned, the reference has no 5PT)"}
     fm5._spectro_job.close()
 

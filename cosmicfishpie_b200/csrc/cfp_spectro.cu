@@ -1313,7 +1313,7 @@ __global__ void math_selftest_kernel(int which, int n, const double* __restrict_
 }
 
 // F[zb] of the bins the pair kernel took: internal order (slots 0..7, shot noise) -> parameters, zeros elsewhere.
-// grid (Z); one warp per element of the lower triangle, lanes over the CTA partials (fixed order: lane l adds CTAs
+// grid (Z, 8); one warp per element of the lower triangle, lanes over the CTA partials (fixed order: lane l adds CTAs
 // l, l + 32, ..., then a shuffle tree).
 __global__ void __launch_bounds__(1024) spectro_reduce_pairs_kernel(const double* __restrict__ partial, int ncta,
                                                                     int npar, const PairPlan* __restrict__ pairs,
@@ -1329,8 +1329,8 @@ __global__ void __launch_bounds__(1024) spectro_reduce_pairs_kernel(const double
     inv[p] = a;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int e = warp; e < npar * npar; e += nwarp) {
+  const int lane = threadIdx.x & 31, nwarp = (blockDim.x >> 5) * gridDim.y;
+  for (int e = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); e < npar * npar; e += nwarp) {
     const int i = e / npar, j = e - i * npar;
     if (j > i) continue;
     const int ai = inv[i], aj = inv[j];
@@ -2624,7 +2624,7 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
     ctx->launches++;
   }
   if (try_pairs) {
-    spectro_reduce_pairs_kernel<<<pl->Z, 1024, 0, st>>>(pl->partial2_d, gx2, pl->npar, pl->pairs_d, pl->fisher_d);
+    spectro_reduce_pairs_kernel<<<dim3(pl->Z, 8), 1024, 0, st>>>(pl->partial2_d, gx2, pl->npar, pl->pairs_d, pl->fisher_d);
     ctx->launches++;
   }
   CFP_CUDA(cudaGetLastError());
