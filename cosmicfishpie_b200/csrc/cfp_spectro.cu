@@ -2574,11 +2574,8 @@ extern "C" int cfp_spectro_plan_run(cfp_spectro_plan* pl, int materialize, void*
                                                                                pl->wd_d, pl->partial2_d);             \
     break;
     switch (pk_warps) {
-      CFP_LAUNCH_PK(12)
+      CFP_LAUNCH_PK(12)  // (A/B variants, CFP_PK_WARPS: 16 warps at 128 registers is the measured optimum)
       CFP_LAUNCH_PK(20)
-      CFP_LAUNCH_PK(24)
-      CFP_LAUNCH_PK(28)
-      CFP_LAUNCH_PK(32)
       default:
         e = cudaFuncSetAttribute(spectro_fisher_pairs_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e == cudaSuccess)
