@@ -38,7 +38,8 @@ EXPORTS = [
     "cfp_dev_release", "cfp_photo_plan_create_zmap", "cfp_ctx_aux_stream", "cfp_photo_plan_create_ex",
     "cfp_photo_plan_set_gc_table", "cfp_spectro_plan_chi2_legendre", "cfp_spectro_plan_kernel_ms_part",
     "cfp_math_selftest", "cfp_spectro_plan_terms", "cfp_photo_plan_fetch_windows", "cfp_photo_fisher",
-    "cfp_fisher_batch_post", "cfp_fisher_batch_add", "cfp_bank_combine",
+    "cfp_fisher_batch_post", "cfp_fisher_batch_add", "cfp_bank_combine", "cfp_photo_plan_create_zmap_shared",
+    "cfp_photo_plan_chi2_launch", "cfp_photo_plan_chi2_collect",
 ]
 
 
@@ -117,6 +118,7 @@ def load():
     lib.cfp_photo_plan_create_zmap.argtypes = [
         _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp, C.c_double, _dp, _dp, _dp,
         _ip, _dp, _dp, C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int, C.POINTER(_vp)]
+    lib.cfp_photo_plan_create_zmap_shared.argtypes = lib.cfp_photo_plan_create_zmap.argtypes
     lib.cfp_photo_plan_create_ex.argtypes = [
         _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp, C.c_double, _dp, _dp, _dp,
         _ip, C.c_int, _ip, _dp, _dp, C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int,
@@ -129,6 +131,8 @@ def load():
     lib.cfp_photo_plan_fisher_d.restype = _vp
     lib.cfp_photo_plan_fetch.argtypes = [_vp, _dp, _dp, _dp]
     lib.cfp_photo_plan_chi2.argtypes = [_vp, _dp, C.c_int, _ip, _ip, _dp, _dp, _vp]
+    lib.cfp_photo_plan_chi2_launch.argtypes = [_vp, _dp, C.c_int, _ip, _ip, _dp, _vp]
+    lib.cfp_photo_plan_chi2_collect.argtypes = [_vp, _dp]
     lib.cfp_spectro_plan_chi2.argtypes = [_vp, _dp, _dp, _dp, _dp, _vp]
     lib.cfp_cells_chi2.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, _ip, _ip, _dp, _dp]
     lib.cfp_wedge_chi2.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
@@ -586,11 +590,16 @@ class PhotoPlan:
         self.Nl, self.Nz, self.Nb, self.npar = self.ell.size, self.z.size, self.kind.size, self.stw.shape[0]
         assert self.chi.shape == (self.NC, self.Nz) and self.hub.shape == (self.NC, self.Nz)
         self.zmap = None if zmap is None else i32(zmap)
-        Kb = self.Nz if self.zmap is None else self.bias.shape[2]
+        Kb = self.Nz if self.zmap is None else self.bias.shape[-1]
         self.win_of_s = None if win_of_s is None else i32(win_of_s)
         NW = 1 if self.win_of_s is None else self.ngal.shape[0]
         assert self.ngal.shape == ((self.Nb, self.Nz) if self.win_of_s is None else (NW, self.Nb, self.Nz))
-        assert self.bias.shape == (self.S, self.Nb, Kb)
+        shared = self.zmap is not None and self.bias.ndim == 2  # [S][Kb]: one bias vector per point for all rows
+        if shared:
+            Kb = self.bias.shape[1]
+            assert self.win_of_s is None and self.bias.shape == (self.S, Kb)
+        else:
+            assert self.bias.shape == (self.S, self.Nb, Kb)
         assert self.ia.shape == (self.S, self.Nz) and self.stw.shape == (self.npar, self.S)
         self.handle = _vp()
         if self.win_of_s is not None:  # several sets of n(z) windows (photo-z parameters vary between points)
@@ -609,9 +618,10 @@ class PhotoPlan:
                 _p(self.wlpref), _p(self.kind, _ip), _p(self.ngal), _p(self.bias), _p(self.ia), _p(self.lmin),
                 _p(self.lmax), _p(self.noise), _p(self.sqrtfsky), _p(self.stw), _p(self.stden), float(kmax), int(tab_p),
                 C.byref(self.handle)), "cfp_photo_plan_create")
-        else:  # bias on Kb samples per (point, row) + z -> sample map
+        else:  # bias on Kb samples per (point, row) -- or per point, shared by the rows -- + z -> sample map
             assert self.zmap.shape == (self.Nz,)
-            _check(ctx.lib.cfp_photo_plan_create_zmap(
+            create = ctx.lib.cfp_photo_plan_create_zmap_shared if shared else ctx.lib.cfp_photo_plan_create_zmap
+            _check(create(
                 ctx.handle, bank.handle, self.S, self.NC, self.Nl, self.Nz, self.Nb, self.npar,
                 _p(self.cosmo_of_s, _ip), _p(self.ell), _p(self.z), float(dz), _p(self.chi), _p(self.hub),
                 _p(self.wlpref), _p(self.kind, _ip), _p(self.ngal), _p(self.bias), int(Kb), _p(self.zmap, _ip),
@@ -649,6 +659,21 @@ class PhotoPlan:
         out = np.empty(self.S)
         _check(self.ctx.lib.cfp_photo_plan_chi2(self.handle, _p(data), off.size, _p(off, _ip), _p(n, _ip), _p(w), _p(out),
                                                 _vp(stream) if stream else None), "cfp_photo_plan_chi2")
+        return out
+
+    def chi2_launch(self, blk_off, blk_n, blk_w, data=None, stream: int = 0) -> None:
+        """Enqueue the chi^2 of every point (no waiting): prepare the next batch, then `chi2_collect()`."""
+        off, n, w = i32(blk_off), i32(blk_n), f64(blk_w)
+        assert w.shape == (off.size, self.Nl)
+        data = None if data is None else f64(data)
+        self._chi_inputs = (off, n, w, data)  # stay alive until the collect
+        _check(self.ctx.lib.cfp_photo_plan_chi2_launch(self.handle, _p(data), off.size, _p(off, _ip), _p(n, _ip), _p(w),
+                                                       _vp(stream) if stream else None), "cfp_photo_plan_chi2_launch")
+
+    def chi2_collect(self) -> np.ndarray:
+        out = np.empty(self.S)
+        _check(self.ctx.lib.cfp_photo_plan_chi2_collect(self.handle, _p(out)), "cfp_photo_plan_chi2_collect")
+        self._chi_inputs = None
         return out
 
     def fetch(self, cls=False, sqrtp=False):

@@ -2,7 +2,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
+#include <mutex>
+#include <utility>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -38,7 +41,33 @@ struct cfp_ctx {
   std::atomic<int64_t> launches{0};  // plans of one context may be driven from two host threads (pipelined batches)
   double last_ms = 0.0;
   cudaMemPool_t pool = nullptr;  // stream-ordered arena: plan create/destroy never reach the driver allocator
+  // page-locked result buffers, recycled: cudaHostAlloc / cudaFreeHost synchronise the device, which would serialise a
+  // pipeline of batches that allocates one per plan
+  std::mutex pin_mu;
+  std::vector<std::pair<size_t, void*>> pin_free;
 };
+
+inline void* cfp_pinned_acquire(cfp_ctx* ctx, size_t bytes) {
+  {
+    std::lock_guard<std::mutex> g(ctx->pin_mu);
+    for (size_t i = 0; i < ctx->pin_free.size(); ++i)
+      if (ctx->pin_free[i].first >= bytes) {
+        void* p = ctx->pin_free[i].second;
+        ctx->pin_free[i] = ctx->pin_free.back();
+        ctx->pin_free.pop_back();
+        return p;  // (capacity >= bytes; returned to the list with its real capacity by the matching release)
+      }
+  }
+  void* p = nullptr;
+  const size_t cap = std::max<size_t>(bytes, (size_t)1 << 16);
+  if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+  return p;
+}
+inline void cfp_pinned_release(cfp_ctx* ctx, void* p, size_t bytes) {
+  if (!p) return;
+  std::lock_guard<std::mutex> g(ctx->pin_mu);
+  ctx->pin_free.emplace_back(std::max<size_t>(bytes, (size_t)1 << 16), p);
+}
 
 // Device memory comes from the context's pool, ordered on the context stream.  Work that runs on a caller's
 // stream synchronises with the context stream after allocating and before releasing (see the plan code).

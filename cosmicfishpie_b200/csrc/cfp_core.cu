@@ -62,6 +62,7 @@ extern "C" int cfp_ctx_destroy(cfp_ctx* ctx) {
   cudaStreamSynchronize(ctx->aux);
   cudaStreamDestroy(ctx->aux);
   cudaStreamDestroy(ctx->stream);
+  for (auto& pr : ctx->pin_free) cudaFreeHost(pr.second);
   delete ctx;
   return CFP_OK;
 }

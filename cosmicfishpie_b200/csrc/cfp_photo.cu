@@ -15,6 +15,7 @@
 //                         tr(A^-1 B) = |L^-1 L_B|^2                                      (photo_like.py:28-97,180-256)
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "cfp_common.cuh"
 
@@ -136,9 +137,9 @@ __global__ void photo_window_kernel(int S, int Nb, int Nz, int ldz, int nrow_pad
                                     const int* __restrict__ kind, const double* __restrict__ z,
                                     const double* __restrict__ chi, const double* __restrict__ hub,
                                     const double* __restrict__ wlpref, const double* __restrict__ ngal,
-                                    const double* __restrict__ bias, int Kb, const int* __restrict__ zmap,
-                                    const double* __restrict__ ia, const double* __restrict__ eff,
-                                    double* __restrict__ U, double* __restrict__ V) {
+                                    const double* __restrict__ bias, int Kb, int bias_rows,
+                                    const int* __restrict__ zmap, const double* __restrict__ ia,
+                                    const double* __restrict__ eff, double* __restrict__ U, double* __restrict__ V) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t tot = (size_t)S * nrow_pad * ldz;
   if (idx >= tot) return;
@@ -158,7 +159,7 @@ __global__ void photo_window_kernel(int S, int Nb, int Nz, int ldz, int nrow_pad
       u = w / sh;
       v = wia / sh;
     } else {  // clustering row, photo_obs.py:542, 715-717
-      const double w = (ng * H) * bias[((size_t)s * Nb + a) * Kb + (zmap ? zmap[iz] : iz)];
+      const double w = (ng * H) * bias[((size_t)s * bias_rows + (bias_rows == 1 ? 0 : a)) * Kb + (zmap ? zmap[iz] : iz)];
       u = w / sh;
       v = 0.0;
     }
@@ -857,6 +858,12 @@ struct cfp_photo_plan {
   int NW = 1, NP = 0;     // n(z) window sets; (cosmology, window set) pairs among the stencil points
   int *win_of_s_d = nullptr, *pair_of_s_d = nullptr, *pair_c_d = nullptr, *pair_w_d = nullptr;
   int Kb = 0;             // bias samples per (point, row): Nz, or fewer with a z -> sample map
+  bool cls_zeroed = false;  // cls_d was zero-filled (see cfp_photo_plan_set_slice)
+  std::vector<void*> chi_tmp;   // device buffers of a launched, not yet collected chi2
+  double* chi2_pin = nullptr;   // page-locked copy of its result
+  cudaEvent_t chi_up = nullptr;
+  bool chi_pending = false;
+  int bias_rows = 0;      // rows of the bias array per point: Nb, or 1 when every clustering row shares one vector
   int* zmap_d = nullptr;  // [Nz] or NULL (identity)
   double *sqrtfsky_d = nullptr, *stw_d = nullptr, *stden_d = nullptr, *strden_d = nullptr, *wz_d = nullptr;
   double* stp_w_d = nullptr;
@@ -873,6 +880,9 @@ struct cfp_photo_plan {
 };
 
 static void photo_free(cfp_photo_plan* p) {
+  for (void* q : p->chi_tmp) cfp_dev_free(p->ctx, q);
+  cfp_pinned_release(p->ctx, p->chi2_pin, (size_t)p->S * sizeof(double));
+  if (p->chi_up) cudaEventDestroy(p->chi_up);
   if (p->run0) cudaEventDestroy(p->run0);
   if (p->run1) cudaEventDestroy(p->run1);
   for (auto& e : p->kev)
@@ -891,6 +901,19 @@ static void photo_free(cfp_photo_plan* p) {
     pl->owned.push_back((void*)(dst));                         \
   } while (0)
 
+// buffers every run overwrites completely before reading: allocation only (a likelihood chunk of 4096 points has
+// 2.6 GB of them; zero-filling that per plan cost more than the Limber table kernel)
+#define PH_ALLOC(T, cnt, dst)                                                              \
+  do {                                                                                     \
+    (dst) = nullptr;                                                                       \
+    if (cfp_dev_alloc(ctx, (void**)&(dst), (size_t)(cnt) * sizeof(T)) != cudaSuccess) {    \
+      cfp_set_error("cfp_photo_plan_create: device allocation of %zu bytes failed", (size_t)(cnt) * sizeof(T)); \
+      photo_free(pl);                                                                      \
+      return CFP_ERR_CUDA;                                                                 \
+    }                                                                                      \
+    pl->owned.push_back((void*)(dst));                                                     \
+  } while (0)
+
 static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb, int npar,
                                   const int32_t* cosmo_of_s_h, const double* ell_h, const double* z_h, double dz,
                                   const double* chi_h, const double* hub_h, const double* wlpref_h,
@@ -898,7 +921,7 @@ static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int
                                   const double* ia_h, const double* lmin_h, const double* lmax_h,
                                   const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
                                   const double* stden_h, double kmax, int tab_p, int Kb, const int32_t* zmap_h,
-                                  int NW, const int32_t* win_of_s_h, cfp_photo_plan** out);
+                                  int NW, const int32_t* win_of_s_h, cfp_photo_plan** out, bool bias_shared = false);
 
 extern "C" int cfp_photo_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb,
                                      int npar, const int32_t* cosmo_of_s_h, const double* ell_h, const double* z_h,
@@ -925,6 +948,21 @@ extern "C" int cfp_photo_plan_create_zmap(cfp_ctx* ctx, const cfp_bank* bank, in
   return photo_plan_create_impl(ctx, bank, S, NC, Nl, Nz, Nb, npar, cosmo_of_s_h, ell_h, z_h, dz, chi_h, hub_h, wlpref_h,
                                 kind_h, ngal_h, bias_h, ia_h, lmin_h, lmax_h, noise_h, sqrtfsky_h, stw_h, stden_h, kmax,
                                 tab_p, Kb, zmap_h, 1, nullptr, out);
+}
+
+extern "C" int cfp_photo_plan_create_zmap_shared(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz,
+                                                 int Nb, int npar, const int32_t* cosmo_of_s_h, const double* ell_h,
+                                                 const double* z_h, double dz, const double* chi_h, const double* hub_h,
+                                                 const double* wlpref_h, const int32_t* kind_h, const double* ngal_h,
+                                                 const double* bias_h, int Kb, const int32_t* zmap_h, const double* ia_h,
+                                                 const double* lmin_h, const double* lmax_h, const double* noise_h,
+                                                 const double* sqrtfsky_h, const double* stw_h, const double* stden_h,
+                                                 double kmax, int tab_p, cfp_photo_plan** out) {
+  CFP_REQUIRE(Kb >= 1 && zmap_h != nullptr, "Kb >= 1 and a z map are required");
+  for (int i = 0; i < Nz; ++i) CFP_REQUIRE(zmap_h[i] >= 0 && zmap_h[i] < Kb, "z map entry out of range");
+  return photo_plan_create_impl(ctx, bank, S, NC, Nl, Nz, Nb, npar, cosmo_of_s_h, ell_h, z_h, dz, chi_h, hub_h, wlpref_h,
+                                kind_h, ngal_h, bias_h, ia_h, lmin_h, lmax_h, noise_h, sqrtfsky_h, stw_h, stden_h, kmax,
+                                tab_p, Kb, zmap_h, 1, nullptr, out, true);
 }
 
 extern "C" int cfp_photo_plan_create_ex(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb,
@@ -954,7 +992,7 @@ static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int
                                   const double* ia_h, const double* lmin_h, const double* lmax_h,
                                   const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
                                   const double* stden_h, double kmax, int tab_p, int Kb, const int32_t* zmap_h,
-                                  int NW, const int32_t* win_of_s_h, cfp_photo_plan** out) {
+                                  int NW, const int32_t* win_of_s_h, cfp_photo_plan** out, bool bias_shared) {
   CFP_REQUIRE(ctx && bank && out, "NULL ctx/bank/out");
   CFP_REQUIRE(cosmo_of_s_h && ell_h && z_h && chi_h && hub_h && wlpref_h && kind_h && ngal_h && bias_h && ia_h &&
                   lmin_h && lmax_h && noise_h && sqrtfsky_h && stw_h && stden_h,
@@ -1024,7 +1062,8 @@ static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int
     }
   }
   pl->Kb = Kb;
-  PH_UP(double, bias_h, (size_t)S * Nb * Kb, pl->bias_d);
+  pl->bias_rows = bias_shared ? 1 : Nb;  // shared: one bias vector per point for every clustering row
+  PH_UP(double, bias_h, (size_t)S * pl->bias_rows * Kb, pl->bias_d);
   if (zmap_h) PH_UP(int, zmap_h, (size_t)Nz, pl->zmap_d);
   PH_UP(double, ia_h, (size_t)S * Nz, pl->ia_d);
   PH_UP(double, lmin_h, (size_t)Nb, pl->lmin_d);
@@ -1058,9 +1097,16 @@ static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int
   }
   PH_UP(double, nullptr, (size_t)NC * Nl * Nz, pl->T_d);
   PH_UP(double, nullptr, (size_t)pl->NP * Nb * Nz, pl->eff_d);
-  PH_UP(double, nullptr, (size_t)S * pl->nb * 8 * ldz, pl->U_d);
-  PH_UP(double, nullptr, (size_t)S * pl->nb * 8 * ldz, pl->V_d);
-  PH_UP(double, nullptr, (size_t)S * Nl * Nb * Nb, pl->cls_d);
+  PH_ALLOC(double, (size_t)S * pl->nb * 8 * ldz, pl->U_d);  // (the window kernel writes every element, padding included)
+  PH_ALLOC(double, (size_t)S * pl->nb * 8 * ldz, pl->V_d);
+  if ((size_t)S * Nl * Nb * Nb * sizeof(double) > ((size_t)64 << 20)) {
+    // a likelihood batch: every multipole is written by every run (a multipole SLICE leaves the rest untouched,
+    // which only Fisher plans -- a few MB, zero-filled below -- are asked for)
+    PH_ALLOC(double, (size_t)S * Nl * Nb * Nb, pl->cls_d);
+  } else {
+    PH_UP(double, nullptr, (size_t)S * Nl * Nb * Nb, pl->cls_d);
+    pl->cls_zeroed = true;
+  }
   PH_UP(double, nullptr, (size_t)(Nl - 1) * npar * pl->zstride, pl->Y_d);
   PH_UP(double, nullptr, (size_t)(Nl - 1) * npar * npar, pl->Fl_d);
   PH_UP(double, nullptr, (size_t)npar * npar, pl->fisher_d);
@@ -1076,7 +1122,17 @@ static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int
 extern "C" int cfp_photo_plan_destroy(cfp_photo_plan* plan) {
   if (!plan) return CFP_OK;
   cudaSetDevice(plan->ctx->device);
-  if (plan->last_st && plan->last_st != plan->ctx->stream) cudaStreamSynchronize(plan->last_st);
+  // the buffers return to the pool on the context stream: wait for THIS plan's work on the caller's stream -- its own
+  // end-of-run events, not the whole stream, which in a pipeline of batches already holds the next plan's kernels
+  if (plan->last_st && plan->last_st != plan->ctx->stream) {
+    if (plan->chi_pending && plan->chi_up) {
+      cudaEventSynchronize(plan->chi_up);
+    } else if (plan->run1) {
+      cudaEventSynchronize(plan->run1);
+    } else {
+      cudaStreamSynchronize(plan->last_st);
+    }
+  }
   photo_free(plan);
   return CFP_OK;
 }
@@ -1102,6 +1158,14 @@ extern "C" int cfp_photo_plan_set_slice(cfp_photo_plan* plan, int l_begin, int l
   CFP_REQUIRE(l_begin >= 0 && l_begin <= l_end && l_end <= plan->Nl - 1, "slice out of range");
   plan->l_begin = l_begin;
   plan->l_end = l_end;
+  if (!plan->cls_zeroed && !(l_begin == 0 && l_end == plan->Nl - 1)) {
+    // a partial run leaves the spectra of the other multipoles untouched: define them (zero) once
+    CFP_CUDA(cudaSetDevice(plan->ctx->device));
+    CFP_CUDA(cudaMemsetAsync(plan->cls_d, 0, (size_t)plan->S * plan->Nl * plan->Nb * plan->Nb * sizeof(double),
+                             plan->ctx->stream));
+    CFP_CUDA(cudaStreamSynchronize(plan->ctx->stream));
+    plan->cls_zeroed = true;
+  }
   return CFP_OK;
 }
 
@@ -1183,7 +1247,7 @@ static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
     photo_window_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
         pl->S, pl->Nb, pl->Nz, pl->ldz, pl->nb * 8, pl->cosmo_of_s_d, pl->win_of_s_d, pl->pair_of_s_d, pl->kind_d,
         pl->z_d, pl->chi_d, pl->hub_d,
-        pl->wlpref_d, pl->ngal_d, pl->bias_d, pl->Kb, pl->zmap_d, pl->ia_d, pl->eff_d, pl->U_d, pl->V_d);
+        pl->wlpref_d, pl->ngal_d, pl->bias_d, pl->Kb, pl->bias_rows, pl->zmap_d, pl->ia_d, pl->eff_d, pl->U_d, pl->V_d);
     ctx->launches++;
     CFP_CUDA(cudaGetLastError());
   }
@@ -1269,10 +1333,21 @@ static int photo_run_fisher(cfp_photo_plan* pl, cudaStream_t st) {
   return CFP_OK;
 }
 
-extern "C" int cfp_photo_plan_chi2(cfp_photo_plan* pl, const double* data_h, int nblk, const int32_t* blk_off_h,
-                                   const int32_t* blk_n_h, const double* blk_w_h, double* chi2_h, void* stream) {
-  CFP_REQUIRE(pl && blk_off_h && blk_n_h && blk_w_h && chi2_h, "NULL argument");
+// chi^2 of every point of the plan, in two halves so that a caller can keep the device busy while it prepares the next
+// batch on the host: _launch uploads the block description, enqueues C_ell, the factorisations and the multipole sums
+// on `stream` (NULL: the context stream) and a copy of the result into a page-locked buffer of the plan, and RETURNS
+// without waiting; _collect waits for that copy and hands out chi2_h[S].  cfp_photo_plan_chi2 = both.
+static void photo_chi_release(cfp_photo_plan* pl) {
+  for (void* q : pl->chi_tmp) cfp_dev_free(pl->ctx, q);
+  pl->chi_tmp.clear();
+  pl->chi_pending = false;
+}
+
+extern "C" int cfp_photo_plan_chi2_launch(cfp_photo_plan* pl, const double* data_h, int nblk, const int32_t* blk_off_h,
+                                          const int32_t* blk_n_h, const double* blk_w_h, void* stream) {
+  CFP_REQUIRE(pl && blk_off_h && blk_n_h && blk_w_h, "NULL argument");
   CFP_REQUIRE(nblk >= 1 && nblk <= 8, "1..8 blocks");
+  CFP_REQUIRE(!pl->chi_pending, "a chi2 launch of this plan has not been collected yet");
   for (int b = 0; b < nblk; ++b)
     CFP_REQUIRE(blk_n_h[b] >= 1 && blk_n_h[b] <= 32 && blk_off_h[b] >= 0 && blk_off_h[b] + blk_n_h[b] <= pl->Nb,
                 "block out of range (at most 32 rows per block)");
@@ -1280,63 +1355,99 @@ extern "C" int cfp_photo_plan_chi2(cfp_photo_plan* pl, const double* data_h, int
   CFP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   const int S = pl->S, Nl = pl->Nl, Nb = pl->Nb;
+  int nmax = 1;
+  for (int b = 0; b < nblk; ++b) nmax = std::max(nmax, (int)blk_n_h[b]);
   int *off_d = nullptr, *n_d = nullptr;
-  double *w_d = nullptr, *data_d = nullptr, *lndet_d = nullptr, *q_d = nullptr, *chi2_d = nullptr;
+  double *w_d = nullptr, *data_d = nullptr, *lndet_d = nullptr, *q_d = nullptr, *chi2_d = nullptr, *zero_d = nullptr,
+         *lb_d = nullptr;
   int rc = CFP_OK;
-  auto cleanup = [&]() {
-    for (void* q : {(void*)off_d, (void*)n_d, (void*)w_d, (void*)data_d, (void*)lndet_d, (void*)q_d, (void*)chi2_d})
-      cfp_dev_free(ctx, q);
-  };
-#define CHI_TRY(x)            \
-  do {                        \
-    rc = (x);                 \
-    if (rc != CFP_OK) {       \
-      cleanup();              \
-      return rc;              \
-    }                         \
+#define CHI_TRY(x, ptr)                      \
+  do {                                       \
+    rc = (x);                                \
+    if (rc != CFP_OK) {                      \
+      photo_chi_release(pl);                 \
+      return rc;                             \
+    }                                        \
+    pl->chi_tmp.push_back((void*)(ptr));     \
   } while (0)
-  CHI_TRY(cfp_upload(ctx, blk_off_h, (size_t)nblk, &off_d));
-  CHI_TRY(cfp_upload(ctx, blk_n_h, (size_t)nblk, &n_d));
-  CHI_TRY(cfp_upload(ctx, blk_w_h, (size_t)nblk * Nl, &w_d));
-  CHI_TRY(cfp_upload<double>(ctx, data_h, (size_t)Nl * Nb * Nb, &data_d));
-  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nl * nblk, &lndet_d));
-  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S * Nl * nblk, &q_d));
-  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d));
-  if (st != ctx->stream) cudaStreamSynchronize(ctx->stream);  // uploads ran on the context stream
+  CHI_TRY(cfp_upload(ctx, blk_off_h, (size_t)nblk, &off_d), off_d);
+  CHI_TRY(cfp_upload(ctx, blk_n_h, (size_t)nblk, &n_d), n_d);
+  CHI_TRY(cfp_upload(ctx, blk_w_h, (size_t)nblk * Nl, &w_d), w_d);
+  CHI_TRY(cfp_upload<double>(ctx, data_h, (size_t)Nl * Nb * Nb, &data_d), data_d);
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nl * nblk, &lndet_d), lndet_d);
+  {  // q is written for every (point, multipole, block): allocation only
+    cudaError_t ea = cfp_dev_alloc(ctx, (void**)&q_d, (size_t)S * Nl * nblk * sizeof(double));
+    CHI_TRY(ea == cudaSuccess ? CFP_OK : CFP_ERR_CUDA, q_d);
+  }
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)S, &chi2_d), chi2_d);
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nb, &zero_d), zero_d);
+  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nl * nblk * nmax * nmax, &lb_d), lb_d);
+#undef CHI_TRY
+  if (!pl->chi2_pin) pl->chi2_pin = (double*)cfp_pinned_acquire(ctx, (size_t)S * sizeof(double));
+  if (!pl->chi2_pin) {
+    photo_chi_release(pl);
+    cfp_set_error("cfp_photo_plan_chi2: cannot allocate the page-locked result buffer");
+    return CFP_ERR_CUDA;
+  }
   if (!pl->run0) {
     cudaEventCreate(&pl->run0);
     cudaEventCreate(&pl->run1);
   }
+  if (!pl->chi_up) cudaEventCreate(&pl->chi_up);
+  if (st != ctx->stream) {  // the uploads ran on the context stream: order the work stream behind them (no host wait)
+    cudaEventRecord(pl->chi_up, ctx->stream);
+    cudaStreamWaitEvent(st, pl->chi_up, 0);
+  }
   cudaEventRecord(pl->run0, st);
-  CHI_TRY(photo_run_cls(pl, st, true));
+  rc = photo_run_cls(pl, st, true);
+  if (rc != CFP_OK) {
+    photo_chi_release(pl);
+    return rc;
+  }
   if (!data_h) {
     photo_add_noise_kernel<<<(Nl * Nb * Nb + 255) / 256, 256, 0, st>>>(Nl, Nb, pl->cls_d, pl->noise_d, data_d);
     ctx->launches++;
   }
-  int nmax = 1;
-  for (int b = 0; b < nblk; ++b) nmax = std::max(nmax, (int)blk_n_h[b]);
-  double *zero_d = nullptr, *lb_d = nullptr;
-  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nb, &zero_d));
-  CHI_TRY(cfp_upload<double>(ctx, nullptr, (size_t)Nl * nblk * nmax * nmax, &lb_d));
-  if (st != ctx->stream) cudaStreamSynchronize(ctx->stream);
   // ln det and Cholesky factor of the data blocks, then every (point, multipole), then the multipole sums
   cudaError_t e = photo_launch_chi2(ctx, st, S, Nl, Nb, nblk, blk_off_h, blk_n_h, nmax, pl->cls_d, pl->noise_d, data_d, w_d,
                                     lb_d, lndet_d, q_d, chi2_d);
   cudaEventRecord(pl->run1, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(chi2_h, chi2_d, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pl->chi2_pin, chi2_d, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaEventRecord(pl->chi_up, st);  // (re-used: marks the end of the result copy)
+  if (e != cudaSuccess) {
+    cudaStreamSynchronize(st);
+    photo_chi_release(pl);
+    cfp_set_error("cfp_photo_plan_chi2: %s", cudaGetErrorString(e));
+    return CFP_ERR_CUDA;
+  }
+  pl->last_st = st;
+  pl->chi_pending = true;
+  return CFP_OK;
+}
+
+extern "C" int cfp_photo_plan_chi2_collect(cfp_photo_plan* pl, double* chi2_h) {
+  CFP_REQUIRE(pl && chi2_h, "NULL argument");
+  CFP_REQUIRE(pl->chi_pending, "no chi2 launch to collect");
+  cfp_ctx* ctx = pl->ctx;
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  cudaError_t e = cudaEventSynchronize(pl->chi_up);
   float ms = 0.f;
   if (e == cudaSuccess && cudaEventElapsedTime(&ms, pl->run0, pl->run1) == cudaSuccess) ctx->last_ms = ms;
-  cfp_dev_free(ctx, zero_d);
-  cfp_dev_free(ctx, lb_d);
-  cleanup();
-#undef CHI_TRY
+  if (e == cudaSuccess) std::memcpy(chi2_h, pl->chi2_pin, (size_t)pl->S * sizeof(double));
+  photo_chi_release(pl);
   if (e != cudaSuccess) {
     cfp_set_error("cfp_photo_plan_chi2: %s", cudaGetErrorString(e));
     return CFP_ERR_CUDA;
   }
   pl->ran = true;
   return CFP_OK;
+}
+
+extern "C" int cfp_photo_plan_chi2(cfp_photo_plan* pl, const double* data_h, int nblk, const int32_t* blk_off_h,
+                                   const int32_t* blk_n_h, const double* blk_w_h, double* chi2_h, void* stream) {
+  CFP_REQUIRE(chi2_h != nullptr, "NULL argument");
+  const int rc = cfp_photo_plan_chi2_launch(pl, data_h, nblk, blk_off_h, blk_n_h, blk_w_h, stream);
+  return rc == CFP_OK ? cfp_photo_plan_chi2_collect(pl, chi2_h) : rc;
 }
 
 extern "C" double cfp_photo_plan_kernel_ms(cfp_photo_plan* pl, int which) {

@@ -2096,7 +2096,14 @@ extern "C" int cfp_spectro_plan_create(cfp_ctx* ctx, const cfp_bank* bank, int S
 extern "C" int cfp_spectro_plan_destroy(cfp_spectro_plan* plan) {
   if (!plan) return CFP_OK;
   cudaSetDevice(plan->ctx->device);
-  if (plan->last_st && plan->last_st != plan->ctx->stream) cudaStreamSynchronize(plan->last_st);
+  // wait for THIS plan's last run on the caller's stream (its own event), not for the whole stream: in a pipeline of
+  // batches the stream already holds the next plan's kernels
+  if (plan->last_st && plan->last_st != plan->ctx->stream) {
+    if (plan->run1)
+      cudaEventSynchronize(plan->run1);
+    else
+      cudaStreamSynchronize(plan->last_st);
+  }
   spectro_free(plan);
   return CFP_OK;
 }

@@ -277,24 +277,22 @@ class PhotometricLikelihood(Likelihood, NautilusMixin):
             out[:] = job.plan().chi2(off, n, w, data=self._data_full)
             job.close()
             return out
-        # software pipeline over the chunks: chunk i's kernels run on the context's second stream from a worker thread
-        # (ctypes releases the GIL while it waits) while this thread assembles and uploads chunk i+1
-        from concurrent.futures import ThreadPoolExecutor
-
-        def run(job, a, b):
-            plan = job.plan()
-            out[a:b] = plan.chi2(off, n, w, data=self._data_full, stream=plan.ctx.aux_stream)
-            job.close()
-
-        with ThreadPoolExecutor(max_workers=1) as pool:
-            pending = None
-            for a, b in spans:
-                job = photo_mod.PhotoJob.from_matrix(self.cosmo_theory, names, matrix[a:b])
-                job.plan()  # create + H2D now, on the context stream
-                if pending is not None:
-                    pending.result()
-                pending = pool.submit(run, job, a, b)
-            pending.result()
+        # software pipeline over the chunks, no threads: chunk i's kernels are ENQUEUED on the context's second stream
+        # (cfp_photo_plan_chi2_launch returns without waiting) and run while this thread assembles and uploads chunk
+        # i + 1; the result of chunk i is collected afterwards
+        pending = None
+        for a, b in spans:
+            job = photo_mod.PhotoJob.from_matrix(self.cosmo_theory, names, matrix[a:b])
+            plan = job.plan()  # create + H2D, on the context stream
+            plan.chi2_launch(off, n, w, data=self._data_full, stream=plan.ctx.aux_stream)
+            if pending is not None:
+                pjob, pa, pb = pending
+                out[pa:pb] = pjob.plan().chi2_collect()
+                pjob.close()
+            pending = (job, a, b)
+        pjob, pa, pb = pending
+        out[pa:pb] = pjob.plan().chi2_collect()
+        pjob.close()
         return out
 
     def chi2_batch(self, param_dicts) -> np.ndarray:

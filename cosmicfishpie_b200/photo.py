@@ -357,7 +357,10 @@ class PhotoJob:
             win = fac[:, None] * z_dep[None, :] ** eta[:, None] * ((nuis._lum_z[None, :] ** beta[:, None]) / growth)
             j = np.clip(np.searchsorted(zz, g.z, side="right") - 1, 0, len(zz) - 2)
             t = (g.z - zz[j]) / (zz[j + 1] - zz[j])
-            self.ia = win[:, j] * (1.0 - t)[None, :] + win[:, j + 1] * t[None, :]
+            # (np.take keeps the result C-ordered; `win[:, j]` comes back transposed in memory and would be copied again
+            # on upload)
+            self.ia = np.take(win, j, axis=1) * (1.0 - t)[None, :]
+            self.ia += np.take(win, j + 1, axis=1) * t[None, :]
         if "GCph" in g.observables:
             bp = cfg.Photobiasparams
             model = bp["bias_model"]
@@ -368,9 +371,7 @@ class PhotoJob:
                 brang = list(configuration.specs["binrange_GCph"])
                 vals = np.stack([column(f"b{k}", bp[f"b{k}"]) for k in brang], axis=1)            # [B, nbins]
                 self.zmap = np.clip(np.searchsorted(edges, g.z, side="right") - 1, 0, brang[-1] - 1).astype(np.int32)
-                self.bias = np.empty((B, Nb, vals.shape[1]))
-                self.bias[:] = 1.0
-                self.bias[:, gc_rows, :] = vals[:, None, :]
+                self.bias = np.ascontiguousarray(vals)  # [B, nbins]: every clustering row shares the point's vector
             elif model == "binned_constant":
                 self.zmap = np.zeros(Nz, dtype=np.int32)
                 self.bias = np.ones((B, Nb, 1))
@@ -397,6 +398,20 @@ class PhotoJob:
         self.NC = len(cs)
         self._plan = None
         return self
+
+    def dense_bias(self) -> np.ndarray:
+        """Galaxy bias [S][Nb][Nz] on the z grid, whatever compact form the job holds it in (per-bin samples and a
+        z -> bin map, per point or per (point, row)); lensing rows carry 1."""
+        b = self.bias
+        zmap = getattr(self, "zmap", None)
+        if zmap is None:
+            return b
+        if b.ndim == 2:  # one vector per point, shared by the clustering rows
+            out = np.ones((b.shape[0], len(self.grid.rows), len(zmap)))
+            gc = [a for a, (o, _) in enumerate(self.grid.rows) if o == "GCph"]
+            out[:, gc, :] = b[:, zmap][:, None, :]
+            return out
+        return b[:, :, zmap]
 
     def plan(self) -> _lib.PhotoPlan:
         if self._plan is None:

@@ -254,6 +254,18 @@ int cfp_photo_plan_create_zmap(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC
                                const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
                                const double* stden_h, double kmax, int tab_p, cfp_photo_plan** out);
 
+/* As cfp_photo_plan_create_zmap with ONE bias vector per point shared by every clustering row, bias_h[S][Kb]: the
+ * `binned` model assigns the same per-bin values to all rows (nuisance.py:118-128), so a likelihood batch uploads
+ * S*n_bins doubles. */
+int cfp_photo_plan_create_zmap_shared(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, int Nl, int Nz, int Nb, int npar,
+                                      const int32_t* cosmo_of_s_h, const double* ell_h, const double* z_h, double dz,
+                                      const double* chi_h, const double* hub_h, const double* wlpref_h,
+                                      const int32_t* kind_h, const double* ngal_h, const double* bias_h, int Kb,
+                                      const int32_t* zmap_h, const double* ia_h, const double* lmin_h,
+                                      const double* lmax_h, const double* noise_h, const double* sqrtfsky_h,
+                                      const double* stw_h, const double* stden_h, double kmax, int tab_p,
+                                      cfp_photo_plan** out);
+
 /* The general form: NW sets of tomographic n_i(z) windows (ngal_h[NW][Nb][Nz]) with one index per stencil point
  * (win_of_s_h[S], NULL when NW == 1) -- stencil points that vary a photo-z parameter carry their own windows
  * (photo_cov.py:116-160 builds a new GalaxyPhotoDist per parameter point); zmap_h may be NULL (bias_h[S][Nb][Nz]). */
@@ -277,6 +289,12 @@ int cfp_photo_plan_set_slice(cfp_photo_plan* plan, int l_begin, int l_end);
 int cfp_photo_plan_run(cfp_photo_plan* plan, void* stream);
 /* Device time [ms] of one kernel of the last run: which = 0 Limber table, 1 C_ell contraction (DMMA),
  * 2 Cholesky/trace Fisher; synchronises. */
+/* cfp_photo_plan_chi2 in two halves: _launch enqueues everything on `stream` (NULL: the context stream) and returns
+ * without waiting, _collect waits for the result and copies chi2_h[S] out.  A sampler prepares and uploads its next
+ * batch between the two, so the device never idles (PhotometricLikelihood.chi2_matrix does exactly that). */
+int cfp_photo_plan_chi2_launch(cfp_photo_plan* plan, const double* data_h, int nblk, const int32_t* blk_off_h,
+                               const int32_t* blk_n_h, const double* blk_w_h, void* stream);
+int cfp_photo_plan_chi2_collect(cfp_photo_plan* plan, double* chi2_h);
 double cfp_photo_plan_kernel_ms(cfp_photo_plan* plan, int which);
 /* Radial kernels of the last run on the plan's z grid, [S][Nb][Nz] each (host): U = W_a / sqrt(H) (lensing efficiency
  * term or galaxy kernel x bias), V = W^IA_a / sqrt(H).  Replaces ComputeCls.lensing_kernel / galaxy_kernel

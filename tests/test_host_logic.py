@@ -155,7 +155,7 @@ def test_photo_job_assembly(extfiles, tmp_path):
     assert np.all(g.lmax[:10] == 1500) and np.all(g.lmax[10:] == 750)
     # b3 step changes only the bias window inside bin 3
     s_b3 = 1 + 2 * (2 + 2)
-    bias = job.bias if getattr(job, "zmap", None) is None else job.bias[:, :, job.zmap]  # (per-bin samples + z -> bin map)
+    bias = job.dense_bias()  # (the job may hold per-bin samples + a z -> bin map)
     diff = np.nonzero(np.any(bias[s_b3] != bias[0], axis=0))[0]
     zb = fm.specs["z_bins_GCph"]
     assert np.all((g.z[diff] >= zb[2]) & (g.z[diff] < zb[3]))

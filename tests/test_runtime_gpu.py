@@ -121,10 +121,10 @@ def test_photo_plan_zmap_equals_dense_bias(extfiles, tmp_path):
     rng = np.random.default_rng(5)
     mat = np.array([fm.allparams[n] for n in names]) * (1 + 0.03 * rng.standard_normal((6, len(names))))
     job = PhotoJob.from_matrix(fm, names, mat)
-    assert job.zmap is not None and job.bias.shape[2] == len(fm.specs["binrange_GCph"])
+    assert job.zmap is not None and job.bias.shape == (6, len(fm.specs["binrange_GCph"]))  # one bias vector per point
     compact = job.run().fetch(cls=True)[1]
     g = job.grid
-    dense_bias = job.bias[:, :, job.zmap]  # [B, Nb, Nz]
+    dense_bias = job.dense_bias()  # [B, Nb, Nz]
     cs = job.cosmo_set
     dense = _lib.PhotoPlan(cs.ctx, cs.bank(), cosmo_of_s=job.cosmo_of_s, ell=g.ell, z=g.z, dz=g.dz, chi=job.chi,
                            hub=job.hub, wlpref=job.wlpref, kind=g.kind, ngal=job.ngal, bias=dense_bias, ia=job.ia,
