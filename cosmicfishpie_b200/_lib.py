@@ -39,7 +39,8 @@ EXPORTS = [
     "cfp_photo_plan_set_gc_table", "cfp_spectro_plan_chi2_legendre", "cfp_spectro_plan_kernel_ms_part",
     "cfp_math_selftest", "cfp_spectro_plan_terms", "cfp_photo_plan_fetch_windows", "cfp_photo_fisher",
     "cfp_fisher_batch_post", "cfp_fisher_batch_add", "cfp_bank_combine", "cfp_photo_plan_create_zmap_shared",
-    "cfp_photo_plan_chi2_launch", "cfp_photo_plan_chi2_collect",
+    "cfp_photo_plan_chi2_launch", "cfp_photo_plan_chi2_collect", "cfp_bank_fit", "cfp_background_fit",
+    "cfp_bank_eval_many", "cfp_bank_nowiggle", "cfp_bank_theta_moments",
 ]
 
 
@@ -131,6 +132,12 @@ def load():
     lib.cfp_photo_plan_fisher_d.restype = _vp
     lib.cfp_photo_plan_fetch.argtypes = [_vp, _dp, _dp, _dp]
     lib.cfp_photo_plan_chi2.argtypes = [_vp, _dp, C.c_int, _ip, _ip, _dp, _dp, _vp]
+    lib.cfp_bank_fit.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, C.POINTER(_vp), _dp, C.POINTER(_vp)]
+    lib.cfp_background_fit.argtypes = [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, _dp, _dp]
+    lib.cfp_bank_eval_many.argtypes = [_vp, _vp, C.c_int, C.c_size_t, _dp, _dp, _dp]
+    lib.cfp_bank_nowiggle.argtypes = [_vp, _vp, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, _ip, _ip, _lp, _dp,
+                                      C.c_size_t, _dp]
+    lib.cfp_bank_theta_moments.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp]
     lib.cfp_photo_plan_chi2_launch.argtypes = [_vp, _dp, C.c_int, _ip, _ip, _dp, _vp]
     lib.cfp_photo_plan_chi2_collect.argtypes = [_vp, _dp]
     lib.cfp_spectro_plan_chi2.argtypes = [_vp, _dp, _dp, _dp, _dp, _vp]
@@ -441,6 +448,72 @@ class Bank:
         _check(ctx.lib.cfp_bank_upload(ctx.handle, _p(self.blob), self.blob.size, _p(desc, _lp), n_cosmo, NTAB,
                                        C.byref(self.handle)), "cfp_bank_upload")
 
+    @classmethod
+    def fit(cls, ctx: Context, z, k, tables, scales) -> "Bank":
+        """Bank fitted ON THE DEVICE from raw tables (cfp_bank_fit): z[Nz], k[NC][Nk], tables[c][slot] = [Nz][Nk] array or
+        None (the same slots for every cosmology), scales[c][slot]."""
+        z, k = f64(z), f64(k)
+        NC, Nk = k.shape
+        keep, ptrs = [], (_vp * (NC * NTAB))()
+        sc = np.ones((NC, NTAB))
+        for c, row in enumerate(tables):
+            for slot in range(NTAB):
+                t = row[slot] if slot < len(row) else None
+                if t is None:
+                    continue
+                a = f64(t)
+                assert a.shape == (z.size, Nk), (a.shape, z.size, Nk)
+                keep.append(a)
+                ptrs[c * NTAB + slot] = a.ctypes.data
+                sc[c, slot] = scales[c][slot]
+        self = cls.__new__(cls)
+        self.ctx, self.rows, self.blob, self.desc, self.n_cosmo = ctx, [], None, None, NC
+        self.nbytes = sum(a.nbytes for a in keep) + z.nbytes + k.nbytes
+        self.handle = _vp()
+        _check(ctx.lib.cfp_bank_fit(ctx.handle, NC, NTAB, z.size, Nk, _p(z), _p(k), ptrs, _p(sc), C.byref(self.handle)),
+               "cfp_bank_fit")
+        return self
+
+    def eval_many(self, table: int, z, k) -> np.ndarray:
+        """[n_cosmo][n] values of one table of EVERY cosmology at the points (z, k) (cfp_bank_eval_many)."""
+        z, k = np.broadcast_arrays(f64(z), f64(k))
+        z, k = f64(z).ravel(), f64(k).ravel()
+        out = np.empty((self.n_cosmo, z.size))
+        _check(self.ctx.lib.cfp_bank_eval_many(self.ctx.handle, self.handle, int(table), z.size, _p(z), _p(k), _p(out)),
+               "cfp_bank_eval_many")
+        return out
+
+    def nowiggle(self, table: int, zq, ks, filt_of_c, filters) -> np.ndarray:
+        """[n_cosmo][nzq][nsamp] no-wiggle spectra (cfp_bank_nowiggle); ks[n_cosmo][nsamp] sample wavenumbers,
+        filters = [(taps[win], off, EL[ne][wc], ER[ne][wc]), ...], filt_of_c[n_cosmo] picks one per cosmology."""
+        zq, ks = f64(zq).ravel(), f64(ks)
+        assert ks.shape[0] == self.n_cosmo
+        fdesc = np.zeros((len(filters), 4), dtype=np.int32)
+        foff = np.zeros(len(filters), dtype=np.int64)
+        parts, off = [], 0
+        for i, (taps, o, EL, ER) in enumerate(filters):
+            taps, EL, ER = f64(taps).ravel(), f64(EL), f64(ER)
+            assert EL.shape == ER.shape
+            fdesc[i] = (taps.size, o, EL.shape[0], EL.shape[1])
+            foff[i] = off
+            parts += [taps, EL.ravel(), ER.ravel()]
+            off += taps.size + 2 * EL.size
+        blob = np.concatenate(parts)
+        out = np.empty((self.n_cosmo, zq.size, ks.shape[1]))
+        fc = i32(filt_of_c)
+        _check(self.ctx.lib.cfp_bank_nowiggle(self.ctx.handle, self.handle, int(table), zq.size, _p(zq), ks.shape[1], _p(ks),
+                                              len(filters), _p(fc, _ip), _p(fdesc, _ip), _p(foff, _lp), _p(blob), blob.size,
+                                              _p(out)), "cfp_bank_nowiggle")
+        return out
+
+    def theta_moments(self, tab_p: int, tab_f: int, zq, k) -> np.ndarray:
+        """[n_cosmo][nzq][3] velocity moments (cfp_bank_theta_moments)."""
+        zq, k = f64(zq).ravel(), f64(k).ravel()
+        out = np.empty((self.n_cosmo, zq.size, 3))
+        _check(self.ctx.lib.cfp_bank_theta_moments(self.ctx.handle, self.handle, int(tab_p), int(tab_f), zq.size, _p(zq),
+                                                   k.size, _p(k), _p(out)), "cfp_bank_theta_moments")
+        return out
+
     def combined(self, W) -> "Bank":
         """A new bank: this bank's rows followed by len(W) rows combined on the device, row m = sum_c W[m][c] * row_c
         (cfp_bank_combine): emulated cosmologies without host fits."""
@@ -476,6 +549,23 @@ class Bank:
             self.close()
         except Exception:
             pass
+
+
+def background_fit(ctx: Context, z, hub, extra, zq=None, ntrap: int = 100, coef: bool = False):
+    """Background functions of NC cosmologies fitted on the device (cfp_background_fit): rows H, comoving distance,
+    angular-diameter distance, then the extra functions of z.  Returns the values [NC][3 + n_extra][nq] at the
+    redshifts zq (None without zq) and, with coef=True, the B-spline coefficients [NC][3 + n_extra][Nz] as well."""
+    z, hub = f64(z).ravel(), f64(hub)
+    zq = f64(zq).ravel() if zq is not None else np.zeros(0)
+    NC = hub.shape[0]
+    extra = f64(extra) if extra is not None and np.size(extra) else np.zeros((NC, 0, z.size))
+    assert hub.shape == (NC, z.size) and extra.shape[0] == NC and extra.shape[2] == z.size
+    out = np.empty((NC, 3 + extra.shape[1], zq.size))
+    cf = np.empty((NC, 3 + extra.shape[1], z.size)) if coef else None
+    _check(ctx.lib.cfp_background_fit(ctx.handle, NC, z.size, _p(z), _p(hub), extra.shape[1], _p(extra), int(ntrap), zq.size,
+                                      _p(zq), _p(out), _p(cf) if coef else None), "cfp_background_fit")
+    out = out if zq.size else None
+    return (out, cf) if coef else out
 
 
 class SpectroPlan:

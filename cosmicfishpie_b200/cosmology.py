@@ -119,16 +119,54 @@ def _dcom_all(zgrid, hfunc):
 class _LazySpline:
     """RectBivariateSpline built on first use (a GCsp job never touches P_nl, a photo job never f)."""
 
-    def __init__(self, zg, kg, table):
-        self._args = (zg, kg, table)
+    def __init__(self, zg, kg, table, scale=1.0):
+        self._args = (zg, kg, table, scale)
         self._spl = None
 
     def get(self):
         if self._spl is None:
-            zg, kg, tab = self._args
-            self._spl = RectBivariateSpline(zg, kg, tab, kx=3, ky=3)
+            zg, kg, tab, scale = self._args
+            tab = np.asarray(tab, float)
+            self._spl = RectBivariateSpline(zg, kg, tab if scale == 1.0 else scale * tab, kx=3, ky=3)
             self._args = None
         return self._spl
+
+
+def device_prep(settings) -> bool:
+    """Spline fits, comoving distances, no-wiggle spectra and velocity moments of a job's cosmologies on the device
+    (csrc/cfp_prep.cu) -- the default; `options["device_prep"] = False` or CFP_HOST_PREP=1 keep them on the host
+    (scipy, as the reference does them)."""
+    if os.environ.get("CFP_HOST_PREP", "0") not in ("", "0"):
+        return False
+    return bool((settings or {}).get("device_prep", True))
+
+
+def nak_knots(x):
+    """FITPACK's knots of an interpolating cubic spline through the abscissae x (fpcurf.f with s = 0)."""
+    x = np.asarray(x, float)
+    return np.concatenate((np.full(4, x[0]), x[2:-2], np.full(4, x[-1])))
+
+
+_SAVGOL_OPS: Dict[tuple, tuple] = {}
+
+
+def savgol_operator(win: int, order: int):
+    """scipy.signal.savgol_filter(x, win, order) (mode="interp") as a linear operator, for cfp_bank_nowiggle:
+    (taps[win], off, EL[half][win], ER[half][win]) -- interior row s is taps . x[s + off : s + off + win]; the first and
+    last half = win // 2 rows are the least-squares polynomial through the first / last `win` samples evaluated at
+    those positions (scipy's _fit_edges_polyfit), here in a centred Legendre basis (agrees with scipy to 1e-14)."""
+    key = (int(win), int(order))
+    if key not in _SAVGOL_OPS:
+        from scipy.signal import savgol_coeffs
+
+        half = win // 2
+        taps = np.ascontiguousarray(savgol_coeffs(win, order)[::-1])  # convolution -> correlation order
+        off = -half if win % 2 else -half + 1  # scipy.ndimage.convolve1d's centre of an even-length kernel
+        x = (np.arange(win, dtype=float) - 0.5 * (win - 1)) / (0.5 * (win - 1))
+        V = np.polynomial.legendre.legvander(x, order)
+        P = np.linalg.pinv(V)
+        _SAVGOL_OPS[key] = (taps, off, np.ascontiguousarray(V[:half] @ P), np.ascontiguousarray(V[win - half:] @ P))
+    return _SAVGOL_OPS[key]
 
 
 class cosmo_functions:
@@ -179,31 +217,52 @@ class cosmo_functions:
         zg = np.asarray(t["z"], float).flatten()
         kg = kf * np.asarray(t["k"], float).flatten()
         self.zgrid, self.kgrid = zg, kg
-        self.h_of_z = InterpolatedUnivariateSpline(zg, (1 / rf) * np.asarray(t["H"], float).flatten())
-        dcom = _dcom_all(zg, self.h_of_z)
-        self.com_dist = InterpolatedUnivariateSpline(zg, dcom)
-        self.ang_dist = InterpolatedUnivariateSpline(zg, dcom / (1 + zg))
+        # raw tables in the bank's units: what the device fits (CosmoSet.prepare / bank) and the host fallbacks fit
+        self._tab1d = {"h_of_z": (1 / rf) * np.asarray(t["H"], float).flatten(), "s8_of_z": np.asarray(t["s8"], float).flatten()}
+        self._tab2d = {_lib.TAB_PLIN: (t["Pl"], pkf), _lib.TAB_PNL: (t["Pnl"], pkf), _lib.TAB_F: (t["f"], 1.0),
+                       _lib.TAB_D: (t["D"], 1.0)}
         self._lazy = {
             "D_growth_zk": _LazySpline(zg, kg, t["D"]),
             "f_growthrate_zk": _LazySpline(zg, kg, t["f"]),
-            "Pk_l": _LazySpline(zg, kg, pkf * np.asarray(t["Pl"], float)),
-            "Pk_nl": _LazySpline(zg, kg, pkf * np.asarray(t["Pnl"], float)),
+            "Pk_l": _LazySpline(zg, kg, t["Pl"], pkf),
+            "Pk_nl": _LazySpline(zg, kg, t["Pnl"], pkf),
         }
-        self.s8_of_z = InterpolatedUnivariateSpline(zg, np.asarray(t["s8"], float).flatten())
         if self.cb_files_on:  # cosmology.py:1508-1531
             self._lazy.update({
                 "f_growthrate_cb_zk": _LazySpline(zg, kg, t["fcb"]),
-                "Pk_cb_l": _LazySpline(zg, kg, pkf * np.asarray(t["Plcb"], float)),
-                "Pk_cb_nl": _LazySpline(zg, kg, pkf * np.asarray(t["Pnlcb"], float)),
+                "Pk_cb_l": _LazySpline(zg, kg, t["Plcb"], pkf),
+                "Pk_cb_nl": _LazySpline(zg, kg, t["Pnlcb"], pkf),
             })
-            self.s8_cb_of_z = InterpolatedUnivariateSpline(zg, np.asarray(t["s8cb"], float).flatten())
+            self._tab1d["s8_cb_of_z"] = np.asarray(t["s8cb"], float).flatten()
+            self._tab2d.update({_lib.TAB_PLIN_CB: (t["Plcb"], pkf), _lib.TAB_PNL_CB: (t["Pnlcb"], pkf),
+                                _lib.TAB_F_CB: (t["fcb"], 1.0)})
+        if not device_prep(self.settings):
+            for name in ("h_of_z", "com_dist", "ang_dist", "s8_of_z"):  # the reference fits these eagerly
+                getattr(self, name)
         self.results = self  # reference code reaches splines through `.results`
         self._nw_cache = {}
+        self._moment_cache = {}
 
-    def __getattr__(self, name):  # the four (z,k) splines, fitted on first access
-        lazy = self.__dict__.get("_lazy")
+    def __getattr__(self, name):
+        """The splines, fitted on first access: the (z, k) surfaces (a GCsp job never touches P_nl, a photo job never f)
+        and the functions of z.  `CosmoSet.prepare` fits the latter on the device for all cosmologies of a job at once
+        and stores them under the same names, so this host fit (scipy, the reference's own calls,
+        cosmology.py:1447-1506) only runs for a facade used on its own."""
+        d = self.__dict__
+        lazy = d.get("_lazy")
         if lazy is not None and name in lazy:
             return lazy[name].get()
+        tab = d.get("_tab1d")
+        if tab is not None:
+            if name in tab:
+                spl = InterpolatedUnivariateSpline(self.zgrid, tab[name])
+                d[name] = spl
+                return spl
+            if name in ("com_dist", "ang_dist"):
+                dcom = _dcom_all(self.zgrid, self.h_of_z)
+                d["com_dist"] = InterpolatedUnivariateSpline(self.zgrid, dcom)
+                d["ang_dist"] = InterpolatedUnivariateSpline(self.zgrid, dcom / (1 + self.zgrid))
+                return d[name]
         raise AttributeError(name)
 
     # --- host accessors --------------------------------------------------------------------
@@ -250,6 +309,9 @@ class cosmo_functions:
         return self.f_growthrate_zk(z, 0.0001 if k is None else k, grid=False)
 
     def growth(self, z, k=None):
+        lowk = self.__dict__.get("_growth_lowk")
+        if k is None and lowk is not None:  # D(z, 1e-4) below the first tabulated k: the spline along z of that column
+            return lowk(z)
         return self.D_growth_zk(z, 0.0001 if k is None else k, grid=False)
 
     def sigma8_of_z(self, z, tracer="matter"):
@@ -267,20 +329,28 @@ class cosmo_functions:
     def SigmaMG(self, z, k):
         return np.array(1)
 
-    def nonwiggle_table(self, z, nonlinear=False, tracer="matter"):
-        """Knots and coefficients of the degree-1 no-wiggle spline at redshift z
-        (Savitzky-Golay smoothing in ln k, cosmology.py:1760-1813)."""
-        key = (float(z), bool(nonlinear), tracer == "clustering")
-        if key not in self._nw_cache:
+    def nonwiggle_samples(self):
+        """(ln k samples, Savitzky-Golay window) of the no-wiggle smoothing (cosmology.py:1767-1779)."""
+        hit = self.__dict__.get("_nw_samples")
+        if hit is None:
             s = self.settings
             h = self.cosmopars["h"]
             lk = np.linspace(np.log(h * s["savgol_internalkmin"]), np.log(h * np.max(self.kgrid)),
                              s["savgol_internalsamples"])
             dlnk = np.mean(lk[1:] - lk[0:-1])
-            n_sg = int(np.round(s["savgol_width"] / np.log(1 + dlnk)))
+            hit = self.__dict__["_nw_samples"] = (lk, int(np.round(s["savgol_width"] / np.log(1 + dlnk))))
+        return hit
+
+    def nonwiggle_table(self, z, nonlinear=False, tracer="matter"):
+        """Knots and coefficients of the degree-1 no-wiggle spline at redshift z
+        (Savitzky-Golay smoothing in ln k, cosmology.py:1760-1813); the third entry is the host spline or None when the
+        table came from the device (`CosmoSet.prepare_spectro`)."""
+        key = (float(z), bool(nonlinear), tracer == "clustering")
+        if key not in self._nw_cache:
+            lk, n_sg = self.nonwiggle_samples()
             lp = InterpolatedUnivariateSpline(
                 lk, np.log(self.matpow(z, np.exp(lk), nonlinear=nonlinear, tracer=tracer).flatten()), k=1)
-            sg = savgol_filter(lp(lk), n_sg, s["savgol_polyorder"])
+            sg = savgol_filter(lp(lk), n_sg, self.settings["savgol_polyorder"])
             spl = InterpolatedUnivariateSpline(np.exp(lk), np.exp(sg), k=1)
             t, c, _ = spl._eval_args
             n = len(t) - 2
@@ -288,7 +358,11 @@ class cosmo_functions:
         return self._nw_cache[key]
 
     def nonwiggle_pow(self, z, k, nonlinear=False, tracer="matter"):
-        return self.nonwiggle_table(z, nonlinear, tracer)[2](k)
+        kk, vv, spl = self.nonwiggle_table(z, nonlinear, tracer)
+        if spl is None:
+            spl = InterpolatedUnivariateSpline(kk, vv, k=1)
+            self._nw_cache[(float(z), bool(nonlinear), tracer == "clustering")] = (kk, vv, spl)
+        return spl(k)
 
     # --- device export -----------------------------------------------------------------------
     def bank_row(self, slots=None):
@@ -322,6 +396,7 @@ def clear_caches():
     """Forget parsed tables and fitted cosmologies (bench.py uses this to time cold end-to-end steps)."""
     _TABLE_CACHE.clear()
     _COSMO_CACHE.clear()
+    _BANK_CACHE.clear()
 
 
 def cached_cosmo(cosmopars, config) -> "cosmo_functions":
@@ -379,7 +454,8 @@ class CosmoSet:
         to the fiducial and the device bank released, so host and device memory stay bounded over a long run."""
         if len(self.cosmos) > limit:
             if self._bank is not None:
-                self._bank.close()
+                if not any(hit[2] is self._bank for hit in _BANK_CACHE.values()):
+                    self._bank.close()  # (a fitted bank in the cache is released when it is evicted there)
                 self._bank = None
             self.cosmos = self.cosmos[:1]
             self._by_key = {k: v for k, v in self._by_key.items() if v == 0}
@@ -394,5 +470,115 @@ class CosmoSet:
     def bank(self) -> _lib.Bank:
         if self._bank is None:
             ctx = self.context()
-            self._bank = _lib.Bank.from_rows(ctx, [c.packed_row(ctx, self.slots) for c in self.cosmos])
+            if device_prep(self.config.settings):
+                self._bank = _fitted_bank(ctx, self.cosmos, self.slots)
+            if self._bank is None:
+                self._bank = _lib.Bank.from_rows(ctx, [c.packed_row(ctx, self.slots) for c in self.cosmos])
         return self._bank
+
+    # --- batched preparation on the device ------------------------------------------
+    def prepare(self):
+        """Functions of z of every cosmology of the set that has none yet, in ONE device call (cfp_background_fit):
+        H(z), the comoving-distance integrals, both distances, sigma8(z) and the low-k growth as cubic splines whose
+        coefficients come back to the facades (cosmology.py:36-55, 1447-1506).  A facade that is never prepared fits the
+        same splines on the host on first access."""
+        if not device_prep(self.config.settings):
+            return
+        todo = [c for c in self.cosmos if "h_of_z" not in c.__dict__ and "com_dist" not in c.__dict__]
+        groups: Dict[tuple, list] = {}
+        for c in todo:
+            groups.setdefault((c.zgrid.tobytes(), tuple(sorted(c._tab1d)), bool(c.kgrid[0] >= 1e-4)), []).append(c)
+        for (_, names, lowk), cs in groups.items():
+            zg = cs[0].zgrid
+            if zg.size < 5 or zg.size > 2048:
+                continue
+            extras = [n for n in names if n != "h_of_z"]
+            ex = [[c._tab1d[n] for n in extras] + ([np.asarray(c._tab2d[_lib.TAB_D][0], float)[:, 0]] if lowk else [])
+                  for c in cs]
+            _, coef = _lib.background_fit(self.context(), zg, np.stack([c._tab1d["h_of_z"] for c in cs]), np.array(ex),
+                                          coef=True)
+            t = nak_knots(zg)
+            for i, c in enumerate(cs):
+                d = c.__dict__
+                for j, n in enumerate(["h_of_z", "com_dist", "ang_dist"] + extras):
+                    d[n] = InterpolatedUnivariateSpline._from_tck((t, coef[i, j], 3))
+                if lowk:
+                    d["_growth_lowk"] = InterpolatedUnivariateSpline._from_tck((t, coef[i, 3 + len(extras)], 3))
+
+    def prepare_spectro(self, zs, tracer="matter"):
+        """Velocity moments and no-wiggle spectra of every cosmology of the set at the redshifts zs, two device calls
+        on the fitted bank (cfp_bank_theta_moments, cfp_bank_nowiggle; spectro_obs.py:724-755, cosmology.py:1760-1813)
+        whose results land in the facades' caches."""
+        if not device_prep(self.config.settings):
+            return
+        from .spectro import _K_MOMENTS  # (the fixed 1024-point grid of spectro_obs.py:261-263)
+
+        cb = tracer == "clustering"
+        tab_p, tab_f = (_lib.TAB_PLIN_CB, _lib.TAB_F_CB) if cb else (_lib.TAB_PLIN, _lib.TAB_F)
+        if self.slots is not None and not (tab_p in self.slots and tab_f in self.slots):
+            return
+        zs = [float(z) for z in zs]
+        need_m = [z for z in zs if any(z not in c._moment_cache for c in self.cosmos)]
+        need_w = [z for z in zs if any((z, False, cb) not in c._nw_cache for c in self.cosmos)]
+        if not need_m and not need_w:
+            return
+        bank = self.bank()
+        if need_m:
+            # the velocity moments are those of the MATTER spectrum whatever the tracer (spectro_obs.py:740-747 calls
+            # matpow / f_growthrate without one): with the cdm+baryon tracer they need a second small bank
+            mbank = bank if not cb else _fitted_bank(self.context(), self.cosmos, (_lib.TAB_PLIN, _lib.TAB_F))
+            if mbank is None:
+                return
+            mom = mbank.theta_moments(_lib.TAB_PLIN, _lib.TAB_F, need_m, _K_MOMENTS)
+            for i, c in enumerate(self.cosmos):
+                for j, z in enumerate(need_m):
+                    c._moment_cache.setdefault(z, tuple(mom[i, j]))
+        if need_w:
+            samples = [c.nonwiggle_samples() for c in self.cosmos]
+            nsamp = samples[0][0].size
+            order = self.config.settings["savgol_polyorder"]
+            wins = sorted({n for _, n in samples})
+            if any(lk.size != nsamp for lk, _ in samples) or any(not order < w <= nsamp for w in wins):
+                return  # (scipy raises on such windows: leave the error to the host path)
+            ks = np.exp(np.stack([lk for lk, _ in samples]))
+            out = bank.nowiggle(tab_p, need_w, ks, [wins.index(n) for _, n in samples],
+                                [savgol_operator(w, order) for w in wins])
+            for i, c in enumerate(self.cosmos):
+                for j, z in enumerate(need_w):
+                    c._nw_cache.setdefault((z, False, cb), (ks[i], np.ascontiguousarray(out[i, j]), None))
+
+
+_BANK_CACHE: Dict[tuple, tuple] = {}
+_BANK_CACHE_MAX = 8
+
+
+def _fitted_bank(ctx, cosmos, slots):
+    """Bank of the cosmologies' raw tables, fitted on the device (cfp_bank_fit) and kept resident: a later job on the same
+    cosmologies (every forecast of a fiducial, every batch of a nuisance-only sampler) uploads nothing.  None when
+    the tables do not share the z grid and the table shapes (the per-cosmology host fits handle that)."""
+    slots = tuple(sorted(slots)) if slots is not None else tuple(sorted(cosmos[0]._tab2d))
+    key = (id(ctx), slots, tuple(id(c) for c in cosmos))
+    hit = _BANK_CACHE.get(key)
+    if hit is not None and hit[0] is ctx and all(a is b for a, b in zip(hit[1], cosmos)) and hit[2].handle:
+        _BANK_CACHE[key] = _BANK_CACHE.pop(key)  # most recently used last
+        return hit[2]
+    zg, nk = cosmos[0].zgrid, cosmos[0].kgrid.size
+    if zg.size < 5 or nk < 5:
+        return None
+    tables, scales = [], []
+    for c in cosmos:
+        if c.kgrid.size != nk or not np.array_equal(c.zgrid, zg) or any(s not in c._tab2d for s in slots):
+            return None
+        row, sc = [None] * _lib.NTAB, [1.0] * _lib.NTAB
+        for s in slots:
+            tab, scale = c._tab2d[s]
+            if np.shape(tab) != (zg.size, nk):
+                return None
+            row[s], sc[s] = tab, scale
+        tables.append(row)
+        scales.append(sc)
+    bank = _lib.Bank.fit(ctx, zg, np.stack([c.kgrid for c in cosmos]), tables, scales)
+    _BANK_CACHE[key] = (ctx, list(cosmos), bank)
+    while len(_BANK_CACHE) > _BANK_CACHE_MAX:
+        _BANK_CACHE.pop(next(iter(_BANK_CACHE)))
+    return bank

@@ -466,6 +466,7 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
                 pts, shots = zip(*[_spectro_point(p, fm) for p in param_dicts[i0:i0 + 4096]])
                 cs = pts[0].cosmo_set
                 S, Z = len(pts), len(zs)
+                spectro_mod.prepare_cosmologies(cs, zs, pts[0])
                 scal = np.array([[p.scalar_block(z) for z in zs] for p in pts])
                 used = {int(c) for c in scal[:, :, _lib.SP_COSMO].ravel()}
                 pk, pp = spectro_mod._pnw_arrays(cs, zs, set() if pts[0].linear_switch else used)
@@ -536,6 +537,7 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
             pts, shots = zip(*[_spectro_point(p, fm) for p in sub])
             cs = pts[0].cosmo_set
             S, Z = len(pts), len(zs)
+            spectro_mod.prepare_cosmologies(cs, zs, pts[0])
             scal = np.array([[p.scalar_block(z) for z in zs] for p in pts])
             used = {int(c) for c in scal[:, :, _lib.SP_COSMO].ravel()}
             pk, pp = spectro_mod._pnw_arrays(cs, zs, set() if pts[0].linear_switch else used)

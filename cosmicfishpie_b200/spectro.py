@@ -408,6 +408,14 @@ def _cosmo_set_of(cfg) -> CosmoSet:
 
 
 
+def prepare_cosmologies(cs: CosmoSet, zs, obs: "ComputeGalSpectro"):
+    """Everything the scalar blocks and no-wiggle tables of the set's cosmologies need from the Boltzmann tables, fitted
+    and integrated on the device for all of them at once (CosmoSet.prepare / prepare_spectro, csrc/cfp_prep.cu)."""
+    cs.prepare()
+    if not obs.linear_switch:
+        cs.prepare_spectro(zs, tracer=obs.tracer)
+
+
 def _base_blocks(fid_obs: "ComputeGalSpectro", cs: CosmoSet, c: int, zs) -> np.ndarray:
     """[Z][NSCAL] scalar blocks of cosmology `c` of the set with the configuration's FIDUCIAL nuisance values.
     Everything in them that is not a nuisance value derives from the cached Boltzmann tables (H, D_A, sigma8, the
@@ -455,6 +463,7 @@ def scalar_blocks_from_matrix(fm, fid_obs: "ComputeGalSpectro", zs, names, matri
             cp.update({k: float(v) for k, v in zip(ckeys, uniq[u])})
             idx[u] = cs.add(cp)
         cosmo_of_s = idx[np.asarray(inv).ravel()]
+    prepare_cosmologies(cs, zs, fid_obs)
     cu, cinv = np.unique(cosmo_of_s, return_inverse=True)
     scal = np.stack([_base_blocks(fid_obs, cs, int(c), zs) for c in cu])[np.asarray(cinv).ravel()]  # [B, Z, NSCAL]
     nu = fid_obs.nuisance
@@ -499,6 +508,7 @@ def _evaluate_lattice(points: List[ComputeGalSpectro], zs, kgrid, mugrid, b_i=No
     """ln P_obs [S][Z][Nmu][Nk] of several parameter points (no derivatives); b_i: a number replacing the bias term."""
     cs = points[0].cosmo_set
     S, Z = len(points), len(zs)
+    prepare_cosmologies(cs, zs, points[0])
     scal = np.array([[p.scalar_block(z) for z in zs] for p in points])
     if b_i is not None:
         scal[:, :, _lib.SP_BIAS] = float(b_i)
@@ -521,6 +531,7 @@ def _evaluate_lattice(points: List[ComputeGalSpectro], zs, kgrid, mugrid, b_i=No
 def _evaluate_terms(point: ComputeGalSpectro, z: float, kgrid, mugrid, b_i=None) -> np.ndarray:
     """[5][Nmu][Nk] factors of P_obs of one parameter point at redshift z (cfp_spectro_plan_terms)."""
     cs = point.cosmo_set
+    prepare_cosmologies(cs, [z], point)
     scal = np.array([[point.scalar_block(z)]])
     if b_i is not None:
         scal[:, :, _lib.SP_BIAS] = float(b_i)
@@ -668,7 +679,9 @@ class SpectroJob:
                 self.stw[ip, s] = w
         self.stden, self.ps_bin, self.ps_src = stden, ps_bin, (0 if ps_src is None else ps_src)
         if fiducial_obs.use_bias_funcs:
-            self.scal = np.array([[p.scalar_block(z) for z in self.zmids] for p in self.points])
+            pts = self.points
+            prepare_cosmologies(cs, self.zmids, fiducial_obs)
+            self.scal = np.array([[p.scalar_block(z) for z in self.zmids] for p in pts])
         else:
             # every stencil point as a row of a matrix: one cached block per (cosmology, bin) + the nuisance columns
             from types import SimpleNamespace

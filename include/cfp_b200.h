@@ -392,6 +392,48 @@ int cfp_legendre_chi2(cfp_ctx* ctx, int S, int Nk, int Z, const double* pl_data_
  * (cosmicfishpie/cosmology/cosmology.py:1375-1421).  All rows of `base` must share table shapes and knots. */
 int cfp_bank_combine(cfp_ctx* ctx, const cfp_bank* base, int M, const double* W_h, cfp_bank** out);
 
+/* ---- device-side preparation of the cosmology input ---------------------------------------------
+ * What `external_input.calculate_interpol_results` and the no-wiggle / velocity-moment helpers redo on the host for
+ * every cosmology of a forecast, batched over all cosmologies of a job (csrc/cfp_prep.cu).
+ *
+ * cfp_bank_fit: the bank of cfp_bank_upload, fitted on the device from the RAW tables -- for every cosmology c and
+ * table slot t with tab_h[c * n_tables + t] != NULL (a [Nz][Nk] array; the same slots for every cosmology) the
+ * interpolating bicubic spline RectBivariateSpline(z, k_c, scale * table, kx=3, ky=3) on FITPACK's knots
+ * (cosmicfishpie/cosmology/cosmology.py:1463-1532; scale_h[c][t] is the unit factor of :1438-1444).
+ * z_h[Nz] is shared, k_h[n_cosmo][Nk] per cosmology (the k-units factor depends on h). */
+int cfp_bank_fit(cfp_ctx* ctx, int n_cosmo, int n_tables, int Nz, int Nk, const double* z_h, const double* k_h,
+                 const double* const* tab_h, const double* scale_h, cfp_bank** out);
+
+/* Background functions of every cosmology at the redshifts zq_h[nq]: out_h[n_cosmo][3 + n_extra][nq] =
+ * { H(z), comoving distance, angular-diameter distance, extra_0(z), ... } where H and the extras (sigma8(z) ...,
+ * hub_h[n_cosmo][Nz], extra_h[n_cosmo][n_extra][Nz]) are InterpolatedUnivariateSpline fits of the tables, the
+ * comoving distance to each tabulated redshift is the ntrap-point trapezoid of 1/H on linspace(0, z, ntrap) and the
+ * two distances are splines through those values (cosmology.py:36-55, 1447-1475, 1500-1506, 1618-1680).
+ * coef_h (may be NULL): [n_cosmo][3 + n_extra][Nz] B-spline coefficients of the same functions on the not-a-knot knot
+ * vector of z_h (z_0 x4, z_2 .. z_{Nz-3}, z_{Nz-1} x4), i.e. the `c` of each spline's FITPACK (t, c, 3); nq may be 0. */
+int cfp_background_fit(cfp_ctx* ctx, int n_cosmo, int Nz, const double* z_h, const double* hub_h, int n_extra,
+                       const double* extra_h, int ntrap, int nq, const double* zq_h, double* out_h, double* coef_h);
+
+/* cfp_bank_eval for every cosmology of the bank at once: out_h[n_cosmo][n] (growth(z, k), f_growthrate(z, k),
+ * cosmology.py:1859-1949). */
+int cfp_bank_eval_many(cfp_ctx* ctx, const cfp_bank* bank, int table, size_t n, const double* z_h, const double* k_h,
+                       double* out_h);
+
+/* No-wiggle spectrum of every cosmology at the redshifts zq_h[nzq] (cosmology.py:1760-1813): ln P(z, k) on the samples
+ * k_h[n_cosmo][nsamp], smoothed by a Savitzky-Golay filter given as a linear operator, exponentiated:
+ * out_h[n_cosmo][nzq][nsamp] (the values of the degree-1 spline whose knots are k_h).  Filter f (filt_of_c_h[c] selects one
+ * per cosmology: the window length depends on h) is fdesc_h[f] = {win, off, ne, wc} and, at fblob_h + foff_h[f],
+ * taps[win] | EL[ne][wc] | ER[ne][wc]: row s of the output is sum_u taps[u] x[s + off + u] in the interior, row s < ne
+ * is EL[s] . x[0 .. wc), row nsamp - ne + s is ER[s] . x[nsamp - wc .. nsamp) (scipy's mode="interp" edge fit). */
+int cfp_bank_nowiggle(cfp_ctx* ctx, const cfp_bank* bank, int table, int nzq, const double* zq_h, int nsamp,
+                      const double* k_h, int n_filt, const int32_t* filt_of_c_h, const int32_t* fdesc_h,
+                      const int64_t* foff_h, const double* fblob_h, size_t fblob_len, double* out_h);
+
+/* Velocity moments (1 / 6 pi^2) int P(z, k) f(z, k)^m dk, m = 0, 1, 2, by the trapezoid rule on k_h[nk], of every
+ * cosmology at zq_h[nzq]: out_h[n_cosmo][nzq][3] (LSSsurvey/spectro_obs.py:724-755). */
+int cfp_bank_theta_moments(cfp_ctx* ctx, const cfp_bank* bank, int tab_p, int tab_f, int nzq, const double* zq_h, int nk,
+                           const double* k_h, double* out_h);
+
 /* ---- batched Fisher-matrix post-processing ------------------------------------------------------
  * B symmetric positive-definite matrices of n <= 64 parameters in one launch.
  * cfp_fisher_batch_post: sigma_h[B][n] = coef * sqrt(diag(F^-1))  (fisher_matrix.get_confidence_bounds,

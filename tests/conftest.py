@@ -13,6 +13,17 @@ GOLDEN = os.path.join(REPO, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The CPU suite exercises the host logic (job assembly against fake plans, world-size-2 gloo): without a device the
+    # batched preparation of the cosmology input (csrc/cfp_prep.cu) cannot run, so these tests take the host fits.
+    # On the GPU box the default (device preparation) is what every test goes through.
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        os.environ.setdefault("CFP_HOST_PREP", "1")
 
 
 @pytest.fixture(scope="session")
