@@ -478,8 +478,11 @@ def run_gpu(args):
 
     def close_fm(f):
         job = f.photo_LSS._job if hasattr(f, "photo_LSS") else f._spectro_job
-        job.close()
-        job.cosmo_set.bank().close()
+        job.close()  # (the fitted table bank stays resident on the device: cosmology._BANK_CACHE; clear_caches drops it)
+
+    def bank_h2d(job):
+        b = job.cosmo_set.bank()
+        return getattr(b, "h2d_last", b.nbytes)  # 0 when the job found its bank resident
 
     def api_single(cold):
         if cold:
@@ -489,8 +492,8 @@ def run_gpu(args):
         b = cdist.shard(make_spectro_fm(bank, tmp), 0, 1)
         Fb = b.compute()
         tot = Fa + Fb
-        h2d = (a.photo_LSS._job.plan().h2d_bytes + a.photo_LSS._job.cosmo_set.bank().nbytes
-               + b._spectro_job.plan().h2d_bytes + b._spectro_job.cosmo_set.bank().nbytes)
+        h2d = (a.photo_LSS._job.plan().h2d_bytes + bank_h2d(a.photo_LSS._job)
+               + b._spectro_job.plan().h2d_bytes + bank_h2d(b._spectro_job))
         d2h = 8 * (a.fisher_array.size + b.pk_fisher_per_bin.size)
         close_fm(a)
         close_fm(b)

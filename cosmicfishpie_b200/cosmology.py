@@ -397,6 +397,9 @@ def clear_caches():
     _TABLE_CACHE.clear()
     _COSMO_CACHE.clear()
     _BANK_CACHE.clear()
+    from . import spectro
+
+    spectro._PNW_MEMO.clear()
 
 
 def cached_cosmo(cosmopars, config) -> "cosmo_functions":
@@ -453,12 +456,17 @@ class CosmoSet:
         accumulated (a sampler that varies cosmological parameters adds one per distinct point) the set is cut back
         to the fiducial and the device bank released, so host and device memory stay bounded over a long run."""
         if len(self.cosmos) > limit:
-            if self._bank is not None:
-                if not any(hit[2] is self._bank for hit in _BANK_CACHE.values()):
-                    self._bank.close()  # (a fitted bank in the cache is released when it is evicted there)
-                self._bank = None
+            self.release_bank()
             self.cosmos = self.cosmos[:1]
             self._by_key = {k: v for k, v in self._by_key.items() if v == 0}
+
+    def release_bank(self):
+        """Drop this set's device bank.  A bank of host-fitted rows belongs to the set and is freed; a bank fitted on the
+        device is shared through the resident cache and lives until it is evicted there (or `clear_caches`)."""
+        if self._bank is not None:
+            if not any(hit[2] is self._bank for hit in _BANK_CACHE.values()):
+                self._bank.close()
+            self._bank = None
 
     def context(self) -> _lib.Context:
         """The device context every bank, plan and likelihood helper of this job uses: options["device"]
@@ -561,6 +569,7 @@ def _fitted_bank(ctx, cosmos, slots):
     hit = _BANK_CACHE.get(key)
     if hit is not None and hit[0] is ctx and all(a is b for a, b in zip(hit[1], cosmos)) and hit[2].handle:
         _BANK_CACHE[key] = _BANK_CACHE.pop(key)  # most recently used last
+        hit[2].h2d_last = 0  # resident: this job uploads nothing
         return hit[2]
     zg, nk = cosmos[0].zgrid, cosmos[0].kgrid.size
     if zg.size < 5 or nk < 5:
@@ -578,6 +587,7 @@ def _fitted_bank(ctx, cosmos, slots):
         tables.append(row)
         scales.append(sc)
     bank = _lib.Bank.fit(ctx, zg, np.stack([c.kgrid for c in cosmos]), tables, scales)
+    bank.h2d_last = bank.nbytes
     _BANK_CACHE[key] = (ctx, list(cosmos), bank)
     while len(_BANK_CACHE) > _BANK_CACHE_MAX:
         _BANK_CACHE.pop(next(iter(_BANK_CACHE)))

@@ -42,7 +42,7 @@ class fisher_matrix:
         elif self.fisher_matrix.ndim == 1:
             self.fisher_matrix = self.fisher_matrix.reshape(1, -1)
         m = self.fisher_matrix
-        if not np.allclose(m, m.T, rtol=1e-03, atol=1e-06):
+        if not (np.abs(m - m.T) <= 1e-06 + 1e-03 * np.abs(m.T)).all():  # == not np.allclose(m, m.T, rtol=1e-3, atol=1e-6)
             m = np.tril(m) + np.triu(m, 1)
         zr = np.where(~m.any(axis=1))[0]
         zc = np.where(~m.any(axis=0))[0]
@@ -58,21 +58,39 @@ class fisher_matrix:
             self.param_names_latex = list(self.param_names)
             self.param_fiducial = np.zeros(self.num_params)
         else:
-            self.param_names = copy.deepcopy(list(param_names))
-            self.param_names_latex = copy.deepcopy(list(param_names))
+            self.param_names = list(param_names)  # (names are strings: a new list is a deep copy)
+            self.param_names_latex = list(param_names)
             self.param_fiducial = np.zeros(self.num_params)
         if param_names_latex is not None:
-            self.param_names_latex = copy.deepcopy(list(param_names_latex))
+            self.param_names_latex = list(param_names_latex)
         if fiducial is not None:
-            self.param_fiducial = np.array(copy.deepcopy(fiducial))
+            self.param_fiducial = np.array(fiducial, dtype=float)
         if len(self.param_names) != self.num_params:
             raise ValueError("The input param_names has not " + str(self.num_params) + " elements.")
         self.param_names_dict = {}
         for i, n in enumerate(self.param_names):
             self.param_names_dict[i + 1] = n
             self.param_names_dict[n] = i + 1
-        self.fisher_eigenvalues, self.fisher_eigenvectors = np.linalg.eigh(self.fisher_matrix)
-        self.fisher_matrix_inv = self.inverse_fisher_matrix()
+
+    # eigen-decomposition and inverse (analysis/fisher_matrix.py computes them in the constructor): on first access
+    def _eigen(self):
+        if "_eig" not in self.__dict__:
+            self._eig = np.linalg.eigh(self.fisher_matrix)
+        return self._eig
+
+    @property
+    def fisher_eigenvalues(self):
+        return self._eigen()[0]
+
+    @property
+    def fisher_eigenvectors(self):
+        return self._eigen()[1]
+
+    @property
+    def fisher_matrix_inv(self):
+        if "_inv" not in self.__dict__:
+            self._inv = self.inverse_fisher_matrix()
+        return self._inv
 
     @staticmethod
     def _read_paramnames(path):

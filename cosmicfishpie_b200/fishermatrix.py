@@ -35,6 +35,64 @@ from . import spectro as spectro_mod
 VERSION = "1.3.0"  # the reference release whose results this package reproduces
 
 
+def _write_text(path, text):
+    """One open / write / close on the file descriptor (no buffered text layer: four small files per Fisher matrix)."""
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o666)
+    try:
+        data = text.encode()
+        while data:
+            data = data[os.write(fd, data):]
+    finally:
+        os.close(fd)
+
+
+_ARRAY_STR = {}
+
+
+def _array_str(a):
+    """str(a) of a specification array, remembered by content: the same few bin-edge arrays are printed into every
+    `_specs.dat`."""
+    key = (a.shape, a.dtype.str, a.tobytes())
+    hit = _ARRAY_STR.get(key)
+    if hit is None:
+        if len(_ARRAY_STR) > 256:
+            _ARRAY_STR.clear()
+        hit = _ARRAY_STR[key] = str(a)
+    return hit
+
+
+def _json_default(o):
+    """What the C encoder of `json` cannot serialise by itself."""
+    if isinstance(o, np.ndarray):
+        return o.tolist()
+    if isinstance(o, (np.floating, np.integer, np.bool_)):
+        return o.item()
+    if isinstance(o, range):
+        return list(o)
+    raise TypeError(type(o).__name__)
+
+
+def _jsonable(o):
+    """`o` as the encoder can take it: in-memory table banks are not written, keys become strings.  The common case --
+    dictionaries whose keys are strings all the way down -- passes through untouched (the C encoder walks it)."""
+    def plain(x):
+        if isinstance(x, dict):
+            # (the encoder itself writes an int key as str(key))
+            return all((type(k) is str or type(k) is int) and k != "tables" and plain(v) for k, v in x.items())
+        if isinstance(x, (list, tuple)):
+            return all(plain(v) for v in x)
+        return True
+
+    def convert(x):
+        if isinstance(x, dict):
+            return {str(k): convert(v) for k, v in x.items() if k != "tables"}
+        if isinstance(x, (list, tuple)):
+            return [convert(v) for v in x]
+        return x
+
+    return o if plain(o) else convert(o)
+
+
 class FisherMatrix:
     cf_version = f"CosmicFish_v{VERSION}"
 
@@ -149,9 +207,8 @@ class FisherMatrix:
         if job is not None:
             job.close()
             cs = getattr(job, "cosmo_set", None)
-            if cs is not None and cs._bank is not None:
-                cs._bank.close()
-                cs._bank = None
+            if cs is not None:
+                cs.release_bank()
 
     # --- spectro ------------------------------------------------------------------------------
     def set_pk_settings(self):
@@ -386,27 +443,28 @@ class FisherMatrix:
         # half-written file; the result object of every rank is built from the text it wrote itself (repr round-trip,
         # exactly what re-reading the file gives).
         rank = (self._shard if self._shard is not None else cdist.rank_world())[0]
-        tag = ".tmp%d_%d" % (rank, os.getpid())
+        if cdist.is_distributed():
+            tag = ".tmp%d_%d" % (rank, os.getpid())
 
-        def write_atomic(path, text):
-            with open(path + tag, "w") as f:
-                f.write(text)
-            os.replace(path + tag, path)
+            def write_atomic(path, text):
+                _write_text(path + tag, text)
+                os.replace(path + tag, path)
+        else:  # a single process owns its files: plain writes
+            write_atomic = _write_text
 
-        fm_text = "#" + " ".join(["", *cols]) + "\n" + "".join(
-            "\t".join(repr(float(v)) for v in row) + "\n" for row in np.atleast_2d(np.asarray(fishmat)))
+        arr = np.atleast_2d(np.asarray(fishmat, dtype=float))
+        fm_text = "#" + " ".join(["", *cols]) + "\n" + "".join("\t".join(map(repr, row)) + "\n" for row in arr.tolist())
+        fid6 = ["{:.6f}".format(self.allparams[par]) for par in cols]
+        latex = [str(self.latex_names.get(par, str(par))) for par in cols]
         pn_text = "#\n#\n# This file contains the parameter names for a derived Fisher matrix.\n#\n" + "".join(
-            str(par) + "    " + str(self.latex_names.get(par, str(par))) + "    " + "{:.6f}".format(self.allparams[par]) + "\n"
-            for par in cols)
+            str(par) + "    " + lt + "    " + f6 + "\n" for par, lt, f6 in zip(cols, latex, fid6))
         write_atomic(root + self.settings["fishermatrix_file_extension"], fm_text)
         write_atomic(root + ".paramnames", pn_text)
-        arr = np.atleast_2d(np.asarray(fishmat, dtype=float))
         if arr.any(axis=1).all() and arr.any(axis=0).all():
             # what re-reading the two files gives (repr round-trips exactly, fiducials carry six decimals), without
             # parsing them back
-            out = fm.fisher_matrix(fisher_matrix=arr, param_names=cols,
-                                   param_names_latex=[str(self.latex_names.get(p, str(p))) for p in cols],
-                                   fiducial=[float("{:.6f}".format(self.allparams[p])) for p in cols])
+            out = fm.fisher_matrix(fisher_matrix=arr, param_names=cols, param_names_latex=latex,
+                                   fiducial=[float(f6) for f6 in fid6])
             out.file_name = root + ".txt"
             out.path = os.path.abspath(out.file_name)
             out.name = os.path.splitext(os.path.basename(out.file_name))[0]
@@ -416,39 +474,27 @@ class FisherMatrix:
         if rank != 0 and cdist.is_distributed():
             return out  # the specification files are rank 0's business
         git = self._git_version()
-        with open(root + "_specs.dat", "w") as f:
-            f.write("**Git version commit: %s \n" % git)
-            if totaltime is not None:
-                f.write("**Time needed for computation of Fisher matrix: {:.3f} seconds \n".format(totaltime))
-            f.write("**Observables: %s \n" % obstring)
-            for title, d in (("CosmicFish settings", self.settings), ("Fiducial parameters", self.fiducialcosmopars),
-                             ("Free parameters", self.freeparams), ("Survey specifications", self.specs)):
-                f.write("### %s ###\n" % title)
-                for key, value in sorted(d.items()):
-                    f.write("%s:%s\n" % (key, value))
-
-        def _jsonify(o):
-            if isinstance(o, dict):
-                return {str(k): _jsonify(v) for k, v in o.items() if k != "tables"}
-            if isinstance(o, (list, tuple, range)):
-                return [_jsonify(v) for v in o]
-            if isinstance(o, np.ndarray):
-                return o.tolist()
-            if isinstance(o, (np.floating, np.integer)):
-                return o.item()
-            return o
-
+        lines = ["**Git version commit: %s \n" % git]
+        if totaltime is not None:
+            lines.append("**Time needed for computation of Fisher matrix: {:.3f} seconds \n".format(totaltime))
+        lines.append("**Observables: %s \n" % obstring)
+        for title, d in (("CosmicFish settings", self.settings), ("Fiducial parameters", self.fiducialcosmopars),
+                         ("Free parameters", self.freeparams), ("Survey specifications", self.specs)):
+            lines.append("### %s ###\n" % title)
+            for key, value in sorted(d.items()):
+                lines.append("%s:%s\n" % (key, _array_str(value) if isinstance(value, np.ndarray) else value))
+        _write_text(root + "_specs.dat", "".join(lines))
         try:
             text = json.dumps({"metadata": {"cf_version": self.cf_version, "git_commit": git,
                                             "observables": list(self.observables),
                                             "totaltime_sec": None if totaltime is None else float(totaltime),
                                             "backend": "cosmicfishpie_b200"},
-                               "options": _jsonify(self.settings), "specifications": _jsonify(self.specs),
-                               "fiducialpars": _jsonify(self.fiducialcosmopars),
-                               "freepars": _jsonify(self.freeparams), "allparams": _jsonify(self.allparams)})
+                               "options": _jsonable(self.settings), "specifications": _jsonable(self.specs),
+                               "fiducialpars": _jsonable(self.fiducialcosmopars),
+                               "freepars": _jsonable(self.freeparams), "allparams": _jsonable(self.allparams)},
+                              default=_json_default)
             # (no indent: the C-accelerated encoder only handles the compact form; same content as the reference's file)
-            with open(root + "_specs.json", "w") as jf:  # one write instead of one per token
-                jf.write(text)
+            _write_text(root + "_specs.json", text)
         except Exception:  # best effort, like the reference
             pass
         return out

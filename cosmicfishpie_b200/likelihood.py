@@ -160,7 +160,7 @@ class PhotometricLikelihood(Likelihood, NautilusMixin):
 
     # --- helpers ---------------------------------------------------------------------------------
     def _grid(self):
-        return photo_mod._PhotoGrid(self.cosmo_data)
+        return photo_mod._photo_grid(self.cosmo_data)
 
     def _cells_from_full(self, cl_noisy):
         """[Nl][Nb][Nb] (noise included) -> {"ells", Cell_LL, Cell_GG, Cell_GL} (photo_like.py:28-75)."""

@@ -180,6 +180,34 @@ class PhotoNuisance:
         return InterpolatedUnivariateSpline(z, win, k=1)
 
 
+_GRID_MEMO = {}
+
+
+def _photo_grid(configuration) -> "_PhotoGrid":
+    """The `_PhotoGrid` of a configuration, remembered by everything that enters it (a forecast builds the grid three
+    times; specifications may be edited between calls, so the key is the values, not the object)."""
+    configuration, cfg = _cfg_of(configuration)
+    sp, st = configuration.specs, configuration.settings
+    try:
+        key = (tuple(configuration.obs), tuple(sp["binrange_GCph"]), tuple(sp["binrange_WL"]),
+               sp["lmax_GCph"], sp["lmax_WL"], sp["lmin_GCph"], sp["lmin_WL"], st["accuracy"], st["ell_sampling"],
+               float(sp["z_bins_GCph"][0]), float(sp["z_bins_WL"][0]), float(sp["z_bins_GCph"][-1]),
+               float(sp["z_bins_WL"][-1]), sp["ellipt_error"], np.asarray(sp["ngalbin_WL"], float).tobytes(),
+               np.asarray(sp["ngalbin_GCph"], float).tobytes(), sp["fsky_GCph"], sp["fsky_WL"], float(sp["kmax"]),
+               st["nonlinear"], st["GCph_Tracer"], bool(st["activateMG"]), bool(st["external_activateMG"]))
+        hash(key)
+    except (KeyError, TypeError):
+        return _PhotoGrid(configuration)
+    g = _GRID_MEMO.get(key)
+    if g is None:
+        if len(_GRID_MEMO) >= 32:
+            _GRID_MEMO.clear()
+        g = _GRID_MEMO[key] = _PhotoGrid(configuration)
+        for a in (g.ell, g.z, g.kind, g.lmin, g.lmax, g.noise, g.sqrtfsky):
+            a.setflags(write=False)
+    return g
+
+
 class _PhotoGrid:
     """ell / z sampling and tomographic row layout shared by every stencil point (photo_obs.py:287-318)."""
 
@@ -249,7 +277,7 @@ class PhotoJob:
     def __init__(self, configuration, points: List[dict], stw, stden, cosmo_set: Optional[CosmoSet] = None):
         configuration, cfg = _cfg_of(configuration)
         self.configuration, self.cfg = configuration, cfg
-        g = self.grid = _PhotoGrid(configuration)
+        g = self.grid = _photo_grid(configuration)
         cs = self.cosmo_set = cosmo_set if cosmo_set is not None else _cosmo_set_of(cfg)
         nuis = PhotoNuisance(configuration)
         fid_photo = cfg.photoparams
@@ -318,7 +346,7 @@ class PhotoJob:
         configuration, cfg = _cfg_of(configuration)
         self = cls.__new__(cls)
         self.configuration, self.cfg = configuration, cfg
-        g = self.grid = _PhotoGrid(configuration)
+        g = self.grid = _photo_grid(configuration)
         cs = self.cosmo_set = cosmo_set if cosmo_set is not None else _cosmo_set_of(cfg)
         nuis = PhotoNuisance(configuration)
         matrix = np.atleast_2d(np.asarray(matrix, dtype=float))
@@ -471,7 +499,7 @@ class ComputeCls:
         self.cosmopars, self.photopars, self.IApars, self.biaspars = cosmopars, photopars, IApars, biaspars
         self.cosmo_set = _cosmo_set_of(cfg)
         self.cosmo = self.cosmo_set.cosmos[self.cosmo_set.add(cosmopars)] if fiducial_cosmo is None else fiducial_cosmo
-        g = self.grid = _PhotoGrid(configuration)
+        g = self.grid = _photo_grid(configuration)
         self.observables, self.binrange = g.observables, g.binrange
         self.binrange_WL, self.binrange_GCph = g.binrange["WL"], g.binrange["GCph"]
         configuration.specs["ellmax"], configuration.specs["ellmin"] = g.ellmax, g.ellmin
@@ -555,7 +583,7 @@ class PhotoCov:
         self.cosmopars, self.photopars, self.IApars, self.biaspars = cosmopars, photopars, IApars, biaspars
         self.allparsfid = {**cosmopars, **IApars, **biaspars, **photopars}
         self.fiducial_Cls = fiducial_Cls
-        g = self.grid = _PhotoGrid(configuration)
+        g = self.grid = _photo_grid(configuration)
         sp = configuration.specs
         self.observables, self.binrange = g.observables, g.binrange
         self.binrange_WL, self.binrange_GCph = sp["binrange_WL"], sp["binrange_GCph"]

@@ -9,11 +9,26 @@ from __future__ import annotations
 import numpy as np
 
 
+_SIMPSON_MEMO = {}
+
+
 def simpson_weights(x) -> np.ndarray:
     """Weights of composite Simpson on the sample points `x` as scipy >= 1.11 computes it:
     per-pair rule with the actual (possibly unequal) spacings, and for an even number of samples
-    Cartwright's correction on the last interval."""
-    x = np.asarray(x, dtype=np.float64)
+    Cartwright's correction on the last interval.  Remembered per grid (every forecast of a lattice asks again);
+    the result is read-only."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    key = x.tobytes()
+    hit = _SIMPSON_MEMO.get(key)
+    if hit is None:
+        if len(_SIMPSON_MEMO) >= 32:
+            _SIMPSON_MEMO.clear()
+        hit = _SIMPSON_MEMO[key] = _simpson_weights(x)
+        hit.setflags(write=False)
+    return hit
+
+
+def _simpson_weights(x) -> np.ndarray:
     n = x.size
     w = np.zeros(n)
     if n == 1:

@@ -489,18 +489,33 @@ def scalar_blocks_from_matrix(fm, fid_obs: "ComputeGalSpectro", zs, names, matri
     return scal, shot, cosmo_of_s
 
 
+_PNW_MEMO = {}
+
+
 def _pnw_arrays(cosmo_set: CosmoSet, zs, used):
-    """No-wiggle knots/values [NC][nnw], [NC][Z][nnw]; rows of unused cosmologies are left as ones."""
+    """No-wiggle knots/values [NC][nnw], [NC][Z][nnw]; rows of unused cosmologies are left as ones.  Remembered per
+    (cosmologies, redshifts): every forecast of a fiducial asks for the same arrays (read-only)."""
+    tracer = cosmo_set.config.settings["GCsp_Tracer"]
     nnw = cosmo_set.config.settings["savgol_internalsamples"]
-    NC, Z = len(cosmo_set), len(zs)
+    cosmos = list(cosmo_set.cosmos)
+    key = (tuple(id(c) for c in cosmos), tuple(float(z) for z in zs), tuple(sorted(used)), tracer, nnw)
+    hit = _PNW_MEMO.get(key)
+    if hit is not None and all(a is b for a, b in zip(hit[0], cosmos)):
+        return hit[1], hit[2]
+    NC, Z = len(cosmos), len(zs)
     pk = np.ones((NC, nnw))
     pk[:] = np.arange(1, nnw + 1)[None, :]
     pp = np.ones((NC, Z, nnw))
     for c in sorted(used):
         for j, z in enumerate(zs):
-            kk, vv, _ = cosmo_set.cosmos[c].nonwiggle_table(z, tracer=cosmo_set.config.settings["GCsp_Tracer"])
+            kk, vv, _ = cosmos[c].nonwiggle_table(z, tracer=tracer)
             pk[c] = kk
             pp[c, j] = vv
+    pk.setflags(write=False)
+    pp.setflags(write=False)
+    if len(_PNW_MEMO) >= 16:
+        _PNW_MEMO.pop(next(iter(_PNW_MEMO)))
+    _PNW_MEMO[key] = (cosmos, pk, pp)
     return pk, pp
 
 
@@ -595,6 +610,14 @@ class SpectroCov:
         return np.array([self.volume_survey(i) for i in range(len(self.global_z_bin_mids))])
 
     def n_density(self, zi):
+        memo = self.__dict__.setdefault("_n_density_memo", {})
+        key = float(zi)
+        if key in memo:
+            return memo[key]
+        memo[key] = out = self._n_density(zi)
+        return out
+
+    def _n_density(self, zi):
         w = np.where(np.isclose(self.inter_z_bin_mids, zi, rtol=1e-2))[0]
         if len(w) == 0:
             print(f"Warning: zi = {zi} not in global_z_bin_mids")

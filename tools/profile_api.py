@@ -27,12 +27,12 @@ def main():
             a = bench.make_photo_fm(bank, tmp)
             res.append(a.compute())
             a.photo_LSS._job.close()
-            a.photo_LSS._job.cosmo_set.bank().close()
+            a.photo_LSS._job.cosmo_set.release_bank()
         if which in ("spectro", "both"):
             b = bench.make_spectro_fm(bank, tmp)
             res.append(b.compute())
             b._spectro_job.close()
-            b._spectro_job.cosmo_set.bank().close()
+            b._spectro_job.cosmo_set.release_bank()
         return res
 
     step("both")
@@ -49,7 +49,7 @@ def main():
             t2 = time.perf_counter()
             job = fm.photo_LSS._job if which == "photo" else fm._spectro_job
             job.close()
-            job.cosmo_set.bank().close()
+            job.cosmo_set.release_bank()
             t3 = time.perf_counter()
             acc["ctor"] += t1 - t0
             acc["host_prep"] += fm.timings["host_prep_s"]
