@@ -70,40 +70,53 @@ __device__ __forceinline__ double splev_any(const double* t, int n, const double
   return sp;
 }
 
-// Knots and LU factors of the collocation matrix of the abscissae x[0..n): t[n + 4]; fac = L[n] | E[n] | D[n] | {h0, f1,
-// m1, g3}.  Rows 2..n-3 sit on knots (three entries a, b, c on the unknowns i-1, i, i+1); row 1 and row n-2 lie inside
-// the first and last knot interval (four entries).  c_0 and c_{n-1} are the end values themselves.
-__device__ void nak_factor(const double* x, int n, double* t, double* fac) {
-  double *L = fac, *E = fac + n, *D = fac + 2 * n, *misc = fac + 3 * n;
-  for (int i = 0; i < 4; ++i) t[i] = x[0], t[n + i] = x[n - 1];
-  for (int i = 2; i < n - 2; ++i) t[i + 2] = x[i];
-  double h[4];
-  bspl3_any(t, 3, x[1], h);
-  const double h0 = h[0], f1 = h[3];
-  L[0] = L[1] = E[0] = D[0] = 0.0;
-  D[1] = h[1];
-  E[1] = h[2];
-  for (int i = 2; i < n - 2; ++i) {
+// Knots and LU factors of the collocation matrix of the abscissae x[0..n): t[n + 4]; fac = L[n] | E[n] | R[n] | {h0, f1,
+// m1, g3} with R = 1 / pivot.  Rows 2..n-3 sit on knots (three entries a, b, c on the unknowns i-1, i, i+1); row 1 and
+// row n-2 lie inside the first and last knot interval (four entries).  c_0 and c_{n-1} are the end values themselves.
+// Called by all threads of a block: the knots and the basis values of every row are computed in parallel (the divisions
+// of the de Boor recurrence are the expensive part), the elimination itself -- one division per row -- by thread 0.
+// `work` holds 3 n doubles (shared or global); all three arrays may be read after the closing barrier.
+__device__ void nak_factor_block(const double* x, int n, double* t, double* fac, double* work) {
+  double *L = fac, *E = fac + n, *R = fac + 2 * n, *misc = fac + 3 * n;
+  double *ha = work, *hb = work + n, *hc = work + 2 * n;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < n + 4; i += nt) t[i] = i < 4 ? x[0] : (i >= n ? x[n - 1] : x[i - 2]);
+  __syncthreads();
+  for (int i = tid + 2; i < n - 2; i += nt) {
+    double h[4];
     bspl3_any(t, i + 2, x[i], h);
-    const double m = h[0] / D[i - 1];
-    L[i] = m;
-    D[i] = h[1] - m * E[i - 1];
-    E[i] = i == 2 ? h[2] - m * f1 : h[2];
+    ha[i] = h[0], hb[i] = h[1], hc[i] = h[2];
   }
-  bspl3_any(t, n - 1, x[n - 2], h);
-  const double m1 = h[0] / D[n - 4];
-  const double g1 = h[1] - m1 * E[n - 4];
-  const double g2 = n - 4 == 1 ? h[2] - m1 * f1 : h[2];
-  const double m2 = g1 / D[n - 3];
-  L[n - 2] = m2;
-  D[n - 2] = g2 - m2 * E[n - 3];
-  E[n - 2] = E[n - 1] = L[n - 1] = D[n - 1] = 0.0;
-  misc[0] = h0, misc[1] = f1, misc[2] = m1, misc[3] = h[3];
+  __syncthreads();
+  if (tid == 0) {
+    double h[4];
+    bspl3_any(t, 3, x[1], h);
+    const double h0 = h[0], f1 = h[3];
+    L[0] = L[1] = E[0] = R[0] = 0.0;
+    R[1] = 1.0 / h[1];
+    E[1] = h[2];
+    for (int i = 2; i < n - 2; ++i) {
+      const double m = ha[i] * R[i - 1];
+      L[i] = m;
+      R[i] = 1.0 / (hb[i] - m * E[i - 1]);
+      E[i] = i == 2 ? hc[i] - m * f1 : hc[i];
+    }
+    bspl3_any(t, n - 1, x[n - 2], h);
+    const double m1 = h[0] * R[n - 4];
+    const double g1 = h[1] - m1 * E[n - 4];
+    const double g2 = n - 4 == 1 ? h[2] - m1 * f1 : h[2];
+    const double m2 = g1 * R[n - 3];
+    L[n - 2] = m2;
+    R[n - 2] = 1.0 / (g2 - m2 * E[n - 3]);
+    E[n - 2] = E[n - 1] = L[n - 1] = R[n - 1] = 0.0;
+    misc[0] = h0, misc[1] = f1, misc[2] = m1, misc[3] = h[3];
+  }
+  __syncthreads();
 }
 
 // In-place solve of one right-hand side y[i * stride], scaled by `scale` on the way in.
 __device__ __forceinline__ void nak_solve(const double* __restrict__ fac, int n, double* y, size_t stride, double scale) {
-  const double *L = fac, *E = fac + n, *D = fac + 2 * n, *misc = fac + 3 * n;
+  const double *L = fac, *E = fac + n, *R = fac + 2 * n, *misc = fac + 3 * n;
   const double h0 = misc[0], f1 = misc[1], m1 = misc[2], g3 = misc[3];
   const double c0 = y[0] * scale, cl = y[(size_t)(n - 1) * stride] * scale;
   y[0] = c0;
@@ -116,25 +129,26 @@ __device__ __forceinline__ void nak_solve(const double* __restrict__ fac, int n,
     prev2 = prev, prev = r;
   }
   // row n-2: entries on c_{n-4}, c_{n-3}, c_{n-2}, c_{n-1}; prev = r_{n-3}, prev2 = r_{n-4}
-  double cn = (y[(size_t)(n - 2) * stride] * scale - g3 * cl - m1 * prev2 - L[n - 2] * prev) / D[n - 2];
+  double cn = (y[(size_t)(n - 2) * stride] * scale - g3 * cl - m1 * prev2 - L[n - 2] * prev) * R[n - 2];
   y[(size_t)(n - 2) * stride] = cn;
   for (int i = n - 3; i >= 2; --i) {
-    cn = (y[(size_t)i * stride] - E[i] * cn) / D[i];
+    cn = (y[(size_t)i * stride] - E[i] * cn) * R[i];
     y[(size_t)i * stride] = cn;
   }
-  y[stride] = (y[stride] - E[1] * y[2 * stride] - f1 * y[3 * stride]) / D[1];
+  y[stride] = (y[stride] - E[1] * y[2 * stride] - f1 * y[3 * stride]) * R[1];
 }
 
 // ---------------------------------------------------------------------------------- bicubic fit
-// one thread per grid: g < NC the k grid of cosmology g, g == NC the shared z grid
-__global__ void prep_factor_kernel(int NC, int Nz, int Nk, const double* __restrict__ z, const double* __restrict__ k,
-                                   double* tz, double* fz, double* tk, double* fk) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g > NC) return;
+// one block per grid: g < NC the k grid of cosmology g, g == NC the shared z grid; work[(NC + 1)][3 max(Nz, Nk)]
+__global__ void __launch_bounds__(128) prep_factor_kernel(int NC, int Nz, int Nk, const double* __restrict__ z,
+                                                          const double* __restrict__ k, double* tz, double* fz, double* tk,
+                                                          double* fk, double* work) {
+  const int g = blockIdx.x;
+  double* w = work + (size_t)g * 3 * max(Nz, Nk);
   if (g == NC)
-    nak_factor(z, Nz, tz, fz);
+    nak_factor_block(z, Nz, tz, fz, w);
   else
-    nak_factor(k + (size_t)g * Nk, Nk, tk + (size_t)g * (Nk + 4), fk + (size_t)g * (3 * Nk + 4));
+    nak_factor_block(k + (size_t)g * Nk, Nk, tk + (size_t)g * (Nk + 4), fk + (size_t)g * (3 * Nk + 4), w);
 }
 
 // jobs[j] = {offset of the slot's tx in the blob, cosmology}; scale[j]
@@ -157,20 +171,35 @@ __global__ void prep_solve_z_kernel(int njobs, const int64_t* __restrict__ jobs,
   nak_solve(fz, Nz, cc + col, (size_t)Nk, scale[j]);
 }
 
-__global__ void prep_solve_k_kernel(int njobs, const int64_t* __restrict__ jobs, int Nz, int Nk, const double* __restrict__ fk,
-                                    double* __restrict__ blob) {
-  const int j = blockIdx.y;
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= njobs || row >= Nz) return;
-  double* cc = blob + jobs[2 * j] + (Nz + 4) + (Nk + 4);
+// Along k every row of a surface is one right-hand side.  A block stages `rpb` rows in shared memory with coalesced
+// loads (row pitch odd: conflict-free), one thread per row runs the serial elimination there, and the block writes the
+// coefficients back coalesced -- a thread walking its own row in global memory would wait on every element.
+__global__ void __launch_bounds__(256) prep_solve_k_kernel(int njobs, const int64_t* __restrict__ jobs, int Nz, int Nk, int rpb,
+                                                           int pitch, const double* __restrict__ fk, double* __restrict__ blob) {
+  extern __shared__ double tile[];
+  const int j = blockIdx.y, tid = threadIdx.x;
+  const int row0 = blockIdx.x * rpb;
+  if (j >= njobs || row0 >= Nz) return;
+  const int nrows = min(rpb, Nz - row0);
+  double* cc = blob + jobs[2 * j] + (Nz + 4) + (Nk + 4) + (size_t)row0 * Nk;
   const int c = (int)jobs[2 * j + 1];
-  nak_solve(fk + (size_t)c * (3 * Nk + 4), Nk, cc + (size_t)row * Nk, 1, 1.0);
+  for (int idx = tid; idx < nrows * Nk; idx += blockDim.x) {
+    const int r = idx / Nk;
+    tile[r * pitch + (idx - r * Nk)] = cc[idx];
+  }
+  __syncthreads();
+  if (tid < nrows) nak_solve(fk + (size_t)c * (3 * Nk + 4), Nk, tile + (size_t)tid * pitch, 1, 1.0);
+  __syncthreads();
+  for (int idx = tid; idx < nrows * Nk; idx += blockDim.x) {
+    const int r = idx / Nk;
+    cc[idx] = tile[r * pitch + (idx - r * Nk)];
+  }
 }
 
 // ---------------------------------------------------------------------------------- background
-// One block per cosmology.  Shared memory: t[Nz+4] | fac[3Nz+4] | coef[(3 + nx)][Nz] | dcom[Nz].
+// One block per cosmology.  Shared memory: t[Nz+4] | fac[3Nz+4] | coef[(3 + nx)][Nz] | work[3 Nz] | ybuf[warps][ntrap].
 // coef rows: 0 H, 1 comoving, 2 angular, 3.. the extra functions of z (sigma8 ...).
-__global__ void __launch_bounds__(128) prep_background_kernel(int Nz, const double* __restrict__ z, const double* __restrict__ hub,
+__global__ void __launch_bounds__(512) prep_background_kernel(int Nz, const double* __restrict__ z, const double* __restrict__ hub,
                                                               int nx, const double* __restrict__ extra, int ntrap, int nq,
                                                               const double* __restrict__ zq, double* __restrict__ out,
                                                               double* __restrict__ coef_out) {
@@ -178,31 +207,39 @@ __global__ void __launch_bounds__(128) prep_background_kernel(int Nz, const doub
   double* t = sm;
   double* fac = t + (Nz + 4);
   double* coef = fac + (3 * Nz + 4);
-  double* dcom = coef + (size_t)(3 + nx) * Nz;
+  double* work = coef + (size_t)(3 + nx) * Nz;
   const int c = blockIdx.x, tid = threadIdx.x;
   for (int i = tid; i < Nz; i += blockDim.x) {
     coef[i] = hub[(size_t)c * Nz + i];
     for (int e = 0; e < nx; ++e) coef[(size_t)(3 + e) * Nz + i] = extra[((size_t)c * nx + e) * Nz + i];
   }
-  if (tid == 0) nak_factor(z, Nz, t, fac);
   __syncthreads();
+  nak_factor_block(z, Nz, t, fac, work);
   if (tid == 0) nak_solve(fac, Nz, coef, 1, 1.0);
   if (tid >= 1 && tid <= nx) nak_solve(fac, Nz, coef + (size_t)(2 + tid) * Nz, 1, 1.0);
   __syncthreads();
-  // comoving distance to every tabulated redshift: trapezoid of 1/H on numpy.linspace(0, z_i, ntrap)
-  for (int i = tid; i < Nz; i += blockDim.x) {
-    const double zi = z[i];
-    const double step = zi / (double)(ntrap - 1);
-    double acc = 0.0, x0 = 0.0, y0 = 1.0 / splev_any(t, Nz, coef, 0.0);
-    for (int s = 1; s < ntrap; ++s) {
-      const double x1 = s == ntrap - 1 ? zi : (double)s * step;
-      const double y1 = 1.0 / splev_any(t, Nz, coef, x1);
-      acc += (x1 - x0) * (y1 + y0) / 2.0;
-      x0 = x1, y0 = y1;
+  // comoving distance to every tabulated redshift: trapezoid of 1/H on numpy.linspace(0, z_i, ntrap); a warp per
+  // redshift, the integrand samples through shared memory ybuf[warp][ntrap]
+  {
+    const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    double* yb = work + (size_t)3 * Nz + (size_t)warp * ntrap;
+    for (int i = warp; i < Nz; i += nw) {
+      const double zi = z[i];
+      const double step = zi / (double)(ntrap - 1);
+      for (int s = lane; s < ntrap; s += 32) yb[s] = 1.0 / splev_any(t, Nz, coef, s == ntrap - 1 ? zi : (double)s * step);
+      __syncwarp();
+      double acc = 0.0;
+      for (int s = lane + 1; s < ntrap; s += 32) {
+        const double x0 = (double)(s - 1) * step, x1 = s == ntrap - 1 ? zi : (double)s * step;
+        acc += (x1 - x0) * (yb[s] + yb[s - 1]) / 2.0;
+      }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        coef[(size_t)Nz + i] = acc;
+        coef[(size_t)2 * Nz + i] = acc / (1.0 + zi);
+      }
+      __syncwarp();
     }
-    dcom[i] = acc;
-    coef[(size_t)Nz + i] = acc;
-    coef[(size_t)2 * Nz + i] = acc / (1.0 + zi);
   }
   __syncthreads();
   if (tid < 2) nak_solve(fac, Nz, coef + (size_t)(1 + tid) * Nz, 1, 1.0);
@@ -387,6 +424,7 @@ extern "C" int cfp_bank_fit(cfp_ctx* ctx, int n_cosmo, int n_tables, int Nz, int
   {
     Scratch s(ctx);
     double *z_d = nullptr, *k_d = nullptr, *tz = nullptr, *fz = nullptr, *tk = nullptr, *fk = nullptr, *sc_d = nullptr;
+    double* work = nullptr;
     int64_t* jobs_d = nullptr;
     cudaError_t e = cfp_dev_alloc(ctx, (void**)&b->blob_d, total * sizeof(double));
     if (e != cudaSuccess) rc = CFP_ERR_NOMEM;
@@ -397,10 +435,11 @@ extern "C" int cfp_bank_fit(cfp_ctx* ctx, int n_cosmo, int n_tables, int Nz, int
     if (rc == CFP_OK) rc = s.up<double>(nullptr, (size_t)3 * Nz + 4, &fz);
     if (rc == CFP_OK) rc = s.up<double>(nullptr, (size_t)n_cosmo * (Nk + 4), &tk);
     if (rc == CFP_OK) rc = s.up<double>(nullptr, (size_t)n_cosmo * (3 * Nk + 4), &fk);
+    if (rc == CFP_OK) rc = s.up<double>(nullptr, (size_t)(n_cosmo + 1) * 3 * (Nz > Nk ? Nz : Nk), &work);
     if (rc == CFP_OK) rc = s.up(scale.data(), scale.size(), &sc_d);
     if (rc == CFP_OK) rc = s.up(jobs.data(), jobs.size(), &jobs_d);
     if (rc == CFP_OK) {
-      prep_factor_kernel<<<(n_cosmo + 1 + 31) / 32, 32, 0, ctx->stream>>>(n_cosmo, Nz, Nk, z_d, k_d, tz, fz, tk, fk);
+      prep_factor_kernel<<<n_cosmo + 1, 128, 0, ctx->stream>>>(n_cosmo, Nz, Nk, z_d, k_d, tz, fz, tk, fk, work);
       // the raw tables go straight into the coefficient areas they are solved in
       for (int j = 0; j < njobs && e == cudaSuccess; ++j) {
         const int c = (int)jobs[2 * j + 1];
@@ -416,8 +455,21 @@ extern "C" int cfp_bank_fit(cfp_ctx* ctx, int n_cosmo, int n_tables, int Nz, int
       const int nkn = Nz + 4 + Nk + 4;
       prep_knots_kernel<<<dim3((nkn + 127) / 128, njobs), 128, 0, ctx->stream>>>(njobs, jobs_d, Nz, Nk, tz, tk, b->blob_d);
       prep_solve_z_kernel<<<dim3((Nk + 63) / 64, njobs), 64, 0, ctx->stream>>>(njobs, jobs_d, sc_d, Nz, Nk, fz, b->blob_d);
-      prep_solve_k_kernel<<<dim3((Nz + 31) / 32, njobs), 32, 0, ctx->stream>>>(njobs, jobs_d, Nz, Nk, fk, b->blob_d);
+      const int pitch = Nk | 1;
+      int rpb = (int)((size_t)160 * 1024 / ((size_t)pitch * sizeof(double)));
+      rpb = rpb > 8 ? 8 : rpb;  // few rows per block: the row solves are serial, the blocks are what runs in parallel
+      if (rpb < 1) {
+        cfp_set_error("cfp_bank_fit: %d wavenumbers per table exceed the shared-memory tile", Nk);
+        rc = CFP_ERR_INVALID;
+      } else {
+        const size_t smem_k = (size_t)rpb * pitch * sizeof(double);
+        cudaFuncSetAttribute(prep_solve_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k);
+        prep_solve_k_kernel<<<dim3((Nz + rpb - 1) / rpb, njobs), 256, smem_k, ctx->stream>>>(njobs, jobs_d, Nz, Nk, rpb, pitch,
+                                                                                          fk, b->blob_d);
+      }
       ctx->launches += 4;
+    }
+    if (rc == CFP_OK) {
       rc = finish(ctx, "cfp_bank_fit");
     }
   }
@@ -448,9 +500,12 @@ extern "C" int cfp_background_fit(cfp_ctx* ctx, int n_cosmo, int Nz, const doubl
   CFP_TRY(s.up(zq_h, (size_t)nq, &q_d));
   CFP_TRY(s.up<double>(nullptr, (size_t)n_cosmo * nf * nq, &o_d));
   if (coef_h) CFP_TRY(s.up<double>(nullptr, (size_t)n_cosmo * nf * Nz, &c_d));
-  const size_t smem = ((size_t)(Nz + 4) + (3 * Nz + 4) + (size_t)(nf + 1) * Nz) * sizeof(double);
+  const int bg_threads = 512;
+  CFP_REQUIRE(ntrap <= 4096, "at most 4096 trapezoid samples");
+  const size_t smem = ((size_t)(Nz + 4) + (3 * Nz + 4) + (size_t)(nf + 3) * Nz + (size_t)(bg_threads / 32) * ntrap) * sizeof(double);
+  CFP_REQUIRE(smem <= 200 * 1024, "redshift grid too long for the background kernel");
   CFP_CUDA(cudaFuncSetAttribute(prep_background_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  prep_background_kernel<<<n_cosmo, 128, smem, ctx->stream>>>(Nz, z_d, h_d, n_extra, x_d, ntrap, nq, q_d, o_d, c_d);
+  prep_background_kernel<<<n_cosmo, bg_threads, smem, ctx->stream>>>(Nz, z_d, h_d, n_extra, x_d, ntrap, nq, q_d, o_d, c_d);
   ctx->launches++;
   CFP_CUDA(cudaGetLastError());
   if (nq > 0)
