@@ -40,7 +40,7 @@ EXPORTS = [
     "cfp_math_selftest", "cfp_spectro_plan_terms", "cfp_photo_plan_fetch_windows", "cfp_photo_fisher",
     "cfp_fisher_batch_post", "cfp_fisher_batch_add", "cfp_bank_combine", "cfp_photo_plan_create_zmap_shared",
     "cfp_photo_plan_chi2_launch", "cfp_photo_plan_chi2_collect", "cfp_bank_fit", "cfp_background_fit",
-    "cfp_bank_eval_many", "cfp_bank_nowiggle", "cfp_bank_theta_moments",
+    "cfp_bank_eval_many", "cfp_bank_nowiggle", "cfp_bank_theta_moments", "cfp_photo_plan_set_ia_enla",
 ]
 
 
@@ -132,6 +132,7 @@ def load():
     lib.cfp_photo_plan_fisher_d.restype = _vp
     lib.cfp_photo_plan_fetch.argtypes = [_vp, _dp, _dp, _dp]
     lib.cfp_photo_plan_chi2.argtypes = [_vp, _dp, C.c_int, _ip, _ip, _dp, _dp, _vp]
+    lib.cfp_photo_plan_set_ia_enla.argtypes = [_vp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp]
     lib.cfp_bank_fit.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, C.POINTER(_vp), _dp, C.POINTER(_vp)]
     lib.cfp_background_fit.argtypes = [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, _dp, _dp]
     lib.cfp_bank_eval_many.argtypes = [_vp, _vp, C.c_int, C.c_size_t, _dp, _dp, _dp]
@@ -667,13 +668,16 @@ class SpectroPlan:
 
 class PhotoPlan:
     def __init__(self, ctx: Context, bank: Bank, *, cosmo_of_s, ell, z, dz, chi, hub, wlpref, kind, ngal, bias, ia,
-                 lmin, lmax, noise, sqrtfsky, stw, stden, kmax, tab_p=TAB_PNL, zmap=None, win_of_s=None, tab_pg=None):
+                 lmin, lmax, noise, sqrtfsky, stw, stden, kmax, tab_p=TAB_PNL, zmap=None, win_of_s=None, tab_pg=None,
+                 ia_model=None):
+        """`ia`: intrinsic-alignment window [S][Nz] of every point, or None with `ia_model` = dict(zdep, lum, growth[NC][nia],
+        fac[S], eta[S], beta[S], j[Nz], t[Nz]) -- the eNLA window evaluated on the device (cfp_photo_plan_set_ia_enla)."""
         self.ctx, self.bank = ctx, bank
         self.cosmo_of_s = i32(cosmo_of_s)
         self.ell, self.z = f64(ell), f64(z)
         self.chi, self.hub, self.wlpref = f64(chi), f64(hub), f64(wlpref)
         self.kind = i32(kind)
-        self.ngal, self.bias, self.ia = f64(ngal), f64(bias), f64(ia)
+        self.ngal, self.bias, self.ia = f64(ngal), f64(bias), (None if ia is None else f64(ia))
         self.lmin, self.lmax, self.noise, self.sqrtfsky = f64(lmin), f64(lmax), f64(noise), f64(sqrtfsky)
         self.stw, self.stden = f64(stw), f64(stden)
         self.S, self.NC = self.cosmo_of_s.size, self.chi.shape[0]
@@ -690,7 +694,7 @@ class PhotoPlan:
             assert self.win_of_s is None and self.bias.shape == (self.S, Kb)
         else:
             assert self.bias.shape == (self.S, self.Nb, Kb)
-        assert self.ia.shape == (self.S, self.Nz) and self.stw.shape == (self.npar, self.S)
+        assert (self.ia is None or self.ia.shape == (self.S, self.Nz)) and self.stw.shape == (self.npar, self.S)
         self.handle = _vp()
         if self.win_of_s is not None:  # several sets of n(z) windows (photo-z parameters vary between points)
             assert self.win_of_s.shape == (self.S,)
@@ -719,9 +723,22 @@ class PhotoPlan:
                 _p(self.stden), float(kmax), int(tab_p), C.byref(self.handle)), "cfp_photo_plan_create_zmap")
         if tab_pg is not None and int(tab_pg) != int(tab_p):  # clustering rows on another spectrum (cdm+baryons)
             _check(ctx.lib.cfp_photo_plan_set_gc_table(self.handle, int(tab_pg)), "cfp_photo_plan_set_gc_table")
-        self.h2d_bytes = sum(a.nbytes for a in (self.cosmo_of_s, self.ell, self.z, self.chi, self.hub, self.wlpref,
-                                                self.kind, self.ngal, self.bias, self.ia, self.lmin, self.lmax,
-                                                self.noise, self.sqrtfsky, self.stw, self.stden))
+        up = [self.cosmo_of_s, self.ell, self.z, self.chi, self.hub, self.wlpref, self.kind, self.ngal, self.bias,
+              self.lmin, self.lmax, self.noise, self.sqrtfsky, self.stw, self.stden]
+        if self.ia is not None:
+            up.append(self.ia)
+        if ia_model is not None:
+            m = ia_model
+            zdep, lum, growth = f64(m["zdep"]).ravel(), f64(m["lum"]).ravel(), f64(m["growth"])
+            fac, eta, beta = f64(m["fac"]).ravel(), f64(m["eta"]).ravel(), f64(m["beta"]).ravel()
+            jj, tt = i32(m["j"]).ravel(), f64(m["t"]).ravel()
+            nia = zdep.size
+            assert lum.size == nia and growth.shape == (self.NC, nia) and jj.size == self.Nz and tt.size == self.Nz
+            assert fac.size == self.S and eta.size == self.S and beta.size == self.S
+            _check(ctx.lib.cfp_photo_plan_set_ia_enla(self.handle, nia, _p(zdep), _p(lum), _p(growth), _p(fac), _p(eta),
+                                                      _p(beta), _p(jj, _ip), _p(tt)), "cfp_photo_plan_set_ia_enla")
+            up += [zdep, lum, growth, fac, eta, beta, jj, tt]
+        self.h2d_bytes = sum(a.nbytes for a in up)
 
     def set_slice(self, l_begin: int, l_end: int):
         _check(self.ctx.lib.cfp_photo_plan_set_slice(self.handle, int(l_begin), int(l_end)), "cfp_photo_plan_set_slice")

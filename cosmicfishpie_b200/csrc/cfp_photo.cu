@@ -994,7 +994,8 @@ static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int
                                   const double* stden_h, double kmax, int tab_p, int Kb, const int32_t* zmap_h,
                                   int NW, const int32_t* win_of_s_h, cfp_photo_plan** out, bool bias_shared) {
   CFP_REQUIRE(ctx && bank && out, "NULL ctx/bank/out");
-  CFP_REQUIRE(cosmo_of_s_h && ell_h && z_h && chi_h && hub_h && wlpref_h && kind_h && ngal_h && bias_h && ia_h &&
+  // (ia_h may be NULL: no intrinsic-alignment window until cfp_photo_plan_set_ia_enla fills it on the device)
+  CFP_REQUIRE(cosmo_of_s_h && ell_h && z_h && chi_h && hub_h && wlpref_h && kind_h && ngal_h && bias_h &&
                   lmin_h && lmax_h && noise_h && sqrtfsky_h && stw_h && stden_h,
               "NULL input array");
   CFP_REQUIRE(S >= 1 && NC >= 1 && Nl >= 2 && Nz >= 2 && Nb >= 1 && npar >= 1, "bad dimensions");
@@ -1135,6 +1136,61 @@ extern "C" int cfp_photo_plan_destroy(cfp_photo_plan* plan) {
   }
   photo_free(plan);
   return CFP_OK;
+}
+
+// eNLA intrinsic-alignment window of every point on the job's z grid, from the point's (amplitude factor, eta, beta):
+// W_IA(z_j) = fac * ((1 + z_j) / (1 + z_piv))^eta * (L(z_j)^beta / D(z_j)) on the nuisance grid (nuisance.py:190-230),
+// then the degree-1 interpolation to the z samples (the products in the order numpy forms them on the host path).
+__global__ void photo_ia_kernel(int S, int Nz, int nia, const int* __restrict__ cosmo_of_s, const double* __restrict__ zdep,
+                                const double* __restrict__ lum, const double* __restrict__ growth,
+                                const double* __restrict__ fac, const double* __restrict__ eta,
+                                const double* __restrict__ beta, const int* __restrict__ jj, const double* __restrict__ tt,
+                                double* __restrict__ ia) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)S * Nz) return;
+  const int s = (int)(idx / Nz), iz = (int)(idx - (size_t)s * Nz);
+  const int j = jj[iz];
+  const double t = tt[iz];
+  const double* g = growth + (size_t)cosmo_of_s[s] * nia;
+  const double f = fac[s], e = eta[s], b = beta[s];
+  const double w0 = __dmul_rn(__dmul_rn(f, pow(zdep[j], e)), __ddiv_rn(pow(lum[j], b), g[j]));
+  const double w1 = __dmul_rn(__dmul_rn(f, pow(zdep[j + 1], e)), __ddiv_rn(pow(lum[j + 1], b), g[j + 1]));
+  ia[idx] = __dadd_rn(__dmul_rn(w0, 1.0 - t), __dmul_rn(w1, t));
+}
+
+extern "C" int cfp_photo_plan_set_ia_enla(cfp_photo_plan* plan, int nia, const double* zdep_h, const double* lum_h,
+                                          const double* growth_h, const double* fac_h, const double* eta_h,
+                                          const double* beta_h, const int32_t* j_h, const double* t_h) {
+  CFP_REQUIRE(plan != nullptr, "plan is NULL");
+  CFP_REQUIRE(zdep_h && lum_h && growth_h && fac_h && eta_h && beta_h && j_h && t_h, "NULL input array");
+  CFP_REQUIRE(nia >= 2, "the nuisance redshift grid needs two samples");
+  for (int i = 0; i < plan->Nz; ++i) CFP_REQUIRE(j_h[i] >= 0 && j_h[i] <= nia - 2, "interpolation index out of range");
+  cfp_ctx* ctx = plan->ctx;
+  cfp_photo_plan* pl = plan;
+  CFP_CUDA(cudaSetDevice(ctx->device));
+  double *zd = nullptr, *lu = nullptr, *gr = nullptr, *fa = nullptr, *et = nullptr, *be = nullptr, *td = nullptr;
+  int* jd = nullptr;
+#define IA_UP(T, src, cnt, dst)                                   \
+  do {                                                            \
+    int _rc = cfp_upload<T>(ctx, src, cnt, &(dst));               \
+    if (_rc != CFP_OK) return _rc;                                \
+    pl->owned.push_back((void*)(dst));                            \
+  } while (0)
+  IA_UP(double, zdep_h, (size_t)nia, zd);
+  IA_UP(double, lum_h, (size_t)nia, lu);
+  IA_UP(double, growth_h, (size_t)pl->NC * nia, gr);
+  IA_UP(double, fac_h, (size_t)pl->S, fa);
+  IA_UP(double, eta_h, (size_t)pl->S, et);
+  IA_UP(double, beta_h, (size_t)pl->S, be);
+  IA_UP(int, j_h, (size_t)pl->Nz, jd);
+  IA_UP(double, t_h, (size_t)pl->Nz, td);
+#undef IA_UP
+  const size_t tot = (size_t)pl->S * pl->Nz;
+  photo_ia_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(pl->S, pl->Nz, nia, pl->cosmo_of_s_d, zd, lu, gr, fa, et, be,
+                                                                         jd, td, pl->ia_d);
+  ctx->launches++;
+  CFP_CUDA(cudaGetLastError());
+  return CFP_OK;  // (pageable host arrays are staged before cudaMemcpyAsync returns, as in plan creation)
 }
 
 extern "C" int cfp_photo_plan_set_gc_table(cfp_photo_plan* plan, int tab_p_gc) {

@@ -375,6 +375,7 @@ class PhotoJob:
         self.zmap = None  # bias sampled on the z grid, or on fewer samples + a z -> sample map (binned models)
         self.bias = None
         self.ia = np.zeros((B, Nz))
+        self.ia_model = None
         if "WL" in g.observables:
             ia = cfg.IAparams
             if ia["IA_model"] != "eNLA":
@@ -382,17 +383,15 @@ class PhotoJob:
             A, eta, beta = column("AIA", ia["AIA"]), column("etaIA", ia["etaIA"]), column("betaIA", ia["betaIA"])
             piv = nuis.settings["pivot_z_IA"]
             zz = nuis.z
-            Om = np.array([c.scalar("Omegam_of_z", 0.0) for c in cs.cosmos])[self.cosmo_of_s]
-            growth = np.array([c.on_grid("growth", zz).flatten() for c in cs.cosmos])[self.cosmo_of_s]  # [B, 50]
-            fac = -A * (0.0134 * (1 + piv)) * Om
-            z_dep = (1 + zz) / (1 + piv)
-            win = fac[:, None] * z_dep[None, :] ** eta[:, None] * ((nuis._lum_z[None, :] ** beta[:, None]) / growth)
+            Om = np.array([c.scalar("Omegam_of_z", 0.0) for c in cs.cosmos])
+            growth = np.array([c.on_grid("growth", zz).flatten() for c in cs.cosmos])  # [NC, 50]
             j = np.clip(np.searchsorted(zz, g.z, side="right") - 1, 0, len(zz) - 2)
             t = (g.z - zz[j]) / (zz[j + 1] - zz[j])
-            # (np.take keeps the result C-ordered; `win[:, j]` comes back transposed in memory and would be copied again
-            # on upload)
-            self.ia = np.take(win, j, axis=1) * (1.0 - t)[None, :]
-            self.ia += np.take(win, j + 1, axis=1) * t[None, :]
+            # the window itself -- two powers per (point, redshift), B x Nz doubles -- is evaluated on the device from
+            # three numbers per point (cfp_photo_plan_set_ia_enla); `ia_window()` gives the same array on the host
+            self.ia = None
+            self.ia_model = dict(zdep=(1 + zz) / (1 + piv), lum=nuis._lum_z, growth=growth,
+                                 fac=-A * (0.0134 * (1 + piv)) * Om[self.cosmo_of_s], eta=eta, beta=beta, j=j, t=t)
         if "GCph" in g.observables:
             bp = cfg.Photobiasparams
             model = bp["bias_model"]
@@ -431,6 +430,16 @@ class PhotoJob:
         self._plan = None
         return self
 
+    def ia_window(self) -> np.ndarray:
+        """Intrinsic-alignment window [S][Nz] of every point on the z grid, on the host (what the device evaluates from
+        `ia_model`; nuisance.py:190-230)."""
+        if self.ia is not None:
+            return self.ia
+        m = self.ia_model
+        gr = m["growth"][self.cosmo_of_s]
+        win = m["fac"][:, None] * m["zdep"][None, :] ** m["eta"][:, None] * ((m["lum"][None, :] ** m["beta"][:, None]) / gr)
+        return np.take(win, m["j"], axis=1) * (1.0 - m["t"])[None, :] + np.take(win, m["j"] + 1, axis=1) * m["t"][None, :]
+
     def dense_bias(self) -> np.ndarray:
         """Galaxy bias [S][Nb][Nz] on the z grid, whatever compact form the job holds it in (per-bin samples and a
         z -> bin map, per point or per (point, row)); lensing rows carry 1."""
@@ -451,7 +460,8 @@ class PhotoJob:
             self._plan = _lib.PhotoPlan(
                 cs.context(), cs.bank(), cosmo_of_s=self.cosmo_of_s, ell=g.ell, z=g.z, dz=g.dz,
                 chi=self.chi, hub=self.hub, wlpref=self.wlpref, kind=g.kind, ngal=self.ngal, bias=self.bias,
-                ia=self.ia, lmin=g.lmin, lmax=g.lmax, noise=g.noise, sqrtfsky=g.sqrtfsky, stw=self.stw,
+                ia=self.ia, ia_model=getattr(self, "ia_model", None), lmin=g.lmin, lmax=g.lmax, noise=g.noise,
+                sqrtfsky=g.sqrtfsky, stw=self.stw,
                 stden=self.stden, kmax=g.kmax, tab_p=g.tab_p, zmap=getattr(self, "zmap", None),
                 win_of_s=getattr(self, "win_of_s", None), tab_pg=g.tab_pg)
         return self._plan

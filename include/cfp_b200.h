@@ -277,6 +277,16 @@ int cfp_photo_plan_create_ex(cfp_ctx* ctx, const cfp_bank* bank, int S, int NC, 
                              const double* noise_h, const double* sqrtfsky_h, const double* stw_h,
                              const double* stden_h, double kmax, int tab_p, cfp_photo_plan** out);
 
+/* Intrinsic-alignment windows of all points computed on the device (the eNLA model, cosmicfishpie/LSSsurvey/
+ * nuisance.py:190-230): point s has W_IA(z_j) = fac_h[s] * zdep_h[j]^eta_h[s] * (lum_h[j]^beta_h[s] / growth_h[c_s][j])
+ * on the nuisance grid of nia redshifts, zdep = (1 + z) / (1 + pivot_z_IA), fac = -A_IA C_IA Omega_m(0); sample iz of
+ * the plan's z grid takes (1 - t_h[iz]) W_IA(z_j) + t_h[iz] W_IA(z_{j+1}) with j = j_h[iz] (the reference's degree-1
+ * spline).  Replaces the `ia_h` array of plan creation (which may then be NULL): a likelihood batch uploads three
+ * numbers per point instead of Nz.  Call before the plan runs. */
+int cfp_photo_plan_set_ia_enla(cfp_photo_plan* plan, int nia, const double* zdep_h, const double* lum_h,
+                               const double* growth_h, const double* fac_h, const double* eta_h, const double* beta_h,
+                               const int32_t* j_h, const double* t_h);
+
 /* Table slot of the spectrum the CLUSTERING rows use when it differs from tab_p (GCph_Tracer = "clustering":
  * photo_obs.py:483-507 evaluates sqrt(P) of GCph on the cdm+baryon spectrum, lensing rows stay on total matter).
  * Call between create and run.                                                                                    */
