@@ -315,7 +315,7 @@ def run_gpu(args):
     s2ptr = stream2.cuda_stream
     two_streams = os.environ.get("CFP_BENCH_ONE_STREAM", "0") != "1"
 
-    def step(sharded=False):
+    def step_kernels(sharded=False):
         # The two probes of a forecast are independent: the photometric plan runs on a second stream, forked from and
         # joined to the launch stream (whose events time the step), so that its small launch-bound kernels overlap the
         # start and the tail of the lattice kernel instead of preceding it.
@@ -331,9 +331,42 @@ def run_gpu(args):
             with torch.cuda.stream(stream):
                 fused[:nph].copy_(Fph.view(-1))
                 fused[nph:].copy_(Fsp.view(-1))
+
+    def reduce_step(sharded):
+        if sharded and world > 1:
+            with torch.cuda.stream(stream):
                 torch.distributed.all_reduce(fused)
 
-    def timed_loop(sharded):
+    def step(sharded=False):
+        step_kernels(sharded)
+        reduce_step(sharded)
+
+    use_graph = os.environ.get("CFP_BENCH_GRAPH", "1") != "0"
+    graph_state = {}
+
+    def captured(sharded):
+        """The kernels of a step (both streams, and the packing of [F_photo | F_spectro]) as ONE CUDA graph: the nine
+        launches of a forecast are issued from Python through ctypes, and once a forecast is split over 4-8 GPUs the
+        kernels are shorter than the time it takes to launch them.  The NCCL all-reduce of the sharded step stays an
+        eager call behind the replay.  Capture is thread-local (the NCCL watchdog thread queries events meanwhile).
+        None when capture is not possible (then the loop stays eager)."""
+        if not use_graph:
+            return None
+        if sharded not in graph_state:
+            try:
+                torch.cuda.synchronize()
+                n0 = ctx.launches
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+                    step_kernels(sharded)
+                graph_state[sharded] = (g, ctx.launches - n0)
+            except Exception as exc:  # noqa: BLE001 -- report and fall back
+                print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); eager launches", file=sys.stderr)
+                graph_state[sharded] = None
+                torch.cuda.synchronize()
+        return graph_state[sharded]
+
+    def timed_loop(sharded, graph=False):
         """W warm-up steps, then exactly K steps timed with CUDA events on the launch stream (L2 flushed between
         steps, outside the event pairs); returns (ms per step = max over ranks, kernels launched)."""
         if sharded:
@@ -345,6 +378,15 @@ def run_gpu(args):
         for _ in range(max(3, args.warmup)):
             step(sharded)
         torch.cuda.synchronize()
+        cap = captured(sharded) if graph else None
+        if graph and cap is None:
+            return None, 0
+        if cap is not None:
+            with torch.cuda.stream(stream):
+                for _ in range(max(3, args.warmup)):
+                    cap[0].replay()
+                    reduce_step(sharded)
+            torch.cuda.synchronize()
         if world > 1:
             torch.distributed.barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -353,18 +395,28 @@ def run_gpu(args):
             for a, b in ev:
                 flush.zero_()  # L2 flush between timed iterations (outside the event pair)
                 a.record(stream)
-                step(sharded)
+                if cap is not None:
+                    cap[0].replay()
+                    reduce_step(sharded)
+                else:
+                    step(sharded)
                 b.record(stream)
         torch.cuda.synchronize()
         if world > 1:
             torch.distributed.barrier()
-        return wmax(sum(a.elapsed_time(b) for a, b in ev)) / args.steps, ctx.launches - n0
+        launched = cap[1] * args.steps if cap is not None else ctx.launches - n0
+        return wmax(sum(a.elapsed_time(b) for a, b in ev)) / args.steps, launched
 
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     # headline: a batch of independent forecasts, one per GPU per step (weak scaling, no collective)
-    ms_per_step, launches_timed = timed_loop(sharded=False)
+    ms_eager, launches_timed = timed_loop(sharded=False)
+    ms_graph, launches_graph = timed_loop(sharded=False, graph=True)
+    graph_used = ms_graph is not None and ms_graph < ms_eager
+    ms_per_step = ms_graph if graph_used else ms_eager
+    if graph_used:
+        launches_timed = launches_graph
     value = world * 1e3 / ms_per_step
     # what the timed steps computed is the forecast: compare the resident plans' results with the public-API run
     torch.cuda.synchronize()
@@ -376,7 +428,9 @@ def run_gpu(args):
     # one forecast split over the GPUs (lattice cells / multipole bins) + ONE NCCL all-reduce of [F_photo | F_spectro]
     strong = None
     if world > 1:
-        ms_strong, _ = timed_loop(sharded=True)
+        ms_strong_eager, _ = timed_loop(sharded=True)
+        ms_strong_graph, _ = timed_loop(sharded=True, graph=True)
+        ms_strong = min(ms_strong_eager, ms_strong_graph) if ms_strong_graph is not None else ms_strong_eager
         torch.cuda.synchronize()
         red = fused.cpu().numpy()
         chk_ph = float(np.max(np.abs(red[:nph].reshape(pplan.npar, pplan.npar) - fm_ph.fisher_array)) / np.max(np.abs(fm_ph.fisher_array)))
@@ -385,6 +439,7 @@ def run_gpu(args):
         if not max(chk_ph, chk_sp) < 1e-12:
             raise RuntimeError(f"sharded + all-reduced forecast differs from the single-GPU one ({chk_ph:.2e}, {chk_sp:.2e})")
         strong = {"value": 1e3 / ms_strong, "unit": "Fisher/s", "ms_per_step": ms_strong, "scaling": "strong",
+                  "ms_per_step_eager_launches": ms_strong_eager, "ms_per_step_cuda_graph": ms_strong_graph,
                   "allreduced_vs_single_gpu_max_rel_diff": max(chk_ph, chk_sp),
                   "what": "ONE forecast per step split over the ranks (spectro lattice cells, photo multipole bins), "
                           "one fused NCCL all-reduce of [F_photo | F_spectro] inside the timed region; result asserted "
@@ -456,7 +511,8 @@ def run_gpu(args):
         if world > 1:
             torch.distributed.destroy_process_group()
         return ({"profile_run": True, "ms_per_step": ms_per_step, "kernel_ms": k_ms, "prepass_ms": w_ms,
-                 "photo_kernel_ms": photo_ms, "roofline": roof} if rank == 0 else None)
+                 "photo_kernel_ms": photo_ms, "roofline": roof, "ms_per_step_eager_launches": ms_eager,
+                 "ms_per_step_cuda_graph": ms_graph, "strong_scaling": strong} if rank == 0 else None)
 
     # ---- the 5PT variant of the GCsp forecast (BASELINE config 4 says 5PT; the reference itself always runs 3PT) ----
     fm5 = cdist.shard(make_spectro_fm(bank, tmp, stencil="5PT"), 0, 1)
@@ -627,8 +683,10 @@ def run_gpu(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2_flush_between_steps": True, "streams_per_step": 2 if two_streams else 1,
+                       "cuda_graph": bool(graph_used),
                        "partition": "a batch of independent forecasts, one per GPU per step, no collective "
                                     "(strong_scaling: one forecast sharded over the GPUs + one fused NCCL all-reduce)"},
+            "ms_per_step_eager_launches": ms_eager, "ms_per_step_cuda_graph": ms_graph,
             "strong_scaling_value": None if strong is None else strong["value"],
             "strong_scaling": strong,
             "clocks": clk,
