@@ -1141,6 +1141,7 @@ extern "C" int cfp_photo_plan_destroy(cfp_photo_plan* plan) {
 // eNLA intrinsic-alignment window of every point on the job's z grid, from the point's (amplitude factor, eta, beta):
 // W_IA(z_j) = fac * ((1 + z_j) / (1 + z_piv))^eta * (L(z_j)^beta / D(z_j)) on the nuisance grid (nuisance.py:190-230),
 // then the degree-1 interpolation to the z samples (the products in the order numpy forms them on the host path).
+namespace {
 __global__ void photo_ia_kernel(int S, int Nz, int nia, const int* __restrict__ cosmo_of_s, const double* __restrict__ zdep,
                                 const double* __restrict__ lum, const double* __restrict__ growth,
                                 const double* __restrict__ fac, const double* __restrict__ eta,
@@ -1157,6 +1158,7 @@ __global__ void photo_ia_kernel(int S, int Nz, int nia, const int* __restrict__ 
   const double w1 = __dmul_rn(__dmul_rn(f, pow(zdep[j + 1], e)), __ddiv_rn(pow(lum[j + 1], b), g[j + 1]));
   ia[idx] = __dadd_rn(__dmul_rn(w0, 1.0 - t), __dmul_rn(w1, t));
 }
+}  // namespace
 
 extern "C" int cfp_photo_plan_set_ia_enla(cfp_photo_plan* plan, int nia, const double* zdep_h, const double* lum_h,
                                           const double* growth_h, const double* fac_h, const double* eta_h,
