@@ -120,32 +120,25 @@ class NautilusMixin:
 
 
 # ------------------------------------------------------------------------------------- photometric
-def ell_subset(ells, limit):
-    """Multipole cut with the cut value inserted (photo_like.py:189-204) -> (n, ells[:n], deltas[:n])."""
-    working = np.array(ells, copy=True)
-    if limit is not None:
-        idx = int(np.searchsorted(working, limit))
-        working = np.insert(working, idx, limit)
-    else:
-        idx = len(working)
-    deltas = np.diff(working)
-    if deltas.size < idx:
-        deltas = np.concatenate([deltas, [deltas[-1] if deltas.size else 1.0]])
-    else:
-        deltas = deltas[:idx]
-    return idx, working[:idx], deltas
-
-
 def quadrature_weights(ells, limit):
-    """w[l] such that sum_l w[l] q[l] == the reference's (2l+1)-weighted trapezoid-like sum (photo_like.py:90-96)."""
-    n, e, d = ell_subset(ells, limit)
-    w = np.zeros(len(ells))
+    """w[l] such that sum_l w[l] q[l] is the reference's sum over multipoles of one chi^2 block (photo_like.py:90-96
+    with the cut of :189-204): the multipoles below `limit` weighted by (2 l + 1), integrated with the trapezoid rule
+    on their own spacings plus one closing rectangle whose width runs from the last kept multipole to the cut itself
+    (without a cut: the previous spacing once more)."""
+    ells = np.asarray(ells, dtype=float)
+    w = np.zeros(ells.size)
+    n = ells.size if limit is None else int(np.searchsorted(ells, limit))
     if n == 0:
         return w
-    w[: n - 1] += d[: n - 1] / 2
-    w[1:n] += d[: n - 1] / 2
-    w[n - 1] += d[n - 1]
-    w[:n] *= 2 * e + 1
+    steps = np.diff(ells[:n])
+    if limit is not None:
+        closing = limit - ells[n - 1]
+    else:
+        closing = steps[-1] if steps.size else 1.0
+    w[: n - 1] += steps / 2
+    w[1:n] += steps / 2
+    w[n - 1] += closing
+    w[:n] *= 2 * ells[:n] + 1
     return w
 
 

@@ -19,13 +19,13 @@ SMALL = {"spectro_Pk_k_samples": 257, "spectro_Pk_mu_samples": 9}
 FREE = {"Omegam": 0.01, "h": 0.01}
 
 
-def _oracle_fisher(bank, fm, hook=None):
+def _oracle_fisher(bank, fm, hook=None, **units):
     from cosmicfishpie_b200 import toy_tables as tt
     from oracle.cosmo import Bank
     from oracle.spectro import spectro_fisher
 
     sp = yaml.safe_load(open(os.path.join(SPECDIR, "Euclid-Spectroscopic-ISTF-Pessimistic.yaml")))["specifications"]
-    ob = Bank(bank, tt.FIDUCIAL, tt.COSMO_KEYS)
+    ob = Bank(bank, tt.FIDUCIAL, tt.COSMO_KEYS, **units)
     if hook is not None:
         make = ob.cosmo
 
@@ -104,6 +104,44 @@ def test_growth_rate_on_its_own_wavenumber_grid(tmp_path, monkeypatch):
             c._coarse_f = True
 
     _check(F, _oracle_fisher(bank, fm, hook))
+    cc.clear_caches()
+
+
+@pytest.mark.parametrize("k_units,r_units", [("h/Mpc", "Mpc/h"), ("h/Mpc", "km/s/Mpc"), ("1/Mpc", "km/s/Mpc")])
+def test_tables_in_other_units(tmp_path, k_units, r_units):
+    """Tables tabulated in h/Mpc and (Mpc/h)^3, H in h/Mpc or km/s/Mpc (cosmology.py:1438-1444): the unit factors depend
+    on the h of each cosmology, so the stencil cosmologies of h have their own wavenumber grids (the device fit takes
+    one k grid per cosmology).  Same physics as the 1/Mpc bank, so the Fisher matrix must also stay close to that one."""
+    from cosmicfishpie_b200 import cosmology as cc
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    full = tt.make_bank(eps_values=(0.01,), pars=tuple(FREE))
+    bank = {}
+    for name, t in full.items():
+        h = tt.FIDUCIAL["h"] * (1.01 if name.startswith("h_pl") else 0.99 if name.startswith("h_mn") else 1.0)
+        u = dict(t)
+        if k_units == "h/Mpc":
+            u["k"] = np.asarray(t["k"]) / h
+            for key in ("Pl", "Pnl", "Plcb", "Pnlcb"):
+                if key in t:
+                    u[key] = np.asarray(t[key]) * h**3
+        u["H"] = np.asarray(t["H"]) / h if r_units == "Mpc/h" else np.asarray(t["H"]) * cc.C_KMS
+        bank[name] = u
+
+    def run(tables, ku, ru):
+        ext = {"tables": tables, "directory": "<memory>", "paramnames": list(tt.COSMO_KEYS),
+               "folder_paramnames": list(tt.COSMO_KEYS), "k-units": ku, "r-units": ru, "eps_values": [0.01]}
+        cc.clear_caches()
+        fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars=dict(FREE), options=base_options(tmp_path, **SMALL),
+                          observables=["GCsp"], extfiles=ext)
+        return fm, fm.compute(max_z_bins=2)
+
+    fm, F = run(bank, k_units, r_units)
+    _check(F, _oracle_fisher(bank, fm, k_units=k_units, r_units=r_units))
+    _, F0 = run(full, "1/Mpc", "Mpc")
+    scale = np.sqrt(np.outer(np.diag(F0.fisher_matrix), np.diag(F0.fisher_matrix)))
+    assert np.max(np.abs(F.fisher_matrix - F0.fisher_matrix) / scale) < 1e-6  # (knots moved by an ulp: not identical)
     cc.clear_caches()
 
 
