@@ -594,8 +594,9 @@ class SpectroCov:
         self.global_z_bins = self.inter_z_bins = self.z_bins
 
     def volume_bin(self, zi, zj):
-        d1 = self.pk_obs.fiducialcosmo.angdist(zi)
-        d2 = self.pk_obs.fiducialcosmo.angdist(zj)
+        fid = self.pk_obs.fiducialcosmo  # (memoised per redshift on the facade: every forecast asks for the bin edges)
+        d1 = fid.scalar("angdist", zi) if hasattr(fid, "scalar") else fid.angdist(zi)
+        d2 = fid.scalar("angdist", zj) if hasattr(fid, "scalar") else fid.angdist(zj)
         return (4 * np.pi / 3) * (pow((1 + zj) * d2, 3) - pow((1 + zi) * d1, 3))
 
     def d_volume(self, ibin):
@@ -618,7 +619,9 @@ class SpectroCov:
         return out
 
     def _n_density(self, zi):
-        w = np.where(np.isclose(self.inter_z_bin_mids, zi, rtol=1e-2))[0]
+        # np.isclose(mids, zi, rtol=1e-2) spelled out for a handful of bins: |m - zi| <= atol + rtol |zi|
+        tol = 1e-8 + 1e-2 * abs(float(zi))
+        w = [i for i, m in enumerate(self.inter_z_bin_mids) if abs(float(m) - float(zi)) <= tol]
         if len(w) == 0:
             print(f"Warning: zi = {zi} not in global_z_bin_mids")
             return 0
