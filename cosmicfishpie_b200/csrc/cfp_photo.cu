@@ -15,14 +15,15 @@
 //                         tr(A^-1 B) = |L^-1 L_B|^2                                      (photo_like.py:28-97,180-256)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "cfp_common.cuh"
 
 namespace {
 
-constexpr int CLS_THREADS = 128;
-constexpr int CLS_WARPS = CLS_THREADS / 32;
+constexpr int CLS_WARPS = 8;  // warps per CTA (A/B on B200, CFP_CLS_WARPS: Fisher job 4: 0.086, 8: 0.076, 16: 0.082 ms;
+                              // 4096-point likelihood chunk incl. chi2 4: 7.83, 8: 7.37, 16: 8.34 ms)
 constexpr int MAX_PNB = 8;  // Nb <= 64 tomographic rows
 
 __global__ void photo_sqrtp_kernel(const double* __restrict__ blob, const int64_t* __restrict__ desc, int n_tables,
@@ -186,8 +187,8 @@ struct ClsParams {
   double* cls;           // [S][Nl][Nb][Nb]
 };
 
-template <int NB, bool TWO>  // TWO: the clustering rows use their own sqrt(P) table (GCph_Tracer = 'clustering')
-__global__ void __launch_bounds__(CLS_THREADS) photo_cls_kernel(ClsParams P) {
+template <int NB, bool TWO, int WARPS>  // TWO: the clustering rows use their own sqrt(P) table (GCph_Tracer = 'clustering')
+__global__ void __launch_bounds__(WARPS * 32) photo_cls_kernel(ClsParams P) {
   constexpr int NT = NB * (NB + 1) / 2;
   extern __shared__ double smem[];
   const int rows = NB * 8;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(CLS_THREADS) photo_cls_kernel(ClsParams P) {
   {
     const double* gU = P.U + (size_t)s * rows * P.ldz;
     const double* gV = P.V + (size_t)s * rows * P.ldz;
-    for (int i = tid; i < rows * P.ldz; i += CLS_THREADS) sK[i] = gU[i] + gV[i];
+    for (int i = tid; i < rows * P.ldz; i += blockDim.x) sK[i] = gU[i] + gV[i];
   }
   __syncthreads();
   const int c = P.cosmo_of_s[s];
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(CLS_THREADS) photo_cls_kernel(ClsParams P) {
     const int row = ib * 8 + g;
     gc_row[ib] = TWO && row < P.Nb && P.kind[row] != 0;
   }
-  for (int il = l0 + warp; il < l1; il += CLS_WARPS) {
+  for (int il = l0 + warp; il < l1; il += (int)(blockDim.x >> 5)) {
     const double* Trow = P.T + ((size_t)c * P.Nl + il) * P.Nz;
     const double* Tgrow = P.Tg + ((size_t)c * P.Nl + il) * P.Nz;
     double acc[NT][2];
@@ -1227,18 +1228,22 @@ extern "C" int cfp_photo_plan_set_slice(cfp_photo_plan* plan, int l_begin, int l
   return CFP_OK;
 }
 
-template <int NB>
-static cudaError_t launch_cls(const ClsParams& P, dim3 grid, size_t smem, cudaStream_t st) {
-  if (P.Tg != P.T) {
-    cudaError_t e = cudaFuncSetAttribute(photo_cls_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    photo_cls_kernel<NB, true><<<grid, CLS_THREADS, smem, st>>>(P);
-  } else {
-    cudaError_t e = cudaFuncSetAttribute(photo_cls_kernel<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    photo_cls_kernel<NB, false><<<grid, CLS_THREADS, smem, st>>>(P);
-  }
+template <int NB, bool TWO, int WARPS>
+static cudaError_t launch_cls_w(const ClsParams& P, dim3 grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(photo_cls_kernel<NB, TWO, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  photo_cls_kernel<NB, TWO, WARPS><<<grid, WARPS * 32, smem, st>>>(P);
   return cudaGetLastError();
+}
+
+template <int NB>
+static cudaError_t launch_cls(const ClsParams& P, dim3 grid, size_t smem, cudaStream_t st, int threads) {
+  const bool two = P.Tg != P.T;
+  switch (threads / 32) {
+    case 8: return two ? launch_cls_w<NB, true, 8>(P, grid, smem, st) : launch_cls_w<NB, false, 8>(P, grid, smem, st);
+    case 16: return two ? launch_cls_w<NB, true, 16>(P, grid, smem, st) : launch_cls_w<NB, false, 16>(P, grid, smem, st);
+    default: return two ? launch_cls_w<NB, true, 4>(P, grid, smem, st) : launch_cls_w<NB, false, 4>(P, grid, smem, st);
+  }
 }
 
 static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell);
@@ -1322,8 +1327,20 @@ static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
     // multipoles per CTA: one wave of as many CTAs as fit beside their staged windows (at most 8 per SM)
     const int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, (size_t)220 * 1024 / std::max<size_t>(smem, 1)));
     const int slots = per_sm * ctx->sm_count;
-    int lch = std::max(CLS_WARPS, (nl * pl->S + slots - 1) / slots);
-    lch = (lch + CLS_WARPS - 1) / CLS_WARPS * CLS_WARPS;
+    // warps per CTA: the CTAs of a point share nothing but re-stage its windows (52 KB for 26 rows), so more warps
+    // beside one staged copy beat more CTAs; CFP_CLS_WARPS overrides for A/B timing
+    static const int cls_warps_env = []() {
+      const char* e = getenv("CFP_CLS_WARPS");
+      const int v = e ? atoi(e) : 0;
+      return (v == 4 || v == 8 || v == 16) ? v : 0;
+    }();
+    const int cls_warps = cls_warps_env ? cls_warps_env : CLS_WARPS;
+    int lch = std::max(cls_warps, (nl * pl->S + slots - 1) / slots);
+    lch = (lch + cls_warps - 1) / cls_warps * cls_warps;
+    {
+      const char* e = getenv("CFP_CLS_LCH");  // (A/B: multipoles per CTA)
+      if (e && atoi(e) > 0) lch = atoi(e);
+    }
     P.lch = lch;
     P.cosmo_of_s = pl->cosmo_of_s_d, P.U = pl->U_d, P.V = pl->V_d, P.T = pl->T_d, P.wz = pl->wz_d;
     P.Tg = pl->tab_pg != pl->tab_p ? pl->Tg_d : pl->T_d, P.kind = pl->kind_d;
@@ -1333,14 +1350,14 @@ static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
     cudaError_t e = cudaSuccess;
     if (nl > 0) {
       switch (pl->nb) {
-        case 1: e = launch_cls<1>(P, grid, smem, st); break;
-        case 2: e = launch_cls<2>(P, grid, smem, st); break;
-        case 3: e = launch_cls<3>(P, grid, smem, st); break;
-        case 4: e = launch_cls<4>(P, grid, smem, st); break;
-        case 5: e = launch_cls<5>(P, grid, smem, st); break;
-        case 6: e = launch_cls<6>(P, grid, smem, st); break;
-        case 7: e = launch_cls<7>(P, grid, smem, st); break;
-        default: e = launch_cls<8>(P, grid, smem, st); break;
+        case 1: e = launch_cls<1>(P, grid, smem, st, cls_warps * 32); break;
+        case 2: e = launch_cls<2>(P, grid, smem, st, cls_warps * 32); break;
+        case 3: e = launch_cls<3>(P, grid, smem, st, cls_warps * 32); break;
+        case 4: e = launch_cls<4>(P, grid, smem, st, cls_warps * 32); break;
+        case 5: e = launch_cls<5>(P, grid, smem, st, cls_warps * 32); break;
+        case 6: e = launch_cls<6>(P, grid, smem, st, cls_warps * 32); break;
+        case 7: e = launch_cls<7>(P, grid, smem, st, cls_warps * 32); break;
+        default: e = launch_cls<8>(P, grid, smem, st, cls_warps * 32); break;
       }
       ctx->launches++;
     }
