@@ -35,7 +35,7 @@ EXPORTS = [
     "cfp_photo_plan_chi2", "cfp_spectro_plan_chi2", "cfp_cells_chi2", "cfp_wedge_chi2",
     "cfp_legendre_project", "cfp_legendre_covariance", "cfp_legendre_chi2",
     "cfp_bank_upload_rows", "cfp_host_alloc", "cfp_host_free", "cfp_spectro_plan_chi2_dev", "cfp_dev_upload",
-    "cfp_dev_release", "cfp_photo_plan_create_zmap", "cfp_ctx_aux_stream", "cfp_photo_plan_create_ex",
+    "cfp_dev_release", "cfp_photo_plan_create_zmap", "cfp_ctx_aux_stream", "cfp_ctx_aux_stream2", "cfp_photo_plan_create_ex",
     "cfp_photo_plan_set_gc_table", "cfp_spectro_plan_chi2_legendre", "cfp_spectro_plan_kernel_ms_part",
     "cfp_math_selftest", "cfp_spectro_plan_terms", "cfp_photo_plan_fetch_windows", "cfp_photo_fisher",
     "cfp_fisher_batch_post", "cfp_fisher_batch_add", "cfp_bank_combine", "cfp_photo_plan_create_zmap_shared",
@@ -75,6 +75,8 @@ def load():
     lib.cfp_ctx_sync.argtypes = [_vp]
     lib.cfp_ctx_aux_stream.argtypes = [_vp]
     lib.cfp_ctx_aux_stream.restype = _vp
+    lib.cfp_ctx_aux_stream2.argtypes = [_vp]
+    lib.cfp_ctx_aux_stream2.restype = _vp
     lib.cfp_ctx_launch_count.argtypes = [_vp]
     lib.cfp_ctx_launch_count.restype = C.c_int64
     lib.cfp_ctx_last_run_ms.argtypes = [_vp]
@@ -191,6 +193,11 @@ class Context:
     def aux_stream(self) -> int:
         """Handle of the context's second stream (pass as `stream=`)."""
         return int(self.lib.cfp_ctx_aux_stream(self.handle) or 0)
+
+    @property
+    def aux_stream2(self) -> int:
+        """Handle of the context's third stream: alternate with `aux_stream` to overlap consecutive batches."""
+        return int(self.lib.cfp_ctx_aux_stream2(self.handle) or 0)
 
     @property
     def launches(self) -> int:

@@ -37,6 +37,7 @@ struct cfp_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t aux = nullptr;  // second stream for callers that overlap a running batch with the next one's uploads
+  cudaStream_t aux2 = nullptr; // and a third: consecutive batches on alternating streams overlap each other's kernels
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::atomic<int64_t> launches{0};  // plans of one context may be driven from two host threads (pipelined batches)
   double last_ms = 0.0;

@@ -33,6 +33,7 @@ extern "C" int cfp_ctx_create(int device, cfp_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   CFP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CFP_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+  CFP_CUDA(cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking));
   CFP_CUDA(cudaEventCreate(&ctx->ev0));
   CFP_CUDA(cudaEventCreate(&ctx->ev1));
   // Arena for every device buffer of banks and plans: a private stream-ordered pool that keeps what it
@@ -61,6 +62,8 @@ extern "C" int cfp_ctx_destroy(cfp_ctx* ctx) {
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   cudaStreamSynchronize(ctx->aux);
   cudaStreamDestroy(ctx->aux);
+  cudaStreamSynchronize(ctx->aux2);
+  cudaStreamDestroy(ctx->aux2);
   cudaStreamDestroy(ctx->stream);
   for (auto& pr : ctx->pin_free) cudaFreeHost(pr.second);
   delete ctx;
@@ -75,6 +78,8 @@ extern "C" int cfp_ctx_sync(cfp_ctx* ctx) {
 }
 
 extern "C" void* cfp_ctx_aux_stream(cfp_ctx* ctx) { return ctx ? (void*)ctx->aux : nullptr; }
+
+extern "C" void* cfp_ctx_aux_stream2(cfp_ctx* ctx) { return ctx ? (void*)ctx->aux2 : nullptr; }
 
 extern "C" int64_t cfp_ctx_launch_count(const cfp_ctx* ctx) { return ctx ? ctx->launches.load() : -1; }
 

@@ -12,6 +12,8 @@ like the reference's `external` input does (cosmology.py:1375-1421); nuisance pa
 """
 from __future__ import annotations
 
+import os
+
 from abc import ABC, abstractmethod
 from copy import deepcopy
 from typing import Any, Dict, Iterable, Optional, Sequence
@@ -270,22 +272,30 @@ class PhotometricLikelihood(Likelihood, NautilusMixin):
             out[:] = job.plan().chi2(off, n, w, data=self._data_full)
             job.close()
             return out
-        # software pipeline over the chunks, no threads: chunk i's kernels are ENQUEUED on the context's second stream
-        # (cfp_photo_plan_chi2_launch returns without waiting) and run while this thread assembles and uploads chunk
-        # i + 1; the result of chunk i is collected afterwards
-        pending = None
-        for a, b in spans:
+        # software pipeline over the chunks, no threads: chunk i's kernels are ENQUEUED on one of the context's two extra
+        # streams in turn (cfp_photo_plan_chi2_launch returns without waiting) and run while this thread assembles and
+        # uploads the next chunks; two chunks are kept in flight, so the C_ell contraction of one (tensor path) overlaps
+        # the factorisations of the other (bound by instruction issue); results are collected two chunks later
+        from collections import deque
+
+        pending = deque()
+        depth = int(os.environ.get("CFP_LIKE_PIPELINE_DEPTH", "2"))
+
+        def collect_oldest():
+            pjob, pa, pb = pending.popleft()
+            out[pa:pb] = pjob.plan().chi2_collect()
+            pjob.close()
+
+        for i, (a, b) in enumerate(spans):
             job = photo_mod.PhotoJob.from_matrix(self.cosmo_theory, names, matrix[a:b])
             plan = job.plan()  # create + H2D, on the context stream
-            plan.chi2_launch(off, n, w, data=self._data_full, stream=plan.ctx.aux_stream)
-            if pending is not None:
-                pjob, pa, pb = pending
-                out[pa:pb] = pjob.plan().chi2_collect()
-                pjob.close()
-            pending = (job, a, b)
-        pjob, pa, pb = pending
-        out[pa:pb] = pjob.plan().chi2_collect()
-        pjob.close()
+            plan.chi2_launch(off, n, w, data=self._data_full,
+                             stream=plan.ctx.aux_stream if i % 2 == 0 else plan.ctx.aux_stream2)
+            pending.append((job, a, b))
+            while len(pending) > depth:
+                collect_oldest()
+        while pending:
+            collect_oldest()
         return out
 
     def chi2_batch(self, param_dicts) -> np.ndarray:

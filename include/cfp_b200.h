@@ -52,6 +52,10 @@ int cfp_ctx_sync(cfp_ctx* ctx);
  * run one batch there (from a worker thread) while it creates the next plan -- whose uploads use the context's own
  * stream -- and so overlap PCIe with compute.  The library itself never launches on it.                          */
 void* cfp_ctx_aux_stream(cfp_ctx* ctx);
+/* One more: consecutive likelihood chunks launched on alternating streams (cfp_photo_plan_chi2_launch) overlap each
+ * other's kernels -- the C_ell contraction of chunk i+1 runs on the tensor path while the factorisations of chunk i
+ * wait on instruction issue. */
+void* cfp_ctx_aux_stream2(cfp_ctx* ctx);
 int64_t cfp_ctx_launch_count(const cfp_ctx* ctx);
 /* device time [ms] of the last *_run call, measured with CUDA events on the launch stream */
 double cfp_ctx_last_run_ms(const cfp_ctx* ctx);
