@@ -19,8 +19,8 @@ Numbers in the JSON line
              of [F_photo | F_spectro] inside the timed region; the reduced result is asserted equal to the
              single-GPU forecast (1e-12) before the number is reported.
   e2e        the same metric through the public API from HOST tables: FisherMatrix(...) per probe, per-job host
-             preparation, pinned H2D of the table bank and job arrays, kernels, D2H of the Fisher matrices and file
-             export inside the timed region -- a batch of forecasts through `FisherMatrix.compute_many` (host
+             preparation, H2D of the job arrays (and of the raw tables when their fitted bank is not yet resident on
+             the device), kernels, D2H of the Fisher matrices and file export inside the timed region -- a batch of forecasts through `FisherMatrix.compute_many` (host
              preparation of forecast i+1 overlaps the kernels of forecast i); `e2e_single` = one blocking
              `compute()` per probe, `e2e_cold` = every cache cleared each step (the reference re-fits its splines
              for every Fisher matrix)
@@ -692,15 +692,17 @@ def run_gpu(args):
             "clocks": clk,
             "e2e": {"value": world / t_api, "unit": "Fisher/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": "public API: a batch of %d forecasts through FisherMatrix.compute_many (FisherMatrix(...) per "
-                            "probe, per-job host prep, H2D of the table bank and job arrays, kernels, D2H, file export; host "
-                            "prep of forecast i+1 overlaps the kernels of forecast i).  The spline facades of the cached "
-                            "Boltzmann tables are reused across steps (north_star: Boltzmann input is computed once on the "
-                            "host and cached); e2e_cold re-fits them every step" % n_many,
+                            "probe, per-job host prep, H2D of the job arrays, kernels, D2H, file export; host prep of forecast "
+                            "i+1 overlaps the kernels of forecast i).  The fitted table bank of the forecast's cosmologies "
+                            "stays resident on the device and the 1-D spline facades of the cached Boltzmann tables are "
+                            "reused across steps (north_star: Boltzmann input is computed once and cached); e2e_cold "
+                            "uploads the raw tables and re-fits everything on the device every step" % n_many,
                     "s_per_step": t_api},
             "e2e_single": {"value": world / t_single, "unit": "Fisher/s", "s_per_step": t_single,
                            "what": "one blocking compute() per probe (the reference's call pattern)"},
             "e2e_cold": {"value": world / t_cold, "unit": "Fisher/s", "s_per_step": t_cold,
-                         "what": "as e2e_single but every cache cleared each step (tables -> FITPACK fits -> bank), i.e. what "
+                         "what": "as e2e_single but every cache cleared each step (raw tables -> H2D -> spline fits, distance integrals, "
+                                 "no-wiggle spectra and velocity moments on the device -> bank), i.e. what "
                                  "the reference redoes for every Fisher matrix"},
             "cabi_e2e": {"value": world / t_cabi, "unit": "Fisher/s", "s_per_step": t_cabi,
                          "what": "cfp_*_plan_create(host buffers) + run + fetch, table bank resident"},
