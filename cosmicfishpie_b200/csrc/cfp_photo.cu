@@ -527,24 +527,25 @@ struct ChiBlocks {
   int child[8];   // the block that is this one's leading sub-block (-1: none)
 };
 
-template <int N, bool DATA>
+template <int N, bool DATA, bool EXACT = false>  // EXACT: n == N, every size test folds at compile time
 __device__ __forceinline__ void chol_trace(const double* __restrict__ A, int lda, const double* __restrict__ noise,
                                            const double* __restrict__ LB, int ldb, int n, int nlead,
                                            double* col /* not __restrict__: the barriers must order its loads */,
                                            int lane, double& tr, double& tr_lead, double& lndet, double& lndet_lead,
                                            double* __restrict__ LBout) {
   double a[N];
+  if (EXACT) n = N;
   const bool in = lane < n;
   const double nz = (noise && in) ? noise[lane] : 0.0;
 #pragma unroll
   for (int i = 0; i < N; ++i)  // row `lane` of the symmetric matrix read as column `lane`: coalesced; beyond n: identity
-    a[i] = (i < n && in) ? A[(size_t)i * lda + lane] + (i == lane ? nz : 0.0) : (i == lane ? 1.0 : 0.0);
+    a[i] = ((EXACT || i < n) && in) ? A[(size_t)i * lda + lane] + (i == lane ? nz : 0.0) : (i == lane ? 1.0 : 0.0);
   double diag = 1.0;
   // ---- pass 1: right-looking Cholesky; column k (scaled) is left in shared memory col[k][0..31], with 1 / L_kk in
   // its diagonal slot
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    if (k < n) {  // (uniform)
+    if (EXACT || k < n) {  // (uniform)
       const double akk = __shfl_sync(0xffffffffu, a[k], k);
       const double rd = chi_rsqrt(akk);
       const double ljk = a[k] * rd;  // lane j > k: L[j][k]; lane k: L[k][k]
@@ -565,6 +566,7 @@ __device__ __forceinline__ void chol_trace(const double* __restrict__ A, int lda
         a[i] = fma(nl, c.x, a[i]);
         a[i + 1] = fma(nl, c.y, a[i + 1]);
       }
+      if ((N & 1) && i < N) a[i] = fma(nl, cb[i], a[i]);  // (odd N: the last element has no partner)
     }
   }
   const double lg = in ? log(diag) : 0.0;
@@ -581,16 +583,16 @@ __device__ __forceinline__ void chol_trace(const double* __restrict__ A, int lda
     if (in) {  // keep the factor: row `lane`, upper triangle zero
 #pragma unroll
       for (int k = 0; k < N; ++k)
-        if (k < n) LBout[(size_t)lane * ldb + k] = (k <= lane) ? a[k] : 0.0;
+        if (EXACT || k < n) LBout[(size_t)lane * ldb + k] = (k <= lane) ? a[k] : 0.0;
     }
   } else {
   // ---- pass 2: M = L^-1 L_B by columns (lane c owns column c of L_B, zero above the diagonal), the columns of L
   // read back from shared memory; tr(A^-1 B) = |M|_F^2 accumulates as the rows are finalised
 #pragma unroll
-  for (int i = 0; i < N; ++i) a[i] = (i < n && in) ? LB[(size_t)i * ldb + lane] : 0.0;
+  for (int i = 0; i < N; ++i) a[i] = ((EXACT || i < n) && in) ? LB[(size_t)i * ldb + lane] : 0.0;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    if (k >= n) break;
+    if (!EXACT && k >= n) break;
     {
       __syncwarp();  // (also keeps the scheduler from hoisting the broadcast loads of every later step up here)
       const double* cb = col + k * 32;
@@ -610,6 +612,7 @@ __device__ __forceinline__ void chol_trace(const double* __restrict__ A, int lda
         a[i] = fma(nx, c.x, a[i]);
         a[i + 1] = fma(nx, c.y, a[i + 1]);
       }
+      if ((N & 1) && i < N) a[i] = fma(nx, cb[i], a[i]);
     }
   }
 #pragma unroll
@@ -632,6 +635,19 @@ __device__ __forceinline__ void chol_dispatch(int n, const double* A, int lda, c
       chol_trace<4 * Q, DATA>(A, lda, noise, LB, ldb, n, nlead, col, lane, tr, tr_lead, lndet, lndet_lead, LBout); \
       return;                                                                                                      \
     }                                                                                                              \
+  }
+  // the Euclid tomography (13 + 13 bins) in exact sizes: straight-line code, no padded pivots
+  if constexpr (4 * NQ >= 26) {
+    if (n == 26) {
+      chol_trace<26, DATA, true>(A, lda, noise, LB, ldb, n, nlead, col, lane, tr, tr_lead, lndet, lndet_lead, LBout);
+      return;
+    }
+  }
+  if constexpr (4 * NQ >= 13) {
+    if (n == 13) {
+      chol_trace<13, DATA, true>(A, lda, noise, LB, ldb, n, nlead, col, lane, tr, tr_lead, lndet, lndet_lead, LBout);
+      return;
+    }
   }
   CHOL_CASE(1)
   CHOL_CASE(2)
