@@ -643,6 +643,46 @@ def run_gpu(args):
     os.environ.pop("CFP_NO_MOMENTS")
     like["spectro_wedges_129x8193_direct_kernels"] = {"batch_per_gpu": Bs, "evals_per_s": world * Bs / dt,
                                                       "what": "moment path switched off: every point and bin is one lattice pass"}
+    # every point its OWN cosmology, continuous in all seven parameters (bank.TaylorEmulator): what a Nautilus chain
+    # over cosmology asks for.  The bank of a batch is combined from the tabulated rows on the device; background
+    # splines, no-wiggle spectra and velocity moments of the batch's cosmologies are fitted there in one call each.
+    try:
+        from cosmicfishpie_b200 import cosmology as ccos_
+        from cosmicfishpie_b200.bank import TaylorEmulator
+
+        emu_ext = dict(ext_dict(bank), emulator=TaylorEmulator(bank, tt.FIDUCIAL, tt.COSMO_KEYS, 0.01))
+        fe_ph = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={p: 0.01 for p in P7},
+                             options=base_options(tmp, survey_name_photo=PHOTO_SPEC, survey_name_spectro=False),
+                             observables=["WL", "GCph"], extfiles=emu_ext)
+        fe_ph.compute()
+        fe_sp = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={p: 0.01 for p in P7},
+                             options=base_options(tmp, survey_name_spectro=SPECTRO_SPEC, survey_name_photo=False,
+                                                  spectro_Pk_k_samples=NK, spectro_Pk_mu_samples=NMU),
+                             observables=["GCsp"], extfiles=emu_ext)
+        fe_sp.compute()
+        rng = np.random.default_rng(99 + rank)
+        for tag, L, fm_e, Be in (("photo_3x2pt_13bins", PhotometricLikelihood(cosmo_data=fe_ph), fe_ph, 2048),
+                                 ("spectro_wedges_129x8193", SpectroLikelihood(cosmoFM_data=fe_sp), fe_sp, 512)):
+            keys_e = list(P7) + [k for k in fm_e.freeparams if k not in P7][:4]
+            fid_e = np.array([fm_e.allparams[k] for k in keys_e])
+            mat_e = np.tile(fid_e, (Be, 1))
+            u = 0.008 * rng.uniform(-1, 1, (Be, 7))
+            mat_e[:, :7] = np.where(fid_e[:7] != 0, fid_e[:7] * (1 + u), u)
+            mat_e[:, 7:] *= 1 + 0.01 * rng.standard_normal((Be, len(keys_e) - 7))
+            L.loglike_batch(mat_e[:64], keys=keys_e)
+            ccos_._BANK_CACHE.clear()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ll = L.loglike_batch(mat_e, keys=keys_e)
+            dt = wmax(time.perf_counter() - t0)
+            like[tag + "_emulated_cosmology_per_point"] = {
+                "batch_per_gpu": Be, "evals_per_s": world * Be / dt, "finite": bool(np.all(np.isfinite(ll))),
+                "what": "every point a distinct cosmology (all 7 parameters vary, second-order Taylor emulator over the "
+                        "table bank); bank rows combined on the device (cfp_bank_combine_rows), 1-D fits / no-wiggle / "
+                        "velocity moments of the batch fitted on the device"}
+            fm_e.release_device()
+    except Exception as exc:  # noqa: BLE001 -- an extra line, never the reason the bench fails
+        like["emulated_cosmology_per_point_error"] = f"{type(exc).__name__}: {exc}"
     # one batch sharded over the ranks through the library (loglike_batch(shard=True)): slices + ONE all-gather
     like["sharded"] = {
         "photo_3x2pt_13bins": like_block(Lp, kp, fm_ph.allparams, 16384 * max(1, world), 0.02, shard=True),

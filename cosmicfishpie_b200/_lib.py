@@ -38,7 +38,7 @@ EXPORTS = [
     "cfp_dev_release", "cfp_photo_plan_create_zmap", "cfp_ctx_aux_stream", "cfp_ctx_aux_stream2", "cfp_photo_plan_create_ex",
     "cfp_photo_plan_set_gc_table", "cfp_spectro_plan_chi2_legendre", "cfp_spectro_plan_kernel_ms_part",
     "cfp_math_selftest", "cfp_spectro_plan_terms", "cfp_photo_plan_fetch_windows", "cfp_photo_fisher",
-    "cfp_fisher_batch_post", "cfp_fisher_batch_add", "cfp_bank_combine", "cfp_photo_plan_create_zmap_shared",
+    "cfp_fisher_batch_post", "cfp_fisher_batch_add", "cfp_bank_combine", "cfp_bank_combine_rows", "cfp_photo_plan_create_zmap_shared",
     "cfp_photo_plan_chi2_launch", "cfp_photo_plan_chi2_collect", "cfp_bank_fit", "cfp_background_fit",
     "cfp_bank_eval_many", "cfp_bank_nowiggle", "cfp_bank_theta_moments", "cfp_photo_plan_set_ia_enla",
 ]
@@ -92,6 +92,7 @@ def load():
     lib.cfp_fisher_batch_post.argtypes = [_vp, C.c_int, C.c_int, _dp, C.c_int, _ip, C.c_double, _dp, _dp, _dp]
     lib.cfp_fisher_batch_add.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
     lib.cfp_bank_combine.argtypes = [_vp, _vp, C.c_int, _dp, C.POINTER(_vp)]
+    lib.cfp_bank_combine_rows.argtypes = [_vp, _vp, C.c_int, _dp, C.POINTER(_vp)]
     lib.cfp_math_selftest.argtypes = [_vp, C.c_int, _dp, C.c_int, _dp]
     lib.cfp_math_selftest.restype = C.c_int
     lib.cfp_photo_plan_kernel_ms.argtypes = [_vp, C.c_int]
@@ -522,18 +523,19 @@ class Bank:
                                                    k.size, _p(k), _p(out)), "cfp_bank_theta_moments")
         return out
 
-    def combined(self, W) -> "Bank":
+    def combined(self, W, keep_base: bool = True) -> "Bank":
         """A new bank: this bank's rows followed by len(W) rows combined on the device, row m = sum_c W[m][c] * row_c
-        (cfp_bank_combine): emulated cosmologies without host fits."""
+        (cfp_bank_combine): emulated cosmologies without host fits.  keep_base=False: the combined rows only
+        (cfp_bank_combine_rows), in the order of W's rows."""
         W = f64(W)
         assert W.ndim == 2 and W.shape[1] == self.n_cosmo
         out = Bank.__new__(Bank)
         out.ctx, out.rows, out.blob, out.desc = self.ctx, [], None, None
-        out.n_cosmo = self.n_cosmo + W.shape[0]
+        out.n_cosmo = (self.n_cosmo if keep_base else 0) + W.shape[0]
         out.nbytes = W.nbytes
         out.handle = _vp()
-        _check(self.ctx.lib.cfp_bank_combine(self.ctx.handle, self.handle, W.shape[0], _p(W), C.byref(out.handle)),
-               "cfp_bank_combine")
+        fn = self.ctx.lib.cfp_bank_combine if keep_base else self.ctx.lib.cfp_bank_combine_rows
+        _check(fn(self.ctx.handle, self.handle, W.shape[0], _p(W), C.byref(out.handle)), "cfp_bank_combine")
         return out
 
     def eval(self, cosmo: int, table: int, z, k) -> np.ndarray:

@@ -69,6 +69,36 @@ def load_bank(path: str, mmap: bool = True):
     return tables, header.get("meta", {})
 
 
+class LazyTables:
+    """Dictionary-like view of an emulated cosmology's tables: `t[name]` forms the weighted sum on first access."""
+
+    def __init__(self, emulator: "TaylorEmulator", weights: Dict[str, float]):
+        self.emulator, self.weights, self._done = emulator, weights, {}
+
+    def __contains__(self, name):
+        return name in self.emulator.tables[self.emulator.fiducial_folder]
+
+    def keys(self):
+        return self.emulator.tables[self.emulator.fiducial_folder].keys()
+
+    def __getitem__(self, name):
+        if name not in self._done:
+            t0 = self.emulator.tables[self.emulator.fiducial_folder]
+            if name in TaylorEmulator.GRID_KEYS:
+                self._done[name] = np.asarray(t0[name])
+            else:
+                if name not in t0:
+                    raise KeyError(name)
+                self._done[name] = self.emulator.combine(name, self.weights)
+        return self._done[name]
+
+    def column0(self, name):
+        """First wavenumber column of a (z, k) table without forming the table."""
+        if name in self._done:
+            return np.asarray(self._done[name])[:, 0]
+        return self.emulator.combine(name, self.weights, column=0)
+
+
 class TaylorEmulator:
     """Second-order (diagonal) Taylor emulator over a fiducial +- eps table bank; see the module docstring."""
 
@@ -124,20 +154,67 @@ class TaylorEmulator:
         d = [x for x in self.offsets(theta).values() if x != 0.0]
         return len(d) == 0 or (len(d) == 1 and abs(abs(d[0]) - 1.0) < 1e-9)
 
-    def tables_at(self, theta: Dict[str, float]) -> Dict[str, np.ndarray]:
-        """The tables of cosmology `theta`: the weighted sum of the bank's folders."""
-        w = self.weights(theta)
-        t0 = self.tables[self.fiducial_folder]
-        out = {g: np.asarray(t0[g]) for g in self.GRID_KEYS}
-        for name in t0:
-            if name in self.GRID_KEYS:
-                continue
+    def combine(self, name: str, weights: Dict[str, float], column: Optional[int] = None) -> np.ndarray:
+        """sum_f weights[f] * tables[f][name] (one table; `column`: only that column of a (z, k) table).  Functions of z
+        and single columns go through a stacked copy [folder][z] made once: a batch of thousands of emulated
+        cosmologies forms three of them per cosmology."""
+        first = np.asarray(self.tables[self.fiducial_folder][name])
+        if first.ndim == 1 or column is not None:
+            key = (name, column)
+            stacks = self.__dict__.setdefault("_stacks", {})
+            st = stacks.get(key)
+            if st is None:
+                st = stacks[key] = np.stack([np.asarray(self.tables[f][name], dtype=float) if column is None
+                                             else np.asarray(self.tables[f][name], dtype=float)[:, column]
+                                             for f in self.folder_order])
+                self.__dict__["_col_of_folder"] = {f: i for i, f in enumerate(self.folder_order)}
+            col = self.__dict__["_col_of_folder"]
             acc = None
-            for folder, x in w.items():
-                term = x * np.asarray(self.tables[folder][name], dtype=float)
+            for folder, x in weights.items():  # (the same order of additions as the loop over full tables)
+                term = x * st[col[folder]]
                 acc = term if acc is None else acc + term
-            out[name] = acc
-        return out
+            return acc
+        acc = None
+        for folder, x in weights.items():
+            term = x * np.asarray(self.tables[folder][name], dtype=float)
+            acc = term if acc is None else acc + term
+        return acc
+
+    def tables_at(self, theta: Dict[str, float], weights: Optional[Dict[str, float]] = None) -> "LazyTables":
+        """The tables of cosmology `theta`: the weighted sum of the bank's folders, each table formed on first access
+        (a facade whose (z, k) surfaces are combined on the device never forms them on the host)."""
+        return LazyTables(self, self.weights(theta) if weights is None else weights)
+
+    @property
+    def folder_order(self):
+        """The bank's folders in a fixed order: the columns of `weight_matrix` / rows of `base_bank`."""
+        return list(self.tables)
+
+    def base_bank(self, ctx, slots, table_of_slot):
+        """Device bank of the tabulated cosmologies (rows in `folder_order`), fitted on the device once per (context,
+        table selection) and kept: the rows every emulated cosmology is combined from (`cfp_bank_combine_rows`).
+        `table_of_slot`: {bank slot: table name}.  None when the folders are not all on one grid."""
+        from . import _lib
+
+        key = (id(ctx), tuple(sorted(slots)))
+        cache = self.__dict__.setdefault("_base_banks", {})
+        hit = cache.get(key)
+        if hit is not None and hit[0] is ctx and hit[1].handle:
+            return hit[1]
+        t0 = self.tables[self.fiducial_folder]
+        z, k = np.asarray(t0["z"], float).ravel(), np.asarray(t0["k"], float).ravel()
+        rows = []
+        for folder in self.folder_order:
+            row = [None] * _lib.NTAB
+            for slot in slots:
+                tab = self.tables[folder].get(table_of_slot[slot])
+                if tab is None or np.shape(tab) != (z.size, k.size):
+                    return None
+                row[slot] = tab
+            rows.append(row)
+        bank = _lib.Bank.fit(ctx, z, np.tile(k, (len(rows), 1)), rows, [[1.0] * _lib.NTAB] * len(rows))
+        cache[key] = (ctx, bank)
+        return bank
 
     def weight_matrix(self, thetas: Iterable[Dict[str, float]], folder_order: Sequence[str]) -> np.ndarray:
         """[M][len(folder_order)] weights for `cfp_bank_combine`, columns in the order of the bank's rows."""

@@ -117,16 +117,17 @@ def _dcom_all(zgrid, hfunc):
 
 
 class _LazySpline:
-    """RectBivariateSpline built on first use (a GCsp job never touches P_nl, a photo job never f)."""
+    """RectBivariateSpline built on first use (a GCsp job never touches P_nl, a photo job never f); the table is read
+    from the cosmology's table mapping at that moment."""
 
-    def __init__(self, zg, kg, table, scale=1.0):
-        self._args = (zg, kg, table, scale)
+    def __init__(self, zg, kg, tables, name, scale=1.0):
+        self._args = (zg, kg, tables, name, scale)
         self._spl = None
 
     def get(self):
         if self._spl is None:
-            zg, kg, tab, scale = self._args
-            tab = np.asarray(tab, float)
+            zg, kg, tables, name, scale = self._args
+            tab = np.asarray(tables[name], float)
             self._spl = RectBivariateSpline(zg, kg, tab if scale == 1.0 else scale * tab, kx=3, ky=3)
             self._args = None
         return self._spl
@@ -217,25 +218,32 @@ class cosmo_functions:
         zg = np.asarray(t["z"], float).flatten()
         kg = kf * np.asarray(t["k"], float).flatten()
         self.zgrid, self.kgrid = zg, kg
-        # raw tables in the bank's units: what the device fits (CosmoSet.prepare / bank) and the host fallbacks fit
+        # raw tables in the bank's units: what the device fits (CosmoSet.prepare / bank) and the host fallbacks fit.
+        # (z, k) surfaces are held by NAME and read from `t` on demand: the tables of an emulated cosmology are formed
+        # lazily (bank.LazyTables), and never on the host when its bank row is combined on the device
+        self._tables = t
         self._tab1d = {"h_of_z": (1 / rf) * np.asarray(t["H"], float).flatten(), "s8_of_z": np.asarray(t["s8"], float).flatten()}
-        self._tab2d = {_lib.TAB_PLIN: (t["Pl"], pkf), _lib.TAB_PNL: (t["Pnl"], pkf), _lib.TAB_F: (t["f"], 1.0),
-                       _lib.TAB_D: (t["D"], 1.0)}
+        self._tab2d = {_lib.TAB_PLIN: ("Pl", pkf), _lib.TAB_PNL: ("Pnl", pkf), _lib.TAB_F: ("f", 1.0), _lib.TAB_D: ("D", 1.0)}
         self._lazy = {
-            "D_growth_zk": _LazySpline(zg, kg, t["D"]),
-            "f_growthrate_zk": _LazySpline(zg, kg, t["f"]),
-            "Pk_l": _LazySpline(zg, kg, t["Pl"], pkf),
-            "Pk_nl": _LazySpline(zg, kg, t["Pnl"], pkf),
+            "D_growth_zk": _LazySpline(zg, kg, t, "D"),
+            "f_growthrate_zk": _LazySpline(zg, kg, t, "f"),
+            "Pk_l": _LazySpline(zg, kg, t, "Pl", pkf),
+            "Pk_nl": _LazySpline(zg, kg, t, "Pnl", pkf),
         }
         if self.cb_files_on:  # cosmology.py:1508-1531
             self._lazy.update({
-                "f_growthrate_cb_zk": _LazySpline(zg, kg, t["fcb"]),
-                "Pk_cb_l": _LazySpline(zg, kg, t["Plcb"], pkf),
-                "Pk_cb_nl": _LazySpline(zg, kg, t["Pnlcb"], pkf),
+                "f_growthrate_cb_zk": _LazySpline(zg, kg, t, "fcb"),
+                "Pk_cb_l": _LazySpline(zg, kg, t, "Plcb", pkf),
+                "Pk_cb_nl": _LazySpline(zg, kg, t, "Pnlcb", pkf),
             })
             self._tab1d["s8_cb_of_z"] = np.asarray(t["s8cb"], float).flatten()
-            self._tab2d.update({_lib.TAB_PLIN_CB: (t["Plcb"], pkf), _lib.TAB_PNL_CB: (t["Pnlcb"], pkf),
-                                _lib.TAB_F_CB: (t["fcb"], 1.0)})
+            self._tab2d.update({_lib.TAB_PLIN_CB: ("Plcb", pkf), _lib.TAB_PNL_CB: ("Pnlcb", pkf), _lib.TAB_F_CB: ("fcb", 1.0)})
+        # D(z, k) at the first tabulated wavenumber: the growth of the intrinsic-alignment window (k = 1e-4 below it)
+        self._growth_col0 = np.ascontiguousarray(t.column0("D") if hasattr(t, "column0") else np.asarray(t["D"], float)[:, 0])
+        # an emulated cosmology whose bank row can be combined on the device from the tabulated rows: its weights
+        self._emu = None
+        if self.folder == "<emulated>" and hasattr(t, "weights") and pkf == 1.0 and kf == 1.0:
+            self._emu = (emulator, t.weights)
         if not device_prep(self.settings):
             for name in ("h_of_z", "com_dist", "ang_dist", "s8_of_z"):  # the reference fits these eagerly
                 getattr(self, name)
@@ -252,6 +260,11 @@ class cosmo_functions:
         lazy = d.get("_lazy")
         if lazy is not None and name in lazy:
             return lazy[name].get()
+        coefs = d.get("_coef1d")
+        if coefs is not None and name in coefs:  # fitted on the device (CosmoSet.prepare): wrap the coefficients
+            t, c = coefs[name]
+            spl = d[name] = InterpolatedUnivariateSpline._from_tck((t, c, 3))
+            return spl
         tab = d.get("_tab1d")
         if tab is not None:
             if name in tab:
@@ -264,6 +277,11 @@ class cosmo_functions:
                 d["ang_dist"] = InterpolatedUnivariateSpline(self.zgrid, dcom / (1 + self.zgrid))
                 return d[name]
         raise AttributeError(name)
+
+    def table2d(self, slot):
+        """(raw (z, k) table, unit factor) of a bank slot."""
+        name, scale = self._tab2d[slot]
+        return self._tables[name], scale
 
     # --- host accessors --------------------------------------------------------------------
     def scalar(self, name, z):
@@ -309,9 +327,8 @@ class cosmo_functions:
         return self.f_growthrate_zk(z, 0.0001 if k is None else k, grid=False)
 
     def growth(self, z, k=None):
-        lowk = self.__dict__.get("_growth_lowk")
-        if k is None and lowk is not None:  # D(z, 1e-4) below the first tabulated k: the spline along z of that column
-            return lowk(z)
+        if k is None and ("_growth_lowk" in self.__dict__ or "_growth_lowk" in self.__dict__.get("_coef1d", ())):
+            return self._growth_lowk(z)  # D(z, 1e-4) below the first tabulated k: the spline along z of that column
         return self.D_growth_zk(z, 0.0001 if k is None else k, grid=False)
 
     def sigma8_of_z(self, z, tracer="matter"):
@@ -324,6 +341,8 @@ class cosmo_functions:
         return self.f_growthrate(z, k, gamma, tracer=tracer) * self.sigma8_of_z(z, tracer=tracer)
 
     def Omegam_of_z(self, z):
+        if np.ndim(z) == 0 and z == 0:  # E(0) = H(0) / H(0) = 1 exactly: no spline call
+            return self.cosmopars["Omegam"] * (1 + z) ** 3 / 1.0
         return (self.cosmopars["Omegam"] * (1 + z) ** 3) / self.E_hubble(z) ** 2
 
     def SigmaMG(self, z, k):
@@ -485,14 +504,25 @@ class CosmoSet:
         return self._bank
 
     # --- batched preparation on the device ------------------------------------------
-    def prepare(self):
+    _ACCESSOR_OF = {"h_of_z": "Hubble", "com_dist": "comoving", "ang_dist": "angdist", "s8_of_z": "sigma8_of_z",
+                    "s8_cb_of_z": "sigma8_cb_of_z", "_growth_lowk": "growth"}
+
+    def prepare(self, grids=(), scalars=()):
         """Functions of z of every cosmology of the set that has none yet, in ONE device call (cfp_background_fit):
         H(z), the comoving-distance integrals, both distances, sigma8(z) and the low-k growth as cubic splines whose
-        coefficients come back to the facades (cosmology.py:36-55, 1447-1506).  A facade that is never prepared fits the
-        same splines on the host on first access."""
+        coefficients come back to the facades (cosmology.py:36-55, 1447-1506; wrapped in scipy spline objects on first
+        use).  `grids` (redshift arrays) and `scalars` (redshifts) a job is about to ask for are evaluated in the same
+        call and land in the facades' memos, so a batch of thousands of cosmologies costs no per-cosmology spline
+        call.  A facade that is never prepared fits the same splines on the host on first access."""
         if not device_prep(self.config.settings):
             return
-        todo = [c for c in self.cosmos if "h_of_z" not in c.__dict__ and "com_dist" not in c.__dict__]
+        todo = [c for c in self.cosmos if "h_of_z" not in c.__dict__ and "com_dist" not in c.__dict__
+                and "h_of_z" not in c.__dict__.get("_coef1d", ())]
+        if not todo:
+            return
+        grids = [np.ascontiguousarray(g, dtype=float).ravel() for g in grids]
+        scalars = [float(z) for z in scalars]
+        zq = np.concatenate(grids + [np.array(scalars, dtype=float)]) if (grids or scalars) else None
         groups: Dict[tuple, list] = {}
         for c in todo:
             groups.setdefault((c.zgrid.tobytes(), tuple(sorted(c._tab1d)), bool(c.kgrid[0] >= 1e-4)), []).append(c)
@@ -501,17 +531,30 @@ class CosmoSet:
             if zg.size < 5 or zg.size > 2048:
                 continue
             extras = [n for n in names if n != "h_of_z"]
-            ex = [[c._tab1d[n] for n in extras] + ([np.asarray(c._tab2d[_lib.TAB_D][0], float)[:, 0]] if lowk else [])
-                  for c in cs]
-            _, coef = _lib.background_fit(self.context(), zg, np.stack([c._tab1d["h_of_z"] for c in cs]), np.array(ex),
-                                          coef=True)
+            ex = [[c._tab1d[n] for n in extras] + ([c._growth_col0] if lowk else []) for c in cs]
+            out, coef = _lib.background_fit(self.context(), zg, np.stack([c._tab1d["h_of_z"] for c in cs]), np.array(ex),
+                                            zq=zq, coef=True)
             t = nak_knots(zg)
+            rows = ["h_of_z", "com_dist", "ang_dist"] + extras + (["_growth_lowk"] if lowk else [])
             for i, c in enumerate(cs):
                 d = c.__dict__
-                for j, n in enumerate(["h_of_z", "com_dist", "ang_dist"] + extras):
-                    d[n] = InterpolatedUnivariateSpline._from_tck((t, coef[i, j], 3))
-                if lowk:
-                    d["_growth_lowk"] = InterpolatedUnivariateSpline._from_tck((t, coef[i, 3 + len(extras)], 3))
+                cf = d.setdefault("_coef1d", {})
+                for j, n in enumerate(rows):
+                    cf[n] = (t, coef[i, j])
+                if out is None:
+                    continue
+                gm, sm = d.setdefault("_grid_memo", {}), d.setdefault("_scalar_memo", {})
+                for j, n in enumerate(rows):
+                    acc = self._ACCESSOR_OF[n]
+                    o = 0
+                    for g in grids:
+                        v = out[i, j, o:o + g.size]
+                        v.setflags(write=False)
+                        gm.setdefault((acc, g.tobytes()), v)
+                        o += g.size
+                    for z in scalars:
+                        sm.setdefault((acc, z), out[i, j, o])
+                        o += 1
 
     def prepare_spectro(self, zs, tracer="matter"):
         """Velocity moments and no-wiggle spectra of every cosmology of the set at the redshifts zs, two device calls
@@ -560,6 +603,38 @@ _BANK_CACHE: Dict[tuple, tuple] = {}
 _BANK_CACHE_MAX = 8
 
 
+def _combined_bank(ctx, cosmos, slots):
+    """Bank of a set that contains EMULATED cosmologies, without their tables ever existing on the host: the rows of
+    the tabulated cosmologies are fitted on the device once (`TaylorEmulator.base_bank`, kept), and every cosmology of
+    the set -- tabulated ones through one-hot weights -- is a weighted sum of those coefficient rows (interpolating
+    spline fits are linear in the table values): one `cfp_bank_combine_rows`.  None when the set has no emulated
+    cosmology or does not qualify (several emulators, tables in h units, a cosmology from neither source)."""
+    emus = [c._emu for c in cosmos if getattr(c, "_emu", None) is not None]
+    if not emus or os.environ.get("CFP_NO_COMBINE", "0") not in ("", "0"):  # (the switch: tests compare the two routes)
+        return None
+    emulator = emus[0][0]
+    if any(e[0] is not emulator for e in emus):
+        return None
+    order = emulator.folder_order
+    col = {f: i for i, f in enumerate(order)}
+    W = np.zeros((len(cosmos), len(order)))
+    for m, c in enumerate(cosmos):
+        if getattr(c, "_emu", None) is not None:
+            for f, x in c._emu[1].items():
+                W[m, col[f]] = x
+        elif c.folder in col and c.external.get("tables") is emulator.tables and c.external.get("k-units") != "h/Mpc":
+            W[m, col[c.folder]] = 1.0  # a tabulated cosmology of the same bank
+        else:
+            return None
+    names = {s: cosmos[0]._tab2d[s][0] for s in slots if s in cosmos[0]._tab2d}
+    if len(names) != len(slots):
+        return None
+    base = emulator.base_bank(ctx, slots, names)
+    if base is None:
+        return None
+    return base.combined(W, keep_base=False)
+
+
 def _fitted_bank(ctx, cosmos, slots):
     """Bank of the cosmologies' raw tables, fitted on the device (cfp_bank_fit) and kept resident: a later job on the same
     cosmologies (every forecast of a fiducial, every batch of a nuisance-only sampler) uploads nothing.  None when
@@ -574,13 +649,20 @@ def _fitted_bank(ctx, cosmos, slots):
     zg, nk = cosmos[0].zgrid, cosmos[0].kgrid.size
     if zg.size < 5 or nk < 5:
         return None
+    bank = _combined_bank(ctx, cosmos, slots)
+    if bank is not None:
+        bank.h2d_last = bank.nbytes
+        _BANK_CACHE[key] = (ctx, list(cosmos), bank)
+        while len(_BANK_CACHE) > _BANK_CACHE_MAX:
+            _BANK_CACHE.pop(next(iter(_BANK_CACHE)))
+        return bank
     tables, scales = [], []
     for c in cosmos:
         if c.kgrid.size != nk or not np.array_equal(c.zgrid, zg) or any(s not in c._tab2d for s in slots):
             return None
         row, sc = [None] * _lib.NTAB, [1.0] * _lib.NTAB
         for s in slots:
-            tab, scale = c._tab2d[s]
+            tab, scale = c.table2d(s)
             if np.shape(tab) != (zg.size, nk):
                 return None
             row[s], sc[s] = tab, scale

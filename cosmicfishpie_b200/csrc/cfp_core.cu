@@ -220,10 +220,22 @@ __global__ void cfp_bank_combine_kernel(int NC, int M, size_t row_len, const dou
   out[(size_t)m * row_len + e] = acc;
 }
 
+static int bank_combine_impl(cfp_ctx* ctx, const cfp_bank* base, int M, const double* W_h, cfp_bank** out, bool keep_base);
+
 extern "C" int cfp_bank_combine(cfp_ctx* ctx, const cfp_bank* base, int M, const double* W_h, cfp_bank** out) {
+  return bank_combine_impl(ctx, base, M, W_h, out, true);
+}
+
+extern "C" int cfp_bank_combine_rows(cfp_ctx* ctx, const cfp_bank* base, int M, const double* W_h, cfp_bank** out) {
+  return bank_combine_impl(ctx, base, M, W_h, out, false);
+}
+
+// keep_base: the new bank starts with the base rows (cfp_bank_combine); otherwise it holds the M combined rows only
+static int bank_combine_impl(cfp_ctx* ctx, const cfp_bank* base, int M, const double* W_h, cfp_bank** out, bool keep_base) {
   CFP_REQUIRE(ctx && base && W_h && out && M >= 1, "bad argument");
   *out = nullptr;
   const int NC = base->n_cosmo, NT = base->n_tables;
+  const int NB = keep_base ? NC : 0;  // rows carried over in front of the combined ones
   CFP_REQUIRE(base->n % (size_t)NC == 0, "the rows of the base bank differ in length");
   const size_t row_len = base->n / (size_t)NC;
   // every row must have the layout of row 0 (same tables on the same knots): descriptors equal up to the row offset
@@ -245,11 +257,11 @@ extern "C" int cfp_bank_combine(cfp_ctx* ctx, const cfp_bank* base, int M, const
   CFP_CUDA(cudaSetDevice(ctx->device));
   cfp_bank* b = new cfp_bank();
   b->ctx = ctx;
-  b->n_cosmo = NC + M;
+  b->n_cosmo = NB + M;
   b->n_tables = NT;
-  b->n = (size_t)(NC + M) * row_len;
-  b->desc_h.resize((size_t)(NC + M) * NT * CFP_BANK_DESC);
-  for (int c = 0; c < NC + M; ++c)
+  b->n = (size_t)(NB + M) * row_len;
+  b->desc_h.resize((size_t)(NB + M) * NT * CFP_BANK_DESC);
+  for (int c = 0; c < NB + M; ++c)
     for (int t = 0; t < NT; ++t) {
       const int64_t* d0 = base->desc(0, t);
       int64_t* d = &b->desc_h[((size_t)c * NT + t) * CFP_BANK_DESC];
@@ -265,10 +277,11 @@ extern "C" int cfp_bank_combine(cfp_ctx* ctx, const cfp_bank* base, int M, const
   if (rc == CFP_OK) rc = cfp_upload(ctx, is_knot.data(), row_len, &k_d);
   if (rc == CFP_OK) rc = cfp_upload(ctx, b->desc_h.data(), b->desc_h.size(), &b->desc_d);
   if (rc == CFP_OK) {
-    e = cudaMemcpyAsync(b->blob_d, base->blob_d, base->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (keep_base)
+      e = cudaMemcpyAsync(b->blob_d, base->blob_d, base->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
     if (e == cudaSuccess) {
       cfp_bank_combine_kernel<<<dim3((unsigned)((row_len + 255) / 256), M), 256, 0, ctx->stream>>>(
-          NC, M, row_len, base->blob_d, W_d, k_d, b->blob_d + base->n);
+          NC, M, row_len, base->blob_d, W_d, k_d, b->blob_d + (size_t)NB * row_len);
       ctx->launches++;
       e = cudaGetLastError();
     }

@@ -293,7 +293,7 @@ class PhotoJob:
         self.win_of_s = np.zeros(S, dtype=np.int32)
         for ap in points:
             cs.add({k: ap[k] for k in cfg.fiducialparams})
-        cs.prepare()  # H, distances, growth of all the job's cosmologies in one device call
+        cs.prepare(grids=[g.z, nuis.z], scalars=[0.0])  # H, distances, growth of all the job's cosmologies: one device call
         for s, ap in enumerate(points):
             photopars = {k: ap[k] for k in fid_photo}
             if photopars != fid_photo:  # a stencil point of a photo-z parameter: its own n_i(z) windows
@@ -371,7 +371,8 @@ class PhotoJob:
                 cp.update({k: float(v) for k, v in zip(ckeys, uniq[u])})
                 idx[u] = cs.add(cp)
             self.cosmo_of_s = idx[np.asarray(inv).ravel()]
-        cs.prepare()
+        # H, distances, growth of all new cosmologies in one device call, evaluated on the grids this job reads
+        cs.prepare(grids=[g.z, nuis.z], scalars=[0.0])
         self.zmap = None  # bias sampled on the z grid, or on fewer samples + a z -> sample map (binned models)
         self.bias = None
         self.ia = np.zeros((B, Nz))

@@ -411,7 +411,7 @@ def _cosmo_set_of(cfg) -> CosmoSet:
 def prepare_cosmologies(cs: CosmoSet, zs, obs: "ComputeGalSpectro"):
     """Everything the scalar blocks and no-wiggle tables of the set's cosmologies need from the Boltzmann tables, fitted
     and integrated on the device for all of them at once (CosmoSet.prepare / prepare_spectro, csrc/cfp_prep.cu)."""
-    cs.prepare()
+    cs.prepare(scalars=zs)
     if not obs.linear_switch:
         cs.prepare_spectro(zs, tracer=obs.tracer)
 

@@ -405,6 +405,10 @@ int cfp_legendre_chi2(cfp_ctx* ctx, int S, int Nk, int Z, const double* pl_data_
  * H2D of tables -- where the reference snaps an off-grid cosmology to the nearest folder
  * (cosmicfishpie/cosmology/cosmology.py:1375-1421).  All rows of `base` must share table shapes and knots. */
 int cfp_bank_combine(cfp_ctx* ctx, const cfp_bank* base, int M, const double* W_h, cfp_bank** out);
+/* The same, but the new bank holds the M combined rows ONLY, in the order of W_h's rows (a row of W_h that is one-hot
+ * reproduces a base row): the bank of a likelihood batch whose every point has its own emulated cosmology, built
+ * without the tables leaving the device. */
+int cfp_bank_combine_rows(cfp_ctx* ctx, const cfp_bank* base, int M, const double* W_h, cfp_bank** out);
 
 /* ---- device-side preparation of the cosmology input ---------------------------------------------
  * What `external_input.calculate_interpol_results` and the no-wiggle / velocity-moment helpers redo on the host for

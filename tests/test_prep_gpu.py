@@ -147,7 +147,7 @@ def test_prepared_facades_match_host_facades(spectro_cfg, extfiles, monkeypatch)
     worst = {}
     assert len(cs.cosmos) == len(pars)
     for q, dev in zip(pars, cs.cosmos):
-        assert "_growth_lowk" in dev.__dict__ and "com_dist" in dev.__dict__  # really the prepared ones
+        assert "_growth_lowk" in dev._coef1d and "com_dist" in dev._coef1d  # really the prepared ones
         monkeypatch.setenv("CFP_HOST_PREP", "1")
         host = cz.cosmo_functions(dict(dev.cosmopars), "external", cfg)
         monkeypatch.delenv("CFP_HOST_PREP")

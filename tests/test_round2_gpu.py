@@ -430,3 +430,57 @@ def test_emulated_cosmology_likelihood_and_device_combine(extfiles, toy_bank, tm
         assert np.array_equal(comb.eval(3, slot, zq, kq), base.eval(3, slot, zq, kq))  # the base rows are carried over
     comb.close()
     base.close()
+
+
+def test_emulated_batch_combines_bank_rows_on_the_device(extfiles, toy_bank, tmp_path, monkeypatch):
+    """A likelihood batch whose every point has its own (emulated) cosmology: the bank of the batch is combined from
+    the tabulated rows on the device (cfp_bank_combine_rows, the emulated tables never exist on the host) and gives
+    the log-likelihoods of the route that forms every emulated table on the host and fits it (CFP_NO_COMBINE=1)."""
+    from cosmicfishpie_b200 import cosmology as cz
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.bank import TaylorEmulator
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+    from cosmicfishpie_b200.likelihood import PhotometricLikelihood, SpectroLikelihood
+
+    emu = TaylorEmulator(toy_bank, tt.FIDUCIAL, tt.COSMO_KEYS, 0.01)
+    ext = dict(extfiles, emulator=emu)
+    rng = np.random.default_rng(5)
+
+    def batch(fm, keys, n):
+        fid = np.array([fm.allparams[k] for k in keys])
+        pts = np.tile(fid, (n, 1))
+        nc = sum(k in tt.COSMO_KEYS for k in keys)
+        pts[:, :nc] *= 1 + 0.008 * rng.uniform(-1, 1, size=(n, nc))
+        pts[0, :nc] = fid[:nc]  # (a tabulated cosmology among them: one-hot weights)
+        pts[:, nc:] *= 1 + 0.01 * rng.standard_normal((n, len(keys) - nc))
+        return pts
+
+    def both(like, pts, keys):
+        cz.clear_caches()
+        fast = like.loglike_batch(pts, keys=keys)
+        used_combine = any(hit[2].blob is None and not hit[2].rows and hit[2].n_cosmo == len(hit[1]) and
+                           any(getattr(c, "_emu", None) for c in hit[1]) for hit in cz._BANK_CACHE.values())
+        assert used_combine
+        cz.clear_caches()
+        monkeypatch.setenv("CFP_NO_COMBINE", "1")
+        slow = like.loglike_batch(pts, keys=keys)
+        monkeypatch.delenv("CFP_NO_COMBINE")
+        cz.clear_caches()
+        return fast, slow
+
+    fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"h": 0.01, "Omegam": 0.01},
+                      options=base_options(tmp_path / "s", spectro_Pk_k_samples=257, spectro_Pk_mu_samples=17),
+                      observables=["GCsp"], extfiles=ext)
+    fm.compute()
+    keys = ["Omegam", "h", "sigma8", "ns", "lnbg_1", "lnbg_3"]
+    fast, slow = both(SpectroLikelihood(cosmoFM_data=fm), batch(fm, keys, 24), keys)
+    assert np.all(np.isfinite(fast)) and np.max(np.abs(fast - slow) / np.abs(slow)) < 1e-9
+
+    fp = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"h": 0.01, "Omegam": 0.01},
+                      options=base_options(tmp_path / "p", survey_name_photo="Euclid-Photometric-ISTF-Pessimistic",
+                                           survey_name_spectro=False, ell_sampling=24),
+                      observables=["WL", "GCph"], extfiles=ext)
+    fp.compute()
+    keys = ["Omegam", "h", "sigma8", "w0", "b1", "b5", "AIA"]
+    fast, slow = both(PhotometricLikelihood(cosmo_data=fp), batch(fp, keys, 40), keys)
+    assert np.all(np.isfinite(fast)) and np.max(np.abs(fast - slow) / np.abs(slow)) < 1e-9

@@ -83,8 +83,8 @@ def test_growth_rate_on_its_own_wavenumber_grid(tmp_path, monkeypatch):
     def patched_init(self, *a, **k):
         orig_init(self, *a, **k)
         lazy = self.__dict__["_lazy"]["f_growthrate_zk"]
-        zg, kg, tab, _ = lazy._args
-        lazy._spl, lazy._args = coarse_f(zg, kg, tab), None
+        zg, kg, tables, name, _ = lazy._args
+        lazy._spl, lazy._args = coarse_f(zg, kg, tables[name]), None
 
     # (tables whose surfaces live on different knots only arise from host fits: the device fit of a bank shares them)
     monkeypatch.setenv("CFP_HOST_PREP", "1")
