@@ -74,6 +74,7 @@ class LazyTables:
 
     def __init__(self, emulator: "TaylorEmulator", weights: Dict[str, float]):
         self.emulator, self.weights, self._done = emulator, weights, {}
+        self._wvec = emulator.weight_vector(weights)
 
     def __contains__(self, name):
         return name in self.emulator.tables[self.emulator.fiducial_folder]
@@ -89,14 +90,15 @@ class LazyTables:
             else:
                 if name not in t0:
                     raise KeyError(name)
-                self._done[name] = self.emulator.combine(name, self.weights)
+                first = np.asarray(t0[name])
+                self._done[name] = self.emulator.combine(name, self._wvec if first.ndim == 1 else self.weights)
         return self._done[name]
 
     def column0(self, name):
         """First wavenumber column of a (z, k) table without forming the table."""
         if name in self._done:
             return np.asarray(self._done[name])[:, 0]
-        return self.emulator.combine(name, self.weights, column=0)
+        return self.emulator.combine(name, self._wvec, column=0)
 
 
 class TaylorEmulator:
@@ -167,18 +169,24 @@ class TaylorEmulator:
                 st = stacks[key] = np.stack([np.asarray(self.tables[f][name], dtype=float) if column is None
                                              else np.asarray(self.tables[f][name], dtype=float)[:, column]
                                              for f in self.folder_order])
-                self.__dict__["_col_of_folder"] = {f: i for i, f in enumerate(self.folder_order)}
-            col = self.__dict__["_col_of_folder"]
-            acc = None
-            for folder, x in weights.items():  # (the same order of additions as the loop over full tables)
-                term = x * st[col[folder]]
-                acc = term if acc is None else acc + term
-            return acc
+            return self.weight_vector(weights) @ st
         acc = None
         for folder, x in weights.items():
             term = x * np.asarray(self.tables[folder][name], dtype=float)
             acc = term if acc is None else acc + term
         return acc
+
+    def weight_vector(self, weights) -> np.ndarray:
+        """The weights {folder: x} as a dense vector over `folder_order` (a vector passes through)."""
+        if isinstance(weights, np.ndarray):
+            return weights
+        col = self.__dict__.get("_col_of_folder")
+        if col is None:
+            col = self.__dict__["_col_of_folder"] = {f: i for i, f in enumerate(self.folder_order)}
+        w = np.zeros(len(col))
+        for folder, x in weights.items():
+            w[col[folder]] = x
+        return w
 
     def tables_at(self, theta: Dict[str, float], weights: Optional[Dict[str, float]] = None) -> "LazyTables":
         """The tables of cosmology `theta`: the weighted sum of the bank's folders, each table formed on first access
