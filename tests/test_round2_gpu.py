@@ -484,3 +484,44 @@ def test_emulated_batch_combines_bank_rows_on_the_device(extfiles, toy_bank, tmp
     keys = ["Omegam", "h", "sigma8", "w0", "b1", "b5", "AIA"]
     fast, slow = both(PhotometricLikelihood(cosmo_data=fp), batch(fp, keys, 40), keys)
     assert np.all(np.isfinite(fast)) and np.max(np.abs(fast - slow) / np.abs(slow)) < 1e-9
+
+
+def test_nautilus_sampler_over_cosmology_with_the_emulator(extfiles, toy_bank, tmp_path, monkeypatch):
+    """A chain that moves in COSMOLOGY (Omegam, h, sigma8 free beside nuisance parameters): with the bank's emulator
+    every proposed point gets its own cosmology (the reference would call its Boltzmann solver per point or, with
+    external tables, snap to the nearest folder); the batches run through the device-combined banks.  The chain's
+    log-likelihoods equal the point-by-point joint likelihood."""
+    monkeypatch.syspath_prepend(os.path.join(REPO, "tools", "_stubs"))
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.bank import TaylorEmulator
+    from cosmicfishpie_b200.sampler import NautilusSampler, load_chain_metadata
+
+    emu = TaylorEmulator(toy_bank, tt.FIDUCIAL, tt.COSMO_KEYS, 0.01)
+    f = tt.FIDUCIAL
+    cfg = {
+        "name": "cosmo", "fiducial": dict(f), "observables": ["WL", "GCph", "GCsp"], "extfiles": dict(extfiles, emulator=emu),
+        "options": {"accuracy": 1, "feedback": 0, "code": "external", "survey_name": "Euclid", "cosmo_model": "w0waCDM",
+                    "survey_name_photo": "Euclid-Photometric-ISTF-Pessimistic",
+                    "survey_name_spectro": "Euclid-Spectroscopic-ISTF-Pessimistic", "ell_sampling": 12,
+                    "spectro_Pk_k_samples": 129, "spectro_Pk_mu_samples": 9},
+        "priors": {"Omegam": [f["Omegam"] * 0.993, f["Omegam"] * 1.007], "h": [f["h"] * 0.993, f["h"] * 1.007],
+                   "sigma8": [f["sigma8"] * 0.993, f["sigma8"] * 1.007], "b3": [1.2, 1.5], "lnbg_2": [0.40, 0.46]},
+        "sampler_settings": {"n_live": 16, "n_networks": 1, "n_batch": 16},
+    }
+    s = NautilusSampler(cfg, base_dir=str(tmp_path))
+    assert s.prior_chosen.keys == ["Omegam", "h", "sigma8", "b3", "lnbg_2"]
+    naut = s.run()
+    assert naut.vectorized and naut.n_calls == 3
+    chain, _, meta, _ = load_chain_metadata(os.path.join(str(tmp_path), "chains", "chains_cosmo"))
+    data = np.loadtxt(chain)
+    assert data.shape == (48, 5 + 2) and np.all(np.isfinite(data[:, -1]))
+    assert np.ptp(data[:, 0]) > 0 and np.ptp(data[:, 1]) > 0  # the chain really moved in cosmology
+    ph, sp = s.likelihood.parts
+    keys = s.prior_chosen.keys
+    for row in data[:3]:
+        d = dict(zip(keys, row[:5]))
+        assert abs(ph.loglike(param_dict=d) + sp.loglike(param_dict=d) - row[6]) <= 1e-9 * abs(row[6])
+    # and the likelihood does depend on the cosmology of the point (it is not snapped to the fiducial folder)
+    d0, d1 = dict(zip(keys, data[0, :5])), dict(zip(keys, data[0, :5]))
+    d1["Omegam"] = d0["Omegam"] * 1.002
+    assert abs(ph.loglike(param_dict=d1) - ph.loglike(param_dict=d0)) > 1e-6 * abs(ph.loglike(param_dict=d0))
