@@ -429,9 +429,17 @@ def _base_blocks(fid_obs: "ComputeGalSpectro", cs: CosmoSet, c: int, zs) -> np.n
     cache = cosmo.__dict__.setdefault("_sp_base_cache", {})
     hit = cache.get(key)
     if hit is None or hit[0] is not fid_obs.fiducialcosmo:  # identity check: the fiducial facade enters q_par, q_perp
-        obs = ComputeGalSpectro(cosmo.cosmopars, spectrobiaspars=fid_obs.fiducial_spectrobiaspars,
-                                spectrononlinearpars=fid_obs.fiducial_spectrononlinearpars,
-                                PShotpars=fid_obs.fiducial_PShotpars, configuration=fid_obs.config, cosmo_set=cs)
+        # the parameter point "cosmology c, fiducial nuisance values": a shallow copy of one template object per
+        # fiducial observable (the constructor costs more than the four blocks when a batch brings thousands of
+        # cosmologies), with the three attributes that name the cosmology rebound
+        tmpl = fid_obs.__dict__.get("_base_template")
+        if tmpl is None or tmpl.cosmo_set is not cs:
+            tmpl = fid_obs.__dict__["_base_template"] = ComputeGalSpectro(
+                fid_obs.fiducial_cosmopars, spectrobiaspars=fid_obs.fiducial_spectrobiaspars,
+                spectrononlinearpars=fid_obs.fiducial_spectrononlinearpars, PShotpars=fid_obs.fiducial_PShotpars,
+                configuration=fid_obs.config, cosmo_set=cs)
+        obs = copy.copy(tmpl)
+        obs.cosmopars, obs.cosmo, obs.cosmo_index = cosmo.cosmopars, cosmo, c
         arr = np.array([obs.scalar_block(z) for z in zs])
         arr.setflags(write=False)
         hit = (fid_obs.fiducialcosmo, arr)
