@@ -26,16 +26,17 @@ constexpr int CLS_WARPS = 8;  // warps per CTA (A/B on B200, CFP_CLS_WARPS: Fish
                               // 4096-point likelihood chunk incl. chi2 4: 7.83, 8: 7.37, 16: 8.34 ms)
 constexpr int MAX_PNB = 8;  // Nb <= 64 tomographic rows
 
+// multipoles [l0, l0 + nl) only: a rank of a sharded forecast fills its own rows of the table
 __global__ void photo_sqrtp_kernel(const double* __restrict__ blob, const int64_t* __restrict__ desc, int n_tables,
-                                   int tab, int NC, int Nl, int Nz, const double* __restrict__ ell,
+                                   int tab, int NC, int Nl, int Nz, int l0, int nl, const double* __restrict__ ell,
                                    const double* __restrict__ z, const double* __restrict__ chi, double kmax,
                                    double* __restrict__ T) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t tot = (size_t)NC * Nl * Nz;
+  const size_t tot = (size_t)NC * nl * Nz;
   if (idx >= tot) return;
   const int iz = (int)(idx % Nz);
-  const int il = (int)((idx / Nz) % Nl);
-  const int c = (int)(idx / ((size_t)Nz * Nl));
+  const int il = l0 + (int)((idx / Nz) % nl);
+  const int c = (int)(idx / ((size_t)Nz * nl));
   const double ch = chi[(size_t)c * Nz + iz];
   const double kappa = (ell[il] + 0.5) / ch;  // photo_obs.py:481
   double v = 0.0;
@@ -44,7 +45,7 @@ __global__ void photo_sqrtp_kernel(const double* __restrict__ blob, const int64_
     const double p = cfp_bispev_point(blob + d[2], (int)d[0], blob + d[3], (int)d[1], blob + d[4], z[iz], kappa);
     v = sqrt(p) / ch;
   }
-  T[idx] = v;
+  T[((size_t)c * Nl + il) * Nz + iz] = v;
 }
 
 // one CTA per cosmology: eff = I1 - chi * I2 with backward cumulative trapezoids (sequential in z like
@@ -1222,6 +1223,7 @@ extern "C" int cfp_photo_plan_set_gc_table(cfp_photo_plan* plan, int tab_p_gc) {
   if (tab_p_gc != plan->tab_p && !plan->Tg_d) {
     CFP_CUDA(cfp_dev_alloc(ctx, (void**)&plan->Tg_d, (size_t)plan->NC * plan->Nl * plan->Nz * sizeof(double)));
     plan->owned.push_back((void*)plan->Tg_d);
+    CFP_CUDA(cudaMemsetAsync(plan->Tg_d, 0, (size_t)plan->NC * plan->Nl * plan->Nz * sizeof(double), ctx->stream));
     CFP_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   plan->tab_pg = tab_p_gc;
@@ -1291,18 +1293,24 @@ static int photo_run_cls(cfp_photo_plan* pl, cudaStream_t st, bool all_ell) {
     if (!e) CFP_CUDA(cudaEventCreate(&e));
   CFP_CUDA(cudaEventRecord(pl->kev[0], st));
   {
-    const size_t tot = (size_t)pl->NC * pl->Nl * pl->Nz;
-    photo_sqrtp_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(
-        pl->bank->blob_d, pl->bank->desc_d, pl->bank->n_tables, pl->tab_p, pl->NC, pl->Nl, pl->Nz, pl->ell_d, pl->z_d,
-        pl->chi_d, pl->kmax, pl->T_d);
-    ctx->launches++;
-    CFP_CUDA(cudaGetLastError());
-    if (pl->tab_pg != pl->tab_p) {
+    // the multipoles of this run (a slice of a sharded forecast computes its own rows of the Limber table only; the
+    // table is zero-filled at plan creation, so the rows of other ranks read as zeros)
+    const int l0 = all_ell ? 0 : pl->l_begin;
+    const int nl = (all_ell ? pl->Nl : std::min(pl->l_end + 1, pl->Nl)) - l0;
+    const size_t tot = (size_t)pl->NC * nl * pl->Nz;
+    if (tot > 0) {
       photo_sqrtp_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(
-          pl->bank->blob_d, pl->bank->desc_d, pl->bank->n_tables, pl->tab_pg, pl->NC, pl->Nl, pl->Nz, pl->ell_d,
-          pl->z_d, pl->chi_d, pl->kmax, pl->Tg_d);
+          pl->bank->blob_d, pl->bank->desc_d, pl->bank->n_tables, pl->tab_p, pl->NC, pl->Nl, pl->Nz, l0, nl, pl->ell_d,
+          pl->z_d, pl->chi_d, pl->kmax, pl->T_d);
       ctx->launches++;
       CFP_CUDA(cudaGetLastError());
+      if (pl->tab_pg != pl->tab_p) {
+        photo_sqrtp_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(
+            pl->bank->blob_d, pl->bank->desc_d, pl->bank->n_tables, pl->tab_pg, pl->NC, pl->Nl, pl->Nz, l0, nl, pl->ell_d,
+            pl->z_d, pl->chi_d, pl->kmax, pl->Tg_d);
+        ctx->launches++;
+        CFP_CUDA(cudaGetLastError());
+      }
     }
   }
   CFP_CUDA(cudaEventRecord(pl->kev[1], st));
