@@ -36,7 +36,7 @@ from . import spectro as spectro_mod
 VERSION = "1.3.0"  # the reference release whose results this package reproduces
 
 
-def _write_text(path, text):
+def _write_now(path, text):
     """One open / write / close on the file descriptor (no buffered text layer: four small files per Fisher matrix)."""
     fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o666)
     try:
@@ -45,6 +45,56 @@ def _write_text(path, text):
             data = data[os.write(fd, data):]
     finally:
         os.close(fd)
+
+
+class _DeferredWrites:
+    """Result files of a batch of forecasts (`FisherMatrix.compute_many`) written by ONE helper thread: the eight
+    open / write / close system calls per forecast release the interpreter lock, so they overlap the assembly of the
+    next forecast.  `flush()` returns when every file handed over so far is on disk and re-raises the first error."""
+
+    def __init__(self):
+        import queue
+        import threading
+
+        self.q, self.err = queue.Queue(), None
+        self.thread = threading.Thread(target=self._run, name="cfp-export", daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        while True:
+            item = self.q.get()
+            try:
+                if item is None:
+                    return
+                if self.err is None:
+                    _write_now(*item)
+            except Exception as exc:  # noqa: BLE001 -- reported by flush()
+                self.err = exc
+            finally:
+                self.q.task_done()
+
+    def put(self, path, text):
+        self.q.put((path, text))
+
+    def flush(self):
+        self.q.join()
+        if self.err is not None:
+            err, self.err = self.err, None
+            raise err
+
+    def close(self):
+        self.q.put(None)
+        self.thread.join()
+
+
+_deferred = None  # set by compute_many for the duration of a batch
+
+
+def _write_text(path, text):
+    if _deferred is not None:
+        _deferred.put(path, text)
+    else:
+        _write_now(path, text)
 
 
 _ARRAY_STR = {}
@@ -186,19 +236,31 @@ class FisherMatrix:
         forecast late.  Returns the list of results in order -- the same objects `compute()` returns.
         (The reference has no batch entry: every forecast is one blocking `compute()`; SURVEY 8e names batches of
         forecasts -- many fiducials or survey specifications -- as the unit that fills a GPU.)"""
+        global _deferred
         out, pending = [], None
 
         def collect(f, launched):
             out.append(f._finish(launched))
             f.release_device()  # a batch keeps at most two forecasts' buffers on the device
 
-        for f in forecasts:
-            launched = f._launch(max_z_bins)
+        sync_export = os.environ.get("CFP_SYNC_EXPORT", "0") not in ("", "0")  # (A/B switch)
+        writer = _DeferredWrites() if _deferred is None and not sync_export else None  # (result files: see _DeferredWrites)
+        if writer is not None:
+            _deferred = writer
+        try:
+            for f in forecasts:
+                launched = f._launch(max_z_bins)
+                if pending is not None:
+                    collect(*pending)
+                pending = (f, launched)
             if pending is not None:
                 collect(*pending)
-            pending = (f, launched)
-        if pending is not None:
-            collect(*pending)
+            if writer is not None:
+                writer.flush()  # every file of the batch is on disk when the results are returned
+        finally:
+            if writer is not None:
+                _deferred = None
+                writer.close()
         return out
 
     def release_device(self):
@@ -482,7 +544,7 @@ class FisherMatrix:
             tag = ".tmp%d_%d" % (rank, os.getpid())
 
             def write_atomic(path, text):
-                _write_text(path + tag, text)
+                _write_now(path + tag, text)
                 os.replace(path + tag, path)
         else:  # a single process owns its files: plain writes
             write_atomic = _write_text
@@ -505,6 +567,8 @@ class FisherMatrix:
             out.name = os.path.splitext(os.path.basename(out.file_name))[0]
             out.indir = os.path.dirname(out.path)
         else:  # all-zero rows / columns are deleted on reading (analysis/fisher_matrix.py:261-268): take that route
+            if _deferred is not None:
+                _deferred.flush()
             out = fm.fisher_matrix(file_name=root + ".txt")
         if rank != 0 and cdist.is_distributed():
             return out  # the specification files are rank 0's business
