@@ -421,15 +421,36 @@ def clear_caches():
     spectro._PNW_MEMO.clear()
 
 
-def cached_cosmo(cosmopars, config) -> "cosmo_functions":
-    """Boltzmann input is computed once and cached (north_star): one spline facade per (table source, folder,
-    parameter values, units, no-wiggle settings), shared by every FisherMatrix / likelihood of the process."""
+def _config_key_part(config):
+    """Everything of a facade's cache key that belongs to the configuration, rebuilt only when one of the values it is
+    made of changes (a forecast asks for thirty facades; sorting and tupling the same dictionaries thirty times was a
+    tenth of its host time).  The check compares the raw values, so editing a setting in place is still seen."""
     ext, st = config.external, config.settings
+    fid = config.fiducialparams
+    tables, emulator, names = ext.get("tables"), ext.get("emulator"), ext["paramnames"]
+    # (objects by identity -- kept alive beside the cached part, so an id cannot be recycled --, values by value)
+    sig = (id(tables), id(emulator), id(names), len(names), ext.get("directory"), ext.get("k-units"), ext.get("r-units"),
+           tuple(ext["eps_values"]), st["savgol_internalkmin"], st["savgol_internalsamples"], st["savgol_width"],
+           st["savgol_polyorder"], st.get("GCsp_Tracer"), st.get("GCph_Tracer"), tuple(fid), tuple(fid.values()))
+    hit = config.__dict__.get("_cosmo_key_part")
+    if hit is not None and hit[0] == sig:
+        return hit[1]
     src = id(ext["tables"]) if ext.get("tables") is not None else os.path.abspath(ext["directory"])
-    key = (src, tuple(sorted((k, v) for k, v in cosmopars.items())), tuple(sorted(config.fiducialparams.items())),
-           tuple(ext["paramnames"]), tuple(ext["eps_values"]), ext.get("k-units"), ext.get("r-units"),
-           st["savgol_internalkmin"], st["savgol_internalsamples"], st["savgol_width"], st["savgol_polyorder"],
-           st.get("GCsp_Tracer"), st.get("GCph_Tracer"), id(ext.get("emulator")))
+    part = (src, tuple(sorted(fid.items())), tuple(ext["paramnames"]), tuple(ext["eps_values"]), ext.get("k-units"),
+            ext.get("r-units"), st["savgol_internalkmin"], st["savgol_internalsamples"], st["savgol_width"],
+            st["savgol_polyorder"], st.get("GCsp_Tracer"), st.get("GCph_Tracer"), id(ext.get("emulator")))
+    config.__dict__["_cosmo_key_part"] = (sig, part, (tables, emulator, names))
+    return part
+
+
+def cached_cosmo(cosmopars, config, cosmo_key=None) -> "cosmo_functions":
+    """Boltzmann input is computed once and cached (north_star): one spline facade per (table source, folder,
+    parameter values, units, no-wiggle settings), shared by every FisherMatrix / likelihood of the process.
+    `cosmo_key`: tuple(sorted(cosmopars.items())) when the caller already has it."""
+    ext = config.external
+    if cosmo_key is None:
+        cosmo_key = tuple(sorted(cosmopars.items()))
+    key = (_config_key_part(config), cosmo_key)
     hit = _COSMO_CACHE.get(key)
     if hit is not None and hit[0] is ext.get("tables"):  # identity check: id() values can be recycled
         return hit[1]
@@ -461,7 +482,7 @@ class CosmoSet:
         key = self._key(cosmopars)
         if key not in self._by_key:
             if cosmo is None:
-                cosmo = cached_cosmo(cosmopars, self.config)
+                cosmo = cached_cosmo(cosmopars, self.config, cosmo_key=key)
             self._by_key[key] = len(self.cosmos)
             self.cosmos.append(cosmo)
             self._bank = None
