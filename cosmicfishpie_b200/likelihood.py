@@ -505,6 +505,8 @@ class SpectroLikelihood(Likelihood, NautilusMixin):
         zs = list(fm.pk_cov.global_z_bin_mids)
         matrix = np.atleast_2d(np.asarray(matrix, dtype=float))
         B, Z = matrix.shape[0], len(zs)
+        if B == 0 or matrix.size == 0:  # an empty batch (a sampler may propose none): nothing to evaluate
+            return np.empty(0)
         scal, shot, cosmo_of_s = spectro_mod.scalar_blocks_from_matrix(fm, fid_obs, zs, names, matrix)
         used = {int(c) for c in np.unique(cosmo_of_s)}
         pk, pp = spectro_mod._pnw_arrays(cs, zs, set() if fid_obs.linear_switch else used)

@@ -209,3 +209,33 @@ def test_spectro_moment_path_equals_direct_kernels(spectro_fm, monkeypatch, flag
     b = like.chi2_matrix(keys, big[:64])
     monkeypatch.delenv("CFP_NO_MOMENTS")
     assert np.all(np.isfinite(a)) and np.max(np.abs(a[:64] - b) / b) < tol
+
+
+def test_batch_edge_sizes(extfiles, tmp_path):
+    """Empty batches, single points and a batch one point longer than a chunk: shapes, finiteness, and the last point
+    equal to its point-by-point evaluation."""
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+    from cosmicfishpie_b200.likelihood import PhotometricLikelihood, SpectroLikelihood
+
+    fp = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"Omegam": 0.01},
+                      options=base_options(tmp_path / "p", survey_name_photo="Euclid-Photometric-ISTF-Pessimistic",
+                                           survey_name_spectro=False, ell_sampling=12),
+                      observables=["WL", "GCph"], extfiles=extfiles)
+    fp.compute()
+    fs = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"Omegam": 0.01},
+                      options=base_options(tmp_path / "s", spectro_Pk_k_samples=65, spectro_Pk_mu_samples=9),
+                      observables=["GCsp"], extfiles=extfiles)
+    fs.compute()
+    rng = np.random.default_rng(0)
+    for like, fm, big in ((PhotometricLikelihood(cosmo_data=fp), fp, 4097), (SpectroLikelihood(cosmoFM_data=fs), fs, 8193),
+                          (SpectroLikelihood(cosmoFM_data=fs, leg_flag="legendre"), fs, 8193)):
+        keys = [k for k in fm.freeparams if k != "Omegam"][:3]
+        fid = np.array([fm.allparams[k] for k in keys])
+        for B in (0, 1, 2, big):
+            mat = fid * (1 + 0.01 * rng.standard_normal((B, len(keys))))
+            ll = like.loglike_batch(mat, keys=keys)
+            assert ll.shape == (B,) and np.all(np.isfinite(ll))
+            if B:
+                one = like.loglike(param_dict=dict(zip(keys, mat[-1])))
+                assert abs(ll[-1] - one) <= 1e-9 * abs(one)
