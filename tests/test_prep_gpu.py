@@ -198,3 +198,34 @@ def test_forecasts_agree_between_device_and_host_preparation(extfiles, tmp_path,
     assert elem_rel_err(Pd, Ph) < 1e-7  # (the photometric off-diagonals cancel to 1e-3: DESIGN section 2)
     assert rel_err(np.sqrt(np.diag(np.linalg.inv(Pd))), np.sqrt(np.diag(np.linalg.inv(Ph)))) < 1e-9
     cz.clear_caches()
+
+
+@pytest.mark.parametrize("nz", [4, 5, 7])
+def test_short_redshift_grids(tmp_path, monkeypatch, nz):
+    """Tables on very few redshifts: with fewer than five the device preparation declines (a not-a-knot cubic needs
+    five samples per axis) and the host fits take over silently; with five or seven it runs -- either way the forecast
+    equals the one prepared on the host."""
+    from cosmicfishpie_b200 import cosmology as cz
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    bank = tt.make_bank(eps_values=(0.01,), pars=("Omegam", "h"), nz=nz, nk=120)
+    ext = {"tables": bank, "directory": "<memory>", "paramnames": list(tt.COSMO_KEYS), "folder_paramnames": list(tt.COSMO_KEYS),
+           "k-units": "1/Mpc", "r-units": "Mpc", "eps_values": [0.01]}
+
+    def run():
+        cz.clear_caches()
+        fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"Omegam": 0.01, "h": 0.01},
+                          options=base_options(tmp_path, spectro_Pk_k_samples=65, spectro_Pk_mu_samples=9),
+                          observables=["GCsp"], extfiles=ext)
+        F = np.array(fm.compute(max_z_bins=2).fisher_matrix)
+        fitted_on_device = any(not hit[2].rows for hit in cz._BANK_CACHE.values())
+        return F, fitted_on_device
+
+    Fd, on_device = run()
+    assert on_device == (nz >= 5)
+    monkeypatch.setenv("CFP_HOST_PREP", "1")
+    Fh, _ = run()
+    monkeypatch.delenv("CFP_HOST_PREP")
+    cz.clear_caches()
+    assert np.all(np.isfinite(Fd)) and elem_rel_err(Fd, Fh) < 1e-8
