@@ -341,3 +341,22 @@ def test_split_range_partitions_exactly():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_tables_from_the_reference_directory_layout(tmp_path):
+    """`extfiles["directory"]`: one folder per cosmology with the reference's text files (cosmology.py:1249-1373).
+    Written with numpy's default format the numbers round-trip exactly, so the loader must return the bank's arrays."""
+    from cosmicfishpie_b200 import cosmology as cz
+    from cosmicfishpie_b200 import toy_tables as tt
+
+    bank = tt.make_bank(eps_values=(0.01,), pars=("h",), nz=12, nk=30)
+    root = tt.write_bank(str(tmp_path / "bank"), bank)
+    ext = tt.extfiles_for(root, pars=tt.COSMO_KEYS)
+    ext["fiducial_folder"] = "fiducial_eps_0"
+    cz.clear_caches()
+    for folder, t in bank.items():
+        got = cz.load_tables(ext, folder)
+        for key in ("z", "k", "H", "s8", "D", "f", "Pl", "Pnl"):
+            assert np.array_equal(got[key], t[key]), (folder, key)
+    assert cz.load_tables(ext, "fiducial_eps_0") is cz.load_tables(ext, "fiducial_eps_0")  # parsed once
+    cz.clear_caches()

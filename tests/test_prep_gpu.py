@@ -229,3 +229,25 @@ def test_short_redshift_grids(tmp_path, monkeypatch, nz):
     monkeypatch.delenv("CFP_HOST_PREP")
     cz.clear_caches()
     assert np.all(np.isfinite(Fd)) and elem_rel_err(Fd, Fh) < 1e-8
+
+
+def test_forecast_from_the_reference_directory_layout(tmp_path, toy_bank, extfiles):
+    """The reference's own input format -- a directory tree of text files -- gives the forecast of the in-memory bank."""
+    from cosmicfishpie_b200 import cosmology as cz
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    sub = {name: t for name, t in toy_bank.items() if name.startswith(("fiducial", "Omegam", "h_"))}
+    root = tt.write_bank(str(tmp_path / "bank"), sub)
+
+    def run(ext):
+        cz.clear_caches()
+        fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"Omegam": 0.01, "h": 0.01},
+                          options=base_options(tmp_path / "out", spectro_Pk_k_samples=129, spectro_Pk_mu_samples=9),
+                          observables=["GCsp"], extfiles=ext)
+        return np.array(fm.compute(max_z_bins=2).fisher_matrix)
+
+    F_dir = run(tt.extfiles_for(root))
+    F_mem = run(extfiles)
+    cz.clear_caches()
+    assert elem_rel_err(F_dir, F_mem) < 1e-13
