@@ -251,3 +251,27 @@ def test_forecast_from_the_reference_directory_layout(tmp_path, toy_bank, extfil
     F_mem = run(extfiles)
     cz.clear_caches()
     assert elem_rel_err(F_dir, F_mem) < 1e-13
+
+
+def test_forecast_from_a_memory_mapped_bank_file(tmp_path, toy_bank, extfiles):
+    """`extfiles["tables"] = load_bank(path)`: read-only arrays of a memory map go to the device fit as they are."""
+    from cosmicfishpie_b200 import cosmology as cz
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.bank import load_bank, save_bank
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+
+    tables, _ = load_bank(save_bank(str(tmp_path / "toy.cfpbank"), toy_bank))
+    assert not tables["fiducial_eps_0"]["Pl"].flags.writeable
+
+    def run(ext, kind):
+        cz.clear_caches()
+        opts = base_options(tmp_path / "out")
+        if kind == "photo":
+            opts.update(survey_name_photo="Euclid-Photometric-ISTF-Pessimistic", survey_name_spectro=False, ell_sampling=12)
+        fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"Omegam": 0.01, "h": 0.01}, options=opts,
+                          observables=["WL", "GCph"] if kind == "photo" else ["GCsp"], extfiles=ext)
+        return np.array(fm.compute().fisher_matrix)
+
+    for kind in ("spectro", "photo"):
+        assert np.array_equal(run(dict(extfiles, tables=tables), kind), run(extfiles, kind)), kind
+    cz.clear_caches()
