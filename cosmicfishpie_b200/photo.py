@@ -664,10 +664,25 @@ class PhotoCov:
                 raise ValueError("Fiducial values missing for free parameters: " + k)
         return fp
 
+    @property
+    def points(self):
+        """Flat {name: number} dictionary of every stencil point of the job (index 0: the fiducial)."""
+        if self._points is None:
+            pts = []
+            for st in self._steps:
+                ap = dict(self.allparsfid)
+                if st is not None:
+                    ap[st[0]] = ap[st[0]] + st[1]
+                pts.append(ap)
+            self._points = pts
+        return self._points
+
     def build_job(self, freeparams=None) -> PhotoJob:
         fp = self._freeparams(freeparams)
         ext_eps = (self._cfg.external or {}).get("eps_values") if self.stencil == "STEM" else None
-        points = [dict(self.allparsfid)]
+        # stencil points as (parameter, offset) steps off the fiducial; the dictionaries of `self.points` are formed on
+        # demand (the job itself works on the matrix of parameter values)
+        steps = [None]
         rows, stden = [], np.ones(len(fp))
         self._offsets = []
         for ip, par in enumerate(fp):
@@ -678,30 +693,32 @@ class PhotoCov:
                     row[0] = row.get(0, 0.0) + w
                     used.append((0, off))
                     continue
-                ap = dict(self.allparsfid)  # flat {name: number}
-                ap[par] = ap[par] + off
-                points.append(ap)
-                row[len(points) - 1] = w
-                used.append((len(points) - 1, off))
+                steps.append((par, off))
+                row[len(steps) - 1] = w
+                used.append((len(steps) - 1, off))
             rows.append(row)
             self._offsets.append(used)
-        stw = np.zeros((len(fp), len(points)))
+        stw = np.zeros((len(fp), len(steps)))
         for ip, row in enumerate(rows):
             for s, w in row.items():
                 stw[ip, s] = w
         self.parnames = list(fp)
-        self.points = points
+        self._steps, self._points = steps, None
         cfg = self._cfg
         if self.stencil != "STEM" and not any(k in cfg.photoparams for k in fp):
             # stencil points as rows of a matrix: windows, IA and bias assembled with array operations (the photo-z
             # parameters, whose stencil points need their own n_i(z) windows, take the point-by-point constructor)
             names = [k for k, v in self.allparsfid.items() if isinstance(v, (int, float, np.floating, np.integer))
                      and not isinstance(v, bool)]
-            mat = np.array([[ap[k] for k in names] for ap in points], dtype=float)
+            col = {n: i for i, n in enumerate(names)}
+            mat = np.tile(np.array([self.allparsfid[k] for k in names], dtype=float), (len(steps), 1))
+            for s, st in enumerate(steps):
+                if st is not None:
+                    mat[s, col[st[0]]] = self.allparsfid[st[0]] + st[1]
             self._job = PhotoJob.from_matrix(self.configuration, names, mat)
             self._job.stw, self._job.stden = np.asarray(stw, float), np.asarray(stden, float)
         else:
-            self._job = PhotoJob(self.configuration, points, stw, stden)
+            self._job = PhotoJob(self.configuration, self.points, stw, stden)
         self._cls_all = None
         return self._job
 
