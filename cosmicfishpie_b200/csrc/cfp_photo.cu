@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <unordered_map>
 
 #include "cfp_common.cuh"
 
@@ -1062,13 +1063,19 @@ static int photo_plan_create_impl(cfp_ctx* ctx, const cfp_bank* bank, int S, int
   {
     // distinct (cosmology, window set) pairs among the stencil points: one lensing-efficiency table each
     std::vector<int> pair_of_s(S), pair_c, pair_w;
-    for (int s = 0; s < S; ++s) {
-      const int c = cosmo_of_s_h[s], w = win_of_s_h ? win_of_s_h[s] : 0;
-      int p = 0;
-      for (; p < (int)pair_c.size(); ++p)
-        if (pair_c[p] == c && pair_w[p] == w) break;
-      if (p == (int)pair_c.size()) pair_c.push_back(c), pair_w.push_back(w);
-      pair_of_s[s] = p;
+    if (NW > 1) {  // (with one window set the pair index is the cosmology index: nothing to search)
+      std::unordered_map<uint64_t, int> seen;  // a batch may bring thousands of cosmologies: no linear search
+      seen.reserve((size_t)S * 2);
+      for (int s = 0; s < S; ++s) {
+        const int c = cosmo_of_s_h[s], w = win_of_s_h ? win_of_s_h[s] : 0;
+        const uint64_t key = ((uint64_t)(uint32_t)c << 32) | (uint32_t)w;
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+          it = seen.emplace(key, (int)pair_c.size()).first;
+          pair_c.push_back(c), pair_w.push_back(w);
+        }
+        pair_of_s[s] = it->second;
+      }
     }
     if (NW == 1) {  // keep the plain layout: pair index = cosmology index, every cosmology has a table
       pl->NP = NC;
