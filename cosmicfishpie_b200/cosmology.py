@@ -622,6 +622,7 @@ class CosmoSet:
 
 _BANK_CACHE: Dict[tuple, tuple] = {}
 _BANK_CACHE_MAX = 8
+_BANK_CACHE_MAX_COSMOS = 64  # larger sets are one-off batches: not kept
 
 
 def _combined_bank(ctx, cosmos, slots):
@@ -673,9 +674,7 @@ def _fitted_bank(ctx, cosmos, slots):
     bank = _combined_bank(ctx, cosmos, slots)
     if bank is not None:
         bank.h2d_last = bank.nbytes
-        _BANK_CACHE[key] = (ctx, list(cosmos), bank)
-        while len(_BANK_CACHE) > _BANK_CACHE_MAX:
-            _BANK_CACHE.pop(next(iter(_BANK_CACHE)))
+        _remember_bank(key, ctx, cosmos, bank)
         return bank
     tables, scales = [], []
     for c in cosmos:
@@ -691,7 +690,16 @@ def _fitted_bank(ctx, cosmos, slots):
         scales.append(sc)
     bank = _lib.Bank.fit(ctx, zg, np.stack([c.kgrid for c in cosmos]), tables, scales)
     bank.h2d_last = bank.nbytes
+    _remember_bank(key, ctx, cosmos, bank)
+    return bank
+
+
+def _remember_bank(key, ctx, cosmos, bank):
+    """Keep a fitted bank resident for the next job on the same cosmologies -- unless it is the bank of a large one-off
+    set (a sampler batch in which every point has its own cosmology: gigabytes that no later job will ask for again;
+    such a bank belongs to its CosmoSet and is freed with it)."""
+    if len(cosmos) > _BANK_CACHE_MAX_COSMOS:
+        return
     _BANK_CACHE[key] = (ctx, list(cosmos), bank)
     while len(_BANK_CACHE) > _BANK_CACHE_MAX:
         _BANK_CACHE.pop(next(iter(_BANK_CACHE)))
-    return bank
