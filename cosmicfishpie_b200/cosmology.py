@@ -560,21 +560,23 @@ class CosmoSet:
             for i, c in enumerate(cs):
                 d = c.__dict__
                 cf = d.setdefault("_coef1d", {})
+                ci = coef[i].copy()  # (a facade keeps its own rows: views would pin the whole batch's arrays)
                 for j, n in enumerate(rows):
-                    cf[n] = (t, coef[i, j])
+                    cf[n] = (t, ci[j])
                 if out is None:
                     continue
+                oi = out[i].copy()
                 gm, sm = d.setdefault("_grid_memo", {}), d.setdefault("_scalar_memo", {})
                 for j, n in enumerate(rows):
                     acc = self._ACCESSOR_OF[n]
                     o = 0
                     for g in grids:
-                        v = out[i, j, o:o + g.size]
+                        v = oi[j, o:o + g.size]
                         v.setflags(write=False)
                         gm.setdefault((acc, g.tobytes()), v)
                         o += g.size
                     for z in scalars:
-                        sm.setdefault((acc, z), out[i, j, o])
+                        sm.setdefault((acc, z), oi[j, o])
                         o += 1
 
     def prepare_spectro(self, zs, tracer="matter"):
