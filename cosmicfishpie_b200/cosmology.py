@@ -248,6 +248,10 @@ class cosmo_functions:
             for name in ("h_of_z", "com_dist", "ang_dist", "s8_of_z"):  # the reference fits these eagerly
                 getattr(self, name)
         self.results = self  # reference code reaches splines through `.results`
+        # the no-wiggle settings this facade is cached under: kept by value (the settings dictionary may be edited in
+        # place after the facade was made; what is computed lazily must still match the cache key)
+        st = self.settings
+        self._savgol = (st["savgol_internalkmin"], st["savgol_internalsamples"], st["savgol_width"], st["savgol_polyorder"])
         self._nw_cache = {}
         self._moment_cache = {}
 
@@ -352,12 +356,11 @@ class cosmo_functions:
         """(ln k samples, Savitzky-Golay window) of the no-wiggle smoothing (cosmology.py:1767-1779)."""
         hit = self.__dict__.get("_nw_samples")
         if hit is None:
-            s = self.settings
             h = self.cosmopars["h"]
-            lk = np.linspace(np.log(h * s["savgol_internalkmin"]), np.log(h * np.max(self.kgrid)),
-                             s["savgol_internalsamples"])
+            kmin, nsamp, width, _ = self._savgol
+            lk = np.linspace(np.log(h * kmin), np.log(h * np.max(self.kgrid)), nsamp)
             dlnk = np.mean(lk[1:] - lk[0:-1])
-            hit = self.__dict__["_nw_samples"] = (lk, int(np.round(s["savgol_width"] / np.log(1 + dlnk))))
+            hit = self.__dict__["_nw_samples"] = (lk, int(np.round(width / np.log(1 + dlnk))))
         return hit
 
     def nonwiggle_table(self, z, nonlinear=False, tracer="matter"):
@@ -369,7 +372,7 @@ class cosmo_functions:
             lk, n_sg = self.nonwiggle_samples()
             lp = InterpolatedUnivariateSpline(
                 lk, np.log(self.matpow(z, np.exp(lk), nonlinear=nonlinear, tracer=tracer).flatten()), k=1)
-            sg = savgol_filter(lp(lk), n_sg, self.settings["savgol_polyorder"])
+            sg = savgol_filter(lp(lk), n_sg, self._savgol[3])
             spl = InterpolatedUnivariateSpline(np.exp(lk), np.exp(sg), k=1)
             t, c, _ = spl._eval_args
             n = len(t) - 2
@@ -610,7 +613,7 @@ class CosmoSet:
         if need_w:
             samples = [c.nonwiggle_samples() for c in self.cosmos]
             nsamp = samples[0][0].size
-            order = self.config.settings["savgol_polyorder"]
+            order = self.cosmos[0]._savgol[3]
             wins = sorted({n for _, n in samples})
             if any(lk.size != nsamp for lk, _ in samples) or any(not order < w <= nsamp for w in wins):
                 return  # (scipy raises on such windows: leave the error to the host path)
