@@ -286,16 +286,23 @@ class PhotometricLikelihood(Likelihood, NautilusMixin):
             out[pa:pb] = pjob.plan().chi2_collect()
             pjob.close()
 
-        for i, (a, b) in enumerate(spans):
-            job = photo_mod.PhotoJob.from_matrix(self.cosmo_theory, names, matrix[a:b])
-            plan = job.plan()  # create + H2D, on the context stream
-            plan.chi2_launch(off, n, w, data=self._data_full,
-                             stream=plan.ctx.aux_stream if i % 2 == 0 else plan.ctx.aux_stream2)
-            pending.append((job, a, b))
-            while len(pending) > depth:
+        try:
+            for i, (a, b) in enumerate(spans):
+                job = photo_mod.PhotoJob.from_matrix(self.cosmo_theory, names, matrix[a:b])
+                plan = job.plan()  # create + H2D, on the context stream
+                plan.chi2_launch(off, n, w, data=self._data_full,
+                                 stream=plan.ctx.aux_stream if i % 2 == 0 else plan.ctx.aux_stream2)
+                pending.append((job, a, b))
+                while len(pending) > depth:
+                    collect_oldest()
+            while pending:
                 collect_oldest()
-        while pending:
-            collect_oldest()
+        finally:
+            for pjob, _, _ in pending:  # (only after an error: chunks still in flight give their buffers back)
+                try:
+                    pjob.close()
+                except Exception:  # noqa: BLE001
+                    pass
         return out
 
     def chi2_batch(self, param_dicts) -> np.ndarray:
