@@ -525,3 +525,53 @@ def test_nautilus_sampler_over_cosmology_with_the_emulator(extfiles, toy_bank, t
     d0, d1 = dict(zip(keys, data[0, :5])), dict(zip(keys, data[0, :5]))
     d1["Omegam"] = d0["Omegam"] * 1.002
     assert abs(ph.loglike(param_dict=d1) - ph.loglike(param_dict=d0)) > 1e-6 * abs(ph.loglike(param_dict=d0))
+
+
+def test_emulated_batch_with_tables_in_h_units(extfiles, toy_bank, tmp_path):
+    """Tables in h/Mpc: the wavenumber grid of an emulated cosmology scales with its own h, so its bank row cannot be a
+    combination of the tabulated rows; the emulated tables are formed (lazily) and fitted on the device instead.  Same
+    physics as the 1/Mpc bank: the log-likelihoods of off-node points agree to the emulator's accuracy."""
+    from cosmicfishpie_b200 import cosmology as cz
+    from cosmicfishpie_b200 import toy_tables as tt
+    from cosmicfishpie_b200.bank import TaylorEmulator
+    from cosmicfishpie_b200.fishermatrix import FisherMatrix
+    from cosmicfishpie_b200.likelihood import SpectroLikelihood
+
+    # a bank tabulated on ONE grid of k in h/Mpc: every folder samples its own physical wavenumbers k_h * h
+    zg = np.asarray(toy_bank["fiducial_eps_0"]["z"])
+    k_h = np.asarray(toy_bank["fiducial_eps_0"]["k"]) / tt.FIDUCIAL["h"]
+    hbank = {}
+    for name, pars in tt.stencil_points(dict(tt.FIDUCIAL), (0.01,)):
+        u = dict(tt.make_tables(pars, zg, k_h * pars["h"]))
+        u["k"] = k_h
+        for key in ("Pl", "Pnl", "Plcb", "Pnlcb"):
+            if key in u:
+                u[key] = np.asarray(u[key]) * pars["h"] ** 3
+        hbank[name] = u
+    rng = np.random.default_rng(8)
+    keys = ["Omegam", "sigma8", "ns", "lnbg_1"]
+
+    def run(bank, k_units, sub):
+        cz.clear_caches()
+        ext = dict(extfiles, tables=bank, emulator=TaylorEmulator(bank, tt.FIDUCIAL, tt.COSMO_KEYS, 0.01))
+        ext["k-units"] = k_units
+        fm = FisherMatrix(fiducialpars=dict(tt.FIDUCIAL), freepars={"Omegam": 0.01},
+                          options=base_options(tmp_path / sub, spectro_Pk_k_samples=129, spectro_Pk_mu_samples=9),
+                          observables=["GCsp"], extfiles=ext)
+        fm.compute()
+        like = SpectroLikelihood(cosmoFM_data=fm)
+        fid = np.array([fm.allparams[k] for k in keys])
+        pts = np.tile(fid, (10, 1))
+        pts[:, :3] *= 1 + 0.006 * np.random.default_rng(8).uniform(-1, 1, size=(10, 3))
+        pts[:, 3] += 0.01
+        ll = like.loglike_batch(pts, keys=keys)
+        emulated = [c for c in like.cosmo_theory.pk_obs_fid.cosmo_set.cosmos if c.folder == "<emulated>"]
+        return ll, emulated
+
+    ll_h, emu_h = run(hbank, "h/Mpc", "h")
+    assert emu_h and all(c._emu is None for c in emu_h)      # not combinable: formed and fitted per cosmology
+    ll_m, emu_m = run(toy_bank, "1/Mpc", "m")
+    assert emu_m and all(c._emu is not None for c in emu_m)  # combined on the device
+    cz.clear_caches()
+    # (the two banks sample the spectra at different wavenumbers and expand different table values in h)
+    assert np.all(np.isfinite(ll_h)) and np.max(np.abs(ll_h - ll_m) / np.abs(ll_m)) < 2e-2
