@@ -275,3 +275,45 @@ def test_forecast_from_a_memory_mapped_bank_file(tmp_path, toy_bank, extfiles):
     for kind in ("spectro", "photo"):
         assert np.array_equal(run(dict(extfiles, tables=tables), kind), run(extfiles, kind)), kind
     cz.clear_caches()
+
+
+@pytest.mark.parametrize("win,order", [(101, 3), (58, 2), (7, 3)])
+def test_nowiggle_and_moments_kernels_against_scipy(ctx, win, order):
+    """cfp_bank_nowiggle (odd and even Savitzky-Golay windows, several polynomial orders) and cfp_bank_theta_moments on
+    a synthetic two-cosmology bank, against scipy.signal.savgol_filter / scipy.integrate.trapezoid of FITPACK values."""
+    from scipy.integrate import trapezoid
+    from scipy.signal import savgol_filter
+
+    from cosmicfishpie_b200 import _lib
+    from cosmicfishpie_b200.cosmology import savgol_operator
+
+    rng = np.random.default_rng(win)
+    z, k = _grids(rng, 24, 160)
+    ks = np.stack([k, 1.03 * k])
+    tabs, scales, spl = [], [], []
+    for c in range(2):
+        kk = ks[c][None, :]
+        pl = 2e4 * kk / (1 + (kk / 0.02) ** 2.6) / (1 + z[:, None]) ** 1.7 * (1 + 0.04 * np.sin(55 * kk + 0.3 * c))
+        f = 0.55 + 0.35 * np.tanh(z[:, None] - 0.8) + 0.005 * np.log(kk)
+        row = [None] * _lib.NTAB
+        row[_lib.TAB_PLIN], row[_lib.TAB_F] = pl, f
+        tabs.append(row)
+        scales.append([1.0] * _lib.NTAB)
+        spl.append((RectBivariateSpline(z, ks[c], pl, kx=3, ky=3), RectBivariateSpline(z, ks[c], f, kx=3, ky=3)))
+    bank = _lib.Bank.fit(ctx, z, ks, tabs, scales)
+    zq = np.array([0.3, 1.1, 2.4])
+    nsamp = 300
+    samp = np.stack([np.exp(np.linspace(np.log(ks[c][0] * 1.5), np.log(ks[c][-1] * 0.7), nsamp)) for c in range(2)])
+    got = bank.nowiggle(_lib.TAB_PLIN, zq, samp, [0, 0], [savgol_operator(win, order)])
+    for c in range(2):
+        for j, zz in enumerate(zq):
+            ref = np.exp(savgol_filter(np.log(spl[c][0](zz, samp[c], grid=False)), win, order))
+            assert np.max(np.abs(got[c, j] / ref - 1)) < 1e-11, (c, zz)
+    kq = np.logspace(np.log10(k[0] * 2), np.log10(k[-1] * 0.5), 777)
+    mom = bank.theta_moments(_lib.TAB_PLIN, _lib.TAB_F, zq, kq)
+    for c in range(2):
+        for j, zz in enumerate(zq):
+            p, f = spl[c][0](zz, kq, grid=False), spl[c][1](zz, kq, grid=False)
+            ref = [trapezoid(p * f**m, x=kq) / (6 * np.pi**2) for m in (0, 1, 2)]
+            assert np.allclose(mom[c, j], ref, rtol=1e-12, atol=0), (c, zz)
+    bank.close()
